@@ -1,0 +1,145 @@
+/*
+ * rpforest.h -- C ABI of the B200-native random-projection-forest engine (librpforest.so).
+ *
+ * This is the drop-in boundary for the hot path of ocramz/rp-tree (Haskell, package rp-tree-0.7.1):
+ *   forestBatch / forest  ->  candidates / knn / knnPQ  ->  recallWith.
+ * The reference has no FFI of its own (pure Haskell); the boundary is the export list of Data.RPTree
+ * (src/Data/RPTree.hs:50-113).  A Haskell shim (hs/Data/RPTree/CUDA.hs) keeps those
+ * signatures and marshals to the entry points below with `foreign import ccall safe`.
+ *
+ * Conventions
+ *  - plain C: pointers + sizes only.  All pointers are HOST memory owned by the caller unless a
+ *    parameter is named *_dev.  Outputs are caller-allocated.
+ *  - every call returns RPF_OK (0) or a negative rpf_status; rpf_last_error(h) gives the message.
+ *  - a handle is bound to one CUDA device and is not re-entrant (one host thread at a time).
+ *  - there is NO CPU fallback: if no CUDA device is usable, rpf_create fails.
+ *  - point identity is the uint32 row number in X (the shim maps rows back to `Embed` payloads).
+ *  - all arithmetic is IEEE binary64 with separate mul/add roundings (no FMA), in the reference's
+ *    evaluation order, so thresholds, margins, leaf sets and knn id lists are bit-exact w.r.t.
+ *    the reference algorithm given the same hyperplanes.
+ */
+#ifndef RPFOREST_H
+#define RPFOREST_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rpf_handle rpf_handle;
+
+typedef enum {
+    RPF_OK = 0,
+    RPF_ERR_CUDA = -1,          /* CUDA runtime error (message has the cudaError string) */
+    RPF_ERR_ARG = -2,           /* invalid argument */
+    RPF_ERR_STATE = -3,         /* call order violated (e.g. build before set_points) */
+    RPF_ERR_UNSUPPORTED = -4,   /* valid in the reference, not yet implemented here */
+    RPF_ERR_NOMEM = -5
+} rpf_status;
+
+/* ---- lifecycle ---------------------------------------------------------------------------------- */
+/* Creates an engine bound to CUDA device `device` (owns a stream and all device buffers). */
+int  rpf_create(rpf_handle** out, int device);
+void rpf_destroy(rpf_handle* h);
+const char* rpf_last_error(const rpf_handle* h);
+/* ABI version of this header. */
+int  rpf_abi_version(void);
+
+/* ---- data: V.Vector (Embed DVector Double x)  (src/Data/RPTree/Internal.hs:56-63,122-126) -------- */
+/* X: n x d row-major doubles (one DVector per row).  Copied to the device; caller keeps ownership. */
+int rpf_set_points(rpf_handle* h, const double* X, int64_t n, int32_t d);
+/* Same, but X_dev is a device pointer on this handle's device; it is borrowed (must outlive the handle's use). */
+int rpf_set_points_device(rpf_handle* h, const double* X_dev, int64_t n, int32_t d);
+
+/* ---- hyperplanes: one SVector per (tree, level)  (Internal.hs:92-93,172-175) ---------------------- */
+/* PRIMARY path: the Haskell host draws rvss with the real `sample seed (replicateM ntrees (V.replicateM
+ * maxd (sparse pnz dim stdNormal)))` (src/Data/RPTree/Batch.hs:57-63, Conduit.hs:114-121) and passes them
+ * here as CSR over (tree-major, level-minor): off has T*maxDepth+1 entries, idx increasing within a row.
+ * For multi-GPU tree sharding pass only this rank's trees. */
+int rpf_set_hyperplanes(rpf_handle* h, int32_t T, int32_t maxDepth,
+                        const int64_t* off, const int32_t* idx, const double* val);
+/* Convenience: regenerate the hyperplanes from the seed in C (SplitMix64 core verified against the
+ * splitmix haddock vectors; the normal sampler of splitmix-distributions-0.9 is restated from memory
+ * and UNVERIFIED -- see DESIGN.md).  Replaces Gen.hs:148-195 under Batch.hs:59-61.
+ * Draws the full forest of T_total trees and keeps trees [t_first, t_first + T_local). */
+int rpf_gen_hyperplanes(rpf_handle* h, uint64_t seed, int32_t T_total, int32_t maxDepth, double pnz, int32_t d,
+                        int32_t t_first, int32_t T_local);
+int64_t rpf_hyperplane_nnz(const rpf_handle* h);
+/* Host-only sampler (no handle, no GPU needed): same draw as rpf_gen_hyperplanes for all T trees.
+ * Returns nnz; call with idx = val = NULL to size (off, if given, has T*maxDepth+1 entries). */
+int64_t rpf_sample_hyperplanes(uint64_t seed, int32_t T, int32_t maxDepth, double pnz, int32_t d,
+                               int64_t* off, int32_t* idx, double* val);
+/* rpTreeCfg (src/Data/RPTree/Conduit.hs:132-141): default maxDepth, chunk size and pnz. Host-only. */
+void rpf_rptree_cfg(int64_t minLeaf, int64_t n, int64_t d, int64_t* maxDepth, int64_t* chunk, double* pnz);
+int rpf_get_hyperplanes(const rpf_handle* h, int64_t* off, int32_t* idx, double* val);
+
+/* ---- build: forestBatch / treeBatch (Batch.hs:29-63) == createMulti/create/insert Tip-case
+ *      (Internal.hs:217-240,287-297) with partitionAtMedian (Internal.hs:484-505) ---------------------- */
+int rpf_build(rpf_handle* h, int32_t maxDepth, int32_t minLeaf);
+/* forest / tree (Conduit.hs:58-121): same, data arriving in chunks of `chunk` points.  chunk >= n is
+ * identical to rpf_build (single insert into an empty Tip); chunk < n (streaming Bin-case update,
+ * Internal.hs:274-285) returns RPF_ERR_UNSUPPORTED in this round. */
+int rpf_build_chunked(rpf_handle* h, int32_t maxDepth, int32_t minLeaf, int64_t chunk);
+
+/* ---- result structure: RPT Bin/Tip (Internal.hs:139-148) as flat arrays ---------------------------- */
+/* The topology (which nodes exist, their sizes) is a pure function of (n, minLeaf, maxDepth) because the
+ * split is positional (first n div 2 of the stable-sorted node go left, Internal.hs:495,503); it is the
+ * same for every tree.  Nodes are numbered in BFS order (level-major, left to right). */
+int64_t rpf_num_nodes(const rpf_handle* h);
+int32_t rpf_num_trees(const rpf_handle* h);
+/* child[g] = BFS id of the left child (right = +1) or -1 for a Tip; seg_start/seg_size = slice of perm
+ * holding the points under node g.  Any pointer may be NULL. */
+int rpf_topology(const rpf_handle* h, int64_t* child, int32_t* depth, int64_t* seg_start, int64_t* seg_size);
+/* Host-only: the topology for (n, maxDepth, minLeaf) without a handle.  Returns the node count; arrays may be NULL. */
+int64_t rpf_topology_plan(int64_t n, int32_t maxDepth, int32_t minLeaf, int64_t* child, int32_t* depth,
+                          int64_t* seg_start, int64_t* seg_size);
+/* 1 if every leaf's internal order equals the reference's (always, unless a leaf is larger than the
+ * shared-memory capacity set by rpf_set_bottom_cap; leaf SETS are exact regardless). */
+int rpf_leaf_order_exact(const rpf_handle* h);
+/* Per tree: thr/mlo/mhi[num_nodes] (_rpThreshold, Margin low/high; valid where child>=0) and
+ * perm[n] = row ids, leaves concatenated left to right, each leaf in the reference's order. */
+int rpf_tree_export(rpf_handle* h, int32_t t, double* thr, double* mlo, double* mhi, uint32_t* perm);
+
+/* ---- queries --------------------------------------------------------------------------------------- */
+/* candidates (src/Data/RPTree.hs:293-314) for tree t (t >= 0) or for all trees concatenated tree-major
+ * (t == -1, i.e. `fold ((`candidates` q) <$> tts)`, RPTree.hs:176).  Q: nq x d row-major.
+ * Two calls: counts -> caller sizes ids -> fill.  off_out has nq+1 entries (CSR). */
+int rpf_candidates_count(rpf_handle* h, const double* Q, int64_t nq, int32_t t, int64_t* off_out);
+int rpf_candidates(rpf_handle* h, const double* Q, int64_t nq, int32_t t, const int64_t* off, uint32_t* ids);
+/* knn metricL2 k (RPTree.hs:168-176; dedup=0: duplicates across trees kept, exactly as the reference)
+ * knnPQ metricL2 k (RPTree.hs:181-194,224-227; dedup=1: one result per distinct distance).
+ * dist/ids: nq x k row-major; count[q] = number of valid results (<= k).  Distances are
+ * sqrt(sum_j (x_j - q_j)^2), left-fold sum, correctly rounded squares (Internal.hs:403-406). */
+int rpf_knn(rpf_handle* h, const double* Q, int64_t nq, int32_t k, int32_t dedup,
+            double* dist, uint32_t* ids, int32_t* count);
+/* recallWith metricL2 forest k q (RPTree.hs:259-282): mean over this handle's trees of
+ * |candidates(t,q) /\ true-top-k| / k.  recall_sum[q] = SUM over local trees (divide by the global
+ * tree count after reducing across GPUs). */
+int rpf_recall(rpf_handle* h, const double* Q, int64_t nq, int32_t k, double* recall_sum);
+/* Exact brute-force k nearest rows (ties by row id): ground truth for forest-level recall. */
+int rpf_brute_knn(rpf_handle* h, const double* Q, int64_t nq, int32_t k, double* dist, uint32_t* ids);
+
+/* ---- multi-GPU: merge per-GPU top-k lists (trees sharded in contiguous blocks, rank-major) ---------- */
+/* dist/ids: G x nq x k, count: G x nq (rank-major).  Result ordered by (distance, rank, position), which
+ * equals the single-GPU order of rpf_knn over the whole forest. */
+int rpf_merge_topk(rpf_handle* h, int32_t G, int64_t nq, int32_t k, int32_t dedup,
+                   const double* dist, const uint32_t* ids, const int32_t* count,
+                   double* dist_out, uint32_t* ids_out, int32_t* count_out);
+
+/* ---- measurement hooks (CUDA events on the engine's own stream) ------------------------------------ */
+/* Device time in ms of the most recent rpf_build / rpf_knn / rpf_recall kernels (events on the stream
+ * the kernels were launched on; excludes host<->device copies of the call's arguments). */
+double rpf_last_device_ms(const rpf_handle* h);
+/* Per-phase profile of the last call when profiling is enabled (adds event records between phases).
+ * Phases: see rpf_phase_name(i).  Returns the number of phases; ms/launches may be NULL. */
+int rpf_set_profiling(rpf_handle* h, int on);
+int rpf_get_profile(const rpf_handle* h, double* ms, int64_t* launches, int cap);
+const char* rpf_phase_name(int i);
+/* Total kernel launches issued by this handle since creation. */
+int64_t rpf_launch_count(const rpf_handle* h);
+/* Tuning knob: bottom-phase shared-memory capacity in points (4096 or 8192). */
+int rpf_set_bottom_cap(rpf_handle* h, int32_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,359 @@
+"""Host-side mirror of the reference's public interface for the hot path (Data.RPTree, src/Data/RPTree.hs:50-113).
+
+Same names and argument meaning as the Haskell functions; every call goes through the C ABI of
+librpforest.so (include/rpforest.h) -- exactly what the Haskell FFI shim would bind.
+Data points are rows of a float64 matrix (one DVector per row); the `Embed` payload is the row number.
+
+    forestBatch seed maxd minl ntrees pnz dim xs      src/Data/RPTree/Batch.hs:48-63
+    treeBatch   seed maxd minl pnz dim xs             src/Data/RPTree/Batch.hs:29-41
+    forest / tree (chunked conduit versions)          src/Data/RPTree/Conduit.hs:58-121
+    rpTreeCfg minl n d                                src/Data/RPTree/Conduit.hs:132-141
+    knn / knnPQ distf k tts q                         src/Data/RPTree.hs:168-194
+    candidates tree q                                 src/Data/RPTree.hs:293-314
+    recallWith distf tts k q                          src/Data/RPTree.hs:259-268
+    treeSize / leafSizes / levels / points            src/Data/RPTree.hs:351-367, Internal.hs:199-208
+"""
+import ctypes as C
+from collections import namedtuple
+
+import numpy as np
+
+from ._lib import lib, RPForestError, i64p, i32p, u32p, f64p, H
+
+RPTreeConfig = namedtuple("RPTreeConfig", ["fpMaxTreeDepth", "fpDataChunkSize", "fpProjNzDensity"])  # Conduit.hs:123-128
+
+
+class _MetricL2:
+    """Stand-in for `metricL2` (Internal.hs:318,337-339): the only distance the engine implements."""
+
+    def __repr__(self):
+        return "metricL2"
+
+
+metricL2 = _MetricL2()
+
+
+def _p(a, t):
+    return a.ctypes.data_as(t)
+
+
+def _as_q(q, d):
+    Q = np.ascontiguousarray(q, dtype=np.float64)
+    single = Q.ndim == 1
+    if single:
+        Q = Q[None, :]
+    if Q.ndim != 2 or Q.shape[1] != d:
+        raise ValueError("query must have dimension %d" % d)
+    return Q, single
+
+
+def rpTreeCfg(minl, n, d):
+    """rpTreeCfg (Conduit.hs:132-141): natural defaults for maxDepth, chunk size, projection density."""
+    maxd = C.c_int64(); chunk = C.c_int64(); pnz = C.c_double()
+    lib().rpf_rptree_cfg(minl, n, d, C.byref(maxd), C.byref(chunk), C.byref(pnz))
+    return RPTreeConfig(maxd.value, chunk.value, pnz.value)
+
+
+def sampleHyperplanes(seed, ntrees, maxd, pnz, dim):
+    """`sample seed (replicateM ntrees (V.replicateM maxd (sparse pnz dim stdNormal)))` (Batch.hs:59-61) as CSR.
+
+    Host-only (no GPU).  The SplitMix64 core is verified; the normal sampler is an unverified restatement.
+    """
+    L = lib()
+    off = np.zeros(ntrees * maxd + 1, np.int64)
+    nnz = L.rpf_sample_hyperplanes(seed, ntrees, maxd, pnz, dim, _p(off, i64p), None, None)
+    if nnz < 0:
+        raise RPForestError("rpf_sample_hyperplanes: bad arguments")
+    idx = np.zeros(max(nnz, 1), np.int32); val = np.zeros(max(nnz, 1), np.float64)
+    L.rpf_sample_hyperplanes(seed, ntrees, maxd, pnz, dim, _p(off, i64p), _p(idx, i32p), _p(val, f64p))
+    return off, idx[:nnz].copy(), val[:nnz].copy()
+
+
+def topologyPlan(n, maxd, minl):
+    """The data-independent tree shape for (n, maxDepth, minLeaf): BFS arrays child/depth/seg_start/seg_size."""
+    L = lib()
+    nn = L.rpf_topology_plan(n, maxd, minl, None, None, None, None)
+    if nn < 0:
+        raise RPForestError("rpf_topology_plan: bad arguments")
+    child = np.zeros(nn, np.int64); depth = np.zeros(nn, np.int32); ss = np.zeros(nn, np.int64); sz = np.zeros(nn, np.int64)
+    L.rpf_topology_plan(n, maxd, minl, _p(child, i64p), _p(depth, i32p), _p(ss, i64p), _p(sz, i64p))
+    return dict(child=child, depth=depth, seg_start=ss, seg_size=sz)
+
+
+def slice_hyperplanes(hp, maxd, t_first, t_local):
+    """CSR rows of trees [t_first, t_first+t_local) -- what one GPU rank passes to rpf_set_hyperplanes."""
+    off, idx, val = hp
+    r0, r1 = t_first * maxd, (t_first + t_local) * maxd
+    lo, hi = off[r0], off[r1]
+    return (off[r0:r1 + 1] - lo).astype(np.int64), idx[lo:hi].copy(), val[lo:hi].copy()
+
+
+class RPForest:
+    """RPForest Double (V.Vector (Embed DVector Double Int)) held on one B200 (Internal.hs:182).
+
+    Wraps one `rpf_handle`.  `t_first` is the global index of this shard's first tree (multi-GPU sharding).
+    """
+
+    def __init__(self, device=0):
+        self._L = lib()
+        self._h = H()
+        rc = self._L.rpf_create(C.byref(self._h), device)
+        if rc != 0:
+            self._h = None
+            raise RPForestError("rpf_create failed (rc=%d): no usable CUDA device %d -- the engine has no CPU fallback" % (rc, device))
+        self.device = device
+        self.n = 0; self.d = 0; self.ntrees = 0; self.maxDepth = 0; self.minLeaf = 0
+        self.t_first = 0; self.ntrees_total = 0
+        self._topo = None
+
+    # -- plumbing
+    def _ck(self, rc, what):
+        if rc != 0:
+            raise RPForestError("%s failed (rc=%d): %s" % (what, rc, self._L.rpf_last_error(self._h).decode()))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.rpf_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- build
+    def setPoints(self, X):
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        if X.ndim != 2:
+            raise ValueError("X must be n x d")
+        self._ck(self._L.rpf_set_points(self._h, _p(X, f64p), X.shape[0], X.shape[1]), "rpf_set_points")
+        self.n, self.d = X.shape
+
+    def setPointsDevice(self, ptr, n, d):
+        self._ck(self._L.rpf_set_points_device(self._h, C.c_void_p(ptr), n, d), "rpf_set_points_device")
+        self.n, self.d = n, d
+
+    def setHyperplanes(self, hp, ntrees, maxd):
+        off, idx, val = hp
+        off = np.ascontiguousarray(off, np.int64)
+        idx = np.ascontiguousarray(idx if len(idx) else np.zeros(1), np.int32)
+        val = np.ascontiguousarray(val if len(val) else np.zeros(1), np.float64)
+        self._ck(self._L.rpf_set_hyperplanes(self._h, ntrees, maxd, _p(off, i64p), _p(idx, i32p), _p(val, f64p)), "rpf_set_hyperplanes")
+        self.ntrees = ntrees
+        self._hp_depth = maxd
+
+    def genHyperplanes(self, seed, ntrees_total, maxd, pnz, dim, t_first=0, t_local=None):
+        t_local = ntrees_total - t_first if t_local is None else t_local
+        self._ck(self._L.rpf_gen_hyperplanes(self._h, seed, ntrees_total, maxd, pnz, dim, t_first, t_local), "rpf_gen_hyperplanes")
+        self.ntrees = t_local
+        self._hp_depth = maxd
+
+    def hyperplanes(self):
+        nnz = self._L.rpf_hyperplane_nnz(self._h)
+        rows = self.ntrees * self._hp_depth
+        off = np.zeros(rows + 1, np.int64); idx = np.zeros(max(nnz, 1), np.int32); val = np.zeros(max(nnz, 1), np.float64)
+        self._ck(self._L.rpf_get_hyperplanes(self._h, _p(off, i64p), _p(idx, i32p), _p(val, f64p)), "rpf_get_hyperplanes")
+        return off, idx[:nnz], val[:nnz]
+
+    def build(self, maxd, minl, chunk=None):
+        if chunk is None:
+            self._ck(self._L.rpf_build(self._h, maxd, minl), "rpf_build")
+        else:
+            self._ck(self._L.rpf_build_chunked(self._h, maxd, minl, chunk), "rpf_build_chunked")
+        self.maxDepth, self.minLeaf = maxd, minl
+        self._topo = None
+
+    # -- structure
+    def topology(self):
+        if self._topo is None:
+            nn = self._L.rpf_num_nodes(self._h)
+            child = np.zeros(nn, np.int64); depth = np.zeros(nn, np.int32); ss = np.zeros(nn, np.int64); sz = np.zeros(nn, np.int64)
+            self._ck(self._L.rpf_topology(self._h, _p(child, i64p), _p(depth, i32p), _p(ss, i64p), _p(sz, i64p)), "rpf_topology")
+            self._topo = dict(child=child, depth=depth, seg_start=ss, seg_size=sz)
+        return self._topo
+
+    def treeExport(self, t):
+        """Flat image of tree t: what the shim turns back into Bin/Tip (Internal.hs:139-148)."""
+        tp = self.topology()
+        nn = len(tp["child"])
+        thr = np.zeros(nn); mlo = np.zeros(nn); mhi = np.zeros(nn); perm = np.zeros(max(self.n, 1), np.uint32)
+        self._ck(self._L.rpf_tree_export(self._h, t, _p(thr, f64p), _p(mlo, f64p), _p(mhi, f64p), _p(perm, u32p)), "rpf_tree_export")
+        out = dict(tp)
+        out.update(thr=thr, mlo=mlo, mhi=mhi, perm=perm[: self.n])
+        return out
+
+    def leafOrderExact(self):
+        return bool(self._L.rpf_leaf_order_exact(self._h))
+
+    # -- queries (batched: Q is nq x d)
+    def candidatesBatch(self, Q, t=-1):
+        Q, _ = _as_q(Q, self.d)
+        nq = Q.shape[0]
+        off = np.zeros(nq + 1, np.int64)
+        self._ck(self._L.rpf_candidates_count(self._h, _p(Q, f64p), nq, t, _p(off, i64p)), "rpf_candidates_count")
+        ids = np.zeros(max(int(off[-1]), 1), np.uint32)
+        self._ck(self._L.rpf_candidates(self._h, _p(Q, f64p), nq, t, _p(off, i64p), _p(ids, u32p)), "rpf_candidates")
+        return off, ids[: off[-1]]
+
+    def knnBatch(self, Q, k, dedup=False):
+        Q, _ = _as_q(Q, self.d)
+        nq = Q.shape[0]
+        dist = np.zeros((nq, k)); ids = np.zeros((nq, k), np.uint32); cnt = np.zeros(nq, np.int32)
+        self._ck(self._L.rpf_knn(self._h, _p(Q, f64p), nq, k, int(dedup), _p(dist, f64p), _p(ids, u32p), _p(cnt, i32p)), "rpf_knn")
+        return dist, ids, cnt
+
+    def recallSumBatch(self, Q, k):
+        Q, _ = _as_q(Q, self.d)
+        nq = Q.shape[0]
+        r = np.zeros(nq)
+        self._ck(self._L.rpf_recall(self._h, _p(Q, f64p), nq, k, _p(r, f64p)), "rpf_recall")
+        return r
+
+    def bruteKnnBatch(self, Q, k):
+        Q, _ = _as_q(Q, self.d)
+        nq = Q.shape[0]
+        dist = np.zeros((nq, k)); ids = np.zeros((nq, k), np.uint32)
+        self._ck(self._L.rpf_brute_knn(self._h, _p(Q, f64p), nq, k, _p(dist, f64p), _p(ids, u32p)), "rpf_brute_knn")
+        return dist, ids
+
+    def mergeTopk(self, dist, ids, cnt, dedup=False):
+        """dist/ids: G x nq x k, cnt: G x nq (rank-major) -> merged nq x k."""
+        dist = np.ascontiguousarray(dist, np.float64); ids = np.ascontiguousarray(ids, np.uint32); cnt = np.ascontiguousarray(cnt, np.int32)
+        G, nq, k = dist.shape
+        od = np.zeros((nq, k)); oi = np.zeros((nq, k), np.uint32); oc = np.zeros(nq, np.int32)
+        self._ck(self._L.rpf_merge_topk(self._h, G, nq, k, int(dedup), _p(dist, f64p), _p(ids, u32p), _p(cnt, i32p),
+                                        _p(od, f64p), _p(oi, u32p), _p(oc, i32p)), "rpf_merge_topk")
+        return od, oi, oc
+
+    # -- measurement
+    def lastDeviceMs(self):
+        return self._L.rpf_last_device_ms(self._h)
+
+    def setProfiling(self, on):
+        self._ck(self._L.rpf_set_profiling(self._h, int(on)), "rpf_set_profiling")
+
+    def profile(self):
+        n = self._L.rpf_get_profile(self._h, None, None, 0)
+        ms = np.zeros(n); la = np.zeros(n, np.int64)
+        self._L.rpf_get_profile(self._h, _p(ms, f64p), _p(la, i64p), n)
+        return {self._L.rpf_phase_name(i).decode(): (float(ms[i]), int(la[i])) for i in range(n)}
+
+    def launchCount(self):
+        return self._L.rpf_launch_count(self._h)
+
+    def setBottomCap(self, cap):
+        self._ck(self._L.rpf_set_bottom_cap(self._h, cap), "rpf_set_bottom_cap")
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the reference's function names
+# ---------------------------------------------------------------------------------------------------------
+def forestBatch(seed, maxd, minl, ntrees, pnz, dim, xs, *, hyperplanes=None, device=0, t_first=0, t_local=None, bottom_cap=None):
+    """forestBatch (Batch.hs:48-63).  `hyperplanes` = CSR (off, idx, val) drawn by the Haskell host overrides the
+    built-in sampler (bit-exact parity path).  t_first/t_local shard the trees for multi-GPU runs."""
+    xs = np.ascontiguousarray(xs, dtype=np.float64)
+    if xs.ndim != 2 or xs.shape[1] != dim:
+        raise ValueError("dataset must be n x %d" % dim)
+    t_local = ntrees - t_first if t_local is None else t_local
+    f = RPForest(device)
+    if bottom_cap is not None:
+        f.setBottomCap(bottom_cap)
+    f.setPoints(xs)
+    if hyperplanes is not None:
+        hp = hyperplanes if (t_first == 0 and t_local == ntrees) else slice_hyperplanes(hyperplanes, maxd, t_first, t_local)
+        f.setHyperplanes(hp, t_local, maxd)
+    else:
+        f.genHyperplanes(seed, ntrees, maxd, pnz, dim, t_first, t_local)
+    f.t_first, f.ntrees_total = t_first, ntrees
+    f.build(maxd, minl)
+    return f
+
+
+def treeBatch(seed, maxd, minl, pnz, dim, xs, **kw):
+    """treeBatch (Batch.hs:29-41): a forest of one tree."""
+    return forestBatch(seed, maxd, minl, 1, pnz, dim, xs, **kw)
+
+
+def forest(seed, maxd, minl, ntrees, chunksize, pnz, dim, xs, *, hyperplanes=None, device=0):
+    """forest (Conduit.hs:104-121): data arrives in chunks of `chunksize`.  chunksize >= n is forestBatch."""
+    xs = np.ascontiguousarray(xs, dtype=np.float64)
+    f = RPForest(device)
+    f.setPoints(xs)
+    if hyperplanes is not None:
+        f.setHyperplanes(hyperplanes, ntrees, maxd)
+    else:
+        f.genHyperplanes(seed, ntrees, maxd, pnz, dim)
+    f.t_first, f.ntrees_total = 0, ntrees
+    f.build(maxd, minl, chunk=chunksize)
+    return f
+
+
+def tree(seed, maxd, minl, chunksize, pnz, dim, xs, **kw):
+    """tree (Conduit.hs:58-75)."""
+    return forest(seed, maxd, minl, 1, chunksize, pnz, dim, xs, **kw)
+
+
+def _need_l2(distf):
+    if distf is not metricL2:
+        raise RPForestError("only distf = metricL2 is implemented on the GPU path")
+
+
+def knn(distf, k, tts, q):
+    """knn (RPTree.hs:168-176): (distances, row ids) in increasing distance; duplicates across trees are kept."""
+    _need_l2(distf)
+    Q, single = _as_q(q, tts.d)
+    dist, ids, cnt = tts.knnBatch(Q, k, dedup=False)
+    if single:
+        return dist[0, : cnt[0]], ids[0, : cnt[0]]
+    return dist, ids, cnt
+
+
+def knnPQ(distf, k, tts, q):
+    """knnPQ (RPTree.hs:181-194): one result per distinct distance."""
+    _need_l2(distf)
+    Q, single = _as_q(q, tts.d)
+    dist, ids, cnt = tts.knnBatch(Q, k, dedup=True)
+    if single:
+        return dist[0, : cnt[0]], ids[0, : cnt[0]]
+    return dist, ids, cnt
+
+
+def candidates(tts, t, q):
+    """candidates (RPTree.hs:293-314) of tree `t` of the forest for query q: row ids in the reference's order."""
+    Q, single = _as_q(q, tts.d)
+    off, ids = tts.candidatesBatch(Q, t)
+    if single:
+        return ids
+    return off, ids
+
+
+def recallWith(distf, tts, k, q):
+    """recallWith (RPTree.hs:259-268): mean over the forest's trees of the per-tree candidate recall@k."""
+    _need_l2(distf)
+    Q, single = _as_q(q, tts.d)
+    r = tts.recallSumBatch(Q, k) / float(tts.ntrees)
+    return float(r[0]) if single else r
+
+
+def levels(tts):
+    """levels (Internal.hs:203-204): number of projection vectors per tree."""
+    return tts.maxDepth
+
+
+def leafSizes(tts):
+    """leafSizes (RPTree.hs:366-367): sizes of the Tips, left to right (identical for every tree)."""
+    tp = tts.topology()
+    leaf = tp["child"] < 0
+    order = np.argsort(tp["seg_start"][leaf], kind="stable")
+    return tp["seg_size"][leaf][order]
+
+
+def treeSize(tts):
+    """treeSize (RPTree.hs:362-363)."""
+    return int(leafSizes(tts).sum())
+
+
+def points(tts, t):
+    """points (Internal.hs:207-208): row ids of tree t, leaves left to right."""
+    return tts.treeExport(t)["perm"]

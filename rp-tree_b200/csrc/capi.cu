@@ -1,0 +1,480 @@
+// capi.cu -- the C ABI declared in include/rpforest.h: handle lifecycle, data upload, the data-independent
+// topology, hyperplane regeneration (SplitMix64), result export and the measurement hooks.
+#include "rpf_internal.h"
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+int rpf_fail(rpf_handle* h, int code, const std::string& msg) {
+    if (h) h->err = msg;
+    return code;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// profiling / timing
+// ---------------------------------------------------------------------------------------------------
+static cudaEvent_t get_event(rpf_handle* h) {
+    if (!h->event_pool.empty()) { cudaEvent_t e = h->event_pool.back(); h->event_pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+void rpf_handle::prof_reset() {
+    for (int i = 0; i < PH_COUNT; ++i) { phase_ms[i] = 0; phase_launches[i] = 0; }
+}
+void rpf_handle::prof_begin(int phase) {
+    ++launches;
+    ++phase_launches[phase];
+    if (!profiling) return;
+    ProfEvent pe; pe.phase = phase; pe.a = get_event(this); pe.b = get_event(this);
+    cudaEventRecord(pe.a, stream);
+    pending.push_back(pe);
+}
+void rpf_handle::prof_end(int) {
+    if (!profiling) return;
+    cudaEventRecord(pending.back().b, stream);
+}
+void rpf_handle::call_begin() {
+    prof_reset();
+    cudaEventRecord(ev_begin, stream);
+}
+int rpf_handle::call_end() {
+    cudaEventRecord(ev_end, stream);
+    cudaError_t e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) return rpf_fail(this, RPF_ERR_CUDA, std::string("stream sync: ") + cudaGetErrorString(e));
+    float ms = 0; cudaEventElapsedTime(&ms, ev_begin, ev_end); last_ms = ms;
+    for (auto& pe : pending) {
+        float m = 0; cudaEventElapsedTime(&m, pe.a, pe.b);
+        phase_ms[pe.phase] += m;
+        event_pool.push_back(pe.a); event_pool.push_back(pe.b);
+    }
+    pending.clear();
+    return RPF_OK;
+}
+
+static const char* kPhaseNames[PH_COUNT] = {
+    "project", "top_hist", "top_pick", "top_compact", "top_finish", "top_ties", "top_relabel", "bottom",
+    "q_project", "q_traverse", "q_knn", "q_candidates", "truth", "recall", "merge", "misc"};
+
+// ---------------------------------------------------------------------------------------------------
+// topology: Internal.hs:289 (Tip iff ixLev >= maxDepth || length xs' <= minLeaf), :495/:503 (nh = n div 2)
+// ---------------------------------------------------------------------------------------------------
+void build_topology(Topology& tp, int64_t n, int maxDepth, int minLeaf) {
+    tp = Topology();
+    tp.n = n; tp.maxDepth = maxDepth; tp.minLeaf = minLeaf;
+    tp.start.push_back(0); tp.size.push_back((uint32_t)n); tp.child.push_back(-1); tp.depth.push_back(0);
+    tp.level_off.push_back(0);
+    int64_t lo = 0, hi = 1;
+    int lev = 0;
+    while (lo < hi) {
+        uint32_t mx = 0; bool any_internal = false;
+        for (int64_t g = lo; g < hi; ++g) {
+            const uint32_t sz = tp.size[g];
+            mx = std::max(mx, sz);
+            const bool leaf = lev >= maxDepth || (int64_t)sz <= (int64_t)minLeaf;
+            if (!leaf) {
+                any_internal = true;
+                const uint32_t nh = sz / 2;
+                tp.child[g] = (int32_t)tp.start.size();
+                tp.start.push_back(tp.start[g]);      tp.size.push_back(nh);      tp.child.push_back(-1); tp.depth.push_back(lev + 1);
+                tp.start.push_back(tp.start[g] + nh); tp.size.push_back(sz - nh); tp.child.push_back(-1); tp.depth.push_back(lev + 1);
+            }
+        }
+        tp.lvl_maxsize.push_back(mx);
+        tp.level_off.push_back(hi);
+        ++lev;
+        if (any_internal) tp.L_eff = lev;
+        lo = hi; hi = (int64_t)tp.start.size();
+    }
+    tp.nlevels = lev;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// SplitMix64 + sparse hyperplane sampler (host side; replaces Gen.hs:148-195 under Batch.hs:59-61).
+// splitmix: mkSMGen s = SMGen (mix64 s) (mixGamma (s + goldenGamma)); nextWord64 advances seed by gamma.
+// ---------------------------------------------------------------------------------------------------
+namespace {
+struct SMGen { uint64_t seed, gamma; };
+inline uint64_t sx(int n, uint64_t w) { return w ^ (w >> n); }
+inline uint64_t mix64(uint64_t z) { z = sx(33, z) * 0xff51afd7ed558ccdULL; z = sx(33, z) * 0xc4ceb9fe1a85ec53ULL; return sx(33, z); }
+inline uint64_t mix_gamma(uint64_t z) {
+    z = sx(30, z) * 0xbf58476d1ce4e5b9ULL; z = sx(27, z) * 0x94d049bb133111ebULL; z = sx(31, z) | 1ULL;
+    return __builtin_popcountll(z ^ (z >> 1)) >= 24 ? z : z ^ 0xaaaaaaaaaaaaaaaaULL;
+}
+inline SMGen mk_smgen(uint64_t s) { return SMGen{mix64(s), mix_gamma(s + 0x9e3779b97f4a7c15ULL)}; }
+inline double next_double(SMGen& g) { g.seed += g.gamma; return (double)(mix64(g.seed) >> 11) * 0x1.0p-53; }
+// inverse normal CDF: Acklam's rational approximation + one Halley step (erf package's invnormcdf, as
+// recalled; UNVERIFIED against Hackage -- use rpf_set_hyperplanes for bit-exact parity with a Haskell host).
+double inv_norm_cdf(double p) {
+    static const double a[6] = {-3.969683028665376e+01, 2.209460984245205e+02, -2.759285104469687e+02, 1.383577518672690e+02, -3.066479806614716e+01, 2.506628277459239e+00};
+    static const double b[5] = {-5.447609879822406e+01, 1.615858368580409e+02, -1.556989798598866e+02, 6.680131188771972e+01, -1.328068155288572e+01};
+    static const double c[6] = {-7.784894002430293e-03, -3.223964580411365e-01, -2.400758277161838e+00, -2.549732539343734e+00, 4.374664141464968e+00, 2.938163982698783e+00};
+    static const double dd[4] = {7.784695709041462e-03, 3.224671290700398e-01, 2.445134137142996e+00, 3.754408661907416e+00};
+    if (p == 0) return -INFINITY;
+    if (p == 1) return INFINITY;
+    const double plow = 0.02425, phigh = 1 - plow;
+    double x;
+    if (p < plow) { double q = std::sqrt(-2 * std::log(p)); x = (((((c[0]*q+c[1])*q+c[2])*q+c[3])*q+c[4])*q+c[5]) / ((((dd[0]*q+dd[1])*q+dd[2])*q+dd[3])*q+1); }
+    else if (p <= phigh) { double q = p - 0.5, r = q*q; x = (((((a[0]*r+a[1])*r+a[2])*r+a[3])*r+a[4])*r+a[5])*q / (((((b[0]*r+b[1])*r+b[2])*r+b[3])*r+b[4])*r+1); }
+    else { double q = std::sqrt(-2 * std::log(1 - p)); x = -(((((c[0]*q+c[1])*q+c[2])*q+c[3])*q+c[4])*q+c[5]) / ((((dd[0]*q+dd[1])*q+dd[2])*q+dd[3])*q+1); }
+    const double e = 0.5 * std::erfc(-x / std::sqrt(2.0)) - p;
+    const double u = e * std::sqrt(2 * M_PI) * std::exp(x * x / 2);
+    return x - u / (1 + x * u / 2);
+}
+}  // namespace
+
+static void free_hp_dev(rpf_handle* h) {
+    if (h->d_hp_off) cudaFree(h->d_hp_off);
+    if (h->d_hp_idx) cudaFree(h->d_hp_idx);
+    if (h->d_hp_val) cudaFree(h->d_hp_val);
+    h->d_hp_off = nullptr; h->d_hp_idx = nullptr; h->d_hp_val = nullptr;
+}
+static void free_topo_dev(rpf_handle* h) {
+    if (h->d_node_start) cudaFree(h->d_node_start);
+    if (h->d_node_size) cudaFree(h->d_node_size);
+    if (h->d_node_child) cudaFree(h->d_node_child);
+    if (h->d_node_depth) cudaFree(h->d_node_depth);
+    h->d_node_start = h->d_node_size = nullptr; h->d_node_child = h->d_node_depth = nullptr;
+}
+static void free_forest_dev(rpf_handle* h) {
+    if (h->d_thr) cudaFree(h->d_thr);
+    if (h->d_mlo) cudaFree(h->d_mlo);
+    if (h->d_mhi) cudaFree(h->d_mhi);
+    if (h->d_perm) cudaFree(h->d_perm);
+    h->d_thr = h->d_mlo = h->d_mhi = nullptr; h->d_perm = nullptr; h->built = false;
+}
+
+static int upload_hyperplanes(rpf_handle* h) {
+    free_hp_dev(h);
+    free_forest_dev(h);
+    const size_t nrow = h->hp_off.size(), nnz = h->hp_idx.size();
+    RPF_CUDA(h, cudaMalloc(&h->d_hp_off, nrow * 8));
+    RPF_CUDA(h, cudaMalloc(&h->d_hp_idx, std::max<size_t>(nnz, 1) * 4));
+    RPF_CUDA(h, cudaMalloc(&h->d_hp_val, std::max<size_t>(nnz, 1) * 8));
+    RPF_CUDA(h, cudaMemcpy(h->d_hp_off, h->hp_off.data(), nrow * 8, cudaMemcpyHostToDevice));
+    if (nnz) {
+        RPF_CUDA(h, cudaMemcpy(h->d_hp_idx, h->hp_idx.data(), nnz * 4, cudaMemcpyHostToDevice));
+        RPF_CUDA(h, cudaMemcpy(h->d_hp_val, h->hp_val.data(), nnz * 8, cudaMemcpyHostToDevice));
+    }
+    return RPF_OK;
+}
+
+#define RPF_SETDEV(h) RPF_CUDA(h, cudaSetDevice((h)->device))
+
+extern "C" {
+
+int rpf_abi_version(void) { return 1; }
+
+int rpf_create(rpf_handle** out, int device) {
+    if (!out) return RPF_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return RPF_ERR_CUDA;   // no CPU fallback
+    if (device < 0 || device >= ndev) return RPF_ERR_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return RPF_ERR_CUDA;
+    rpf_handle* h = new rpf_handle();
+    h->device = device;
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&h->ev_begin) != cudaSuccess || cudaEventCreate(&h->ev_end) != cudaSuccess) {
+        delete h;
+        return RPF_ERR_CUDA;
+    }
+    *out = h;
+    return RPF_OK;
+}
+
+void rpf_destroy(rpf_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    if (h->ownX && h->dX) cudaFree((void*)h->dX);
+    free_hp_dev(h); free_topo_dev(h); free_forest_dev(h);
+    for (auto e : h->event_pool) cudaEventDestroy(e);
+    if (h->ev_begin) cudaEventDestroy(h->ev_begin);
+    if (h->ev_end) cudaEventDestroy(h->ev_end);
+    cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+const char* rpf_last_error(const rpf_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+int rpf_set_points(rpf_handle* h, const double* X, int64_t n, int32_t d) {
+    if (!h) return RPF_ERR_ARG;
+    if (n < 0 || d < 1 || (n > 0 && !X)) return rpf_fail(h, RPF_ERR_ARG, "set_points: bad n/d/X");
+    if (n >= (int64_t)1 << 31) return rpf_fail(h, RPF_ERR_UNSUPPORTED, "set_points: n must be < 2^31");
+    RPF_SETDEV(h);
+    if (h->ownX && h->dX) cudaFree((void*)h->dX);
+    h->dX = nullptr; h->ownX = false;
+    free_forest_dev(h);
+    double* p = nullptr;
+    RPF_CUDA(h, cudaMalloc(&p, std::max<size_t>((size_t)n * d * 8, 16)));
+    if (n > 0) RPF_CUDA(h, cudaMemcpyAsync(p, X, (size_t)n * d * 8, cudaMemcpyHostToDevice, h->stream));
+    RPF_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->dX = p; h->ownX = true; h->n = n; h->d = d;
+    return RPF_OK;
+}
+
+int rpf_set_points_device(rpf_handle* h, const double* X_dev, int64_t n, int32_t d) {
+    if (!h) return RPF_ERR_ARG;
+    if (n < 0 || d < 1 || (n > 0 && !X_dev)) return rpf_fail(h, RPF_ERR_ARG, "set_points_device: bad n/d/X");
+    if (n >= (int64_t)1 << 31) return rpf_fail(h, RPF_ERR_UNSUPPORTED, "set_points_device: n must be < 2^31");
+    RPF_SETDEV(h);
+    if (h->ownX && h->dX) cudaFree((void*)h->dX);
+    free_forest_dev(h);
+    h->dX = X_dev; h->ownX = false; h->n = n; h->d = d;
+    return RPF_OK;
+}
+
+int rpf_set_hyperplanes(rpf_handle* h, int32_t T, int32_t maxDepth, const int64_t* off, const int32_t* idx, const double* val) {
+    if (!h) return RPF_ERR_ARG;
+    if (T < 1 || maxDepth < 0 || !off) return rpf_fail(h, RPF_ERR_ARG, "set_hyperplanes: bad T/maxDepth/off");
+    RPF_SETDEV(h);
+    const int64_t nrow = (int64_t)T * maxDepth;
+    const int64_t nnz = off[nrow];
+    if (off[0] != 0 || nnz < 0 || (nnz > 0 && (!idx || !val))) return rpf_fail(h, RPF_ERR_ARG, "set_hyperplanes: bad CSR");
+    for (int64_t r = 0; r < nrow; ++r) if (off[r + 1] < off[r]) return rpf_fail(h, RPF_ERR_ARG, "set_hyperplanes: offsets not monotone");
+    if (h->d > 0) for (int64_t q = 0; q < nnz; ++q) if (idx[q] < 0 || idx[q] >= h->d) return rpf_fail(h, RPF_ERR_ARG, "set_hyperplanes: component index out of range");
+    h->T = T; h->hpDepth = maxDepth;
+    h->hp_off.assign(off, off + nrow + 1);
+    h->hp_idx.assign(idx, idx + nnz);
+    h->hp_val.assign(val, val + nnz);
+    return upload_hyperplanes(h);
+}
+
+int rpf_gen_hyperplanes(rpf_handle* h, uint64_t seed, int32_t T_total, int32_t maxDepth, double pnz, int32_t d,
+                        int32_t t_first, int32_t T_local) {
+    if (!h) return RPF_ERR_ARG;
+    if (T_total < 1 || maxDepth < 0 || d < 1 || t_first < 0 || T_local < 1 || t_first + T_local > T_total)
+        return rpf_fail(h, RPF_ERR_ARG, "gen_hyperplanes: bad arguments");
+    RPF_SETDEV(h);
+    // One sequential generator for the whole forest: tree-major, level-major, component-minor; per component
+    // one uniform (bernoulli p = u < p) and, on a hit, one more for the normal (Gen.hs:183-195).
+    SMGen g = mk_smgen(seed);
+    h->hp_off.clear(); h->hp_idx.clear(); h->hp_val.clear();
+    for (int t = 0; t < T_total; ++t) {
+        const bool keep = t >= t_first && t < t_first + T_local;
+        for (int l = 0; l < maxDepth; ++l) {
+            if (keep) h->hp_off.push_back((int64_t)h->hp_idx.size());
+            for (int i = 0; i < d; ++i) {
+                const double u = next_double(g);
+                if (u < pnz) {
+                    const double x = inv_norm_cdf(next_double(g)) * 1.0 + 0.0;
+                    if (keep) { h->hp_idx.push_back(i); h->hp_val.push_back(x); }
+                }
+            }
+        }
+    }
+    h->hp_off.push_back((int64_t)h->hp_idx.size());
+    h->T = T_local; h->hpDepth = maxDepth;
+    return upload_hyperplanes(h);
+}
+
+// host-only variants (no handle, no GPU): used by the shim for sizing and by the CPU test-suite
+int64_t rpf_sample_hyperplanes(uint64_t seed, int32_t T, int32_t maxDepth, double pnz, int32_t d,
+                               int64_t* off, int32_t* idx, double* val) {
+    if (T < 0 || maxDepth < 0 || d < 0) return RPF_ERR_ARG;
+    SMGen g = mk_smgen(seed);
+    int64_t nnz = 0;
+    for (int t = 0; t < T; ++t)
+        for (int l = 0; l < maxDepth; ++l) {
+            if (off) off[(int64_t)t * maxDepth + l] = nnz;
+            for (int i = 0; i < d; ++i) {
+                const double u = next_double(g);
+                if (u < pnz) {
+                    const double x = inv_norm_cdf(next_double(g)) * 1.0 + 0.0;
+                    if (idx) idx[nnz] = i;
+                    if (val) val[nnz] = x;
+                    ++nnz;
+                }
+            }
+        }
+    if (off) off[(int64_t)T * maxDepth] = nnz;
+    return nnz;
+}
+
+int64_t rpf_topology_plan(int64_t n, int32_t maxDepth, int32_t minLeaf, int64_t* child, int32_t* depth,
+                          int64_t* seg_start, int64_t* seg_size) {
+    if (n < 0 || maxDepth < 0 || minLeaf < 0 || n >= ((int64_t)1 << 31)) return RPF_ERR_ARG;
+    Topology tp;
+    build_topology(tp, n, maxDepth, minLeaf);
+    for (int64_t g = 0; g < tp.nnodes(); ++g) {
+        if (child) child[g] = tp.child[g];
+        if (depth) depth[g] = tp.depth[g];
+        if (seg_start) seg_start[g] = tp.start[g];
+        if (seg_size) seg_size[g] = tp.size[g];
+    }
+    return tp.nnodes();
+}
+
+/* rpTreeCfg, src/Data/RPTree/Conduit.hs:132-141 */
+void rpf_rptree_cfg(int64_t minLeaf, int64_t n, int64_t d, int64_t* maxDepth, int64_t* chunk, double* pnz) {
+    if (maxDepth) *maxDepth = (int64_t)std::ceil(std::log((double)n / (double)minLeaf) / std::log(2.0));
+    if (chunk) *chunk = (int64_t)std::ceil((double)n / 100.0);
+    if (pnz) { const double p = 1.0 / (std::log((double)d) / std::log(10.0)); *pnz = p < 1.0 ? p : 1.0; }
+}
+
+int rpf_leaf_order_exact(const rpf_handle* h) { return h ? (h->leaf_order_exact ? 1 : 0) : -1; }
+
+int64_t rpf_hyperplane_nnz(const rpf_handle* h) { return h ? (int64_t)h->hp_idx.size() : -1; }
+
+int rpf_get_hyperplanes(const rpf_handle* h, int64_t* off, int32_t* idx, double* val) {
+    if (!h) return RPF_ERR_ARG;
+    if (off) std::memcpy(off, h->hp_off.data(), h->hp_off.size() * 8);
+    if (idx && !h->hp_idx.empty()) std::memcpy(idx, h->hp_idx.data(), h->hp_idx.size() * 4);
+    if (val && !h->hp_val.empty()) std::memcpy(val, h->hp_val.data(), h->hp_val.size() * 8);
+    return RPF_OK;
+}
+
+int rpf_build(rpf_handle* h, int32_t maxDepth, int32_t minLeaf) {
+    if (!h) return RPF_ERR_ARG;
+    if (!h->dX && h->n != 0) return rpf_fail(h, RPF_ERR_STATE, "build: call rpf_set_points first");
+    if (h->d < 1) return rpf_fail(h, RPF_ERR_STATE, "build: call rpf_set_points first");
+    if (h->T < 1) return rpf_fail(h, RPF_ERR_STATE, "build: call rpf_set_hyperplanes / rpf_gen_hyperplanes first");
+    if (maxDepth < 0 || minLeaf < 0) return rpf_fail(h, RPF_ERR_ARG, "build: maxDepth and minLeaf must be >= 0");
+    if (maxDepth > h->hpDepth) return rpf_fail(h, RPF_ERR_ARG, "build: maxDepth exceeds the number of hyperplanes per tree");
+    if (maxDepth > 62) return rpf_fail(h, RPF_ERR_UNSUPPORTED, "build: maxDepth > 62");
+    for (int32_t q : h->hp_idx) if (q < 0 || q >= h->d) return rpf_fail(h, RPF_ERR_ARG, "build: hyperplane component index out of range");
+    RPF_SETDEV(h);
+    build_topology(h->topo, h->n, maxDepth, minLeaf);
+    const Topology& tp = h->topo;
+    free_topo_dev(h);
+    const size_t nn = (size_t)tp.nnodes();
+    RPF_CUDA(h, cudaMalloc(&h->d_node_start, nn * 4));
+    RPF_CUDA(h, cudaMalloc(&h->d_node_size, nn * 4));
+    RPF_CUDA(h, cudaMalloc(&h->d_node_child, nn * 4));
+    RPF_CUDA(h, cudaMalloc(&h->d_node_depth, nn * 4));
+    RPF_CUDA(h, cudaMemcpy(h->d_node_start, tp.start.data(), nn * 4, cudaMemcpyHostToDevice));
+    RPF_CUDA(h, cudaMemcpy(h->d_node_size, tp.size.data(), nn * 4, cudaMemcpyHostToDevice));
+    RPF_CUDA(h, cudaMemcpy(h->d_node_child, tp.child.data(), nn * 4, cudaMemcpyHostToDevice));
+    RPF_CUDA(h, cudaMemcpy(h->d_node_depth, tp.depth.data(), nn * 4, cudaMemcpyHostToDevice));
+    h->built = false;
+    h->call_begin();
+    int rc = rpf_build_impl(h);
+    int rc2 = h->call_end();
+    if (rc) return rc;
+    if (rc2) return rc2;
+    h->built = true;
+    return RPF_OK;
+}
+
+int rpf_build_chunked(rpf_handle* h, int32_t maxDepth, int32_t minLeaf, int64_t chunk) {
+    if (!h) return RPF_ERR_ARG;
+    if (chunk < 1) return rpf_fail(h, RPF_ERR_ARG, "build_chunked: chunk must be >= 1");
+    if (chunk >= h->n) return rpf_build(h, maxDepth, minLeaf);   // one chunk == insert into an empty Tip == forestBatch
+    return rpf_fail(h, RPF_ERR_UNSUPPORTED,
+                    "build_chunked: streaming update with chunk < n (insert Bin case, Internal.hs:274-285) is not implemented yet");
+}
+
+int64_t rpf_num_nodes(const rpf_handle* h) { return h ? h->topo.nnodes() : -1; }
+int32_t rpf_num_trees(const rpf_handle* h) { return h ? h->T : -1; }
+
+int rpf_topology(const rpf_handle* h, int64_t* child, int32_t* depth, int64_t* seg_start, int64_t* seg_size) {
+    if (!h) return RPF_ERR_ARG;
+    const Topology& tp = h->topo;
+    for (int64_t g = 0; g < tp.nnodes(); ++g) {
+        if (child) child[g] = tp.child[g];
+        if (depth) depth[g] = tp.depth[g];
+        if (seg_start) seg_start[g] = tp.start[g];
+        if (seg_size) seg_size[g] = tp.size[g];
+    }
+    return RPF_OK;
+}
+
+int rpf_tree_export(rpf_handle* h, int32_t t, double* thr, double* mlo, double* mhi, uint32_t* perm) {
+    if (!h) return RPF_ERR_ARG;
+    if (!h->built) return rpf_fail(h, RPF_ERR_STATE, "tree_export: forest not built");
+    if (t < 0 || t >= h->T) return rpf_fail(h, RPF_ERR_ARG, "tree_export: tree index out of range");
+    RPF_SETDEV(h);
+    const size_t nn = (size_t)h->topo.nnodes();
+    if (thr) RPF_CUDA(h, cudaMemcpy(thr, h->d_thr + (size_t)t * nn, nn * 8, cudaMemcpyDeviceToHost));
+    if (mlo) RPF_CUDA(h, cudaMemcpy(mlo, h->d_mlo + (size_t)t * nn, nn * 8, cudaMemcpyDeviceToHost));
+    if (mhi) RPF_CUDA(h, cudaMemcpy(mhi, h->d_mhi + (size_t)t * nn, nn * 8, cudaMemcpyDeviceToHost));
+    if (perm && h->n > 0) RPF_CUDA(h, cudaMemcpy(perm, h->d_perm + (size_t)t * h->n, (size_t)h->n * 4, cudaMemcpyDeviceToHost));
+    return RPF_OK;
+}
+
+int rpf_candidates_count(rpf_handle* h, const double* Q, int64_t nq, int32_t t, int64_t* off_out) {
+    if (!h) return RPF_ERR_ARG;
+    if (!h->built) return rpf_fail(h, RPF_ERR_STATE, "candidates: forest not built");
+    if (nq < 0 || (nq > 0 && !Q) || !off_out || t < -1 || t >= h->T) return rpf_fail(h, RPF_ERR_ARG, "candidates_count: bad arguments");
+    RPF_SETDEV(h);
+    h->call_begin();
+    int rc = rpf_candidates_impl(h, Q, nq, t, off_out, nullptr, nullptr);
+    int rc2 = h->call_end();
+    return rc ? rc : rc2;
+}
+
+int rpf_candidates(rpf_handle* h, const double* Q, int64_t nq, int32_t t, const int64_t* off, uint32_t* ids) {
+    if (!h) return RPF_ERR_ARG;
+    if (!h->built) return rpf_fail(h, RPF_ERR_STATE, "candidates: forest not built");
+    if (nq < 0 || (nq > 0 && !Q) || !off || t < -1 || t >= h->T) return rpf_fail(h, RPF_ERR_ARG, "candidates: bad arguments");
+    RPF_SETDEV(h);
+    h->call_begin();
+    int rc = rpf_candidates_impl(h, Q, nq, t, nullptr, off, ids);
+    int rc2 = h->call_end();
+    return rc ? rc : rc2;
+}
+
+int rpf_knn(rpf_handle* h, const double* Q, int64_t nq, int32_t k, int32_t dedup, double* dist, uint32_t* ids, int32_t* count) {
+    if (!h) return RPF_ERR_ARG;
+    if (!h->built) return rpf_fail(h, RPF_ERR_STATE, "knn: forest not built");
+    if (nq < 0 || (nq > 0 && (!Q || !dist || !ids)) || k < 1 || k > 1024) return rpf_fail(h, RPF_ERR_ARG, "knn: bad arguments (1 <= k <= 1024)");
+    RPF_SETDEV(h);
+    h->call_begin();
+    int rc = rpf_knn_impl(h, Q, nq, k, dedup, dist, ids, count);
+    int rc2 = h->call_end();
+    return rc ? rc : rc2;
+}
+
+int rpf_recall(rpf_handle* h, const double* Q, int64_t nq, int32_t k, double* recall_sum) {
+    if (!h) return RPF_ERR_ARG;
+    if (!h->built) return rpf_fail(h, RPF_ERR_STATE, "recall: forest not built");
+    if (nq < 0 || (nq > 0 && (!Q || !recall_sum)) || k < 1 || k > 1024) return rpf_fail(h, RPF_ERR_ARG, "recall: bad arguments (1 <= k <= 1024)");
+    RPF_SETDEV(h);
+    h->call_begin();
+    int rc = rpf_recall_impl(h, Q, nq, k, recall_sum);
+    int rc2 = h->call_end();
+    return rc ? rc : rc2;
+}
+
+int rpf_brute_knn(rpf_handle* h, const double* Q, int64_t nq, int32_t k, double* dist, uint32_t* ids) {
+    if (!h) return RPF_ERR_ARG;
+    if (!h->dX) return rpf_fail(h, RPF_ERR_STATE, "brute_knn: call rpf_set_points first");
+    if (nq < 0 || (nq > 0 && (!Q || !dist || !ids)) || k < 1 || k > 1024) return rpf_fail(h, RPF_ERR_ARG, "brute_knn: bad arguments (1 <= k <= 1024)");
+    RPF_SETDEV(h);
+    h->call_begin();
+    int rc = rpf_brute_knn_impl(h, Q, nq, k, dist, ids);
+    int rc2 = h->call_end();
+    return rc ? rc : rc2;
+}
+
+int rpf_merge_topk(rpf_handle* h, int32_t G, int64_t nq, int32_t k, int32_t dedup, const double* dist, const uint32_t* ids,
+                   const int32_t* count, double* dist_out, uint32_t* ids_out, int32_t* count_out) {
+    if (!h) return RPF_ERR_ARG;
+    if (G < 1 || nq < 0 || k < 1 || k > 1024 || (nq > 0 && (!dist || !ids || !count || !dist_out || !ids_out)))
+        return rpf_fail(h, RPF_ERR_ARG, "merge_topk: bad arguments");
+    RPF_SETDEV(h);
+    h->call_begin();
+    int rc = rpf_merge_impl(h, G, nq, k, dedup, dist, ids, count, dist_out, ids_out, count_out);
+    int rc2 = h->call_end();
+    return rc ? rc : rc2;
+}
+
+double rpf_last_device_ms(const rpf_handle* h) { return h ? h->last_ms : -1.0; }
+int rpf_set_profiling(rpf_handle* h, int on) { if (!h) return RPF_ERR_ARG; h->profiling = on != 0; return RPF_OK; }
+int rpf_get_profile(const rpf_handle* h, double* ms, int64_t* launches, int cap) {
+    if (!h) return RPF_ERR_ARG;
+    for (int i = 0; i < PH_COUNT && i < cap; ++i) {
+        if (ms) ms[i] = h->phase_ms[i];
+        if (launches) launches[i] = h->phase_launches[i];
+    }
+    return PH_COUNT;
+}
+const char* rpf_phase_name(int i) { return (i >= 0 && i < PH_COUNT) ? kPhaseNames[i] : ""; }
+int64_t rpf_launch_count(const rpf_handle* h) { return h ? h->launches : -1; }
+int rpf_set_bottom_cap(rpf_handle* h, int32_t cap) {
+    if (!h) return RPF_ERR_ARG;
+    if (cap != 256 && cap != 1024 && cap != 4096 && cap != 8192) return rpf_fail(h, RPF_ERR_ARG, "bottom_cap must be 256, 1024, 4096 or 8192");
+    h->bottom_cap = cap;
+    return RPF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,666 @@
+// query.cu -- candidates / knn / knnPQ / recallWith on sm_100a.
+//
+// Replaces, for dense Double data and distf = metricL2, the reference's
+//   candidates   src/Data/RPTree.hs:289-314   (margin-aware descent, may fork into both children)
+//   knn          src/Data/RPTree.hs:168-176   (all candidates of all trees, duplicates kept, stable sort, take k)
+//   knnPQ        src/Data/RPTree.hs:181-194,224-227 (one result per distinct distance)
+//   recallWith   src/Data/RPTree.hs:259-282   (mean over trees of |candidates /\ true top-k| / k)
+//   metricDDL2   src/Data/RPTree/Internal.hs:403-406
+//
+// Queries are projected onto every (tree, level) hyperplane with the same exact-order kernel as the build
+// (k_project), so the descent is a pure table walk over the 24-byte node records (L2 resident).  The re-rank is
+// HBM bound: one thread per candidate streams the candidate's row with 256-bit loads and accumulates
+// sum (x-q)^2 strictly left to right (no FMA) so distances, hence orderings, match the reference.
+#include "rpf_internal.h"
+#include <algorithm>
+#include <vector>
+
+typedef unsigned long long ull;
+
+int rpf_project_launch(rpf_handle* h, int phase, const double* dX, int64_t n, int t0, int Tg, int L, bool ord, void* out,
+                       ull* kmin, ull* kmax);
+
+__device__ __forceinline__ int q_ilog2(unsigned v) { return 31 - __clz(v); }
+__device__ __forceinline__ unsigned q_next_pow2(unsigned v) { return v <= 1 ? 1u : 1u << (32 - __clz(v - 1)); }
+
+// ---------------------------------------------------------------------------------------------------
+// descent
+// ---------------------------------------------------------------------------------------------------
+// One thread per (query, tree).  Emits the BFS ids of the reached leaves, left to right, into
+// segs[(q*Tq + tt)*S ..]; cnt holds the true count (may exceed S -> caller retries with a larger S).
+__global__ void k_traverse(const double* __restrict__ keysQ, int64_t nq, int T, int L, int64_t nn,
+                           const int32_t* __restrict__ child, const int32_t* __restrict__ depth,
+                           const double* __restrict__ thr, const double* __restrict__ mlo, const double* __restrict__ mhi,
+                           int S, int t_only, uint32_t* __restrict__ segs, uint32_t* __restrict__ cnt, uint32_t* __restrict__ maxcnt) {
+    const int Tq = t_only >= 0 ? 1 : T;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nq * Tq) return;
+    const int64_t q = idx % nq;
+    const int tt = (int)(idx / nq);
+    const int t = t_only >= 0 ? t_only : tt;
+    const double* thr_t = thr + (int64_t)t * nn;
+    const double* mlo_t = mlo + (int64_t)t * nn;
+    const double* mhi_t = mhi + (int64_t)t * nn;
+    const double* kq = keysQ + (int64_t)t * L * nq + q;
+    int stk[64];
+    int sp = 0, g = 0;
+    uint32_t c = 0;
+    uint32_t* out = segs + (q * Tq + tt) * (int64_t)S;
+    while (true) {
+        int ch;
+        while ((ch = __ldg(child + g)) >= 0) {
+            const int lev = __ldg(depth + g);
+            const double proj = kq[(int64_t)lev * nq];
+            const double th = thr_t[g], lo = mlo_t[g], hi = mhi_t[g];
+            const double dl = fabs(__dsub_rn(lo, proj)), dr = fabs(__dsub_rn(hi, proj));
+            if (proj < th && dl > dr) { stk[sp++] = ch + 1; g = ch; }
+            else if (proj < th) g = ch;
+            else if (proj > th && dl < dr) { stk[sp++] = ch + 1; g = ch; }
+            else g = ch + 1;
+        }
+        if (c < (uint32_t)S) out[c] = (uint32_t)g;
+        ++c;
+        if (sp == 0) break;
+        g = stk[--sp];
+    }
+    cnt[q * Tq + tt] = c;
+    if (c > (uint32_t)S) atomicMax(maxcnt, c);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// exact distance
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ld256(const double* p, double& a, double& b, double& c, double& d) {
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+// sqrt (sum_j (x_j - q_j)^2), left fold from 0, separate roundings (Internal.hs:403-406)
+__device__ __forceinline__ double dist_exact(const double* __restrict__ row, const double* __restrict__ sq, int d, bool vec) {
+    double acc = 0.0;
+    if (vec) {
+        for (int j = 0; j < d; j += 4) {
+            double x0, x1, x2, x3;
+            ld256(row + j, x0, x1, x2, x3);
+            const double d0 = __dsub_rn(x0, sq[j]), d1 = __dsub_rn(x1, sq[j + 1]), d2 = __dsub_rn(x2, sq[j + 2]), d3 = __dsub_rn(x3, sq[j + 3]);
+            acc = __dadd_rn(acc, __dmul_rn(d0, d0));
+            acc = __dadd_rn(acc, __dmul_rn(d1, d1));
+            acc = __dadd_rn(acc, __dmul_rn(d2, d2));
+            acc = __dadd_rn(acc, __dmul_rn(d3, d3));
+        }
+    } else {
+        for (int j = 0; j < d; ++j) {
+            const double df = __dsub_rn(__ldg(row + j), sq[j]);
+            acc = __dadd_rn(acc, __dmul_rn(df, df));
+        }
+    }
+    return __dsqrt_rn(acc);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// (key, pos, id) sort + keep-k in shared memory.  Keys are the raw bits of non-negative doubles (order
+// preserving); pos is the candidate's position in the reference's concatenation order, which makes the
+// bitonic network reproduce the reference's STABLE sort (RPTree.hs:174).
+// ---------------------------------------------------------------------------------------------------
+#define KNN_NT 256
+#define KNN_BUF 4096
+
+template <int NT>
+__device__ void sort3(ull* skey, uint32_t* spos, uint32_t* sid, unsigned m) {
+    const unsigned Pv = q_next_pow2(m), half = Pv >> 1;
+    for (unsigned k = 2; k <= Pv; k <<= 1) {
+        const int lk = q_ilog2(k);
+        for (unsigned c = threadIdx.x; c < half; c += NT) {
+            const unsigned blk = c >> (lk - 1), w = c & ((k >> 1) - 1);
+            const unsigned i = (blk << lk) + w, p = (blk << lk) + (k - 1 - w);
+            if (p < m) {
+                ull a = skey[i], b = skey[p]; uint32_t pa = spos[i], pb = spos[p];
+                if (a > b || (a == b && pa > pb)) { skey[i] = b; skey[p] = a; spos[i] = pb; spos[p] = pa; uint32_t x = sid[i]; sid[i] = sid[p]; sid[p] = x; }
+            }
+        }
+        __syncthreads();
+        for (unsigned j = k >> 2; j > 0; j >>= 1) {
+            const int lj = q_ilog2(j);
+            for (unsigned c = threadIdx.x; c < half; c += NT) {
+                const unsigned i = ((c >> lj) << (lj + 1)) + (c & (j - 1)), p = i + j;
+                if (p < m) {
+                    ull a = skey[i], b = skey[p]; uint32_t pa = spos[i], pb = spos[p];
+                    if (a > b || (a == b && pa > pb)) { skey[i] = b; skey[p] = a; spos[i] = pb; spos[p] = pa; uint32_t x = sid[i]; sid[i] = sid[p]; sid[p] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// after sort3: keep the first k entries (dedup: first of every run of equal keys). Returns kept count.
+template <int NT>
+__device__ unsigned keep_k(ull* skey, uint32_t* spos, uint32_t* sid, unsigned tot, unsigned k, int dedup, unsigned* s_n) {
+    if (!dedup) return tot < k ? tot : k;
+    if (threadIdx.x < 32) {
+        const unsigned lane = threadIdx.x;
+        unsigned w = 0;
+        for (unsigned base = 0; base < tot && w < k; base += 32) {
+            const unsigned i = base + lane;
+            ull kv = 0; uint32_t pv = 0, iv = 0; bool keep = false;
+            if (i < tot) { kv = skey[i]; pv = spos[i]; iv = sid[i]; keep = (i == 0) || (skey[i - 1] != kv); }
+            const unsigned bal = __ballot_sync(0xffffffffu, keep);
+            const unsigned dst = w + __popc(bal & ((1u << lane) - 1));
+            __syncwarp();
+            if (keep && dst < k) { skey[dst] = kv; spos[dst] = pv; sid[dst] = iv; }
+            __syncwarp();
+            w += __popc(bal);
+        }
+        if (lane == 0) *s_n = w < k ? w : k;
+    }
+    __syncthreads();
+    return *s_n;
+}
+
+// exclusive prefix of slot sizes (nslots entries) -> pre[0..nslots]; all threads participate
+template <int NT>
+__device__ void slot_prefix(uint32_t* pre, unsigned nslots, uint32_t* part /*NT+1*/) {
+    const unsigned per = (nslots + NT - 1) / NT, b0 = threadIdx.x * per, b1 = min(nslots, b0 + per);
+    uint32_t s = 0;
+    for (unsigned i = b0; i < b1; ++i) s += pre[i];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) { uint32_t c = 0; for (int j = 0; j < NT; ++j) { uint32_t v = part[j]; part[j] = c; c += v; } part[NT] = c; }
+    __syncthreads();
+    uint32_t c = part[threadIdx.x];
+    for (unsigned i = b0; i < b1; ++i) { uint32_t v = pre[i]; pre[i] = c; c += v; }
+    if (threadIdx.x == 0) pre[nslots] = part[NT];
+    __syncthreads();
+}
+
+struct QArgs {
+    int64_t n, nq, nn;
+    int d, T, S, k, dedup, vec;
+    const double* X;
+    const double* Q;
+    const uint32_t* perm;
+    const uint32_t* nstart;
+    const uint32_t* nsize;
+    const uint32_t* segs;
+    const uint32_t* cnt;
+    double* dist;
+    uint32_t* ids;
+    int32_t* count;
+};
+
+// slot sizes for query q into pre[0..nslots): slot = tt*S + j
+__device__ __forceinline__ void load_slots(const QArgs& A, int64_t q, int Tq, uint32_t* pre, int NT) {
+    const unsigned nslots = (unsigned)Tq * A.S;
+    for (unsigned s = threadIdx.x; s < nslots; s += NT) {
+        const int tt = s / A.S, j = s % A.S;
+        const uint32_t c = A.cnt[q * Tq + tt];
+        pre[s] = (uint32_t)j < c ? A.nsize[A.segs[(q * Tq + tt) * (int64_t)A.S + j]] : 0u;
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ unsigned find_slot(const uint32_t* pre, unsigned nslots, uint32_t c) {
+    unsigned lo = 0, hi = nslots;     // last slot with pre[slot] <= c and non-empty
+    while (hi - lo > 1) { unsigned mid = (lo + hi) >> 1; if (pre[mid] <= c) lo = mid; else hi = mid; }
+    return lo;
+}
+
+// One CTA per query: distances of every candidate (re-rank) + stable top-k.
+__global__ void __launch_bounds__(KNN_NT) k_knn(QArgs A) {
+    __shared__ uint32_t part[KNN_NT + 1];
+    __shared__ unsigned s_n;
+    extern __shared__ unsigned char dyn[];
+    ull* skey = (ull*)dyn;
+    uint32_t* spos = (uint32_t*)(skey + KNN_BUF);
+    uint32_t* sid = spos + KNN_BUF;
+    double* sq = (double*)(sid + KNN_BUF);
+    uint32_t* pre = (uint32_t*)(sq + ((A.d + 3) & ~3));
+    const int64_t q = blockIdx.x;
+    const int tid = threadIdx.x;
+    const unsigned nslots = (unsigned)A.T * A.S;
+    for (int j = tid; j < A.d; j += KNN_NT) sq[j] = A.Q[q * A.d + j];
+    load_slots(A, q, A.T, pre, KNN_NT);
+    slot_prefix<KNN_NT>(pre, nslots, part);
+    const uint32_t C = pre[nslots];
+    const unsigned k = (unsigned)A.k, CHK = KNN_BUF - k;
+    unsigned nbest = 0;
+    for (uint32_t base = 0; base < C; base += CHK) {
+        const unsigned m = min((uint32_t)CHK, C - base);
+        for (unsigned j = tid; j < m; j += KNN_NT) {
+            const uint32_t c = base + j;
+            const unsigned slot = find_slot(pre, nslots, c);
+            const int tt = slot / A.S;
+            const uint32_t g = A.segs[(q * A.T + tt) * (int64_t)A.S + (slot % A.S)];
+            const uint32_t id = A.perm[(int64_t)tt * A.n + A.nstart[g] + (c - pre[slot])];
+            const double dist = dist_exact(A.X + (int64_t)id * A.d, sq, A.d, A.vec);
+            skey[nbest + j] = (ull)__double_as_longlong(dist);
+            spos[nbest + j] = c;
+            sid[nbest + j] = id;
+        }
+        __syncthreads();
+        const unsigned tot = nbest + m;
+        sort3<KNN_NT>(skey, spos, sid, tot);
+        nbest = keep_k<KNN_NT>(skey, spos, sid, tot, k, A.dedup, &s_n);
+        __syncthreads();
+    }
+    for (unsigned i = tid; i < k; i += KNN_NT) {
+        const bool ok = i < nbest;
+        A.dist[q * k + i] = ok ? __longlong_as_double((long long)skey[i]) : __longlong_as_double(0x7ff0000000000000LL);
+        A.ids[q * k + i] = ok ? sid[i] : 0xffffffffu;
+    }
+    if (tid == 0 && A.count) A.count[q] = (int32_t)nbest;
+}
+
+// candidate counts per query (sum of reached leaf sizes over Tq trees)
+__global__ void k_cand_count(QArgs A, int Tq, unsigned long long* out) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= A.nq) return;
+    unsigned long long tot = 0;
+    for (int tt = 0; tt < Tq; ++tt) {
+        const uint32_t c = A.cnt[q * Tq + tt];
+        for (uint32_t j = 0; j < c; ++j) tot += A.nsize[A.segs[(q * Tq + tt) * (int64_t)A.S + j]];
+    }
+    out[q] = tot;
+}
+
+// candidate ids per query in the reference's order (tree-major, leaves left to right, leaf order)
+__global__ void __launch_bounds__(KNN_NT) k_cand_fill(QArgs A, int Tq, int t_only, const int64_t* __restrict__ off, uint32_t* __restrict__ out) {
+    __shared__ uint32_t part[KNN_NT + 1];
+    extern __shared__ unsigned char dyn[];
+    uint32_t* pre = (uint32_t*)dyn;
+    const int64_t q = blockIdx.x;
+    const unsigned nslots = (unsigned)Tq * A.S;
+    load_slots(A, q, Tq, pre, KNN_NT);
+    slot_prefix<KNN_NT>(pre, nslots, part);
+    const uint32_t C = pre[nslots];
+    uint32_t* o = out + off[q];
+    for (uint32_t c = threadIdx.x; c < C; c += KNN_NT) {
+        const unsigned slot = find_slot(pre, nslots, c);
+        const int tt = slot / A.S;
+        const int t = t_only >= 0 ? t_only : tt;
+        const uint32_t g = A.segs[(q * Tq + tt) * (int64_t)A.S + (slot % A.S)];
+        o[c] = A.perm[(int64_t)t * A.n + A.nstart[g] + (c - pre[slot])];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// brute force: all distances for a tile of queries, then exact per-query top-k (ties by row id)
+// ---------------------------------------------------------------------------------------------------
+#define BF_TQ 8
+#define BF_NT 256
+// D[qi][i] = raw bits of dist(X[i], Q[q0+qi]);  thread per point, query tile in shared memory
+__global__ void __launch_bounds__(BF_NT) k_dist_all(const double* __restrict__ X, int64_t n, int d, const double* __restrict__ Q,
+                                                    int64_t q0, int nqt, ull* __restrict__ D, int vec) {
+    extern __shared__ double sqt[];   // [BF_TQ][d]
+    for (int e = threadIdx.x; e < nqt * d; e += BF_NT) sqt[e] = Q[q0 * d + e];
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * BF_NT + threadIdx.x;
+    if (i >= n) return;
+    const double* row = X + i * d;
+    double acc[BF_TQ];
+#pragma unroll
+    for (int qi = 0; qi < BF_TQ; ++qi) acc[qi] = 0.0;
+    if (vec) {
+        for (int j = 0; j < d; j += 4) {
+            double x[4];
+            ld256(row + j, x[0], x[1], x[2], x[3]);
+#pragma unroll
+            for (int qi = 0; qi < BF_TQ; ++qi) {
+                if (qi < nqt) {
+                    const double* s = sqt + qi * d + j;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) { const double df = __dsub_rn(x[u], s[u]); acc[qi] = __dadd_rn(acc[qi], __dmul_rn(df, df)); }
+                }
+            }
+        }
+    } else {
+        for (int j = 0; j < d; ++j) {
+            const double x = __ldg(row + j);
+#pragma unroll
+            for (int qi = 0; qi < BF_TQ; ++qi)
+                if (qi < nqt) { const double df = __dsub_rn(x, sqt[qi * d + j]); acc[qi] = __dadd_rn(acc[qi], __dmul_rn(df, df)); }
+        }
+    }
+#pragma unroll
+    for (int qi = 0; qi < BF_TQ; ++qi)
+        if (qi < nqt) D[(int64_t)qi * n + i] = (ull)__double_as_longlong(__dsqrt_rn(acc[qi]));
+}
+
+// One CTA per query of the tile: k smallest of D[qi][0..n) ordered by (distance, row id)
+__global__ void __launch_bounds__(512) k_select_topk(const ull* __restrict__ D, int64_t n, int k, int64_t q0,
+                                                     double* __restrict__ dist, uint32_t* __restrict__ ids) {
+    __shared__ uint32_t sh[260];
+    __shared__ ull s_pref;
+    __shared__ ull skey[1024];
+    __shared__ uint32_t sidv[1024];
+    __shared__ unsigned s_cnt, s_cnt_eq;
+    const int qi = blockIdx.x, tid = threadIdx.x;
+    const ull* Dq = D + (int64_t)qi * n;
+    const uint32_t kk = (uint32_t)min((int64_t)k, n);
+    // radix select of rank kk-1
+    ull prefix = 0; uint32_t rr = kk - 1;
+    for (int pass = 0; pass < 8; ++pass) {
+        const int shift = 56 - 8 * pass;
+        const ull mask_hi = pass == 0 ? 0ull : (~0ull << (shift + 8));
+        for (int j = tid; j < 256; j += 512) sh[j] = 0;
+        __syncthreads();
+        for (int64_t i = tid; i < n; i += 512) { ull v = Dq[i]; if ((v & mask_hi) == prefix) atomicAdd(&sh[(v >> shift) & 255], 1u); }
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t cum = 0; int dg = 255;
+            for (int b = 0; b < 256; ++b) { if (rr < cum + sh[b]) { dg = b; break; } cum += sh[b]; }
+            sh[256] = cum; s_pref = prefix | ((ull)dg << shift);
+        }
+        __syncthreads();
+        prefix = s_pref; rr -= sh[256];
+        __syncthreads();
+    }
+    const ull kth = prefix;       // rr = rank of the wanted element among the values equal to kth
+    const uint32_t need_eq = rr + 1;
+    if (tid == 0) { s_cnt = 0; s_cnt_eq = 0; }
+    __syncthreads();
+    // everything strictly below kth
+    for (int64_t i = tid; i < n; i += 512) {
+        ull v = Dq[i];
+        if (v < kth) { unsigned p = atomicAdd(&s_cnt, 1u); skey[p] = v; sidv[p] = (uint32_t)i; }
+    }
+    __syncthreads();
+    const unsigned nlt = s_cnt;   // == kk - need_eq
+    // the need_eq smallest row ids among the values equal to kth: ordered scan by one warp (ties are rare)
+    if (tid < 32) {
+        unsigned w = 0;
+        for (int64_t base = 0; base < n && w < need_eq; base += 32) {
+            const int64_t i = base + tid;
+            const bool eq = i < n && Dq[i] == kth;
+            const unsigned bal = __ballot_sync(0xffffffffu, eq);
+            const unsigned dst = w + __popc(bal & ((1u << tid) - 1));
+            if (eq && dst < need_eq) { skey[nlt + dst] = kth; sidv[nlt + dst] = (uint32_t)i; }
+            w += __popc(bal);
+        }
+    }
+    __syncthreads();
+    // order the kk results by (distance, row id)
+    {
+        const unsigned m = kk, Pv = q_next_pow2(m), half = Pv >> 1;
+        for (unsigned kq = 2; kq <= Pv; kq <<= 1) {
+            const int lk = q_ilog2(kq);
+            for (unsigned c = tid; c < half; c += 512) {
+                const unsigned blk = c >> (lk - 1), w = c & ((kq >> 1) - 1);
+                const unsigned i = (blk << lk) + w, p = (blk << lk) + (kq - 1 - w);
+                if (p < m) {
+                    ull a = skey[i], b = skey[p]; uint32_t ia = sidv[i], ib = sidv[p];
+                    if (a > b || (a == b && ia > ib)) { skey[i] = b; skey[p] = a; sidv[i] = ib; sidv[p] = ia; }
+                }
+            }
+            __syncthreads();
+            for (unsigned j = kq >> 2; j > 0; j >>= 1) {
+                const int lj = q_ilog2(j);
+                for (unsigned c = tid; c < half; c += 512) {
+                    const unsigned i = ((c >> lj) << (lj + 1)) + (c & (j - 1)), p = i + j;
+                    if (p < m) {
+                        ull a = skey[i], b = skey[p]; uint32_t ia = sidv[i], ib = sidv[p];
+                        if (a > b || (a == b && ia > ib)) { skey[i] = b; skey[p] = a; sidv[i] = ib; sidv[p] = ia; }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+    }
+    for (unsigned i = tid; i < (unsigned)k; i += 512) {
+        const bool ok = i < kk;
+        dist[(q0 + qi) * k + i] = ok ? __longlong_as_double((long long)skey[i]) : __longlong_as_double(0x7ff0000000000000LL);
+        ids[(q0 + qi) * k + i] = ok ? sidv[i] : 0xffffffffu;
+    }
+}
+
+// recallWith: per query, per tree: |candidates /\ truth| ; recall_sum = fold over trees of hits/k
+__global__ void __launch_bounds__(KNN_NT) k_recall(QArgs A, const uint32_t* __restrict__ truth, double* __restrict__ recall_sum) {
+    __shared__ uint32_t part[KNN_NT + 1];
+    __shared__ uint32_t s_truth[1024];
+    extern __shared__ unsigned char dyn[];
+    uint32_t* pre = (uint32_t*)dyn;
+    uint32_t* hits = pre + (unsigned)A.T * A.S + 1;
+    const int64_t q = blockIdx.x;
+    const int tid = threadIdx.x;
+    const unsigned nslots = (unsigned)A.T * A.S;
+    const unsigned kk = (unsigned)min((int64_t)A.k, A.n);
+    for (unsigned i = tid; i < kk; i += KNN_NT) s_truth[i] = truth[q * A.k + i];
+    for (int t = tid; t < A.T; t += KNN_NT) hits[t] = 0;
+    load_slots(A, q, A.T, pre, KNN_NT);
+    slot_prefix<KNN_NT>(pre, nslots, part);
+    const uint32_t C = pre[nslots];
+    for (uint32_t c = tid; c < C; c += KNN_NT) {
+        const unsigned slot = find_slot(pre, nslots, c);
+        const int tt = slot / A.S;
+        const uint32_t g = A.segs[(q * A.T + tt) * (int64_t)A.S + (slot % A.S)];
+        const uint32_t id = A.perm[(int64_t)tt * A.n + A.nstart[g] + (c - pre[slot])];
+        bool hit = false;
+        for (unsigned i = 0; i < kk; ++i) hit |= (s_truth[i] == id);
+        if (hit) atomicAdd(&hits[tt], 1u);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double s = 0.0;
+        for (int t = 0; t < A.T; ++t) s = s + (double)hits[t] / (double)A.k;   // left fold in tree order
+        recall_sum[q] = s;
+    }
+}
+
+// multi-GPU merge: G rank-major lists of up to k (dist, id) per query -> global top-k by (dist, rank, position)
+__global__ void __launch_bounds__(KNN_NT) k_merge(int G, int64_t nq, int k, int dedup, const double* __restrict__ dist,
+                                                  const uint32_t* __restrict__ ids, const int32_t* __restrict__ count,
+                                                  double* __restrict__ dist_out, uint32_t* __restrict__ ids_out, int32_t* __restrict__ count_out) {
+    extern __shared__ unsigned char dyn[];
+    ull* skey = (ull*)dyn;
+    uint32_t* spos = (uint32_t*)(skey + KNN_BUF);
+    uint32_t* sid = spos + KNN_BUF;
+    __shared__ unsigned s_n;
+    const int64_t q = blockIdx.x;
+    const int tid = threadIdx.x;
+    unsigned nbest = 0;
+    const unsigned per = (KNN_BUF - k) / k;     // ranks per chunk (k <= 1024 -> per >= 3)
+    for (int g0 = 0; g0 < G; g0 += per) {
+        const int g1 = min(G, g0 + (int)per);
+        unsigned m = 0;
+        for (int g = g0; g < g1; ++g) {
+            const unsigned c = (unsigned)count[(int64_t)g * nq + q];
+            for (unsigned j = tid; j < c; j += KNN_NT) {
+                skey[nbest + m + j] = (ull)__double_as_longlong(dist[((int64_t)g * nq + q) * k + j]);
+                spos[nbest + m + j] = (uint32_t)(g * k + j);
+                sid[nbest + m + j] = ids[((int64_t)g * nq + q) * k + j];
+            }
+            m += c;
+        }
+        __syncthreads();
+        const unsigned tot = nbest + m;
+        sort3<KNN_NT>(skey, spos, sid, tot);
+        nbest = keep_k<KNN_NT>(skey, spos, sid, tot, (unsigned)k, dedup, &s_n);
+        __syncthreads();
+    }
+    for (unsigned i = tid; i < (unsigned)k; i += KNN_NT) {
+        const bool ok = i < nbest;
+        dist_out[q * k + i] = ok ? __longlong_as_double((long long)skey[i]) : __longlong_as_double(0x7ff0000000000000LL);
+        ids_out[q * k + i] = ok ? sid[i] : 0xffffffffu;
+    }
+    if (tid == 0 && count_out) count_out[q] = (int32_t)nbest;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+struct QBuf {
+    void* p = nullptr;
+    ~QBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16); }
+    template <typename T> T* as() { return (T*)p; }
+};
+
+// shared front half of every query entry point: upload Q, project, descend (with retry on fork overflow)
+struct QState {
+    QBuf dQ, keysQ, segs, cnt, maxcnt;
+    int S = 2, Tq = 0;
+};
+
+static int run_descent(rpf_handle* h, const double* Q, int64_t nq, int t_only, QState& st) {
+    const int L = h->topo.L_eff, T = h->T;
+    st.Tq = t_only >= 0 ? 1 : T;
+    RPF_CUDA(h, st.dQ.alloc((size_t)nq * h->d * 8));
+    RPF_CUDA(h, cudaMemcpyAsync(st.dQ.p, Q, (size_t)nq * h->d * 8, cudaMemcpyHostToDevice, h->stream));
+    RPF_CUDA(h, st.keysQ.alloc((size_t)std::max(1, T * L) * nq * 8));
+    if (L > 0) { int rc = rpf_project_queries(h, st.dQ.as<double>(), nq, st.keysQ.as<double>()); if (rc) return rc; }
+    RPF_CUDA(h, st.cnt.alloc((size_t)nq * st.Tq * 4));
+    RPF_CUDA(h, st.maxcnt.alloc(4));
+    while (true) {
+        RPF_CUDA(h, st.segs.alloc((size_t)nq * st.Tq * st.S * 4));
+        RPF_CUDA(h, cudaMemsetAsync(st.maxcnt.p, 0, 4, h->stream));
+        const int64_t tot = nq * st.Tq;
+        RPF_LAUNCH(h, PH_Q_TRAVERSE, k_traverse, (unsigned)((tot + 127) / 128), 128, 0, st.keysQ.as<double>(), nq, T, L, h->topo.nnodes(),
+                   h->d_node_child, h->d_node_depth, h->d_thr, h->d_mlo, h->d_mhi, st.S, t_only, st.segs.as<uint32_t>(),
+                   st.cnt.as<uint32_t>(), st.maxcnt.as<uint32_t>());
+        uint32_t mx = 0;
+        RPF_CUDA(h, cudaMemcpyAsync(&mx, st.maxcnt.p, 4, cudaMemcpyDeviceToHost, h->stream));
+        RPF_CUDA(h, cudaStreamSynchronize(h->stream));
+        if (mx <= (uint32_t)st.S) break;
+        cudaFree(st.segs.p); st.segs.p = nullptr;
+        st.S = (int)mx;          // a query forked into more leaves than the stride: redo with the exact maximum
+    }
+    return RPF_OK;
+}
+
+static QArgs make_qargs(rpf_handle* h, int64_t nq, const QState& st) {
+    QArgs A{};
+    A.n = h->n; A.nq = nq; A.nn = h->topo.nnodes(); A.d = h->d; A.T = h->T; A.S = st.S;
+    A.vec = (h->d % 4 == 0) && (((uintptr_t)h->dX & 31) == 0);
+    A.X = h->dX; A.Q = (const double*)st.dQ.p; A.perm = h->d_perm; A.nstart = h->d_node_start; A.nsize = h->d_node_size;
+    A.segs = (const uint32_t*)st.segs.p; A.cnt = (const uint32_t*)st.cnt.p;
+    return A;
+}
+
+int rpf_knn_impl(rpf_handle* h, const double* Q, int64_t nq, int k, int dedup, double* dist, uint32_t* ids, int32_t* count) {
+    if (nq == 0) return RPF_OK;
+    QState st;
+    int rc = run_descent(h, Q, nq, -1, st);
+    if (rc) return rc;
+    QBuf ddist, dids, dcount;
+    RPF_CUDA(h, ddist.alloc((size_t)nq * k * 8));
+    RPF_CUDA(h, dids.alloc((size_t)nq * k * 4));
+    RPF_CUDA(h, dcount.alloc((size_t)nq * 4));
+    QArgs A = make_qargs(h, nq, st);
+    A.k = k; A.dedup = dedup; A.dist = ddist.as<double>(); A.ids = dids.as<uint32_t>(); A.count = dcount.as<int32_t>();
+    const size_t dyn = (size_t)KNN_BUF * 16 + (size_t)((h->d + 3) & ~3) * 8 + ((size_t)h->T * st.S + 1) * 4;
+    if (dyn > 200 * 1024) return rpf_fail(h, RPF_ERR_UNSUPPORTED, "knn: d / tree count too large for the query kernel's shared memory");
+    RPF_CUDA(h, cudaFuncSetAttribute(k_knn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    RPF_LAUNCH(h, PH_Q_KNN, k_knn, (unsigned)nq, KNN_NT, dyn, A);
+    RPF_CUDA(h, cudaMemcpyAsync(dist, ddist.p, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, h->stream));
+    RPF_CUDA(h, cudaMemcpyAsync(ids, dids.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (count) RPF_CUDA(h, cudaMemcpyAsync(count, dcount.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, h->stream));
+    RPF_CUDA(h, cudaStreamSynchronize(h->stream));
+    return RPF_OK;
+}
+
+int rpf_candidates_impl(rpf_handle* h, const double* Q, int64_t nq, int t, int64_t* off_out, const int64_t* off_in, uint32_t* ids) {
+    if (nq == 0) { if (off_out) off_out[0] = 0; return RPF_OK; }
+    QState st;
+    int rc = run_descent(h, Q, nq, t, st);
+    if (rc) return rc;
+    QArgs A = make_qargs(h, nq, st);
+    if (off_out) {
+        QBuf dc;
+        RPF_CUDA(h, dc.alloc((size_t)nq * 8));
+        RPF_LAUNCH(h, PH_Q_CAND, k_cand_count, (unsigned)((nq + 127) / 128), 128, 0, A, st.Tq, dc.as<unsigned long long>());
+        std::vector<unsigned long long> c((size_t)nq);
+        RPF_CUDA(h, cudaMemcpyAsync(c.data(), dc.p, (size_t)nq * 8, cudaMemcpyDeviceToHost, h->stream));
+        RPF_CUDA(h, cudaStreamSynchronize(h->stream));
+        int64_t acc = 0;
+        for (int64_t q = 0; q < nq; ++q) { off_out[q] = acc; acc += (int64_t)c[q]; }
+        off_out[nq] = acc;
+        return RPF_OK;
+    }
+    const int64_t total = off_in[nq];
+    if (total == 0) return RPF_OK;
+    if (!ids) return rpf_fail(h, RPF_ERR_ARG, "candidates: ids is NULL");
+    QBuf doff, dout;
+    RPF_CUDA(h, doff.alloc((size_t)(nq + 1) * 8));
+    RPF_CUDA(h, dout.alloc((size_t)total * 4));
+    RPF_CUDA(h, cudaMemcpyAsync(doff.p, off_in, (size_t)(nq + 1) * 8, cudaMemcpyHostToDevice, h->stream));
+    const size_t dyn = ((size_t)st.Tq * st.S + 1) * 4;
+    RPF_CUDA(h, cudaFuncSetAttribute(k_cand_fill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(dyn, 1024)));
+    RPF_LAUNCH(h, PH_Q_CAND, k_cand_fill, (unsigned)nq, KNN_NT, dyn, A, st.Tq, t, doff.as<int64_t>(), dout.as<uint32_t>());
+    RPF_CUDA(h, cudaMemcpyAsync(ids, dout.p, (size_t)total * 4, cudaMemcpyDeviceToHost, h->stream));
+    RPF_CUDA(h, cudaStreamSynchronize(h->stream));
+    return RPF_OK;
+}
+
+// exact top-k of all n rows for queries dQ[0..nq) -> device arrays d_dist/d_ids (nq x k)
+static int brute_device(rpf_handle* h, const double* dQ, int64_t nq, int k, double* d_dist, uint32_t* d_ids) {
+    const int64_t n = h->n;
+    const int d = h->d;
+    if (n == 0) return rpf_fail(h, RPF_ERR_STATE, "brute_knn: no points");
+    QBuf D;
+    RPF_CUDA(h, D.alloc((size_t)BF_TQ * n * 8));
+    const int vec = (d % 4 == 0) && (((uintptr_t)h->dX & 31) == 0);
+    const size_t smem = (size_t)BF_TQ * d * 8;
+    if (smem > 160 * 1024) return rpf_fail(h, RPF_ERR_UNSUPPORTED, "brute_knn: dimension too large");
+    RPF_CUDA(h, cudaFuncSetAttribute(k_dist_all, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (int64_t q0 = 0; q0 < nq; q0 += BF_TQ) {
+        const int nqt = (int)std::min<int64_t>(BF_TQ, nq - q0);
+        RPF_LAUNCH(h, PH_TRUTH, k_dist_all, (unsigned)((n + BF_NT - 1) / BF_NT), BF_NT, smem, h->dX, n, d, dQ, q0, nqt, D.as<ull>(), vec);
+        RPF_LAUNCH(h, PH_TRUTH, k_select_topk, (unsigned)nqt, 512, 0, D.as<ull>(), n, k, q0, d_dist, d_ids);
+    }
+    RPF_CUDA(h, cudaStreamSynchronize(h->stream));
+    return RPF_OK;
+}
+
+int rpf_brute_knn_impl(rpf_handle* h, const double* Q, int64_t nq, int k, double* dist, uint32_t* ids) {
+    if (nq == 0) return RPF_OK;
+    QBuf dQ, dd, di;
+    RPF_CUDA(h, dQ.alloc((size_t)nq * h->d * 8));
+    RPF_CUDA(h, dd.alloc((size_t)nq * k * 8));
+    RPF_CUDA(h, di.alloc((size_t)nq * k * 4));
+    RPF_CUDA(h, cudaMemcpyAsync(dQ.p, Q, (size_t)nq * h->d * 8, cudaMemcpyHostToDevice, h->stream));
+    int rc = brute_device(h, dQ.as<double>(), nq, k, dd.as<double>(), di.as<uint32_t>());
+    if (rc) return rc;
+    RPF_CUDA(h, cudaMemcpyAsync(dist, dd.p, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, h->stream));
+    RPF_CUDA(h, cudaMemcpyAsync(ids, di.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, h->stream));
+    RPF_CUDA(h, cudaStreamSynchronize(h->stream));
+    return RPF_OK;
+}
+
+int rpf_recall_impl(rpf_handle* h, const double* Q, int64_t nq, int k, double* recall_sum) {
+    if (nq == 0) return RPF_OK;
+    QState st;
+    int rc = run_descent(h, Q, nq, -1, st);
+    if (rc) return rc;
+    QBuf dd, di, dr;
+    RPF_CUDA(h, dd.alloc((size_t)nq * k * 8));
+    RPF_CUDA(h, di.alloc((size_t)nq * k * 4));
+    RPF_CUDA(h, dr.alloc((size_t)nq * 8));
+    rc = brute_device(h, st.dQ.as<double>(), nq, k, dd.as<double>(), di.as<uint32_t>());
+    if (rc) return rc;
+    QArgs A = make_qargs(h, nq, st);
+    A.k = k;
+    const size_t dyn = ((size_t)h->T * st.S + 1) * 4 + (size_t)h->T * 4;
+    RPF_CUDA(h, cudaFuncSetAttribute(k_recall, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(dyn, 1024)));
+    RPF_LAUNCH(h, PH_RECALL, k_recall, (unsigned)nq, KNN_NT, dyn, A, di.as<uint32_t>(), dr.as<double>());
+    RPF_CUDA(h, cudaMemcpyAsync(recall_sum, dr.p, (size_t)nq * 8, cudaMemcpyDeviceToHost, h->stream));
+    RPF_CUDA(h, cudaStreamSynchronize(h->stream));
+    return RPF_OK;
+}
+
+int rpf_merge_impl(rpf_handle* h, int G, int64_t nq, int k, int dedup, const double* dist, const uint32_t* ids,
+                   const int32_t* count, double* dist_out, uint32_t* ids_out, int32_t* count_out) {
+    if (nq == 0) return RPF_OK;
+    QBuf dd, di, dc, od, oi, oc;
+    const size_t ne = (size_t)G * nq * k;
+    RPF_CUDA(h, dd.alloc(ne * 8)); RPF_CUDA(h, di.alloc(ne * 4)); RPF_CUDA(h, dc.alloc((size_t)G * nq * 4));
+    RPF_CUDA(h, od.alloc((size_t)nq * k * 8)); RPF_CUDA(h, oi.alloc((size_t)nq * k * 4)); RPF_CUDA(h, oc.alloc((size_t)nq * 4));
+    RPF_CUDA(h, cudaMemcpyAsync(dd.p, dist, ne * 8, cudaMemcpyHostToDevice, h->stream));
+    RPF_CUDA(h, cudaMemcpyAsync(di.p, ids, ne * 4, cudaMemcpyHostToDevice, h->stream));
+    RPF_CUDA(h, cudaMemcpyAsync(dc.p, count, (size_t)G * nq * 4, cudaMemcpyHostToDevice, h->stream));
+    const size_t dynm = (size_t)KNN_BUF * 16;
+    RPF_CUDA(h, cudaFuncSetAttribute(k_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dynm));
+    RPF_LAUNCH(h, PH_MERGE, k_merge, (unsigned)nq, KNN_NT, dynm, G, nq, k, dedup, dd.as<double>(), di.as<uint32_t>(), dc.as<int32_t>(),
+               od.as<double>(), oi.as<uint32_t>(), oc.as<int32_t>());
+    RPF_CUDA(h, cudaMemcpyAsync(dist_out, od.p, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, h->stream));
+    RPF_CUDA(h, cudaMemcpyAsync(ids_out, oi.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (count_out) RPF_CUDA(h, cudaMemcpyAsync(count_out, oc.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, h->stream));
+    RPF_CUDA(h, cudaStreamSynchronize(h->stream));
+    return RPF_OK;
+}

@@ -1,0 +1,137 @@
+// rpf_internal.h -- engine state shared by the C ABI (capi.cu), the build path (build.cu) and the
+// query path (query.cu).  Not part of the public interface (that is include/rpforest.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/rpforest.h"
+
+// ---- phases (profiling) -----------------------------------------------------------------------------
+enum rpf_phase {
+    PH_PROJECT = 0,     // K1: sparse-hyperplane . dense-row projections of all points (innerSD)
+    PH_TOP_HIST,        // top phase: per-node histogram of keys
+    PH_TOP_PICK,        // top phase: locate the median bin
+    PH_TOP_COMPACT,     // top phase: gather the median bin's keys
+    PH_TOP_FINISH,      // top phase: exact median inside the bin
+    PH_TOP_TIES,        // top phase: lexicographic tie resolution (rare)
+    PH_TOP_RELABEL,     // top phase: relabel / scatter points to children
+    PH_BOTTOM,          // bottom phase: whole subtrees in shared memory
+    PH_Q_PROJECT,       // query projections
+    PH_Q_TRAVERSE,      // candidates descent
+    PH_Q_KNN,           // leaf re-rank + top-k
+    PH_Q_CAND,          // candidates materialisation
+    PH_TRUTH,           // brute-force top-k
+    PH_RECALL,          // candidate-set /\ truth
+    PH_MERGE,           // multi-GPU top-k merge
+    PH_MISC,            // memsets, setup kernels
+    PH_COUNT
+};
+
+// ---- data-independent tree topology (pure function of n, minLeaf, maxDepth) ---------------------------
+// Internal.hs:289 (leaf iff lev >= maxDepth || size <= minLeaf), :495,:503 (left = n div 2, right = rest).
+struct Topology {
+    int64_t n = 0;
+    int maxDepth = 0, minLeaf = 0;
+    int nlevels = 0;                    // depths 0 .. nlevels-1 hold at least one node
+    int L_eff = 0;                      // depths 0 .. L_eff-1 hold at least one internal node (need projections)
+    std::vector<uint32_t> start, size;  // per node (BFS id)
+    std::vector<int32_t> child;         // left child BFS id or -1
+    std::vector<int32_t> depth;
+    std::vector<int64_t> level_off;     // nlevels+1
+    std::vector<uint32_t> lvl_maxsize;  // per level
+    int64_t nnodes() const { return (int64_t)start.size(); }
+};
+void build_topology(Topology& tp, int64_t n, int maxDepth, int minLeaf);
+
+struct ProfEvent { int phase; cudaEvent_t a, b; };
+
+struct rpf_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+
+    // points
+    int64_t n = 0; int d = 0;
+    const double* dX = nullptr; bool ownX = false;
+
+    // hyperplanes: CSR over (tree, level); host copy + device copy
+    int T = 0, hpDepth = 0;
+    std::vector<int64_t> hp_off; std::vector<int32_t> hp_idx; std::vector<double> hp_val;
+    int64_t* d_hp_off = nullptr; int32_t* d_hp_idx = nullptr; double* d_hp_val = nullptr;
+
+    // topology
+    Topology topo;
+    uint32_t* d_node_start = nullptr; uint32_t* d_node_size = nullptr; int32_t* d_node_child = nullptr; int32_t* d_node_depth = nullptr;
+
+    // forest
+    bool built = false;
+    double *d_thr = nullptr, *d_mlo = nullptr, *d_mhi = nullptr;   // [T][nnodes]
+    uint32_t* d_perm = nullptr;                                       // [T][n]
+    bool leaf_order_exact = true;
+
+    // tuning
+    int bottom_cap = 4096;
+
+    // measurement
+    bool profiling = false;
+    double last_ms = 0.0;
+    double phase_ms[PH_COUNT] = {0};
+    int64_t phase_launches[PH_COUNT] = {0};
+    int64_t launches = 0;
+    std::vector<ProfEvent> pending;
+    std::vector<cudaEvent_t> event_pool;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+
+    void prof_reset();
+    void prof_begin(int phase);
+    void prof_end(int phase);
+    void call_begin();
+    int  call_end();    // syncs the stream, accumulates timings; returns RPF_OK or error
+};
+
+int rpf_fail(rpf_handle* h, int code, const std::string& msg);
+
+#define RPF_CUDA(h, expr)                                                                              \
+    do {                                                                                               \
+        cudaError_t _e = (expr);                                                                       \
+        if (_e != cudaSuccess)                                                                         \
+            return rpf_fail((h), RPF_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));    \
+    } while (0)
+
+// Launch wrapper: counts launches, brackets with profiling events when enabled.
+#define RPF_LAUNCH(h, phase, kern, grid, block, smem, ...)                                             \
+    do {                                                                                               \
+        (h)->prof_begin(phase);                                                                        \
+        kern<<<(grid), (block), (smem), (h)->stream>>>(__VA_ARGS__);                                   \
+        (h)->prof_end(phase);                                                                          \
+        cudaError_t _e = cudaGetLastError();                                                           \
+        if (_e != cudaSuccess)                                                                         \
+            return rpf_fail((h), RPF_ERR_CUDA, std::string(#kern) + " launch: " + cudaGetErrorString(_e)); \
+    } while (0)
+
+// implemented in build.cu / query.cu
+int rpf_build_impl(rpf_handle* h);
+int rpf_project_queries(rpf_handle* h, const double* dQ, int64_t nq, double* d_keysQ);
+int rpf_knn_impl(rpf_handle* h, const double* Q, int64_t nq, int k, int dedup, double* dist, uint32_t* ids, int32_t* count);
+int rpf_candidates_impl(rpf_handle* h, const double* Q, int64_t nq, int t, int64_t* off_out, const int64_t* off_in, uint32_t* ids);
+int rpf_recall_impl(rpf_handle* h, const double* Q, int64_t nq, int k, double* recall_sum);
+int rpf_brute_knn_impl(rpf_handle* h, const double* Q, int64_t nq, int k, double* dist, uint32_t* ids);
+int rpf_merge_impl(rpf_handle* h, int G, int64_t nq, int k, int dedup, const double* dist, const uint32_t* ids,
+                   const int32_t* count, double* dist_out, uint32_t* ids_out, int32_t* count_out);
+
+// ---- device helpers ---------------------------------------------------------------------------------
+#ifdef __CUDACC__
+// order-preserving map double -> uint64 (total order == IEEE order on non-NaN; -0 canonicalised to +0)
+__device__ __forceinline__ uint64_t f2ord(double x) {
+    uint64_t b = (uint64_t)__double_as_longlong(x);
+    if (x == 0.0) b = 0ull;
+    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double ord2f(uint64_t o) {
+    uint64_t b = (o & 0x8000000000000000ull) ? (o & 0x7fffffffffffffffull) : ~o;
+    return __longlong_as_double((long long)b);
+}
+#define ORD_NONE_LO 0ull                       /* below every finite key */
+#define ORD_NONE_HI 0xffffffffffffffffull      /* above every finite key */
+#endif

@@ -1,0 +1,75 @@
+"""CPU tests of the product library's host-side logic: the .so loads, exports every symbol the header declares,
+and its host-only entry points (sampler, topology, rpTreeCfg) agree with the oracle.  No compute calls."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(built):
+    import rp_tree_b200 as R
+    L = R.lib()
+    hdr = open(os.path.join(ROOT, "include", "rpforest.h")).read()
+    declared = set(re.findall(r"\b(rpf_[a-z0-9_]+)\s*\(", hdr)) - {"rpf_status"}
+    assert len(declared) >= 30
+    for name in sorted(declared):
+        assert hasattr(L, name), "librpforest.so does not export " + name
+    assert declared == set(R.SIGNATURES), declared ^ set(R.SIGNATURES)
+    assert L.rpf_abi_version() == 1
+
+
+def test_no_cpu_fallback(built):
+    """Without a CUDA device the engine refuses to come up (it must never route through the oracle)."""
+    import torch
+    import rp_tree_b200 as R
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(R.RPForestError):
+        R.RPForest(0)
+    src = "".join(open(os.path.join(ROOT, "rp-tree_b200", f)).read() for f in ("api.py", "_lib.py", "__init__.py", "dist.py"))
+    assert "oracle" not in src.replace("no CPU fallback", "")
+
+
+def test_sampler_matches_oracle_restatement(built):
+    import rp_tree_b200 as R
+    from oracle import orc
+    for seed, T, maxd, pnz, d in [(1235137, 4, 6, 0.3, 16), (42, 2, 14, 0.1, 128), (7, 3, 5, 1.0, 2), (9, 2, 3, 0.0, 10)]:
+        a = R.sampleHyperplanes(seed, T, maxd, pnz, d)
+        b = orc.gen_hyperplanes(seed, T, maxd, pnz, d)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+        assert np.array_equal(a[2].view(np.uint64), b[2].view(np.uint64))
+
+
+def test_rptree_cfg_matches(built):
+    import rp_tree_b200 as R
+    from oracle import orc
+    for minl, n, d in [(20, 10000, 2), (64, 1000000, 128), (10, 1000, 1000), (64, 10**7, 96)]:
+        assert tuple(R.rpTreeCfg(minl, n, d)) == orc.rptree_cfg(minl, n, d)
+
+
+@pytest.mark.parametrize("n,maxd,minl", [(10000, 9, 20), (1000, 6, 10), (777, 20, 0), (3000, 12, 1), (1, 3, 0), (0, 3, 1),
+                                         (5, 2, 1), (100003, 14, 64), (4096, 30, 3)])
+def test_topology_plan_matches_oracle_tree_shape(built, n, maxd, minl):
+    """The engine's arithmetic topology == the shape the oracle's recursion actually produces on data."""
+    import rp_tree_b200 as R
+    from oracle import orc
+    d = 3
+    X = np.random.default_rng(n + maxd).normal(size=(max(n, 1), d))[:n].reshape(n, d)
+    hp = orc.gen_hyperplanes(1, 1, maxd, 1.0, d)
+    e = orc.Forest(X, hp, 1, maxd, minl).export(0)
+    tp = R.topologyPlan(n, maxd, minl)
+    for k in ("child", "depth", "seg_start", "seg_size"):
+        assert np.array_equal(tp[k], e[k]), k
+
+
+def test_slice_hyperplanes(built):
+    import rp_tree_b200 as R
+    hp = R.sampleHyperplanes(3, 8, 5, 0.4, 20)
+    parts = [R.slice_hyperplanes(hp, 5, g * 2, 2) for g in range(4)]
+    assert sum(len(p[1]) for p in parts) == len(hp[1])
+    assert np.array_equal(np.concatenate([p[2] for p in parts]), hp[2])
+    for p in parts:
+        assert p[0][0] == 0 and len(p[0]) == 11 and p[0][-1] == len(p[1])

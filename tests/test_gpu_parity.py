@@ -1,0 +1,222 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Bar: thresholds / margins bit-exact (uint64 view of the doubles), leaf sets AND leaf order identical,
+candidate id lists identical, knn ids identical and distances bit-exact, recall identical up to fp summation.
+"""
+import numpy as np
+import pytest
+
+from helpers import make_data, compare_tree, bits
+
+pytestmark = pytest.mark.gpu
+
+
+def _mods():
+    import rp_tree_b200 as R
+    from oracle import orc
+    return R, orc
+
+
+def _build_pair(n, d, T, maxd, minl, pnz, kind="gauss", cap=None, seed=3):
+    R, orc = _mods()
+    X = make_data(n, d, seed, kind)
+    hp = orc.gen_hyperplanes(1235137 + seed, T, maxd, pnz, d)
+    f = R.forestBatch(0, maxd, minl, T, pnz, d, X, hyperplanes=hp, bottom_cap=cap)
+    of = orc.Forest(X, hp, T, maxd, minl)
+    return X, hp, f, of
+
+
+BUILD_CASES = [
+    # n, d, T, maxd, minl, pnz, kind, cap
+    pytest.param(1000, 8, 3, 6, 10, 0.5, "gauss", None, id="bottom-only"),
+    pytest.param(10000, 16, 4, 9, 20, 0.3, "gauss", 1024, id="top4-bottom"),
+    pytest.param(10000, 2, 10, 9, 20, 1.0, "gauss", None, id="reference-test-shape"),
+    pytest.param(20000, 32, 3, 11, 16, 0.3, "mixture", 256, id="top7-cap256"),
+    pytest.param(5000, 2, 6, 8, 10, 0.5, "gauss", 256, id="empty-hyperplanes-ties"),
+    pytest.param(6000, 6, 4, 9, 8, 0.5, "integer", 256, id="integer-data-massive-ties"),
+    pytest.param(4000, 5, 3, 9, 7, 0.6, "dupes", 256, id="duplicate-rows"),
+    pytest.param(3000, 4, 3, 12, 1, 0.7, "gauss", 256, id="minleaf1-deep"),
+    pytest.param(777, 3, 2, 20, 0, 1.0, "gauss", 256, id="minleaf0-maxdepth20"),
+    pytest.param(9000, 12, 2, 3, 5, 0.4, "gauss", 1024, id="shallow-big-leaves"),
+    pytest.param(40000, 24, 2, 12, 12, 0.25, "mixture", 4096, id="cap4096-top4"),
+    pytest.param(70000, 8, 2, 13, 10, 0.5, "gauss", 8192, id="cap8192-top4"),
+]
+
+
+@pytest.mark.parametrize("n,d,T,maxd,minl,pnz,kind,cap", BUILD_CASES)
+def test_build_parity(built, n, d, T, maxd, minl, pnz, kind, cap):
+    X, hp, f, of = _build_pair(n, d, T, maxd, minl, pnz, kind, cap)
+    order = f.leafOrderExact()
+    problems = []
+    for t in range(T):
+        bad = compare_tree(f.treeExport(t), of.export(t), check_order=order)
+        problems += ["tree %d: %s" % (t, b) for b in bad]
+    assert not problems, "\n".join(problems[:20])
+    if kind == "gauss" and minl >= 5 and maxd >= 6:
+        assert order
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 4, 5])
+def test_tiny_inputs(built, n):
+    R, orc = _mods()
+    d, T, maxd = 3, 2, 4
+    X = make_data(max(n, 1), d, 11)[:n].reshape(n, d)
+    hp = orc.gen_hyperplanes(5, T, maxd, 1.0, d)
+    for minl in (0, 1, 2):
+        f = R.forestBatch(0, maxd, minl, T, 1.0, d, X, hyperplanes=hp)
+        of = orc.Forest(X, hp, T, maxd, minl)
+        for t in range(T):
+            bad = compare_tree(f.treeExport(t), of.export(t))
+            assert not bad, "n=%d minl=%d tree %d: %s" % (n, minl, t, bad)
+
+
+def test_all_points_in_every_tree(built):
+    """The reference's own invariant (test/Data/RPTreeSpec.hs:67-68): treeSize t == n for every tree."""
+    R, orc = _mods()
+    n, d, T, minl = 10000, 2, 10, 20
+    X = make_data(n, d, 1)
+    cfg = R.rpTreeCfg(minl, n, d)
+    f = R.forestBatch(42, cfg.fpMaxTreeDepth, minl, T, 1.0, d, X)     # built-in sampler
+    assert R.treeSize(f) == n
+    for t in range(T):
+        assert np.array_equal(np.sort(R.points(f, t)), np.arange(n, dtype=np.uint32))
+    # knn of the origin is close (RPTreeSpec.hs:69-74 checks < 1 on its 2-cluster data; here: finds the true 1-NN region)
+    dist, ids = R.knn(R.metricL2, 5, f, np.zeros(d))
+    assert len(dist) == 5 and np.all(np.diff(dist) >= 0)
+
+
+def test_projection_matches_oracle_fold_order(built):
+    """thresholds are projections of data points: bit equality of thr already pins innerSD's right fold; this
+    checks a level-0 threshold explicitly against the oracle's inner_sd of the median point."""
+    R, orc = _mods()
+    n, d = 2001, 64
+    X = make_data(n, d, 5) * 1e3
+    hp = orc.gen_hyperplanes(9, 1, 1, 0.9, d)
+    f = R.forestBatch(0, 1, 10, 1, 0.9, d, X, hyperplanes=hp)
+    e = f.treeExport(0)
+    keys = np.array([orc.inner_sd(hp[1], hp[2], X[i]) for i in range(n)])
+    ks = np.sort(keys, kind="stable")
+    assert bits(e["thr"])[0] == bits(ks[n // 2 : n // 2 + 1])[0]
+    assert bits(e["mlo"])[0] == bits(ks[n // 2 - 1 : n // 2])[0]
+    assert bits(e["mhi"])[0] == bits(ks[n // 2 + 1 : n // 2 + 2])[0]
+
+
+QUERY_CASES = [
+    pytest.param(10000, 16, 4, 9, 20, 0.3, "gauss", 1024, id="gauss"),
+    pytest.param(20000, 32, 6, 10, 16, 0.3, "mixture", None, id="mixture"),
+    pytest.param(4000, 5, 3, 9, 7, 0.6, "dupes", 256, id="dupes"),
+    pytest.param(3000, 3, 8, 8, 10, 0.7, "integer", 256, id="integer"),
+]
+
+
+@pytest.mark.parametrize("n,d,T,maxd,minl,pnz,kind,cap", QUERY_CASES)
+def test_candidates_knn_recall_parity(built, n, d, T, maxd, minl, pnz, kind, cap):
+    R, orc = _mods()
+    X, hp, f, of = _build_pair(n, d, T, maxd, minl, pnz, kind, cap)
+    rng = np.random.default_rng(17)
+    nq = 40
+    Q = X[rng.integers(0, n, size=nq)] + (0.05 * rng.normal(size=(nq, d)) if kind != "integer" else 0.0)
+    Q[0] = X[0]                       # an exact data point (distance 0, proj == some key)
+    order = f.leafOrderExact()
+    # candidates, per tree and concatenated
+    for t in list(range(T)) + [-1]:
+        off, ids = f.candidatesBatch(Q, t)
+        for i in range(nq):
+            got = ids[off[i]:off[i + 1]]
+            exp = of.candidates(t, Q[i]) if t >= 0 else np.concatenate([of.candidates(tt, Q[i]) for tt in range(T)])
+            if order:
+                assert np.array_equal(got, exp), "candidates differ: tree %d query %d" % (t, i)
+            else:
+                assert np.array_equal(np.sort(got), np.sort(exp)), "candidate sets differ: tree %d query %d" % (t, i)
+    # knn and knnPQ
+    for dedup in (False, True):
+        for k in (1, 10, 37):
+            dist, ids, cnt = f.knnBatch(Q, k, dedup=dedup)
+            for i in range(nq):
+                od, oi = of.knn(Q[i], k, dedup=dedup)
+                assert cnt[i] == len(od), "count: dedup=%s k=%d q=%d: %d vs %d" % (dedup, k, i, cnt[i], len(od))
+                assert np.array_equal(bits(dist[i, :cnt[i]]), bits(od)), "distances: dedup=%s k=%d q=%d" % (dedup, k, i)
+                if order or kind in ("gauss", "mixture"):
+                    assert np.array_equal(ids[i, :cnt[i]], oi), "ids: dedup=%s k=%d q=%d" % (dedup, k, i)
+    # recallWith
+    r = R.recallWith(R.metricL2, f, 10, Q)
+    if kind in ("gauss", "mixture"):        # row identity == vector identity (no duplicate rows)
+        ro = np.array([of.recall(Q[i], 10) for i in range(nq)])
+        assert np.allclose(r, ro, rtol=0, atol=1e-12), (r, ro)
+    # brute force
+    bd, bi = f.bruteKnnBatch(Q[:8], 10)
+    for i in range(8):
+        od, oi = orc.brute_knn(X, Q[i], 10)
+        assert np.array_equal(bits(bd[i]), bits(od)) and np.array_equal(bi[i], oi)
+
+
+def test_fork_heavy_queries(built):
+    """Queries sitting exactly between threshold and margin force `candidates` to take both branches."""
+    R, orc = _mods()
+    X, hp, f, of = _build_pair(2000, 2, 3, 7, 10, 1.0, "gauss", 256)
+    Q = []
+    for t in range(3):
+        e = of.export(t)
+        # build queries whose projection on level 0 lies just beside the root threshold
+        h0 = (hp[1][hp[0][t * 7]:hp[0][t * 7 + 1]], hp[2][hp[0][t * 7]:hp[0][t * 7 + 1]])
+        v = np.zeros(2); v[h0[0]] = h0[1]
+        for target in (np.nextafter(e["thr"][0], -np.inf), np.nextafter(e["thr"][0], np.inf), e["thr"][0],
+                       0.5 * (e["thr"][0] + e["mlo"][0]), 0.5 * (e["thr"][0] + e["mhi"][0])):
+            Q.append(v * (target / np.dot(v, v)))
+    Q = np.array(Q)
+    off, ids = f.candidatesBatch(Q, -1)
+    for i in range(len(Q)):
+        exp = np.concatenate([of.candidates(t, Q[i]) for t in range(3)])
+        assert np.array_equal(ids[off[i]:off[i + 1]], exp)
+    dist, idk, cnt = f.knnBatch(Q, 5)
+    for i in range(len(Q)):
+        od, oi = of.knn(Q[i], 5)
+        assert np.array_equal(idk[i, :cnt[i]], oi)
+
+
+def test_merge_topk_equals_single_forest(built):
+    """Tree-sharded build on one device emulating G ranks: merged per-shard top-k == whole-forest top-k."""
+    R, orc = _mods()
+    n, d, T, maxd, minl, pnz = 8000, 12, 8, 9, 12, 0.4
+    X = make_data(n, d, 2, "mixture")
+    hp = orc.gen_hyperplanes(77, T, maxd, pnz, d)
+    whole = R.forestBatch(0, maxd, minl, T, pnz, d, X, hyperplanes=hp)
+    Q = X[:32] + 0.01
+    for dedup in (False, True):
+        wd, wi, wc = whole.knnBatch(Q, 10, dedup=dedup)
+        for G in (2, 4):
+            per = T // G
+            ds, is_, cs = [], [], []
+            for g in range(G):
+                sh = R.forestBatch(0, maxd, minl, T, pnz, d, X, hyperplanes=hp, t_first=g * per, t_local=per)
+                a, b, c = sh.knnBatch(Q, 10, dedup=dedup)
+                ds.append(a); is_.append(b); cs.append(c)
+            md, mi, mc = whole.mergeTopk(np.stack(ds), np.stack(is_), np.stack(cs), dedup=dedup)
+            assert np.array_equal(mc, wc)
+            assert np.array_equal(bits(md), bits(wd)) and np.array_equal(mi, wi)
+
+
+def test_chunked_single_chunk_equals_batch_and_multi_chunk_unsupported(built):
+    R, orc = _mods()
+    n, d, T, maxd, minl = 3000, 6, 2, 7, 10
+    X = make_data(n, d, 8)
+    hp = orc.gen_hyperplanes(3, T, maxd, 0.5, d)
+    f = R.forest(0, maxd, minl, T, n, 0.5, d, X, hyperplanes=hp)
+    of = orc.Forest(X, hp, T, maxd, minl, chunk=n)
+    for t in range(T):
+        assert not compare_tree(f.treeExport(t), of.export(t))
+    with pytest.raises(R.RPForestError):
+        R.forest(0, maxd, minl, T, 100, 0.5, d, X, hyperplanes=hp)
+
+
+def test_profile_and_launch_count(built):
+    R, orc = _mods()
+    X = make_data(30000, 16, 4)
+    f = R.RPForest(0)
+    f.setProfiling(True)
+    f.setPoints(X)
+    f.genHyperplanes(1, 4, 11, 0.3, 16)
+    f.build(11, 16)
+    prof = f.profile()
+    assert prof["project"][1] >= 1 and prof["bottom"][1] >= 1
+    assert f.lastDeviceMs() > 0 and f.launchCount() > 0
