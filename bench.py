@@ -1,0 +1,398 @@
+#!/usr/bin/env python
+"""bench.py -- forest-build points/s (+ kNN queries/s, recall@10) on BASELINE.json configs[1]:
+synthetic SIFT-like 1M x 128 fp64, 32-tree forest, pnz = 0.1, 10k queries, k = 10.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one pass of the hot path over the batch: build the whole forest (points already resident in HBM)
+and answer the whole query batch.  `value` = points/s of the forest build (device time, CUDA events on the
+engine's stream, max over ranks); knn throughput and recall ride along as extra keys.  `e2e` = the same through
+the public API with HOST buffers (pinned), H2D of the points and D2H of the forest inside the timed region.
+For N > 1 (launched by torchrun) the 32 trees are sharded in contiguous blocks over the ranks, the data is
+replicated, and the per-rank top-k lists are all-gathered over NCCL and merged by the engine's merge kernel.
+`--impl reference` times the reference's CPU algorithm (the oracle port: no GHC in this image) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(name="configs[1]: synthetic SIFT-like 1Mx128 fp64, 32 trees, pnz 0.1, 10k queries k=10",
+                n=1_000_000, d=128, ntrees=32, pnz=0.1, min_leaf=64, nq=10_000, k=10,
+                data_seed=1234, query_seed=4321, forest_seed=1235137, clusters=256, sigma=0.25)
+
+
+def make_points(n, d, seed, clusters, sigma, center_seed=99):
+    """Clustered Gaussian mixture: centres ~ N(0,1)^d, points = centre + N(0, sigma^2)^d."""
+    cen = np.random.default_rng(center_seed).normal(size=(clusters, d))
+    rng = np.random.default_rng(seed)
+    X = rng.normal(size=(n, d))
+    X *= sigma
+    X += cen[rng.integers(0, clusters, size=n)]
+    return X
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.idx = gpu_index
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.p:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=2)
+        except Exception:
+            self.p.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=sorted(reasons),
+                    samples=len(sm))
+
+
+def algorithmic_bytes(W, tlocal, L, s_top, C_mean):
+    """Algorithmic HBM bytes per launch for every kernel class."""
+    n, d = W["n"], W["d"]
+    return {
+        "project": 8 * d * n + 8 * tlocal * L * n,                     # read X once, write every (tree, level) key
+        "top_hist": tlocal * n * (8 + 2),                              # key + label
+        "top_compact": tlocal * n * (8 + 2),
+        "top_relabel": tlocal * n * (8 + 2 + 2),                       # + label write
+        "bottom": tlocal * n * (4 + 4 + 8 * (L - s_top) + (8 if s_top > 0 else 0)),   # perm r/w + one key per bottom level
+        "q_knn": W["nq"] * (C_mean * (8 * d + 4) + 8 * d + 12 * W["k"]),
+    }
+
+
+def run_ours(args):
+    import torch
+    import rp_tree_b200 as R
+
+    W = WORKLOAD
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun for --gpus > 1")
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+
+    n, d, T, k, nq = W["n"], W["d"], W["ntrees"], W["k"], W["nq"]
+    cfg = R.rpTreeCfg(W["min_leaf"], n, d)
+    maxd = cfg.fpMaxTreeDepth
+    per = (T + world - 1) // world
+    t_first = min(rank * per, T)
+    t_local = max(0, min(T, t_first + per) - t_first)
+    assert t_local > 0, "more ranks than trees"
+
+    # synthetic inputs in PINNED host memory (so the e2e H2D is a real DMA)
+    Xp = torch.empty((n, d), dtype=torch.float64, pin_memory=True)
+    X = Xp.numpy()
+    X[:] = make_points(n, d, W["data_seed"], W["clusters"], W["sigma"])
+    Qp = torch.empty((nq, d), dtype=torch.float64, pin_memory=True)
+    Q = Qp.numpy()
+    Q[:] = make_points(nq, d, W["query_seed"], W["clusters"], W["sigma"])
+    hp_all = R.sampleHyperplanes(W["forest_seed"], T, maxd, W["pnz"], d)
+    hp = R.slice_hyperplanes(hp_all, maxd, t_first, t_local)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def allmax(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    f = R.RPForest(local_rank)
+    f.setHyperplanes(hp, t_local, maxd)
+    f.setPoints(X)                      # resident in HBM before the timed region (the `value` arm)
+    merger = f
+
+    def knn_step():
+        """local knn over this rank's trees -> NCCL all-gather -> merge kernel.  Returns device ms + merged result."""
+        dd, ii, cc = f.knnBatch(Q, k, dedup=False)
+        ms = f.lastDeviceMs()
+        if dist is None:
+            return ms, (dd, ii, cc), 0.0
+        t0 = time.perf_counter()
+        gd = [torch.empty((nq, k), dtype=torch.float64, device=dev) for _ in range(world)]
+        gi = [torch.empty((nq, k), dtype=torch.int32, device=dev) for _ in range(world)]
+        gc = [torch.empty((nq,), dtype=torch.int32, device=dev) for _ in range(world)]
+        dist.all_gather(gd, torch.from_numpy(dd).to(dev))
+        dist.all_gather(gi, torch.from_numpy(ii.view(np.int32)).to(dev))
+        dist.all_gather(gc, torch.from_numpy(cc).to(dev))
+        D = torch.stack(gd).cpu().numpy(); I = torch.stack(gi).cpu().numpy().view(np.uint32); Cn = torch.stack(gc).cpu().numpy()
+        out = merger.mergeTopk(D, I, Cn, dedup=False)
+        ms += merger.lastDeviceMs()
+        return ms, out, (time.perf_counter() - t0) * 1e3
+
+    # ---- warm-up
+    for _ in range(args.warmup):
+        f.build(maxd, W["min_leaf"])
+        knn_step()
+
+    # ---- timed: device-resident arm
+    lc0 = f.launchCount()
+    cs = ClockSampler(local_rank)
+    cs.start()
+    barrier()
+    b_ms, q_ms = [], []
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        f.build(maxd, W["min_leaf"])
+        b_ms.append(f.lastDeviceMs())
+        ms, merged, _ = knn_step()
+        q_ms.append(ms)
+    barrier()
+    wall_ms = (time.perf_counter() - t_wall0) * 1e3 / args.steps
+    clocks = cs.stop()
+    launches = f.launchCount() - lc0
+    build_ms = allmax(float(np.mean(b_ms)))
+    knn_ms = allmax(float(np.mean(q_ms)))
+
+    # ---- timed: e2e arm (host buffers through the public API, H2D + D2H inside)
+    e2e_b, e2e_q = [], []
+    nn = None
+    barrier()
+    for _ in range(max(1, min(args.steps, 3))):
+        barrier()
+        t0 = time.perf_counter()
+        g = R.RPForest(local_rank)
+        g.setHyperplanes(hp, t_local, maxd)
+        g.setPoints(X)                                           # H2D n*d*8
+        g.build(maxd, W["min_leaf"])
+        exp = [g.treeExport(t) for t in range(t_local)]          # D2H: thr/mlo/mhi + perm of every local tree
+        nn = len(exp[0]["thr"])
+        barrier()
+        e2e_b.append(time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        dd, ii, cc = g.knnBatch(Q, k)                            # H2D queries, D2H results
+        if dist is not None:
+            gd = [torch.empty((nq, k), dtype=torch.float64, device=dev) for _ in range(world)]
+            gi = [torch.empty((nq, k), dtype=torch.int32, device=dev) for _ in range(world)]
+            gc = [torch.empty((nq,), dtype=torch.int32, device=dev) for _ in range(world)]
+            dist.all_gather(gd, torch.from_numpy(dd).to(dev)); dist.all_gather(gi, torch.from_numpy(ii.view(np.int32)).to(dev))
+            dist.all_gather(gc, torch.from_numpy(cc).to(dev))
+            g.mergeTopk(torch.stack(gd).cpu().numpy(), torch.stack(gi).cpu().numpy().view(np.uint32), torch.stack(gc).cpu().numpy())
+        barrier()
+        e2e_q.append(time.perf_counter() - t0)
+        g.close()
+    e2e_build_s = allmax(float(np.mean(e2e_b)))
+    e2e_knn_s = allmax(float(np.mean(e2e_q)))
+
+    # ---- per-kernel profile (separate pass: event pairs around every launch) -> roofline of the dominant kernel
+    f.setProfiling(True)
+    f.build(maxd, W["min_leaf"])
+    prof = f.profile()
+    f.knnBatch(Q, k)
+    prof_q = f.profile()
+    f.setProfiling(False)
+    for name in ("q_project", "q_traverse", "q_knn"):
+        prof[name] = prof_q[name]
+    off, _ = f.candidatesBatch(Q[:512], -1)
+    C_mean = float(off[-1]) / 512.0
+    tp = f.topology()
+    L = int(tp["depth"][tp["child"] >= 0].max()) + 1
+    cap = 4096
+    lvl_max = [int(tp["seg_size"][tp["depth"] == l].max()) for l in range(int(tp["depth"].max()) + 1)]
+    s_top = next((l for l, m in enumerate(lvl_max) if m <= cap), len(lvl_max))
+    s_top = min(s_top, L)
+    ab = algorithmic_bytes(W, t_local, L, s_top, C_mean)
+    peak, peak_src = peaks()
+    kern = {kname: v for kname, v in prof.items() if v[1] > 0 and kname in ab}
+    dom = max(kern, key=lambda kname: kern[kname][0])
+    dom_ms, dom_launches = kern[dom]
+    # top_* entries are bytes per level launch (every launch streams all local trees' points once); the others are
+    # bytes per step, issued in dom_launches launches (one per tree group)
+    per_launch_bytes = ab[dom] if dom.startswith("top_") else ab[dom] / dom_launches
+    avg_ms = dom_ms / dom_launches
+    achieved = per_launch_bytes / (avg_ms * 1e-3) / 1e9
+    roofline = dict(bound="hbm", kernel=dom, achieved=round(achieved, 1), peak=peak, unit="GB/s", frac=round(achieved / peak, 4),
+                    traffic=None, peak_source=peak_src, launches_per_step=dom_launches, avg_launch_ms=round(avg_ms, 4),
+                    algorithmic_bytes_per_launch=int(per_launch_bytes))
+    build_bytes = 8 * d * n + t_local * L * n * 24
+    knn_bytes = ab["q_knn"]
+    phases = {kname: dict(ms=round(v[0], 3), launches=v[1]) for kname, v in prof.items() if v[1] > 0}
+
+    # ---- quality: recallWith (reference definition) and forest-level recall@10 on a query sample (untimed)
+    ns = 64
+    rs = f.recallSumBatch(Q[:ns], k)
+    if dist is not None:
+        t = torch.from_numpy(rs).to(dev)
+        dist.all_reduce(t)
+        rs = t.cpu().numpy()
+    recall_ref_def = float(np.mean(rs / T))
+    bd, bi = f.bruteKnnBatch(Q[:ns], k)
+    if dist is None:
+        pd_, pi_, pc_ = f.knnBatch(Q[:ns], k, dedup=True)
+    else:
+        pd_, pi_, pc_ = f.knnBatch(Q[:ns], k, dedup=True)
+        gd = [torch.empty((ns, k), dtype=torch.float64, device=dev) for _ in range(world)]
+        gi = [torch.empty((ns, k), dtype=torch.int32, device=dev) for _ in range(world)]
+        gc = [torch.empty((ns,), dtype=torch.int32, device=dev) for _ in range(world)]
+        dist.all_gather(gd, torch.from_numpy(pd_).to(dev)); dist.all_gather(gi, torch.from_numpy(pi_.view(np.int32)).to(dev))
+        dist.all_gather(gc, torch.from_numpy(pc_).to(dev))
+        pd_, pi_, pc_ = f.mergeTopk(torch.stack(gd).cpu().numpy(), torch.stack(gi).cpu().numpy().view(np.uint32), torch.stack(gc).cpu().numpy(), dedup=True)
+    forest_recall = float(np.mean([len(set(pi_[i, :pc_[i]].tolist()) & set(bi[i].tolist())) / k for i in range(ns)]))
+
+    out = None
+    if rank == 0:
+        value = n / (build_ms * 1e-3)
+        out = {
+            "metric": "forest_build_points_per_s", "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": build_ms + knn_ms, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": W["name"], "n": n, "d": d, "ntrees": T, "trees_per_gpu": t_local, "pnz": W["pnz"], "max_depth": maxd,
+                       "min_leaf": W["min_leaf"], "queries": nq, "k": k, "parallelism": "trees sharded x%d, data replicated" % world,
+                       "l2": "inputs larger than L2 (X 1.02 GB, keys %.1f GB per build)" % (t_local * L * n * 8 / 1e9)},
+            "build_ms": build_ms, "knn_ms": knn_ms, "knn_queries_per_s": nq / (knn_ms * 1e-3),
+            "recall_at_10_recallWith": recall_ref_def, "recall_at_10_forest": forest_recall, "recall_queries": ns,
+            "candidates_per_query": C_mean,
+            "e2e": {"value": n / e2e_build_s, "unit": "points/s", "h2d_bytes_per_step": int(n * d * 8 + len(hp[1]) * 12 + len(hp[0]) * 8),
+                    "d2h_bytes_per_step": int(t_local * (nn * 24 + n * 4)), "build_s": e2e_build_s,
+                    "knn_queries_per_s": nq / e2e_knn_s, "knn_s": e2e_knn_s,
+                    "knn_h2d_bytes": int(nq * d * 8), "knn_d2h_bytes": int(nq * k * 12 + nq * 4)},
+            "gpu_launches": int(launches), "wall_ms_per_step": wall_ms,
+            "roofline": roofline,
+            "roofline_build": dict(bound="hbm", achieved=round(build_bytes / (build_ms * 1e-3) / 1e9, 1), peak=peak, unit="GB/s",
+                                   frac=round(build_bytes / (build_ms * 1e-3) / 1e9 / peak, 4), algorithmic_bytes=int(build_bytes)),
+            "roofline_knn": dict(bound="hbm", achieved=round(knn_bytes / (knn_ms * 1e-3) / 1e9, 1), peak=peak, unit="GB/s",
+                                 frac=round(knn_bytes / (knn_ms * 1e-3) / 1e9 / peak, 4), algorithmic_bytes=int(knn_bytes)),
+            "phases": phases, "clocks": clocks,
+        }
+        if not args.no_cpu and world == 1:
+            out["cpu_baseline"] = cpu_baseline(X, hp_all, W, maxd, sample_trees=None, threads=1)
+    barrier()
+    if dist is not None:
+        dist.destroy_process_group()
+    if out is not None:
+        print(json.dumps(out))
+
+
+def cpu_baseline(X, hp_all, W, maxd, sample_trees, threads):
+    """The reference algorithm (oracle port, `kind: port`) on the host cores, bounded sample: `threads` trees of the
+    forest built concurrently (one tree per thread; the reference itself is single threaded) on the full 1M x 128."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import orc
+    import rp_tree_b200 as R
+    T = W["ntrees"]
+    ntr = threads if sample_trees is None else sample_trees
+
+    def one(t):
+        hp = R.slice_hyperplanes(hp_all, maxd, t, 1)
+        f = orc.Forest(X, hp, 1, maxd, W["min_leaf"])
+        return f.tree_size(0)
+
+    orc.lib()
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        sizes = list(ex.map(one, range(ntr)))
+    dt = time.perf_counter() - t0
+    assert all(s == W["n"] for s in sizes)
+    forest_s = dt * T / ntr                     # time for the whole T-tree forest at this concurrency
+    return {"value": W["n"] / forest_s, "unit": "points/s", "cores": threads, "kind": "port",
+            "sample": "%d of %d trees built on the full %dx%d data by the C oracle (reference algorithm: per-node stable merge sort), "
+                      "%.1f s; forest time extrapolated x%g" % (ntr, T, W["n"], W["d"], dt, T / ntr),
+            "seconds": dt}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm for the same metric/config on all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import rp_tree_b200 as R
+    W = WORKLOAD
+    n, d, T = W["n"], W["d"], W["ntrees"]
+    maxd = R.rpTreeCfg(W["min_leaf"], n, d).fpMaxTreeDepth
+    X = make_points(n, d, W["data_seed"], W["clusters"], W["sigma"])
+    hp_all = R.sampleHyperplanes(W["forest_seed"], T, maxd, W["pnz"], d)
+    threads = os.cpu_count() or 1
+    threads = min(threads, T)
+    vals = []
+    for i in range(args.warmup + args.steps):
+        cb = cpu_baseline(X, hp_all, W, maxd, sample_trees=threads, threads=threads)
+        if i >= args.warmup:
+            vals.append(cb)
+        if sum(v["seconds"] for v in vals) > 150:
+            break
+    v = float(np.mean([c["value"] for c in vals]))
+    cb = dict(vals[-1]); cb["value"] = v
+    out = {"impl": "reference", "metric": "forest_build_points_per_s", "value": v, "unit": "points/s", "n_gpus": args.gpus,
+           "steps": len(vals), "warmup": args.warmup, "ms_per_step": float(np.mean([c["seconds"] for c in vals])) * 1e3,
+           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": W["name"], "n": n, "d": d, "ntrees": T, "pnz": W["pnz"], "max_depth": maxd, "min_leaf": W["min_leaf"]},
+           "cpu_baseline": cb,
+           "e2e": {"value": v, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "note": "reference = C port of the Haskell algorithm (no GHC toolchain in this image); each step builds `cores` trees "
+                   "of the forest concurrently on the full data and extrapolates to the 32-tree forest"}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
