@@ -50,6 +50,7 @@ SIGNATURES = {
     "rpf_phase_name": (C.c_char_p, [C.c_int]),
     "rpf_launch_count": (C.c_int64, [H]),
     "rpf_set_bottom_cap": (C.c_int, [H, C.c_int32]),
+    "rpf_set_option": (C.c_int, [H, C.c_char_p, C.c_int64]),
 }
 
 _LIB = None

@@ -242,6 +242,9 @@ class RPForest:
     def launchCount(self):
         return self._L.rpf_launch_count(self._h)
 
+    def setOption(self, name, value):
+        self._ck(self._L.rpf_set_option(self._h, name.encode(), int(value)), "rpf_set_option")
+
     def setBottomCap(self, cap):
         self._ck(self._L.rpf_set_bottom_cap(self._h, cap), "rpf_set_bottom_cap")
 
@@ -249,7 +252,7 @@ class RPForest:
 # ---------------------------------------------------------------------------------------------------------
 # the reference's function names
 # ---------------------------------------------------------------------------------------------------------
-def forestBatch(seed, maxd, minl, ntrees, pnz, dim, xs, *, hyperplanes=None, device=0, t_first=0, t_local=None, bottom_cap=None):
+def forestBatch(seed, maxd, minl, ntrees, pnz, dim, xs, *, hyperplanes=None, device=0, t_first=0, t_local=None, bottom_cap=None, options=None):
     """forestBatch (Batch.hs:48-63).  `hyperplanes` = CSR (off, idx, val) drawn by the Haskell host overrides the
     built-in sampler (bit-exact parity path).  t_first/t_local shard the trees for multi-GPU runs."""
     xs = np.ascontiguousarray(xs, dtype=np.float64)
@@ -259,6 +262,8 @@ def forestBatch(seed, maxd, minl, ntrees, pnz, dim, xs, *, hyperplanes=None, dev
     f = RPForest(device)
     if bottom_cap is not None:
         f.setBottomCap(bottom_cap)
+    for name, value in (options or {}).items():
+        f.setOption(name, value)
     f.setPoints(xs)
     if hyperplanes is not None:
         hp = hyperplanes if (t_first == 0 and t_local == ntrees) else slice_hyperplanes(hyperplanes, maxd, t_first, t_local)

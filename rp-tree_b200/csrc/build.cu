@@ -18,95 +18,177 @@
 // All comparisons are on order-preserving uint64 images of the doubles; projections use __dmul_rn/__dadd_rn in
 // the reference's right-fold order, so thresholds/margins/leaf sets are bit exact.
 #include "rpf_internal.h"
+#include "rpf_device.cuh"
 #include <algorithm>
 #include <cstdio>
-
-typedef unsigned long long ull;
 
 // =====================================================================================================
 // K1  projections: key[h][i] = hp[h] . X[i]   (innerSD, right fold, no FMA)
 // =====================================================================================================
-// Tile of P points staged in shared memory (row stride ld = d|1 doubles -> conflict-free column gathers),
-// thread (p, g) walks hyperplanes g, g+G, ...  Output row j corresponds to CSR row
-// (t0 + j / L) * hpDepth + (j % L).  ORD: write order-preserving uint64 + track per-row min/max.
-template <int NT, bool ORD>
-__global__ void __launch_bounds__(NT) k_project(const double* __restrict__ X, int64_t n, int d, int ld, int P,
-                                                 const int64_t* __restrict__ hp_off, const int32_t* __restrict__ hp_idx,
-                                                 const double* __restrict__ hp_val, int t0, int L, int hpDepth, int H,
+// A tile of P = 32*R points is staged in shared memory (row stride ld = d|1 doubles -> conflict-free column
+// gathers).  One warp owns one hyperplane at a time; every lane carries R points, so each (val, idx) pair is
+// fetched once (one 16-byte uniform load from the packed CSR) and feeds R independent mul/add chains.
+// Output row j corresponds to CSR row (t0 + j / L) * hpDepth + (j % L).
+// ORD: write order-preserving uint64 keys and track the per-row min/max (bin ranges of the top phase).
+template <int NT, int R, bool ORD>
+__global__ void __launch_bounds__(NT) k_project(const double* __restrict__ X, int64_t n, int d, int ld,
+                                                 const int64_t* __restrict__ hp_off, const double2* __restrict__ hp_pack,
+                                                 int t0, int L, int hpDepth, int H,
                                                  void* __restrict__ out, ull* __restrict__ kmin, ull* __restrict__ kmax) {
+    constexpr int P = 32 * R, NW = NT / 32;
     extern __shared__ double xs[];
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int64_t i0 = (int64_t)blockIdx.x * P;
     const int rows = (int)min((int64_t)P, n - i0);
-    // coalesced tile load
-    for (int r = 0; r < rows; ++r) {
-        const double* src = X + (i0 + r) * (int64_t)d;
-        for (int c = tid; c < d; c += NT) xs[r * ld + c] = src[c];
+    for (int r = w; r < P; r += NW) {
+        if (r < rows) {
+            const double* src = X + (i0 + r) * (int64_t)d;
+            for (int c = lane; c < d; c += 32) xs[r * ld + c] = src[c];
+        } else {
+            for (int c = lane; c < d; c += 32) xs[r * ld + c] = 0.0;
+        }
     }
     __syncthreads();
-    const int p = tid % P, g = tid / P, G = NT / P;
-    const bool live = p < rows;
-    const double* xr = xs + p * ld;
-    for (int jb = 0; jb < H; jb += G) {      // uniform trip count: the warp shuffles below need every lane
-        const int j = jb + g;
-        const bool hv = j < H;
-        double acc = 0.0;
-        if (hv && live) {
-            const int row = (t0 + j / L) * hpDepth + (j % L);
-            const int64_t s = hp_off[row];
-            int64_t e = hp_off[row + 1];
-            if (e - s > d) e = s + d;   // innerSD's `i >= nz2` guard (Internal.hs:376)
-            for (int64_t q = e - 1; q >= s; --q) acc = __dadd_rn(__dmul_rn(__ldg(hp_val + q), xr[__ldg(hp_idx + q)]), acc);
+    // 32-bit shared-window addresses of this lane's R rows (one IADD + LDS per term instead of 64-bit pointer math)
+    unsigned rowaddr[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) rowaddr[r] = (unsigned)__cvta_generic_to_shared(xs + (size_t)(lane + 32 * r) * ld);
+    for (int j = w; j < H; j += NW) {          // warp-uniform
+        const int row = (t0 + j / L) * hpDepth + (j % L);
+        const int64_t s = hp_off[row];
+        int64_t e = hp_off[row + 1];
+        if (e - s > d) e = s + d;               // innerSD's `i >= nz2` guard (Internal.hs:376)
+        double acc[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] = 0.0;
+        const double2* hq = hp_pack + e - 1;    // right fold: innermost (last) term first
+        int cntq = (int)(e - s);
+        for (; cntq >= 2; cntq -= 2, hq -= 2) {
+            const double2 h0 = __ldg(hq), h1 = __ldg(hq - 1);
+            const unsigned c0 = (unsigned)__double_as_longlong(h0.y) << 3, c1 = (unsigned)__double_as_longlong(h1.y) << 3;
+            double x0[R], x1[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                asm("ld.shared.f64 %0, [%1];" : "=d"(x0[r]) : "r"(rowaddr[r] + c0));
+                asm("ld.shared.f64 %0, [%1];" : "=d"(x1[r]) : "r"(rowaddr[r] + c1));
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                acc[r] = __dadd_rn(__dmul_rn(h0.x, x0[r]), acc[r]);
+                acc[r] = __dadd_rn(__dmul_rn(h1.x, x1[r]), acc[r]);
+            }
+        }
+        if (cntq) {
+            const double2 h0 = __ldg(hq);
+            const unsigned c0 = (unsigned)__double_as_longlong(h0.y) << 3;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                double x0;
+                asm("ld.shared.f64 %0, [%1];" : "=d"(x0) : "r"(rowaddr[r] + c0));
+                acc[r] = __dadd_rn(__dmul_rn(h0.x, x0), acc[r]);
+            }
         }
         if (ORD) {
-            const ull o = f2ord(acc);
-            if (hv && live) ((ull*)out)[(int64_t)j * n + i0 + p] = o;
-            ull vmin = (hv && live) ? o : ORD_NONE_HI, vmax = (hv && live) ? o : ORD_NONE_LO;
-            const int w = P < 32 ? P : 32;
-            for (int off = w >> 1; off > 0; off >>= 1) {
-                ull a = __shfl_xor_sync(0xffffffffu, vmin, off);
-                ull b = __shfl_xor_sync(0xffffffffu, vmax, off);
-                vmin = a < vmin ? a : vmin;
-                vmax = b > vmax ? b : vmax;
+            ull vmin = ORD_NONE_HI, vmax = ORD_NONE_LO;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int64_t i = i0 + lane + 32 * r;
+                if (i < n) {
+                    const ull o = f2ord(acc[r]);
+                    ((ull*)out)[(int64_t)j * n + i] = o;
+                    vmin = o < vmin ? o : vmin;
+                    vmax = o > vmax ? o : vmax;
+                }
             }
-            if (hv && (tid & (w - 1)) == 0 && vmin != ORD_NONE_HI) {
+            for (int off = 16; off > 0; off >>= 1) {
+                const ull a2 = __shfl_xor_sync(0xffffffffu, vmin, off), b2 = __shfl_xor_sync(0xffffffffu, vmax, off);
+                vmin = a2 < vmin ? a2 : vmin;
+                vmax = b2 > vmax ? b2 : vmax;
+            }
+            if (lane == 0 && vmin != ORD_NONE_HI) {
                 if (vmin < kmin[j]) atomicMin(&kmin[j], vmin);
                 if (vmax > kmax[j]) atomicMax(&kmax[j], vmax);
             }
         } else {
-            if (hv && live) ((double*)out)[(int64_t)j * n + i0 + p] = acc;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int64_t i = i0 + lane + 32 * r;
+                if (i < n) ((double*)out)[(int64_t)j * n + i] = acc[r];
+            }
         }
     }
 }
 
-static int project_tile_points(int d) {
-    // shared bytes = P * (d|1) * 8 ; keep <= ~72 KB so 3 CTAs fit an SM
-    int ld = d | 1;
-    int P = 64;
-    while (P > 1 && (size_t)P * ld * 8 > 72 * 1024) P >>= 1;
-    return P;
+// Fallback for very large d (tile does not fit shared memory): same arithmetic, rows read through L1/L2.
+template <bool ORD>
+__global__ void __launch_bounds__(256) k_project_direct(const double* __restrict__ X, int64_t n, int d,
+                                                         const int64_t* __restrict__ hp_off, const double2* __restrict__ hp_pack,
+                                                         int t0, int L, int hpDepth, int H,
+                                                         void* __restrict__ out, ull* __restrict__ kmin, ull* __restrict__ kmax) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t i = (int64_t)blockIdx.x * 32 + lane;
+    const bool live = i < n;
+    const double* xr = X + (live ? i : 0) * (int64_t)d;
+    for (int j = w; j < H; j += 8) {
+        const int row = (t0 + j / L) * hpDepth + (j % L);
+        const int64_t s = hp_off[row];
+        int64_t e = hp_off[row + 1];
+        if (e - s > d) e = s + d;
+        double acc = 0.0;
+        for (int64_t q = e - 1; q >= s; --q) {
+            const double2 hv = __ldg(hp_pack + q);
+            acc = __dadd_rn(__dmul_rn(hv.x, __ldg(xr + (int)__double_as_longlong(hv.y))), acc);
+        }
+        if (ORD) {
+            const ull o = f2ord(acc);
+            if (live) ((ull*)out)[(int64_t)j * n + i] = o;
+            ull vmin = live ? o : ORD_NONE_HI, vmax = live ? o : ORD_NONE_LO;
+            for (int off = 16; off > 0; off >>= 1) {
+                const ull a2 = __shfl_xor_sync(0xffffffffu, vmin, off), b2 = __shfl_xor_sync(0xffffffffu, vmax, off);
+                vmin = a2 < vmin ? a2 : vmin;
+                vmax = b2 > vmax ? b2 : vmax;
+            }
+            if (lane == 0 && vmin != ORD_NONE_HI) {
+                if (vmin < kmin[j]) atomicMin(&kmin[j], vmin);
+                if (vmax > kmax[j]) atomicMax(&kmax[j], vmax);
+            }
+        } else if (live) {
+            ((double*)out)[(int64_t)j * n + i] = acc;
+        }
+    }
+}
+
+template <int NT, int R, bool ORD>
+static int launch_project(rpf_handle* h, int phase, const double* dX, int64_t n, int t0, int L, int H, void* out, ull* kmin, ull* kmax) {
+    const int d = h->d, ld = d | 1;
+    const size_t smem = (size_t)32 * R * ld * sizeof(double);
+    auto kfn = k_project<NT, R, ORD>;
+    RPF_CUDA(h, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t grid = (n + 32 * R - 1) / (32 * R);
+    RPF_LAUNCH(h, phase, kfn, (unsigned)grid, NT, smem, dX, n, d, ld, h->d_hp_off, (const double2*)h->d_hp_pack, t0, L, h->hpDepth, H, out, kmin, kmax);
+    return RPF_OK;
 }
 
 int rpf_project_launch(rpf_handle* h, int phase, const double* dX, int64_t n, int t0, int Tg, int L, bool ord, void* out,
                        ull* kmin, ull* kmax) {
     const int d = h->d, ld = d | 1;
-    const int P = project_tile_points(d);
-    const size_t smem = (size_t)P * ld * sizeof(double);
-    if (smem > 200 * 1024) return rpf_fail(h, RPF_ERR_UNSUPPORTED, "dimension too large for the projection tile");
     const int H = Tg * L;
-    const int64_t grid = (n + P - 1) / P;
-    if (grid <= 0 || H <= 0) return RPF_OK;
-    constexpr int NT = 256;
+    if (n <= 0 || H <= 0) return RPF_OK;
+    const size_t row = (size_t)ld * 8;
+    if (128 * row <= 140 * 1024)
+        return ord ? launch_project<1024, 4, true>(h, phase, dX, n, t0, L, H, out, kmin, kmax)
+                   : launch_project<1024, 4, false>(h, phase, dX, n, t0, L, H, out, kmin, kmax);
+    if (64 * row <= 110 * 1024)
+        return ord ? launch_project<256, 2, true>(h, phase, dX, n, t0, L, H, out, kmin, kmax)
+                   : launch_project<256, 2, false>(h, phase, dX, n, t0, L, H, out, kmin, kmax);
+    if (32 * row <= 110 * 1024)
+        return ord ? launch_project<256, 1, true>(h, phase, dX, n, t0, L, H, out, kmin, kmax)
+                   : launch_project<256, 1, false>(h, phase, dX, n, t0, L, H, out, kmin, kmax);
+    const int64_t grid = (n + 31) / 32;
     if (ord) {
-        auto kfn = k_project<NT, true>;
-        RPF_CUDA(h, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        RPF_LAUNCH(h, phase, kfn, (unsigned)grid, NT, smem, dX, n, d, ld, P, h->d_hp_off, h->d_hp_idx,
-                   h->d_hp_val, t0, L, h->hpDepth, H, out, kmin, kmax);
+        RPF_LAUNCH(h, phase, k_project_direct<true>, (unsigned)grid, 256, 0, dX, n, d, h->d_hp_off, (const double2*)h->d_hp_pack, t0, L, h->hpDepth, H, out, kmin, kmax);
     } else {
-        auto kfn = k_project<NT, false>;
-        RPF_CUDA(h, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        RPF_LAUNCH(h, phase, kfn, (unsigned)grid, NT, smem, dX, n, d, ld, P, h->d_hp_off, h->d_hp_idx,
-                   h->d_hp_val, t0, L, h->hpDepth, H, out, kmin, kmax);
+        RPF_LAUNCH(h, phase, k_project_direct<false>, (unsigned)grid, 256, 0, dX, n, d, h->d_hp_off, (const double2*)h->d_hp_pack, t0, L, h->hpDepth, H, out, kmin, kmax);
     }
     return RPF_OK;
 }
@@ -115,8 +197,6 @@ int rpf_project_launch(rpf_handle* h, int phase, const double* dX, int64_t n, in
 // shared bitonic helpers (normalised network: every comparator puts the smaller element at the lower
 // index, so positions >= m behave as +inf padding and comparators touching them are skipped)
 // =====================================================================================================
-__device__ __forceinline__ int ilog2_pow2(unsigned v) { return 31 - __clz(v); }
-__device__ __forceinline__ unsigned next_pow2_u32(unsigned v) { return v <= 1 ? 1u : 1u << (32 - __clz(v - 1)); }
 
 // sort m uint64 keys ascending in shared memory
 template <int NT>
@@ -298,43 +378,10 @@ __global__ void __launch_bounds__(TOP_NT) k_top_compact(TopArgs A) {
     }
 }
 
-// 8-bit MSD radix select of rank r over `c` values fetched by `get(i)`; all threads of the CTA call it.
-// Returns the selected value; cl = #values < it, ce = #values == it.
-template <int NT, typename Get>
-__device__ ull cta_radix_select(uint32_t c, uint32_t r, Get get, uint32_t* sh /*256+*/, ull* sh64 /*1*/, uint32_t& cl, uint32_t& ce) {
-    ull prefix = 0;
-    uint32_t rr = r, below = 0;
-    for (int pass = 0; pass < 8; ++pass) {
-        const int shift = 56 - 8 * pass;
-        const ull mask_hi = pass == 0 ? 0ull : (~0ull << (shift + 8));
-        for (int j = threadIdx.x; j < 256; j += NT) sh[j] = 0;
-        __syncthreads();
-        for (uint32_t i = threadIdx.x; i < c; i += NT) {
-            ull v = get(i);
-            if ((v & mask_hi) == prefix) atomicAdd(&sh[(v >> shift) & 255], 1u);
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            uint32_t cum = 0; int dg = 255;
-            for (int b = 0; b < 256; ++b) { if (rr < cum + sh[b]) { dg = b; break; } cum += sh[b]; }
-            sh[256] = cum; sh[257] = sh[dg];
-            *sh64 = prefix | ((ull)dg << shift);
-        }
-        __syncthreads();
-        prefix = *sh64;
-        rr -= sh[256];
-        below += sh[256];
-        ce = sh[257];
-        __syncthreads();
-    }
-    cl = below;
-    return prefix;
-}
-
 // one CTA per (node, tree): exact order statistic inside the median bin
 __global__ void __launch_bounds__(512) k_top_finish(TopArgs A) {
     __shared__ ull buf[FIN_CAP];
-    __shared__ uint32_t sh[260];
+    __shared__ uint32_t sh[264];
     __shared__ ull sh64[3];
     const int t = blockIdx.y, nl = blockIdx.x, g = A.node0 + nl, tid = threadIdx.x;
     if (A.child[g] < 0) return;
@@ -386,7 +433,7 @@ __global__ void __launch_bounds__(512) k_top_finish(TopArgs A) {
 // (key_{l-1}, key_{l-2}, ..., key_0, row id) such that exactly tie_r tied points are lexicographically below it:
 // this is the order the reference's stable merge sort leaves tied points in (Internal.hs:504-512).
 __global__ void __launch_bounds__(512) k_top_ties(TopArgs A) {
-    __shared__ uint32_t sh[260];
+    __shared__ uint32_t sh[264];
     __shared__ ull sh64[1];
     __shared__ uint32_t cnt;
     const int t = blockIdx.y, nl = blockIdx.x, g = A.node0 + nl, tid = threadIdx.x;
@@ -689,26 +736,381 @@ __global__ void __launch_bounds__(NT) k_bottom(BottomArgs A) {
 }
 
 // =====================================================================================================
+// bottom phase, fast path: uniform padded layout + packed (key48 | slot16) sort words
+// =====================================================================================================
+// The node's P0 = next_pow2(size) slots form a complete binary layout: at relative depth j a segment owns Pv = P0>>j
+// slots, real elements first, then padding.  Every level is ONE uniform bitonic network over all slots on 64-bit
+// words w = (order-preserving key with its low 16 bits replaced by the element's slot).  Comparing w compares the
+// top 48 key bits, then the incoming slot -- i.e. the reference's stable sort whenever the low 16 key bits do not
+// decide.  Adjacent words with equal top-48 bits (rare) are re-checked with the full keys and fixed by odd-even
+// transposition, so the result is exactly Merge.sortBy (comparing snd) (Internal.hs:504-512).
+// No entry tables, no bounds checks and no payload in the network: 2 LDS.64 + compare + 2 STS.64 per comparator.
+#define BOT2_TAB 512
+#define W_SENT 0xffffffffffffffffull
+
+template <int NT>
+__device__ __forceinline__ void bitonic_uniform(ull* w, unsigned nslots, unsigned Pv) {
+    const unsigned half = nslots >> 1;
+    for (unsigned k = 2; k <= Pv; k <<= 1) {
+        const int lk = ilog2_pow2(k);
+        for (unsigned c = threadIdx.x; c < half; c += NT) {
+            const unsigned blk = c >> (lk - 1), x = c & ((k >> 1) - 1);
+            const unsigned i = (blk << lk) + x, p = (blk << lk) + (k - 1 - x);
+            const ull a = w[i], b = w[p];
+            if (a > b) { w[i] = b; w[p] = a; }
+        }
+        __syncthreads();
+        for (unsigned j = k >> 2; j > 0; j >>= 1) {
+            const int lj = ilog2_pow2(j);
+            for (unsigned c = threadIdx.x; c < half; c += NT) {
+                const unsigned i = ((c >> lj) << (lj + 1)) + (c & (j - 1)), p = i + j;
+                const ull a = w[i], b = w[p];
+                if (a > b) { w[i] = b; w[p] = a; }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// ---- register-blocked bitonic network --------------------------------------------------------------------------
+// Thread t owns the 8 consecutive slots [8t, 8t+8) in registers.  Comparator distances 1,2,4 are register-to-register,
+// 8..128 are lane-to-lane shuffles inside the warp, >= 256 go through shared memory in a transposed layout
+// (slot x lives at (x & 7) * NT + (x >> 3), so consecutive threads touch consecutive words: no bank conflicts).
+__device__ __forceinline__ void ce_min_first(ull& a, ull& b) { if (a > b) { const ull t = a; a = b; b = t; } }
+
+template <int K>
+__device__ __forceinline__ void flip_in(ull (&v)[8]) {      // mirror pairs inside blocks of K <= 8 registers
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { const int p = e ^ (K - 1); if (e < p) ce_min_first(v[e], v[p]); }
+}
+template <int J>
+__device__ __forceinline__ void half_in(ull (&v)[8]) {      // pairs (e, e+J), J in {1,2,4}
+#pragma unroll
+    for (int e = 0; e < 8; ++e) if ((e & J) == 0) ce_min_first(v[e], v[e + J]);
+}
+__device__ __forceinline__ void flip_shfl(ull (&v)[8], unsigned g, unsigned lane) {   // block of g lanes (8g slots)
+    const bool lower = (lane & (g >> 1)) == 0;
+    ull o[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = __shfl_xor_sync(0xffffffffu, v[7 - e], g - 1);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { const bool lt = v[e] < o[e]; v[e] = (lt == lower) ? v[e] : o[e]; }
+}
+__device__ __forceinline__ void half_shfl(ull (&v)[8], unsigned jl, unsigned lane) {  // partner lane = lane ^ jl
+    const bool lower = (lane & jl) == 0;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const ull o = __shfl_xor_sync(0xffffffffu, v[e], jl);
+        const bool lt = v[e] < o;
+        v[e] = (lt == lower) ? v[e] : o;
+    }
+}
+__device__ __forceinline__ void tail_in(ull (&v)[8]) { half_in<4>(v); half_in<2>(v); half_in<1>(v); }
+
+// sorts every aligned block of Pv slots (Pv a power of two, 2 <= Pv <= 8*NT) ascending; all threads must call
+template <int NT>
+__device__ void sort_regs(ull (&v)[8], ull* w, unsigned Pv) {
+    const unsigned tid = threadIdx.x, lane = tid & 31;
+    flip_in<2>(v);
+    if (Pv >= 4) { flip_in<4>(v); half_in<1>(v); }
+    if (Pv >= 8) { flip_in<8>(v); half_in<2>(v); half_in<1>(v); }
+    for (unsigned g = 2; g <= 32 && 8 * g <= Pv; g <<= 1) {           // k = 8g = 16 .. 256: inside one warp
+        flip_shfl(v, g, lane);
+        for (unsigned jl = g >> 2; jl >= 1; jl >>= 1) half_shfl(v, jl, lane);
+        tail_in(v);
+    }
+    if (NT > 32) {
+        for (unsigned k = 512; k <= Pv; k <<= 1) {                    // cross-warp merges
+            const unsigned kt = k >> 3;                                // block size in threads
+            const int lkt = ilog2_pow2(kt);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) w[e * NT + tid] = v[e];
+            __syncthreads();
+            // flip: slot (e, u) with u in the lower half of its kt-block <-> (7-e, mirrored u)
+            for (unsigned c = tid; c < 4u * NT; c += NT) {
+                const unsigned e = c / (NT / 2), cc = c % (NT / 2);
+                const unsigned blk = cc >> (lkt - 1), uo = cc & ((kt >> 1) - 1);
+                const unsigned u = (blk << lkt) + uo, up = (blk << lkt) + (kt - 1 - uo);
+                const unsigned ia = e * NT + u, ib = (7 - e) * NT + up;
+                const ull a = w[ia], b = w[ib];
+                if (a > b) { w[ia] = b; w[ib] = a; }
+            }
+            __syncthreads();
+            for (unsigned jt = kt >> 2; jt >= 32; jt >>= 1) {          // distances j = 8*jt >= 256
+                const int lj = ilog2_pow2(jt);
+                for (unsigned c = tid; c < 4u * NT; c += NT) {
+                    const unsigned e = c / (NT / 2), cc = c % (NT / 2);
+                    const unsigned u = ((cc >> lj) << (lj + 1)) + (cc & (jt - 1));
+                    const unsigned ia = e * NT + u, ib = ia + jt;
+                    const ull a = w[ia], b = w[ib];
+                    if (a > b) { w[ia] = b; w[ib] = a; }
+                }
+                __syncthreads();
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = w[e * NT + tid];
+            for (unsigned jl = 16; jl >= 1; jl >>= 1) half_shfl(v, jl, lane);
+            tail_in(v);
+        }
+    }
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT) k_bottom3(BottomArgs A) {
+    constexpr unsigned P0 = 8 * NT;               // slots (>= node size), 8 per thread
+    constexpr int lp0 = (NT == 32 ? 8 : NT == 64 ? 9 : NT == 128 ? 10 : NT == 256 ? 11 : NT == 512 ? 12 : 13);
+    extern __shared__ unsigned char smraw[];
+    ull* w = (ull*)smraw;                         // [P0] sort words
+    uint32_t* sidx = (uint32_t*)(w + P0);         // [P0] row id held by each slot
+    __shared__ uint16_t t_sz[2][BOT2_TAB];        // size of the segment if it splits at this level, else 0
+    __shared__ uint16_t t_ps[2][BOT2_TAB];        // offset of the segment inside this CTA's slice of perm
+    __shared__ int32_t t_gid[2][BOT2_TAB];        // BFS id
+    __shared__ uint16_t t_lsz[BOT2_TAB];          // size if the segment just became a Tip (to be emitted), else 0
+    const int t = blockIdx.y, tid = threadIdx.x;
+    const int e0 = A.first_gid + blockIdx.x;
+    const uint32_t m = A.nsize[e0], start = A.nstart[e0];
+    if (m == 0) return;
+    const int64_t n = A.n;
+    const ull* keys_t = A.keys + (int64_t)t * A.L * n;
+    uint32_t* perm = A.perm + (int64_t)t * n + start;
+    const bool root_internal = A.child[e0] >= 0;
+
+    for (uint32_t p = tid; p < P0; p += NT) sidx[p] = p < m ? perm[p] : 0u;
+    __syncthreads();
+
+    // composite order (key_{s-1}, ..., key_0, row id) of the whole node: only needed when the node arrives unordered
+    // (s > 0) AND either it is a Tip itself or its first sort hits a tie in the top 48 key bits.
+    auto composite_sort = [&]() {
+        const ull* k1 = keys_t + (int64_t)(A.s - 1) * n;
+        for (uint32_t p = tid; p < m; p += NT) w[p] = k1[sidx[p]];
+        __syncthreads();
+        auto after = [&](ull ka, uint32_t ia, ull kb, uint32_t ib) -> bool {
+            if (ka != kb) return ka > kb;
+            for (int lvl = A.s - 2; lvl >= 0; --lvl) {
+                const ull xa = keys_t[(int64_t)lvl * n + ia], xb = keys_t[(int64_t)lvl * n + ib];
+                if (xa != xb) return xa > xb;
+            }
+            return ia > ib;
+        };
+        const unsigned Pm = next_pow2_u32(m), half = Pm >> 1;
+        for (unsigned k = 2; k <= Pm; k <<= 1) {
+            const int lk = ilog2_pow2(k);
+            for (unsigned c = tid; c < half; c += NT) {
+                const unsigned blk = c >> (lk - 1), x = c & ((k >> 1) - 1);
+                const unsigned i = (blk << lk) + x, p = (blk << lk) + (k - 1 - x);
+                if (p < m) {
+                    const ull a = w[i], b = w[p]; const uint32_t ia = sidx[i], ib = sidx[p];
+                    if (after(a, ia, b, ib)) { w[i] = b; w[p] = a; sidx[i] = ib; sidx[p] = ia; }
+                }
+            }
+            __syncthreads();
+            for (unsigned j = k >> 2; j > 0; j >>= 1) {
+                const int lj = ilog2_pow2(j);
+                for (unsigned c = tid; c < half; c += NT) {
+                    const unsigned i = ((c >> lj) << (lj + 1)) + (c & (j - 1)), p = i + j;
+                    if (p < m) {
+                        const ull a = w[i], b = w[p]; const uint32_t ia = sidx[i], ib = sidx[p];
+                        if (after(a, ia, b, ib)) { w[i] = b; w[p] = a; sidx[i] = ib; sidx[p] = ia; }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+    };
+
+    if (!root_internal) {        // the node is a Tip: its points must simply be in the reference's order
+        if (A.s > 0) { composite_sort(); for (uint32_t p = tid; p < m; p += NT) perm[p] = sidx[p]; }
+        return;
+    }
+    if (tid == 0) { t_sz[0][0] = (uint16_t)m; t_ps[0][0] = 0; t_gid[0][0] = e0; }
+    __syncthreads();
+
+    int cur = 0;
+    bool need_check_order = A.s > 0;       // slots are not yet in the reference's incoming order
+    const unsigned x0 = 8u * tid;          // first slot owned by this thread
+    for (int j = 0;; ++j) {
+        const int l = A.s + j;
+        const unsigned Pv = P0 >> j, nseg = 1u << j;
+        const int lpv = lp0 - j;
+        const ull* kl = keys_t + (int64_t)l * n;
+        const uint16_t* sz = t_sz[cur];
+
+        // ---- gather keys into registers, build sort words, sort, store back in slot order
+        auto gather_and_sort = [&]() {
+            ull v[8];
+            const unsigned e = x0 >> lpv;                 // all 8 slots share a segment when Pv >= 8
+            if (Pv >= 8) {
+                const unsigned se = sz[e], i0 = x0 & (Pv - 1);
+                uint32_t ids[8];
+                const uint4 ia = *(const uint4*)(sidx + x0), ib = *(const uint4*)(sidx + x0 + 4);
+                ids[0] = ia.x; ids[1] = ia.y; ids[2] = ia.z; ids[3] = ia.w; ids[4] = ib.x; ids[5] = ib.y; ids[6] = ib.z; ids[7] = ib.w;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v[q] = (i0 + q < se) ? kl[ids[q]] : 0ull;      // 8 independent loads in flight
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v[q] = (i0 + q < se) ? ((v[q] & ~0xffffull) | (x0 + q)) : W_SENT;
+            } else {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const unsigned x = x0 + q, eq = x >> lpv, i = x & (Pv - 1);
+                    v[q] = (i < sz[eq]) ? ((kl[sidx[x]] & ~0xffffull) | x) : W_SENT;
+                }
+            }
+            __syncthreads();                              // every thread has read sidx/w before w is reused
+            sort_regs<NT>(v, w, Pv);
+            __syncthreads();                              // other threads may still be reading the transposed staging
+            *(ulonglong2*)(w + x0) = make_ulonglong2(v[0], v[1]);
+            *(ulonglong2*)(w + x0 + 2) = make_ulonglong2(v[2], v[3]);
+            *(ulonglong2*)(w + x0 + 4) = make_ulonglong2(v[4], v[5]);
+            *(ulonglong2*)(w + x0 + 6) = make_ulonglong2(v[6], v[7]);
+            __syncthreads();
+        };
+        gather_and_sort();
+
+        // ---- ties in the top 48 bits: re-check with full keys
+        auto tie_flag = [&]() -> int {
+            int f = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const unsigned slot = x0 + q;
+                if (slot + 1 < P0) {
+                    const unsigned e = slot >> lpv, i = slot & (Pv - 1);
+                    if (i + 1 < sz[e]) f |= ((w[slot] >> 16) == (w[slot + 1] >> 16));
+                }
+            }
+            return __syncthreads_or(f);
+        };
+        int flag = tie_flag();
+        if (flag && need_check_order) {
+            // the incoming slot order was arbitrary: establish the reference's order first, then redo this level
+            composite_sort();
+            need_check_order = false;
+            gather_and_sort();
+            flag = tie_flag();
+        }
+        need_check_order = false;
+        if (flag) {
+            // exact comparator on neighbours: (full key, incoming slot); odd-even transposition until stable
+            while (true) {
+                int swapped = 0;
+                for (int par = 0; par < 2; ++par) {
+                    for (unsigned c = tid; c < (P0 >> 1); c += NT) {
+                        const unsigned slot = 2 * c + par;
+                        if (slot + 1 < P0) {
+                            const unsigned e = slot >> lpv, i = slot & (Pv - 1);
+                            if (i + 1 < sz[e]) {
+                                const ull a = w[slot], b = w[slot + 1];
+                                if ((a >> 16) == (b >> 16)) {
+                                    const ull fa = kl[sidx[a & 0xffff]], fb = kl[sidx[b & 0xffff]];
+                                    if (fa > fb || (fa == fb && (a & 0xffff) > (b & 0xffff))) { w[slot] = b; w[slot + 1] = a; swapped = 1; }
+                                }
+                            }
+                        }
+                    }
+                    __syncthreads();
+                }
+                if (!__syncthreads_or(swapped)) break;
+            }
+        }
+
+        // ---- thresholds / margins at the sorted positions (Internal.hs:496-503)
+        for (unsigned e = tid; e < nseg; e += NT) {
+            const unsigned se = sz[e];
+            if (!se) continue;
+            const unsigned off = e << lpv, nh = se >> 1;
+            auto full = [&](unsigned slot) { return kl[sidx[w[slot] & 0xffff]]; };
+            const ull th = full(off + nh);
+            ull ml, mh;
+            if (se >= 3) { ml = full(off + nh - 1); mh = full(off + nh + 1); }
+            else if (se == 2) { ml = full(off); mh = full(off + 1); }
+            else { ml = th; mh = th; }
+            const int64_t o = (int64_t)(A.gt0 + t) * A.nn_all + t_gid[cur][e];
+            A.thr[o] = ord2f(th); A.mlo[o] = ord2f(ml); A.mhi[o] = ord2f(mh);
+        }
+
+        // ---- children tables
+        const int nxt = cur ^ 1;
+        const bool can_grow = (nseg * 2 <= BOT2_TAB) && Pv >= 2;
+        int any_internal = 0;
+        if (can_grow) {
+            for (unsigned c = tid; c < nseg * 2; c += NT) {
+                const unsigned e = c >> 1, ps = sz[e];
+                uint16_t csz = 0, lsz = 0, cps = 0; int32_t cg = -1;
+                if (ps) {
+                    const unsigned nh = ps >> 1;
+                    const unsigned s2 = (c & 1) ? ps - nh : nh;
+                    cps = (uint16_t)(t_ps[cur][e] + ((c & 1) ? nh : 0));
+                    cg = A.child[t_gid[cur][e]] + (int)(c & 1);
+                    if (A.child[cg] >= 0) { csz = (uint16_t)s2; any_internal = 1; }
+                    else lsz = (uint16_t)s2;
+                }
+                t_sz[nxt][c] = csz; t_ps[nxt][c] = cps; t_gid[nxt][c] = cg; t_lsz[c] = lsz;
+            }
+        }
+        // ---- move the row ids: left half stays, right half starts at the middle of the segment
+        {
+            uint32_t val[8]; uint32_t dst[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const unsigned slot = x0 + q;
+                dst[q] = 0xffffffffu;
+                const unsigned e = slot >> lpv, i = slot & (Pv - 1), se = sz[e];
+                if (i < se) {
+                    const unsigned nh = se >> 1;
+                    val[q] = sidx[w[slot] & 0xffff];
+                    dst[q] = i < nh ? slot : (e << lpv) + (Pv >> 1) + (i - nh);
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int q = 0; q < 8; ++q) if (dst[q] != 0xffffffffu) sidx[dst[q]] = val[q];
+        }
+        any_internal = __syncthreads_or(any_internal);
+        if (!can_grow) break;      // unreachable for the shapes the host routes here
+        // ---- emit the children that are Tips
+        {
+            const unsigned Pc = Pv >> 1;
+            const int lpc = lpv - 1;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const unsigned slot = x0 + q;
+                const unsigned c = slot >> lpc, i = slot & (Pc - 1);
+                if (i < t_lsz[c]) perm[t_ps[nxt][c] + i] = sidx[slot];
+            }
+        }
+        __syncthreads();
+        cur = nxt;
+        if (!any_internal) break;
+    }
+}
+
+// =====================================================================================================
 // host orchestration
 // =====================================================================================================
-struct DevBuf {
-    void* p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
-    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16); }
-    template <typename T> T* as() { return (T*)p; }
-};
-
 static unsigned next_pow2_host(unsigned v) { unsigned p = 1; while (p < v) p <<= 1; return p; }
 
 template <int CAP, int NT>
-static int launch_bottom(rpf_handle* h, const BottomArgs& B, int nnodes_s, int tg) {
+static int launch_bottom_generic(rpf_handle* h, const BottomArgs& B, int nnodes_s, int tg) {
+    dim3 grid((unsigned)nnodes_s, (unsigned)tg);
     const size_t smem = (size_t)CAP * 16;
     auto kfn = k_bottom<CAP, NT>;
     RPF_CUDA(h, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((unsigned)nnodes_s, (unsigned)tg);
     RPF_LAUNCH(h, PH_BOTTOM, kfn, grid, NT, smem, B);
     return RPF_OK;
 }
+template <int NT>
+static int launch_bottom_fast(rpf_handle* h, const BottomArgs& B, int nnodes_s, int tg) {
+    dim3 grid((unsigned)nnodes_s, (unsigned)tg);
+    const size_t smem = (size_t)NT * 8 * 12;
+    auto kfn = k_bottom3<NT>;
+    RPF_CUDA(h, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RPF_CUDA(h, cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    RPF_LAUNCH(h, PH_BOTTOM, kfn, grid, NT, smem, B);
+    return RPF_OK;
+}
+
+#define WS(h, var, type, slot, bytes)                                   \
+    type* var = (type*)(h)->ws_get((slot), (bytes));                    \
+    if (!var) return RPF_ERR_NOMEM;
 
 int rpf_build_impl(rpf_handle* h) {
     const Topology& tp = h->topo;
@@ -716,15 +1118,19 @@ int rpf_build_impl(rpf_handle* h) {
     const int T = h->T, L = tp.L_eff, CAP = h->bottom_cap;
     h->leaf_order_exact = true;
 
-    // ---- result arrays
-    if (h->d_thr) { cudaFree(h->d_thr); cudaFree(h->d_mlo); cudaFree(h->d_mhi); cudaFree(h->d_perm); h->d_thr = h->d_mlo = h->d_mhi = nullptr; h->d_perm = nullptr; }
-    RPF_CUDA(h, cudaMalloc(&h->d_thr, sizeof(double) * (size_t)(T * nn)));
-    RPF_CUDA(h, cudaMalloc(&h->d_mlo, sizeof(double) * (size_t)(T * nn)));
-    RPF_CUDA(h, cudaMalloc(&h->d_mhi, sizeof(double) * (size_t)(T * nn)));
-    RPF_CUDA(h, cudaMalloc(&h->d_perm, sizeof(uint32_t) * (size_t)std::max<int64_t>(T * n, 1)));
-    RPF_CUDA(h, cudaMemsetAsync(h->d_thr, 0, sizeof(double) * (size_t)(T * nn), h->stream));
-    RPF_CUDA(h, cudaMemsetAsync(h->d_mlo, 0, sizeof(double) * (size_t)(T * nn), h->stream));
-    RPF_CUDA(h, cudaMemsetAsync(h->d_mhi, 0, sizeof(double) * (size_t)(T * nn), h->stream));
+    // ---- result arrays (kept across builds of the same shape)
+    const size_t node_bytes = sizeof(double) * (size_t)(T * nn), perm_bytes = sizeof(uint32_t) * (size_t)std::max<int64_t>(T * n, 1);
+    if (h->res_node_bytes != node_bytes || h->res_perm_bytes != perm_bytes || !h->d_thr) {
+        if (h->d_thr) { cudaFree(h->d_thr); cudaFree(h->d_mlo); cudaFree(h->d_mhi); cudaFree(h->d_perm); h->d_thr = h->d_mlo = h->d_mhi = nullptr; h->d_perm = nullptr; }
+        RPF_CUDA(h, cudaMalloc(&h->d_thr, node_bytes));
+        RPF_CUDA(h, cudaMalloc(&h->d_mlo, node_bytes));
+        RPF_CUDA(h, cudaMalloc(&h->d_mhi, node_bytes));
+        RPF_CUDA(h, cudaMalloc(&h->d_perm, perm_bytes));
+        h->res_node_bytes = node_bytes; h->res_perm_bytes = perm_bytes;
+    }
+    RPF_CUDA(h, cudaMemsetAsync(h->d_thr, 0, node_bytes, h->stream));
+    RPF_CUDA(h, cudaMemsetAsync(h->d_mlo, 0, node_bytes, h->stream));
+    RPF_CUDA(h, cudaMemsetAsync(h->d_mhi, 0, node_bytes, h->stream));
 
     // ---- phase split: first level whose nodes all fit the shared-memory capacity
     int s = tp.nlevels;
@@ -757,38 +1163,43 @@ int rpf_build_impl(rpf_handle* h) {
     }
     const int MAXTD = L + 1;
 
-    // ---- tree group size from free memory
+    // ---- tree group size from the memory budget (free memory + what the workspace already holds)
     size_t freeB = 0, totalB = 0;
     RPF_CUDA(h, cudaMemGetInfo(&freeB, &totalB));
     const size_t per_tree = (size_t)L * n * 8 + (s_top > 0 ? (size_t)n * 10 : 0) + (size_t)HSZ * 4 +
                             (size_t)NTOP * (sizeof(NodeSel) + 4 + (size_t)MAXTD * 8) + 4096;
-    int Tg = (int)std::min<size_t>((size_t)T, std::max<size_t>(1, (size_t)(freeB * 0.7) / per_tree));
-    if ((size_t)per_tree > freeB) return rpf_fail(h, RPF_ERR_NOMEM, "not enough device memory for one tree's keys");
+    const size_t budget = (size_t)((double)(freeB + h->ws_bytes) * 0.7);
+    if (per_tree > budget) return rpf_fail(h, RPF_ERR_NOMEM, "not enough device memory for one tree's keys");
+    const int Tg = (int)std::min<size_t>((size_t)T, std::max<size_t>(1, budget / per_tree));
 
-    DevBuf keys, label, hist, sel, cand, cand_total, pivots, fill, kmin, kmax, binlo, binscale, nbdev, range, lvlpv;
-    RPF_CUDA(h, keys.alloc((size_t)Tg * L * n * 8));
-    RPF_CUDA(h, kmin.alloc((size_t)Tg * L * 8));
-    RPF_CUDA(h, kmax.alloc((size_t)Tg * L * 8));
+    WS(h, keys, ull, WS_KEYS, (size_t)Tg * L * n * 8);
+    WS(h, kmin, ull, WS_KMIN, (size_t)Tg * L * 8);
+    WS(h, kmax, ull, WS_KMAX, (size_t)Tg * L * 8);
+    uint16_t* label = nullptr; uint32_t *hist = nullptr, *cand_total = nullptr, *fill = nullptr; NodeSel* sel = nullptr;
+    ull *cand = nullptr, *pivots = nullptr; double *binlo = nullptr, *binscale = nullptr; int* nbdev = nullptr;
     if (s_top > 0) {
-        RPF_CUDA(h, label.alloc((size_t)Tg * n * 2));
-        RPF_CUDA(h, hist.alloc((size_t)Tg * HSZ * 4));
-        RPF_CUDA(h, sel.alloc((size_t)Tg * NTOP * sizeof(NodeSel)));
-        RPF_CUDA(h, cand.alloc((size_t)Tg * n * 8));
-        RPF_CUDA(h, cand_total.alloc((size_t)Tg * 4));
-        RPF_CUDA(h, pivots.alloc((size_t)Tg * NTOP * MAXTD * 8));
-        RPF_CUDA(h, fill.alloc((size_t)Tg * NTOP * 4));
-        RPF_CUDA(h, binlo.alloc((size_t)Tg * L * 8));
-        RPF_CUDA(h, binscale.alloc((size_t)Tg * L * 8));
-        RPF_CUDA(h, nbdev.alloc((size_t)L * 4));
-        RPF_CUDA(h, cudaMemcpyAsync(nbdev.p, nb_level.data(), (size_t)L * 4, cudaMemcpyHostToDevice, h->stream));
+        label = (uint16_t*)h->ws_get(WS_LABEL, (size_t)Tg * n * 2);
+        hist = (uint32_t*)h->ws_get(WS_HIST, (size_t)Tg * HSZ * 4);
+        sel = (NodeSel*)h->ws_get(WS_SEL, (size_t)Tg * NTOP * sizeof(NodeSel));
+        cand = (ull*)h->ws_get(WS_CAND, (size_t)Tg * n * 8);
+        cand_total = (uint32_t*)h->ws_get(WS_CANDTOT, (size_t)Tg * 4);
+        pivots = (ull*)h->ws_get(WS_PIVOTS, (size_t)Tg * NTOP * MAXTD * 8);
+        fill = (uint32_t*)h->ws_get(WS_FILL, (size_t)Tg * NTOP * 4);
+        binlo = (double*)h->ws_get(WS_BINLO, (size_t)Tg * L * 8);
+        binscale = (double*)h->ws_get(WS_BINSC, (size_t)Tg * L * 8);
+        nbdev = (int*)h->ws_get(WS_NBDEV, (size_t)L * 4);
+        if (!label || !hist || !sel || !cand || !cand_total || !pivots || !fill || !binlo || !binscale || !nbdev) return RPF_ERR_NOMEM;
+        RPF_CUDA(h, cudaMemcpyAsync(nbdev, nb_level.data(), (size_t)L * 4, cudaMemcpyHostToDevice, h->stream));
     }
 
     // ---- bottom-phase tables: per level-s node, the BFS id range of its descendants at each deeper level
     int nnodes_s = 0, nlb = 0;
+    int2* range = nullptr; uint32_t* lvlpv = nullptr;
+    std::vector<int2> rg; std::vector<uint32_t> pv;
     if (s < tp.nlevels) {
         nnodes_s = (int)(tp.level_off[s + 1] - tp.level_off[s]);
         nlb = std::max(1, tp.nlevels - s);
-        std::vector<int2> rg((size_t)nnodes_s * nlb, make_int2(0, 0));
+        rg.assign((size_t)nnodes_s * nlb, make_int2(0, 0));
         for (int e = 0; e < nnodes_s; ++e) {
             int64_t lo = tp.level_off[s] + e, hi = lo + 1;
             for (int j = 0; j < nlb; ++j) {
@@ -799,40 +1210,43 @@ int rpf_build_impl(rpf_handle* h) {
                 lo = tp.child[fi]; hi = (int64_t)tp.child[li] + 2;
             }
         }
-        std::vector<uint32_t> pv(tp.nlevels);
+        pv.resize(tp.nlevels);
         for (int l = 0; l < tp.nlevels; ++l) pv[l] = next_pow2_host(std::max<uint32_t>(tp.lvl_maxsize[l], 1));
-        RPF_CUDA(h, range.alloc(rg.size() * sizeof(int2)));
-        RPF_CUDA(h, lvlpv.alloc(pv.size() * 4));
-        RPF_CUDA(h, cudaMemcpyAsync(range.p, rg.data(), rg.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
-        RPF_CUDA(h, cudaMemcpyAsync(lvlpv.p, pv.data(), pv.size() * 4, cudaMemcpyHostToDevice, h->stream));
-        RPF_CUDA(h, cudaStreamSynchronize(h->stream));   // host vectors go out of scope below
+        range = (int2*)h->ws_get(WS_RANGE, rg.size() * sizeof(int2));
+        lvlpv = (uint32_t*)h->ws_get(WS_LVLPV, pv.size() * 4);
+        if (!range || !lvlpv) return RPF_ERR_NOMEM;
+        RPF_CUDA(h, cudaMemcpyAsync(range, rg.data(), rg.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
+        RPF_CUDA(h, cudaMemcpyAsync(lvlpv, pv.data(), pv.size() * 4, cudaMemcpyHostToDevice, h->stream));
     }
+    // fast bottom kernel: needs non-empty children slots (minLeaf >= 1) and <= BOT2_TAB segments at the deepest level
+    int bot2_levels = 0; { int v = BOT2_TAB; while (v > 1) { v >>= 1; ++bot2_levels; } }
+    const bool fast_bottom = tp.minLeaf >= 1 && (L - s) <= bot2_levels && !h->force_generic_bottom;
 
     for (int t0 = 0; t0 < T; t0 += Tg) {
         const int tg = std::min(Tg, T - t0);
         // K1
-        RPF_CUDA(h, cudaMemsetAsync(kmin.p, 0xff, (size_t)tg * L * 8, h->stream));
-        RPF_CUDA(h, cudaMemsetAsync(kmax.p, 0x00, (size_t)tg * L * 8, h->stream));
-        int rc = rpf_project_launch(h, PH_PROJECT, h->dX, n, t0, tg, L, true, keys.p, kmin.as<ull>(), kmax.as<ull>());
+        RPF_CUDA(h, cudaMemsetAsync(kmin, 0xff, (size_t)tg * L * 8, h->stream));
+        RPF_CUDA(h, cudaMemsetAsync(kmax, 0x00, (size_t)tg * L * 8, h->stream));
+        int rc = rpf_project_launch(h, PH_PROJECT, h->dX, n, t0, tg, L, true, keys, kmin, kmax);
         if (rc) return rc;
 
         uint32_t* perm_g = h->d_perm + (int64_t)t0 * n;
         if (s_top > 0) {
             TopArgs A{};
             A.n = n; A.Tg = tg; A.L = L; A.NTOP = (int)NTOP; A.HSZ = (int)HSZ; A.MAXTD = MAXTD; A.gt0 = t0; A.nn_all = nn;
-            A.keys = keys.as<ull>(); A.label = label.as<uint16_t>(); A.child = h->d_node_child; A.nstart = h->d_node_start;
-            A.nsize = h->d_node_size; A.binlo = binlo.as<double>(); A.binscale = binscale.as<double>();
-            A.kmin = kmin.as<ull>(); A.kmax = kmax.as<ull>(); A.hist = hist.as<uint32_t>(); A.sel = sel.as<NodeSel>();
-            A.cand = cand.as<ull>(); A.cand_total = cand_total.as<uint32_t>(); A.pivots = pivots.as<ull>();
-            A.fill = fill.as<uint32_t>(); A.perm = perm_g; A.thr = h->d_thr; A.mlo = h->d_mlo; A.mhi = h->d_mhi;
-            RPF_LAUNCH(h, PH_MISC, k_bin_setup, (unsigned)((tg * L + 127) / 128), 128, 0, A, nbdev.as<int>(), s_top);
-            RPF_CUDA(h, cudaMemsetAsync(fill.p, 0, (size_t)tg * NTOP * 4, h->stream));
+            A.keys = keys; A.label = label; A.child = h->d_node_child; A.nstart = h->d_node_start;
+            A.nsize = h->d_node_size; A.binlo = binlo; A.binscale = binscale;
+            A.kmin = kmin; A.kmax = kmax; A.hist = hist; A.sel = sel;
+            A.cand = cand; A.cand_total = cand_total; A.pivots = pivots;
+            A.fill = fill; A.perm = perm_g; A.thr = h->d_thr; A.mlo = h->d_mlo; A.mhi = h->d_mhi;
+            RPF_LAUNCH(h, PH_MISC, k_bin_setup, (unsigned)((tg * L + 127) / 128), 128, 0, A, nbdev, s_top);
+            RPF_CUDA(h, cudaMemsetAsync(fill, 0, (size_t)tg * NTOP * 4, h->stream));
             const unsigned nchunks = (unsigned)((n + TOP_CH - 1) / TOP_CH);
             for (int l = 0; l < s_top; ++l) {
                 A.l = l; A.node0 = (int)tp.level_off[l]; A.nnodes = (int)(tp.level_off[l + 1] - tp.level_off[l]);
                 A.NB = nb_level[l]; A.smem_hist = smem_level[l];
-                RPF_CUDA(h, cudaMemsetAsync(hist.p, 0, (size_t)tg * HSZ * 4, h->stream));
-                RPF_CUDA(h, cudaMemsetAsync(cand_total.p, 0, (size_t)tg * 4, h->stream));
+                RPF_CUDA(h, cudaMemsetAsync(hist, 0, (size_t)tg * HSZ * 4, h->stream));
+                RPF_CUDA(h, cudaMemsetAsync(cand_total, 0, (size_t)tg * 4, h->stream));
                 dim3 gs(nchunks, (unsigned)tg), gn((unsigned)A.nnodes, (unsigned)tg);
                 const size_t hs = A.smem_hist ? (size_t)A.nnodes * A.NB * 4 : 0;
                 RPF_LAUNCH(h, PH_TOP_HIST, k_top_hist, gs, TOP_NT, hs, A);
@@ -851,20 +1265,33 @@ int rpf_build_impl(rpf_handle* h) {
         if (s < tp.nlevels) {
             BottomArgs B{};
             B.n = n; B.nn_all = nn; B.L = L; B.s = s; B.nlb = nlb; B.gt0 = t0; B.first_gid = (int)tp.level_off[s];
-            B.keys = keys.as<ull>(); B.perm = perm_g; B.child = h->d_node_child; B.nstart = h->d_node_start; B.nsize = h->d_node_size;
-            B.range = range.as<int2>(); B.lvl_pv = lvlpv.as<uint32_t>(); B.thr = h->d_thr; B.mlo = h->d_mlo; B.mhi = h->d_mhi;
+            B.keys = keys; B.perm = perm_g; B.child = h->d_node_child; B.nstart = h->d_node_start; B.nsize = h->d_node_size;
+            B.range = range; B.lvl_pv = lvlpv; B.thr = h->d_thr; B.mlo = h->d_mlo; B.mhi = h->d_mhi;
             int rc2;
-            switch (CAP) {
-                case 256: rc2 = launch_bottom<256, 128>(h, B, nnodes_s, tg); break;
-                case 1024: rc2 = launch_bottom<1024, 256>(h, B, nnodes_s, tg); break;
-                case 4096: rc2 = launch_bottom<4096, 512>(h, B, nnodes_s, tg); break;
-                case 8192: rc2 = launch_bottom<8192, 1024>(h, B, nnodes_s, tg); break;
-                default: return rpf_fail(h, RPF_ERR_ARG, "bottom_cap must be 256, 1024, 4096 or 8192");
+            if (fast_bottom) {
+                const unsigned slots = std::max(256u, next_pow2_host(tp.lvl_maxsize[s]));
+                switch (slots) {
+                    case 256: rc2 = launch_bottom_fast<32>(h, B, nnodes_s, tg); break;
+                    case 512: rc2 = launch_bottom_fast<64>(h, B, nnodes_s, tg); break;
+                    case 1024: rc2 = launch_bottom_fast<128>(h, B, nnodes_s, tg); break;
+                    case 2048: rc2 = launch_bottom_fast<256>(h, B, nnodes_s, tg); break;
+                    case 4096: rc2 = launch_bottom_fast<512>(h, B, nnodes_s, tg); break;
+                    case 8192: rc2 = launch_bottom_fast<1024>(h, B, nnodes_s, tg); break;
+                    default: return rpf_fail(h, RPF_ERR_ARG, "internal: bad bottom slot count");
+                }
+            } else {
+                switch (CAP) {
+                    case 256: rc2 = launch_bottom_generic<256, 128>(h, B, nnodes_s, tg); break;
+                    case 1024: rc2 = launch_bottom_generic<1024, 256>(h, B, nnodes_s, tg); break;
+                    case 4096: rc2 = launch_bottom_generic<4096, 512>(h, B, nnodes_s, tg); break;
+                    case 8192: rc2 = launch_bottom_generic<8192, 1024>(h, B, nnodes_s, tg); break;
+                    default: return rpf_fail(h, RPF_ERR_ARG, "bottom_cap must be 256, 1024, 4096 or 8192");
+                }
             }
             if (rc2) return rc2;
         }
     }
-    RPF_CUDA(h, cudaStreamSynchronize(h->stream));   // group buffers are freed on return
+    RPF_CUDA(h, cudaStreamSynchronize(h->stream));   // host staging vectors (rg, pv, nb_level) go out of scope
     return RPF_OK;
 }
 

@@ -50,6 +50,23 @@ int rpf_handle::call_end() {
     return RPF_OK;
 }
 
+void* rpf_handle::ws_get(int slot, size_t bytes) {
+    WsBuf& b = ws[slot];
+    if (bytes < 16) bytes = 16;
+    if (b.cap >= bytes) return b.p;
+    if (b.p) { cudaStreamSynchronize(stream); cudaFree(b.p); ws_bytes -= b.cap; b.p = nullptr; b.cap = 0; }
+    size_t want = bytes + bytes / 16;          // a little slack so slowly growing requests do not thrash
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) { want = bytes; e = cudaMalloc(&b.p, want); }
+    if (e != cudaSuccess) { b.p = nullptr; err = std::string("workspace cudaMalloc: ") + cudaGetErrorString(e); cudaGetLastError(); return nullptr; }
+    b.cap = want; ws_bytes += want;
+    return b.p;
+}
+void rpf_handle::ws_free_all() {
+    for (int i = 0; i < WS_COUNT; ++i) if (ws[i].p) { cudaFree(ws[i].p); ws[i].p = nullptr; ws[i].cap = 0; }
+    ws_bytes = 0;
+}
+
 static const char* kPhaseNames[PH_COUNT] = {
     "project", "top_hist", "top_pick", "top_compact", "top_finish", "top_ties", "top_relabel", "bottom",
     "q_project", "q_traverse", "q_knn", "q_candidates", "truth", "recall", "merge", "misc"};
@@ -125,7 +142,8 @@ static void free_hp_dev(rpf_handle* h) {
     if (h->d_hp_off) cudaFree(h->d_hp_off);
     if (h->d_hp_idx) cudaFree(h->d_hp_idx);
     if (h->d_hp_val) cudaFree(h->d_hp_val);
-    h->d_hp_off = nullptr; h->d_hp_idx = nullptr; h->d_hp_val = nullptr;
+    if (h->d_hp_pack) cudaFree(h->d_hp_pack);
+    h->d_hp_off = nullptr; h->d_hp_idx = nullptr; h->d_hp_val = nullptr; h->d_hp_pack = nullptr;
 }
 static void free_topo_dev(rpf_handle* h) {
     if (h->d_node_start) cudaFree(h->d_node_start);
@@ -140,6 +158,7 @@ static void free_forest_dev(rpf_handle* h) {
     if (h->d_mhi) cudaFree(h->d_mhi);
     if (h->d_perm) cudaFree(h->d_perm);
     h->d_thr = h->d_mlo = h->d_mhi = nullptr; h->d_perm = nullptr; h->built = false;
+    h->res_node_bytes = h->res_perm_bytes = 0;
 }
 
 static int upload_hyperplanes(rpf_handle* h) {
@@ -150,9 +169,17 @@ static int upload_hyperplanes(rpf_handle* h) {
     RPF_CUDA(h, cudaMalloc(&h->d_hp_idx, std::max<size_t>(nnz, 1) * 4));
     RPF_CUDA(h, cudaMalloc(&h->d_hp_val, std::max<size_t>(nnz, 1) * 8));
     RPF_CUDA(h, cudaMemcpy(h->d_hp_off, h->hp_off.data(), nrow * 8, cudaMemcpyHostToDevice));
+    RPF_CUDA(h, cudaMalloc(&h->d_hp_pack, std::max<size_t>(nnz, 1) * 16));
     if (nnz) {
         RPF_CUDA(h, cudaMemcpy(h->d_hp_idx, h->hp_idx.data(), nnz * 4, cudaMemcpyHostToDevice));
         RPF_CUDA(h, cudaMemcpy(h->d_hp_val, h->hp_val.data(), nnz * 8, cudaMemcpyHostToDevice));
+        std::vector<double> pack(nnz * 2);
+        for (size_t q = 0; q < nnz; ++q) {
+            pack[2 * q] = h->hp_val[q];
+            const int64_t ib = (int64_t)h->hp_idx[q];
+            std::memcpy(&pack[2 * q + 1], &ib, 8);      // index travels in the bit pattern of the second double
+        }
+        RPF_CUDA(h, cudaMemcpy(h->d_hp_pack, pack.data(), nnz * 16, cudaMemcpyHostToDevice));
     }
     return RPF_OK;
 }
@@ -187,6 +214,7 @@ void rpf_destroy(rpf_handle* h) {
     cudaStreamSynchronize(h->stream);
     if (h->ownX && h->dX) cudaFree((void*)h->dX);
     free_hp_dev(h); free_topo_dev(h); free_forest_dev(h);
+    h->ws_free_all();
     for (auto e : h->event_pool) cudaEventDestroy(e);
     if (h->ev_begin) cudaEventDestroy(h->ev_begin);
     if (h->ev_end) cudaEventDestroy(h->ev_end);
@@ -470,6 +498,13 @@ int rpf_get_profile(const rpf_handle* h, double* ms, int64_t* launches, int cap)
 }
 const char* rpf_phase_name(int i) { return (i >= 0 && i < PH_COUNT) ? kPhaseNames[i] : ""; }
 int64_t rpf_launch_count(const rpf_handle* h) { return h ? h->launches : -1; }
+int rpf_set_option(rpf_handle* h, const char* name, int64_t value) {
+    if (!h || !name) return RPF_ERR_ARG;
+    const std::string s(name);
+    if (s == "force_generic_bottom") { h->force_generic_bottom = value != 0; return RPF_OK; }
+    if (s == "release_workspace") { cudaStreamSynchronize(h->stream); h->ws_free_all(); return RPF_OK; }
+    return rpf_fail(h, RPF_ERR_ARG, "unknown option " + s);
+}
 int rpf_set_bottom_cap(rpf_handle* h, int32_t cap) {
     if (!h) return RPF_ERR_ARG;
     if (cap != 256 && cap != 1024 && cap != 4096 && cap != 8192) return rpf_fail(h, RPF_ERR_ARG, "bottom_cap must be 256, 1024, 4096 or 8192");

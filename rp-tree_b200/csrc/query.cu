@@ -12,16 +12,15 @@
 // HBM bound: one thread per candidate streams the candidate's row with 256-bit loads and accumulates
 // sum (x-q)^2 strictly left to right (no FMA) so distances, hence orderings, match the reference.
 #include "rpf_internal.h"
+#include "rpf_device.cuh"
 #include <algorithm>
 #include <vector>
-
-typedef unsigned long long ull;
 
 int rpf_project_launch(rpf_handle* h, int phase, const double* dX, int64_t n, int t0, int Tg, int L, bool ord, void* out,
                        ull* kmin, ull* kmax);
 
-__device__ __forceinline__ int q_ilog2(unsigned v) { return 31 - __clz(v); }
-__device__ __forceinline__ unsigned q_next_pow2(unsigned v) { return v <= 1 ? 1u : 1u << (32 - __clz(v - 1)); }
+__device__ __forceinline__ int q_ilog2(unsigned v) { return ilog2_pow2(v); }
+__device__ __forceinline__ unsigned q_next_pow2(unsigned v) { return next_pow2_u32(v); }
 
 // ---------------------------------------------------------------------------------------------------
 // descent
@@ -71,20 +70,44 @@ __global__ void k_traverse(const double* __restrict__ keysQ, int64_t nq, int T, 
 // exact distance
 // ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void ld256(const double* p, double& a, double& b, double& c, double& d) {
-    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
 }
-// sqrt (sum_j (x_j - q_j)^2), left fold from 0, separate roundings (Internal.hs:403-406)
+// four 256-bit loads in ONE asm statement: the compiler cannot interleave their uses, so every thread keeps
+// 128 bytes in flight (the kernel is DRAM-latency bound otherwise)
+__device__ __forceinline__ void ld1024(const double* p, double* x) {
+    asm volatile(
+        "ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%16];\n\t"
+        "ld.global.nc.v4.f64 {%4,%5,%6,%7}, [%16+32];\n\t"
+        "ld.global.nc.v4.f64 {%8,%9,%10,%11}, [%16+64];\n\t"
+        "ld.global.nc.v4.f64 {%12,%13,%14,%15}, [%16+96];"
+        : "=d"(x[0]), "=d"(x[1]), "=d"(x[2]), "=d"(x[3]), "=d"(x[4]), "=d"(x[5]), "=d"(x[6]), "=d"(x[7]),
+          "=d"(x[8]), "=d"(x[9]), "=d"(x[10]), "=d"(x[11]), "=d"(x[12]), "=d"(x[13]), "=d"(x[14]), "=d"(x[15])
+        : "l"(p));
+}
+// sqrt (sum_j (x_j - q_j)^2), left fold from 0, separate roundings (Internal.hs:403-406).
 __device__ __forceinline__ double dist_exact(const double* __restrict__ row, const double* __restrict__ sq, int d, bool vec) {
     double acc = 0.0;
     if (vec) {
-        for (int j = 0; j < d; j += 4) {
-            double x0, x1, x2, x3;
-            ld256(row + j, x0, x1, x2, x3);
-            const double d0 = __dsub_rn(x0, sq[j]), d1 = __dsub_rn(x1, sq[j + 1]), d2 = __dsub_rn(x2, sq[j + 2]), d3 = __dsub_rn(x3, sq[j + 3]);
-            acc = __dadd_rn(acc, __dmul_rn(d0, d0));
-            acc = __dadd_rn(acc, __dmul_rn(d1, d1));
-            acc = __dadd_rn(acc, __dmul_rn(d2, d2));
-            acc = __dadd_rn(acc, __dmul_rn(d3, d3));
+        int j = 0;
+        if (d >= 16) {
+            double x[16], y[16];
+            ld1024(row, x);
+            for (; j + 32 <= d; j += 16) {          // software pipeline: next 128 B requested before this batch is consumed
+                ld1024(row + j + 16, y);
+#pragma unroll
+                for (int u = 0; u < 16; ++u) { const double df = __dsub_rn(x[u], sq[j + u]); acc = __dadd_rn(acc, __dmul_rn(df, df)); }
+#pragma unroll
+                for (int u = 0; u < 16; ++u) x[u] = y[u];
+            }
+#pragma unroll
+            for (int u = 0; u < 16; ++u) { const double df = __dsub_rn(x[u], sq[j + u]); acc = __dadd_rn(acc, __dmul_rn(df, df)); }
+            j += 16;
+        }
+        for (; j < d; j += 4) {
+            double x[4];
+            ld256(row + j, x[0], x[1], x[2], x[3]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { const double df = __dsub_rn(x[u], sq[j + u]); acc = __dadd_rn(acc, __dmul_rn(df, df)); }
         }
     } else {
         for (int j = 0; j < d; ++j) {
@@ -101,7 +124,8 @@ __device__ __forceinline__ double dist_exact(const double* __restrict__ row, con
 // bitonic network reproduce the reference's STABLE sort (RPTree.hs:174).
 // ---------------------------------------------------------------------------------------------------
 #define KNN_NT 256
-#define KNN_BUF 4096
+#define KNN_BUF 2304   /* candidate entries per chunk (incl. the running best) */
+#define KNN_SREG 768   /* side region for the selected front */
 
 template <int NT>
 __device__ void sort3(ull* skey, uint32_t* spos, uint32_t* sid, unsigned m) {
@@ -155,6 +179,45 @@ __device__ unsigned keep_k(ull* skey, uint32_t* spos, uint32_t* sid, unsigned to
     return *s_n;
 }
 
+// Front selection: instead of sorting all `tot` entries, radix-select the value of rank r-1 (r = k, or 32k when
+// de-duplicating), compact the entries <= it into a side region, sort only those and keep k.  Falls back to the
+// full sort whenever that is not provably sufficient.  On exit entries [0, ret) of (skey,spos,sid) hold the result.
+template <int NT>
+__device__ unsigned topk_front(ull* skey, uint32_t* spos, uint32_t* sid, unsigned tot, unsigned k, int dedup,
+                               ull* rkey, uint32_t* rpos, uint32_t* rid, uint32_t* sh, ull* sh64, unsigned* s_n) {
+    unsigned r = dedup ? min(tot, 32u * k) : min(tot, k);
+    bool full = (r >= tot) || (r > KNN_SREG / 2);
+    unsigned cnt = 0;
+    if (!full) {
+        uint32_t cl, ce;
+        const ull v = cta_radix_select<NT>(tot, r - 1, [&](uint32_t i) { return skey[i]; }, sh, sh64, cl, ce);
+        cnt = cl + ce;
+        full = cnt > KNN_SREG;
+        if (!full) {
+            if (threadIdx.x == 0) *s_n = 0;
+            __syncthreads();
+            for (unsigned i = threadIdx.x; i < tot; i += NT) {
+                const ull kv = skey[i];
+                if (kv <= v) { const unsigned p = atomicAdd(s_n, 1u); rkey[p] = kv; rpos[p] = spos[i]; rid[p] = sid[i]; }
+            }
+            __syncthreads();
+            sort3<NT>(rkey, rpos, rid, cnt);
+            const unsigned nb = keep_k<NT>(rkey, rpos, rid, cnt, k, dedup, s_n);
+            __syncthreads();
+            if (dedup && nb < k && cnt < tot) full = true;      // not enough distinct distances in the front
+            else {
+                for (unsigned i = threadIdx.x; i < nb; i += NT) { skey[i] = rkey[i]; spos[i] = rpos[i]; sid[i] = rid[i]; }
+                __syncthreads();
+                return nb;
+            }
+        }
+    }
+    sort3<NT>(skey, spos, sid, tot);
+    const unsigned nb = keep_k<NT>(skey, spos, sid, tot, k, dedup, s_n);
+    __syncthreads();
+    return nb;
+}
+
 // exclusive prefix of slot sizes (nslots entries) -> pre[0..nslots]; all threads participate
 template <int NT>
 __device__ void slot_prefix(uint32_t* pre, unsigned nslots, uint32_t* part /*NT+1*/) {
@@ -206,11 +269,16 @@ __device__ __forceinline__ unsigned find_slot(const uint32_t* pre, unsigned nslo
 __global__ void __launch_bounds__(KNN_NT) k_knn(QArgs A) {
     __shared__ uint32_t part[KNN_NT + 1];
     __shared__ unsigned s_n;
+    __shared__ uint32_t sh[264];
+    __shared__ ull sh64;
     extern __shared__ unsigned char dyn[];
     ull* skey = (ull*)dyn;
-    uint32_t* spos = (uint32_t*)(skey + KNN_BUF);
+    ull* rkey = skey + KNN_BUF;
+    uint32_t* spos = (uint32_t*)(rkey + KNN_SREG);
     uint32_t* sid = spos + KNN_BUF;
-    double* sq = (double*)(sid + KNN_BUF);
+    uint32_t* rpos = sid + KNN_BUF;
+    uint32_t* rid = rpos + KNN_SREG;
+    double* sq = (double*)(rid + KNN_SREG);
     uint32_t* pre = (uint32_t*)(sq + ((A.d + 3) & ~3));
     const int64_t q = blockIdx.x;
     const int tid = threadIdx.x;
@@ -236,9 +304,7 @@ __global__ void __launch_bounds__(KNN_NT) k_knn(QArgs A) {
         }
         __syncthreads();
         const unsigned tot = nbest + m;
-        sort3<KNN_NT>(skey, spos, sid, tot);
-        nbest = keep_k<KNN_NT>(skey, spos, sid, tot, k, A.dedup, &s_n);
-        __syncthreads();
+        nbest = topk_front<KNN_NT>(skey, spos, sid, tot, k, A.dedup, rkey, rpos, rid, sh, &sh64, &s_n);
     }
     for (unsigned i = tid; i < k; i += KNN_NT) {
         const bool ok = i < nbest;
@@ -483,42 +549,39 @@ __global__ void __launch_bounds__(KNN_NT) k_merge(int G, int64_t nq, int k, int 
 }
 
 // ---------------------------------------------------------------------------------------------------
-// host side
+// host side (all device buffers come from the handle's persistent workspace)
 // ---------------------------------------------------------------------------------------------------
-struct QBuf {
-    void* p = nullptr;
-    ~QBuf() { if (p) cudaFree(p); }
-    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16); }
-    template <typename T> T* as() { return (T*)p; }
-};
+#define QWS(h, var, type, slot, bytes)                                  \
+    type* var = (type*)(h)->ws_get((slot), (bytes));                    \
+    if (!var) return RPF_ERR_NOMEM;
 
 // shared front half of every query entry point: upload Q, project, descend (with retry on fork overflow)
 struct QState {
-    QBuf dQ, keysQ, segs, cnt, maxcnt;
+    double* dQ = nullptr; double* keysQ = nullptr; uint32_t* segs = nullptr; uint32_t* cnt = nullptr; uint32_t* maxcnt = nullptr;
     int S = 2, Tq = 0;
 };
 
 static int run_descent(rpf_handle* h, const double* Q, int64_t nq, int t_only, QState& st) {
     const int L = h->topo.L_eff, T = h->T;
     st.Tq = t_only >= 0 ? 1 : T;
-    RPF_CUDA(h, st.dQ.alloc((size_t)nq * h->d * 8));
-    RPF_CUDA(h, cudaMemcpyAsync(st.dQ.p, Q, (size_t)nq * h->d * 8, cudaMemcpyHostToDevice, h->stream));
-    RPF_CUDA(h, st.keysQ.alloc((size_t)std::max(1, T * L) * nq * 8));
-    if (L > 0) { int rc = rpf_project_queries(h, st.dQ.as<double>(), nq, st.keysQ.as<double>()); if (rc) return rc; }
-    RPF_CUDA(h, st.cnt.alloc((size_t)nq * st.Tq * 4));
-    RPF_CUDA(h, st.maxcnt.alloc(4));
+    QWS(h, dQ, double, WS_Q, (size_t)nq * h->d * 8);
+    RPF_CUDA(h, cudaMemcpyAsync(dQ, Q, (size_t)nq * h->d * 8, cudaMemcpyHostToDevice, h->stream));
+    QWS(h, keysQ, double, WS_KEYSQ, (size_t)std::max(1, T * L) * nq * 8);
+    if (L > 0) { int rc = rpf_project_queries(h, dQ, nq, keysQ); if (rc) return rc; }
+    QWS(h, cnt, uint32_t, WS_CNT, (size_t)nq * st.Tq * 4);
+    QWS(h, maxcnt, uint32_t, WS_MAXCNT, 4);
+    st.dQ = dQ; st.keysQ = keysQ; st.cnt = cnt; st.maxcnt = maxcnt;
     while (true) {
-        RPF_CUDA(h, st.segs.alloc((size_t)nq * st.Tq * st.S * 4));
-        RPF_CUDA(h, cudaMemsetAsync(st.maxcnt.p, 0, 4, h->stream));
+        QWS(h, segs, uint32_t, WS_SEGS, (size_t)nq * st.Tq * st.S * 4);
+        st.segs = segs;
+        RPF_CUDA(h, cudaMemsetAsync(maxcnt, 0, 4, h->stream));
         const int64_t tot = nq * st.Tq;
-        RPF_LAUNCH(h, PH_Q_TRAVERSE, k_traverse, (unsigned)((tot + 127) / 128), 128, 0, st.keysQ.as<double>(), nq, T, L, h->topo.nnodes(),
-                   h->d_node_child, h->d_node_depth, h->d_thr, h->d_mlo, h->d_mhi, st.S, t_only, st.segs.as<uint32_t>(),
-                   st.cnt.as<uint32_t>(), st.maxcnt.as<uint32_t>());
+        RPF_LAUNCH(h, PH_Q_TRAVERSE, k_traverse, (unsigned)((tot + 127) / 128), 128, 0, keysQ, nq, T, L, h->topo.nnodes(),
+                   h->d_node_child, h->d_node_depth, h->d_thr, h->d_mlo, h->d_mhi, st.S, t_only, segs, cnt, maxcnt);
         uint32_t mx = 0;
-        RPF_CUDA(h, cudaMemcpyAsync(&mx, st.maxcnt.p, 4, cudaMemcpyDeviceToHost, h->stream));
+        RPF_CUDA(h, cudaMemcpyAsync(&mx, maxcnt, 4, cudaMemcpyDeviceToHost, h->stream));
         RPF_CUDA(h, cudaStreamSynchronize(h->stream));
         if (mx <= (uint32_t)st.S) break;
-        cudaFree(st.segs.p); st.segs.p = nullptr;
         st.S = (int)mx;          // a query forked into more leaves than the stride: redo with the exact maximum
     }
     return RPF_OK;
@@ -528,8 +591,8 @@ static QArgs make_qargs(rpf_handle* h, int64_t nq, const QState& st) {
     QArgs A{};
     A.n = h->n; A.nq = nq; A.nn = h->topo.nnodes(); A.d = h->d; A.T = h->T; A.S = st.S;
     A.vec = (h->d % 4 == 0) && (((uintptr_t)h->dX & 31) == 0);
-    A.X = h->dX; A.Q = (const double*)st.dQ.p; A.perm = h->d_perm; A.nstart = h->d_node_start; A.nsize = h->d_node_size;
-    A.segs = (const uint32_t*)st.segs.p; A.cnt = (const uint32_t*)st.cnt.p;
+    A.X = h->dX; A.Q = st.dQ; A.perm = h->d_perm; A.nstart = h->d_node_start; A.nsize = h->d_node_size;
+    A.segs = st.segs; A.cnt = st.cnt;
     return A;
 }
 
@@ -538,19 +601,18 @@ int rpf_knn_impl(rpf_handle* h, const double* Q, int64_t nq, int k, int dedup, d
     QState st;
     int rc = run_descent(h, Q, nq, -1, st);
     if (rc) return rc;
-    QBuf ddist, dids, dcount;
-    RPF_CUDA(h, ddist.alloc((size_t)nq * k * 8));
-    RPF_CUDA(h, dids.alloc((size_t)nq * k * 4));
-    RPF_CUDA(h, dcount.alloc((size_t)nq * 4));
+    QWS(h, ddist, double, WS_OUT_D, (size_t)nq * k * 8);
+    QWS(h, dids, uint32_t, WS_OUT_I, (size_t)nq * k * 4);
+    QWS(h, dcount, int32_t, WS_OUT_C, (size_t)nq * 4);
     QArgs A = make_qargs(h, nq, st);
-    A.k = k; A.dedup = dedup; A.dist = ddist.as<double>(); A.ids = dids.as<uint32_t>(); A.count = dcount.as<int32_t>();
-    const size_t dyn = (size_t)KNN_BUF * 16 + (size_t)((h->d + 3) & ~3) * 8 + ((size_t)h->T * st.S + 1) * 4;
+    A.k = k; A.dedup = dedup; A.dist = ddist; A.ids = dids; A.count = dcount;
+    const size_t dyn = (size_t)(KNN_BUF + KNN_SREG) * 16 + (size_t)((h->d + 3) & ~3) * 8 + ((size_t)h->T * st.S + 1) * 4;
     if (dyn > 200 * 1024) return rpf_fail(h, RPF_ERR_UNSUPPORTED, "knn: d / tree count too large for the query kernel's shared memory");
     RPF_CUDA(h, cudaFuncSetAttribute(k_knn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     RPF_LAUNCH(h, PH_Q_KNN, k_knn, (unsigned)nq, KNN_NT, dyn, A);
-    RPF_CUDA(h, cudaMemcpyAsync(dist, ddist.p, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, h->stream));
-    RPF_CUDA(h, cudaMemcpyAsync(ids, dids.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, h->stream));
-    if (count) RPF_CUDA(h, cudaMemcpyAsync(count, dcount.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, h->stream));
+    RPF_CUDA(h, cudaMemcpyAsync(dist, ddist, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, h->stream));
+    RPF_CUDA(h, cudaMemcpyAsync(ids, dids, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (count) RPF_CUDA(h, cudaMemcpyAsync(count, dcount, (size_t)nq * 4, cudaMemcpyDeviceToHost, h->stream));
     RPF_CUDA(h, cudaStreamSynchronize(h->stream));
     return RPF_OK;
 }
@@ -562,11 +624,10 @@ int rpf_candidates_impl(rpf_handle* h, const double* Q, int64_t nq, int t, int64
     if (rc) return rc;
     QArgs A = make_qargs(h, nq, st);
     if (off_out) {
-        QBuf dc;
-        RPF_CUDA(h, dc.alloc((size_t)nq * 8));
-        RPF_LAUNCH(h, PH_Q_CAND, k_cand_count, (unsigned)((nq + 127) / 128), 128, 0, A, st.Tq, dc.as<unsigned long long>());
+        QWS(h, dc, unsigned long long, WS_CANDCNT, (size_t)nq * 8);
+        RPF_LAUNCH(h, PH_Q_CAND, k_cand_count, (unsigned)((nq + 127) / 128), 128, 0, A, st.Tq, dc);
         std::vector<unsigned long long> c((size_t)nq);
-        RPF_CUDA(h, cudaMemcpyAsync(c.data(), dc.p, (size_t)nq * 8, cudaMemcpyDeviceToHost, h->stream));
+        RPF_CUDA(h, cudaMemcpyAsync(c.data(), dc, (size_t)nq * 8, cudaMemcpyDeviceToHost, h->stream));
         RPF_CUDA(h, cudaStreamSynchronize(h->stream));
         int64_t acc = 0;
         for (int64_t q = 0; q < nq; ++q) { off_out[q] = acc; acc += (int64_t)c[q]; }
@@ -576,14 +637,13 @@ int rpf_candidates_impl(rpf_handle* h, const double* Q, int64_t nq, int t, int64
     const int64_t total = off_in[nq];
     if (total == 0) return RPF_OK;
     if (!ids) return rpf_fail(h, RPF_ERR_ARG, "candidates: ids is NULL");
-    QBuf doff, dout;
-    RPF_CUDA(h, doff.alloc((size_t)(nq + 1) * 8));
-    RPF_CUDA(h, dout.alloc((size_t)total * 4));
-    RPF_CUDA(h, cudaMemcpyAsync(doff.p, off_in, (size_t)(nq + 1) * 8, cudaMemcpyHostToDevice, h->stream));
+    QWS(h, doff, int64_t, WS_CANDOFF, (size_t)(nq + 1) * 8);
+    QWS(h, dout, uint32_t, WS_CANDOUT, (size_t)total * 4);
+    RPF_CUDA(h, cudaMemcpyAsync(doff, off_in, (size_t)(nq + 1) * 8, cudaMemcpyHostToDevice, h->stream));
     const size_t dyn = ((size_t)st.Tq * st.S + 1) * 4;
     RPF_CUDA(h, cudaFuncSetAttribute(k_cand_fill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(dyn, 1024)));
-    RPF_LAUNCH(h, PH_Q_CAND, k_cand_fill, (unsigned)nq, KNN_NT, dyn, A, st.Tq, t, doff.as<int64_t>(), dout.as<uint32_t>());
-    RPF_CUDA(h, cudaMemcpyAsync(ids, dout.p, (size_t)total * 4, cudaMemcpyDeviceToHost, h->stream));
+    RPF_LAUNCH(h, PH_Q_CAND, k_cand_fill, (unsigned)nq, KNN_NT, dyn, A, st.Tq, t, doff, dout);
+    RPF_CUDA(h, cudaMemcpyAsync(ids, dout, (size_t)total * 4, cudaMemcpyDeviceToHost, h->stream));
     RPF_CUDA(h, cudaStreamSynchronize(h->stream));
     return RPF_OK;
 }
@@ -593,32 +653,29 @@ static int brute_device(rpf_handle* h, const double* dQ, int64_t nq, int k, doub
     const int64_t n = h->n;
     const int d = h->d;
     if (n == 0) return rpf_fail(h, RPF_ERR_STATE, "brute_knn: no points");
-    QBuf D;
-    RPF_CUDA(h, D.alloc((size_t)BF_TQ * n * 8));
+    QWS(h, D, ull, WS_BF_D, (size_t)BF_TQ * n * 8);
     const int vec = (d % 4 == 0) && (((uintptr_t)h->dX & 31) == 0);
     const size_t smem = (size_t)BF_TQ * d * 8;
     if (smem > 160 * 1024) return rpf_fail(h, RPF_ERR_UNSUPPORTED, "brute_knn: dimension too large");
     RPF_CUDA(h, cudaFuncSetAttribute(k_dist_all, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     for (int64_t q0 = 0; q0 < nq; q0 += BF_TQ) {
         const int nqt = (int)std::min<int64_t>(BF_TQ, nq - q0);
-        RPF_LAUNCH(h, PH_TRUTH, k_dist_all, (unsigned)((n + BF_NT - 1) / BF_NT), BF_NT, smem, h->dX, n, d, dQ, q0, nqt, D.as<ull>(), vec);
-        RPF_LAUNCH(h, PH_TRUTH, k_select_topk, (unsigned)nqt, 512, 0, D.as<ull>(), n, k, q0, d_dist, d_ids);
+        RPF_LAUNCH(h, PH_TRUTH, k_dist_all, (unsigned)((n + BF_NT - 1) / BF_NT), BF_NT, smem, h->dX, n, d, dQ, q0, nqt, D, vec);
+        RPF_LAUNCH(h, PH_TRUTH, k_select_topk, (unsigned)nqt, 512, 0, D, n, k, q0, d_dist, d_ids);
     }
-    RPF_CUDA(h, cudaStreamSynchronize(h->stream));
     return RPF_OK;
 }
 
 int rpf_brute_knn_impl(rpf_handle* h, const double* Q, int64_t nq, int k, double* dist, uint32_t* ids) {
     if (nq == 0) return RPF_OK;
-    QBuf dQ, dd, di;
-    RPF_CUDA(h, dQ.alloc((size_t)nq * h->d * 8));
-    RPF_CUDA(h, dd.alloc((size_t)nq * k * 8));
-    RPF_CUDA(h, di.alloc((size_t)nq * k * 4));
-    RPF_CUDA(h, cudaMemcpyAsync(dQ.p, Q, (size_t)nq * h->d * 8, cudaMemcpyHostToDevice, h->stream));
-    int rc = brute_device(h, dQ.as<double>(), nq, k, dd.as<double>(), di.as<uint32_t>());
+    QWS(h, dQ, double, WS_Q, (size_t)nq * h->d * 8);
+    QWS(h, dd, double, WS_TRUTH_D, (size_t)nq * k * 8);
+    QWS(h, di, uint32_t, WS_TRUTH_I, (size_t)nq * k * 4);
+    RPF_CUDA(h, cudaMemcpyAsync(dQ, Q, (size_t)nq * h->d * 8, cudaMemcpyHostToDevice, h->stream));
+    int rc = brute_device(h, dQ, nq, k, dd, di);
     if (rc) return rc;
-    RPF_CUDA(h, cudaMemcpyAsync(dist, dd.p, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, h->stream));
-    RPF_CUDA(h, cudaMemcpyAsync(ids, di.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, h->stream));
+    RPF_CUDA(h, cudaMemcpyAsync(dist, dd, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, h->stream));
+    RPF_CUDA(h, cudaMemcpyAsync(ids, di, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, h->stream));
     RPF_CUDA(h, cudaStreamSynchronize(h->stream));
     return RPF_OK;
 }
@@ -628,18 +685,17 @@ int rpf_recall_impl(rpf_handle* h, const double* Q, int64_t nq, int k, double* r
     QState st;
     int rc = run_descent(h, Q, nq, -1, st);
     if (rc) return rc;
-    QBuf dd, di, dr;
-    RPF_CUDA(h, dd.alloc((size_t)nq * k * 8));
-    RPF_CUDA(h, di.alloc((size_t)nq * k * 4));
-    RPF_CUDA(h, dr.alloc((size_t)nq * 8));
-    rc = brute_device(h, st.dQ.as<double>(), nq, k, dd.as<double>(), di.as<uint32_t>());
+    QWS(h, dd, double, WS_TRUTH_D, (size_t)nq * k * 8);
+    QWS(h, di, uint32_t, WS_TRUTH_I, (size_t)nq * k * 4);
+    QWS(h, dr, double, WS_RECALL, (size_t)nq * 8);
+    rc = brute_device(h, st.dQ, nq, k, dd, di);
     if (rc) return rc;
     QArgs A = make_qargs(h, nq, st);
     A.k = k;
     const size_t dyn = ((size_t)h->T * st.S + 1) * 4 + (size_t)h->T * 4;
     RPF_CUDA(h, cudaFuncSetAttribute(k_recall, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(dyn, 1024)));
-    RPF_LAUNCH(h, PH_RECALL, k_recall, (unsigned)nq, KNN_NT, dyn, A, di.as<uint32_t>(), dr.as<double>());
-    RPF_CUDA(h, cudaMemcpyAsync(recall_sum, dr.p, (size_t)nq * 8, cudaMemcpyDeviceToHost, h->stream));
+    RPF_LAUNCH(h, PH_RECALL, k_recall, (unsigned)nq, KNN_NT, dyn, A, di, dr);
+    RPF_CUDA(h, cudaMemcpyAsync(recall_sum, dr, (size_t)nq * 8, cudaMemcpyDeviceToHost, h->stream));
     RPF_CUDA(h, cudaStreamSynchronize(h->stream));
     return RPF_OK;
 }
@@ -647,20 +703,22 @@ int rpf_recall_impl(rpf_handle* h, const double* Q, int64_t nq, int k, double* r
 int rpf_merge_impl(rpf_handle* h, int G, int64_t nq, int k, int dedup, const double* dist, const uint32_t* ids,
                    const int32_t* count, double* dist_out, uint32_t* ids_out, int32_t* count_out) {
     if (nq == 0) return RPF_OK;
-    QBuf dd, di, dc, od, oi, oc;
     const size_t ne = (size_t)G * nq * k;
-    RPF_CUDA(h, dd.alloc(ne * 8)); RPF_CUDA(h, di.alloc(ne * 4)); RPF_CUDA(h, dc.alloc((size_t)G * nq * 4));
-    RPF_CUDA(h, od.alloc((size_t)nq * k * 8)); RPF_CUDA(h, oi.alloc((size_t)nq * k * 4)); RPF_CUDA(h, oc.alloc((size_t)nq * 4));
-    RPF_CUDA(h, cudaMemcpyAsync(dd.p, dist, ne * 8, cudaMemcpyHostToDevice, h->stream));
-    RPF_CUDA(h, cudaMemcpyAsync(di.p, ids, ne * 4, cudaMemcpyHostToDevice, h->stream));
-    RPF_CUDA(h, cudaMemcpyAsync(dc.p, count, (size_t)G * nq * 4, cudaMemcpyHostToDevice, h->stream));
+    QWS(h, dd, double, WS_MRG_D, ne * 8);
+    QWS(h, di, uint32_t, WS_MRG_I, ne * 4);
+    QWS(h, dc, int32_t, WS_MRG_C, (size_t)G * nq * 4);
+    QWS(h, od, double, WS_OUT_D, (size_t)nq * k * 8);
+    QWS(h, oi, uint32_t, WS_OUT_I, (size_t)nq * k * 4);
+    QWS(h, oc, int32_t, WS_OUT_C, (size_t)nq * 4);
+    RPF_CUDA(h, cudaMemcpyAsync(dd, dist, ne * 8, cudaMemcpyHostToDevice, h->stream));
+    RPF_CUDA(h, cudaMemcpyAsync(di, ids, ne * 4, cudaMemcpyHostToDevice, h->stream));
+    RPF_CUDA(h, cudaMemcpyAsync(dc, count, (size_t)G * nq * 4, cudaMemcpyHostToDevice, h->stream));
     const size_t dynm = (size_t)KNN_BUF * 16;
     RPF_CUDA(h, cudaFuncSetAttribute(k_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dynm));
-    RPF_LAUNCH(h, PH_MERGE, k_merge, (unsigned)nq, KNN_NT, dynm, G, nq, k, dedup, dd.as<double>(), di.as<uint32_t>(), dc.as<int32_t>(),
-               od.as<double>(), oi.as<uint32_t>(), oc.as<int32_t>());
-    RPF_CUDA(h, cudaMemcpyAsync(dist_out, od.p, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, h->stream));
-    RPF_CUDA(h, cudaMemcpyAsync(ids_out, oi.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, h->stream));
-    if (count_out) RPF_CUDA(h, cudaMemcpyAsync(count_out, oc.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, h->stream));
+    RPF_LAUNCH(h, PH_MERGE, k_merge, (unsigned)nq, KNN_NT, dynm, G, nq, k, dedup, dd, di, dc, od, oi, oc);
+    RPF_CUDA(h, cudaMemcpyAsync(dist_out, od, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, h->stream));
+    RPF_CUDA(h, cudaMemcpyAsync(ids_out, oi, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (count_out) RPF_CUDA(h, cudaMemcpyAsync(count_out, oc, (size_t)nq * 4, cudaMemcpyDeviceToHost, h->stream));
     RPF_CUDA(h, cudaStreamSynchronize(h->stream));
     return RPF_OK;
 }

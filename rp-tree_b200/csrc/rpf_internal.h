@@ -46,6 +46,16 @@ void build_topology(Topology& tp, int64_t n, int maxDepth, int minLeaf);
 
 struct ProfEvent { int phase; cudaEvent_t a, b; };
 
+// persistent device workspace (grow-only): no cudaMalloc/cudaFree inside the steady-state hot path
+enum rpf_ws_slot {
+    WS_KEYS = 0, WS_LABEL, WS_HIST, WS_SEL, WS_CAND, WS_CANDTOT, WS_PIVOTS, WS_FILL, WS_KMIN, WS_KMAX, WS_BINLO, WS_BINSC,
+    WS_NBDEV, WS_RANGE, WS_LVLPV, WS_HPPACK,
+    WS_Q, WS_KEYSQ, WS_SEGS, WS_CNT, WS_MAXCNT, WS_OUT_D, WS_OUT_I, WS_OUT_C, WS_BF_D, WS_TRUTH_D, WS_TRUTH_I, WS_RECALL,
+    WS_CANDCNT, WS_CANDOFF, WS_CANDOUT, WS_MRG_D, WS_MRG_I, WS_MRG_C,
+    WS_COUNT
+};
+struct WsBuf { void* p = nullptr; size_t cap = 0; };
+
 struct rpf_handle {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -59,6 +69,7 @@ struct rpf_handle {
     int T = 0, hpDepth = 0;
     std::vector<int64_t> hp_off; std::vector<int32_t> hp_idx; std::vector<double> hp_val;
     int64_t* d_hp_off = nullptr; int32_t* d_hp_idx = nullptr; double* d_hp_val = nullptr;
+    void* d_hp_pack = nullptr;   // (val, idx) pairs, 16 bytes each, CSR order
 
     // topology
     Topology topo;
@@ -69,6 +80,15 @@ struct rpf_handle {
     double *d_thr = nullptr, *d_mlo = nullptr, *d_mhi = nullptr;   // [T][nnodes]
     uint32_t* d_perm = nullptr;                                       // [T][n]
     bool leaf_order_exact = true;
+    size_t res_node_bytes = 0, res_perm_bytes = 0;
+    bool force_generic_bottom = false;   // test hook: run the generic (entry-table) bottom kernel
+
+    // workspace
+    WsBuf ws[WS_COUNT];
+    size_t ws_bytes = 0;
+    void* ws_get(int slot, size_t bytes);   // nullptr on allocation failure (err is set)
+    void ws_free_all();
+    int64_t hp_pack_rows = 0;
 
     // tuning
     int bottom_cap = 4096;

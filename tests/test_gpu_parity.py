@@ -17,11 +17,12 @@ def _mods():
     return R, orc
 
 
-def _build_pair(n, d, T, maxd, minl, pnz, kind="gauss", cap=None, seed=3):
+def _build_pair(n, d, T, maxd, minl, pnz, kind="gauss", cap=None, seed=3, generic=False):
     R, orc = _mods()
     X = make_data(n, d, seed, kind)
     hp = orc.gen_hyperplanes(1235137 + seed, T, maxd, pnz, d)
-    f = R.forestBatch(0, maxd, minl, T, pnz, d, X, hyperplanes=hp, bottom_cap=cap)
+    f = R.forestBatch(0, maxd, minl, T, pnz, d, X, hyperplanes=hp, bottom_cap=cap,
+                      options={"force_generic_bottom": 1} if generic else None)
     of = orc.Forest(X, hp, T, maxd, minl)
     return X, hp, f, of
 
@@ -40,12 +41,17 @@ BUILD_CASES = [
     pytest.param(9000, 12, 2, 3, 5, 0.4, "gauss", 1024, id="shallow-big-leaves"),
     pytest.param(40000, 24, 2, 12, 12, 0.25, "mixture", 4096, id="cap4096-top4"),
     pytest.param(70000, 8, 2, 13, 10, 0.5, "gauss", 8192, id="cap8192-top4"),
+    pytest.param(50000, 3, 2, 12, 9, 0.5, "integer", 4096, id="cap4096-integer-ties"),
+    pytest.param(30000, 2, 4, 11, 11, 0.4, "gauss", 4096, id="cap4096-empty-hyperplanes"),
+    pytest.param(3000, 1100, 2, 5, 40, 0.02, "gauss", 1024, id="large-d-direct-projection"),
+    pytest.param(2500, 300, 2, 6, 20, 0.05, "gauss", 1024, id="d300-r1-tile"),
 ]
 
 
+@pytest.mark.parametrize("generic", [False, True], ids=["fast-bottom", "generic-bottom"])
 @pytest.mark.parametrize("n,d,T,maxd,minl,pnz,kind,cap", BUILD_CASES)
-def test_build_parity(built, n, d, T, maxd, minl, pnz, kind, cap):
-    X, hp, f, of = _build_pair(n, d, T, maxd, minl, pnz, kind, cap)
+def test_build_parity(built, n, d, T, maxd, minl, pnz, kind, cap, generic):
+    X, hp, f, of = _build_pair(n, d, T, maxd, minl, pnz, kind, cap, generic=generic)
     order = f.leafOrderExact()
     problems = []
     for t in range(T):
