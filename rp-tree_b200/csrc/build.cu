@@ -294,6 +294,50 @@ __device__ __forceinline__ int point_node(const TopArgs& A, const uint16_t* lab,
     return nl;
 }
 
+// ---- streaming access to the points of one tree: 4 points per thread per step (one 32-byte key load + one 8-byte
+// label load), two steps in flight.  Falls back to scalar accesses when the rows are not 32-byte aligned (n % 4 != 0).
+struct Pt4 { ull k[4]; uint16_t g[4]; };
+__device__ __forceinline__ void load_pt4(const TopArgs& A, const ull* __restrict__ keys, const uint16_t* lab, int64_t i, Pt4& p) {
+    asm("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(p.k[0]), "=l"(p.k[1]), "=l"(p.k[2]), "=l"(p.k[3]) : "l"(keys + i));
+    if (A.l > 0) {
+        const uint2 q = *(const uint2*)(lab + i);
+        p.g[0] = (uint16_t)(q.x & 0xffff); p.g[1] = (uint16_t)(q.x >> 16); p.g[2] = (uint16_t)(q.y & 0xffff); p.g[3] = (uint16_t)(q.y >> 16);
+    } else {
+        p.g[0] = p.g[1] = p.g[2] = p.g[3] = 0;
+    }
+}
+// local node index of a point sitting in node g, or -1 when g is not an internal node of level A.l
+__device__ __forceinline__ int node_of(const TopArgs& A, int g) {
+    const int nl = g - A.node0;
+    if ((unsigned)nl >= (unsigned)A.nnodes) return -1;
+    if (__ldg(A.child + g) < 0) return -1;
+    return nl;
+}
+template <typename F>
+__device__ __forceinline__ void stream_points(const TopArgs& A, const ull* __restrict__ keys, const uint16_t* lab, int64_t i0, int64_t i1, F&& f) {
+    if ((A.n & 3) == 0) {
+        const int64_t step = 4 * TOP_NT;
+        int64_t i = i0 + 4 * (int64_t)threadIdx.x;
+        for (; i + step < i1; i += 2 * step) {
+            Pt4 a, b;
+            load_pt4(A, keys, lab, i, a);
+            load_pt4(A, keys, lab, i + step, b);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) f(i + u, a.k[u], (int)a.g[u]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) f(i + step + u, b.k[u], (int)b.g[u]);
+        }
+        if (i < i1) {
+            Pt4 a;
+            load_pt4(A, keys, lab, i, a);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) f(i + u, a.k[u], (int)a.g[u]);
+        }
+    } else {
+        for (int64_t i = i0 + threadIdx.x; i < i1; i += TOP_NT) f(i, keys[i], A.l == 0 ? 0 : (int)lab[i]);
+    }
+}
+
 __global__ void __launch_bounds__(TOP_NT) k_top_hist(TopArgs A) {
     extern __shared__ uint32_t sh[];
     const int t = blockIdx.y, tid = threadIdx.x;
@@ -307,13 +351,13 @@ __global__ void __launch_bounds__(TOP_NT) k_top_hist(TopArgs A) {
         for (int j = tid; j < tot; j += TOP_NT) sh[j] = 0;
         __syncthreads();
     }
-    for (int64_t i = i0 + tid; i < i1; i += TOP_NT) {
-        int nl = point_node(A, lab, i);
-        if (nl < 0) continue;
-        int b = key_bin(keys[i], lo, sc, NB);
+    stream_points(A, keys, lab, i0, i1, [&](int64_t, ull kv, int g) {
+        const int nl = node_of(A, g);
+        if (nl < 0) return;
+        const int b = key_bin(kv, lo, sc, NB);
         if (A.smem_hist) atomicAdd(&sh[nl * NB + b], 1u);
         else atomicAdd(&gh[nl * NB + b], 1u);
-    }
+    });
     if (A.smem_hist) {
         __syncthreads();
         for (int j = tid; j < tot; j += TOP_NT) { uint32_t v = sh[j]; if (v) atomicAdd(&gh[j], v); }
@@ -365,17 +409,16 @@ __global__ void __launch_bounds__(TOP_NT) k_top_compact(TopArgs A) {
         __syncthreads();
     }
     ull* cand = A.cand + (int64_t)t * A.n;
-    for (int64_t i = i0 + tid; i < i1; i += TOP_NT) {
-        int nl = point_node(A, lab, i);
-        if (nl < 0) continue;
-        ull kv = keys[i];
-        int b = key_bin(kv, lo, sc, A.NB);
-        int sb = cached ? s_bin[nl] : sel[nl].sel_bin;
+    stream_points(A, keys, lab, i0, i1, [&](int64_t, ull kv, int g) {
+        const int nl = node_of(A, g);
+        if (nl < 0) return;
+        const int b = key_bin(kv, lo, sc, A.NB);
+        const int sb = cached ? s_bin[nl] : sel[nl].sel_bin;
         if (b == sb) {
-            uint32_t pos = atomicAdd(&sel[nl].cand_fill, 1u);
+            const uint32_t pos = atomicAdd(&sel[nl].cand_fill, 1u);
             cand[sel[nl].cand_off + pos] = kv;
         }
-    }
+    });
 }
 
 // one CTA per (node, tree): exact order statistic inside the median bin
@@ -499,12 +542,11 @@ __global__ void __launch_bounds__(TOP_NT) k_top_relabel(TopArgs A, int last) {
     }
     uint32_t* fill = A.fill + (int64_t)t * A.NTOP;
     uint32_t* perm = A.perm + (int64_t)t * A.n;
-    for (int64_t i = i0 + tid; i < i1; i += TOP_NT) {
-        int g = A.l == 0 ? 0 : (int)lab[i];
-        int nl = g - A.node0;
-        int ch = ((unsigned)nl < (unsigned)A.nnodes) ? __ldg(A.child + g) : -1;
+    // returns the point's node after this level's split (unchanged when it does not sit in a splitting node)
+    auto relabel_one = [&](int64_t i, ull kv, int g) -> int {
+        const int nl = g - A.node0;
+        const int ch = ((unsigned)nl < (unsigned)A.nnodes) ? __ldg(A.child + g) : -1;
         if (ch >= 0) {
-            const ull kv = keys[i];
             const ull thr = cached ? s_thr[nl] : sel[nl].thr;
             bool left = kv < thr;
             if (kv == thr) {
@@ -527,12 +569,38 @@ __global__ void __launch_bounds__(TOP_NT) k_top_relabel(TopArgs A, int last) {
                 else if (kv < sel[nl].succ) atomicMin(&sel[nl].succ, kv);
             }
             g = ch + (left ? 0 : 1);
-            lab[i] = (uint16_t)g;
         }
         if (last) {
-            uint32_t pos = atomicAdd(&fill[g], 1u);
+            const uint32_t pos = atomicAdd(&fill[g], 1u);
             perm[A.nstart[g] + pos] = (uint32_t)i;
         }
+        return g;
+    };
+    if ((A.n & 3) == 0) {
+        const int64_t step = 4 * TOP_NT;
+        int64_t i = i0 + 4 * (int64_t)tid;
+        for (; i + step < i1; i += 2 * step) {
+            Pt4 a, b;
+            load_pt4(A, keys, lab, i, a);
+            load_pt4(A, keys, lab, i + step, b);
+            uint32_t ga[4], gb[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) ga[u] = (uint32_t)relabel_one(i + u, a.k[u], (int)a.g[u]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) gb[u] = (uint32_t)relabel_one(i + step + u, b.k[u], (int)b.g[u]);
+            *(uint2*)(lab + i) = make_uint2(ga[0] | (ga[1] << 16), ga[2] | (ga[3] << 16));
+            *(uint2*)(lab + i + step) = make_uint2(gb[0] | (gb[1] << 16), gb[2] | (gb[3] << 16));
+        }
+        if (i < i1) {
+            Pt4 a;
+            load_pt4(A, keys, lab, i, a);
+            uint32_t ga[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) ga[u] = (uint32_t)relabel_one(i + u, a.k[u], (int)a.g[u]);
+            *(uint2*)(lab + i) = make_uint2(ga[0] | (ga[1] << 16), ga[2] | (ga[3] << 16));
+        }
+    } else {
+        for (int64_t i = i0 + tid; i < i1; i += TOP_NT) lab[i] = (uint16_t)relabel_one(i, keys[i], A.l == 0 ? 0 : (int)lab[i]);
     }
     if (cached) {
         __syncthreads();

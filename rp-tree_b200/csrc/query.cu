@@ -182,17 +182,17 @@ __device__ unsigned keep_k(ull* skey, uint32_t* spos, uint32_t* sid, unsigned to
 // Front selection: instead of sorting all `tot` entries, radix-select the value of rank r-1 (r = k, or 32k when
 // de-duplicating), compact the entries <= it into a side region, sort only those and keep k.  Falls back to the
 // full sort whenever that is not provably sufficient.  On exit entries [0, ret) of (skey,spos,sid) hold the result.
-template <int NT>
+template <int NT, int SREG = KNN_SREG>
 __device__ unsigned topk_front(ull* skey, uint32_t* spos, uint32_t* sid, unsigned tot, unsigned k, int dedup,
                                ull* rkey, uint32_t* rpos, uint32_t* rid, uint32_t* sh, ull* sh64, unsigned* s_n) {
     unsigned r = dedup ? min(tot, 32u * k) : min(tot, k);
-    bool full = (r >= tot) || (r > KNN_SREG / 2);
+    bool full = (r >= tot) || (r > SREG / 2);
     unsigned cnt = 0;
     if (!full) {
         uint32_t cl, ce;
         const ull v = cta_radix_select<NT>(tot, r - 1, [&](uint32_t i) { return skey[i]; }, sh, sh64, cl, ce);
         cnt = cl + ce;
-        full = cnt > KNN_SREG;
+        full = cnt > SREG;
         if (!full) {
             if (threadIdx.x == 0) *s_n = 0;
             __syncthreads();
@@ -307,6 +307,139 @@ __global__ void __launch_bounds__(KNN_NT) k_knn(QArgs A) {
         nbest = topk_front<KNN_NT>(skey, spos, sid, tot, k, A.dedup, rkey, rpos, rid, sh, &sh64, &s_n);
     }
     for (unsigned i = tid; i < k; i += KNN_NT) {
+        const bool ok = i < nbest;
+        A.dist[q * k + i] = ok ? __longlong_as_double((long long)skey[i]) : __longlong_as_double(0x7ff0000000000000LL);
+        A.ids[q * k + i] = ok ? sid[i] : 0xffffffffu;
+    }
+    if (tid == 0 && A.count) A.count[q] = (int32_t)nbest;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// knn, B200 path: candidate rows are gathered by the TMA engine (cp.async.bulk, one 8d-byte bulk copy per row)
+// into a 2-stage shared-memory ring guarded by mbarriers; a producer warp resolves candidate -> row id and issues
+// the copies, one consumer warp per stage folds each staged row into its exact distance (one lane per row, strictly
+// left to right).  Per-thread 32-byte gathers are limited by the number of outstanding L1 requests (~1.7 TB/s
+// measured); bulk copies move whole rows and bypass that limit.
+// ---------------------------------------------------------------------------------------------------
+#define KT_NT 256
+#define KT_STAGES 2
+#define KT_BUF 1280      /* candidate entries per chunk (incl. the running best) */
+#define KT_SREG 512
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t a = smem_u32(bar);
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(KT_NT) k_knn_tma(QArgs A, int rows_per_stage, int pitch /* bytes, multiple of 16 */) {
+    __shared__ uint32_t part[KT_NT + 1];
+    __shared__ unsigned s_n;
+    __shared__ uint32_t sh[264];
+    __shared__ ull sh64;
+    __shared__ __align__(8) uint64_t full_bar[KT_STAGES], empty_bar[KT_STAGES];
+    extern __shared__ __align__(16) unsigned char dyn[];
+    unsigned char* stage_buf = dyn;                                              // [KT_STAGES][rows][pitch]
+    ull* skey = (ull*)(dyn + (size_t)KT_STAGES * rows_per_stage * pitch);
+    ull* rkey = skey + KT_BUF;
+    uint32_t* spos = (uint32_t*)(rkey + KT_SREG);
+    uint32_t* sid = spos + KT_BUF;
+    uint32_t* rpos = sid + KT_BUF;
+    uint32_t* rid = rpos + KT_SREG;
+    double* sq = (double*)(rid + KT_SREG);
+    uint32_t* pre = (uint32_t*)(sq + ((A.d + 3) & ~3));
+    const int64_t q = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned nslots = (unsigned)A.T * A.S;
+    const int R = rows_per_stage;
+    const uint32_t row_bytes = (uint32_t)A.d * 8u;
+
+    if (tid == 0) {
+        for (int s2 = 0; s2 < KT_STAGES; ++s2) { mbar_init(&full_bar[s2], 1); mbar_init(&empty_bar[s2], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    for (int j = tid; j < A.d; j += KT_NT) sq[j] = A.Q[q * A.d + j];
+    load_slots(A, q, A.T, pre, KT_NT);
+    slot_prefix<KT_NT>(pre, nslots, part);
+    const uint32_t C = pre[nslots];
+    const unsigned k = (unsigned)A.k, CHK = KT_BUF - k;
+    unsigned nbest = 0;
+    uint32_t uses = 0;            // tiles issued so far (all roles advance it identically)
+    for (uint32_t base = 0; base < C; base += CHK) {
+        const unsigned m = min((uint32_t)CHK, C - base);
+        const unsigned ntiles = (m + R - 1) / R;
+        if (warp == 0) {
+            // ---- producer
+            for (unsigned ti = 0; ti < ntiles; ++ti) {
+                const uint32_t u = uses + ti, st = u % KT_STAGES, round = u / KT_STAGES;
+                if (round > 0) mbar_wait(&empty_bar[st], (round - 1) & 1);
+                const unsigned j = ti * R + lane;
+                const bool valid = lane < R && j < m;
+                uint32_t id = 0;
+                if (valid) {
+                    const uint32_t c = base + j;
+                    const unsigned slot = find_slot(pre, nslots, c);
+                    const int tt = slot / A.S;
+                    const uint32_t g = A.segs[(q * A.T + tt) * (int64_t)A.S + (slot % A.S)];
+                    id = A.perm[(int64_t)tt * A.n + A.nstart[g] + (c - pre[slot])];
+                    spos[nbest + j] = c;
+                    sid[nbest + j] = id;
+                }
+                const unsigned nrows = min((unsigned)R, m - ti * R);
+                if (lane == 0) mbar_arrive_expect_tx(&full_bar[st], nrows * row_bytes);
+                __syncwarp();
+                if (valid) bulk_g2s(stage_buf + ((size_t)st * R + lane) * pitch, A.X + (int64_t)id * A.d, row_bytes, &full_bar[st]);
+            }
+        } else if (warp <= KT_STAGES) {
+            // ---- consumer of stage warp-1
+            const uint32_t st = warp - 1;
+            for (unsigned ti = 0; ti < ntiles; ++ti) {
+                const uint32_t u = uses + ti;
+                if (u % KT_STAGES != st) continue;
+                mbar_wait(&full_bar[st], (u / KT_STAGES) & 1);
+                const unsigned j = ti * R + lane;
+                if (lane < R && j < m) {
+                    const double2* row = (const double2*)(stage_buf + ((size_t)st * R + lane) * pitch);
+                    const double2* q2 = (const double2*)sq;
+                    double acc = 0.0;
+                    const int d2 = A.d >> 1;
+#pragma unroll 4
+                    for (int jj = 0; jj < d2; ++jj) {
+                        const double2 x = row[jj], y = q2[jj];
+                        const double d0 = __dsub_rn(x.x, y.x), d1 = __dsub_rn(x.y, y.y);
+                        acc = __dadd_rn(acc, __dmul_rn(d0, d0));
+                        acc = __dadd_rn(acc, __dmul_rn(d1, d1));
+                    }
+                    skey[nbest + j] = (ull)__double_as_longlong(__dsqrt_rn(acc));
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty_bar[st]);
+            }
+        }
+        uses += ntiles;
+        __syncthreads();
+        const unsigned tot = nbest + m;
+        nbest = topk_front<KT_NT, KT_SREG>(skey, spos, sid, tot, k, A.dedup, rkey, rpos, rid, sh, &sh64, &s_n);
+    }
+    for (unsigned i = tid; i < k; i += KT_NT) {
         const bool ok = i < nbest;
         A.dist[q * k + i] = ok ? __longlong_as_double((long long)skey[i]) : __longlong_as_double(0x7ff0000000000000LL);
         A.ids[q * k + i] = ok ? sid[i] : 0xffffffffu;
@@ -606,10 +739,23 @@ int rpf_knn_impl(rpf_handle* h, const double* Q, int64_t nq, int k, int dedup, d
     QWS(h, dcount, int32_t, WS_OUT_C, (size_t)nq * 4);
     QArgs A = make_qargs(h, nq, st);
     A.k = k; A.dedup = dedup; A.dist = ddist; A.ids = dids; A.count = dcount;
-    const size_t dyn = (size_t)(KNN_BUF + KNN_SREG) * 16 + (size_t)((h->d + 3) & ~3) * 8 + ((size_t)h->T * st.S + 1) * 4;
-    if (dyn > 200 * 1024) return rpf_fail(h, RPF_ERR_UNSUPPORTED, "knn: d / tree count too large for the query kernel's shared memory");
-    RPF_CUDA(h, cudaFuncSetAttribute(k_knn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-    RPF_LAUNCH(h, PH_Q_KNN, k_knn, (unsigned)nq, KNN_NT, dyn, A);
+    // TMA path: rows are 16-byte multiples and a 2-stage ring of up to 32 rows fits next to the selection buffers
+    const size_t tail = (size_t)((h->d + 3) & ~3) * 8 + ((size_t)h->T * st.S + 1) * 4;
+    const int pitch = h->d * 8 + 16;
+    int rows = (int)std::min<size_t>(32, (size_t)(72 * 1024) / ((size_t)KT_STAGES * pitch));
+    const size_t dyn_tma = (size_t)KT_STAGES * rows * pitch + (size_t)(KT_BUF + KT_SREG) * 16 + tail;
+    const bool use_tma = (h->d % 2 == 0) && rows >= 1 && k <= KT_BUF / 2 && dyn_tma <= 110 * 1024 && !h->force_simple_knn &&
+                         (((uintptr_t)h->dX & 15) == 0);
+    if (use_tma) {
+        RPF_CUDA(h, cudaFuncSetAttribute(k_knn_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_tma));
+        RPF_CUDA(h, cudaFuncSetAttribute(k_knn_tma, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        RPF_LAUNCH(h, PH_Q_KNN, k_knn_tma, (unsigned)nq, KT_NT, dyn_tma, A, rows, pitch);
+    } else {
+        const size_t dyn = (size_t)(KNN_BUF + KNN_SREG) * 16 + tail;
+        if (dyn > 200 * 1024) return rpf_fail(h, RPF_ERR_UNSUPPORTED, "knn: d / tree count too large for the query kernel's shared memory");
+        RPF_CUDA(h, cudaFuncSetAttribute(k_knn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+        RPF_LAUNCH(h, PH_Q_KNN, k_knn, (unsigned)nq, KNN_NT, dyn, A);
+    }
     RPF_CUDA(h, cudaMemcpyAsync(dist, ddist, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, h->stream));
     RPF_CUDA(h, cudaMemcpyAsync(ids, dids, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, h->stream));
     if (count) RPF_CUDA(h, cudaMemcpyAsync(count, dcount, (size_t)nq * 4, cudaMemcpyDeviceToHost, h->stream));

@@ -112,13 +112,17 @@ QUERY_CASES = [
     pytest.param(20000, 32, 6, 10, 16, 0.3, "mixture", None, id="mixture"),
     pytest.param(4000, 5, 3, 9, 7, 0.6, "dupes", 256, id="dupes"),
     pytest.param(3000, 3, 8, 8, 10, 0.7, "integer", 256, id="integer"),
+    pytest.param(6000, 128, 40, 7, 30, 0.1, "mixture", None, id="d128-T40-chunked"),
+    pytest.param(3000, 600, 4, 6, 30, 0.05, "gauss", None, id="d600-small-ring"),
 ]
 
 
+@pytest.mark.parametrize("simple_knn", [False, True], ids=["tma-knn", "gather-knn"])
 @pytest.mark.parametrize("n,d,T,maxd,minl,pnz,kind,cap", QUERY_CASES)
-def test_candidates_knn_recall_parity(built, n, d, T, maxd, minl, pnz, kind, cap):
+def test_candidates_knn_recall_parity(built, n, d, T, maxd, minl, pnz, kind, cap, simple_knn):
     R, orc = _mods()
     X, hp, f, of = _build_pair(n, d, T, maxd, minl, pnz, kind, cap)
+    f.setOption("force_simple_knn", int(simple_knn))
     rng = np.random.default_rng(17)
     nq = 40
     Q = X[rng.integers(0, n, size=nq)] + (0.05 * rng.normal(size=(nq, d)) if kind != "integer" else 0.0)
