@@ -127,9 +127,7 @@ def run_ours(args):
     n, d, T, k, nq = W["n"], W["d"], W["ntrees"], W["k"], W["nq"]
     cfg = R.rpTreeCfg(W["min_leaf"], n, d)
     maxd = cfg.fpMaxTreeDepth
-    per = (T + world - 1) // world
-    t_first = min(rank * per, T)
-    t_local = max(0, min(T, t_first + per) - t_first)
+    t_first, t_local = R.dist.shard_trees(T, world, rank)
     assert t_local > 0, "more ranks than trees"
 
     # synthetic inputs in PINNED host memory (so the e2e H2D is a real DMA)
@@ -155,6 +153,8 @@ def run_ours(args):
         return float(t.item())
 
     f = R.RPForest(local_rank)
+    if os.environ.get("RPF_BOTTOM_CAP"):
+        f.setBottomCap(int(os.environ["RPF_BOTTOM_CAP"]))
     f.setHyperplanes(hp, t_local, maxd)
     f.setPoints(X)                      # resident in HBM before the timed region (the `value` arm)
     merger = f
@@ -166,13 +166,7 @@ def run_ours(args):
         if dist is None:
             return ms, (dd, ii, cc), 0.0
         t0 = time.perf_counter()
-        gd = [torch.empty((nq, k), dtype=torch.float64, device=dev) for _ in range(world)]
-        gi = [torch.empty((nq, k), dtype=torch.int32, device=dev) for _ in range(world)]
-        gc = [torch.empty((nq,), dtype=torch.int32, device=dev) for _ in range(world)]
-        dist.all_gather(gd, torch.from_numpy(dd).to(dev))
-        dist.all_gather(gi, torch.from_numpy(ii.view(np.int32)).to(dev))
-        dist.all_gather(gc, torch.from_numpy(cc).to(dev))
-        D = torch.stack(gd).cpu().numpy(); I = torch.stack(gi).cpu().numpy().view(np.uint32); Cn = torch.stack(gc).cpu().numpy()
+        D, I, Cn = R.dist.gather_topk(dd, ii, cc, device=dev)     # NCCL all-gather over NVLink
         out = merger.mergeTopk(D, I, Cn, dedup=False)
         ms += merger.lastDeviceMs()
         return ms, out, (time.perf_counter() - t0) * 1e3
@@ -219,12 +213,8 @@ def run_ours(args):
         t0 = time.perf_counter()
         dd, ii, cc = g.knnBatch(Q, k)                            # H2D queries, D2H results
         if dist is not None:
-            gd = [torch.empty((nq, k), dtype=torch.float64, device=dev) for _ in range(world)]
-            gi = [torch.empty((nq, k), dtype=torch.int32, device=dev) for _ in range(world)]
-            gc = [torch.empty((nq,), dtype=torch.int32, device=dev) for _ in range(world)]
-            dist.all_gather(gd, torch.from_numpy(dd).to(dev)); dist.all_gather(gi, torch.from_numpy(ii.view(np.int32)).to(dev))
-            dist.all_gather(gc, torch.from_numpy(cc).to(dev))
-            g.mergeTopk(torch.stack(gd).cpu().numpy(), torch.stack(gi).cpu().numpy().view(np.uint32), torch.stack(gc).cpu().numpy())
+            D, I, Cn = R.dist.gather_topk(dd, ii, cc, device=dev)
+            g.mergeTopk(D, I, Cn)
         barrier()
         e2e_q.append(time.perf_counter() - t0)
         g.close()
@@ -244,7 +234,7 @@ def run_ours(args):
     C_mean = float(off[-1]) / 512.0
     tp = f.topology()
     L = int(tp["depth"][tp["child"] >= 0].max()) + 1
-    cap = 4096
+    cap = int(os.environ.get("RPF_BOTTOM_CAP", "1024"))      # engine default (rpf_set_bottom_cap)
     lvl_max = [int(tp["seg_size"][tp["depth"] == l].max()) for l in range(int(tp["depth"].max()) + 1)]
     s_top = next((l for l, m in enumerate(lvl_max) if m <= cap), len(lvl_max))
     s_top = min(s_top, L)
@@ -274,16 +264,10 @@ def run_ours(args):
         rs = t.cpu().numpy()
     recall_ref_def = float(np.mean(rs / T))
     bd, bi = f.bruteKnnBatch(Q[:ns], k)
-    if dist is None:
-        pd_, pi_, pc_ = f.knnBatch(Q[:ns], k, dedup=True)
-    else:
-        pd_, pi_, pc_ = f.knnBatch(Q[:ns], k, dedup=True)
-        gd = [torch.empty((ns, k), dtype=torch.float64, device=dev) for _ in range(world)]
-        gi = [torch.empty((ns, k), dtype=torch.int32, device=dev) for _ in range(world)]
-        gc = [torch.empty((ns,), dtype=torch.int32, device=dev) for _ in range(world)]
-        dist.all_gather(gd, torch.from_numpy(pd_).to(dev)); dist.all_gather(gi, torch.from_numpy(pi_.view(np.int32)).to(dev))
-        dist.all_gather(gc, torch.from_numpy(pc_).to(dev))
-        pd_, pi_, pc_ = f.mergeTopk(torch.stack(gd).cpu().numpy(), torch.stack(gi).cpu().numpy().view(np.uint32), torch.stack(gc).cpu().numpy(), dedup=True)
+    pd_, pi_, pc_ = f.knnBatch(Q[:ns], k, dedup=True)
+    if dist is not None:
+        D, I, Cn = R.dist.gather_topk(pd_, pi_, pc_, device=dev)
+        pd_, pi_, pc_ = f.mergeTopk(D, I, Cn, dedup=True)
     forest_recall = float(np.mean([len(set(pi_[i, :pc_[i]].tolist()) & set(bi[i].tolist())) / k for i in range(ns)]))
 
     out = None

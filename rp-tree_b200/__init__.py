@@ -10,6 +10,7 @@ from .api import (RPForest, RPTreeConfig, metricL2, rpTreeCfg, sampleHyperplanes
                   forestBatch, treeBatch, forest, tree, knn, knnPQ, candidates, recallWith, levels, leafSizes,
                   treeSize, points)
 from . import _build
+from . import dist
 
 __all__ = ["RPForest", "RPForestError", "RPTreeConfig", "metricL2", "rpTreeCfg", "sampleHyperplanes", "topologyPlan",
            "slice_hyperplanes", "forestBatch", "treeBatch", "forest", "tree", "knn", "knnPQ", "candidates", "recallWith",

@@ -260,7 +260,7 @@ struct TopArgs {
 #define TOP_NT 512
 #define HBINS 8192        /* shared-memory histogram counters */
 #define FIN_CAP 4096      /* in-bin sort capacity */
-#define SMEM_NODES 256    /* relabel keeps per-node state in shared memory up to this many nodes */
+#define SMEM_NODES 1024   /* compact/relabel keep per-node state in shared memory up to this many nodes */
 
 __device__ __forceinline__ int key_bin(ull o, double lo, double sc, int NB) {
     double v = (ord2f(o) - lo) * sc;
@@ -1224,8 +1224,8 @@ int rpf_build_impl(rpf_handle* h) {
     for (int l = 0; l < s_top; ++l) {
         const int nodes = (int)(tp.level_off[l + 1] - tp.level_off[l]);
         int nb;
-        if (nodes <= 128) { nb = HBINS / (int)next_pow2_host((unsigned)nodes); smem_level[l] = 1; }
-        else { nb = 256; smem_level[l] = 0; }
+        if (nodes <= 128) { nb = HBINS / (int)next_pow2_host((unsigned)nodes); smem_level[l] = 1; }   // >= 64 bins per node
+        else { nb = 256; smem_level[l] = 0; }                                                           // global-atomic histogram
         nb_level[l] = nb;
         HSZ = std::max<int64_t>(HSZ, (int64_t)nodes * nb);
     }
@@ -1348,13 +1348,10 @@ int rpf_build_impl(rpf_handle* h) {
                     default: return rpf_fail(h, RPF_ERR_ARG, "internal: bad bottom slot count");
                 }
             } else {
-                switch (CAP) {
-                    case 256: rc2 = launch_bottom_generic<256, 128>(h, B, nnodes_s, tg); break;
-                    case 1024: rc2 = launch_bottom_generic<1024, 256>(h, B, nnodes_s, tg); break;
-                    case 4096: rc2 = launch_bottom_generic<4096, 512>(h, B, nnodes_s, tg); break;
-                    case 8192: rc2 = launch_bottom_generic<8192, 1024>(h, B, nnodes_s, tg); break;
-                    default: return rpf_fail(h, RPF_ERR_ARG, "bottom_cap must be 256, 1024, 4096 or 8192");
-                }
+                if (CAP <= 256) rc2 = launch_bottom_generic<256, 128>(h, B, nnodes_s, tg);
+                else if (CAP <= 1024) rc2 = launch_bottom_generic<1024, 256>(h, B, nnodes_s, tg);
+                else if (CAP <= 4096) rc2 = launch_bottom_generic<4096, 512>(h, B, nnodes_s, tg);
+                else rc2 = launch_bottom_generic<8192, 1024>(h, B, nnodes_s, tg);
             }
             if (rc2) return rc2;
         }

@@ -508,7 +508,8 @@ int rpf_set_option(rpf_handle* h, const char* name, int64_t value) {
 }
 int rpf_set_bottom_cap(rpf_handle* h, int32_t cap) {
     if (!h) return RPF_ERR_ARG;
-    if (cap != 256 && cap != 1024 && cap != 4096 && cap != 8192) return rpf_fail(h, RPF_ERR_ARG, "bottom_cap must be 256, 1024, 4096 or 8192");
+    if (cap != 256 && cap != 512 && cap != 1024 && cap != 2048 && cap != 4096 && cap != 8192)
+        return rpf_fail(h, RPF_ERR_ARG, "bottom_cap must be a power of two in [256, 8192]");
     h->bottom_cap = cap;
     return RPF_OK;
 }

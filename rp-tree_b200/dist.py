@@ -1,0 +1,69 @@
+"""Tree-sharded multi-GPU plumbing: one process per GPU, torch.distributed (NCCL over NVLink on the GPU box, gloo in the
+CPU tests).  Trees are independent (createMulti maps over the IntMap of trees, src/Data/RPTree/Internal.hs:234-240; knn
+folds the per-tree candidates in ascending tree order, src/Data/RPTree.hs:176), so the forest is partitioned in
+CONTIGUOUS blocks of trees, the data is replicated, the build needs no communication, and a query needs exactly one
+exchange: an all-gather of the per-rank (dist, id, count) top-k lists followed by the engine's merge kernel
+(rpf_merge_topk).  Contiguous blocks make (rank, position) order equal to the reference's tree order, so the merged
+result is identical to the single-GPU result, ties included.
+"""
+import numpy as np
+
+
+def shard_trees(ntrees, world, rank):
+    """Contiguous block of trees owned by `rank`: (t_first, t_local)."""
+    per = (ntrees + world - 1) // world
+    t_first = min(rank * per, ntrees)
+    return t_first, max(0, min(ntrees, t_first + per) - t_first)
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist
+
+
+def gather_topk(dist_arr, ids_arr, cnt_arr, group=None, device=None):
+    """All-gather per-rank top-k lists.  Inputs: nq x k float64, nq x k uint32, nq int32 (numpy).
+    Returns rank-major stacks (G x nq x k, G x nq x k, G x nq) as numpy arrays on every rank."""
+    import torch
+    dist = _dist()
+    world = dist.get_world_size(group)
+    dev = device if device is not None else torch.device("cpu")
+    d = torch.from_numpy(np.ascontiguousarray(dist_arr, np.float64)).to(dev)
+    i = torch.from_numpy(np.ascontiguousarray(ids_arr, np.uint32).view(np.int32)).to(dev)
+    c = torch.from_numpy(np.ascontiguousarray(cnt_arr, np.int32)).to(dev)
+    gd = [torch.empty_like(d) for _ in range(world)]
+    gi = [torch.empty_like(i) for _ in range(world)]
+    gc = [torch.empty_like(c) for _ in range(world)]
+    dist.all_gather(gd, d, group=group)
+    dist.all_gather(gi, i, group=group)
+    dist.all_gather(gc, c, group=group)
+    return (torch.stack(gd).cpu().numpy(), torch.stack(gi).cpu().numpy().view(np.uint32), torch.stack(gc).cpu().numpy())
+
+
+def forestBatchSharded(seed, maxd, minl, ntrees, pnz, dim, xs, *, hyperplanes=None, device=0, group=None, bottom_cap=None):
+    """forestBatch (Batch.hs:48-63) with this rank's contiguous block of trees; data replicated on every GPU."""
+    from .api import forestBatch
+    dist = _dist()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    t_first, t_local = shard_trees(ntrees, world, rank)
+    if t_local == 0:
+        raise ValueError("more ranks (%d) than trees (%d)" % (world, ntrees))
+    return forestBatch(seed, maxd, minl, ntrees, pnz, dim, xs, hyperplanes=hyperplanes, device=device,
+                       t_first=t_first, t_local=t_local, bottom_cap=bottom_cap)
+
+
+def knnSharded(forest, k, Q, dedup=False, group=None, device=None):
+    """knn / knnPQ over the whole forest: local top-k on this rank's trees, all-gather, merge kernel (on every rank)."""
+    d, i, c = forest.knnBatch(Q, k, dedup=dedup)
+    D, I, Cn = gather_topk(d, i, c, group=group, device=device)
+    return forest.mergeTopk(D, I, Cn, dedup=dedup)
+
+
+def recallSharded(forest, k, Q, group=None, device=None):
+    """recallWith (RPTree.hs:259-268): per-rank sums over local trees, all-reduced, divided by the forest size."""
+    import torch
+    dist = _dist()
+    dev = device if device is not None else torch.device("cpu")
+    r = torch.from_numpy(forest.recallSumBatch(Q, k)).to(dev)
+    dist.all_reduce(r, group=group)
+    return r.cpu().numpy() / float(forest.ntrees_total)

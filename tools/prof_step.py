@@ -17,6 +17,8 @@ X = bench.make_points(n, d, W["data_seed"], W["clusters"], W["sigma"])
 Q = bench.make_points(nq, d, W["query_seed"], W["clusters"], W["sigma"])
 hp = R.sampleHyperplanes(W["forest_seed"], T, maxd, W["pnz"], d)
 f = R.RPForest(0)
+if os.environ.get("RPF_BOTTOM_CAP"):
+    f.setBottomCap(int(os.environ["RPF_BOTTOM_CAP"]))
 f.setHyperplanes(hp, T, maxd)
 f.setPoints(X)
 for i in range(passes):
@@ -24,3 +26,6 @@ for i in range(passes):
     b = f.lastDeviceMs()
     f.knnBatch(Q, k)
     print("pass %d: build %.3f ms, knn %.3f ms" % (i, b, f.lastDeviceMs()))
+f.setProfiling(True)
+f.build(maxd, W["min_leaf"])
+print({k: v for k, v in f.profile().items() if v[1]})
