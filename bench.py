@@ -49,47 +49,60 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons sampled through NVML every few ms DURING the timed region (the in-process
+    equivalent of the nvidia-smi --query-gpu=clocks.sm,...,clocks_event_reasons.* line in B200_PROFILING.md)."""
 
-    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
-
-    def __init__(self, gpu_index):
-        self.rows = []
-        self.idx = gpu_index
-        self.p = None
+    def __init__(self, gpu_index, period_s=0.004):
+        self.idx, self.period = gpu_index, period_s
+        self.sm, self.reasons, self.power = [], set(), []
+        self.max_sm = None
+        self._stop = threading.Event()
+        self.th = None
+        self.err = None
 
     def start(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
-                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.th = threading.Thread(target=self._read, daemon=True)
-            self.th.start()
-        except Exception:
-            self.p = None
+            import pynvml as nv
+            nv.nvmlInit()
+            self.nv = nv
+            self.h = nv.nvmlDeviceGetHandleByIndex(self.idx)
+            self.max_sm = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+        except Exception as e:      # pragma: no cover
+            self.err = "nvml unavailable: %r" % (e,)
+            return
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
 
-    def _read(self):
-        for line in self.p.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for name, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+            except Exception as e:  # pragma: no cover
+                self.err = repr(e)
+                break
+            time.sleep(self.period)
 
     def stop(self):
-        if not self.p:
-            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=2)
-        except Exception:
-            self.p.kill()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
-        reasons = set()
-        for r in self.rows:
-            if len(r) >= 8:
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=sorted(reasons),
-                    samples=len(sm))
+        self._stop.set()
+        if self.th:
+            self.th.join(timeout=2)
+        if not self.sm:
+            return dict(sm_mhz=None, sm_max_mhz=self.max_sm, reasons=[self.err or "no samples"], samples=0)
+        return dict(sm_mhz=float(np.median(self.sm)), sm_max_mhz=self.max_sm, reasons=sorted(self.reasons), samples=len(self.sm),
+                    power_w_max=max(self.power) if self.power else None)
 
 
 def algorithmic_bytes(W, tlocal, L, s_top, C_mean):
@@ -195,29 +208,40 @@ def run_ours(args):
     build_ms = allmax(float(np.mean(b_ms)))
     knn_ms = allmax(float(np.mean(q_ms)))
 
-    # ---- timed: e2e arm (host buffers through the public API, H2D + D2H inside)
+    # ---- timed: e2e arm -- host (pinned) buffers through the public API; every step copies the points H2D, builds, and
+    # reads the forest back D2H; the query step copies the queries H2D and the results D2H (+ NCCL gather / merge)
     e2e_b, e2e_q = [], []
+    g = R.RPForest(local_rank)
+    if os.environ.get("RPF_BOTTOM_CAP"):
+        g.setBottomCap(int(os.environ["RPF_BOTTOM_CAP"]))
+    g.setHyperplanes(hp, t_local, maxd)
     nn = None
-    barrier()
-    for _ in range(max(1, min(args.steps, 3))):
-        barrier()
-        t0 = time.perf_counter()
-        g = R.RPForest(local_rank)
-        g.setHyperplanes(hp, t_local, maxd)
+
+    def e2e_build():
         g.setPoints(X)                                           # H2D n*d*8
         g.build(maxd, W["min_leaf"])
-        exp = [g.treeExport(t) for t in range(t_local)]          # D2H: thr/mlo/mhi + perm of every local tree
-        nn = len(exp[0]["thr"])
-        barrier()
-        e2e_b.append(time.perf_counter() - t0)
-        t0 = time.perf_counter()
+        return [g.treeExport(t) for t in range(t_local)]         # D2H: thr/mlo/mhi + perm of every local tree
+
+    def e2e_knn():
         dd, ii, cc = g.knnBatch(Q, k)                            # H2D queries, D2H results
         if dist is not None:
             D, I, Cn = R.dist.gather_topk(dd, ii, cc, device=dev)
             g.mergeTopk(D, I, Cn)
+
+    for _ in range(2):                                           # warm-up (workspace allocation)
+        e2e_build(); e2e_knn()
+    for _ in range(args.steps):
+        barrier()
+        t0 = time.perf_counter()
+        exp = e2e_build()
+        barrier()
+        e2e_b.append(time.perf_counter() - t0)
+        nn = len(exp[0]["thr"])
+        t0 = time.perf_counter()
+        e2e_knn()
         barrier()
         e2e_q.append(time.perf_counter() - t0)
-        g.close()
+    g.close()
     e2e_build_s = allmax(float(np.mean(e2e_b)))
     e2e_knn_s = allmax(float(np.mean(e2e_q)))
 

@@ -229,11 +229,18 @@ int rpf_set_points(rpf_handle* h, const double* X, int64_t n, int32_t d) {
     if (n < 0 || d < 1 || (n > 0 && !X)) return rpf_fail(h, RPF_ERR_ARG, "set_points: bad n/d/X");
     if (n >= (int64_t)1 << 31) return rpf_fail(h, RPF_ERR_UNSUPPORTED, "set_points: n must be < 2^31");
     RPF_SETDEV(h);
-    if (h->ownX && h->dX) cudaFree((void*)h->dX);
-    h->dX = nullptr; h->ownX = false;
-    free_forest_dev(h);
     double* p = nullptr;
-    RPF_CUDA(h, cudaMalloc(&p, std::max<size_t>((size_t)n * d * 8, 16)));
+    const size_t bytes = std::max<size_t>((size_t)n * d * 8, 16);
+    if (h->ownX && h->dX && h->x_bytes == bytes) {
+        p = (double*)h->dX;                       // same footprint: reuse the device buffer
+        h->built = false;
+    } else {
+        if (h->ownX && h->dX) cudaFree((void*)h->dX);
+        h->dX = nullptr; h->ownX = false;
+        free_forest_dev(h);
+        RPF_CUDA(h, cudaMalloc(&p, bytes));
+        h->x_bytes = bytes;
+    }
     if (n > 0) RPF_CUDA(h, cudaMemcpyAsync(p, X, (size_t)n * d * 8, cudaMemcpyHostToDevice, h->stream));
     RPF_CUDA(h, cudaStreamSynchronize(h->stream));
     h->dX = p; h->ownX = true; h->n = n; h->d = d;

@@ -63,7 +63,7 @@ struct rpf_handle {
 
     // points
     int64_t n = 0; int d = 0;
-    const double* dX = nullptr; bool ownX = false;
+    const double* dX = nullptr; bool ownX = false; size_t x_bytes = 0;
 
     // hyperplanes: CSR over (tree, level); host copy + device copy
     int T = 0, hpDepth = 0;
