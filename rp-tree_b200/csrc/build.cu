@@ -1183,7 +1183,14 @@ static int launch_bottom_fast(rpf_handle* h, const BottomArgs& B, int nnodes_s, 
 int rpf_build_impl(rpf_handle* h) {
     const Topology& tp = h->topo;
     const int64_t n = h->n, nn = tp.nnodes();
-    const int T = h->T, L = tp.L_eff, CAP = h->bottom_cap;
+    const int T = h->T, L = tp.L_eff;
+    int CAP = h->bottom_cap;
+    {   // Tips larger than the configured capacity still get the reference's internal order as long as they fit the
+        // largest bottom-phase instance (8192 points): raise the capacity for this build.
+        uint32_t maxleaf = 0;
+        for (int64_t g = 0; g < nn; ++g) if (tp.child[g] < 0) maxleaf = std::max(maxleaf, tp.size[g]);
+        if ((int64_t)maxleaf > CAP && maxleaf <= 8192) { CAP = 256; while ((uint32_t)CAP < maxleaf) CAP <<= 1; }
+    }
     h->leaf_order_exact = true;
 
     // ---- result arrays (kept across builds of the same shape)
