@@ -222,6 +222,89 @@ __device__ void bitonic_keys(ull* buf, unsigned m) {
     }
 }
 
+// ---- register-blocked bitonic network --------------------------------------------------------------------------
+// Thread t owns the 8 consecutive slots [8t, 8t+8) in registers.  Comparator distances 1,2,4 are register-to-register,
+// 8..128 are lane-to-lane shuffles inside the warp, >= 256 go through shared memory in a transposed layout
+// (slot x lives at (x & 7) * NT + (x >> 3), so consecutive threads touch consecutive words: no bank conflicts).
+__device__ __forceinline__ void ce_min_first(ull& a, ull& b) { if (a > b) { const ull t = a; a = b; b = t; } }
+
+template <int K>
+__device__ __forceinline__ void flip_in(ull (&v)[8]) {      // mirror pairs inside blocks of K <= 8 registers
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { const int p = e ^ (K - 1); if (e < p) ce_min_first(v[e], v[p]); }
+}
+template <int J>
+__device__ __forceinline__ void half_in(ull (&v)[8]) {      // pairs (e, e+J), J in {1,2,4}
+#pragma unroll
+    for (int e = 0; e < 8; ++e) if ((e & J) == 0) ce_min_first(v[e], v[e + J]);
+}
+__device__ __forceinline__ void flip_shfl(ull (&v)[8], unsigned g, unsigned lane) {   // block of g lanes (8g slots)
+    const bool lower = (lane & (g >> 1)) == 0;
+    ull o[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = __shfl_xor_sync(0xffffffffu, v[7 - e], g - 1);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { const bool lt = v[e] < o[e]; v[e] = (lt == lower) ? v[e] : o[e]; }
+}
+__device__ __forceinline__ void half_shfl(ull (&v)[8], unsigned jl, unsigned lane) {  // partner lane = lane ^ jl
+    const bool lower = (lane & jl) == 0;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const ull o = __shfl_xor_sync(0xffffffffu, v[e], jl);
+        const bool lt = v[e] < o;
+        v[e] = (lt == lower) ? v[e] : o;
+    }
+}
+__device__ __forceinline__ void tail_in(ull (&v)[8]) { half_in<4>(v); half_in<2>(v); half_in<1>(v); }
+
+// sorts every aligned block of Pv slots (Pv a power of two, 2 <= Pv <= 8*NT) ascending; all threads must call
+template <int NT>
+__device__ void sort_regs(ull (&v)[8], ull* w, unsigned Pv) {
+    const unsigned tid = threadIdx.x, lane = tid & 31;
+    flip_in<2>(v);
+    if (Pv >= 4) { flip_in<4>(v); half_in<1>(v); }
+    if (Pv >= 8) { flip_in<8>(v); half_in<2>(v); half_in<1>(v); }
+    for (unsigned g = 2; g <= 32 && 8 * g <= Pv; g <<= 1) {           // k = 8g = 16 .. 256: inside one warp
+        flip_shfl(v, g, lane);
+        for (unsigned jl = g >> 2; jl >= 1; jl >>= 1) half_shfl(v, jl, lane);
+        tail_in(v);
+    }
+    if (NT > 32) {
+        for (unsigned k = 512; k <= Pv; k <<= 1) {                    // cross-warp merges
+            const unsigned kt = k >> 3;                                // block size in threads
+            const int lkt = ilog2_pow2(kt);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) w[e * NT + tid] = v[e];
+            __syncthreads();
+            // flip: slot (e, u) with u in the lower half of its kt-block <-> (7-e, mirrored u)
+            for (unsigned c = tid; c < 4u * NT; c += NT) {
+                const unsigned e = c / (NT / 2), cc = c % (NT / 2);
+                const unsigned blk = cc >> (lkt - 1), uo = cc & ((kt >> 1) - 1);
+                const unsigned u = (blk << lkt) + uo, up = (blk << lkt) + (kt - 1 - uo);
+                const unsigned ia = e * NT + u, ib = (7 - e) * NT + up;
+                const ull a = w[ia], b = w[ib];
+                if (a > b) { w[ia] = b; w[ib] = a; }
+            }
+            __syncthreads();
+            for (unsigned jt = kt >> 2; jt >= 32; jt >>= 1) {          // distances j = 8*jt >= 256
+                const int lj = ilog2_pow2(jt);
+                for (unsigned c = tid; c < 4u * NT; c += NT) {
+                    const unsigned e = c / (NT / 2), cc = c % (NT / 2);
+                    const unsigned u = ((cc >> lj) << (lj + 1)) + (cc & (jt - 1));
+                    const unsigned ia = e * NT + u, ib = ia + jt;
+                    const ull a = w[ia], b = w[ib];
+                    if (a > b) { w[ia] = b; w[ib] = a; }
+                }
+                __syncthreads();
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = w[e * NT + tid];
+            for (unsigned jl = 16; jl >= 1; jl >>= 1) half_shfl(v, jl, lane);
+            tail_in(v);
+        }
+    }
+}
+
 // =====================================================================================================
 // top phase
 // =====================================================================================================
@@ -236,6 +319,9 @@ struct NodeSel {
 struct TopArgs {
     int64_t n;
     int Tg, L, l, node0, nnodes, NTOP, NB, HSZ, MAXTD, smem_hist, gt0;   // gt0: global tree id of the group's first tree
+    int all_internal, child0;        // every node of level l splits; BFS id of the first node of level l+1
+    int scatter_fast;                // last top level: every point lands in a child of this level (CTA-aggregated scatter)
+    uint32_t* track_any;             // [Tg] set by k_top_finish when a margin neighbour lies outside the median bin
     int64_t nn_all;                                                         // nodes per tree (stride of thr/mlo/mhi)
     const ull* keys;
     uint16_t* label;
@@ -258,9 +344,11 @@ struct TopArgs {
 
 #define TOP_CH 32768      /* points per CTA in the streaming top-phase kernels */
 #define TOP_NT 512
-#define HBINS 8192        /* shared-memory histogram counters */
+#define HBINS 32768       /* shared-memory histogram counters (16-bit, two per word; a CTA streams TOP_CH <= 65535 points) */
+#define HBINS_MAXNB 16384
 #define FIN_CAP 4096      /* in-bin sort capacity */
 #define SMEM_NODES 1024   /* compact/relabel keep per-node state in shared memory up to this many nodes */
+#define SCAT_MAX 2048     /* children handled by the CTA-aggregated scatter of the last top level */
 
 __device__ __forceinline__ int key_bin(ull o, double lo, double sc, int NB) {
     double v = (ord2f(o) - lo) * sc;
@@ -310,7 +398,7 @@ __device__ __forceinline__ void load_pt4(const TopArgs& A, const ull* __restrict
 __device__ __forceinline__ int node_of(const TopArgs& A, int g) {
     const int nl = g - A.node0;
     if ((unsigned)nl >= (unsigned)A.nnodes) return -1;
-    if (__ldg(A.child + g) < 0) return -1;
+    if (!A.all_internal && __ldg(A.child + g) < 0) return -1;
     return nl;
 }
 template <typename F>
@@ -348,19 +436,24 @@ __global__ void __launch_bounds__(TOP_NT) k_top_hist(TopArgs A) {
     const int NB = A.NB, tot = A.nnodes * NB;
     uint32_t* gh = A.hist + (int64_t)t * A.HSZ;
     if (A.smem_hist) {
-        for (int j = tid; j < tot; j += TOP_NT) sh[j] = 0;
+        for (int j = tid; j < (tot + 1) / 2; j += TOP_NT) sh[j] = 0;
         __syncthreads();
     }
     stream_points(A, keys, lab, i0, i1, [&](int64_t, ull kv, int g) {
         const int nl = node_of(A, g);
         if (nl < 0) return;
         const int b = key_bin(kv, lo, sc, NB);
-        if (A.smem_hist) atomicAdd(&sh[nl * NB + b], 1u);
-        else atomicAdd(&gh[nl * NB + b], 1u);
+        const int j = nl * NB + b;
+        if (A.smem_hist) atomicAdd(&sh[j >> 1], 1u << ((j & 1) << 4));
+        else atomicAdd(&gh[j], 1u);
     });
     if (A.smem_hist) {
         __syncthreads();
-        for (int j = tid; j < tot; j += TOP_NT) { uint32_t v = sh[j]; if (v) atomicAdd(&gh[j], v); }
+        for (int w2 = tid; w2 < (tot + 1) / 2; w2 += TOP_NT) {
+            const uint32_t v = sh[w2];
+            if (v & 0xffffu) atomicAdd(&gh[2 * w2], v & 0xffffu);
+            if (v >> 16) atomicAdd(&gh[2 * w2 + 1], v >> 16);
+        }
     }
 }
 
@@ -421,7 +514,47 @@ __global__ void __launch_bounds__(TOP_NT) k_top_compact(TopArgs A) {
     });
 }
 
-// one CTA per (node, tree): exact order statistic inside the median bin
+// one WARP per (node, tree) whose median bin holds <= 256 keys: register-blocked bitonic sort, no block barriers
+#define FW_MAX 256
+#define FW_WARPS 8
+__global__ void __launch_bounds__(FW_WARPS * 32) k_top_finish_warp(TopArgs A) {
+    __shared__ ull buf[FW_WARPS][FW_MAX];
+    const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+    const int64_t item = (int64_t)blockIdx.x * FW_WARPS + wi;
+    if (item >= (int64_t)A.nnodes * A.Tg) return;
+    const int t = (int)(item / A.nnodes), nl = (int)(item % A.nnodes), g = A.node0 + nl;
+    if (A.child[g] < 0) return;
+    NodeSel& S = A.sel[(int64_t)t * A.NTOP + g];
+    const uint32_t c = S.cand_cnt, nh = A.nsize[g] >> 1, r = nh - S.below;
+    if (c > FW_MAX) return;
+    const ull* seg = A.cand + (int64_t)t * A.n + S.cand_off;
+    ull v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { const uint32_t i = lane * 8 + e; v[e] = i < c ? seg[i] : 0xffffffffffffffffull; }
+    sort_regs<32>(v, nullptr, FW_MAX);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) buf[wi][lane * 8 + e] = v[e];
+    __syncwarp();
+    const ull thr = buf[wi][r];
+    uint32_t lt = 0, eq = 0;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { const uint32_t i = lane * 8 + e; if (i < c) { lt += v[e] < thr; eq += v[e] == thr; } }
+    for (int off = 16; off > 0; off >>= 1) { lt += __shfl_xor_sync(0xffffffffu, lt, off); eq += __shfl_xor_sync(0xffffffffu, eq, off); }
+    if (lane == 0) {
+        const uint32_t lower = lt, upper = lt + eq;
+        const ull pred = lower > 0 ? buf[wi][lower - 1] : ORD_NONE_LO;
+        const ull succ = upper < c ? buf[wi][upper] : ORD_NONE_HI;
+        S.thr = thr; S.pred = pred; S.succ = succ;
+        S.cless = S.below + lower; S.ceq = eq;
+        S.tie_r = nh - S.cless;
+        S.tie_depth = 0;
+        const bool need_pred = (S.cless == nh) && pred == ORD_NONE_LO;
+        const bool need_succ = (S.cless + eq == nh + 1) && succ == ORD_NONE_HI;
+        if (need_pred || need_succ) atomicOr(&A.track_any[t], 1u);
+    }
+}
+
+// one CTA per (node, tree): exact order statistic inside the median bin (bins with more than FW_MAX keys)
 __global__ void __launch_bounds__(512) k_top_finish(TopArgs A) {
     __shared__ ull buf[FIN_CAP];
     __shared__ uint32_t sh[264];
@@ -430,6 +563,7 @@ __global__ void __launch_bounds__(512) k_top_finish(TopArgs A) {
     if (A.child[g] < 0) return;
     NodeSel& S = A.sel[(int64_t)t * A.NTOP + g];
     const uint32_t c = S.cand_cnt, nh = A.nsize[g] >> 1, r = nh - S.below;
+    if (c <= FW_MAX) return;                      // small bins are finished by k_top_finish_warp (one warp per node)
     const ull* seg = A.cand + (int64_t)t * A.n + S.cand_off;
     ull thr, pred = ORD_NONE_LO, succ = ORD_NONE_HI;
     uint32_t lower, ceq;
@@ -469,6 +603,11 @@ __global__ void __launch_bounds__(512) k_top_finish(TopArgs A) {
         S.cless = S.below + lower; S.ceq = ceq;
         S.tie_r = nh - S.cless;      // tied points that must go left; > 0 => the split cuts through a tie
         S.tie_depth = 0;
+        // sorted[nh-1] / sorted[nh+1] are taken from the bin's sorted keys; only when they fall outside the bin must
+        // k_top_relabel track the nearest keys below / above the threshold over all points of the node
+        const bool need_pred = (S.cless == nh) && pred == ORD_NONE_LO;
+        const bool need_succ = (S.cless + ceq == nh + 1) && succ == ORD_NONE_HI;
+        if (need_pred || need_succ) atomicOr(&A.track_any[t], 1u);
     }
 }
 
@@ -527,31 +666,33 @@ __global__ void __launch_bounds__(512) k_top_ties(TopArgs A) {
 __global__ void __launch_bounds__(TOP_NT) k_top_relabel(TopArgs A, int last) {
     __shared__ ull s_thr[SMEM_NODES], s_pred[SMEM_NODES], s_succ[SMEM_NODES];
     __shared__ uint32_t s_tie[SMEM_NODES];
+    __shared__ uint32_t s_cnt[SCAT_MAX], s_base[SCAT_MAX];
     const int t = blockIdx.y, tid = threadIdx.x;
     const int64_t i0 = (int64_t)blockIdx.x * TOP_CH, i1 = min(A.n, i0 + TOP_CH);
     const ull* keys_t = A.keys + (int64_t)t * A.L * A.n;
     const ull* keys = keys_t + (int64_t)A.l * A.n;
     uint16_t* lab = A.label + (int64_t)t * A.n;
+    const bool sf = last && A.scatter_fast;
+    if (sf) for (int j = tid; j < 2 * A.nnodes; j += TOP_NT) s_cnt[j] = 0;
     NodeSel* sel = A.sel + (int64_t)t * A.NTOP + A.node0;
     const bool cached = A.nnodes <= SMEM_NODES;
     if (cached) {
         for (int j = tid; j < A.nnodes; j += TOP_NT) {
             s_thr[j] = sel[j].thr; s_pred[j] = sel[j].pred; s_succ[j] = sel[j].succ; s_tie[j] = sel[j].tie_r;
         }
-        __syncthreads();
     }
+    __syncthreads();
     uint32_t* fill = A.fill + (int64_t)t * A.NTOP;
     uint32_t* perm = A.perm + (int64_t)t * A.n;
+    const bool fast = cached && A.all_internal && A.track_any[t] == 0;     // block-uniform
     // returns the point's node after this level's split (unchanged when it does not sit in a splitting node)
     auto relabel_one = [&](int64_t i, ull kv, int g) -> int {
         const int nl = g - A.node0;
-        const int ch = ((unsigned)nl < (unsigned)A.nnodes) ? __ldg(A.child + g) : -1;
-        if (ch >= 0) {
-            const ull thr = cached ? s_thr[nl] : sel[nl].thr;
-            bool left = kv < thr;
-            if (kv == thr) {
-                const uint32_t tr = cached ? s_tie[nl] : sel[nl].tie_r;
-                if (tr > 0) {   // composite compare against the tie pivot
+        if (fast) {
+            if ((unsigned)nl < (unsigned)A.nnodes) {
+                const ull thr = s_thr[nl];
+                bool left = kv < thr;
+                if (kv == thr && s_tie[nl] > 0) {   // composite compare against the tie pivot (rare)
                     const int td = sel[nl].tie_depth;
                     const ull* piv = A.pivots + ((int64_t)t * A.NTOP + g) * A.MAXTD;
                     for (int j = 0; j < td; ++j) {
@@ -561,18 +702,38 @@ __global__ void __launch_bounds__(TOP_NT) k_top_relabel(TopArgs A, int last) {
                         if (kq != pv) { left = kq < pv; break; }
                     }
                 }
-            } else if (kv < thr) {
-                if (cached) { if (kv > s_pred[nl]) atomicMax(&s_pred[nl], kv); }
-                else if (kv > sel[nl].pred) atomicMax(&sel[nl].pred, kv);
-            } else {
-                if (cached) { if (kv < s_succ[nl]) atomicMin(&s_succ[nl], kv); }
-                else if (kv < sel[nl].succ) atomicMin(&sel[nl].succ, kv);
+                g = A.child0 + 2 * nl + (left ? 0 : 1);
             }
-            g = ch + (left ? 0 : 1);
+        } else {
+            const int ch = ((unsigned)nl < (unsigned)A.nnodes) ? __ldg(A.child + g) : -1;
+            if (ch >= 0) {
+                const ull thr = cached ? s_thr[nl] : sel[nl].thr;
+                bool left = kv < thr;
+                if (kv == thr) {
+                    const uint32_t tr = cached ? s_tie[nl] : sel[nl].tie_r;
+                    if (tr > 0) {   // composite compare against the tie pivot
+                        const int td = sel[nl].tie_depth;
+                        const ull* piv = A.pivots + ((int64_t)t * A.NTOP + g) * A.MAXTD;
+                        for (int j = 0; j < td; ++j) {
+                            const int lvl = A.l - 1 - j;
+                            const ull kq = lvl >= 0 ? keys_t[(int64_t)lvl * A.n + i] : (ull)i;
+                            const ull pv = piv[j];
+                            if (kq != pv) { left = kq < pv; break; }
+                        }
+                    }
+                } else if (kv < thr) {
+                    if (cached) { if (kv > s_pred[nl]) atomicMax(&s_pred[nl], kv); }
+                    else if (kv > sel[nl].pred) atomicMax(&sel[nl].pred, kv);
+                } else {
+                    if (cached) { if (kv < s_succ[nl]) atomicMin(&s_succ[nl], kv); }
+                    else if (kv < sel[nl].succ) atomicMin(&sel[nl].succ, kv);
+                }
+                g = ch + (left ? 0 : 1);
+            }
         }
         if (last) {
-            const uint32_t pos = atomicAdd(&fill[g], 1u);
-            perm[A.nstart[g] + pos] = (uint32_t)i;
+            if (sf) atomicAdd(&s_cnt[g - A.child0], 1u);
+            else { const uint32_t pos = atomicAdd(&fill[g], 1u); perm[A.nstart[g] + pos] = (uint32_t)i; }
         }
         return g;
     };
@@ -602,7 +763,30 @@ __global__ void __launch_bounds__(TOP_NT) k_top_relabel(TopArgs A, int last) {
     } else {
         for (int64_t i = i0 + tid; i < i1; i += TOP_NT) lab[i] = (uint16_t)relabel_one(i, keys[i], A.l == 0 ? 0 : (int)lab[i]);
     }
-    if (cached) {
+    if (sf) {
+        // reserve a range per child for this CTA (one global atomic per non-empty child), then place the points
+        __syncthreads();
+        for (int j = tid; j < 2 * A.nnodes; j += TOP_NT) {
+            const uint32_t c = s_cnt[j];
+            s_base[j] = c ? atomicAdd(&fill[A.child0 + j], c) : 0u;
+            s_cnt[j] = 0;
+        }
+        __syncthreads();
+        auto place = [&](int64_t i, int g) {
+            const int j = g - A.child0;
+            const uint32_t pos = s_base[j] + atomicAdd(&s_cnt[j], 1u);
+            perm[A.nstart[g] + pos] = (uint32_t)i;
+        };
+        if ((A.n & 3) == 0) {
+            for (int64_t i = i0 + 4 * (int64_t)tid; i < i1; i += 4 * TOP_NT) {
+                const uint2 q = *(const uint2*)(lab + i);          // labels written by this same thread above
+                place(i, (int)(q.x & 0xffff)); place(i + 1, (int)(q.x >> 16)); place(i + 2, (int)(q.y & 0xffff)); place(i + 3, (int)(q.y >> 16));
+            }
+        } else {
+            for (int64_t i = i0 + tid; i < i1; i += TOP_NT) place(i, (int)lab[i]);
+        }
+    }
+    if (cached && !fast) {
         __syncthreads();
         for (int j = tid; j < A.nnodes; j += TOP_NT) {
             if (s_pred[j] > sel[j].pred) atomicMax(&sel[j].pred, s_pred[j]);
@@ -836,89 +1020,6 @@ __device__ __forceinline__ void bitonic_uniform(ull* w, unsigned nslots, unsigne
                 if (a > b) { w[i] = b; w[p] = a; }
             }
             __syncthreads();
-        }
-    }
-}
-
-// ---- register-blocked bitonic network --------------------------------------------------------------------------
-// Thread t owns the 8 consecutive slots [8t, 8t+8) in registers.  Comparator distances 1,2,4 are register-to-register,
-// 8..128 are lane-to-lane shuffles inside the warp, >= 256 go through shared memory in a transposed layout
-// (slot x lives at (x & 7) * NT + (x >> 3), so consecutive threads touch consecutive words: no bank conflicts).
-__device__ __forceinline__ void ce_min_first(ull& a, ull& b) { if (a > b) { const ull t = a; a = b; b = t; } }
-
-template <int K>
-__device__ __forceinline__ void flip_in(ull (&v)[8]) {      // mirror pairs inside blocks of K <= 8 registers
-#pragma unroll
-    for (int e = 0; e < 8; ++e) { const int p = e ^ (K - 1); if (e < p) ce_min_first(v[e], v[p]); }
-}
-template <int J>
-__device__ __forceinline__ void half_in(ull (&v)[8]) {      // pairs (e, e+J), J in {1,2,4}
-#pragma unroll
-    for (int e = 0; e < 8; ++e) if ((e & J) == 0) ce_min_first(v[e], v[e + J]);
-}
-__device__ __forceinline__ void flip_shfl(ull (&v)[8], unsigned g, unsigned lane) {   // block of g lanes (8g slots)
-    const bool lower = (lane & (g >> 1)) == 0;
-    ull o[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) o[e] = __shfl_xor_sync(0xffffffffu, v[7 - e], g - 1);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) { const bool lt = v[e] < o[e]; v[e] = (lt == lower) ? v[e] : o[e]; }
-}
-__device__ __forceinline__ void half_shfl(ull (&v)[8], unsigned jl, unsigned lane) {  // partner lane = lane ^ jl
-    const bool lower = (lane & jl) == 0;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-        const ull o = __shfl_xor_sync(0xffffffffu, v[e], jl);
-        const bool lt = v[e] < o;
-        v[e] = (lt == lower) ? v[e] : o;
-    }
-}
-__device__ __forceinline__ void tail_in(ull (&v)[8]) { half_in<4>(v); half_in<2>(v); half_in<1>(v); }
-
-// sorts every aligned block of Pv slots (Pv a power of two, 2 <= Pv <= 8*NT) ascending; all threads must call
-template <int NT>
-__device__ void sort_regs(ull (&v)[8], ull* w, unsigned Pv) {
-    const unsigned tid = threadIdx.x, lane = tid & 31;
-    flip_in<2>(v);
-    if (Pv >= 4) { flip_in<4>(v); half_in<1>(v); }
-    if (Pv >= 8) { flip_in<8>(v); half_in<2>(v); half_in<1>(v); }
-    for (unsigned g = 2; g <= 32 && 8 * g <= Pv; g <<= 1) {           // k = 8g = 16 .. 256: inside one warp
-        flip_shfl(v, g, lane);
-        for (unsigned jl = g >> 2; jl >= 1; jl >>= 1) half_shfl(v, jl, lane);
-        tail_in(v);
-    }
-    if (NT > 32) {
-        for (unsigned k = 512; k <= Pv; k <<= 1) {                    // cross-warp merges
-            const unsigned kt = k >> 3;                                // block size in threads
-            const int lkt = ilog2_pow2(kt);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) w[e * NT + tid] = v[e];
-            __syncthreads();
-            // flip: slot (e, u) with u in the lower half of its kt-block <-> (7-e, mirrored u)
-            for (unsigned c = tid; c < 4u * NT; c += NT) {
-                const unsigned e = c / (NT / 2), cc = c % (NT / 2);
-                const unsigned blk = cc >> (lkt - 1), uo = cc & ((kt >> 1) - 1);
-                const unsigned u = (blk << lkt) + uo, up = (blk << lkt) + (kt - 1 - uo);
-                const unsigned ia = e * NT + u, ib = (7 - e) * NT + up;
-                const ull a = w[ia], b = w[ib];
-                if (a > b) { w[ia] = b; w[ib] = a; }
-            }
-            __syncthreads();
-            for (unsigned jt = kt >> 2; jt >= 32; jt >>= 1) {          // distances j = 8*jt >= 256
-                const int lj = ilog2_pow2(jt);
-                for (unsigned c = tid; c < 4u * NT; c += NT) {
-                    const unsigned e = c / (NT / 2), cc = c % (NT / 2);
-                    const unsigned u = ((cc >> lj) << (lj + 1)) + (cc & (jt - 1));
-                    const unsigned ia = e * NT + u, ib = ia + jt;
-                    const ull a = w[ia], b = w[ib];
-                    if (a > b) { w[ia] = b; w[ib] = a; }
-                }
-                __syncthreads();
-            }
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = w[e * NT + tid];
-            for (unsigned jl = 16; jl >= 1; jl >>= 1) half_shfl(v, jl, lane);
-            tail_in(v);
         }
     }
 }
@@ -1231,7 +1332,7 @@ int rpf_build_impl(rpf_handle* h) {
     for (int l = 0; l < s_top; ++l) {
         const int nodes = (int)(tp.level_off[l + 1] - tp.level_off[l]);
         int nb;
-        if (nodes <= 128) { nb = HBINS / (int)next_pow2_host((unsigned)nodes); smem_level[l] = 1; }   // >= 64 bins per node
+        if (nodes <= 512) { nb = std::min(HBINS_MAXNB, HBINS / (int)next_pow2_host((unsigned)nodes)); smem_level[l] = 1; }   // >= 64 bins per node
         else { nb = 256; smem_level[l] = 0; }                                                           // global-atomic histogram
         nb_level[l] = nb;
         HSZ = std::max<int64_t>(HSZ, (int64_t)nodes * nb);
@@ -1257,7 +1358,7 @@ int rpf_build_impl(rpf_handle* h) {
         hist = (uint32_t*)h->ws_get(WS_HIST, (size_t)Tg * HSZ * 4);
         sel = (NodeSel*)h->ws_get(WS_SEL, (size_t)Tg * NTOP * sizeof(NodeSel));
         cand = (ull*)h->ws_get(WS_CAND, (size_t)Tg * n * 8);
-        cand_total = (uint32_t*)h->ws_get(WS_CANDTOT, (size_t)Tg * 4);
+        cand_total = (uint32_t*)h->ws_get(WS_CANDTOT, (size_t)Tg * 8);      // [Tg] candidate totals + [Tg] margin-tracking flags
         pivots = (ull*)h->ws_get(WS_PIVOTS, (size_t)Tg * NTOP * MAXTD * 8);
         fill = (uint32_t*)h->ws_get(WS_FILL, (size_t)Tg * NTOP * 4);
         binlo = (double*)h->ws_get(WS_BINLO, (size_t)Tg * L * 8);
@@ -1312,21 +1413,29 @@ int rpf_build_impl(rpf_handle* h) {
             A.keys = keys; A.label = label; A.child = h->d_node_child; A.nstart = h->d_node_start;
             A.nsize = h->d_node_size; A.binlo = binlo; A.binscale = binscale;
             A.kmin = kmin; A.kmax = kmax; A.hist = hist; A.sel = sel;
-            A.cand = cand; A.cand_total = cand_total; A.pivots = pivots;
+            A.cand = cand; A.cand_total = cand_total; A.track_any = cand_total + Tg; A.pivots = pivots;
             A.fill = fill; A.perm = perm_g; A.thr = h->d_thr; A.mlo = h->d_mlo; A.mhi = h->d_mhi;
+            RPF_CUDA(h, cudaFuncSetAttribute(k_top_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, HBINS * 2));
             RPF_LAUNCH(h, PH_MISC, k_bin_setup, (unsigned)((tg * L + 127) / 128), 128, 0, A, nbdev, s_top);
             RPF_CUDA(h, cudaMemsetAsync(fill, 0, (size_t)tg * NTOP * 4, h->stream));
             const unsigned nchunks = (unsigned)((n + TOP_CH - 1) / TOP_CH);
+            bool all_top_internal = true;
             for (int l = 0; l < s_top; ++l) {
                 A.l = l; A.node0 = (int)tp.level_off[l]; A.nnodes = (int)(tp.level_off[l + 1] - tp.level_off[l]);
                 A.NB = nb_level[l]; A.smem_hist = smem_level[l];
+                A.child0 = (int)tp.level_off[l + 1];
+                A.all_internal = 1;
+                for (int64_t g = tp.level_off[l]; g < tp.level_off[l + 1]; ++g) if (tp.child[g] < 0) { A.all_internal = 0; break; }
+                all_top_internal = all_top_internal && A.all_internal;
+                A.scatter_fast = (all_top_internal && 2 * A.nnodes <= SCAT_MAX) ? 1 : 0;
                 RPF_CUDA(h, cudaMemsetAsync(hist, 0, (size_t)tg * HSZ * 4, h->stream));
-                RPF_CUDA(h, cudaMemsetAsync(cand_total, 0, (size_t)tg * 4, h->stream));
+                RPF_CUDA(h, cudaMemsetAsync(cand_total, 0, (size_t)Tg * 8, h->stream));
                 dim3 gs(nchunks, (unsigned)tg), gn((unsigned)A.nnodes, (unsigned)tg);
-                const size_t hs = A.smem_hist ? (size_t)A.nnodes * A.NB * 4 : 0;
+                const size_t hs = A.smem_hist ? ((size_t)A.nnodes * A.NB + 1) / 2 * 4 : 0;     // 16-bit counters
                 RPF_LAUNCH(h, PH_TOP_HIST, k_top_hist, gs, TOP_NT, hs, A);
                 RPF_LAUNCH(h, PH_TOP_PICK, k_top_pick, gn, 256, 0, A);
                 RPF_LAUNCH(h, PH_TOP_COMPACT, k_top_compact, gs, TOP_NT, 0, A);
+                RPF_LAUNCH(h, PH_TOP_FINISH, k_top_finish_warp, (unsigned)(((int64_t)A.nnodes * tg + FW_WARPS - 1) / FW_WARPS), FW_WARPS * 32, 0, A);
                 RPF_LAUNCH(h, PH_TOP_FINISH, k_top_finish, gn, 512, 0, A);
                 RPF_LAUNCH(h, PH_TOP_TIES, k_top_ties, gn, 512, 0, A);
                 RPF_LAUNCH(h, PH_TOP_RELABEL, k_top_relabel, gs, TOP_NT, 0, A, (int)(l == s_top - 1));
