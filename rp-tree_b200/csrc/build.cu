@@ -53,41 +53,8 @@ __global__ void __launch_bounds__(NT) k_project(const double* __restrict__ X, in
     unsigned rowaddr[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) rowaddr[r] = (unsigned)__cvta_generic_to_shared(xs + (size_t)(lane + 32 * r) * ld);
-    for (int j = w; j < H; j += NW) {          // warp-uniform
-        const int row = (t0 + j / L) * hpDepth + (j % L);
-        const int64_t s = hp_off[row];
-        int64_t e = hp_off[row + 1];
-        if (e - s > d) e = s + d;               // innerSD's `i >= nz2` guard (Internal.hs:376)
-        double acc[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) acc[r] = 0.0;
-        const double2* hq = hp_pack + e - 1;    // right fold: innermost (last) term first
-        int cntq = (int)(e - s);
-        for (; cntq >= 2; cntq -= 2, hq -= 2) {
-            const double2 h0 = __ldg(hq), h1 = __ldg(hq - 1);
-            const unsigned c0 = (unsigned)__double_as_longlong(h0.y) << 3, c1 = (unsigned)__double_as_longlong(h1.y) << 3;
-            double x0[R], x1[R];
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                asm("ld.shared.f64 %0, [%1];" : "=d"(x0[r]) : "r"(rowaddr[r] + c0));
-                asm("ld.shared.f64 %0, [%1];" : "=d"(x1[r]) : "r"(rowaddr[r] + c1));
-            }
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                acc[r] = __dadd_rn(__dmul_rn(h0.x, x0[r]), acc[r]);
-                acc[r] = __dadd_rn(__dmul_rn(h1.x, x1[r]), acc[r]);
-            }
-        }
-        if (cntq) {
-            const double2 h0 = __ldg(hq);
-            const unsigned c0 = (unsigned)__double_as_longlong(h0.y) << 3;
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                double x0;
-                asm("ld.shared.f64 %0, [%1];" : "=d"(x0) : "r"(rowaddr[r] + c0));
-                acc[r] = __dadd_rn(__dmul_rn(h0.x, x0), acc[r]);
-            }
-        }
+    // write one output row (and fold its min/max) -- warp-uniform call
+    auto emit = [&](int j, const double (&acc)[R]) {
         if (ORD) {
             ull vmin = ORD_NONE_HI, vmax = ORD_NONE_LO;
 #pragma unroll
@@ -116,6 +83,42 @@ __global__ void __launch_bounds__(NT) k_project(const double* __restrict__ X, in
                 if (i < n) ((double*)out)[(int64_t)j * n + i] = acc[r];
             }
         }
+    };
+    // one term of one hyperplane for this lane's R points: acc = val * x[idx] + acc  (separate roundings, right fold)
+    auto term = [&](const double2 hv, double (&acc)[R]) {
+        const unsigned c = (unsigned)__double_as_longlong(hv.y) << 3;
+        double x[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) asm("ld.shared.f64 %0, [%1];" : "=d"(x[r]) : "r"(rowaddr[r] + c));
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] = __dadd_rn(__dmul_rn(hv.x, x[r]), acc[r]);
+    };
+    // two hyperplanes per warp in flight (2R independent accumulate chains per lane)
+    for (int j = w; j < H; j += 2 * NW) {          // warp-uniform
+        const int jB = j + NW;
+        const bool hasB = jB < H;
+        const int rowA = (t0 + j / L) * hpDepth + (j % L);
+        const int rowB = hasB ? (t0 + jB / L) * hpDepth + (jB % L) : rowA;
+        const int64_t sA = hp_off[rowA], sB = hp_off[rowB];
+        int64_t eA = hp_off[rowA + 1], eB = hp_off[rowB + 1];
+        if (eA - sA > d) eA = sA + d;               // innerSD's `i >= nz2` guard (Internal.hs:376)
+        if (eB - sB > d) eB = sB + d;
+        int cA = (int)(eA - sA), cB = hasB ? (int)(eB - sB) : 0;
+        const double2* hA = hp_pack + eA - 1;       // right fold: innermost (last) term first
+        const double2* hB = hp_pack + eB - 1;
+        double accA[R], accB[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) { accA[r] = 0.0; accB[r] = 0.0; }
+        while (cA > 0 && cB > 0) {
+            const double2 a = __ldg(hA), b2 = __ldg(hB);
+            --hA; --hB; --cA; --cB;
+            term(a, accA);
+            term(b2, accB);
+        }
+        while (cA > 0) { const double2 a = __ldg(hA); --hA; --cA; term(a, accA); }
+        while (cB > 0) { const double2 b2 = __ldg(hB); --hB; --cB; term(b2, accB); }
+        emit(j, accA);
+        if (hasB) emit(jB, accB);
     }
 }
 
@@ -175,6 +178,12 @@ int rpf_project_launch(rpf_handle* h, int phase, const double* dX, int64_t n, in
     const int H = Tg * L;
     if (n <= 0 || H <= 0) return RPF_OK;
     const size_t row = (size_t)ld * 8;
+    if (h->project_variant == 1 && 64 * row <= 110 * 1024)
+        return ord ? launch_project<1024, 2, true>(h, phase, dX, n, t0, L, H, out, kmin, kmax)
+                   : launch_project<1024, 2, false>(h, phase, dX, n, t0, L, H, out, kmin, kmax);
+    if (h->project_variant == 2 && 128 * row <= 140 * 1024)
+        return ord ? launch_project<512, 4, true>(h, phase, dX, n, t0, L, H, out, kmin, kmax)
+                   : launch_project<512, 4, false>(h, phase, dX, n, t0, L, H, out, kmin, kmax);
     if (128 * row <= 140 * 1024)
         return ord ? launch_project<1024, 4, true>(h, phase, dX, n, t0, L, H, out, kmin, kmax)
                    : launch_project<1024, 4, false>(h, phase, dX, n, t0, L, H, out, kmin, kmax);

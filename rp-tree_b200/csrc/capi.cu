@@ -510,6 +510,7 @@ int rpf_set_option(rpf_handle* h, const char* name, int64_t value) {
     const std::string s(name);
     if (s == "force_generic_bottom") { h->force_generic_bottom = value != 0; return RPF_OK; }
     if (s == "force_simple_knn") { h->force_simple_knn = value != 0; return RPF_OK; }
+    if (s == "project_variant") { h->project_variant = (int)value; return RPF_OK; }
     if (s == "release_workspace") { cudaStreamSynchronize(h->stream); h->ws_free_all(); return RPF_OK; }
     return rpf_fail(h, RPF_ERR_ARG, "unknown option " + s);
 }

@@ -81,6 +81,7 @@ struct rpf_handle {
     uint32_t* d_perm = nullptr;                                       // [T][n]
     bool leaf_order_exact = true;
     size_t res_node_bytes = 0, res_perm_bytes = 0;
+    int project_variant = 0;             // tuning hook: 0 = 1024 threads x 4 points/lane, 1 = 1024 x 2 (two CTAs/SM), 2 = 512 x 4
     bool force_simple_knn = false;       // test hook: per-thread gather knn kernel instead of the TMA ring
     bool force_generic_bottom = false;   // test hook: run the generic (entry-table) bottom kernel
 

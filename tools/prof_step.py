@@ -17,6 +17,8 @@ X = bench.make_points(n, d, W["data_seed"], W["clusters"], W["sigma"])
 Q = bench.make_points(nq, d, W["query_seed"], W["clusters"], W["sigma"])
 hp = R.sampleHyperplanes(W["forest_seed"], T, maxd, W["pnz"], d)
 f = R.RPForest(0)
+if os.environ.get("RPF_PROJECT_VARIANT"):
+    f.setOption("project_variant", int(os.environ["RPF_PROJECT_VARIANT"]))
 if os.environ.get("RPF_BOTTOM_CAP"):
     f.setBottomCap(int(os.environ["RPF_BOTTOM_CAP"]))
 f.setHyperplanes(hp, T, maxd)
