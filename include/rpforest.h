@@ -98,6 +98,9 @@ int rpf_leaf_order_exact(const rpf_handle* h);
 /* Per tree: thr/mlo/mhi[num_nodes] (_rpThreshold, Margin low/high; valid where child>=0) and
  * perm[n] = row ids, leaves concatenated left to right, each leaf in the reference's order. */
 int rpf_tree_export(rpf_handle* h, int32_t t, double* thr, double* mlo, double* mhi, uint32_t* perm);
+/* Whole forest in one call: thr/mlo/mhi[T][num_nodes], perm[T][n] (tree-major; any pointer may be NULL).
+ * The copies run back to back on the engine's stream; pass page-locked buffers for full PCIe speed. */
+int rpf_forest_export(rpf_handle* h, double* thr, double* mlo, double* mhi, uint32_t* perm);
 
 /* ---- queries --------------------------------------------------------------------------------------- */
 /* candidates (src/Data/RPTree.hs:293-314) for tree t (t >= 0) or for all trees concatenated tree-major

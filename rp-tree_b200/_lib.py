@@ -38,6 +38,7 @@ SIGNATURES = {
     "rpf_topology_plan": (C.c_int64, [C.c_int64, C.c_int32, C.c_int32, i64p, i32p, i64p, i64p]),
     "rpf_leaf_order_exact": (C.c_int, [H]),
     "rpf_tree_export": (C.c_int, [H, C.c_int32, f64p, f64p, f64p, u32p]),
+    "rpf_forest_export": (C.c_int, [H, f64p, f64p, f64p, u32p]),
     "rpf_candidates_count": (C.c_int, [H, f64p, C.c_int64, C.c_int32, i64p]),
     "rpf_candidates": (C.c_int, [H, f64p, C.c_int64, C.c_int32, i64p, u32p]),
     "rpf_knn": (C.c_int, [H, f64p, C.c_int64, C.c_int32, C.c_int32, f64p, u32p, i32p]),

@@ -183,6 +183,23 @@ class RPForest:
         out.update(thr=thr, mlo=mlo, mhi=mhi, perm=perm[: self.n])
         return out
 
+    def forestExport(self, out=None):
+        """Flat image of every tree in one call: thr/mlo/mhi [T][nodes], perm [T][n].  `out` may hold preallocated
+        (ideally page-locked) arrays of those shapes under the same keys; they are filled in place."""
+        tp = self.topology()
+        nn, T, n = len(tp["child"]), self.ntrees, self.n
+        out = {} if out is None else out
+        for key in ("thr", "mlo", "mhi"):
+            if key not in out:
+                out[key] = np.zeros((T, nn))
+            assert out[key].shape == (T, nn) and out[key].dtype == np.float64 and out[key].flags.c_contiguous
+        if "perm" not in out:
+            out["perm"] = np.zeros((T, max(n, 1)), np.uint32)[:, :n] if n == 0 else np.zeros((T, n), np.uint32)
+        assert out["perm"].shape == (T, n) and out["perm"].dtype == np.uint32
+        self._ck(self._L.rpf_forest_export(self._h, _p(out["thr"], f64p), _p(out["mlo"], f64p), _p(out["mhi"], f64p),
+                                           _p(out["perm"], u32p) if n else None), "rpf_forest_export")
+        return out
+
     def leafOrderExact(self):
         return bool(self._L.rpf_leaf_order_exact(self._h))
 

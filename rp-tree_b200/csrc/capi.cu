@@ -426,6 +426,20 @@ int rpf_tree_export(rpf_handle* h, int32_t t, double* thr, double* mlo, double* 
     return RPF_OK;
 }
 
+int rpf_forest_export(rpf_handle* h, double* thr, double* mlo, double* mhi, uint32_t* perm) {
+    if (!h) return RPF_ERR_ARG;
+    if (!h->built) return rpf_fail(h, RPF_ERR_STATE, "forest_export: forest not built");
+    RPF_SETDEV(h);
+    // the device arrays are already [T][nodes] / [T][n]: four straight copies on the engine's stream, one sync
+    const size_t nb = (size_t)h->T * (size_t)h->topo.nnodes() * 8, pb = (size_t)h->T * (size_t)h->n * 4;
+    if (thr && nb) RPF_CUDA(h, cudaMemcpyAsync(thr, h->d_thr, nb, cudaMemcpyDeviceToHost, h->stream));
+    if (mlo && nb) RPF_CUDA(h, cudaMemcpyAsync(mlo, h->d_mlo, nb, cudaMemcpyDeviceToHost, h->stream));
+    if (mhi && nb) RPF_CUDA(h, cudaMemcpyAsync(mhi, h->d_mhi, nb, cudaMemcpyDeviceToHost, h->stream));
+    if (perm && pb) RPF_CUDA(h, cudaMemcpyAsync(perm, h->d_perm, pb, cudaMemcpyDeviceToHost, h->stream));
+    RPF_CUDA(h, cudaStreamSynchronize(h->stream));
+    return RPF_OK;
+}
+
 int rpf_candidates_count(rpf_handle* h, const double* Q, int64_t nq, int32_t t, int64_t* off_out) {
     if (!h) return RPF_ERR_ARG;
     if (!h->built) return rpf_fail(h, RPF_ERR_STATE, "candidates: forest not built");
@@ -510,6 +524,7 @@ int rpf_set_option(rpf_handle* h, const char* name, int64_t value) {
     const std::string s(name);
     if (s == "force_generic_bottom") { h->force_generic_bottom = value != 0; return RPF_OK; }
     if (s == "force_simple_knn") { h->force_simple_knn = value != 0; return RPF_OK; }
+    if (s == "no_query_order") { h->no_query_order = value != 0; return RPF_OK; }
     if (s == "project_variant") { h->project_variant = (int)value; return RPF_OK; }
     if (s == "release_workspace") { cudaStreamSynchronize(h->stream); h->ws_free_all(); return RPF_OK; }
     return rpf_fail(h, RPF_ERR_ARG, "unknown option " + s);

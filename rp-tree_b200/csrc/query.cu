@@ -185,8 +185,29 @@ __device__ unsigned keep_k(ull* skey, uint32_t* spos, uint32_t* sid, unsigned to
 template <int NT, int SREG = KNN_SREG>
 __device__ unsigned topk_front(ull* skey, uint32_t* spos, uint32_t* sid, unsigned tot, unsigned k, int dedup,
                                ull* rkey, uint32_t* rpos, uint32_t* rid, uint32_t* sh, ull* sh64, unsigned* s_n) {
+    if (tot <= 32) {
+        // one warp, no block barriers: rank every entry by (key, pos) with shuffles and write it to its rank
+        if (threadIdx.x < 32) {
+            const unsigned lane = threadIdx.x;
+            const bool have = lane < tot;
+            const ull kv = have ? skey[lane] : ~0ull;
+            const uint32_t pv = have ? spos[lane] : 0xffffffffu, iv = have ? sid[lane] : 0u;
+            unsigned rank = 0;
+            for (unsigned o = 0; o < tot; ++o) {
+                const ull ko = __shfl_sync(0xffffffffu, kv, o);
+                const uint32_t po = __shfl_sync(0xffffffffu, pv, o);
+                rank += (ko < kv || (ko == kv && po < pv)) ? 1u : 0u;
+            }
+            __syncwarp();
+            if (have) { skey[rank] = kv; spos[rank] = pv; sid[rank] = iv; }
+        }
+        __syncthreads();
+        const unsigned nb = keep_k<NT>(skey, spos, sid, tot, k, dedup, s_n);
+        __syncthreads();
+        return nb;
+    }
     unsigned r = dedup ? min(tot, 32u * k) : min(tot, k);
-    bool full = (r >= tot) || (r > SREG / 2);
+    bool full = (r >= tot) || (r > SREG / 2) || tot <= 128;
     unsigned cnt = 0;
     if (!full) {
         uint32_t cl, ce;
@@ -244,6 +265,7 @@ struct QArgs {
     const uint32_t* nsize;
     const uint32_t* segs;
     const uint32_t* cnt;
+    const uint32_t* order;     // knn only: CTA b answers query order[b] (queries grouped by their tree-0 leaf, see k_qorder_*)
     double* dist;
     uint32_t* ids;
     int32_t* count;
@@ -280,7 +302,7 @@ __global__ void __launch_bounds__(KNN_NT) k_knn(QArgs A) {
     uint32_t* rid = rpos + KNN_SREG;
     double* sq = (double*)(rid + KNN_SREG);
     uint32_t* pre = (uint32_t*)(sq + ((A.d + 3) & ~3));
-    const int64_t q = blockIdx.x;
+    const int64_t q = A.order ? (int64_t)A.order[blockIdx.x] : (int64_t)blockIdx.x;
     const int tid = threadIdx.x;
     const unsigned nslots = (unsigned)A.T * A.S;
     for (int j = tid; j < A.d; j += KNN_NT) sq[j] = A.Q[q * A.d + j];
@@ -349,11 +371,52 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// sum_j (x_j - q_j)^2 of one staged row, strictly left to right with separate roundings (Internal.hs:403-406).
+// Software pipelined: the loads, differences and squares of the NEXT eight components are issued before the eight
+// dependent adds of the current ones, so the only loop-carried latency is one DADD per component.
+__device__ __forceinline__ double row_dist2(const double2* __restrict__ row, const double2* __restrict__ q2, int d2) {
+    double acc = 0.0;
+    int jj = 0;
+    const int nblk = d2 >> 2;
+    if (nblk > 0) {
+        double2 x0 = row[0], x1 = row[1], x2 = row[2], x3 = row[3];
+        double2 y0 = q2[0], y1 = q2[1], y2 = q2[2], y3 = q2[3];
+        for (int b = 0; b < nblk; ++b) {
+            const int nx = (b + 1 < nblk) ? 4 * (b + 1) : 4 * b;      // last block re-reads itself (values unused)
+            const double2 nx0 = row[nx], nx1 = row[nx + 1], nx2 = row[nx + 2], nx3 = row[nx + 3];
+            const double2 ny0 = q2[nx], ny1 = q2[nx + 1], ny2 = q2[nx + 2], ny3 = q2[nx + 3];
+            const double a0 = __dsub_rn(x0.x, y0.x), a1 = __dsub_rn(x0.y, y0.y), a2 = __dsub_rn(x1.x, y1.x), a3 = __dsub_rn(x1.y, y1.y);
+            const double a4 = __dsub_rn(x2.x, y2.x), a5 = __dsub_rn(x2.y, y2.y), a6 = __dsub_rn(x3.x, y3.x), a7 = __dsub_rn(x3.y, y3.y);
+            const double s0 = __dmul_rn(a0, a0), s1 = __dmul_rn(a1, a1), s2 = __dmul_rn(a2, a2), s3 = __dmul_rn(a3, a3);
+            const double s4 = __dmul_rn(a4, a4), s5 = __dmul_rn(a5, a5), s6 = __dmul_rn(a6, a6), s7 = __dmul_rn(a7, a7);
+            acc = __dadd_rn(acc, s0); acc = __dadd_rn(acc, s1); acc = __dadd_rn(acc, s2); acc = __dadd_rn(acc, s3);
+            acc = __dadd_rn(acc, s4); acc = __dadd_rn(acc, s5); acc = __dadd_rn(acc, s6); acc = __dadd_rn(acc, s7);
+            x0 = nx0; x1 = nx1; x2 = nx2; x3 = nx3; y0 = ny0; y1 = ny1; y2 = ny2; y3 = ny3;
+        }
+        jj = nblk * 4;
+    }
+    for (; jj < d2; ++jj) {
+        const double2 x = row[jj], y = q2[jj];
+        const double d0 = __dsub_rn(x.x, y.x), d1 = __dsub_rn(x.y, y.y);
+        acc = __dadd_rn(acc, __dmul_rn(d0, d0));
+        acc = __dadd_rn(acc, __dmul_rn(d1, d1));
+    }
+    return acc;
+}
+
+#define KT_INF_BITS 0x7ff0000000000000ull
+
+// Roles per chunk of CH = KT_BUF - k candidates: warp 0 = TMA producer, warps 1..KT_STAGES = consumers (one per ring
+// stage), the remaining warps resolve candidate -> row id for the NEXT chunk (two dependent global reads, segs ->
+// perm) while the ring runs.  Consumers keep only candidates whose distance does not exceed the running k-th best
+// (tau): after the first select nearly everything is filtered, so a query costs ~one radix select however many
+// candidates it has.  Survivors carry their position in the reference's concatenation order; the final
+// (distance, position) sort therefore equals the reference's stable sort (RPTree.hs:174).
 __global__ void __launch_bounds__(KT_NT) k_knn_tma(QArgs A, int rows_per_stage, int pitch /* bytes, multiple of 16 */) {
     __shared__ uint32_t part[KT_NT + 1];
-    __shared__ unsigned s_n;
+    __shared__ unsigned s_n, s_nsurv;
     __shared__ uint32_t sh[264];
-    __shared__ ull sh64;
+    __shared__ ull sh64, s_tau;
     __shared__ __align__(8) uint64_t full_bar[KT_STAGES], empty_bar[KT_STAGES];
     extern __shared__ __align__(16) unsigned char dyn[];
     unsigned char* stage_buf = dyn;                                              // [KT_STAGES][rows][pitch]
@@ -363,9 +426,10 @@ __global__ void __launch_bounds__(KT_NT) k_knn_tma(QArgs A, int rows_per_stage, 
     uint32_t* sid = spos + KT_BUF;
     uint32_t* rpos = sid + KT_BUF;
     uint32_t* rid = rpos + KT_SREG;
-    double* sq = (double*)(rid + KT_SREG);
+    uint32_t* cid = rid + KT_SREG;                                               // [2][KT_BUF] row ids of the current / next chunk
+    double* sq = (double*)(cid + 2 * KT_BUF);
     uint32_t* pre = (uint32_t*)(sq + ((A.d + 3) & ~3));
-    const int64_t q = blockIdx.x;
+    const int64_t q = A.order ? (int64_t)A.order[blockIdx.x] : (int64_t)blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned nslots = (unsigned)A.T * A.S;
     const int R = rows_per_stage;
@@ -375,17 +439,33 @@ __global__ void __launch_bounds__(KT_NT) k_knn_tma(QArgs A, int rows_per_stage, 
         for (int s2 = 0; s2 < KT_STAGES; ++s2) { mbar_init(&full_bar[s2], 1); mbar_init(&empty_bar[s2], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        s_nsurv = 0; s_tau = KT_INF_BITS;
     }
     for (int j = tid; j < A.d; j += KT_NT) sq[j] = A.Q[q * A.d + j];
     load_slots(A, q, A.T, pre, KT_NT);
     slot_prefix<KT_NT>(pre, nslots, part);
     const uint32_t C = pre[nslots];
     const unsigned k = (unsigned)A.k, CHK = KT_BUF - k;
+    auto resolve = [&](uint32_t base, unsigned m, uint32_t* dst, unsigned r, unsigned nthr) {
+        for (unsigned j = r; j < m; j += nthr) {
+            const uint32_t c = base + j;
+            const unsigned slot = find_slot(pre, nslots, c);
+            const int tt = slot / A.S;
+            const uint32_t g = A.segs[(q * A.T + tt) * (int64_t)A.S + (slot % A.S)];
+            dst[j] = A.perm[(int64_t)tt * A.n + A.nstart[g] + (c - pre[slot])];
+        }
+    };
+    resolve(0, min((uint32_t)CHK, C), cid, tid, KT_NT);
+    __syncthreads();
     unsigned nbest = 0;
     uint32_t uses = 0;            // tiles issued so far (all roles advance it identically)
-    for (uint32_t base = 0; base < C; base += CHK) {
+    int cb = 0;
+    for (uint32_t base = 0; base < C; base += CHK, cb ^= 1) {
         const unsigned m = min((uint32_t)CHK, C - base);
         const unsigned ntiles = (m + R - 1) / R;
+        const uint32_t nbase = base + CHK;
+        const unsigned next_m = nbase < C ? min((uint32_t)CHK, C - nbase) : 0u;
+        const uint32_t* ids = cid + cb * KT_BUF;
         if (warp == 0) {
             // ---- producer
             for (unsigned ti = 0; ti < ntiles; ++ti) {
@@ -393,16 +473,7 @@ __global__ void __launch_bounds__(KT_NT) k_knn_tma(QArgs A, int rows_per_stage, 
                 if (round > 0) mbar_wait(&empty_bar[st], (round - 1) & 1);
                 const unsigned j = ti * R + lane;
                 const bool valid = lane < R && j < m;
-                uint32_t id = 0;
-                if (valid) {
-                    const uint32_t c = base + j;
-                    const unsigned slot = find_slot(pre, nslots, c);
-                    const int tt = slot / A.S;
-                    const uint32_t g = A.segs[(q * A.T + tt) * (int64_t)A.S + (slot % A.S)];
-                    id = A.perm[(int64_t)tt * A.n + A.nstart[g] + (c - pre[slot])];
-                    spos[nbest + j] = c;
-                    sid[nbest + j] = id;
-                }
+                const uint32_t id = valid ? ids[j] : 0u;
                 const unsigned nrows = min((unsigned)R, m - ti * R);
                 if (lane == 0) mbar_arrive_expect_tx(&full_bar[st], nrows * row_bytes);
                 __syncwarp();
@@ -411,33 +482,35 @@ __global__ void __launch_bounds__(KT_NT) k_knn_tma(QArgs A, int rows_per_stage, 
         } else if (warp <= KT_STAGES) {
             // ---- consumer of stage warp-1
             const uint32_t st = warp - 1;
+            const ull tau = s_tau;
             for (unsigned ti = 0; ti < ntiles; ++ti) {
                 const uint32_t u = uses + ti;
                 if (u % KT_STAGES != st) continue;
                 mbar_wait(&full_bar[st], (u / KT_STAGES) & 1);
                 const unsigned j = ti * R + lane;
                 if (lane < R && j < m) {
-                    const double2* row = (const double2*)(stage_buf + ((size_t)st * R + lane) * pitch);
-                    const double2* q2 = (const double2*)sq;
-                    double acc = 0.0;
-                    const int d2 = A.d >> 1;
-#pragma unroll 4
-                    for (int jj = 0; jj < d2; ++jj) {
-                        const double2 x = row[jj], y = q2[jj];
-                        const double d0 = __dsub_rn(x.x, y.x), d1 = __dsub_rn(x.y, y.y);
-                        acc = __dadd_rn(acc, __dmul_rn(d0, d0));
-                        acc = __dadd_rn(acc, __dmul_rn(d1, d1));
+                    const double acc = row_dist2((const double2*)(stage_buf + ((size_t)st * R + lane) * pitch), (const double2*)sq, A.d >> 1);
+                    const ull bits = (ull)__double_as_longlong(__dsqrt_rn(acc));
+                    if (bits <= tau) {
+                        const unsigned p = atomicAdd(&s_nsurv, 1u);
+                        skey[p] = bits; spos[p] = base + j; sid[p] = ids[j];
                     }
-                    skey[nbest + j] = (ull)__double_as_longlong(__dsqrt_rn(acc));
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty_bar[st]);
             }
+        } else if (next_m) {
+            // ---- the other warps look up the next chunk's row ids while the ring runs
+            resolve(nbase, next_m, cid + (cb ^ 1) * KT_BUF, (unsigned)tid - 32u * (KT_STAGES + 1), (unsigned)KT_NT - 32u * (KT_STAGES + 1));
         }
         uses += ntiles;
         __syncthreads();
-        const unsigned tot = nbest + m;
-        nbest = topk_front<KT_NT, KT_SREG>(skey, spos, sid, tot, k, A.dedup, rkey, rpos, rid, sh, &sh64, &s_n);
+        const unsigned nsurv = s_nsurv;
+        if (next_m == 0 || nsurv + next_m > KT_BUF) {
+            nbest = topk_front<KT_NT, KT_SREG>(skey, spos, sid, nsurv, k, A.dedup, rkey, rpos, rid, sh, &sh64, &s_n);
+            if (tid == 0) { s_nsurv = nbest; s_tau = nbest >= k ? skey[k - 1] : KT_INF_BITS; }
+            __syncthreads();
+        }
     }
     for (unsigned i = tid; i < k; i += KT_NT) {
         const bool ok = i < nbest;
@@ -445,6 +518,45 @@ __global__ void __launch_bounds__(KT_NT) k_knn_tma(QArgs A, int rows_per_stage, 
         A.ids[q * k + i] = ok ? sid[i] : 0xffffffffu;
     }
     if (tid == 0 && A.count) A.count[q] = (int32_t)nbest;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// query scheduling order: CTAs that run at the same time should re-rank the same rows, so that a candidate row is
+// fetched from HBM once and then served from the 126 MB L2.  Queries are grouped (counting sort) by the position of
+// their first tree-0 leaf in that tree's left-to-right leaf order: neighbours in that order share the top of the
+// tree, i.e. lie on the same side of the same hyperplanes.  Only the SCHEDULE changes; results are per query.
+// ---------------------------------------------------------------------------------------------------
+#define QO_BUCKETS 4096
+__device__ __forceinline__ unsigned q_bucket(const QArgs& A, int64_t q) {
+    const uint32_t g = A.segs[q * (int64_t)A.T * A.S];
+    const unsigned long long st = A.nstart[g];
+    return (unsigned)((st * QO_BUCKETS) / (unsigned long long)(A.n > 0 ? A.n : 1)) & (QO_BUCKETS - 1);
+}
+__global__ void k_qorder_hist(QArgs A, uint32_t* __restrict__ hist) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < A.nq) atomicAdd(&hist[q_bucket(A, q)], 1u);
+}
+__global__ void __launch_bounds__(1024) k_qorder_scan(uint32_t* __restrict__ hist) {   // exclusive scan of QO_BUCKETS counters
+    __shared__ uint32_t part[1024];
+    const int tid = threadIdx.x;
+    uint32_t v[QO_BUCKETS / 1024], s = 0;
+#pragma unroll
+    for (int e = 0; e < QO_BUCKETS / 1024; ++e) { v[e] = hist[tid * (QO_BUCKETS / 1024) + e]; s += v[e]; }
+    part[tid] = s;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {
+        const uint32_t y = tid >= off ? part[tid - off] : 0u;
+        __syncthreads();
+        part[tid] += y;
+        __syncthreads();
+    }
+    uint32_t c = part[tid] - s;
+#pragma unroll
+    for (int e = 0; e < QO_BUCKETS / 1024; ++e) { hist[tid * (QO_BUCKETS / 1024) + e] = c; c += v[e]; }
+}
+__global__ void k_qorder_scatter(QArgs A, uint32_t* __restrict__ cursor, uint32_t* __restrict__ order) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < A.nq) order[atomicAdd(&cursor[q_bucket(A, q)], 1u)] = (uint32_t)q;
 }
 
 // candidate counts per query (sum of reached leaf sizes over Tq trees)
@@ -739,12 +851,21 @@ int rpf_knn_impl(rpf_handle* h, const double* Q, int64_t nq, int k, int dedup, d
     QWS(h, dcount, int32_t, WS_OUT_C, (size_t)nq * 4);
     QArgs A = make_qargs(h, nq, st);
     A.k = k; A.dedup = dedup; A.dist = ddist; A.ids = dids; A.count = dcount;
+    if (nq >= 64 && !h->no_query_order) {
+        QWS(h, qhist, uint32_t, WS_QHIST, (size_t)QO_BUCKETS * 4);
+        QWS(h, qorder, uint32_t, WS_QORDER, (size_t)nq * 4);
+        RPF_CUDA(h, cudaMemsetAsync(qhist, 0, (size_t)QO_BUCKETS * 4, h->stream));
+        RPF_LAUNCH(h, PH_Q_TRAVERSE, k_qorder_hist, (unsigned)((nq + 255) / 256), 256, 0, A, qhist);
+        RPF_LAUNCH(h, PH_Q_TRAVERSE, k_qorder_scan, 1, 1024, 0, qhist);
+        RPF_LAUNCH(h, PH_Q_TRAVERSE, k_qorder_scatter, (unsigned)((nq + 255) / 256), 256, 0, A, qhist, qorder);
+        A.order = qorder;
+    }
     // TMA path: rows are 16-byte multiples and a 2-stage ring of up to 32 rows fits next to the selection buffers
     const size_t tail = (size_t)((h->d + 3) & ~3) * 8 + ((size_t)h->T * st.S + 1) * 4;
     const int pitch = h->d * 8 + 16;
     int rows = (int)std::min<size_t>(32, (size_t)(72 * 1024) / ((size_t)KT_STAGES * pitch));
-    const size_t dyn_tma = (size_t)KT_STAGES * rows * pitch + (size_t)(KT_BUF + KT_SREG) * 16 + tail;
-    const bool use_tma = (h->d % 2 == 0) && rows >= 1 && k <= KT_BUF / 2 && dyn_tma <= 110 * 1024 && !h->force_simple_knn &&
+    const size_t dyn_tma = (size_t)KT_STAGES * rows * pitch + (size_t)(KT_BUF + KT_SREG) * 16 + (size_t)2 * KT_BUF * 4 + tail;
+    const bool use_tma = (h->d % 2 == 0) && rows >= 1 && k <= KT_BUF / 2 && dyn_tma <= 112 * 1024 && !h->force_simple_knn &&
                          (((uintptr_t)h->dX & 15) == 0);
     if (use_tma) {
         RPF_CUDA(h, cudaFuncSetAttribute(k_knn_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_tma));
