@@ -34,10 +34,11 @@ def build(force=False, verbose=False):
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
     nvcc = _nvcc()
+    extra = os.environ.get("RPF_NVCC_EXTRA", "").split()      # tuning experiments only (e.g. -DKT_STAGES=3)
     procs = []
     for s in SOURCES:
         obj = os.path.join(objdir, s.replace(".cu", ".o"))
-        cmd = [nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, s), "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + extra + ["-c", os.path.join(CSRC, s), "-o", obj]
         if verbose:
             print(" ".join(cmd), file=sys.stderr)
         procs.append((cmd, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))

@@ -344,7 +344,12 @@ __global__ void __launch_bounds__(KNN_NT) k_knn(QArgs A) {
 // measured); bulk copies move whole rows and bypass that limit.
 // ---------------------------------------------------------------------------------------------------
 #define KT_NT 256
+#ifndef KT_STAGES
 #define KT_STAGES 2
+#endif
+#ifndef KT_NPROD
+#define KT_NPROD 4     /* producer warps (must divide 32) */
+#endif
 #define KT_BUF 1280      /* candidate entries per chunk (incl. the running best) */
 #define KT_SREG 512
 
@@ -436,7 +441,7 @@ __global__ void __launch_bounds__(KT_NT) k_knn_tma(QArgs A, int rows_per_stage, 
     const uint32_t row_bytes = (uint32_t)A.d * 8u;
 
     if (tid == 0) {
-        for (int s2 = 0; s2 < KT_STAGES; ++s2) { mbar_init(&full_bar[s2], 1); mbar_init(&empty_bar[s2], 1); }
+        for (int s2 = 0; s2 < KT_STAGES; ++s2) { mbar_init(&full_bar[s2], KT_NPROD); mbar_init(&empty_bar[s2], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         s_nsurv = 0; s_tau = KT_INF_BITS;
@@ -447,12 +452,25 @@ __global__ void __launch_bounds__(KT_NT) k_knn_tma(QArgs A, int rows_per_stage, 
     const uint32_t C = pre[nslots];
     const unsigned k = (unsigned)A.k, CHK = KT_BUF - k;
     auto resolve = [&](uint32_t base, unsigned m, uint32_t* dst, unsigned r, unsigned nthr) {
-        for (unsigned j = r; j < m; j += nthr) {
-            const uint32_t c = base + j;
-            const unsigned slot = find_slot(pre, nslots, c);
-            const int tt = slot / A.S;
-            const uint32_t g = A.segs[(q * A.T + tt) * (int64_t)A.S + (slot % A.S)];
-            dst[j] = A.perm[(int64_t)tt * A.n + A.nstart[g] + (c - pre[slot])];
+        for (unsigned j0 = r; j0 < m; j0 += 4 * nthr) {          // four independent segs -> perm chains in flight per thread
+            const uint32_t* src[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const unsigned j = j0 + u * nthr;
+                src[u] = nullptr;
+                if (j < m) {
+                    const uint32_t c = base + j;
+                    const unsigned slot = find_slot(pre, nslots, c);
+                    const int tt = slot / A.S;
+                    const uint32_t g = A.segs[(q * A.T + tt) * (int64_t)A.S + (slot % A.S)];
+                    src[u] = A.perm + (int64_t)tt * A.n + A.nstart[g] + (c - pre[slot]);
+                }
+            }
+            uint32_t v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = src[u] ? __ldg(src[u]) : 0u;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) if (src[u]) dst[j0 + u * nthr] = v[u];
         }
     };
     resolve(0, min((uint32_t)CHK, C), cid, tid, KT_NT);
@@ -466,22 +484,30 @@ __global__ void __launch_bounds__(KT_NT) k_knn_tma(QArgs A, int rows_per_stage, 
         const uint32_t nbase = base + CHK;
         const unsigned next_m = nbase < C ? min((uint32_t)CHK, C - nbase) : 0u;
         const uint32_t* ids = cid + cb * KT_BUF;
-        if (warp == 0) {
-            // ---- producer
+        if (warp < KT_NPROD) {
+            // ---- producers: warp p issues rows [p*RP, (p+1)*RP) of every tile.  cp.async.bulk takes uniform operands, so
+            // the per-lane copies of one warp are issued one after the other (~60 cycles each); several producer warps
+            // issue concurrently.
+            constexpr unsigned RP = 32 / KT_NPROD;
             for (unsigned ti = 0; ti < ntiles; ++ti) {
                 const uint32_t u = uses + ti, st = u % KT_STAGES, round = u / KT_STAGES;
                 if (round > 0) mbar_wait(&empty_bar[st], (round - 1) & 1);
-                const unsigned j = ti * R + lane;
-                const bool valid = lane < R && j < m;
+                const unsigned rloc = (unsigned)warp * RP + lane;                 // row inside the tile
+                const unsigned j = ti * R + rloc;
+                const bool valid = lane < RP && rloc < (unsigned)R && j < m;
                 const uint32_t id = valid ? ids[j] : 0u;
                 const unsigned nrows = min((unsigned)R, m - ti * R);
-                if (lane == 0) mbar_arrive_expect_tx(&full_bar[st], nrows * row_bytes);
+                const unsigned lo = min(nrows, (unsigned)warp * RP), hi = min(nrows, (unsigned)(warp + 1) * RP);
+                if (lane == 0) {
+                    if (hi > lo) mbar_arrive_expect_tx(&full_bar[st], (hi - lo) * row_bytes);
+                    else mbar_arrive(&full_bar[st]);
+                }
                 __syncwarp();
-                if (valid) bulk_g2s(stage_buf + ((size_t)st * R + lane) * pitch, A.X + (int64_t)id * A.d, row_bytes, &full_bar[st]);
+                if (valid) bulk_g2s(stage_buf + ((size_t)st * R + rloc) * pitch, A.X + (int64_t)id * A.d, row_bytes, &full_bar[st]);
             }
-        } else if (warp <= KT_STAGES) {
-            // ---- consumer of stage warp-1
-            const uint32_t st = warp - 1;
+        } else if (warp < KT_NPROD + KT_STAGES) {
+            // ---- consumer of stage warp-KT_NPROD
+            const uint32_t st = warp - KT_NPROD;
             const ull tau = s_tau;
             for (unsigned ti = 0; ti < ntiles; ++ti) {
                 const uint32_t u = uses + ti;
@@ -501,7 +527,7 @@ __global__ void __launch_bounds__(KT_NT) k_knn_tma(QArgs A, int rows_per_stage, 
             }
         } else if (next_m) {
             // ---- the other warps look up the next chunk's row ids while the ring runs
-            resolve(nbase, next_m, cid + (cb ^ 1) * KT_BUF, (unsigned)tid - 32u * (KT_STAGES + 1), (unsigned)KT_NT - 32u * (KT_STAGES + 1));
+            resolve(nbase, next_m, cid + (cb ^ 1) * KT_BUF, (unsigned)tid - 32u * (KT_NPROD + KT_STAGES), (unsigned)KT_NT - 32u * (KT_NPROD + KT_STAGES));
         }
         uses += ntiles;
         __syncthreads();
