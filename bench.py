@@ -217,10 +217,17 @@ def run_ours(args):
     g.setHyperplanes(hp, t_local, maxd)
     nn = None
 
+    exp_bufs = {}
+
     def e2e_build():
-        g.setPoints(X)                                           # H2D n*d*8
+        g.setPoints(X)                                           # H2D n*d*8 from pinned host memory
         g.build(maxd, W["min_leaf"])
-        return [g.treeExport(t) for t in range(t_local)]         # D2H: thr/mlo/mhi + perm of every local tree
+        if not exp_bufs:                                         # page-locked result buffers, allocated once (first warm-up)
+            nn_ = len(g.topology()["child"])
+            for key in ("thr", "mlo", "mhi"):
+                exp_bufs[key] = torch.empty((t_local, nn_), dtype=torch.float64, pin_memory=True).numpy()
+            exp_bufs["perm"] = torch.empty((t_local, n), dtype=torch.int32, pin_memory=True).numpy().view(np.uint32)
+        return g.forestExport(exp_bufs)                          # D2H: thr/mlo/mhi + perm of every local tree, one call
 
     def e2e_knn():
         dd, ii, cc = g.knnBatch(Q, k)                            # H2D queries, D2H results
@@ -236,12 +243,15 @@ def run_ours(args):
         exp = e2e_build()
         barrier()
         e2e_b.append(time.perf_counter() - t0)
-        nn = len(exp[0]["thr"])
+        nn = exp["thr"].shape[1]
         t0 = time.perf_counter()
         e2e_knn()
         barrier()
         e2e_q.append(time.perf_counter() - t0)
     g.close()
+    if rank == 0:
+        print("per-step build device ms: %s | e2e build s: %s | e2e knn s: %s" % (
+            [round(x, 3) for x in b_ms], [round(x, 4) for x in e2e_b], [round(x, 4) for x in e2e_q]), file=sys.stderr)
     e2e_build_s = allmax(float(np.mean(e2e_b)))
     e2e_knn_s = allmax(float(np.mean(e2e_q)))
 
@@ -272,8 +282,16 @@ def run_ours(args):
     per_launch_bytes = ab[dom] if dom.startswith("top_") else ab[dom] / dom_launches
     avg_ms = dom_ms / dom_launches
     achieved = per_launch_bytes / (avg_ms * 1e-3) / 1e9
+    # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture (tools/ncu_traffic.py)
+    traffic, traffic_src = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as fh:
+            tj = json.load(fh)[dom]
+        traffic, traffic_src = int(tj["dram_bytes_per_launch"]), "ncu dram__bytes_read+write: profiles/%s" % ",".join(tj["source"])
+    except Exception:
+        pass
     roofline = dict(bound="hbm", kernel=dom, achieved=round(achieved, 1), peak=peak, unit="GB/s", frac=round(achieved / peak, 4),
-                    traffic=None, peak_source=peak_src, launches_per_step=dom_launches, avg_launch_ms=round(avg_ms, 4),
+                    traffic=traffic, traffic_source=traffic_src, peak_source=peak_src, launches_per_step=dom_launches, avg_launch_ms=round(avg_ms, 4),
                     algorithmic_bytes_per_launch=int(per_launch_bytes))
     build_bytes = 8 * d * n + t_local * L * n * 24
     knn_bytes = ab["q_knn"]
@@ -320,7 +338,7 @@ def run_ours(args):
             "phases": phases, "clocks": clocks,
         }
         if not args.no_cpu and world == 1:
-            out["cpu_baseline"] = cpu_baseline(X, hp_all, W, maxd, sample_trees=None, threads=1)
+            out["cpu_baseline"] = cpu_baseline(X, hp_all, W, maxd, sample_trees=args.cpu_trees, threads=1)
     barrier()
     if dist is not None:
         dist.destroy_process_group()
@@ -395,6 +413,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-trees", type=int, default=8, help="trees built by the cpu_baseline leg (about 2 s each on one core)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

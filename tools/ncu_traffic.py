@@ -1,0 +1,45 @@
+"""DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) of every profiled kernel in one or more
+.ncu-rep files -> profiles/r01_traffic.json, keyed by the engine's phase names (what bench.py's `roofline.traffic` reads).
+
+  python tools/ncu_traffic.py gpurun_out/prof_v8.ncu-rep gpurun_out/prof_v7.ncu-rep
+"""
+import csv
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PHASE = [("k_knn_tma", "q_knn"), ("k_knn", "q_knn"), ("k_project<", "project"), ("k_bottom", "bottom"), ("k_top_hist", "top_hist"),
+         ("k_top_compact", "top_compact"), ("k_top_relabel", "top_relabel")]
+UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+
+
+def main(paths):
+    acc = {}
+    for path in paths:
+        out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(out.splitlines()))
+        hdr, units = rows[0], rows[1]
+        ir, iw, it, ik = (hdr.index(x) for x in ("dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__time_duration.sum", "Kernel Name"))
+        for r in rows[2:]:
+            name = r[ik]
+            ph = next((p for key, p in PHASE if key in name), None)
+            if ph is None:
+                continue
+            if ph == "project" and float(r[ir].replace(",", "")) * UNIT[units[ir]] < 1e8:
+                continue            # the query-projection launch of the same template
+            b = float(r[ir].replace(",", "")) * UNIT[units[ir]] + float(r[iw].replace(",", "")) * UNIT[units[iw]]
+            acc.setdefault(ph, []).append((b, float(r[it].replace(",", "")), os.path.basename(path), name[:48]))
+    res = {}
+    for ph, lst in acc.items():
+        res[ph] = dict(dram_bytes_per_launch=sum(x[0] for x in lst) / len(lst), launches_profiled=len(lst),
+                       ncu_ms_per_launch=sum(x[1] for x in lst) / len(lst), source=sorted({x[2] for x in lst}), kernel=lst[0][3])
+    dst = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    with open(dst, "w") as fh:
+        json.dump(res, fh, indent=1, sort_keys=True)
+    print(json.dumps(res, indent=1, sort_keys=True))
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:])
