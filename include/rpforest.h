@@ -75,9 +75,13 @@ int rpf_get_hyperplanes(const rpf_handle* h, int64_t* off, int32_t* idx, double*
 /* ---- build: forestBatch / treeBatch (Batch.hs:29-63) == createMulti/create/insert Tip-case
  *      (Internal.hs:217-240,287-297) with partitionAtMedian (Internal.hs:484-505) ---------------------- */
 int rpf_build(rpf_handle* h, int32_t maxDepth, int32_t minLeaf);
-/* forest / tree (Conduit.hs:58-121): same, data arriving in chunks of `chunk` points.  chunk >= n is
- * identical to rpf_build (single insert into an empty Tip); chunk < n (streaming Bin-case update,
- * Internal.hs:274-285) returns RPF_ERR_UNSUPPORTED in this round. */
+/* forest / tree (Conduit.hs:58-121; insertMulti/insert, Internal.hs:243-297): the rows of X arrive in chunks of
+ * `chunk` points, in row order.  chunk >= n is identical to rpf_build (one insert into an empty Tip).  chunk < n runs
+ * the reference's streaming update per chunk: every Bin a chunk passes through gets thr' = (thr0 + thr)/2 and
+ * margin' = margin0 <> margin with the CHUNK's positional median (Internal.hs:274-285); every Tip gets xs <> xs0 and is
+ * split again once it outgrows minLeaf (Internal.hs:287-297).  The reference's quirk is kept: an empty piece reaching a
+ * Bin replaces that subtree by an empty Tip (Internal.hs:279), dropping its points -- see rpf_points_lost.
+ * Limits: a Tip that must be re-split may hold at most 8192 points (minLeaf <= 4095 in practice). */
 int rpf_build_chunked(rpf_handle* h, int32_t maxDepth, int32_t minLeaf, int64_t chunk);
 
 /* ---- result structure: RPT Bin/Tip (Internal.hs:139-148) as flat arrays ---------------------------- */
@@ -92,6 +96,12 @@ int rpf_topology(const rpf_handle* h, int64_t* child, int32_t* depth, int64_t* s
 /* Host-only: the topology for (n, maxDepth, minLeaf) without a handle.  Returns the node count; arrays may be NULL. */
 int64_t rpf_topology_plan(int64_t n, int32_t maxDepth, int32_t minLeaf, int64_t* child, int32_t* depth,
                           int64_t* seg_start, int64_t* seg_size);
+/* Host-only: the tree shape after a streaming build with the given chunk size (chunk >= n: same as rpf_topology_plan).
+ * points_lost (may be NULL) receives the number of points the reference's empty-piece rule drops. */
+int64_t rpf_topology_plan_chunked(int64_t n, int32_t maxDepth, int32_t minLeaf, int64_t chunk, int64_t* child, int32_t* depth,
+                                  int64_t* seg_start, int64_t* seg_size, int64_t* points_lost);
+/* Points dropped by the last rpf_build_chunked (0 for rpf_build).  The slots of perm past seg_size[0] hold 0xffffffff. */
+int64_t rpf_points_lost(const rpf_handle* h);
 /* 1 if every leaf's internal order equals the reference's (always, unless a leaf is larger than the
  * shared-memory capacity set by rpf_set_bottom_cap; leaf SETS are exact regardless). */
 int rpf_leaf_order_exact(const rpf_handle* h);

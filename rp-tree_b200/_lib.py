@@ -2,7 +2,7 @@
 
 The product path has no CPU fallback: if the shared library is missing or no CUDA device is usable,
 creating an engine raises.  (Loading the library itself and calling the host-only entry points --
-rpf_sample_hyperplanes, rpf_topology_plan, rpf_rptree_cfg -- works without a GPU.)
+rpf_sample_hyperplanes, rpf_topology_plan, rpf_topology_plan_chunked, rpf_rptree_cfg -- works without a GPU.)
 """
 import ctypes as C
 import os
@@ -36,6 +36,8 @@ SIGNATURES = {
     "rpf_num_trees": (C.c_int32, [H]),
     "rpf_topology": (C.c_int, [H, i64p, i32p, i64p, i64p]),
     "rpf_topology_plan": (C.c_int64, [C.c_int64, C.c_int32, C.c_int32, i64p, i32p, i64p, i64p]),
+    "rpf_topology_plan_chunked": (C.c_int64, [C.c_int64, C.c_int32, C.c_int32, C.c_int64, i64p, i32p, i64p, i64p, i64p]),
+    "rpf_points_lost": (C.c_int64, [H]),
     "rpf_leaf_order_exact": (C.c_int, [H]),
     "rpf_tree_export": (C.c_int, [H, C.c_int32, f64p, f64p, f64p, u32p]),
     "rpf_forest_export": (C.c_int, [H, f64p, f64p, f64p, u32p]),

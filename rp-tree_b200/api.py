@@ -69,15 +69,23 @@ def sampleHyperplanes(seed, ntrees, maxd, pnz, dim):
     return off, idx[:nnz].copy(), val[:nnz].copy()
 
 
-def topologyPlan(n, maxd, minl):
-    """The data-independent tree shape for (n, maxDepth, minLeaf): BFS arrays child/depth/seg_start/seg_size."""
+def topologyPlan(n, maxd, minl, chunk=None):
+    """The data-independent tree shape for (n, maxDepth, minLeaf[, chunk size]): BFS arrays child/depth/seg_start/
+    seg_size.  With `chunk` (the streaming `forest`/`tree`, Conduit.hs:58-121) also `points_lost`."""
     L = lib()
-    nn = L.rpf_topology_plan(n, maxd, minl, None, None, None, None)
+    if chunk is None:
+        nn = L.rpf_topology_plan(n, maxd, minl, None, None, None, None)
+    else:
+        nn = L.rpf_topology_plan_chunked(n, maxd, minl, chunk, None, None, None, None, None)
     if nn < 0:
-        raise RPForestError("rpf_topology_plan: bad arguments")
+        raise RPForestError("rpf_topology_plan: bad or unsupported arguments (rc=%d)" % nn)
     child = np.zeros(nn, np.int64); depth = np.zeros(nn, np.int32); ss = np.zeros(nn, np.int64); sz = np.zeros(nn, np.int64)
-    L.rpf_topology_plan(n, maxd, minl, _p(child, i64p), _p(depth, i32p), _p(ss, i64p), _p(sz, i64p))
-    return dict(child=child, depth=depth, seg_start=ss, seg_size=sz)
+    if chunk is None:
+        L.rpf_topology_plan(n, maxd, minl, _p(child, i64p), _p(depth, i32p), _p(ss, i64p), _p(sz, i64p))
+        return dict(child=child, depth=depth, seg_start=ss, seg_size=sz)
+    lost = C.c_int64()
+    L.rpf_topology_plan_chunked(n, maxd, minl, chunk, _p(child, i64p), _p(depth, i32p), _p(ss, i64p), _p(sz, i64p), C.byref(lost))
+    return dict(child=child, depth=depth, seg_start=ss, seg_size=sz, points_lost=lost.value)
 
 
 def slice_hyperplanes(hp, maxd, t_first, t_local):
@@ -203,6 +211,10 @@ class RPForest:
     def leafOrderExact(self):
         return bool(self._L.rpf_leaf_order_exact(self._h))
 
+    def pointsLost(self):
+        """Points the reference's streaming insert drops (empty piece reaching a Bin, Internal.hs:279); 0 for batch builds."""
+        return int(self._L.rpf_points_lost(self._h))
+
     # -- queries (batched: Q is nq x d)
     def candidatesBatch(self, Q, t=-1):
         Q, _ = _as_q(Q, self.d)
@@ -297,16 +309,26 @@ def treeBatch(seed, maxd, minl, pnz, dim, xs, **kw):
     return forestBatch(seed, maxd, minl, 1, pnz, dim, xs, **kw)
 
 
-def forest(seed, maxd, minl, ntrees, chunksize, pnz, dim, xs, *, hyperplanes=None, device=0):
-    """forest (Conduit.hs:104-121): data arrives in chunks of `chunksize`.  chunksize >= n is forestBatch."""
+def forest(seed, maxd, minl, ntrees, chunksize, pnz, dim, xs, *, hyperplanes=None, device=0, t_first=0, t_local=None,
+           bottom_cap=None, options=None):
+    """forest (Conduit.hs:104-121): the rows of xs arrive in chunks of `chunksize` (the conduit's `chunksOf`), each chunk
+    updates every tree (insertMulti, Internal.hs:243-255).  chunksize >= n is forestBatch."""
     xs = np.ascontiguousarray(xs, dtype=np.float64)
+    if xs.ndim != 2 or xs.shape[1] != dim:
+        raise ValueError("dataset must be n x %d" % dim)
+    t_local = ntrees - t_first if t_local is None else t_local
     f = RPForest(device)
+    if bottom_cap is not None:
+        f.setBottomCap(bottom_cap)
+    for name, value in (options or {}).items():
+        f.setOption(name, value)
     f.setPoints(xs)
     if hyperplanes is not None:
-        f.setHyperplanes(hyperplanes, ntrees, maxd)
+        hp = hyperplanes if (t_first == 0 and t_local == ntrees) else slice_hyperplanes(hyperplanes, maxd, t_first, t_local)
+        f.setHyperplanes(hp, t_local, maxd)
     else:
-        f.genHyperplanes(seed, ntrees, maxd, pnz, dim)
-    f.t_first, f.ntrees_total = 0, ntrees
+        f.genHyperplanes(seed, ntrees, maxd, pnz, dim, t_first, t_local)
+    f.t_first, f.ntrees_total = t_first, ntrees
     f.build(maxd, minl, chunk=chunksize)
     return f
 

@@ -34,7 +34,7 @@ template <int NT, int R, bool ORD>
 __global__ void __launch_bounds__(NT) k_project(const double* __restrict__ X, int64_t n, int d, int ld,
                                                  const int64_t* __restrict__ hp_off, const double2* __restrict__ hp_pack,
                                                  int t0, int L, int hpDepth, int H,
-                                                 void* __restrict__ out, ull* __restrict__ kmin, ull* __restrict__ kmax) {
+                                                 void* __restrict__ out, int64_t ostride, ull* __restrict__ kmin, ull* __restrict__ kmax) {
     constexpr int P = 32 * R, NW = NT / 32;
     extern __shared__ double xs[];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(NT) k_project(const double* __restrict__ X, in
                 const int64_t i = i0 + lane + 32 * r;
                 if (i < n) {
                     const ull o = f2ord(acc[r]);
-                    ((ull*)out)[(int64_t)j * n + i] = o;
+                    ((ull*)out)[(int64_t)j * ostride + i] = o;
                     vmin = o < vmin ? o : vmin;
                     vmax = o > vmax ? o : vmax;
                 }
@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(NT) k_project(const double* __restrict__ X, in
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const int64_t i = i0 + lane + 32 * r;
-                if (i < n) ((double*)out)[(int64_t)j * n + i] = acc[r];
+                if (i < n) ((double*)out)[(int64_t)j * ostride + i] = acc[r];
             }
         }
     };
@@ -127,7 +127,7 @@ template <bool ORD>
 __global__ void __launch_bounds__(256) k_project_direct(const double* __restrict__ X, int64_t n, int d,
                                                          const int64_t* __restrict__ hp_off, const double2* __restrict__ hp_pack,
                                                          int t0, int L, int hpDepth, int H,
-                                                         void* __restrict__ out, ull* __restrict__ kmin, ull* __restrict__ kmax) {
+                                                         void* __restrict__ out, int64_t ostride, ull* __restrict__ kmin, ull* __restrict__ kmax) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int64_t i = (int64_t)blockIdx.x * 32 + lane;
     const bool live = i < n;
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(256) k_project_direct(const double* __restrict
         }
         if (ORD) {
             const ull o = f2ord(acc);
-            if (live) ((ull*)out)[(int64_t)j * n + i] = o;
+            if (live) ((ull*)out)[(int64_t)j * ostride + i] = o;
             ull vmin = live ? o : ORD_NONE_HI, vmax = live ? o : ORD_NONE_LO;
             for (int off = 16; off > 0; off >>= 1) {
                 const ull a2 = __shfl_xor_sync(0xffffffffu, vmin, off), b2 = __shfl_xor_sync(0xffffffffu, vmax, off);
@@ -156,48 +156,49 @@ __global__ void __launch_bounds__(256) k_project_direct(const double* __restrict
                 if (vmax > kmax[j]) atomicMax(&kmax[j], vmax);
             }
         } else if (live) {
-            ((double*)out)[(int64_t)j * n + i] = acc;
+            ((double*)out)[(int64_t)j * ostride + i] = acc;
         }
     }
 }
 
 template <int NT, int R, bool ORD>
-static int launch_project(rpf_handle* h, int phase, const double* dX, int64_t n, int t0, int L, int H, void* out, ull* kmin, ull* kmax) {
+static int launch_project(rpf_handle* h, int phase, const double* dX, int64_t n, int t0, int L, int H, void* out, int64_t ostride, ull* kmin, ull* kmax) {
     const int d = h->d, ld = d | 1;
     const size_t smem = (size_t)32 * R * ld * sizeof(double);
     auto kfn = k_project<NT, R, ORD>;
     RPF_CUDA(h, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t grid = (n + 32 * R - 1) / (32 * R);
-    RPF_LAUNCH(h, phase, kfn, (unsigned)grid, NT, smem, dX, n, d, ld, h->d_hp_off, (const double2*)h->d_hp_pack, t0, L, h->hpDepth, H, out, kmin, kmax);
+    RPF_LAUNCH(h, phase, kfn, (unsigned)grid, NT, smem, dX, n, d, ld, h->d_hp_off, (const double2*)h->d_hp_pack, t0, L, h->hpDepth, H, out, ostride, kmin, kmax);
     return RPF_OK;
 }
 
+// out row j (= tree-in-group * L + level) starts at out + j * ostride; point i of dX lands at column i
 int rpf_project_launch(rpf_handle* h, int phase, const double* dX, int64_t n, int t0, int Tg, int L, bool ord, void* out,
-                       ull* kmin, ull* kmax) {
+                       int64_t ostride, ull* kmin, ull* kmax) {
     const int d = h->d, ld = d | 1;
     const int H = Tg * L;
     if (n <= 0 || H <= 0) return RPF_OK;
     const size_t row = (size_t)ld * 8;
     if (h->project_variant == 1 && 64 * row <= 110 * 1024)
-        return ord ? launch_project<1024, 2, true>(h, phase, dX, n, t0, L, H, out, kmin, kmax)
-                   : launch_project<1024, 2, false>(h, phase, dX, n, t0, L, H, out, kmin, kmax);
+        return ord ? launch_project<1024, 2, true>(h, phase, dX, n, t0, L, H, out, ostride, kmin, kmax)
+                   : launch_project<1024, 2, false>(h, phase, dX, n, t0, L, H, out, ostride, kmin, kmax);
     if (h->project_variant == 2 && 128 * row <= 140 * 1024)
-        return ord ? launch_project<512, 4, true>(h, phase, dX, n, t0, L, H, out, kmin, kmax)
-                   : launch_project<512, 4, false>(h, phase, dX, n, t0, L, H, out, kmin, kmax);
+        return ord ? launch_project<512, 4, true>(h, phase, dX, n, t0, L, H, out, ostride, kmin, kmax)
+                   : launch_project<512, 4, false>(h, phase, dX, n, t0, L, H, out, ostride, kmin, kmax);
     if (128 * row <= 140 * 1024)
-        return ord ? launch_project<1024, 4, true>(h, phase, dX, n, t0, L, H, out, kmin, kmax)
-                   : launch_project<1024, 4, false>(h, phase, dX, n, t0, L, H, out, kmin, kmax);
+        return ord ? launch_project<1024, 4, true>(h, phase, dX, n, t0, L, H, out, ostride, kmin, kmax)
+                   : launch_project<1024, 4, false>(h, phase, dX, n, t0, L, H, out, ostride, kmin, kmax);
     if (64 * row <= 110 * 1024)
-        return ord ? launch_project<256, 2, true>(h, phase, dX, n, t0, L, H, out, kmin, kmax)
-                   : launch_project<256, 2, false>(h, phase, dX, n, t0, L, H, out, kmin, kmax);
+        return ord ? launch_project<256, 2, true>(h, phase, dX, n, t0, L, H, out, ostride, kmin, kmax)
+                   : launch_project<256, 2, false>(h, phase, dX, n, t0, L, H, out, ostride, kmin, kmax);
     if (32 * row <= 110 * 1024)
-        return ord ? launch_project<256, 1, true>(h, phase, dX, n, t0, L, H, out, kmin, kmax)
-                   : launch_project<256, 1, false>(h, phase, dX, n, t0, L, H, out, kmin, kmax);
+        return ord ? launch_project<256, 1, true>(h, phase, dX, n, t0, L, H, out, ostride, kmin, kmax)
+                   : launch_project<256, 1, false>(h, phase, dX, n, t0, L, H, out, ostride, kmin, kmax);
     const int64_t grid = (n + 31) / 32;
     if (ord) {
-        RPF_LAUNCH(h, phase, k_project_direct<true>, (unsigned)grid, 256, 0, dX, n, d, h->d_hp_off, (const double2*)h->d_hp_pack, t0, L, h->hpDepth, H, out, kmin, kmax);
+        RPF_LAUNCH(h, phase, k_project_direct<true>, (unsigned)grid, 256, 0, dX, n, d, h->d_hp_off, (const double2*)h->d_hp_pack, t0, L, h->hpDepth, H, out, ostride, kmin, kmax);
     } else {
-        RPF_LAUNCH(h, phase, k_project_direct<false>, (unsigned)grid, 256, 0, dX, n, d, h->d_hp_off, (const double2*)h->d_hp_pack, t0, L, h->hpDepth, H, out, kmin, kmax);
+        RPF_LAUNCH(h, phase, k_project_direct<false>, (unsigned)grid, 256, 0, dX, n, d, h->d_hp_off, (const double2*)h->d_hp_pack, t0, L, h->hpDepth, H, out, ostride, kmin, kmax);
     }
     return RPF_OK;
 }
@@ -326,7 +327,9 @@ struct NodeSel {
 };
 
 struct TopArgs {
-    int64_t n;
+    int64_t n;                       // points of this job (labels, cand are [Tg][n])
+    int64_t ks, ps;                  // element stride between key rows / between the trees' slices of perm
+    int vec;                         // key rows and labels are 32-byte / 8-byte aligned: 4-point vector accesses allowed
     int Tg, L, l, node0, nnodes, NTOP, NB, HSZ, MAXTD, smem_hist, gt0;   // gt0: global tree id of the group's first tree
     int all_internal, child0;        // every node of level l splits; BFS id of the first node of level l+1
     int scatter_fast;                // last top level: every point lands in a child of this level (CTA-aggregated scatter)
@@ -412,7 +415,7 @@ __device__ __forceinline__ int node_of(const TopArgs& A, int g) {
 }
 template <typename F>
 __device__ __forceinline__ void stream_points(const TopArgs& A, const ull* __restrict__ keys, const uint16_t* lab, int64_t i0, int64_t i1, F&& f) {
-    if ((A.n & 3) == 0) {
+    if (A.vec) {
         const int64_t step = 4 * TOP_NT;
         int64_t i = i0 + 4 * (int64_t)threadIdx.x;
         for (; i + step < i1; i += 2 * step) {
@@ -439,7 +442,7 @@ __global__ void __launch_bounds__(TOP_NT) k_top_hist(TopArgs A) {
     extern __shared__ uint32_t sh[];
     const int t = blockIdx.y, tid = threadIdx.x;
     const int64_t i0 = (int64_t)blockIdx.x * TOP_CH, i1 = min(A.n, i0 + TOP_CH);
-    const ull* keys = A.keys + ((int64_t)t * A.L + A.l) * A.n;
+    const ull* keys = A.keys + ((int64_t)t * A.L + A.l) * A.ks;
     const uint16_t* lab = A.label + (int64_t)t * A.n;
     const double lo = A.binlo[t * A.L + A.l], sc = A.binscale[t * A.L + A.l];
     const int NB = A.NB, tot = A.nnodes * NB;
@@ -501,7 +504,7 @@ __global__ void __launch_bounds__(TOP_NT) k_top_compact(TopArgs A) {
     __shared__ int s_bin[SMEM_NODES];
     const int t = blockIdx.y, tid = threadIdx.x;
     const int64_t i0 = (int64_t)blockIdx.x * TOP_CH, i1 = min(A.n, i0 + TOP_CH);
-    const ull* keys = A.keys + ((int64_t)t * A.L + A.l) * A.n;
+    const ull* keys = A.keys + ((int64_t)t * A.L + A.l) * A.ks;
     const uint16_t* lab = A.label + (int64_t)t * A.n;
     const double lo = A.binlo[t * A.L + A.l], sc = A.binscale[t * A.L + A.l];
     NodeSel* sel = A.sel + (int64_t)t * A.NTOP + A.node0;
@@ -631,8 +634,8 @@ __global__ void __launch_bounds__(512) k_top_ties(TopArgs A) {
     if (A.child[g] < 0) return;
     NodeSel& S = A.sel[(int64_t)t * A.NTOP + g];
     if (S.tie_r == 0) return;
-    const ull* keys_t = A.keys + (int64_t)t * A.L * A.n;
-    const ull* keys_l = keys_t + (int64_t)A.l * A.n;
+    const ull* keys_t = A.keys + (int64_t)t * A.L * A.ks;
+    const ull* keys_l = keys_t + (int64_t)A.l * A.ks;
     const uint16_t* lab = A.label + (int64_t)t * A.n;
     const ull thr = S.thr;
     uint32_t* la = (uint32_t*)(A.cand + (int64_t)t * A.n) + 2 * (int64_t)A.nstart[g];
@@ -649,7 +652,7 @@ __global__ void __launch_bounds__(512) k_top_ties(TopArgs A) {
     ull* piv = A.pivots + ((int64_t)t * A.NTOP + g) * A.MAXTD;
     while (true) {
         const int lvl = A.l - 1 - depth;
-        const ull* kk = lvl >= 0 ? keys_t + (int64_t)lvl * A.n : nullptr;
+        const ull* kk = lvl >= 0 ? keys_t + (int64_t)lvl * A.ks : nullptr;
         uint32_t cl, ce;
         ull pv = cta_radix_select<512>(c, rr, [&](uint32_t i) { uint32_t id = la[i]; return kk ? kk[id] : (ull)id; }, sh, sh64, cl, ce);
         if (tid == 0) piv[depth] = pv;
@@ -678,8 +681,8 @@ __global__ void __launch_bounds__(TOP_NT) k_top_relabel(TopArgs A, int last) {
     __shared__ uint32_t s_cnt[SCAT_MAX], s_base[SCAT_MAX];
     const int t = blockIdx.y, tid = threadIdx.x;
     const int64_t i0 = (int64_t)blockIdx.x * TOP_CH, i1 = min(A.n, i0 + TOP_CH);
-    const ull* keys_t = A.keys + (int64_t)t * A.L * A.n;
-    const ull* keys = keys_t + (int64_t)A.l * A.n;
+    const ull* keys_t = A.keys + (int64_t)t * A.L * A.ks;
+    const ull* keys = keys_t + (int64_t)A.l * A.ks;
     uint16_t* lab = A.label + (int64_t)t * A.n;
     const bool sf = last && A.scatter_fast;
     if (sf) for (int j = tid; j < 2 * A.nnodes; j += TOP_NT) s_cnt[j] = 0;
@@ -692,7 +695,7 @@ __global__ void __launch_bounds__(TOP_NT) k_top_relabel(TopArgs A, int last) {
     }
     __syncthreads();
     uint32_t* fill = A.fill + (int64_t)t * A.NTOP;
-    uint32_t* perm = A.perm + (int64_t)t * A.n;
+    uint32_t* perm = A.perm + (int64_t)t * A.ps;
     const bool fast = cached && A.all_internal && A.track_any[t] == 0;     // block-uniform
     // returns the point's node after this level's split (unchanged when it does not sit in a splitting node)
     auto relabel_one = [&](int64_t i, ull kv, int g) -> int {
@@ -706,7 +709,7 @@ __global__ void __launch_bounds__(TOP_NT) k_top_relabel(TopArgs A, int last) {
                     const ull* piv = A.pivots + ((int64_t)t * A.NTOP + g) * A.MAXTD;
                     for (int j = 0; j < td; ++j) {
                         const int lvl = A.l - 1 - j;
-                        const ull kq = lvl >= 0 ? keys_t[(int64_t)lvl * A.n + i] : (ull)i;
+                        const ull kq = lvl >= 0 ? keys_t[(int64_t)lvl * A.ks + i] : (ull)i;
                         const ull pv = piv[j];
                         if (kq != pv) { left = kq < pv; break; }
                     }
@@ -725,7 +728,7 @@ __global__ void __launch_bounds__(TOP_NT) k_top_relabel(TopArgs A, int last) {
                         const ull* piv = A.pivots + ((int64_t)t * A.NTOP + g) * A.MAXTD;
                         for (int j = 0; j < td; ++j) {
                             const int lvl = A.l - 1 - j;
-                            const ull kq = lvl >= 0 ? keys_t[(int64_t)lvl * A.n + i] : (ull)i;
+                            const ull kq = lvl >= 0 ? keys_t[(int64_t)lvl * A.ks + i] : (ull)i;
                             const ull pv = piv[j];
                             if (kq != pv) { left = kq < pv; break; }
                         }
@@ -746,7 +749,7 @@ __global__ void __launch_bounds__(TOP_NT) k_top_relabel(TopArgs A, int last) {
         }
         return g;
     };
-    if ((A.n & 3) == 0) {
+    if (A.vec) {
         const int64_t step = 4 * TOP_NT;
         int64_t i = i0 + 4 * (int64_t)tid;
         for (; i + step < i1; i += 2 * step) {
@@ -786,7 +789,7 @@ __global__ void __launch_bounds__(TOP_NT) k_top_relabel(TopArgs A, int last) {
             const uint32_t pos = s_base[j] + atomicAdd(&s_cnt[j], 1u);
             perm[A.nstart[g] + pos] = (uint32_t)i;
         };
-        if ((A.n & 3) == 0) {
+        if (A.vec) {
             for (int64_t i = i0 + 4 * (int64_t)tid; i < i1; i += 4 * TOP_NT) {
                 const uint2 q = *(const uint2*)(lab + i);          // labels written by this same thread above
                 place(i, (int)(q.x & 0xffff)); place(i + 1, (int)(q.x >> 16)); place(i + 2, (int)(q.y & 0xffff)); place(i + 3, (int)(q.y >> 16));
@@ -820,26 +823,14 @@ __global__ void k_top_finalize(TopArgs A) {
     A.mhi[o] = ord2f(hi);
 }
 
-__global__ void k_iota_perm(uint32_t* perm, int64_t n, int Tg) {
+__global__ void k_iota_perm(uint32_t* perm, int64_t n, int64_t ps, int Tg) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n * Tg) perm[i] = (uint32_t)(i % n);
+    if (i < n * Tg) perm[(i / n) * ps + (i % n)] = (uint32_t)(i % n);
 }
 
 // =====================================================================================================
 // bottom phase: one CTA = one level-s node and its whole subtree, resident in shared memory
 // =====================================================================================================
-struct BottomArgs {
-    int64_t n, nn_all;
-    int L, s, nlb, gt0, first_gid;      // nlb = levels recorded per node in `range`
-    const ull* keys;                     // [Tg][L][n]
-    uint32_t* perm;                      // [Tg][n]  (in: node segments in any order; out: final leaf order)
-    const int32_t* child;
-    const uint32_t* nstart;
-    const uint32_t* nsize;
-    const int2* range;                   // [nodes at level s][nlb]: BFS id range of the descendants that split
-    const uint32_t* lvl_pv;              // per level: next_pow2(max node size)
-    double *thr, *mlo, *mhi;
-};
 
 #define BOT_EMAX 1024
 #define POS_NONE 0xffffffffu
@@ -855,14 +846,14 @@ __global__ void __launch_bounds__(NT) k_bottom(BottomArgs A) {
     const int e0 = A.first_gid + blockIdx.x;
     const uint32_t m = A.nsize[e0], start = A.nstart[e0];
     if (m == 0) return;
-    const int64_t n = A.n;
+    const int64_t n = A.ks;
     const ull* keys_t = A.keys + (int64_t)t * A.L * n;
-    uint32_t* perm = A.perm + (int64_t)t * n + start;
+    uint32_t* perm = A.perm + (int64_t)t * A.ps + start;
 
     for (uint32_t p = tid; p < m; p += NT) sidx[p] = perm[p];
     __syncthreads();
 
-    if (A.s > 0) {
+    if (A.s > 0 && !A.given_order) {
         // Establish the reference's incoming order O_s: lexicographic (key_{s-1}, ..., key_0, row id).
         const ull* k1 = keys_t + (int64_t)(A.s - 1) * n;
         for (uint32_t p = tid; p < m; p += NT) skey[p] = k1[sidx[p]];
@@ -1048,10 +1039,11 @@ __global__ void __launch_bounds__(NT) k_bottom3(BottomArgs A) {
     const int e0 = A.first_gid + blockIdx.x;
     const uint32_t m = A.nsize[e0], start = A.nstart[e0];
     if (m == 0) return;
-    const int64_t n = A.n;
+    const int64_t n = A.ks;
     const ull* keys_t = A.keys + (int64_t)t * A.L * n;
-    uint32_t* perm = A.perm + (int64_t)t * n + start;
+    uint32_t* perm = A.perm + (int64_t)t * A.ps + start;
     const bool root_internal = A.child[e0] >= 0;
+    const bool unordered = A.s > 0 && !A.given_order;   // the slots do not arrive in the reference's order
 
     for (uint32_t p = tid; p < P0; p += NT) sidx[p] = p < m ? perm[p] : 0u;
     __syncthreads();
@@ -1097,14 +1089,14 @@ __global__ void __launch_bounds__(NT) k_bottom3(BottomArgs A) {
     };
 
     if (!root_internal) {        // the node is a Tip: its points must simply be in the reference's order
-        if (A.s > 0) { composite_sort(); for (uint32_t p = tid; p < m; p += NT) perm[p] = sidx[p]; }
+        if (unordered) { composite_sort(); for (uint32_t p = tid; p < m; p += NT) perm[p] = sidx[p]; }
         return;
     }
     if (tid == 0) { t_sz[0][0] = (uint16_t)m; t_ps[0][0] = 0; t_gid[0][0] = e0; }
     __syncthreads();
 
     int cur = 0;
-    bool need_check_order = A.s > 0;       // slots are not yet in the reference's incoming order
+    bool need_check_order = unordered;     // slots are not yet in the reference's incoming order
     const unsigned x0 = 8u * tid;          // first slot owned by this thread
     for (int j = 0;; ++j) {
         const int l = A.s + j;
@@ -1286,206 +1278,261 @@ static int launch_bottom_fast(rpf_handle* h, const BottomArgs& B, int nnodes_s, 
     return RPF_OK;
 }
 
-#define WS(h, var, type, slot, bytes)                                   \
-    type* var = (type*)(h)->ws_get((slot), (bytes));                    \
-    if (!var) return RPF_ERR_NOMEM;
+// Bottom phase over `nroots` consecutive nodes (BFS ids B.first_gid ..) of `tg` trees; every root holds at most
+// max_root points.  fast: uniform-layout kernel (needs: every node that splits holds >= 2 points and the subtrees
+// are at most BOT2_LEVELS levels deep); otherwise the generic entry-table kernel (needs B.range / B.lvl_pv).
+int rpf_bottom_launch(rpf_handle* h, const BottomArgs& B, int nroots, int tg, bool fast, unsigned max_root) {
+    if (nroots <= 0 || tg <= 0) return RPF_OK;
+    if (max_root > 8192) return rpf_fail(h, RPF_ERR_UNSUPPORTED, "bottom phase: node larger than 8192 points");
+    if (fast) {
+        const unsigned slots = std::max(256u, next_pow2_host(std::max(max_root, 1u)));
+        switch (slots) {
+            case 256: return launch_bottom_fast<32>(h, B, nroots, tg);
+            case 512: return launch_bottom_fast<64>(h, B, nroots, tg);
+            case 1024: return launch_bottom_fast<128>(h, B, nroots, tg);
+            case 2048: return launch_bottom_fast<256>(h, B, nroots, tg);
+            case 4096: return launch_bottom_fast<512>(h, B, nroots, tg);
+            case 8192: return launch_bottom_fast<1024>(h, B, nroots, tg);
+            default: return rpf_fail(h, RPF_ERR_ARG, "internal: bad bottom slot count");
+        }
+    }
+    if (max_root <= 256) return launch_bottom_generic<256, 128>(h, B, nroots, tg);
+    if (max_root <= 1024) return launch_bottom_generic<1024, 256>(h, B, nroots, tg);
+    if (max_root <= 4096) return launch_bottom_generic<4096, 512>(h, B, nroots, tg);
+    return launch_bottom_generic<8192, 1024>(h, B, nroots, tg);
+}
+int rpf_bottom_fast_levels() { int v = BOT2_TAB, l = 0; while (v > 1) { v >>= 1; ++l; } return l; }
 
-int rpf_build_impl(rpf_handle* h) {
-    const Topology& tp = h->topo;
-    const int64_t n = h->n, nn = tp.nnodes();
-    const int T = h->T, L = tp.L_eff;
-    int CAP = h->bottom_cap;
+// ---- geometry of a job: phase split and top-phase histogram shapes (pure host arithmetic on the topology) ----------
+void rpf_job_geometry(const Topology& tp, int cap_cfg, int Lk, JobGeom& G) {
+    G = JobGeom();
+    const int64_t nn = tp.nnodes();
+    int CAP = cap_cfg;
     {   // Tips larger than the configured capacity still get the reference's internal order as long as they fit the
-        // largest bottom-phase instance (8192 points): raise the capacity for this build.
+        // largest bottom-phase instance (8192 points): raise the capacity for this job.
         uint32_t maxleaf = 0;
         for (int64_t g = 0; g < nn; ++g) if (tp.child[g] < 0) maxleaf = std::max(maxleaf, tp.size[g]);
         if ((int64_t)maxleaf > CAP && maxleaf <= 8192) { CAP = 256; while ((uint32_t)CAP < maxleaf) CAP <<= 1; }
     }
-    h->leaf_order_exact = true;
+    G.CAP = CAP;
+    const int L = std::min(tp.L_eff, Lk);
+    G.L = L;
+    int s = tp.nlevels;
+    for (int l = 0; l < tp.nlevels; ++l) if ((int64_t)tp.lvl_maxsize[l] <= CAP) { s = l; break; }
+    G.s = s;
+    G.s_top = std::min(s, L);                        // levels 0..s_top-1 are split by the top phase
+    G.NTOP = tp.level_off[std::min(G.s_top + 1, tp.nlevels)];
+    G.order_exact = true;
+    if (s >= tp.nlevels) G.order_exact = false;     // leaves larger than the capacity: membership exact, order not
+    for (int l = 0; l < s && l < tp.nlevels; ++l)
+        for (int64_t g = tp.level_off[l]; g < tp.level_off[l + 1]; ++g) if (tp.child[g] < 0 && tp.size[g] > 1) G.order_exact = false;
+    G.nb_level.assign(std::max(L, 1), 0);
+    G.smem_level.assign(std::max(L, 1), 0);
+    G.HSZ = 1;
+    for (int l = 0; l < G.s_top; ++l) {
+        const int nodes = (int)(tp.level_off[l + 1] - tp.level_off[l]);
+        int nb;
+        if (nodes <= 512) { nb = std::min(HBINS_MAXNB, HBINS / (int)next_pow2_host((unsigned)nodes)); G.smem_level[l] = 1; }   // >= 64 bins per node
+        else { nb = 256; G.smem_level[l] = 0; }                                                         // global-atomic histogram
+        G.nb_level[l] = nb;
+        G.HSZ = std::max<int64_t>(G.HSZ, (int64_t)nodes * nb);
+    }
+    G.MAXTD = L + 1;
+    // fast bottom kernel: every node that splits at level >= s holds >= 2 points, and at most BOT2 levels below s
+    G.fast_bottom = (L - s) <= rpf_bottom_fast_levels();
+    for (int l = s; l < tp.nlevels && G.fast_bottom; ++l)
+        for (int64_t g = tp.level_off[l]; g < tp.level_off[l + 1]; ++g) if (tp.child[g] >= 0 && tp.size[g] < 2) { G.fast_bottom = false; break; }
+}
+size_t rpf_job_ws_per_tree(const JobGeom& G, int64_t n) {
+    return (G.s_top > 0 ? (size_t)n * 10 : 0) + (size_t)G.HSZ * 4 + (size_t)G.NTOP * (sizeof(NodeSel) + 4 + (size_t)G.MAXTD * 8) + 4096;
+}
+
+// Runs the level-synchronous build of one job (see BuildJob in rpf_internal.h).  Everything is enqueued on the
+// engine's stream; the host tables travel through the page-locked staging ring, so the call does not synchronise.
+int rpf_run_job(rpf_handle* h, BuildJob& J) {
+    const Topology& tp = *J.tp;
+    const int64_t n = J.n, nn = tp.nnodes();
+    const int tg = J.tg;
+    JobGeom G;
+    rpf_job_geometry(tp, h->bottom_cap, J.Lk, G);
+    if (h->force_generic_bottom) G.fast_bottom = false;
+    const int L = G.L, s = G.s, s_top = G.s_top;
+    const int64_t NTOP = G.NTOP, HSZ = G.HSZ;
+    const int MAXTD = G.MAXTD;
+    J.order_exact = G.order_exact;
+    if (s_top > 0 && NTOP > 65535) return rpf_fail(h, RPF_ERR_UNSUPPORTED, "too many top-phase nodes for 16-bit labels");
+
+    if (L == 0 || n == 0) {   // every tree is a single Tip holding the points in input order
+        if (n > 0) {
+            const int64_t tot = n * tg;
+            RPF_LAUNCH(h, PH_MISC, k_iota_perm, (unsigned)((tot + 255) / 256), 256, 0, J.perm, n, J.ps, tg);
+        }
+        return RPF_OK;
+    }
+
+    // ---- bottom-phase tables: per level-s node, the BFS id range of its descendants at each deeper level
+    int nnodes_s = 0, nlb = 0;
+    std::vector<int2> rg; std::vector<uint32_t> pv;
+    if (s < tp.nlevels) {
+        nnodes_s = (int)(tp.level_off[s + 1] - tp.level_off[s]);
+        nlb = std::max(1, tp.nlevels - s);
+        pv.resize(tp.nlevels);
+        for (int l = 0; l < tp.nlevels; ++l) pv[l] = next_pow2_host(std::max<uint32_t>(tp.lvl_maxsize[l], 1));
+        if (!G.fast_bottom) {
+            rg.assign((size_t)nnodes_s * nlb, make_int2(0, 0));
+            for (int e = 0; e < nnodes_s; ++e) {
+                int64_t lo = tp.level_off[s] + e, hi = lo + 1;
+                for (int j = 0; j < nlb; ++j) {
+                    int64_t fi = -1, li = -1;
+                    for (int64_t g = lo; g < hi; ++g) if (tp.child[g] >= 0) { if (fi < 0) fi = g; li = g; }
+                    if (fi < 0) break;
+                    rg[(size_t)e * nlb + j] = make_int2((int)lo, (int)hi);
+                    lo = tp.child[fi]; hi = (int64_t)tp.child[li] + 2;
+                }
+            }
+        }
+    }
+    // ---- one staged upload for all host tables of this job
+    int rc = h->stage_begin(rg.size() * sizeof(int2) + pv.size() * 4 + (size_t)std::max(L, 1) * 4 + 1024);
+    if (rc) return rc;
+    const int2* range = rg.empty() ? nullptr : h->stage_put(rg.data(), rg.size());
+    const uint32_t* lvlpv = pv.empty() ? nullptr : h->stage_put(pv.data(), pv.size());
+    const int* nbdev = h->stage_put(G.nb_level.data(), G.nb_level.size());
+    rc = h->stage_flush();
+    if (rc) return rc;
+
+    if (s_top > 0) {
+        uint16_t* label = (uint16_t*)h->ws_get(WS_LABEL, (size_t)tg * n * 2);
+        uint32_t* hist = (uint32_t*)h->ws_get(WS_HIST, (size_t)tg * HSZ * 4);
+        NodeSel* sel = (NodeSel*)h->ws_get(WS_SEL, (size_t)tg * NTOP * sizeof(NodeSel));
+        ull* cand = (ull*)h->ws_get(WS_CAND, (size_t)tg * n * 8);
+        uint32_t* cand_total = (uint32_t*)h->ws_get(WS_CANDTOT, (size_t)tg * 8);      // [tg] candidate totals + [tg] margin-tracking flags
+        ull* pivots = (ull*)h->ws_get(WS_PIVOTS, (size_t)tg * NTOP * MAXTD * 8);
+        uint32_t* fill = (uint32_t*)h->ws_get(WS_FILL, (size_t)tg * NTOP * 4);
+        double* binlo = (double*)h->ws_get(WS_BINLO, (size_t)tg * J.Lk * 8);
+        double* binscale = (double*)h->ws_get(WS_BINSC, (size_t)tg * J.Lk * 8);
+        if (!label || !hist || !sel || !cand || !cand_total || !pivots || !fill || !binlo || !binscale) return RPF_ERR_NOMEM;
+        TopArgs A{};
+        A.n = n; A.ks = J.ks; A.ps = J.ps; A.Tg = tg; A.L = J.Lk; A.NTOP = (int)NTOP; A.HSZ = (int)HSZ; A.MAXTD = MAXTD; A.gt0 = J.gt0; A.nn_all = J.ns;
+        A.vec = ((n & 3) == 0 && (J.ks & 3) == 0 && ((uintptr_t)J.keys & 31) == 0) ? 1 : 0;
+        A.keys = J.keys; A.label = label; A.child = J.d_child; A.nstart = J.d_start;
+        A.nsize = J.d_size; A.binlo = binlo; A.binscale = binscale;
+        A.kmin = J.kmin; A.kmax = J.kmax; A.hist = hist; A.sel = sel;
+        A.cand = cand; A.cand_total = cand_total; A.track_any = cand_total + tg; A.pivots = pivots;
+        A.fill = fill; A.perm = J.perm; A.thr = J.thr; A.mlo = J.mlo; A.mhi = J.mhi;
+        RPF_CUDA(h, cudaFuncSetAttribute(k_top_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, HBINS * 2));
+        RPF_LAUNCH(h, PH_MISC, k_bin_setup, (unsigned)((tg * J.Lk + 127) / 128), 128, 0, A, nbdev, s_top);
+        RPF_CUDA(h, cudaMemsetAsync(fill, 0, (size_t)tg * NTOP * 4, h->stream));
+        const unsigned nchunks = (unsigned)((n + TOP_CH - 1) / TOP_CH);
+        bool all_top_internal = true;
+        for (int l = 0; l < s_top; ++l) {
+            A.l = l; A.node0 = (int)tp.level_off[l]; A.nnodes = (int)(tp.level_off[l + 1] - tp.level_off[l]);
+            A.NB = G.nb_level[l]; A.smem_hist = G.smem_level[l];
+            A.child0 = (int)tp.level_off[l + 1];
+            A.all_internal = 1;
+            for (int64_t g = tp.level_off[l]; g < tp.level_off[l + 1]; ++g) if (tp.child[g] < 0) { A.all_internal = 0; break; }
+            all_top_internal = all_top_internal && A.all_internal;
+            A.scatter_fast = (all_top_internal && 2 * A.nnodes <= SCAT_MAX) ? 1 : 0;
+            RPF_CUDA(h, cudaMemsetAsync(hist, 0, (size_t)tg * HSZ * 4, h->stream));
+            RPF_CUDA(h, cudaMemsetAsync(cand_total, 0, (size_t)tg * 8, h->stream));
+            dim3 gs(nchunks, (unsigned)tg), gn((unsigned)A.nnodes, (unsigned)tg);
+            const size_t hs = A.smem_hist ? ((size_t)A.nnodes * A.NB + 1) / 2 * 4 : 0;     // 16-bit counters
+            RPF_LAUNCH(h, PH_TOP_HIST, k_top_hist, gs, TOP_NT, hs, A);
+            RPF_LAUNCH(h, PH_TOP_PICK, k_top_pick, gn, 256, 0, A);
+            RPF_LAUNCH(h, PH_TOP_COMPACT, k_top_compact, gs, TOP_NT, 0, A);
+            RPF_LAUNCH(h, PH_TOP_FINISH, k_top_finish_warp, (unsigned)(((int64_t)A.nnodes * tg + FW_WARPS - 1) / FW_WARPS), FW_WARPS * 32, 0, A);
+            RPF_LAUNCH(h, PH_TOP_FINISH, k_top_finish, gn, 512, 0, A);
+            RPF_LAUNCH(h, PH_TOP_TIES, k_top_ties, gn, 512, 0, A);
+            RPF_LAUNCH(h, PH_TOP_RELABEL, k_top_relabel, gs, TOP_NT, 0, A, (int)(l == s_top - 1));
+            RPF_LAUNCH(h, PH_MISC, k_top_finalize, (unsigned)((A.nnodes * tg + 127) / 128), 128, 0, A);
+        }
+    } else {
+        const int64_t tot = n * tg;
+        RPF_LAUNCH(h, PH_MISC, k_iota_perm, (unsigned)((tot + 255) / 256), 256, 0, J.perm, n, J.ps, tg);
+    }
+
+    if (s < tp.nlevels) {
+        BottomArgs B{};
+        B.ks = J.ks; B.ps = J.ps; B.nn_all = J.ns; B.L = J.Lk; B.s = s; B.nlb = nlb; B.gt0 = J.gt0; B.first_gid = (int)tp.level_off[s];
+        B.given_order = 0;
+        B.keys = J.keys; B.perm = J.perm; B.child = J.d_child; B.nstart = J.d_start; B.nsize = J.d_size;
+        B.range = range; B.lvl_pv = lvlpv; B.thr = J.thr; B.mlo = J.mlo; B.mhi = J.mhi;
+        rc = rpf_bottom_launch(h, B, nnodes_s, tg, G.fast_bottom, tp.lvl_maxsize[s]);
+        if (rc) return rc;
+    }
+    return RPF_OK;
+}
+
+#define WS(h, var, type, slot, bytes)                                   \
+    type* var = (type*)(h)->ws_get((slot), (bytes));                    \
+    if (!var) return RPF_ERR_NOMEM;
+
+// forestBatch: the whole data set is one chunk (Batch.hs:48-63)
+int rpf_build_impl(rpf_handle* h) {
+    const Topology& tp = h->topo;
+    const int64_t n = h->n, nn = tp.nnodes();
+    const int T = h->T, L = tp.L_eff;
 
     // ---- result arrays (kept across builds of the same shape)
-    const size_t node_bytes = sizeof(double) * (size_t)(T * nn), perm_bytes = sizeof(uint32_t) * (size_t)std::max<int64_t>(T * n, 1);
+    int rc = rpf_alloc_forest(h, nn, n);
+    if (rc) return rc;
+    RPF_CUDA(h, cudaMemsetAsync(h->d_thr, 0, h->res_node_bytes, h->stream));
+    RPF_CUDA(h, cudaMemsetAsync(h->d_mlo, 0, h->res_node_bytes, h->stream));
+    RPF_CUDA(h, cudaMemsetAsync(h->d_mhi, 0, h->res_node_bytes, h->stream));
+
+    JobGeom G;
+    rpf_job_geometry(tp, h->bottom_cap, L, G);
+    h->leaf_order_exact = G.order_exact;
+
+    // ---- tree group size from the memory budget (free memory + what the workspace already holds)
+    size_t freeB = 0, totalB = 0;
+    RPF_CUDA(h, cudaMemGetInfo(&freeB, &totalB));
+    const size_t per_tree = (size_t)L * n * 8 + rpf_job_ws_per_tree(G, n);
+    const size_t budget = (size_t)((double)(freeB + h->ws_bytes) * 0.7);
+    if (per_tree > budget) return rpf_fail(h, RPF_ERR_NOMEM, "not enough device memory for one tree's keys");
+    const int Tg = (int)std::min<size_t>((size_t)T, std::max<size_t>(1, budget / per_tree));
+
+    WS(h, keys, ull, WS_KEYS, (size_t)Tg * std::max(L, 1) * std::max<int64_t>(n, 1) * 8);
+    WS(h, kmin, ull, WS_KMIN, (size_t)Tg * std::max(L, 1) * 8);
+    WS(h, kmax, ull, WS_KMAX, (size_t)Tg * std::max(L, 1) * 8);
+
+    for (int t0 = 0; t0 < T; t0 += Tg) {
+        const int tg = std::min(Tg, T - t0);
+        if (L > 0 && n > 0) {   // K1
+            RPF_CUDA(h, cudaMemsetAsync(kmin, 0xff, (size_t)tg * L * 8, h->stream));
+            RPF_CUDA(h, cudaMemsetAsync(kmax, 0x00, (size_t)tg * L * 8, h->stream));
+            rc = rpf_project_launch(h, PH_PROJECT, h->dX, n, t0, tg, L, true, keys, n, kmin, kmax);
+            if (rc) return rc;
+        }
+        BuildJob J{};
+        J.tp = &tp; J.d_start = h->d_node_start; J.d_size = h->d_node_size; J.d_child = h->d_node_child;
+        J.n = n; J.ks = n; J.ps = n; J.ns = nn; J.Lk = L;
+        J.keys = keys; J.kmin = kmin; J.kmax = kmax;
+        J.perm = h->d_perm + (int64_t)t0 * n; J.thr = h->d_thr; J.mlo = h->d_mlo; J.mhi = h->d_mhi;
+        J.gt0 = t0; J.tg = tg;
+        rc = rpf_run_job(h, J);
+        if (rc) return rc;
+    }
+    return RPF_OK;
+}
+
+// (re)allocate the forest arrays thr/mlo/mhi [T][nn] and perm [T][n]
+int rpf_alloc_forest(rpf_handle* h, int64_t nn, int64_t n) {
+    const int T = h->T;
+    const size_t node_bytes = sizeof(double) * (size_t)std::max<int64_t>(T * nn, 1), perm_bytes = sizeof(uint32_t) * (size_t)std::max<int64_t>(T * n, 1);
     if (h->res_node_bytes != node_bytes || h->res_perm_bytes != perm_bytes || !h->d_thr) {
         if (h->d_thr) { cudaFree(h->d_thr); cudaFree(h->d_mlo); cudaFree(h->d_mhi); cudaFree(h->d_perm); h->d_thr = h->d_mlo = h->d_mhi = nullptr; h->d_perm = nullptr; }
+        h->res_node_bytes = h->res_perm_bytes = 0;
         RPF_CUDA(h, cudaMalloc(&h->d_thr, node_bytes));
         RPF_CUDA(h, cudaMalloc(&h->d_mlo, node_bytes));
         RPF_CUDA(h, cudaMalloc(&h->d_mhi, node_bytes));
         RPF_CUDA(h, cudaMalloc(&h->d_perm, perm_bytes));
         h->res_node_bytes = node_bytes; h->res_perm_bytes = perm_bytes;
     }
-    RPF_CUDA(h, cudaMemsetAsync(h->d_thr, 0, node_bytes, h->stream));
-    RPF_CUDA(h, cudaMemsetAsync(h->d_mlo, 0, node_bytes, h->stream));
-    RPF_CUDA(h, cudaMemsetAsync(h->d_mhi, 0, node_bytes, h->stream));
-
-    // ---- phase split: first level whose nodes all fit the shared-memory capacity
-    int s = tp.nlevels;
-    for (int l = 0; l < tp.nlevels; ++l) if ((int64_t)tp.lvl_maxsize[l] <= CAP) { s = l; break; }
-    const int s_top = std::min(s, L);                       // levels 0..s_top-1 are split by the top phase
-    const int64_t NTOP = tp.level_off[std::min(s_top + 1, tp.nlevels)];
-    if (s_top > 0 && NTOP > 65535) return rpf_fail(h, RPF_ERR_UNSUPPORTED, "too many top-phase nodes for 16-bit labels");
-    if (s >= tp.nlevels) h->leaf_order_exact = false;     // leaves larger than the capacity: membership exact, order not
-    for (int l = 0; l < s && l < tp.nlevels; ++l)
-        for (int64_t g = tp.level_off[l]; g < tp.level_off[l + 1]; ++g) if (tp.child[g] < 0) h->leaf_order_exact = false;
-
-    if (L == 0 || n == 0) {   // every tree is a single Tip holding the points in input order
-        if (n > 0) {
-            const int64_t tot = n * T;
-            RPF_LAUNCH(h, PH_MISC, k_iota_perm, (unsigned)((tot + 255) / 256), 256, 0, h->d_perm, n, T);
-        }
-        return RPF_OK;
-    }
-
-    // ---- per-level histogram geometry for the top phase
-    std::vector<int> nb_level(std::max(L, 1), 0), smem_level(std::max(L, 1), 0);
-    int64_t HSZ = 1;
-    for (int l = 0; l < s_top; ++l) {
-        const int nodes = (int)(tp.level_off[l + 1] - tp.level_off[l]);
-        int nb;
-        if (nodes <= 512) { nb = std::min(HBINS_MAXNB, HBINS / (int)next_pow2_host((unsigned)nodes)); smem_level[l] = 1; }   // >= 64 bins per node
-        else { nb = 256; smem_level[l] = 0; }                                                           // global-atomic histogram
-        nb_level[l] = nb;
-        HSZ = std::max<int64_t>(HSZ, (int64_t)nodes * nb);
-    }
-    const int MAXTD = L + 1;
-
-    // ---- tree group size from the memory budget (free memory + what the workspace already holds)
-    size_t freeB = 0, totalB = 0;
-    RPF_CUDA(h, cudaMemGetInfo(&freeB, &totalB));
-    const size_t per_tree = (size_t)L * n * 8 + (s_top > 0 ? (size_t)n * 10 : 0) + (size_t)HSZ * 4 +
-                            (size_t)NTOP * (sizeof(NodeSel) + 4 + (size_t)MAXTD * 8) + 4096;
-    const size_t budget = (size_t)((double)(freeB + h->ws_bytes) * 0.7);
-    if (per_tree > budget) return rpf_fail(h, RPF_ERR_NOMEM, "not enough device memory for one tree's keys");
-    const int Tg = (int)std::min<size_t>((size_t)T, std::max<size_t>(1, budget / per_tree));
-
-    WS(h, keys, ull, WS_KEYS, (size_t)Tg * L * n * 8);
-    WS(h, kmin, ull, WS_KMIN, (size_t)Tg * L * 8);
-    WS(h, kmax, ull, WS_KMAX, (size_t)Tg * L * 8);
-    uint16_t* label = nullptr; uint32_t *hist = nullptr, *cand_total = nullptr, *fill = nullptr; NodeSel* sel = nullptr;
-    ull *cand = nullptr, *pivots = nullptr; double *binlo = nullptr, *binscale = nullptr; int* nbdev = nullptr;
-    if (s_top > 0) {
-        label = (uint16_t*)h->ws_get(WS_LABEL, (size_t)Tg * n * 2);
-        hist = (uint32_t*)h->ws_get(WS_HIST, (size_t)Tg * HSZ * 4);
-        sel = (NodeSel*)h->ws_get(WS_SEL, (size_t)Tg * NTOP * sizeof(NodeSel));
-        cand = (ull*)h->ws_get(WS_CAND, (size_t)Tg * n * 8);
-        cand_total = (uint32_t*)h->ws_get(WS_CANDTOT, (size_t)Tg * 8);      // [Tg] candidate totals + [Tg] margin-tracking flags
-        pivots = (ull*)h->ws_get(WS_PIVOTS, (size_t)Tg * NTOP * MAXTD * 8);
-        fill = (uint32_t*)h->ws_get(WS_FILL, (size_t)Tg * NTOP * 4);
-        binlo = (double*)h->ws_get(WS_BINLO, (size_t)Tg * L * 8);
-        binscale = (double*)h->ws_get(WS_BINSC, (size_t)Tg * L * 8);
-        nbdev = (int*)h->ws_get(WS_NBDEV, (size_t)L * 4);
-        if (!label || !hist || !sel || !cand || !cand_total || !pivots || !fill || !binlo || !binscale || !nbdev) return RPF_ERR_NOMEM;
-        RPF_CUDA(h, cudaMemcpyAsync(nbdev, nb_level.data(), (size_t)L * 4, cudaMemcpyHostToDevice, h->stream));
-    }
-
-    // ---- bottom-phase tables: per level-s node, the BFS id range of its descendants at each deeper level
-    int nnodes_s = 0, nlb = 0;
-    int2* range = nullptr; uint32_t* lvlpv = nullptr;
-    std::vector<int2> rg; std::vector<uint32_t> pv;
-    if (s < tp.nlevels) {
-        nnodes_s = (int)(tp.level_off[s + 1] - tp.level_off[s]);
-        nlb = std::max(1, tp.nlevels - s);
-        rg.assign((size_t)nnodes_s * nlb, make_int2(0, 0));
-        for (int e = 0; e < nnodes_s; ++e) {
-            int64_t lo = tp.level_off[s] + e, hi = lo + 1;
-            for (int j = 0; j < nlb; ++j) {
-                int64_t fi = -1, li = -1;
-                for (int64_t g = lo; g < hi; ++g) if (tp.child[g] >= 0) { if (fi < 0) fi = g; li = g; }
-                if (fi < 0) break;
-                rg[(size_t)e * nlb + j] = make_int2((int)lo, (int)hi);
-                lo = tp.child[fi]; hi = (int64_t)tp.child[li] + 2;
-            }
-        }
-        pv.resize(tp.nlevels);
-        for (int l = 0; l < tp.nlevels; ++l) pv[l] = next_pow2_host(std::max<uint32_t>(tp.lvl_maxsize[l], 1));
-        range = (int2*)h->ws_get(WS_RANGE, rg.size() * sizeof(int2));
-        lvlpv = (uint32_t*)h->ws_get(WS_LVLPV, pv.size() * 4);
-        if (!range || !lvlpv) return RPF_ERR_NOMEM;
-        RPF_CUDA(h, cudaMemcpyAsync(range, rg.data(), rg.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
-        RPF_CUDA(h, cudaMemcpyAsync(lvlpv, pv.data(), pv.size() * 4, cudaMemcpyHostToDevice, h->stream));
-    }
-    // fast bottom kernel: needs non-empty children slots (minLeaf >= 1) and <= BOT2_TAB segments at the deepest level
-    int bot2_levels = 0; { int v = BOT2_TAB; while (v > 1) { v >>= 1; ++bot2_levels; } }
-    const bool fast_bottom = tp.minLeaf >= 1 && (L - s) <= bot2_levels && !h->force_generic_bottom;
-
-    for (int t0 = 0; t0 < T; t0 += Tg) {
-        const int tg = std::min(Tg, T - t0);
-        // K1
-        RPF_CUDA(h, cudaMemsetAsync(kmin, 0xff, (size_t)tg * L * 8, h->stream));
-        RPF_CUDA(h, cudaMemsetAsync(kmax, 0x00, (size_t)tg * L * 8, h->stream));
-        int rc = rpf_project_launch(h, PH_PROJECT, h->dX, n, t0, tg, L, true, keys, kmin, kmax);
-        if (rc) return rc;
-
-        uint32_t* perm_g = h->d_perm + (int64_t)t0 * n;
-        if (s_top > 0) {
-            TopArgs A{};
-            A.n = n; A.Tg = tg; A.L = L; A.NTOP = (int)NTOP; A.HSZ = (int)HSZ; A.MAXTD = MAXTD; A.gt0 = t0; A.nn_all = nn;
-            A.keys = keys; A.label = label; A.child = h->d_node_child; A.nstart = h->d_node_start;
-            A.nsize = h->d_node_size; A.binlo = binlo; A.binscale = binscale;
-            A.kmin = kmin; A.kmax = kmax; A.hist = hist; A.sel = sel;
-            A.cand = cand; A.cand_total = cand_total; A.track_any = cand_total + Tg; A.pivots = pivots;
-            A.fill = fill; A.perm = perm_g; A.thr = h->d_thr; A.mlo = h->d_mlo; A.mhi = h->d_mhi;
-            RPF_CUDA(h, cudaFuncSetAttribute(k_top_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, HBINS * 2));
-            RPF_LAUNCH(h, PH_MISC, k_bin_setup, (unsigned)((tg * L + 127) / 128), 128, 0, A, nbdev, s_top);
-            RPF_CUDA(h, cudaMemsetAsync(fill, 0, (size_t)tg * NTOP * 4, h->stream));
-            const unsigned nchunks = (unsigned)((n + TOP_CH - 1) / TOP_CH);
-            bool all_top_internal = true;
-            for (int l = 0; l < s_top; ++l) {
-                A.l = l; A.node0 = (int)tp.level_off[l]; A.nnodes = (int)(tp.level_off[l + 1] - tp.level_off[l]);
-                A.NB = nb_level[l]; A.smem_hist = smem_level[l];
-                A.child0 = (int)tp.level_off[l + 1];
-                A.all_internal = 1;
-                for (int64_t g = tp.level_off[l]; g < tp.level_off[l + 1]; ++g) if (tp.child[g] < 0) { A.all_internal = 0; break; }
-                all_top_internal = all_top_internal && A.all_internal;
-                A.scatter_fast = (all_top_internal && 2 * A.nnodes <= SCAT_MAX) ? 1 : 0;
-                RPF_CUDA(h, cudaMemsetAsync(hist, 0, (size_t)tg * HSZ * 4, h->stream));
-                RPF_CUDA(h, cudaMemsetAsync(cand_total, 0, (size_t)Tg * 8, h->stream));
-                dim3 gs(nchunks, (unsigned)tg), gn((unsigned)A.nnodes, (unsigned)tg);
-                const size_t hs = A.smem_hist ? ((size_t)A.nnodes * A.NB + 1) / 2 * 4 : 0;     // 16-bit counters
-                RPF_LAUNCH(h, PH_TOP_HIST, k_top_hist, gs, TOP_NT, hs, A);
-                RPF_LAUNCH(h, PH_TOP_PICK, k_top_pick, gn, 256, 0, A);
-                RPF_LAUNCH(h, PH_TOP_COMPACT, k_top_compact, gs, TOP_NT, 0, A);
-                RPF_LAUNCH(h, PH_TOP_FINISH, k_top_finish_warp, (unsigned)(((int64_t)A.nnodes * tg + FW_WARPS - 1) / FW_WARPS), FW_WARPS * 32, 0, A);
-                RPF_LAUNCH(h, PH_TOP_FINISH, k_top_finish, gn, 512, 0, A);
-                RPF_LAUNCH(h, PH_TOP_TIES, k_top_ties, gn, 512, 0, A);
-                RPF_LAUNCH(h, PH_TOP_RELABEL, k_top_relabel, gs, TOP_NT, 0, A, (int)(l == s_top - 1));
-                RPF_LAUNCH(h, PH_MISC, k_top_finalize, (unsigned)((A.nnodes * tg + 127) / 128), 128, 0, A);
-            }
-        } else {
-            const int64_t tot = n * tg;
-            RPF_LAUNCH(h, PH_MISC, k_iota_perm, (unsigned)((tot + 255) / 256), 256, 0, perm_g, n, tg);
-        }
-
-        if (s < tp.nlevels) {
-            BottomArgs B{};
-            B.n = n; B.nn_all = nn; B.L = L; B.s = s; B.nlb = nlb; B.gt0 = t0; B.first_gid = (int)tp.level_off[s];
-            B.keys = keys; B.perm = perm_g; B.child = h->d_node_child; B.nstart = h->d_node_start; B.nsize = h->d_node_size;
-            B.range = range; B.lvl_pv = lvlpv; B.thr = h->d_thr; B.mlo = h->d_mlo; B.mhi = h->d_mhi;
-            int rc2;
-            if (fast_bottom) {
-                const unsigned slots = std::max(256u, next_pow2_host(tp.lvl_maxsize[s]));
-                switch (slots) {
-                    case 256: rc2 = launch_bottom_fast<32>(h, B, nnodes_s, tg); break;
-                    case 512: rc2 = launch_bottom_fast<64>(h, B, nnodes_s, tg); break;
-                    case 1024: rc2 = launch_bottom_fast<128>(h, B, nnodes_s, tg); break;
-                    case 2048: rc2 = launch_bottom_fast<256>(h, B, nnodes_s, tg); break;
-                    case 4096: rc2 = launch_bottom_fast<512>(h, B, nnodes_s, tg); break;
-                    case 8192: rc2 = launch_bottom_fast<1024>(h, B, nnodes_s, tg); break;
-                    default: return rpf_fail(h, RPF_ERR_ARG, "internal: bad bottom slot count");
-                }
-            } else {
-                if (CAP <= 256) rc2 = launch_bottom_generic<256, 128>(h, B, nnodes_s, tg);
-                else if (CAP <= 1024) rc2 = launch_bottom_generic<1024, 256>(h, B, nnodes_s, tg);
-                else if (CAP <= 4096) rc2 = launch_bottom_generic<4096, 512>(h, B, nnodes_s, tg);
-                else rc2 = launch_bottom_generic<8192, 1024>(h, B, nnodes_s, tg);
-            }
-            if (rc2) return rc2;
-        }
-    }
-    RPF_CUDA(h, cudaStreamSynchronize(h->stream));   // host staging vectors (rg, pv, nb_level) go out of scope
     return RPF_OK;
 }
 
 // projections of a query batch onto every (tree, level) hyperplane: keysQ[(t*L + l) * nq + q]
 int rpf_project_queries(rpf_handle* h, const double* dQ, int64_t nq, double* d_keysQ) {
-    return rpf_project_launch(h, PH_Q_PROJECT, dQ, nq, 0, h->T, h->topo.L_eff, false, d_keysQ, nullptr, nullptr);
+    return rpf_project_launch(h, PH_Q_PROJECT, dQ, nq, 0, h->T, h->topo.L_eff, false, d_keysQ, nq, nullptr, nullptr);
 }

@@ -67,9 +67,61 @@ void rpf_handle::ws_free_all() {
     ws_bytes = 0;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// staging ring (page-locked host tables -> device, one async copy per flush)
+// ---------------------------------------------------------------------------------------------------
+int rpf_handle::stage_begin(size_t bytes) {
+    stage_cur = (stage_cur + 1) % RPF_STAGE_SLOTS;
+    StageSlot& S = stage[stage_cur];
+    if (!S.ev && cudaEventCreateWithFlags(&S.ev, cudaEventDisableTiming) != cudaSuccess) return rpf_fail(this, RPF_ERR_CUDA, "stage: event");
+    if (S.pending) { cudaEventSynchronize(S.ev); S.pending = false; }      // the slot's previous upload has left host memory
+    bytes += 4096;
+    if (S.cap < bytes) {
+        // kernels of an earlier job may still read the old device block: cudaFree waits for them (growth is rare)
+        if (S.h) cudaFreeHost(S.h);
+        if (S.d) cudaFree(S.d);
+        S.h = nullptr; S.d = nullptr; S.cap = 0;
+        const size_t want = bytes + bytes / 4;
+        if (cudaMallocHost(&S.h, want) != cudaSuccess || cudaMalloc(&S.d, want) != cudaSuccess) {
+            cudaGetLastError();
+            return rpf_fail(this, RPF_ERR_NOMEM, "stage: allocation failed");
+        }
+        S.cap = want;
+    }
+    stage_off = 0; stage_flushed = 0;
+    return RPF_OK;
+}
+void* rpf_handle::stage_put_raw(const void* src, size_t bytes) {
+    StageSlot& S = stage[stage_cur];
+    const size_t off = (stage_off + 255) & ~(size_t)255;
+    if (off + bytes > S.cap) { err = "stage: overflow (internal sizing error)"; return nullptr; }
+    if (bytes) std::memcpy(S.h + off, src, bytes);
+    stage_off = off + bytes;
+    return S.d + off;
+}
+int rpf_handle::stage_flush() {
+    StageSlot& S = stage[stage_cur];
+    if (stage_off > stage_flushed) {
+        RPF_CUDA(this, cudaMemcpyAsync(S.d + stage_flushed, S.h + stage_flushed, stage_off - stage_flushed, cudaMemcpyHostToDevice, stream));
+        RPF_CUDA(this, cudaEventRecord(S.ev, stream));
+        S.pending = true;
+        stage_flushed = stage_off;
+    }
+    return RPF_OK;
+}
+void rpf_handle::stage_free_all() {
+    for (auto& S : stage) {
+        if (S.h) cudaFreeHost(S.h);
+        if (S.d) cudaFree(S.d);
+        if (S.ev) cudaEventDestroy(S.ev);
+        S = StageSlot();
+    }
+    stage_cur = -1;
+}
+
 static const char* kPhaseNames[PH_COUNT] = {
     "project", "top_hist", "top_pick", "top_compact", "top_finish", "top_ties", "top_relabel", "bottom",
-    "q_project", "q_traverse", "q_knn", "q_candidates", "truth", "recall", "merge", "misc"};
+    "q_project", "q_traverse", "q_knn", "q_candidates", "truth", "recall", "merge", "stream", "misc"};
 
 // ---------------------------------------------------------------------------------------------------
 // topology: Internal.hs:289 (Tip iff ixLev >= maxDepth || length xs' <= minLeaf), :495/:503 (nh = n div 2)
@@ -186,6 +238,22 @@ static int upload_hyperplanes(rpf_handle* h) {
 
 #define RPF_SETDEV(h) RPF_CUDA(h, cudaSetDevice((h)->device))
 
+// device copies of h->topo (start, size, child, depth per BFS node)
+int rpf_upload_topology(rpf_handle* h) {
+    const Topology& tp = h->topo;
+    free_topo_dev(h);
+    const size_t nn = (size_t)tp.nnodes();
+    RPF_CUDA(h, cudaMalloc(&h->d_node_start, nn * 4));
+    RPF_CUDA(h, cudaMalloc(&h->d_node_size, nn * 4));
+    RPF_CUDA(h, cudaMalloc(&h->d_node_child, nn * 4));
+    RPF_CUDA(h, cudaMalloc(&h->d_node_depth, nn * 4));
+    RPF_CUDA(h, cudaMemcpy(h->d_node_start, tp.start.data(), nn * 4, cudaMemcpyHostToDevice));
+    RPF_CUDA(h, cudaMemcpy(h->d_node_size, tp.size.data(), nn * 4, cudaMemcpyHostToDevice));
+    RPF_CUDA(h, cudaMemcpy(h->d_node_child, tp.child.data(), nn * 4, cudaMemcpyHostToDevice));
+    RPF_CUDA(h, cudaMemcpy(h->d_node_depth, tp.depth.data(), nn * 4, cudaMemcpyHostToDevice));
+    return RPF_OK;
+}
+
 extern "C" {
 
 int rpf_abi_version(void) { return 1; }
@@ -214,7 +282,9 @@ void rpf_destroy(rpf_handle* h) {
     cudaStreamSynchronize(h->stream);
     if (h->ownX && h->dX) cudaFree((void*)h->dX);
     free_hp_dev(h); free_topo_dev(h); free_forest_dev(h);
+    if (h->stream_pool) cudaFree(h->stream_pool);
     h->ws_free_all();
+    h->stage_free_all();
     for (auto e : h->event_pool) cudaEventDestroy(e);
     if (h->ev_begin) cudaEventDestroy(h->ev_begin);
     if (h->ev_end) cudaEventDestroy(h->ev_end);
@@ -347,6 +417,7 @@ void rpf_rptree_cfg(int64_t minLeaf, int64_t n, int64_t d, int64_t* maxDepth, in
 }
 
 int rpf_leaf_order_exact(const rpf_handle* h) { return h ? (h->leaf_order_exact ? 1 : 0) : -1; }
+int64_t rpf_points_lost(const rpf_handle* h) { return h ? h->stream_lost : -1; }
 
 int64_t rpf_hyperplane_nnz(const rpf_handle* h) { return h ? (int64_t)h->hp_idx.size() : -1; }
 
@@ -358,8 +429,7 @@ int rpf_get_hyperplanes(const rpf_handle* h, int64_t* off, int32_t* idx, double*
     return RPF_OK;
 }
 
-int rpf_build(rpf_handle* h, int32_t maxDepth, int32_t minLeaf) {
-    if (!h) return RPF_ERR_ARG;
+static int check_build_args(rpf_handle* h, int32_t maxDepth, int32_t minLeaf) {
     if (!h->dX && h->n != 0) return rpf_fail(h, RPF_ERR_STATE, "build: call rpf_set_points first");
     if (h->d < 1) return rpf_fail(h, RPF_ERR_STATE, "build: call rpf_set_points first");
     if (h->T < 1) return rpf_fail(h, RPF_ERR_STATE, "build: call rpf_set_hyperplanes / rpf_gen_hyperplanes first");
@@ -367,22 +437,21 @@ int rpf_build(rpf_handle* h, int32_t maxDepth, int32_t minLeaf) {
     if (maxDepth > h->hpDepth) return rpf_fail(h, RPF_ERR_ARG, "build: maxDepth exceeds the number of hyperplanes per tree");
     if (maxDepth > 62) return rpf_fail(h, RPF_ERR_UNSUPPORTED, "build: maxDepth > 62");
     for (int32_t q : h->hp_idx) if (q < 0 || q >= h->d) return rpf_fail(h, RPF_ERR_ARG, "build: hyperplane component index out of range");
+    return RPF_OK;
+}
+
+int rpf_build(rpf_handle* h, int32_t maxDepth, int32_t minLeaf) {
+    if (!h) return RPF_ERR_ARG;
+    int rc = check_build_args(h, maxDepth, minLeaf);
+    if (rc) return rc;
     RPF_SETDEV(h);
     build_topology(h->topo, h->n, maxDepth, minLeaf);
-    const Topology& tp = h->topo;
-    free_topo_dev(h);
-    const size_t nn = (size_t)tp.nnodes();
-    RPF_CUDA(h, cudaMalloc(&h->d_node_start, nn * 4));
-    RPF_CUDA(h, cudaMalloc(&h->d_node_size, nn * 4));
-    RPF_CUDA(h, cudaMalloc(&h->d_node_child, nn * 4));
-    RPF_CUDA(h, cudaMalloc(&h->d_node_depth, nn * 4));
-    RPF_CUDA(h, cudaMemcpy(h->d_node_start, tp.start.data(), nn * 4, cudaMemcpyHostToDevice));
-    RPF_CUDA(h, cudaMemcpy(h->d_node_size, tp.size.data(), nn * 4, cudaMemcpyHostToDevice));
-    RPF_CUDA(h, cudaMemcpy(h->d_node_child, tp.child.data(), nn * 4, cudaMemcpyHostToDevice));
-    RPF_CUDA(h, cudaMemcpy(h->d_node_depth, tp.depth.data(), nn * 4, cudaMemcpyHostToDevice));
+    rc = rpf_upload_topology(h);
+    if (rc) return rc;
     h->built = false;
+    h->stream_lost = 0;
     h->call_begin();
-    int rc = rpf_build_impl(h);
+    rc = rpf_build_impl(h);
     int rc2 = h->call_end();
     if (rc) return rc;
     if (rc2) return rc2;
@@ -394,8 +463,17 @@ int rpf_build_chunked(rpf_handle* h, int32_t maxDepth, int32_t minLeaf, int64_t 
     if (!h) return RPF_ERR_ARG;
     if (chunk < 1) return rpf_fail(h, RPF_ERR_ARG, "build_chunked: chunk must be >= 1");
     if (chunk >= h->n) return rpf_build(h, maxDepth, minLeaf);   // one chunk == insert into an empty Tip == forestBatch
-    return rpf_fail(h, RPF_ERR_UNSUPPORTED,
-                    "build_chunked: streaming update with chunk < n (insert Bin case, Internal.hs:274-285) is not implemented yet");
+    int rc = check_build_args(h, maxDepth, minLeaf);
+    if (rc) return rc;
+    RPF_SETDEV(h);
+    h->built = false;
+    h->call_begin();
+    rc = rpf_build_stream_impl(h, maxDepth, minLeaf, chunk);     // sets h->topo and the device topology itself
+    int rc2 = h->call_end();
+    if (rc) return rc;
+    if (rc2) return rc2;
+    h->built = true;
+    return RPF_OK;
 }
 
 int64_t rpf_num_nodes(const rpf_handle* h) { return h ? h->topo.nnodes() : -1; }

@@ -17,7 +17,7 @@
 #include <vector>
 
 int rpf_project_launch(rpf_handle* h, int phase, const double* dX, int64_t n, int t0, int Tg, int L, bool ord, void* out,
-                       ull* kmin, ull* kmax);
+                       int64_t ostride, ull* kmin, ull* kmax);
 
 __device__ __forceinline__ int q_ilog2(unsigned v) { return ilog2_pow2(v); }
 __device__ __forceinline__ unsigned q_next_pow2(unsigned v) { return next_pow2_u32(v); }

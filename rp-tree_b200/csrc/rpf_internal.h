@@ -24,6 +24,7 @@ enum rpf_phase {
     PH_TRUTH,           // brute-force top-k
     PH_RECALL,          // candidate-set /\ truth
     PH_MERGE,           // multi-GPU top-k merge
+    PH_STREAM,          // streaming build: threshold/margin updates, Tip concatenation, export
     PH_MISC,            // memsets, setup kernels
     PH_COUNT
 };
@@ -46,12 +47,42 @@ void build_topology(Topology& tp, int64_t n, int maxDepth, int minLeaf);
 
 struct ProfEvent { int phase; cudaEvent_t a, b; };
 
+// One level-synchronous build over an explicit topology (build.cu: rpf_run_job).  The batch build is one job over all
+// points; the streaming build (stream.cu) runs one job per data chunk over the part of the current tree the chunk
+// descends through.  Key row (t, l) of the job lives at keys + (t * Lk + l) * ks and holds the job's points 0..n-1.
+struct BuildJob {
+    const Topology* tp = nullptr;                                             // host topology (BFS ids, root at level 0)
+    const uint32_t* d_start = nullptr; const uint32_t* d_size = nullptr; const int32_t* d_child = nullptr;   // device copies
+    int64_t n = 0, ks = 0, ps = 0, ns = 0;      // points; key-row stride; stride between trees in perm; nodes-per-tree stride
+    int Lk = 0;                                 // key rows per tree
+    const unsigned long long* keys = nullptr;   // order-preserving images of the projections
+    const unsigned long long* kmin = nullptr;   // [tg][Lk] range of the job's keys per (tree, level)
+    const unsigned long long* kmax = nullptr;
+    uint32_t* perm = nullptr;                   // [tg][ps] out: point ids 0..n-1, leaves left to right
+    double *thr = nullptr, *mlo = nullptr, *mhi = nullptr;   // [..][ns] out, indexed (gt0 + t) * ns + node
+    int gt0 = 0, tg = 0;
+    bool order_exact = true;                    // out: every leaf is in the reference's order
+};
+struct JobGeom {
+    int CAP = 0, L = 0, s = 0, s_top = 0, MAXTD = 0;
+    int64_t NTOP = 0, HSZ = 1;
+    bool order_exact = true, fast_bottom = false;
+    std::vector<int> nb_level, smem_level;
+};
+
+// host -> device table staging: tables are written into page-locked memory and travel with one async copy per flush,
+// so planning the next job overlaps the kernels of the previous one (no stream synchronisation in the build loop)
+#define RPF_STAGE_SLOTS 8
+struct StageSlot { char* h = nullptr; char* d = nullptr; size_t cap = 0; cudaEvent_t ev = nullptr; bool pending = false; };
+
+
 // persistent device workspace (grow-only): no cudaMalloc/cudaFree inside the steady-state hot path
 enum rpf_ws_slot {
     WS_KEYS = 0, WS_LABEL, WS_HIST, WS_SEL, WS_CAND, WS_CANDTOT, WS_PIVOTS, WS_FILL, WS_KMIN, WS_KMAX, WS_BINLO, WS_BINSC,
     WS_NBDEV, WS_RANGE, WS_LVLPV, WS_HPPACK,
     WS_Q, WS_KEYSQ, WS_SEGS, WS_CNT, WS_MAXCNT, WS_OUT_D, WS_OUT_I, WS_OUT_C, WS_BF_D, WS_TRUTH_D, WS_TRUTH_I, WS_RECALL,
     WS_CANDCNT, WS_CANDOFF, WS_CANDOUT, WS_MRG_D, WS_MRG_I, WS_MRG_C, WS_QHIST, WS_QORDER,
+    WS_S_ARENA0, WS_S_ARENA1, WS_S_CPERM, WS_S_TMPN,
     WS_COUNT
 };
 struct WsBuf { void* p = nullptr; size_t cap = 0; };
@@ -80,11 +111,22 @@ struct rpf_handle {
     double *d_thr = nullptr, *d_mlo = nullptr, *d_mhi = nullptr;   // [T][nnodes]
     uint32_t* d_perm = nullptr;                                       // [T][n]
     bool leaf_order_exact = true;
+    int64_t stream_lost = 0;             // points dropped by the reference's empty-piece rule during a streaming build
+    void* stream_pool = nullptr;         // node pool of a streaming build in flight
     size_t res_node_bytes = 0, res_perm_bytes = 0;
     int project_variant = 0;             // tuning hook: 0 = 1024 threads x 4 points/lane, 1 = 1024 x 2 (two CTAs/SM), 2 = 512 x 4
     bool no_query_order = false;         // test/tuning hook: answer queries in input order (no locality grouping)
     bool force_simple_knn = false;       // test hook: per-thread gather knn kernel instead of the TMA ring
     bool force_generic_bottom = false;   // test hook: run the generic (entry-table) bottom kernel
+
+    // staging ring
+    StageSlot stage[RPF_STAGE_SLOTS];
+    int stage_cur = -1; size_t stage_off = 0, stage_flushed = 0;
+    int stage_begin(size_t bytes);                 // next slot, sized for `bytes` of tables (+ alignment slack)
+    void* stage_put_raw(const void* src, size_t bytes);   // returns the DEVICE address the bytes will have after the flush
+    template <typename T> T* stage_put(const T* src, size_t count) { return (T*)stage_put_raw(src, count * sizeof(T)); }
+    int stage_flush();
+    void stage_free_all();
 
     // workspace
     WsBuf ws[WS_COUNT];
@@ -133,8 +175,17 @@ int rpf_fail(rpf_handle* h, int code, const std::string& msg);
             return rpf_fail((h), RPF_ERR_CUDA, std::string(#kern) + " launch: " + cudaGetErrorString(_e)); \
     } while (0)
 
-// implemented in build.cu / query.cu
+// implemented in build.cu / stream.cu / query.cu
 int rpf_build_impl(rpf_handle* h);
+int rpf_alloc_forest(rpf_handle* h, int64_t nn, int64_t n);
+void rpf_job_geometry(const Topology& tp, int cap_cfg, int Lk, JobGeom& G);
+size_t rpf_job_ws_per_tree(const JobGeom& G, int64_t n);
+int rpf_run_job(rpf_handle* h, BuildJob& J);
+int rpf_bottom_fast_levels();
+int rpf_project_launch(rpf_handle* h, int phase, const double* dX, int64_t n, int t0, int Tg, int L, bool ord, void* out,
+                       int64_t ostride, unsigned long long* kmin, unsigned long long* kmax);
+int rpf_upload_topology(rpf_handle* h);
+int rpf_build_stream_impl(rpf_handle* h, int maxDepth, int minLeaf, int64_t chunk);
 int rpf_project_queries(rpf_handle* h, const double* dQ, int64_t nq, double* d_keysQ);
 int rpf_knn_impl(rpf_handle* h, const double* Q, int64_t nq, int k, int dedup, double* dist, uint32_t* ids, int32_t* count);
 int rpf_candidates_impl(rpf_handle* h, const double* Q, int64_t nq, int t, int64_t* off_out, const int64_t* off_in, uint32_t* ids);
@@ -142,6 +193,24 @@ int rpf_recall_impl(rpf_handle* h, const double* Q, int64_t nq, int k, double* r
 int rpf_brute_knn_impl(rpf_handle* h, const double* Q, int64_t nq, int k, double* dist, uint32_t* ids);
 int rpf_merge_impl(rpf_handle* h, int G, int64_t nq, int k, int dedup, const double* dist, const uint32_t* ids,
                    const int32_t* count, double* dist_out, uint32_t* ids_out, int32_t* count_out);
+
+// ---- bottom phase launch arguments (build.cu kernels; also filled by stream.cu for Tip re-splits) --------
+typedef unsigned long long ull;
+struct BottomArgs {
+    int64_t ks, ps, nn_all;              // key-row stride, stride between the trees' slices of perm, nodes per tree
+    int L, s, nlb, gt0, first_gid;      // nlb = levels recorded per node in `range`
+    int given_order;                     // 1: the incoming order of perm IS the reference's order (streaming re-split of
+                                         //    a Tip, Internal.hs:287-297); 0: establish (key_{s-1}, ..., key_0, row id)
+    const ull* keys;                     // [Tg][L][n]
+    uint32_t* perm;                      // [Tg][n]  (in: node segments in any order; out: final leaf order)
+    const int32_t* child;
+    const uint32_t* nstart;
+    const uint32_t* nsize;
+    const int2* range;                   // [nodes at level s][nlb]: BFS id range of the descendants that split
+    const uint32_t* lvl_pv;              // per level: next_pow2(max node size)
+    double *thr, *mlo, *mhi;
+};
+int rpf_bottom_launch(rpf_handle* h, const BottomArgs& B, int nroots, int tg, bool fast, unsigned max_root);
 
 // ---- device helpers ---------------------------------------------------------------------------------
 #ifdef __CUDACC__

@@ -206,7 +206,7 @@ def test_merge_topk_equals_single_forest(built):
             assert np.array_equal(bits(md), bits(wd)) and np.array_equal(mi, wi)
 
 
-def test_chunked_single_chunk_equals_batch_and_multi_chunk_unsupported(built):
+def test_chunked_single_chunk_equals_batch(built):
     R, orc = _mods()
     n, d, T, maxd, minl = 3000, 6, 2, 7, 10
     X = make_data(n, d, 8)
@@ -215,8 +215,88 @@ def test_chunked_single_chunk_equals_batch_and_multi_chunk_unsupported(built):
     of = orc.Forest(X, hp, T, maxd, minl, chunk=n)
     for t in range(T):
         assert not compare_tree(f.treeExport(t), of.export(t))
-    with pytest.raises(R.RPForestError):
-        R.forest(0, maxd, minl, T, 100, 0.5, d, X, hyperplanes=hp)
+    assert f.pointsLost() == 0
+
+
+STREAM_CASES = [
+    # n, d, T, maxd, minl, chunk, pnz, kind, cap
+    pytest.param(1000, 8, 3, 8, 10, 100, 0.5, "gauss", None, id="small-chunks"),
+    pytest.param(10000, 16, 4, 10, 20, 1000, 0.3, "gauss", 256, id="chunk1000-top-phase-cap256"),
+    pytest.param(20000, 16, 3, 11, 16, 5000, 0.3, "mixture", 1024, id="chunk5000-top-phase"),
+    pytest.param(10007, 12, 3, 10, 12, 1001, 0.4, "gauss", 256, id="ragged-chunks-unaligned"),
+    pytest.param(6000, 6, 4, 10, 8, 600, 0.5, "integer", 256, id="integer-ties"),
+    pytest.param(4000, 5, 3, 9, 7, 512, 0.6, "dupes", 256, id="duplicate-rows"),
+    pytest.param(5000, 2, 6, 9, 10, 700, 0.5, "gauss", 256, id="empty-hyperplanes"),
+    pytest.param(1000, 4, 3, 10, 5, 64, 0.7, "gauss", None, id="reference-drops-subtrees"),
+    pytest.param(3000, 4, 2, 6, 40, 999, 0.7, "gauss", None, id="tiny-last-chunk-wipes-tree"),
+    pytest.param(997, 3, 2, 20, 6, 101, 1.0, "gauss", None, id="deep-maxdepth20"),
+    pytest.param(1000, 3, 2, 5, 2, 1, 1.0, "gauss", None, id="chunk-of-one"),
+    pytest.param(500, 3, 2, 7, 64, 20, 1.0, "gauss", None, id="chunks-accumulate-in-root-tip"),
+    pytest.param(3000, 4, 3, 12, 1, 300, 0.7, "gauss", 256, id="minleaf1"),
+    pytest.param(600, 3, 2, 8, 0, 50, 1.0, "gauss", 256, id="minleaf0"),
+    pytest.param(40000, 8, 2, 12, 1000, 10000, 0.5, "gauss", 1024, id="big-leaves-resplit-2000"),
+    pytest.param(100000, 16, 2, 12, 32, 1000, 0.3, "mixture", 1024, id="rptreecfg-like-100-chunks"),
+]
+
+
+@pytest.mark.parametrize("generic", [False, True], ids=["fast-bottom", "generic-bottom"])
+@pytest.mark.parametrize("n,d,T,maxd,minl,chunk,pnz,kind,cap", STREAM_CASES)
+def test_streaming_build_parity(built, n, d, T, maxd, minl, chunk, pnz, kind, cap, generic):
+    """forest / tree with chunk < n (Conduit.hs:58-121, insert Bin + Tip cases Internal.hs:257-297) against the oracle's
+    chunked insert: shape, thresholds (running averages), margins (semigroup), leaf sets and leaf order."""
+    R, orc = _mods()
+    X = make_data(n, d, 21, kind)
+    hp = orc.gen_hyperplanes(99, T, maxd, pnz, d)
+    f = R.forest(0, maxd, minl, T, chunk, pnz, d, X, hyperplanes=hp, bottom_cap=cap,
+                 options={"force_generic_bottom": 1} if generic else None)
+    of = orc.Forest(X, hp, T, maxd, minl, chunk=chunk)
+    plan = R.topologyPlan(n, maxd, minl, chunk=chunk)
+    assert f.pointsLost() == plan["points_lost"] == n - of.tree_size(0)
+    order = f.leafOrderExact()
+    problems = []
+    for t in range(T):
+        bad = compare_tree(f.treeExport(t), of.export(t), check_order=order)
+        problems += ["tree %d: %s" % (t, b) for b in bad]
+    assert not problems, "\n".join(problems[:20])
+    assert order
+    # queries against the streamed forest
+    rng = np.random.default_rng(5)
+    nq = 16
+    Q = X[rng.integers(0, n, size=nq)] + (0.05 * rng.normal(size=(nq, d)) if kind != "integer" else 0.0)
+    off, ids = f.candidatesBatch(Q, -1)
+    for i in range(nq):
+        exp = np.concatenate([of.candidates(t, Q[i]) for t in range(T)])
+        assert np.array_equal(ids[off[i]:off[i + 1]], exp), "candidates differ: query %d" % i
+    dist, idk, cnt = f.knnBatch(Q, 10)
+    for i in range(nq):
+        od, oi = of.knn(Q[i], 10)
+        assert cnt[i] == len(od) and np.array_equal(bits(dist[i, :cnt[i]]), bits(od))
+        if kind in ("gauss", "mixture"):
+            assert np.array_equal(idk[i, :cnt[i]], oi)
+
+
+def test_streaming_rebuild_and_batch_on_same_handle(built):
+    """A handle can go batch -> streamed -> batch; the streamed result does not depend on what ran before."""
+    R, orc = _mods()
+    n, d, T, maxd, minl = 6000, 8, 3, 9, 12
+    X = make_data(n, d, 4)
+    hp = orc.gen_hyperplanes(5, T, maxd, 0.5, d)
+    f = R.forestBatch(0, maxd, minl, T, 0.5, d, X, hyperplanes=hp)
+    for chunk in (500, None, 750):
+        f.build(maxd, minl, chunk=chunk)
+        of = orc.Forest(X, hp, T, maxd, minl, chunk=chunk if chunk else n)
+        for t in range(T):
+            assert not compare_tree(f.treeExport(t), of.export(t)), "chunk=%r tree %d" % (chunk, t)
+
+
+def test_streaming_unsupported_shape_reports(built):
+    """A Tip of more than 8192 points that must be re-split is outside the streaming path's limits."""
+    R, orc = _mods()
+    n, d = 30000, 4
+    X = make_data(n, d, 4)
+    hp = orc.gen_hyperplanes(5, 1, 4, 1.0, d)
+    with pytest.raises(R.RPForestError, match="8192"):
+        R.forest(0, 4, 9000, 1, 6000, 1.0, d, X, hyperplanes=hp)
 
 
 def test_profile_and_launch_count(built):
