@@ -330,6 +330,7 @@ struct TopArgs {
     int64_t n;                       // points of this job (labels, cand are [Tg][n])
     int64_t ks, ps;                  // element stride between key rows / between the trees' slices of perm
     int vec;                         // key rows and labels are 32-byte / 8-byte aligned: 4-point vector accesses allowed
+    int haslab;                      // labels are valid (level > 0, or a job with several roots); else every point sits in node 0
     int Tg, L, l, node0, nnodes, NTOP, NB, HSZ, MAXTD, smem_hist, gt0;   // gt0: global tree id of the group's first tree
     int all_internal, child0;        // every node of level l splits; BFS id of the first node of level l+1
     int scatter_fast;                // last top level: every point lands in a child of this level (CTA-aggregated scatter)
@@ -387,7 +388,7 @@ __global__ void k_bin_setup(TopArgs A, const int* __restrict__ nb_per_level, int
 
 // point -> (local node index at level l) or -1 when the point does not sit in an internal node of level l
 __device__ __forceinline__ int point_node(const TopArgs& A, const uint16_t* lab, int64_t i) {
-    int g = A.l == 0 ? 0 : (int)lab[i];
+    int g = A.haslab ? (int)lab[i] : 0;
     int nl = g - A.node0;
     if ((unsigned)nl >= (unsigned)A.nnodes) return -1;
     if (__ldg(A.child + g) < 0) return -1;
@@ -399,7 +400,7 @@ __device__ __forceinline__ int point_node(const TopArgs& A, const uint16_t* lab,
 struct Pt4 { ull k[4]; uint16_t g[4]; };
 __device__ __forceinline__ void load_pt4(const TopArgs& A, const ull* __restrict__ keys, const uint16_t* lab, int64_t i, Pt4& p) {
     asm("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(p.k[0]), "=l"(p.k[1]), "=l"(p.k[2]), "=l"(p.k[3]) : "l"(keys + i));
-    if (A.l > 0) {
+    if (A.haslab) {
         const uint2 q = *(const uint2*)(lab + i);
         p.g[0] = (uint16_t)(q.x & 0xffff); p.g[1] = (uint16_t)(q.x >> 16); p.g[2] = (uint16_t)(q.y & 0xffff); p.g[3] = (uint16_t)(q.y >> 16);
     } else {
@@ -434,7 +435,7 @@ __device__ __forceinline__ void stream_points(const TopArgs& A, const ull* __res
             for (int u = 0; u < 4; ++u) f(i + u, a.k[u], (int)a.g[u]);
         }
     } else {
-        for (int64_t i = i0 + threadIdx.x; i < i1; i += TOP_NT) f(i, keys[i], A.l == 0 ? 0 : (int)lab[i]);
+        for (int64_t i = i0 + threadIdx.x; i < i1; i += TOP_NT) f(i, keys[i], A.haslab ? (int)lab[i] : 0);
     }
 }
 
@@ -643,7 +644,7 @@ __global__ void __launch_bounds__(512) k_top_ties(TopArgs A) {
     if (tid == 0) cnt = 0;
     __syncthreads();
     for (int64_t i = tid; i < A.n; i += 512) {
-        int gi = A.l == 0 ? 0 : (int)lab[i];
+        int gi = A.haslab ? (int)lab[i] : 0;
         if (gi == g && keys_l[i] == thr) { uint32_t p = atomicAdd(&cnt, 1u); la[p] = (uint32_t)i; }
     }
     __syncthreads();
@@ -773,7 +774,7 @@ __global__ void __launch_bounds__(TOP_NT) k_top_relabel(TopArgs A, int last) {
             *(uint2*)(lab + i) = make_uint2(ga[0] | (ga[1] << 16), ga[2] | (ga[3] << 16));
         }
     } else {
-        for (int64_t i = i0 + tid; i < i1; i += TOP_NT) lab[i] = (uint16_t)relabel_one(i, keys[i], A.l == 0 ? 0 : (int)lab[i]);
+        for (int64_t i = i0 + tid; i < i1; i += TOP_NT) lab[i] = (uint16_t)relabel_one(i, keys[i], A.haslab ? (int)lab[i] : 0);
     }
     if (sf) {
         // reserve a range per child for this CTA (one global atomic per non-empty child), then place the points
@@ -807,20 +808,32 @@ __global__ void __launch_bounds__(TOP_NT) k_top_relabel(TopArgs A, int last) {
     }
 }
 
-// thr / margins of the level's nodes (Internal.hs:496-501); top-phase nodes always have size >= 3
+// thr / margins of the level's nodes (Internal.hs:496-501).  A batch build's top-phase nodes hold >= 3 points; the
+// streaming build's chunk trees can carry tiny pieces (a short last chunk) through the same levels
 __global__ void k_top_finalize(TopArgs A) {
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= A.nnodes * A.Tg) return;
     int t = idx / A.nnodes, nl = idx % A.nnodes, g = A.node0 + nl;
     if (A.child[g] < 0) return;
     const NodeSel& S = A.sel[(int64_t)t * A.NTOP + g];
-    const uint32_t nh = A.nsize[g] >> 1;
-    const ull lo = (S.cless == nh) ? S.pred : S.thr;                 // sorted[nh-1]
-    const ull hi = (S.cless + S.ceq >= nh + 2) ? S.thr : S.succ;     // sorted[nh+1]
+    const uint32_t sz = A.nsize[g], nh = sz >> 1;
+    ull lo = (S.cless == nh) ? S.pred : S.thr;                       // sorted[nh-1]
+    ull hi = (S.cless + S.ceq >= nh + 2) ? S.thr : S.succ;           // sorted[nh+1]
+    if (sz == 2) hi = S.thr;                                         // (sorted[0], sorted[1]), Internal.hs:499
+    if (sz == 1) { lo = S.thr; hi = S.thr; }                         // (z, z), Internal.hs:500
     const int64_t o = (int64_t)(A.gt0 + t) * A.nn_all + g;
     A.thr[o] = ord2f(S.thr);
     A.mlo[o] = ord2f(lo);
     A.mhi[o] = ord2f(hi);
+}
+
+// jobs with several roots (one per data chunk): label[t][i] = root whose row range holds point i
+__global__ void k_label_roots(uint16_t* __restrict__ label, int64_t n, int Tg, const uint32_t* __restrict__ nstart, int nroots) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int lo = 0, hi = nroots - 1;                  // last root with start <= i (roots are consecutive row ranges)
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (__ldg(nstart + mid) <= (uint32_t)i) lo = mid; else hi = mid - 1; }
+    for (int t = 0; t < Tg; ++t) label[(int64_t)t * n + i] = (uint16_t)lo;
 }
 
 __global__ void k_iota_perm(uint32_t* perm, int64_t n, int64_t ps, int Tg) {
@@ -997,7 +1010,8 @@ __global__ void __launch_bounds__(NT) k_bottom(BottomArgs A) {
 // decide.  Adjacent words with equal top-48 bits (rare) are re-checked with the full keys and fixed by odd-even
 // transposition, so the result is exactly Merge.sortBy (comparing snd) (Internal.hs:504-512).
 // No entry tables, no bounds checks and no payload in the network: 2 LDS.64 + compare + 2 STS.64 per comparator.
-#define BOT2_TAB 512
+#define BOT2_TAB 512        /* segment-table entries of the default instance: subtrees of <= 9 splitting levels */
+#define BOT2_TAB_DEEP 1024  /* deep instance (streaming chunk trees, minLeaf 0/1 chains): <= 10 splitting levels */
 #define W_SENT 0xffffffffffffffffull
 
 template <int NT>
@@ -1024,17 +1038,17 @@ __device__ __forceinline__ void bitonic_uniform(ull* w, unsigned nslots, unsigne
     }
 }
 
-template <int NT>
+template <int NT, int TAB>
 __global__ void __launch_bounds__(NT) k_bottom3(BottomArgs A) {
     constexpr unsigned P0 = 8 * NT;               // slots (>= node size), 8 per thread
     constexpr int lp0 = (NT == 32 ? 8 : NT == 64 ? 9 : NT == 128 ? 10 : NT == 256 ? 11 : NT == 512 ? 12 : 13);
     extern __shared__ unsigned char smraw[];
     ull* w = (ull*)smraw;                         // [P0] sort words
     uint32_t* sidx = (uint32_t*)(w + P0);         // [P0] row id held by each slot
-    __shared__ uint16_t t_sz[2][BOT2_TAB];        // size of the segment if it splits at this level, else 0
-    __shared__ uint16_t t_ps[2][BOT2_TAB];        // offset of the segment inside this CTA's slice of perm
-    __shared__ int32_t t_gid[2][BOT2_TAB];        // BFS id
-    __shared__ uint16_t t_lsz[BOT2_TAB];          // size if the segment just became a Tip (to be emitted), else 0
+    __shared__ uint16_t t_sz[2][TAB];        // size of the segment if it splits at this level, else 0
+    __shared__ uint16_t t_ps[2][TAB];        // offset of the segment inside this CTA's slice of perm
+    __shared__ int32_t t_gid[2][TAB];        // BFS id
+    __shared__ uint16_t t_lsz[TAB];          // size if the segment just became a Tip (to be emitted), else 0
     const int t = blockIdx.y, tid = threadIdx.x;
     const int e0 = A.first_gid + blockIdx.x;
     const uint32_t m = A.nsize[e0], start = A.nstart[e0];
@@ -1199,7 +1213,7 @@ __global__ void __launch_bounds__(NT) k_bottom3(BottomArgs A) {
 
         // ---- children tables
         const int nxt = cur ^ 1;
-        const bool can_grow = (nseg * 2 <= BOT2_TAB) && Pv >= 2;
+        const bool can_grow = (nseg * 2 <= (unsigned)TAB) && Pv >= 2;
         int any_internal = 0;
         if (can_grow) {
             for (unsigned c = tid; c < nseg * 2; c += NT) {
@@ -1267,11 +1281,11 @@ static int launch_bottom_generic(rpf_handle* h, const BottomArgs& B, int nnodes_
     RPF_LAUNCH(h, PH_BOTTOM, kfn, grid, NT, smem, B);
     return RPF_OK;
 }
-template <int NT>
+template <int NT, int TAB>
 static int launch_bottom_fast(rpf_handle* h, const BottomArgs& B, int nnodes_s, int tg) {
     dim3 grid((unsigned)nnodes_s, (unsigned)tg);
     const size_t smem = (size_t)NT * 8 * 12;
-    auto kfn = k_bottom3<NT>;
+    auto kfn = k_bottom3<NT, TAB>;
     RPF_CUDA(h, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     RPF_CUDA(h, cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     RPF_LAUNCH(h, PH_BOTTOM, kfn, grid, NT, smem, B);
@@ -1279,29 +1293,36 @@ static int launch_bottom_fast(rpf_handle* h, const BottomArgs& B, int nnodes_s, 
 }
 
 // Bottom phase over `nroots` consecutive nodes (BFS ids B.first_gid ..) of `tg` trees; every root holds at most
-// max_root points.  fast: uniform-layout kernel (needs: every node that splits holds >= 2 points and the subtrees
-// are at most BOT2_LEVELS levels deep); otherwise the generic entry-table kernel (needs B.range / B.lvl_pv).
-int rpf_bottom_launch(rpf_handle* h, const BottomArgs& B, int nroots, int tg, bool fast, unsigned max_root) {
+// max_root points and its subtree has `levels` splitting levels.  fast: uniform-layout kernel -- a segment at relative
+// depth j owns slots >> j slots and must keep >= 2 of them while it splits, so slots >= 2^levels and levels <= 10;
+// otherwise the generic entry-table kernel (needs B.range / B.lvl_pv).
+int rpf_bottom_launch(rpf_handle* h, const BottomArgs& B, int nroots, int tg, bool fast, unsigned max_root, int levels) {
     if (nroots <= 0 || tg <= 0) return RPF_OK;
     if (max_root > 8192) return rpf_fail(h, RPF_ERR_UNSUPPORTED, "bottom phase: node larger than 8192 points");
     if (fast) {
-        const unsigned slots = std::max(256u, next_pow2_host(std::max(max_root, 1u)));
+        unsigned slots = std::max(256u, next_pow2_host(std::max(max_root, 1u)));
+        while (levels > 0 && (slots >> levels) == 0) slots <<= 1;          // slots >= 2^levels
+        if (slots > 8192 || levels > rpf_bottom_fast_levels()) return rpf_fail(h, RPF_ERR_ARG, "internal: subtree too deep for the fast bottom kernel");
+        const bool deep = levels > 9;
+#define RPF_BOT_CASE(SL, NT_)                                                                                         \
+        case SL: return deep ? launch_bottom_fast<NT_, BOT2_TAB_DEEP>(h, B, nroots, tg) : launch_bottom_fast<NT_, BOT2_TAB>(h, B, nroots, tg);
         switch (slots) {
-            case 256: return launch_bottom_fast<32>(h, B, nroots, tg);
-            case 512: return launch_bottom_fast<64>(h, B, nroots, tg);
-            case 1024: return launch_bottom_fast<128>(h, B, nroots, tg);
-            case 2048: return launch_bottom_fast<256>(h, B, nroots, tg);
-            case 4096: return launch_bottom_fast<512>(h, B, nroots, tg);
-            case 8192: return launch_bottom_fast<1024>(h, B, nroots, tg);
+            RPF_BOT_CASE(256, 32)
+            RPF_BOT_CASE(512, 64)
+            RPF_BOT_CASE(1024, 128)
+            RPF_BOT_CASE(2048, 256)
+            RPF_BOT_CASE(4096, 512)
+            RPF_BOT_CASE(8192, 1024)
             default: return rpf_fail(h, RPF_ERR_ARG, "internal: bad bottom slot count");
         }
+#undef RPF_BOT_CASE
     }
     if (max_root <= 256) return launch_bottom_generic<256, 128>(h, B, nroots, tg);
     if (max_root <= 1024) return launch_bottom_generic<1024, 256>(h, B, nroots, tg);
     if (max_root <= 4096) return launch_bottom_generic<4096, 512>(h, B, nroots, tg);
     return launch_bottom_generic<8192, 1024>(h, B, nroots, tg);
 }
-int rpf_bottom_fast_levels() { int v = BOT2_TAB, l = 0; while (v > 1) { v >>= 1; ++l; } return l; }
+int rpf_bottom_fast_levels() { int v = BOT2_TAB_DEEP, l = 0; while (v > 1) { v >>= 1; ++l; } return l; }
 
 // ---- geometry of a job: phase split and top-phase histogram shapes (pure host arithmetic on the topology) ----------
 void rpf_job_geometry(const Topology& tp, int cap_cfg, int Lk, JobGeom& G) {
@@ -1338,68 +1359,82 @@ void rpf_job_geometry(const Topology& tp, int cap_cfg, int Lk, JobGeom& G) {
         G.HSZ = std::max<int64_t>(G.HSZ, (int64_t)nodes * nb);
     }
     G.MAXTD = L + 1;
-    // fast bottom kernel: every node that splits at level >= s holds >= 2 points, and at most BOT2 levels below s
-    G.fast_bottom = (L - s) <= rpf_bottom_fast_levels();
-    for (int l = s; l < tp.nlevels && G.fast_bottom; ++l)
-        for (int64_t g = tp.level_off[l]; g < tp.level_off[l + 1]; ++g) if (tp.child[g] >= 0 && tp.size[g] < 2) { G.fast_bottom = false; break; }
+    // fast bottom kernel: at most 10 splitting levels below s, and 2^levels slots fit one CTA (8192)
+    G.bottom_levels = std::max(0, L - s);
+    G.fast_bottom = G.bottom_levels <= rpf_bottom_fast_levels();
+    if (G.fast_bottom && s < tp.nlevels) {
+        unsigned slots = std::max(256u, next_pow2_host(std::max<uint32_t>(tp.lvl_maxsize[s], 1)));
+        while (G.bottom_levels > 0 && (slots >> G.bottom_levels) == 0) slots <<= 1;
+        if (slots > 8192) G.fast_bottom = false;
+    }
 }
 size_t rpf_job_ws_per_tree(const JobGeom& G, int64_t n) {
     return (G.s_top > 0 ? (size_t)n * 10 : 0) + (size_t)G.HSZ * 4 + (size_t)G.NTOP * (sizeof(NodeSel) + 4 + (size_t)G.MAXTD * 8) + 4096;
 }
 
-// Runs the level-synchronous build of one job (see BuildJob in rpf_internal.h).  Everything is enqueued on the
-// engine's stream; the host tables travel through the page-locked staging ring, so the call does not synchronise.
-int rpf_run_job(rpf_handle* h, BuildJob& J) {
-    const Topology& tp = *J.tp;
-    const int64_t n = J.n, nn = tp.nnodes();
+// Host half of a job: geometry, per-level flags and the device tables (bottom-phase ranges, histogram shapes) appended
+// to TB.  Pure function of the topology, so callers may cache the result (the streaming build does).
+void rpf_plan_job(const Topology& tp, int cap_cfg, int Lk, bool force_generic, TableBuf& TB, JobPlan& P) {
+    P = JobPlan();
+    JobGeom& G = P.G;
+    rpf_job_geometry(tp, cap_cfg, Lk, G);
+    if (force_generic) G.fast_bottom = false;
+    P.n = tp.n; P.nn = tp.nnodes(); P.nlevels = tp.nlevels;
+    P.level_off = tp.level_off;
+    P.nroots = (int)tp.level_off[1];
+    P.lvl_all_internal.assign(std::max(tp.nlevels, 1), 1);
+    for (int l = 0; l < tp.nlevels; ++l)
+        for (int64_t g = tp.level_off[l]; g < tp.level_off[l + 1]; ++g) if (tp.child[g] < 0) { P.lvl_all_internal[l] = 0; break; }
+    const int s = G.s;
+    // ---- bottom-phase tables: per level-s node, the BFS id range of its descendants at each deeper level
+    std::vector<int2> rg; std::vector<uint32_t> pv;
+    if (s < tp.nlevels) {
+        P.nnodes_s = (int)(tp.level_off[s + 1] - tp.level_off[s]);
+        P.nlb = std::max(1, tp.nlevels - s);
+        P.maxsize_s = tp.lvl_maxsize[s];
+        pv.resize(tp.nlevels);
+        for (int l = 0; l < tp.nlevels; ++l) pv[l] = next_pow2_host(std::max<uint32_t>(tp.lvl_maxsize[l], 1));
+        if (!G.fast_bottom) {
+            rg.assign((size_t)P.nnodes_s * P.nlb, make_int2(0, 0));
+            for (int e = 0; e < P.nnodes_s; ++e) {
+                int64_t lo = tp.level_off[s] + e, hi = lo + 1;
+                for (int j = 0; j < P.nlb; ++j) {
+                    int64_t fi = -1, li = -1;
+                    for (int64_t g = lo; g < hi; ++g) if (tp.child[g] >= 0) { if (fi < 0) fi = g; li = g; }
+                    if (fi < 0) break;
+                    rg[(size_t)e * P.nlb + j] = make_int2((int)lo, (int)hi);
+                    lo = tp.child[fi]; hi = (int64_t)tp.child[li] + 2;
+                }
+            }
+        }
+    }
+    P.off_range = rg.empty() ? (size_t)-1 : TB.put(rg.data(), rg.size() * sizeof(int2));
+    P.off_lvlpv = pv.empty() ? (size_t)-1 : TB.put(pv.data(), pv.size() * 4);
+    P.off_nb = TB.put(G.nb_level.data(), G.nb_level.size() * sizeof(int));
+}
+
+// Device half: enqueues every kernel of the job on the engine's stream.  `tab` = device address of the table block
+// the plan's offsets refer to.  No host synchronisation.
+int rpf_launch_job(rpf_handle* h, BuildJob& J, const JobPlan& P, const char* tab) {
+    const JobGeom& G = P.G;
+    const int64_t n = J.n;
     const int tg = J.tg;
-    JobGeom G;
-    rpf_job_geometry(tp, h->bottom_cap, J.Lk, G);
-    if (h->force_generic_bottom) G.fast_bottom = false;
     const int L = G.L, s = G.s, s_top = G.s_top;
     const int64_t NTOP = G.NTOP, HSZ = G.HSZ;
     const int MAXTD = G.MAXTD;
     J.order_exact = G.order_exact;
     if (s_top > 0 && NTOP > 65535) return rpf_fail(h, RPF_ERR_UNSUPPORTED, "too many top-phase nodes for 16-bit labels");
 
-    if (L == 0 || n == 0) {   // every tree is a single Tip holding the points in input order
+    if (L == 0 || n == 0) {   // every root is a single Tip holding its points in input order
         if (n > 0) {
             const int64_t tot = n * tg;
             RPF_LAUNCH(h, PH_MISC, k_iota_perm, (unsigned)((tot + 255) / 256), 256, 0, J.perm, n, J.ps, tg);
         }
         return RPF_OK;
     }
-
-    // ---- bottom-phase tables: per level-s node, the BFS id range of its descendants at each deeper level
-    int nnodes_s = 0, nlb = 0;
-    std::vector<int2> rg; std::vector<uint32_t> pv;
-    if (s < tp.nlevels) {
-        nnodes_s = (int)(tp.level_off[s + 1] - tp.level_off[s]);
-        nlb = std::max(1, tp.nlevels - s);
-        pv.resize(tp.nlevels);
-        for (int l = 0; l < tp.nlevels; ++l) pv[l] = next_pow2_host(std::max<uint32_t>(tp.lvl_maxsize[l], 1));
-        if (!G.fast_bottom) {
-            rg.assign((size_t)nnodes_s * nlb, make_int2(0, 0));
-            for (int e = 0; e < nnodes_s; ++e) {
-                int64_t lo = tp.level_off[s] + e, hi = lo + 1;
-                for (int j = 0; j < nlb; ++j) {
-                    int64_t fi = -1, li = -1;
-                    for (int64_t g = lo; g < hi; ++g) if (tp.child[g] >= 0) { if (fi < 0) fi = g; li = g; }
-                    if (fi < 0) break;
-                    rg[(size_t)e * nlb + j] = make_int2((int)lo, (int)hi);
-                    lo = tp.child[fi]; hi = (int64_t)tp.child[li] + 2;
-                }
-            }
-        }
-    }
-    // ---- one staged upload for all host tables of this job
-    int rc = h->stage_begin(rg.size() * sizeof(int2) + pv.size() * 4 + (size_t)std::max(L, 1) * 4 + 1024);
-    if (rc) return rc;
-    const int2* range = rg.empty() ? nullptr : h->stage_put(rg.data(), rg.size());
-    const uint32_t* lvlpv = pv.empty() ? nullptr : h->stage_put(pv.data(), pv.size());
-    const int* nbdev = h->stage_put(G.nb_level.data(), G.nb_level.size());
-    rc = h->stage_flush();
-    if (rc) return rc;
+    const int2* range = P.off_range == (size_t)-1 ? nullptr : (const int2*)(tab + P.off_range);
+    const uint32_t* lvlpv = P.off_lvlpv == (size_t)-1 ? nullptr : (const uint32_t*)(tab + P.off_lvlpv);
+    const int* nbdev = (const int*)(tab + P.off_nb);
 
     if (s_top > 0) {
         uint16_t* label = (uint16_t*)h->ws_get(WS_LABEL, (size_t)tg * n * 2);
@@ -1423,14 +1458,15 @@ int rpf_run_job(rpf_handle* h, BuildJob& J) {
         RPF_CUDA(h, cudaFuncSetAttribute(k_top_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, HBINS * 2));
         RPF_LAUNCH(h, PH_MISC, k_bin_setup, (unsigned)((tg * J.Lk + 127) / 128), 128, 0, A, nbdev, s_top);
         RPF_CUDA(h, cudaMemsetAsync(fill, 0, (size_t)tg * NTOP * 4, h->stream));
+        if (P.nroots > 1) RPF_LAUNCH(h, PH_MISC, k_label_roots, (unsigned)((n + 255) / 256), 256, 0, label, n, tg, J.d_start, P.nroots);
         const unsigned nchunks = (unsigned)((n + TOP_CH - 1) / TOP_CH);
         bool all_top_internal = true;
         for (int l = 0; l < s_top; ++l) {
-            A.l = l; A.node0 = (int)tp.level_off[l]; A.nnodes = (int)(tp.level_off[l + 1] - tp.level_off[l]);
+            A.l = l; A.node0 = (int)P.level_off[l]; A.nnodes = (int)(P.level_off[l + 1] - P.level_off[l]);
+            A.haslab = (l > 0 || P.nroots > 1) ? 1 : 0;
             A.NB = G.nb_level[l]; A.smem_hist = G.smem_level[l];
-            A.child0 = (int)tp.level_off[l + 1];
-            A.all_internal = 1;
-            for (int64_t g = tp.level_off[l]; g < tp.level_off[l + 1]; ++g) if (tp.child[g] < 0) { A.all_internal = 0; break; }
+            A.child0 = (int)P.level_off[l + 1];
+            A.all_internal = P.lvl_all_internal[l];
             all_top_internal = all_top_internal && A.all_internal;
             A.scatter_fast = (all_top_internal && 2 * A.nnodes <= SCAT_MAX) ? 1 : 0;
             RPF_CUDA(h, cudaMemsetAsync(hist, 0, (size_t)tg * HSZ * 4, h->stream));
@@ -1451,16 +1487,29 @@ int rpf_run_job(rpf_handle* h, BuildJob& J) {
         RPF_LAUNCH(h, PH_MISC, k_iota_perm, (unsigned)((tot + 255) / 256), 256, 0, J.perm, n, J.ps, tg);
     }
 
-    if (s < tp.nlevels) {
+    if (s < P.nlevels) {
         BottomArgs B{};
-        B.ks = J.ks; B.ps = J.ps; B.nn_all = J.ns; B.L = J.Lk; B.s = s; B.nlb = nlb; B.gt0 = J.gt0; B.first_gid = (int)tp.level_off[s];
+        B.ks = J.ks; B.ps = J.ps; B.nn_all = J.ns; B.L = J.Lk; B.s = s; B.nlb = P.nlb; B.gt0 = J.gt0; B.first_gid = (int)P.level_off[s];
         B.given_order = 0;
         B.keys = J.keys; B.perm = J.perm; B.child = J.d_child; B.nstart = J.d_start; B.nsize = J.d_size;
         B.range = range; B.lvl_pv = lvlpv; B.thr = J.thr; B.mlo = J.mlo; B.mhi = J.mhi;
-        rc = rpf_bottom_launch(h, B, nnodes_s, tg, G.fast_bottom, tp.lvl_maxsize[s]);
+        int rc = rpf_bottom_launch(h, B, P.nnodes_s, tg, G.fast_bottom, P.maxsize_s, G.bottom_levels);
         if (rc) return rc;
     }
     return RPF_OK;
+}
+
+// plan + stage + launch (the batch build: the plan is cheap and the tables travel through the staging ring)
+int rpf_run_job(rpf_handle* h, BuildJob& J) {
+    TableBuf TB; JobPlan P;
+    rpf_plan_job(*J.tp, h->bottom_cap, J.Lk, h->force_generic_bottom, TB, P);
+    int rc = h->stage_begin(TB.bytes.size() + 1024);
+    if (rc) return rc;
+    const char* tab = (const char*)h->stage_put_raw(TB.bytes.data(), TB.bytes.size());
+    if (!tab) return rpf_fail(h, RPF_ERR_NOMEM, h->err);
+    rc = h->stage_flush();
+    if (rc) return rc;
+    return rpf_launch_job(h, J, P, tab);
 }
 
 #define WS(h, var, type, slot, bytes)                                   \

@@ -121,7 +121,7 @@ void rpf_handle::stage_free_all() {
 
 static const char* kPhaseNames[PH_COUNT] = {
     "project", "top_hist", "top_pick", "top_compact", "top_finish", "top_ties", "top_relabel", "bottom",
-    "q_project", "q_traverse", "q_knn", "q_candidates", "truth", "recall", "merge", "stream", "misc"};
+    "q_project", "q_traverse", "q_knn", "q_candidates", "truth", "recall", "merge", "stream", "stream_concat", "misc"};
 
 // ---------------------------------------------------------------------------------------------------
 // topology: Internal.hs:289 (Tip iff ixLev >= maxDepth || length xs' <= minLeaf), :495/:503 (nh = n div 2)
@@ -282,7 +282,7 @@ void rpf_destroy(rpf_handle* h) {
     cudaStreamSynchronize(h->stream);
     if (h->ownX && h->dX) cudaFree((void*)h->dX);
     free_hp_dev(h); free_topo_dev(h); free_forest_dev(h);
-    if (h->stream_pool) cudaFree(h->stream_pool);
+    if (h->stream_plan && h->stream_plan_free) h->stream_plan_free(h->stream_plan);
     h->ws_free_all();
     h->stage_free_all();
     for (auto e : h->event_pool) cudaEventDestroy(e);

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
+#include <string.h>
 #include <vector>
 #include "../../include/rpforest.h"
 
@@ -24,7 +25,8 @@ enum rpf_phase {
     PH_TRUTH,           // brute-force top-k
     PH_RECALL,          // candidate-set /\ truth
     PH_MERGE,           // multi-GPU top-k merge
-    PH_STREAM,          // streaming build: threshold/margin updates, Tip concatenation, export
+    PH_STREAM,          // streaming build: threshold/margin updates, export
+    PH_STREAM_CONCAT,   // streaming build: Tip concatenation (leaf arena rewrite)
     PH_MISC,            // memsets, setup kernels
     PH_COUNT
 };
@@ -64,10 +66,31 @@ struct BuildJob {
     bool order_exact = true;                    // out: every leaf is in the reference's order
 };
 struct JobGeom {
-    int CAP = 0, L = 0, s = 0, s_top = 0, MAXTD = 0;
+    int CAP = 0, L = 0, s = 0, s_top = 0, MAXTD = 0, bottom_levels = 0;
     int64_t NTOP = 0, HSZ = 1;
     bool order_exact = true, fast_bottom = false;
     std::vector<int> nb_level, smem_level;
+};
+
+// host tables of a plan, addressed by offset (256-byte aligned) so the block can live in the staging ring or in a cached
+// device buffer
+struct TableBuf {
+    std::vector<char> bytes;
+    size_t put(const void* p, size_t n) {
+        const size_t off = (bytes.size() + 255) & ~(size_t)255;
+        bytes.resize(off + n);
+        if (n) memcpy(bytes.data() + off, p, n);
+        return off;
+    }
+};
+struct JobPlan {
+    JobGeom G;
+    int64_t n = 0, nn = 0;
+    int nlevels = 0, nroots = 1, nnodes_s = 0, nlb = 0;
+    uint32_t maxsize_s = 0;
+    std::vector<int64_t> level_off;
+    std::vector<char> lvl_all_internal;
+    size_t off_range = (size_t)-1, off_lvlpv = (size_t)-1, off_nb = 0;   // offsets into the job's table block
 };
 
 // host -> device table staging: tables are written into page-locked memory and travel with one async copy per flush,
@@ -82,7 +105,7 @@ enum rpf_ws_slot {
     WS_NBDEV, WS_RANGE, WS_LVLPV, WS_HPPACK,
     WS_Q, WS_KEYSQ, WS_SEGS, WS_CNT, WS_MAXCNT, WS_OUT_D, WS_OUT_I, WS_OUT_C, WS_BF_D, WS_TRUTH_D, WS_TRUTH_I, WS_RECALL,
     WS_CANDCNT, WS_CANDOFF, WS_CANDOUT, WS_MRG_D, WS_MRG_I, WS_MRG_C, WS_QHIST, WS_QORDER,
-    WS_S_ARENA0, WS_S_ARENA1, WS_S_CPERM, WS_S_TMPN,
+    WS_S_ARENA0, WS_S_ARENA1, WS_S_CPERM, WS_S_TMPN, WS_S_POOL,
     WS_COUNT
 };
 struct WsBuf { void* p = nullptr; size_t cap = 0; };
@@ -112,7 +135,8 @@ struct rpf_handle {
     uint32_t* d_perm = nullptr;                                       // [T][n]
     bool leaf_order_exact = true;
     int64_t stream_lost = 0;             // points dropped by the reference's empty-piece rule during a streaming build
-    void* stream_pool = nullptr;         // node pool of a streaming build in flight
+    void* stream_plan = nullptr;         // cached plan of the last streaming build shape (stream.cu: StreamPlanAll)
+    void (*stream_plan_free)(void*) = nullptr;
     size_t res_node_bytes = 0, res_perm_bytes = 0;
     int project_variant = 0;             // tuning hook: 0 = 1024 threads x 4 points/lane, 1 = 1024 x 2 (two CTAs/SM), 2 = 512 x 4
     bool no_query_order = false;         // test/tuning hook: answer queries in input order (no locality grouping)
@@ -181,6 +205,8 @@ int rpf_alloc_forest(rpf_handle* h, int64_t nn, int64_t n);
 void rpf_job_geometry(const Topology& tp, int cap_cfg, int Lk, JobGeom& G);
 size_t rpf_job_ws_per_tree(const JobGeom& G, int64_t n);
 int rpf_run_job(rpf_handle* h, BuildJob& J);
+void rpf_plan_job(const Topology& tp, int cap_cfg, int Lk, bool force_generic, TableBuf& TB, JobPlan& P);
+int rpf_launch_job(rpf_handle* h, BuildJob& J, const JobPlan& P, const char* tab);
 int rpf_bottom_fast_levels();
 int rpf_project_launch(rpf_handle* h, int phase, const double* dX, int64_t n, int t0, int Tg, int L, bool ord, void* out,
                        int64_t ostride, unsigned long long* kmin, unsigned long long* kmax);
@@ -210,7 +236,7 @@ struct BottomArgs {
     const uint32_t* lvl_pv;              // per level: next_pow2(max node size)
     double *thr, *mlo, *mhi;
 };
-int rpf_bottom_launch(rpf_handle* h, const BottomArgs& B, int nroots, int tg, bool fast, unsigned max_root);
+int rpf_bottom_launch(rpf_handle* h, const BottomArgs& B, int nroots, int tg, bool fast, unsigned max_root, int levels);
 
 // ---- device helpers ---------------------------------------------------------------------------------
 #ifdef __CUDACC__

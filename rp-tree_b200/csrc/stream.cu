@@ -43,7 +43,7 @@ struct SNode {
 
 struct TipCopy { uint32_t dst, src_old, n_old, src_new, n_new; };
 
-struct RtGroup { int depth = 0, first = 0, count = 0, nlb = 0; uint32_t max_root = 0; bool fast = true; };
+struct RtGroup { int depth = 0, first = 0, count = 0, nlb = 0, levels = 0; uint32_t max_root = 0; bool fast = true; };
 
 struct ChunkPlan {
     Topology ct;                         // chunk tree (BFS); leaves = Tips (or wiped Bins) of the current tree
@@ -56,6 +56,13 @@ struct ChunkPlan {
     std::vector<int32_t> rt_upd_g, rt_upd_u;
     std::vector<RtGroup> groups;
     int64_t kept = 0;                    // points held by the tree after this chunk
+    void reset() {                       // keeps the vectors' storage (a fresh plan per chunk would page-fault it in again)
+        ct.n = 0; ct.nlevels = 0; ct.L_eff = 0;
+        ct.start.clear(); ct.size.clear(); ct.child.clear(); ct.depth.clear(); ct.level_off.clear(); ct.lvl_maxsize.clear();
+        upd_g.clear(); upd_u.clear(); ct_set = false; copies.clear();
+        rt_child.clear(); rt_pool.clear(); rt_depth.clear(); rt_start.clear(); rt_size.clear(); rt_upd_g.clear(); rt_upd_u.clear();
+        groups.clear(); kept = 0;
+    }
 };
 
 struct StreamPlanner {
@@ -65,10 +72,29 @@ struct StreamPlanner {
     int64_t lost = 0;                    // points dropped by the reference's empty-piece rule (Internal.hs:279)
     std::string err;
 
+    // per-node scratch of the chunk being planned (valid where the stamp equals the chunk counter)
+    std::vector<uint32_t> pend_src, pend_n;
+    std::vector<int32_t> tstamp;
+    std::vector<int64_t> newcnt, root_region;
+    int32_t cur_chunk = 0;
+    size_t last_ct_nodes = 0;
+    struct Pend { int32_t u; uint32_t src_new, n_new; };
+    std::vector<Pend> tips;              // chunk-tree leaves sitting on Tips: piece location inside the chunk's perm
+    std::vector<int32_t> ct_pool;        // pool id of every chunk-tree node
+    std::vector<int32_t> resplit;        // Tips that split after this chunk (pool ids)
+    struct Fr { int32_t u; bool inside; };
+    std::vector<Fr> lay_stack;
+
     void begin(int64_t n_, int maxd, int minl) {
-        n = n_; maxDepth = maxd; minLeaf = minl; pool.clear(); pool.emplace_back(); root = 0; lost = 0; err.clear();
+        n = n_; maxDepth = maxd; minLeaf = minl; pool.clear(); root = 0; lost = 0; err.clear(); cur_chunk = 0; last_ct_nodes = 0;
+        pend_src.clear(); pend_n.clear(); tstamp.clear(); newcnt.clear(); root_region.clear();
+        new_node(0);
     }
-    int32_t new_node(int depth) { pool.emplace_back(); pool.back().depth = depth; return (int32_t)pool.size() - 1; }
+    int32_t new_node(int depth) {
+        pool.emplace_back(); pool.back().depth = depth;
+        pend_src.push_back(0); pend_n.push_back(0); tstamp.push_back(-1); newcnt.push_back(0); root_region.push_back(-1);
+        return (int32_t)pool.size() - 1;
+    }
     int64_t subtree_points(int32_t u) const {
         int64_t tot = 0; std::vector<int32_t> st{u};
         while (!st.empty()) { const int32_t v = st.back(); st.pop_back(); if (pool[v].l < 0) tot += pool[v].cnt; else { st.push_back(pool[v].l); st.push_back(pool[v].r); } }
@@ -77,15 +103,17 @@ struct StreamPlanner {
 
     // Plans the insertion of a chunk of m points.  Returns false on an unsupported shape (err is set).
     bool plan_chunk(int64_t m, ChunkPlan& P) {
-        P = ChunkPlan();
+        P.reset();
+        ++cur_chunk;
         Topology& ct = P.ct;
+        if (last_ct_nodes) {
+            const size_t r = last_ct_nodes + last_ct_nodes / 8 + 64;
+            ct.start.reserve(r); ct.size.reserve(r); ct.child.reserve(r); ct.depth.reserve(r);
+            P.upd_g.reserve(r / 2 + 8); P.upd_u.reserve(r / 2 + 8); P.copies.reserve(r / 2 + 8);
+        }
         ct.n = m; ct.maxDepth = maxDepth; ct.minLeaf = minLeaf;
-        std::vector<int32_t> ct_pool;
-        struct Pend { int32_t u; uint32_t src_new, n_new; };
-        std::vector<Pend> tips;            // CT leaves sitting on Tips: piece location inside the chunk's perm
+        ct_pool.clear(); tips.clear(); resplit.clear();
         const bool fresh = pool[root].l < 0 && pool[root].cnt == 0 && m > minLeaf && maxDepth > 0;
-        std::vector<int32_t> resplit;      // Tips that split after this chunk (pool ids)
-        std::vector<char> is_new_tip;
         if (fresh) {
             // first chunk into an empty tree: the Tip case splits xs recursively == the batch build of the chunk
             build_topology(ct, m, maxDepth, minLeaf);
@@ -146,10 +174,8 @@ struct StreamPlanner {
         }
 
         // ---- Tip case: xs' = xs <> xs0; split when it outgrew minLeaf (Internal.hs:287-297)
-        std::vector<uint32_t> pend_src(pool.size(), 0), pend_n(pool.size(), 0);
-        std::vector<char> touched(pool.size(), 0), is_root(pool.size(), 0);
-        std::vector<int64_t> newcnt(pool.size(), 0);
-        for (const Pend& t : tips) { pend_src[t.u] = t.src_new; pend_n[t.u] = t.n_new; touched[t.u] = 1; newcnt[t.u] = pool[t.u].cnt + t.n_new; }
+        last_ct_nodes = (size_t)ct.nnodes();
+        for (const Pend& t : tips) { pend_src[t.u] = t.src_new; pend_n[t.u] = t.n_new; tstamp[t.u] = cur_chunk; newcnt[t.u] = pool[t.u].cnt + t.n_new; }
         if (!fresh) {
             for (const Pend& t : tips) {
                 const int32_t u = t.u;
@@ -187,20 +213,18 @@ struct StreamPlanner {
                 lo = hi; hi = P.rt_size.size();
             }
             P.rt_start.assign(P.rt_size.size(), 0);
-            for (size_t i = 0; i < R; ++i) is_root[resplit[i]] = 1;
         }
 
         // ---- new left-to-right layout of the leaf arena + copy descriptors
-        std::vector<int64_t> root_region(pool.size(), -1);
         {
             int64_t cur = 0;
-            struct Fr { int32_t u; bool inside; };
-            std::vector<Fr> st; st.push_back(Fr{root, false});
+            std::vector<Fr>& st = lay_stack;
+            st.clear(); st.push_back(Fr{root, false});
             while (!st.empty()) {
                 const Fr f = st.back(); st.pop_back();
                 SNode& N = pool[f.u];
                 bool inside = f.inside;
-                if (!inside && f.u < (int32_t)touched.size() && touched[f.u]) {
+                if (!inside && tstamp[f.u] == cur_chunk) {
                     // a Tip of the tree as the chunk found it (possibly the root of a new subtree now)
                     if (cur + newcnt[f.u] > (int64_t)0xffffffffu) { err = "arena offset overflow"; return false; }
                     P.copies.push_back(TipCopy{(uint32_t)cur, (uint32_t)N.off, (uint32_t)(newcnt[f.u] - pend_n[f.u]), pend_src[f.u], pend_n[f.u]});
@@ -309,21 +333,30 @@ __global__ void k_pool_update(const int32_t* __restrict__ src_g, const int32_t* 
     pmhi[o] = (hi0 <= hi) ? hi0 : hi;
 }
 
-// new content of every Tip: the chunk's piece (ids local to the chunk, + row0) followed by the old content
-// (Internal.hs:288 `xs <> xs0`).  One warp per (Tip, tree).
-__global__ void __launch_bounds__(256) k_tip_concat(const TipCopy* __restrict__ cp, int ncopy, int tg,
+// new content of every Tip: the chunk's piece (ids local to the batch, + row0) followed by the old content
+// (Internal.hs:288 `xs <> xs0`).  The descriptors are sorted by destination (the arena is laid out left to right), so
+// a thread owns one arena slot: it finds the slot's Tip by binary search once and moves that slot for every tree --
+// consecutive threads touch consecutive words of both arenas.
+__global__ void __launch_bounds__(256) k_tip_concat(const TipCopy* __restrict__ cp, int ncopy, int tg, uint32_t kept,
                                                      const uint32_t* __restrict__ piece, int64_t piece_stride, uint32_t row0,
                                                      const uint32_t* __restrict__ old_arena, uint32_t* __restrict__ new_arena, int64_t astride) {
-    const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (wid >= (int64_t)ncopy * tg) return;
-    const int i = (int)(wid / tg), t = (int)(wid % tg);
-    const TipCopy c = cp[i];
-    uint32_t* dst = new_arena + (int64_t)t * astride + c.dst;
-    const uint32_t* pn = piece + (int64_t)t * piece_stride + c.src_new;
-    const uint32_t* po = old_arena + (int64_t)t * astride + c.src_old;
-    for (uint32_t j = lane; j < c.n_new; j += 32) dst[j] = pn[j] + row0;
-    for (uint32_t j = lane; j < c.n_old; j += 32) dst[c.n_new + j] = po[j];
+    const uint32_t o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= kept) return;
+    int lo = 0, hi = ncopy - 1;                   // last descriptor with dst <= o
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (__ldg(&cp[mid].dst) <= o) lo = mid; else hi = mid - 1; }
+    const TipCopy c = cp[lo];
+    const uint32_t j = o - c.dst;
+    if (j >= c.n_new + c.n_old) return;           // (cannot happen: the descriptors tile [0, kept))
+    // blockIdx.y owns 8 trees; the 8 moves are independent (all loads issued before the stores)
+    const int tA = blockIdx.y * 8, tB = min(tg, tA + 8);
+    const uint32_t* src; int64_t sstride; uint32_t add;
+    if (j < c.n_new) { src = piece + c.src_new + j; sstride = piece_stride; add = row0; }
+    else { src = old_arena + c.src_old + (j - c.n_new); sstride = astride; add = 0; }
+    uint32_t v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) if (tA + q < tB) v[q] = __ldg(src + (int64_t)(tA + q) * sstride);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) if (tA + q < tB) new_arena[(int64_t)(tA + q) * astride + o] = v[q] + add;
 }
 
 // node-major pool -> canonical [T][nodes] forest arrays
@@ -340,8 +373,181 @@ __global__ void k_pool_export(const int32_t* __restrict__ pool_of, const int32_t
 }
 
 // =====================================================================================================
-// host orchestration
+// the plan of a whole streaming build (pure function of the shape: cached in the handle across builds)
 // =====================================================================================================
+namespace {
+
+struct RtGroupL { RtGroup g; size_t off_rg = (size_t)-1, off_pv = (size_t)-1; };
+struct StreamChunk {
+    int batch = 0; int64_t row0 = 0;
+    int n_upd = 0; size_t off_upd_g = 0, off_upd_u = 0; bool ct_set = false;
+    int n_copies = 0; size_t off_copies = 0; int64_t kept = 0;
+    int nnrt = 0; size_t off_rt_start = 0, off_rt_size = 0, off_rt_child = 0;
+    int n_rt_upd = 0; size_t off_rt_upd_g = 0, off_rt_upd_u = 0;
+    std::vector<RtGroupL> groups;
+};
+struct StreamBatch {
+    int64_t row0 = 0, rows = 0, nn = 0;
+    int first_chunk = 0, nchunks = 0;
+    JobPlan JP;                                  // the descent of all the batch's chunks, one level-synchronous job
+    size_t off_start = 0, off_size = 0, off_child = 0;
+};
+struct StreamPlanAll {
+    int64_t n = 0, chunk = 0; int maxDepth = 0, minLeaf = 0, cap = 0, Lk = 0; bool force_generic = false;
+    TableBuf TB;
+    char* d_tab = nullptr;
+    std::vector<StreamBatch> batches;
+    std::vector<StreamChunk> chunks;
+    Topology final_tp;
+    size_t off_pool_of = 0;
+    int64_t lost = 0, max_nn = 0, max_nnrt = 0, max_rows = 0;
+    size_t pool_nodes = 0;
+    bool order_exact = true;
+    ~StreamPlanAll() { if (d_tab) cudaFree(d_tab); }
+};
+void free_stream_plan(void* p) { delete (StreamPlanAll*)p; }
+
+// Plans every chunk (sequentially: the shape after chunk c depends on chunks < c) and groups the chunks into batches
+// whose descents run as ONE job: the routing of a chunk depends only on the tree SHAPE the chunk finds, which the
+// planner knows, never on the thresholds or leaf contents earlier chunks produced.
+bool build_stream_plan(StreamPlanAll& S, std::string& err) {
+    StreamPlanner SP;
+    SP.begin(S.n, S.maxDepth, S.minLeaf);
+    ChunkPlan P;
+    const int64_t node_cap = 6000000;            // temp node arrays of a batch: tg * nodes * 24 bytes
+    const int64_t top_per_chunk = 4 * ((S.chunk + S.cap - 1) / S.cap) + 2;      // top-phase nodes a chunk can contribute
+    const int64_t chunk_cap = S.chunk <= S.cap ? ((int64_t)1 << 40) : std::max<int64_t>(1, 60000 / top_per_chunk);
+    int64_t row = 0;
+    std::vector<Topology> cts;
+    std::vector<std::vector<int32_t>> upd_gs;
+    while (row < S.n) {
+        StreamBatch B;
+        B.row0 = row; B.first_chunk = (int)S.chunks.size();
+        size_t ncts = 0;
+        int64_t nodes = 0;
+        do {
+            const int64_t m = std::min(S.chunk, S.n - row);
+            if (!SP.plan_chunk(m, P)) { err = SP.err; return false; }
+            StreamChunk C;
+            C.batch = (int)S.batches.size(); C.row0 = row; C.ct_set = P.ct_set;
+            const uint32_t rel = (uint32_t)(row - B.row0);
+            for (TipCopy& c : P.copies) c.src_new += rel;
+            C.kept = P.kept;
+            C.n_copies = (int)P.copies.size(); C.off_copies = S.TB.put(P.copies.data(), P.copies.size() * sizeof(TipCopy));
+            C.n_upd = (int)P.upd_g.size(); C.off_upd_u = S.TB.put(P.upd_u.data(), P.upd_u.size() * 4);
+            C.nnrt = (int)P.rt_size.size();
+            C.off_rt_start = S.TB.put(P.rt_start.data(), P.rt_start.size() * 4);
+            C.off_rt_size = S.TB.put(P.rt_size.data(), P.rt_size.size() * 4);
+            C.off_rt_child = S.TB.put(P.rt_child.data(), P.rt_child.size() * 4);
+            C.n_rt_upd = (int)P.rt_upd_g.size();
+            C.off_rt_upd_g = S.TB.put(P.rt_upd_g.data(), P.rt_upd_g.size() * 4);
+            C.off_rt_upd_u = S.TB.put(P.rt_upd_u.data(), P.rt_upd_u.size() * 4);
+            S.max_nnrt = std::max<int64_t>(S.max_nnrt, C.nnrt);
+            for (RtGroup& G : P.groups) {
+                RtGroupL GL;
+                int maxrel = 0;                   // depth of the deepest descendant below this group's roots
+                std::vector<int32_t> fr, nx;
+                std::vector<uint32_t> pv((size_t)G.depth, 1);
+                for (int e = 0; e < G.count; ++e) fr.push_back(G.first + e);
+                for (int rl = 0; !fr.empty(); ++rl) {
+                    uint32_t mx = 1; nx.clear();
+                    for (int32_t g : fr) { mx = std::max(mx, P.rt_size[g]); if (P.rt_child[g] >= 0) { nx.push_back(P.rt_child[g]); nx.push_back(P.rt_child[g] + 1); } }
+                    uint32_t p2 = 1; while (p2 < mx) p2 <<= 1;
+                    pv.push_back(p2);              // next_pow2(max size) at absolute level G.depth + rl
+                    if (!nx.empty()) maxrel = rl + 1;
+                    fr.swap(nx);
+                }
+                G.nlb = std::max(1, maxrel + 1);
+                G.levels = maxrel;
+                G.fast = maxrel <= rpf_bottom_fast_levels() && !S.force_generic;
+                if (G.fast) {
+                    unsigned slots = 256; while (slots < G.max_root) slots <<= 1;
+                    while (maxrel > 0 && (slots >> maxrel) == 0) slots <<= 1;
+                    if (slots > 8192) G.fast = false;
+                }
+                GL.g = G;
+                if (!G.fast) {
+                    std::vector<int2> rg;
+                    make_ranges(P.rt_child, G.first, G.count, G.nlb, rg);
+                    GL.off_rg = S.TB.put(rg.data(), rg.size() * sizeof(int2));
+                    GL.off_pv = S.TB.put(pv.data(), pv.size() * 4);
+                }
+                C.groups.push_back(GL);
+            }
+            S.chunks.push_back(std::move(C));
+            nodes += P.ct.nnodes();
+            if (ncts == cts.size()) { cts.emplace_back(); upd_gs.emplace_back(); }
+            std::swap(cts[ncts], P.ct);            // P gets an old chunk tree's storage back
+            upd_gs[ncts].assign(P.upd_g.begin(), P.upd_g.end());
+            ++ncts;
+            row += m;
+        } while (row < S.n && nodes < node_cap && (int64_t)ncts < chunk_cap);
+        B.rows = row - B.row0; B.nchunks = (int)ncts;
+
+        // ---- super topology of the batch: level l = the level-l nodes of every chunk tree, chunk-major
+        Topology sup;
+        sup.n = B.rows; sup.maxDepth = S.maxDepth; sup.minLeaf = S.minLeaf;
+        int nl = 0;
+        for (size_t j = 0; j < ncts; ++j) nl = std::max(nl, cts[j].nlevels);
+        std::vector<std::vector<int64_t>> base(ncts, std::vector<int64_t>(nl + 1, 0));
+        sup.level_off.assign(nl + 1, 0);
+        {
+            int64_t tot = 0;
+            for (int l = 0; l < nl; ++l) {
+                sup.level_off[l] = tot;
+                for (size_t j = 0; j < ncts; ++j) {
+                    base[j][l] = tot;
+                    if (l < cts[j].nlevels) tot += cts[j].level_off[l + 1] - cts[j].level_off[l];
+                }
+            }
+            sup.level_off[nl] = tot;
+            sup.start.resize(tot); sup.size.resize(tot); sup.child.resize(tot); sup.depth.resize(tot);
+        }
+        sup.nlevels = nl; sup.lvl_maxsize.assign(nl, 0); sup.L_eff = 0;
+        for (size_t j = 0; j < ncts; ++j) {
+            const Topology& ct = cts[j];
+            const uint32_t rel = (uint32_t)(S.chunks[B.first_chunk + j].row0 - B.row0);
+            sup.L_eff = std::max(sup.L_eff, ct.L_eff);
+            for (int l = 0; l < ct.nlevels; ++l) {
+                const int64_t lo = ct.level_off[l], hi = ct.level_off[l + 1];
+                for (int64_t g = lo; g < hi; ++g) {
+                    const int64_t sg = base[j][l] + (g - lo);
+                    sup.start[sg] = rel + ct.start[g]; sup.size[sg] = ct.size[g]; sup.depth[sg] = l;
+                    sup.child[sg] = ct.child[g] < 0 ? -1 : (int32_t)(base[j][l + 1] + (ct.child[g] - ct.level_off[l + 1]));
+                    sup.lvl_maxsize[l] = std::max(sup.lvl_maxsize[l], ct.size[g]);
+                }
+            }
+            // pool updates of this chunk: chunk-tree id -> id in the batch job
+            std::vector<int32_t>& ug = upd_gs[j];
+            for (int32_t& g : ug) { const int l = ct.depth[g]; g = (int32_t)(base[j][l] + (g - ct.level_off[l])); }
+            S.chunks[B.first_chunk + j].off_upd_g = S.TB.put(ug.data(), ug.size() * 4);
+        }
+        B.nn = sup.nnodes();
+        B.off_start = S.TB.put(sup.start.data(), sup.start.size() * 4);
+        B.off_size = S.TB.put(sup.size.data(), sup.size.size() * 4);
+        B.off_child = S.TB.put(sup.child.data(), sup.child.size() * 4);
+        TableBuf jt;
+        rpf_plan_job(sup, S.cap, S.Lk, S.force_generic, jt, B.JP);
+        {   // re-base the job's table offsets into the plan's block
+            const size_t o = S.TB.put(jt.bytes.data(), jt.bytes.size());
+            if (B.JP.off_range != (size_t)-1) B.JP.off_range += o;
+            if (B.JP.off_lvlpv != (size_t)-1) B.JP.off_lvlpv += o;
+            B.JP.off_nb += o;
+        }
+        if (B.JP.G.s_top > 0 && B.JP.G.NTOP > 65535) { err = "internal: batch exceeds 16-bit labels"; return false; }
+        if (!B.JP.G.order_exact) S.order_exact = false;
+        S.max_nn = std::max(S.max_nn, B.nn); S.max_rows = std::max(S.max_rows, B.rows);
+        S.batches.push_back(std::move(B));
+    }
+    std::vector<int32_t> pool_of;
+    SP.final_topology(S.final_tp, pool_of);
+    S.off_pool_of = S.TB.put(pool_of.data(), pool_of.size() * 4);
+    S.lost = SP.lost; S.pool_nodes = SP.pool.size();
+    return true;
+}
+
+}  // namespace
+
 #define WSX(h, var, type, slot, bytes)                                  \
     type* var = (type*)(h)->ws_get((slot), (bytes));                    \
     if (!var) return RPF_ERR_NOMEM;
@@ -350,13 +556,35 @@ int rpf_build_stream_impl(rpf_handle* h, int maxDepth, int minLeaf, int64_t chun
     const int64_t n = h->n;
     const int T = h->T;
     const int Lk = std::max(maxDepth, 1);
-    h->leaf_order_exact = true;
 
-    // ---- tree group size: persistent key store [Tg][Lk][n] + two leaf arenas + per-chunk job workspace
+    // ---- the plan: cached per shape (like the batch topology, it does not depend on the data)
+    StreamPlanAll* S = (StreamPlanAll*)h->stream_plan;
+    if (!S || S->n != n || S->chunk != chunk || S->maxDepth != maxDepth || S->minLeaf != minLeaf || S->cap != h->bottom_cap ||
+        S->force_generic != h->force_generic_bottom) {
+        if (S) { cudaStreamSynchronize(h->stream); delete S; h->stream_plan = nullptr; }
+        S = new StreamPlanAll();
+        S->n = n; S->chunk = chunk; S->maxDepth = maxDepth; S->minLeaf = minLeaf; S->cap = h->bottom_cap; S->Lk = Lk;
+        S->force_generic = h->force_generic_bottom;
+        std::string err;
+        if (!build_stream_plan(*S, err)) { delete S; return rpf_fail(h, RPF_ERR_UNSUPPORTED, err); }
+        if (cudaMalloc(&S->d_tab, std::max<size_t>(S->TB.bytes.size(), 256)) != cudaSuccess) { cudaGetLastError(); delete S; return rpf_fail(h, RPF_ERR_NOMEM, "stream plan: device tables"); }
+        cudaError_t e = cudaMemcpyAsync(S->d_tab, S->TB.bytes.data(), S->TB.bytes.size(), cudaMemcpyHostToDevice, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) { delete S; return rpf_fail(h, RPF_ERR_CUDA, std::string("stream plan upload: ") + cudaGetErrorString(e)); }
+        S->TB.bytes.clear(); S->TB.bytes.shrink_to_fit();      // the tables live on the device from here on
+        h->stream_plan = S; h->stream_plan_free = free_stream_plan;
+    }
+    h->leaf_order_exact = S->order_exact;
+    h->stream_lost = S->lost;
+    const char* tab = S->d_tab;
+
+    // ---- tree group size: persistent key store [Tg][Lk][n] + two leaf arenas + the batch jobs' workspace
     size_t freeB = 0, totalB = 0;
     RPF_CUDA(h, cudaMemGetInfo(&freeB, &totalB));
-    const int64_t mmax = std::min(chunk, n);
-    const size_t per_tree = (size_t)Lk * n * 8 + (size_t)n * 8 + (size_t)mmax * 32 + ((size_t)1 << 20);
+    size_t job_ws = 0;
+    for (const StreamBatch& B : S->batches) job_ws = std::max(job_ws, rpf_job_ws_per_tree(B.JP.G, B.rows));
+    const size_t per_tree = (size_t)Lk * n * 8 + (size_t)n * 8 + (size_t)S->max_rows * 4 + job_ws +
+                            (size_t)(S->max_nn + S->max_nnrt + 2 + (int64_t)S->pool_nodes) * 24 + ((size_t)1 << 16);
     const size_t budget = (size_t)((double)(freeB + h->ws_bytes) * 0.7);
     if (per_tree > budget) return rpf_fail(h, RPF_ERR_NOMEM, "not enough device memory for one tree's keys");
     const int Tg = (int)std::min<size_t>((size_t)T, std::max<size_t>(1, budget / per_tree));
@@ -366,176 +594,81 @@ int rpf_build_stream_impl(rpf_handle* h, int maxDepth, int minLeaf, int64_t chun
     WSX(h, kmax, ull, WS_KMAX, (size_t)Tg * Lk * 8);
     WSX(h, arena0, uint32_t, WS_S_ARENA0, (size_t)Tg * n * 4);
     WSX(h, arena1, uint32_t, WS_S_ARENA1, (size_t)Tg * n * 4);
-    WSX(h, cperm, uint32_t, WS_S_CPERM, (size_t)Tg * mmax * 4);
+    WSX(h, cperm, uint32_t, WS_S_CPERM, (size_t)Tg * S->max_rows * 4);
+    WSX(h, tmpn, double, WS_S_TMPN, (size_t)Tg * (S->max_nn + S->max_nnrt + 2) * 8 * 3);
+    WSX(h, pool, double, WS_S_POOL, (size_t)Tg * (S->pool_nodes + 1) * 8 * 3);
 
-    if (h->stream_pool) { cudaFree(h->stream_pool); h->stream_pool = nullptr; }     // left over from a failed call
-    StreamPlanner SP;
-    Topology final_tp; std::vector<int32_t> pool_of;
-    ChunkPlan P;
+    // ---- canonical result shape
+    h->topo = S->final_tp;
+    int rc = rpf_upload_topology(h);
+    if (rc) return rc;
+    const int64_t nn = h->topo.nnodes();
+    rc = rpf_alloc_forest(h, nn, n);
+    if (rc) return rc;
+
     for (int t0 = 0; t0 < T; t0 += Tg) {
         const int tg = std::min(Tg, T - t0);
-        SP.begin(n, maxDepth, minLeaf);
         uint32_t* arena_old = arena0; uint32_t* arena_new = arena1;
         RPF_CUDA(h, cudaMemsetAsync(arena0, 0xff, (size_t)tg * n * 4, h->stream));     // slots past the kept points stay 0xffffffff
         RPF_CUDA(h, cudaMemsetAsync(arena1, 0xff, (size_t)tg * n * 4, h->stream));
-        double* pthr = nullptr; double* pmlo = nullptr; double* pmhi = nullptr; size_t pool_cap = 0;
-        for (int64_t row0 = 0; row0 < n; row0 += chunk) {
-            const int64_t m = std::min(chunk, n - row0);
-            if (!SP.plan_chunk(m, P)) return rpf_fail(h, RPF_ERR_UNSUPPORTED, SP.err);
-            const Topology& ct = P.ct;
-            const int64_t nnct = ct.nnodes(), nnrt = (int64_t)P.rt_size.size();
-
-            // ---- pool arrays (node-major [cap][tg]); growth copies the prefix
-            if (SP.pool.size() > pool_cap) {
-                // without dropped subtrees the pool never exceeds min(2^(maxDepth+1), 2n) nodes: one allocation
-                const size_t bound = (size_t)std::min<int64_t>(maxDepth < 40 ? ((int64_t)1 << (maxDepth + 1)) : (int64_t)1 << 41, 2 * n + 2) + 2;
-                const size_t want = std::max<size_t>(std::max<size_t>(SP.pool.size() * 2, bound), 1024);
-                double* nb = nullptr;
-                RPF_CUDA(h, cudaMalloc(&nb, want * tg * 8 * 3));
-                if (pthr) {
-                    RPF_CUDA(h, cudaMemcpyAsync(nb, pthr, pool_cap * tg * 8, cudaMemcpyDeviceToDevice, h->stream));
-                    RPF_CUDA(h, cudaMemcpyAsync(nb + want * tg, pmlo, pool_cap * tg * 8, cudaMemcpyDeviceToDevice, h->stream));
-                    RPF_CUDA(h, cudaMemcpyAsync(nb + 2 * want * tg, pmhi, pool_cap * tg * 8, cudaMemcpyDeviceToDevice, h->stream));
-                    RPF_CUDA(h, cudaStreamSynchronize(h->stream));
-                    cudaFree(pthr);
-                }
-                pthr = nb; pmlo = nb + want * tg; pmhi = nb + 2 * want * tg; pool_cap = want;
-                h->stream_pool = nb;      // owned by the handle until the end of the call (freed on error paths too)
-            }
-
-            // ---- stage this chunk's tables (CT topology, update lists, copy descriptors, RT forest)
-            size_t bytes = (size_t)nnct * 12 + (P.upd_g.size() + P.rt_upd_g.size()) * 8 + P.copies.size() * sizeof(TipCopy) + (size_t)nnrt * 12;
-            std::vector<std::vector<int2>> g_rg(P.groups.size());
-            std::vector<std::vector<uint32_t>> g_pv(P.groups.size());
-            for (size_t gi = 0; gi < P.groups.size(); ++gi) {
-                RtGroup& G = P.groups[gi];
-                // depth of the deepest descendant below this group's roots
-                int maxrel = 0;
-                {
-                    std::vector<int32_t> fr;
-                    for (int e = 0; e < G.count; ++e) fr.push_back(G.first + e);
-                    int rel = 0;
-                    while (!fr.empty()) {
-                        std::vector<int32_t> nx;
-                        for (int32_t g : fr) if (P.rt_child[g] >= 0) { nx.push_back(P.rt_child[g]); nx.push_back(P.rt_child[g] + 1); }
-                        if (!nx.empty()) maxrel = ++rel;
-                        fr.swap(nx);
-                    }
-                }
-                G.nlb = std::max(1, maxrel + 1);
-                G.fast = minLeaf >= 1 && maxrel <= rpf_bottom_fast_levels() && !h->force_generic_bottom;
-                if (!G.fast) {
-                    make_ranges(P.rt_child, G.first, G.count, G.nlb, g_rg[gi]);
-                    // next_pow2(max size) per absolute level among this group's descendants
-                    g_pv[gi].assign((size_t)G.depth + G.nlb, 1);
-                    std::vector<int32_t> fr;
-                    for (int e = 0; e < G.count; ++e) fr.push_back(G.first + e);
-                    for (int rel = 0; !fr.empty(); ++rel) {
-                        uint32_t mx = 1; std::vector<int32_t> nx;
-                        for (int32_t g : fr) { mx = std::max(mx, P.rt_size[g]); if (P.rt_child[g] >= 0) { nx.push_back(P.rt_child[g]); nx.push_back(P.rt_child[g] + 1); } }
-                        uint32_t p2 = 1; while (p2 < mx) p2 <<= 1;
-                        g_pv[gi][(size_t)G.depth + rel] = p2;
-                        fr.swap(nx);
-                    }
-                    bytes += g_rg[gi].size() * sizeof(int2) + g_pv[gi].size() * 4 + 512;
-                }
-            }
-            int rc = h->stage_begin(bytes + 16 * 256);
-            if (rc) return rc;
-            const uint32_t* d_ct_start = h->stage_put(ct.start.data(), ct.start.size());
-            const uint32_t* d_ct_size = h->stage_put(ct.size.data(), ct.size.size());
-            const int32_t* d_ct_child = h->stage_put(ct.child.data(), ct.child.size());
-            const int32_t* d_upd_g = h->stage_put(P.upd_g.data(), P.upd_g.size());
-            const int32_t* d_upd_u = h->stage_put(P.upd_u.data(), P.upd_u.size());
-            const TipCopy* d_copies = h->stage_put(P.copies.data(), P.copies.size());
-            const uint32_t* d_rt_start = h->stage_put(P.rt_start.data(), P.rt_start.size());
-            const uint32_t* d_rt_size = h->stage_put(P.rt_size.data(), P.rt_size.size());
-            const int32_t* d_rt_child = h->stage_put(P.rt_child.data(), P.rt_child.size());
-            const int32_t* d_rt_upd_g = h->stage_put(P.rt_upd_g.data(), P.rt_upd_g.size());
-            const int32_t* d_rt_upd_u = h->stage_put(P.rt_upd_u.data(), P.rt_upd_u.size());
-            std::vector<const int2*> d_rg(P.groups.size(), nullptr);
-            std::vector<const uint32_t*> d_pv(P.groups.size(), nullptr);
-            for (size_t gi = 0; gi < P.groups.size(); ++gi)
-                if (!P.groups[gi].fast) { d_rg[gi] = h->stage_put(g_rg[gi].data(), g_rg[gi].size()); d_pv[gi] = h->stage_put(g_pv[gi].data(), g_pv[gi].size()); }
-            if (!d_ct_start || !d_ct_size || !d_ct_child) return rpf_fail(h, RPF_ERR_NOMEM, h->err);
-            rc = h->stage_flush();
-            if (rc) return rc;
-
-            // ---- temp node arrays of the chunk job and of the re-splits
-            WSX(h, tmpn, double, WS_S_TMPN, (size_t)tg * (nnct + nnrt + 2) * 8 * 3);
-            double* cthr = tmpn; double* cmlo = cthr + (size_t)tg * nnct; double* cmhi = cmlo + (size_t)tg * nnct;
-            double* rthr = cmhi + (size_t)tg * nnct; double* rmlo = rthr + (size_t)tg * nnrt; double* rmhi = rmlo + (size_t)tg * nnrt;
-
-            // ---- 1. keys of the chunk's points
+        double* pthr = pool; double* pmlo = pthr + (size_t)tg * S->pool_nodes; double* pmhi = pmlo + (size_t)tg * S->pool_nodes;
+        for (const StreamBatch& B : S->batches) {
+            const int64_t nnb = B.nn;
+            double* cthr = tmpn; double* cmlo = cthr + (size_t)tg * nnb; double* cmhi = cmlo + (size_t)tg * nnb;
+            double* rthr = cmhi + (size_t)tg * nnb; double* rmlo = rthr + (size_t)tg * S->max_nnrt; double* rmhi = rmlo + (size_t)tg * S->max_nnrt;
+            // ---- 1. keys of the batch's points
             RPF_CUDA(h, cudaMemsetAsync(kmin, 0xff, (size_t)tg * Lk * 8, h->stream));
             RPF_CUDA(h, cudaMemsetAsync(kmax, 0x00, (size_t)tg * Lk * 8, h->stream));
             if (maxDepth > 0) {
-                rc = rpf_project_launch(h, PH_PROJECT, h->dX + row0 * (int64_t)h->d, m, t0, tg, Lk, true, keys + row0, n, kmin, kmax);
+                rc = rpf_project_launch(h, PH_PROJECT, h->dX + B.row0 * (int64_t)h->d, B.rows, t0, tg, Lk, true, keys + B.row0, n, kmin, kmax);
                 if (rc) return rc;
             }
-            // ---- 2. the chunk descends through the Bins of the current tree
+            // ---- 2. every chunk of the batch descends through the Bins of the tree it finds (one job)
             BuildJob J{};
-            J.tp = &ct; J.d_start = d_ct_start; J.d_size = d_ct_size; J.d_child = d_ct_child;
-            J.n = m; J.ks = n; J.ps = mmax; J.ns = nnct; J.Lk = Lk;
-            J.keys = keys + row0; J.kmin = kmin; J.kmax = kmax;
+            J.d_start = (const uint32_t*)(tab + B.off_start); J.d_size = (const uint32_t*)(tab + B.off_size); J.d_child = (const int32_t*)(tab + B.off_child);
+            J.n = B.rows; J.ks = n; J.ps = S->max_rows; J.ns = nnb; J.Lk = Lk;
+            J.keys = keys + B.row0; J.kmin = kmin; J.kmax = kmax;
             J.perm = cperm; J.thr = cthr; J.mlo = cmlo; J.mhi = cmhi; J.gt0 = 0; J.tg = tg;
-            rc = rpf_run_job(h, J);
+            rc = rpf_launch_job(h, J, B.JP, tab);
             if (rc) return rc;
-            if (!J.order_exact) h->leaf_order_exact = false;
-            // ---- 3. thr' = (thr0 + thr) / 2, margin' = margin0 <> margin
-            if (!P.upd_g.empty()) {
-                const int64_t tot = (int64_t)P.upd_g.size() * tg;
-                RPF_LAUNCH(h, PH_STREAM, k_pool_update, (unsigned)((tot + 255) / 256), 256, 0, d_upd_g, d_upd_u, (int)P.upd_g.size(), tg, nnct,
-                           cthr, cmlo, cmhi, pthr, pmlo, pmhi, P.ct_set ? 0 : 1);
+            // ---- 3..5 per chunk, in arrival order
+            for (int ci = B.first_chunk; ci < B.first_chunk + B.nchunks; ++ci) {
+                const StreamChunk& C = S->chunks[ci];
+                if (C.n_upd) {        // thr' = (thr0 + thr) / 2, margin' = margin0 <> margin
+                    const int64_t tot = (int64_t)C.n_upd * tg;
+                    RPF_LAUNCH(h, PH_STREAM, k_pool_update, (unsigned)((tot + 255) / 256), 256, 0, (const int32_t*)(tab + C.off_upd_g),
+                               (const int32_t*)(tab + C.off_upd_u), C.n_upd, tg, nnb, cthr, cmlo, cmhi, pthr, pmlo, pmhi, C.ct_set ? 0 : 1);
+                }
+                if (C.n_copies && C.kept) {     // Tip contents: piece ++ old
+                    RPF_LAUNCH(h, PH_STREAM_CONCAT, k_tip_concat, dim3((unsigned)((C.kept + 255) / 256), (unsigned)((tg + 7) / 8)), 256, 0, (const TipCopy*)(tab + C.off_copies), C.n_copies, tg,
+                               (uint32_t)C.kept, cperm, S->max_rows, (uint32_t)B.row0, arena_old, arena_new, n);
+                }
+                for (const RtGroupL& GL : C.groups) {      // Tips that outgrew minLeaf split in place
+                    const RtGroup& G = GL.g;
+                    BottomArgs A{};
+                    A.ks = n; A.ps = n; A.nn_all = S->max_nnrt; A.L = Lk; A.s = G.depth; A.nlb = G.nlb; A.gt0 = 0; A.first_gid = G.first;
+                    A.given_order = 1;
+                    A.keys = keys; A.perm = arena_new; A.child = (const int32_t*)(tab + C.off_rt_child);
+                    A.nstart = (const uint32_t*)(tab + C.off_rt_start); A.nsize = (const uint32_t*)(tab + C.off_rt_size);
+                    A.range = GL.off_rg == (size_t)-1 ? nullptr : (const int2*)(tab + GL.off_rg);
+                    A.lvl_pv = GL.off_pv == (size_t)-1 ? nullptr : (const uint32_t*)(tab + GL.off_pv);
+                    A.thr = rthr; A.mlo = rmlo; A.mhi = rmhi;
+                    rc = rpf_bottom_launch(h, A, G.count, tg, G.fast, G.max_root, G.levels);
+                    if (rc) return rc;
+                }
+                if (C.n_rt_upd) {
+                    const int64_t tot = (int64_t)C.n_rt_upd * tg;
+                    RPF_LAUNCH(h, PH_STREAM, k_pool_update, (unsigned)((tot + 255) / 256), 256, 0, (const int32_t*)(tab + C.off_rt_upd_g),
+                               (const int32_t*)(tab + C.off_rt_upd_u), C.n_rt_upd, tg, S->max_nnrt, rthr, rmlo, rmhi, pthr, pmlo, pmhi, 0);
+                }
+                std::swap(arena_old, arena_new);
             }
-            // ---- 4. Tip contents: piece ++ old
-            if (!P.copies.empty()) {
-                const int64_t warps = (int64_t)P.copies.size() * tg;
-                RPF_LAUNCH(h, PH_STREAM, k_tip_concat, (unsigned)((warps + 7) / 8), 256, 0, d_copies, (int)P.copies.size(), tg,
-                           cperm, mmax, (uint32_t)row0, arena_old, arena_new, n);
-            }
-            // ---- 5. Tips that outgrew minLeaf split in place
-            for (size_t gi = 0; gi < P.groups.size(); ++gi) {
-                const RtGroup& G = P.groups[gi];
-                BottomArgs B{};
-                B.ks = n; B.ps = n; B.nn_all = nnrt; B.L = Lk; B.s = G.depth; B.nlb = G.nlb; B.gt0 = 0; B.first_gid = G.first;
-                B.given_order = 1;
-                B.keys = keys; B.perm = arena_new; B.child = d_rt_child; B.nstart = d_rt_start; B.nsize = d_rt_size;
-                B.range = d_rg[gi]; B.lvl_pv = d_pv[gi]; B.thr = rthr; B.mlo = rmlo; B.mhi = rmhi;
-                rc = rpf_bottom_launch(h, B, G.count, tg, G.fast, G.max_root);
-                if (rc) return rc;
-            }
-            if (!P.rt_upd_g.empty()) {
-                const int64_t tot = (int64_t)P.rt_upd_g.size() * tg;
-                RPF_LAUNCH(h, PH_STREAM, k_pool_update, (unsigned)((tot + 255) / 256), 256, 0, d_rt_upd_g, d_rt_upd_u, (int)P.rt_upd_g.size(), tg, nnrt,
-                           rthr, rmlo, rmhi, pthr, pmlo, pmhi, 0);
-            }
-            std::swap(arena_old, arena_new);
         }
-
-        // ---- canonical export of this tree group: BFS topology, [T][nodes] node arrays, perm = final arena
-        SP.final_topology(final_tp, pool_of);
-        const int64_t nn = final_tp.nnodes();
-        if (t0 == 0) {
-            h->topo = final_tp;
-            int rc = rpf_upload_topology(h);
-            if (rc) return rc;
-            rc = rpf_alloc_forest(h, nn, n);
-            if (rc) return rc;
-            h->stream_lost = SP.lost;
-        }
-        int rc = h->stage_begin((size_t)nn * 4 + 1024);
-        if (rc) return rc;
-        const int32_t* d_pool_of = h->stage_put(pool_of.data(), pool_of.size());
-        rc = h->stage_flush();
-        if (rc) return rc;
-        RPF_LAUNCH(h, PH_STREAM, k_pool_export, (unsigned)((nn * tg + 255) / 256), 256, 0, d_pool_of, h->d_node_child, nn, tg, t0,
+        // ---- canonical export of this tree group: [T][nodes] node arrays, perm = final arena
+        RPF_LAUNCH(h, PH_STREAM, k_pool_export, (unsigned)((nn * tg + 255) / 256), 256, 0, (const int32_t*)(tab + S->off_pool_of), h->d_node_child, nn, tg, t0,
                    pthr, pmlo, pmhi, h->d_thr, h->d_mlo, h->d_mhi);
         for (int t = 0; t < tg; ++t)
             RPF_CUDA(h, cudaMemcpyAsync(h->d_perm + (int64_t)(t0 + t) * n, arena_old + (int64_t)t * n, (size_t)n * 4, cudaMemcpyDeviceToDevice, h->stream));
-        RPF_CUDA(h, cudaStreamSynchronize(h->stream));
-        if (pthr) cudaFree(pthr);
-        h->stream_pool = nullptr;
     }
     return RPF_OK;
 }

@@ -236,6 +236,9 @@ STREAM_CASES = [
     pytest.param(600, 3, 2, 8, 0, 50, 1.0, "gauss", 256, id="minleaf0"),
     pytest.param(40000, 8, 2, 12, 1000, 10000, 0.5, "gauss", 1024, id="big-leaves-resplit-2000"),
     pytest.param(100000, 16, 2, 12, 32, 1000, 0.3, "mixture", 1024, id="rptreecfg-like-100-chunks"),
+    pytest.param(10003, 6, 3, 10, 10, 5000, 0.5, "gauss", 256, id="three-point-last-chunk-in-top-phase"),
+    pytest.param(10001, 6, 3, 10, 10, 2500, 0.5, "integer", 256, id="one-point-last-chunk-in-top-phase-ties"),
+    pytest.param(60000, 8, 2, 13, 10, 3000, 0.5, "gauss", 512, id="20-chunks-top-phase-cap512"),
 ]
 
 
