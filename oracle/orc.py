@@ -42,6 +42,7 @@ def lib():
         L.orc_std_normal.restype = C.c_double
         L.orc_inner_sd.restype = C.c_double
         L.orc_inner_sd.argtypes = [C.c_int64, c_i32p, c_f64p, c_f64p, C.c_int64]
+        L.orc_project_all.argtypes = [C.c_int64, c_i32p, c_f64p, c_f64p, C.c_int64, C.c_int64, c_f64p]
         L.orc_inner_ss.restype = C.c_double
         L.orc_inner_ss.argtypes = [C.c_int64, c_i32p, c_f64p, C.c_int64, c_i32p, c_f64p]
         L.orc_inner_dd.restype = C.c_double
@@ -102,6 +103,18 @@ def inner_sd(idx, val, x):
     val = np.ascontiguousarray(val, np.float64)
     x = np.ascontiguousarray(x, np.float64)
     return lib().orc_inner_sd(len(idx), _p(idx, c_i32p), _p(val, c_f64p), _p(x, c_f64p), len(x))
+
+
+def project_all(hp, row, X):
+    """innerSD of CSR row `row` of hp = (off, idx, val) against every row of X."""
+    off, idx, val = hp
+    X = np.ascontiguousarray(X, np.float64)
+    a, b = int(off[row]), int(off[row + 1])
+    ii = np.ascontiguousarray(idx[a:b] if b > a else np.zeros(1), np.int32)
+    vv = np.ascontiguousarray(val[a:b] if b > a else np.zeros(1), np.float64)
+    out = np.zeros(X.shape[0])
+    lib().orc_project_all(b - a, _p(ii, c_i32p), _p(vv, c_f64p), _p(X, c_f64p), X.shape[0], X.shape[1], _p(out, c_f64p))
+    return out
 
 
 def inner_ss(i1, v1, i2, v2):

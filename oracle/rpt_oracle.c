@@ -101,6 +101,12 @@ double orc_inner_sd(int64_t nz, const int32_t* idx, const double* val, const dou
     return acc;
 }
 
+/* innerSD of one hyperplane against every row of X (n x d row-major): the keys partitionAtMedian sorts by
+ * (Internal.hs:504).  Used by the full-size property tests. */
+void orc_project_all(int64_t nz, const int32_t* idx, const double* val, const double* X, int64_t n, int64_t d, double* out) {
+    for (int64_t i = 0; i < n; ++i) out[i] = orc_inner_sd(nz, idx, val, X + i * d, d);
+}
+
 /* innerSS, Internal.hs:351-366: merge join, right fold over the matches. */
 double orc_inner_ss(int64_t nz1, const int32_t* i1, const double* v1, int64_t nz2, const int32_t* i2, const double* v2) {
     /* collect matches left to right, then fold from the right */

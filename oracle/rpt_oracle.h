@@ -35,6 +35,7 @@ double   orc_std_normal(orc_smgen* g);
 
 /* ---- vector algebra: src/Data/RPTree/Internal.hs ---- */
 double orc_inner_sd(int64_t nz, const int32_t* idx, const double* val, const double* x, int64_t d); /* :369-382 */
+void   orc_project_all(int64_t nz, const int32_t* idx, const double* val, const double* X, int64_t n, int64_t d, double* out);
 double orc_inner_ss(int64_t nz1, const int32_t* i1, const double* v1,
                     int64_t nz2, const int32_t* i2, const double* v2);                            /* :351-366 */
 double orc_inner_dd(const double* u, const double* v, int64_t d);                                  /* :384-385 */
