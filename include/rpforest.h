@@ -50,6 +50,18 @@ int rpf_set_points(rpf_handle* h, const double* X, int64_t n, int32_t d);
 /* Same, but X_dev is a device pointer on this handle's device; it is borrowed (must outlive the handle's use). */
 int rpf_set_points_device(rpf_handle* h, const double* X_dev, int64_t n, int32_t d);
 
+/* ---- data: V.Vector (Embed SVector Double x)  (Internal.hs:92-97; the reference bench's own data type,
+ *      bench/time/Main.hs:77,113-122) -------------------------------------------------------------------------- */
+/* n SVectors of dimension d as CSR rows (off[n+1]; idx strictly ascending per row).  The engine keeps a dense n x d
+ * image plus every row's last stored component.  Projections are innerSS (Internal.hs:351-366) -- identical to innerSD
+ * on the dense image for finite data; distances are metricSDL2 / metricSSL2 (Internal.hs:389-400) INCLUDING the
+ * reference's quirk: binSDD / binSS stop when either operand is exhausted (Internal.hs:432-470), so components past the
+ * sparse operand's last stored index are ignored. */
+int rpf_set_points_sparse(rpf_handle* h, int64_t n, int32_t d, const int64_t* off, const int32_t* idx, const double* val);
+int rpf_points_are_sparse(const rpf_handle* h);
+/* Host-only helper for SVector QUERIES: CSR rows -> dense nq x d image Q + q_last[i] = last stored component (-1: none). */
+int rpf_densify_rows(int64_t nq, int32_t d, const int64_t* off, const int32_t* idx, const double* val, double* Q, int32_t* q_last);
+
 /* ---- hyperplanes: one SVector per (tree, level)  (Internal.hs:92-93,172-175) ---------------------- */
 /* PRIMARY path: the Haskell host draws rvss with the real `sample seed (replicateM ntrees (V.replicateM
  * maxd (sparse pnz dim stdNormal)))` (src/Data/RPTree/Batch.hs:57-63, Conduit.hs:114-121) and passes them
@@ -130,6 +142,15 @@ int rpf_knn(rpf_handle* h, const double* Q, int64_t nq, int32_t k, int32_t dedup
 int rpf_recall(rpf_handle* h, const double* Q, int64_t nq, int32_t k, double* recall_sum);
 /* Exact brute-force k nearest rows (ties by row id): ground truth for forest-level recall. */
 int rpf_brute_knn(rpf_handle* h, const double* Q, int64_t nq, int32_t k, double* dist, uint32_t* ids);
+
+/* The same three for SVector data with the query's representation made explicit: q_last == NULL means DVector queries
+ * (metricSDL2; identical to rpf_knn / rpf_recall / rpf_brute_knn), otherwise SVector queries given as their dense image
+ * plus q_last (rpf_densify_rows) -> metricSSL2.  SVector queries against DVector data are rejected (no such Inner
+ * instance in the reference, Internal.hs:322-341). */
+int rpf_knn_s(rpf_handle* h, const double* Q, const int32_t* q_last, int64_t nq, int32_t k, int32_t dedup,
+              double* dist, uint32_t* ids, int32_t* count);
+int rpf_recall_s(rpf_handle* h, const double* Q, const int32_t* q_last, int64_t nq, int32_t k, double* recall_sum);
+int rpf_brute_knn_s(rpf_handle* h, const double* Q, const int32_t* q_last, int64_t nq, int32_t k, double* dist, uint32_t* ids);
 
 /* ---- multi-GPU: merge per-GPU top-k lists (trees sharded in contiguous blocks, rank-major) ---------- */
 /* dist/ids: G x nq x k, count: G x nq (rank-major).  Result ordered by (distance, rank, position), which

@@ -59,6 +59,19 @@ def lib():
         L.orc_forest_new.argtypes = [c_f64p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_i64p, c_i32p, c_f64p]
         L.orc_forest_new_chunked.restype = C.c_void_p
         L.orc_forest_new_chunked.argtypes = [c_f64p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64, c_i64p, c_i32p, c_f64p]
+        L.orc_forest_new_sparse.restype = C.c_void_p
+        L.orc_forest_new_sparse.argtypes = [C.c_int64, C.c_int32, c_i64p, c_i32p, c_f64p, C.c_int32, C.c_int32, C.c_int32, C.c_int64,
+                                            c_i64p, c_i32p, c_f64p]
+        L.orc_candidates_sq.restype = C.c_int64
+        L.orc_candidates_sq.argtypes = [C.c_void_p, C.c_int32, C.c_int64, c_i32p, c_f64p, c_u32p, C.c_int64]
+        L.orc_knn_sq.restype = C.c_int64
+        L.orc_knn_sq.argtypes = [C.c_void_p, C.c_int64, c_i32p, c_f64p, C.c_int32, C.c_int32, c_f64p, c_u32p]
+        L.orc_recall_sq.restype = C.c_double
+        L.orc_recall_sq.argtypes = [C.c_void_p, C.c_int64, c_i32p, c_f64p, C.c_int32]
+        L.orc_metric_ss_l2.restype = C.c_double
+        L.orc_metric_ss_l2.argtypes = [C.c_int64, c_i32p, c_f64p, C.c_int64, c_i32p, c_f64p]
+        L.orc_metric_sd_l2.restype = C.c_double
+        L.orc_metric_sd_l2.argtypes = [C.c_int64, c_i32p, c_f64p, c_f64p, C.c_int64]
         L.orc_forest_free.argtypes = [C.c_void_p]
         L.orc_tree_export.restype = C.c_int64
         L.orc_tree_export.argtypes = [C.c_void_p, C.c_int32, c_i64p, c_i32p, c_f64p, c_f64p, c_f64p, c_i64p, c_i64p, c_u32p]
@@ -218,6 +231,71 @@ class Forest:
     def recall(self, q, k):
         q = np.ascontiguousarray(q, np.float64)
         return lib().orc_recall(self.h, _p(q, c_f64p), k)
+
+
+def _sv(idx, val):
+    ii = np.ascontiguousarray(idx if len(idx) else np.zeros(1), np.int32)
+    vv = np.ascontiguousarray(val if len(val) else np.zeros(1), np.float64)
+    return len(idx), ii, vv
+
+
+def metric_ss_l2(i1, v1, i2, v2):
+    n1, a, b = _sv(i1, v1); n2, c, d = _sv(i2, v2)
+    return lib().orc_metric_ss_l2(n1, _p(a, c_i32p), _p(b, c_f64p), n2, _p(c, c_i32p), _p(d, c_f64p))
+
+
+def metric_sd_l2(idx, val, x):
+    n1, a, b = _sv(idx, val)
+    x = np.ascontiguousarray(x, np.float64)
+    return lib().orc_metric_sd_l2(n1, _p(a, c_i32p), _p(b, c_f64p), _p(x, c_f64p), len(x))
+
+
+class SparseForest(Forest):
+    """Oracle forest over SVector data points: csr = (off int64[n+1], idx int32, val float64), indices ascending per
+    row.  Queries: a dense vector (metricSDL2) or an (idx, val) pair (metricSSL2)."""
+
+    def __init__(self, csr, d, hp, T, maxd, minl, chunk=None):
+        off, idx, val = csr
+        self.sp_off = np.ascontiguousarray(off, np.int64)
+        self.sp_idx = np.ascontiguousarray(idx if len(idx) else np.zeros(1), np.int32)
+        self.sp_val = np.ascontiguousarray(val if len(val) else np.zeros(1), np.float64)
+        self.n, self.d = len(off) - 1, d
+        hoff, hidx, hval = hp
+        self.off = np.ascontiguousarray(hoff, np.int64)
+        self.idx = np.ascontiguousarray(hidx if len(hidx) else np.zeros(1), np.int32)
+        self.val = np.ascontiguousarray(hval if len(hval) else np.zeros(1), np.float64)
+        self.T, self.maxd, self.minl = T, maxd, minl
+        self.h = lib().orc_forest_new_sparse(self.n, d, _p(self.sp_off, c_i64p), _p(self.sp_idx, c_i32p), _p(self.sp_val, c_f64p),
+                                             T, maxd, minl, chunk if chunk else 0,
+                                             _p(self.off, c_i64p), _p(self.idx, c_i32p), _p(self.val, c_f64p))
+
+    @staticmethod
+    def _is_sparse(q):
+        return isinstance(q, tuple)
+
+    def candidates(self, t, q):
+        if not self._is_sparse(q):
+            return Forest.candidates(self, t, q)
+        nz, ii, vv = _sv(*q)
+        L = lib()
+        c = L.orc_candidates_sq(self.h, t, nz, _p(ii, c_i32p), _p(vv, c_f64p), None, 0)
+        ids = np.zeros(max(c, 1), np.uint32)
+        L.orc_candidates_sq(self.h, t, nz, _p(ii, c_i32p), _p(vv, c_f64p), _p(ids, c_u32p), c)
+        return ids[:c]
+
+    def knn(self, q, k, dedup=False):
+        if not self._is_sparse(q):
+            return Forest.knn(self, q, k, dedup)
+        nz, ii, vv = _sv(*q)
+        dist = np.zeros(k); ids = np.zeros(k, np.uint32)
+        m = lib().orc_knn_sq(self.h, nz, _p(ii, c_i32p), _p(vv, c_f64p), k, int(dedup), _p(dist, c_f64p), _p(ids, c_u32p))
+        return dist[:m], ids[:m]
+
+    def recall(self, q, k):
+        if not self._is_sparse(q):
+            return Forest.recall(self, q, k)
+        nz, ii, vv = _sv(*q)
+        return lib().orc_recall_sq(self.h, nz, _p(ii, c_i32p), _p(vv, c_f64p), k)
 
 
 def brute_knn(X, q, k):

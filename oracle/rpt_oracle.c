@@ -147,6 +147,22 @@ double orc_metric_dd_l2(const double* u, const double* v, int64_t d) {
     return sqrt(acc);
 }
 
+/* metricSSL2, Internal.hs:389-393: sqrt $ VG.sum $ VG.map (\(_, x) -> x ** 2) (u `diffSS` v) with
+ * diffSS = binSS (-) 0 (Internal.hs:432-453): a merge join that STOPS when either operand is exhausted, so the
+ * components of the longer-lasting vector beyond the other's last index are dropped (the reference's quirk). */
+double orc_metric_ss_l2(int64_t nz1, const int32_t* i1, const double* v1, int64_t nz2, const int32_t* i2, const double* v2) {
+    int64_t a = 0, b = 0;
+    double acc = 0.0;
+    while (a < nz1 && b < nz2) {
+        double df;
+        if (i1[a] == i2[b])     { df = v1[a] - v2[b]; ++a; ++b; }
+        else if (i1[a] < i2[b]) { df = v1[a] - 0.0; ++a; }
+        else                    { df = 0.0 - v2[b]; ++b; }
+        acc = acc + (g_use_pow ? pow(df, 2.0) : df * df);
+    }
+    return sqrt(acc);
+}
+
 /* binSDD, Internal.hs:455-470 -- note the quirk: stops when EITHER operand is exhausted. */
 static int64_t bin_sdd(int sub, int64_t nz, const int32_t* idx, const double* val, const double* x, int64_t d, double* out) {
     int64_t i1 = 0, i2 = 0, m = 0;
@@ -161,6 +177,16 @@ static int64_t bin_sdd(int sub, int64_t nz, const int32_t* idx, const double* va
 }
 int64_t orc_sum_sd (int64_t nz, const int32_t* idx, const double* val, const double* x, int64_t d, double* out) { return bin_sdd(0, nz, idx, val, x, d, out); }
 int64_t orc_diff_sd(int64_t nz, const int32_t* idx, const double* val, const double* x, int64_t d, double* out) { return bin_sdd(1, nz, idx, val, x, d, out); }
+/* metricSDL2, Internal.hs:396-400: sqrt $ VG.sum $ VG.map (** 2) (u `diffSD` v): the dense operand is only
+ * visited up to the sparse operand's last index (binSDD stops when the sparse side is exhausted). */
+double orc_metric_sd_l2(int64_t nz, const int32_t* idx, const double* val, const double* x, int64_t d) {
+    double* tmp = (double*)malloc(sizeof(double) * (size_t)(nz + d + 1));
+    int64_t m = bin_sdd(1, nz, idx, val, x, d, tmp);
+    double acc = 0.0;
+    for (int64_t i = 0; i < m; ++i) acc = acc + (g_use_pow ? pow(tmp[i], 2.0) : tmp[i] * tmp[i]);
+    free(tmp);
+    return sqrt(acc);
+}
 
 /* rpTreeCfg, Conduit.hs:132-141 */
 void orc_rptree_cfg(int64_t minl, int64_t n, int64_t d, int64_t* maxd, int64_t* nchunk, double* pnz) {
@@ -207,6 +233,7 @@ typedef struct onode {
 
 struct orc_forest {
     const double* X; int64_t n; int32_t d; int32_t T, maxd, minl;
+    const int64_t* sp_off; const int32_t* sp_idx; const double* sp_val;   /* data points as SVectors (CSR) when X == NULL */
     int64_t* hp_off; int32_t* hp_idx; double* hp_val;
     onode** roots;
 };
@@ -225,6 +252,29 @@ static void node_free(onode* t) {
 }
 
 typedef struct { uint32_t id; double key; } pk;
+
+/* a query point: DVector (dense != NULL) or SVector (nz, idx, val) */
+typedef struct { const double* dense; int64_t nz; const int32_t* idx; const double* val; } qref;
+
+/* r `inner` x for a data point: innerSD (dense data) or innerSS (sparse data) -- instances Internal.hs:322-341 */
+static double point_proj(const orc_forest* f, int64_t hp, uint32_t id) {
+    int64_t s = f->hp_off[hp], e = f->hp_off[hp + 1];
+    if (f->X) return orc_inner_sd(e - s, f->hp_idx + s, f->hp_val + s, f->X + (int64_t)id * f->d, f->d);
+    int64_t a = f->sp_off[id], b = f->sp_off[id + 1];
+    return orc_inner_ss(e - s, f->hp_idx + s, f->hp_val + s, b - a, f->sp_idx + a, f->sp_val + a);
+}
+static double query_proj(const orc_forest* f, int64_t hp, const qref* q) {
+    int64_t s = f->hp_off[hp], e = f->hp_off[hp + 1];
+    if (q->dense) return orc_inner_sd(e - s, f->hp_idx + s, f->hp_val + s, q->dense, f->d);
+    return orc_inner_ss(e - s, f->hp_idx + s, f->hp_val + s, q->nz, q->idx, q->val);
+}
+/* eEmbed xe `metricL2` q: metricDDL2 / metricSDL2 / metricSSL2 by the operand types (Internal.hs:322-341) */
+static double point_dist(const orc_forest* f, uint32_t id, const qref* q) {
+    if (f->X) return orc_metric_dd_l2(f->X + (int64_t)id * f->d, q->dense, f->d);
+    int64_t a = f->sp_off[id], b = f->sp_off[id + 1];
+    if (q->dense) return orc_metric_sd_l2(b - a, f->sp_idx + a, f->sp_val + a, q->dense, f->d);
+    return orc_metric_ss_l2(b - a, f->sp_idx + a, f->sp_val + a, q->nz, q->idx, q->val);
+}
 
 /* Ord Double compare as GHC defines it: LT if a<b, EQ if a==b, else GT (so NaN -> GT). */
 static int cmp_double(double a, double b) { return a < b ? -1 : (a == b ? 0 : 1); }
@@ -248,12 +298,11 @@ static void msort(pk* a, pk* tmp, int64_t n) {
 static int partition_at_median(const orc_forest* f, int64_t hp, uint32_t* ids, int64_t n,
                                double* thr, double* mlo, double* mhi, int64_t* nh_out) {
     if (n < 1) return 0;
-    int64_t s = f->hp_off[hp], e = f->hp_off[hp + 1];
     pk* a = (pk*)malloc(sizeof(pk) * (size_t)n);
     pk* tmp = (pk*)malloc(sizeof(pk) * (size_t)n);
     for (int64_t i = 0; i < n; ++i) {
         a[i].id = ids[i];
-        a[i].key = orc_inner_sd(e - s, f->hp_idx + s, f->hp_val + s, f->X + (int64_t)ids[i] * f->d, f->d);
+        a[i].key = point_proj(f, hp, ids[i]);
     }
     msort(a, tmp, n);
     int64_t nh = n / 2;
@@ -337,6 +386,35 @@ orc_forest* orc_forest_new_chunked(const double* X, int64_t n, int32_t d, int32_
     free(ids);
     return f;
 }
+/* forest over SVector data points (Embed SVector Double x): CSR rows with ascending indices; borrowed pointers */
+orc_forest* orc_forest_new_sparse(int64_t n, int32_t d, const int64_t* sp_off, const int32_t* sp_idx, const double* sp_val,
+                                  int32_t T, int32_t maxd, int32_t minl, int64_t chunk,
+                                  const int64_t* hp_off, const int32_t* hp_idx, const double* hp_val) {
+    /* build through the common path: X == NULL switches point_proj / point_dist to the sparse instances */
+    orc_forest* f = (orc_forest*)calloc(1, sizeof(orc_forest));
+    f->X = NULL; f->sp_off = sp_off; f->sp_idx = sp_idx; f->sp_val = sp_val;
+    f->n = n; f->d = d; f->T = T; f->maxd = maxd; f->minl = minl;
+    int64_t nhp = (int64_t)T * maxd, nnz = hp_off[nhp];
+    f->hp_off = (int64_t*)malloc(sizeof(int64_t) * (size_t)(nhp + 1));
+    memcpy(f->hp_off, hp_off, sizeof(int64_t) * (size_t)(nhp + 1));
+    f->hp_idx = (int32_t*)malloc(sizeof(int32_t) * (size_t)(nnz > 0 ? nnz : 1));
+    f->hp_val = (double*)malloc(sizeof(double) * (size_t)(nnz > 0 ? nnz : 1));
+    if (nnz > 0) { memcpy(f->hp_idx, hp_idx, sizeof(int32_t) * (size_t)nnz); memcpy(f->hp_val, hp_val, sizeof(double) * (size_t)nnz); }
+    f->roots = (onode**)calloc((size_t)T, sizeof(onode*));
+    if (chunk < 1) chunk = n > 0 ? n : 1;
+    uint32_t* ids = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)(n > 0 ? n : 1));
+    for (int64_t i = 0; i < n; ++i) ids[i] = (uint32_t)i;
+    for (int32_t t = 0; t < T; ++t) {
+        onode* tt = tip_new(NULL, 0);
+        for (int64_t s = 0; s < n; s += chunk) {
+            int64_t m = n - s < chunk ? n - s : chunk;
+            tt = insert_loop(f, t, 0, tt, ids + s, m);
+        }
+        f->roots[t] = tt;
+    }
+    free(ids);
+    return f;
+}
 orc_forest* orc_forest_new(const double* X, int64_t n, int32_t d, int32_t T, int32_t maxd, int32_t minl,
                            const int64_t* hp_off, const int32_t* hp_idx, const double* hp_val) {
     return orc_forest_new_chunked(X, n, d, T, maxd, minl, n > 0 ? n : 1, hp_off, hp_idx, hp_val);
@@ -385,17 +463,17 @@ static void idbuf_push(idbuf* b, const uint32_t* ids, int64_t n) {
     }
     b->n += n;
 }
-static void cand_go(const orc_forest* f, int32_t tree, int32_t lev, const onode* tt, const double* x, idbuf* out) {
+static void cand_go(const orc_forest* f, int32_t tree, int32_t lev, const onode* tt, const qref* x, idbuf* out) {
     if (!tt->is_bin) { idbuf_push(out, tt->ids, tt->n); return; }
-    int64_t hp = (int64_t)tree * f->maxd + lev, s = f->hp_off[hp], e = f->hp_off[hp + 1];
-    double proj = orc_inner_sd(e - s, f->hp_idx + s, f->hp_val + s, x, f->d);
+    int64_t hp = (int64_t)tree * f->maxd + lev;
+    double proj = query_proj(f, hp, x);
     double dl = fabs(tt->mlo - proj), dr = fabs(tt->mhi - proj);
     if (proj < tt->thr && dl > dr)      { cand_go(f, tree, lev + 1, tt->l, x, out); cand_go(f, tree, lev + 1, tt->r, x, out); }
     else if (proj < tt->thr)            { cand_go(f, tree, lev + 1, tt->l, x, out); }
     else if (proj > tt->thr && dl < dr) { cand_go(f, tree, lev + 1, tt->l, x, out); cand_go(f, tree, lev + 1, tt->r, x, out); }
     else                                { cand_go(f, tree, lev + 1, tt->r, x, out); }
 }
-int64_t orc_candidates(const orc_forest* f, int32_t t, const double* q, uint32_t* ids, int64_t cap) {
+static int64_t candidates_q(const orc_forest* f, int32_t t, const qref* q, uint32_t* ids, int64_t cap) {
     idbuf b = {0};
     b.count_only = (ids == NULL);
     cand_go(f, t, 0, f->roots[t], q, &b);
@@ -407,7 +485,16 @@ int64_t orc_candidates(const orc_forest* f, int32_t t, const double* q, uint32_t
  * stable sort by distance, take k.  dedup=1: knnPQ/nub semantics -- one entry per distinct DISTANCE
  * (heaps' Entry compares on priority only, RPTree.hs:187-194,224-227); the survivor of a group is
  * unpinned in the reference (heap internals), here: first in candidate order. */
-int64_t orc_knn(const orc_forest* f, const double* q, int32_t k, int32_t dedup, double* dist, uint32_t* ids) {
+int64_t orc_candidates(const orc_forest* f, int32_t t, const double* q, uint32_t* ids, int64_t cap) {
+    qref r = {q, 0, NULL, NULL};
+    return candidates_q(f, t, &r, ids, cap);
+}
+int64_t orc_candidates_sq(const orc_forest* f, int32_t t, int64_t qnz, const int32_t* qidx, const double* qval, uint32_t* ids, int64_t cap) {
+    qref r = {NULL, qnz, qidx, qval};
+    return candidates_q(f, t, &r, ids, cap);
+}
+
+static int64_t knn_q(const orc_forest* f, const qref* q, int32_t k, int32_t dedup, double* dist, uint32_t* ids) {
     idbuf b = {0};
     for (int32_t t = 0; t < f->T; ++t) cand_go(f, t, 0, f->roots[t], q, &b);
     int64_t c = b.n;
@@ -415,7 +502,7 @@ int64_t orc_knn(const orc_forest* f, const double* q, int32_t k, int32_t dedup, 
     pk* tmp = (pk*)malloc(sizeof(pk) * (size_t)(c > 0 ? c : 1));
     for (int64_t i = 0; i < c; ++i) {
         a[i].id = b.ids[i];
-        a[i].key = orc_metric_dd_l2(f->X + (int64_t)b.ids[i] * f->d, q, f->d);
+        a[i].key = point_dist(f, b.ids[i], q);
     }
     msort(a, tmp, c);
     int64_t m = 0;
@@ -427,12 +514,21 @@ int64_t orc_knn(const orc_forest* f, const double* q, int32_t k, int32_t dedup, 
     return m;
 }
 
+int64_t orc_knn(const orc_forest* f, const double* q, int32_t k, int32_t dedup, double* dist, uint32_t* ids) {
+    qref r = {q, 0, NULL, NULL};
+    return knn_q(f, &r, k, dedup, dist, ids);
+}
+int64_t orc_knn_sq(const orc_forest* f, int64_t qnz, const int32_t* qidx, const double* qval, int32_t k, int32_t dedup, double* dist, uint32_t* ids) {
+    qref r = {NULL, qnz, qidx, qval};
+    return knn_q(f, &r, k, dedup, dist, ids);
+}
+
 static int cmp_u32(const void* a, const void* b) { uint32_t x = *(const uint32_t*)a, y = *(const uint32_t*)b; return x < y ? -1 : x > y; }
 
 /* recallWith / recallWith1, RPTree.hs:265-282.  `points tt` = leaves left to right; Data.List.sortBy is
  * a stable merge sort.  Sets are over row ids here (the reference's Set is over Embed values, which
  * collapses exact duplicate vectors carrying equal payloads). */
-double orc_recall(const orc_forest* f, const double* q, int32_t k) {
+static double recall_q(const orc_forest* f, const qref* q, int32_t k) {
     double sum = 0.0;
     pk* a = (pk*)malloc(sizeof(pk) * (size_t)(f->n > 0 ? f->n : 1));
     pk* tmp = (pk*)malloc(sizeof(pk) * (size_t)(f->n > 0 ? f->n : 1));
@@ -448,7 +544,7 @@ double orc_recall(const orc_forest* f, const double* q, int32_t k) {
         }
         orc_tree_export(f, t, child, depth, thr, mlo, mhi, ss, sz, perm);
         int64_t np = count_points(f->roots[t]);
-        for (int64_t i = 0; i < np; ++i) { a[i].id = perm[i]; a[i].key = orc_metric_dd_l2(f->X + (int64_t)perm[i] * f->d, q, f->d); }
+        for (int64_t i = 0; i < np; ++i) { a[i].id = perm[i]; a[i].key = point_dist(f, perm[i], q); }
         msort(a, tmp, np);
         int64_t kk = np < k ? np : k;
         uint32_t* top = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)(kk > 0 ? kk : 1));
@@ -469,6 +565,15 @@ double orc_recall(const orc_forest* f, const double* q, int32_t k) {
     }
     free(a); free(tmp); free(child); free(depth); free(thr); free(mlo); free(mhi); free(ss); free(sz); free(perm);
     return sum / (double)f->T;
+}
+
+double orc_recall(const orc_forest* f, const double* q, int32_t k) {
+    qref r = {q, 0, NULL, NULL};
+    return recall_q(f, &r, k);
+}
+double orc_recall_sq(const orc_forest* f, int64_t qnz, const int32_t* qidx, const double* qval, int32_t k) {
+    qref r = {NULL, qnz, qidx, qval};
+    return recall_q(f, &r, k);
 }
 
 void orc_brute_knn(const double* X, int64_t n, int32_t d, const double* q, int32_t k, double* dist, uint32_t* ids) {

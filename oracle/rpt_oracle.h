@@ -40,6 +40,9 @@ double orc_inner_ss(int64_t nz1, const int32_t* i1, const double* v1,
                     int64_t nz2, const int32_t* i2, const double* v2);                            /* :351-366 */
 double orc_inner_dd(const double* u, const double* v, int64_t d);                                  /* :384-385 */
 double orc_metric_dd_l2(const double* u, const double* v, int64_t d);                              /* :403-406 */
+double orc_metric_ss_l2(int64_t nz1, const int32_t* i1, const double* v1,
+                        int64_t nz2, const int32_t* i2, const double* v2);                        /* :389-393 */
+double orc_metric_sd_l2(int64_t nz, const int32_t* idx, const double* val, const double* x, int64_t d); /* :396-400 */
 /* binSDD (+)/(-) with the "stop when either operand is exhausted" quirk, :455-470.  Returns length. */
 int64_t orc_sum_sd (int64_t nz, const int32_t* idx, const double* val, const double* x, int64_t d, double* out);
 int64_t orc_diff_sd(int64_t nz, const int32_t* idx, const double* val, const double* x, int64_t d, double* out);
@@ -61,6 +64,11 @@ orc_forest* orc_forest_new(const double* X, int64_t n, int32_t d, int32_t T, int
 orc_forest* orc_forest_new_chunked(const double* X, int64_t n, int32_t d, int32_t T, int32_t maxd, int32_t minl,
                                    int64_t chunk,
                                    const int64_t* hp_off, const int32_t* hp_idx, const double* hp_val);
+/* same over SVector data points (CSR, ascending indices; pointers are borrowed): projections by innerSS
+ * (Internal.hs:351-366), distances by metricSDL2 (dense query) / metricSSL2 (sparse query). chunk < 1 == batch */
+orc_forest* orc_forest_new_sparse(int64_t n, int32_t d, const int64_t* sp_off, const int32_t* sp_idx, const double* sp_val,
+                                  int32_t T, int32_t maxd, int32_t minl, int64_t chunk,
+                                  const int64_t* hp_off, const int32_t* hp_idx, const double* hp_val);
 void orc_forest_free(orc_forest* f);
 
 /* Canonical flat export of tree t: nodes in BFS (level-major, left-to-right) order.
@@ -76,6 +84,10 @@ int64_t orc_candidates(const orc_forest* f, int32_t t, const double* q, uint32_t
 /* knn (RPTree.hs:174-176) dedup=0; knnPQ-like (RPTree.hs:187-194,224-227: dedup by distance equality,
  * first in candidate order kept) dedup=1.  Returns the number of results (<= k). */
 int64_t orc_knn(const orc_forest* f, const double* q, int32_t k, int32_t dedup, double* dist, uint32_t* ids);
+/* the same three with an SVector query (nz, idx, val) */
+int64_t orc_candidates_sq(const orc_forest* f, int32_t t, int64_t qnz, const int32_t* qidx, const double* qval, uint32_t* ids, int64_t cap);
+int64_t orc_knn_sq(const orc_forest* f, int64_t qnz, const int32_t* qidx, const double* qval, int32_t k, int32_t dedup, double* dist, uint32_t* ids);
+double  orc_recall_sq(const orc_forest* f, int64_t qnz, const int32_t* qidx, const double* qval, int32_t k);
 /* recallWith (RPTree.hs:265-282): mean over trees of |cands(t) n topk| / k; point identity = row id. */
 double  orc_recall(const orc_forest* f, const double* q, int32_t k);
 /* exact brute-force k nearest (stable by row id) -- used for forest-level recall */

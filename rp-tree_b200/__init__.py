@@ -6,12 +6,12 @@ plus tree-sharded multi-GPU plumbing (dist.py).  The directory name has a hyphen
 `rp_tree_b200` (see the shim rp_tree_b200.py at the repo root).
 """
 from ._lib import RPForestError, lib, SO_PATH, SIGNATURES
-from .api import (RPForest, RPTreeConfig, metricL2, rpTreeCfg, sampleHyperplanes, topologyPlan, slice_hyperplanes,
+from .api import (RPForest, SparseRows, RPTreeConfig, metricL2, rpTreeCfg, sampleHyperplanes, topologyPlan, slice_hyperplanes,
                   forestBatch, treeBatch, forest, tree, knn, knnPQ, candidates, recallWith, levels, leafSizes,
                   treeSize, points)
 from . import _build
 from . import dist
 
-__all__ = ["RPForest", "RPForestError", "RPTreeConfig", "metricL2", "rpTreeCfg", "sampleHyperplanes", "topologyPlan",
+__all__ = ["RPForest", "SparseRows", "RPForestError", "RPTreeConfig", "metricL2", "rpTreeCfg", "sampleHyperplanes", "topologyPlan",
            "slice_hyperplanes", "forestBatch", "treeBatch", "forest", "tree", "knn", "knnPQ", "candidates", "recallWith",
            "levels", "leafSizes", "treeSize", "points", "lib", "SO_PATH", "SIGNATURES"]

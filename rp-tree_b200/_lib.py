@@ -24,6 +24,12 @@ SIGNATURES = {
     "rpf_abi_version": (C.c_int, []),
     "rpf_set_points": (C.c_int, [H, f64p, C.c_int64, C.c_int32]),
     "rpf_set_points_device": (C.c_int, [H, C.c_void_p, C.c_int64, C.c_int32]),
+    "rpf_set_points_sparse": (C.c_int, [H, C.c_int64, C.c_int32, i64p, i32p, f64p]),
+    "rpf_points_are_sparse": (C.c_int, [H]),
+    "rpf_densify_rows": (C.c_int, [C.c_int64, C.c_int32, i64p, i32p, f64p, f64p, i32p]),
+    "rpf_knn_s": (C.c_int, [H, f64p, i32p, C.c_int64, C.c_int32, C.c_int32, f64p, u32p, i32p]),
+    "rpf_recall_s": (C.c_int, [H, f64p, i32p, C.c_int64, C.c_int32, f64p]),
+    "rpf_brute_knn_s": (C.c_int, [H, f64p, i32p, C.c_int64, C.c_int32, f64p, u32p]),
     "rpf_set_hyperplanes": (C.c_int, [H, C.c_int32, C.c_int32, i64p, i32p, f64p]),
     "rpf_gen_hyperplanes": (C.c_int, [H, C.c_uint64, C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_int32, C.c_int32]),
     "rpf_hyperplane_nnz": (C.c_int64, [H]),

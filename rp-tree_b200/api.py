@@ -37,7 +37,47 @@ def _p(a, t):
     return a.ctypes.data_as(t)
 
 
+class SparseRows:
+    """A batch of SVectors (Internal.hs:92-97) as CSR rows: off int64[n+1], idx int32 (strictly ascending per row), val."""
+
+    def __init__(self, off, idx, val, d):
+        self.off = np.ascontiguousarray(off, np.int64)
+        self.idx = np.ascontiguousarray(idx if len(idx) else np.zeros(1), np.int32)
+        self.val = np.ascontiguousarray(val if len(val) else np.zeros(1), np.float64)
+        self.n, self.d = len(self.off) - 1, int(d)
+
+    @classmethod
+    def fromDense(cls, M):
+        """fromListSv-style: keep the nonzero components of every row of M."""
+        M = np.asarray(M, np.float64)
+        if M.ndim == 1:
+            M = M[None, :]
+        r, c = np.nonzero(M)
+        off = np.zeros(M.shape[0] + 1, np.int64)
+        np.add.at(off, r + 1, 1)
+        return cls(np.cumsum(off), c.astype(np.int32), M[r, c], M.shape[1])
+
+    def densify(self):
+        """(dense n x d image, last stored component per row) through the library's host helper."""
+        Q = np.zeros((self.n, self.d)); last = np.zeros(max(self.n, 1), np.int32)
+        rc = lib().rpf_densify_rows(self.n, self.d, _p(self.off, i64p), _p(self.idx, i32p), _p(self.val, f64p), _p(Q, f64p), _p(last, i32p))
+        if rc != 0:
+            raise RPForestError("rpf_densify_rows: malformed CSR rows (rc=%d)" % rc)
+        return Q, last[: self.n]
+
+
 def _as_q(q, d):
+    """-> (dense image nq x d, single?, q_last or None)"""
+    if isinstance(q, SparseRows):
+        if q.d != d:
+            raise ValueError("query must have dimension %d" % d)
+        Q, last = q.densify()
+        return Q, False, last
+    Q, single = _as_qd(q, d)
+    return Q, single, None
+
+
+def _as_qd(q, d):
     Q = np.ascontiguousarray(q, dtype=np.float64)
     single = Q.ndim == 1
     if single:
@@ -138,6 +178,15 @@ class RPForest:
         self._ck(self._L.rpf_set_points(self._h, _p(X, f64p), X.shape[0], X.shape[1]), "rpf_set_points")
         self.n, self.d = X.shape
 
+    def setPointsSparse(self, rows):
+        """Data points as SVectors (Embed SVector Double x): rows is a SparseRows."""
+        self._ck(self._L.rpf_set_points_sparse(self._h, rows.n, rows.d, _p(rows.off, i64p), _p(rows.idx, i32p), _p(rows.val, f64p)),
+                 "rpf_set_points_sparse")
+        self.n, self.d = rows.n, rows.d
+
+    def pointsAreSparse(self):
+        return bool(self._L.rpf_points_are_sparse(self._h))
+
     def setPointsDevice(self, ptr, n, d):
         self._ck(self._L.rpf_set_points_device(self._h, C.c_void_p(ptr), n, d), "rpf_set_points_device")
         self.n, self.d = n, d
@@ -217,7 +266,7 @@ class RPForest:
 
     # -- queries (batched: Q is nq x d)
     def candidatesBatch(self, Q, t=-1):
-        Q, _ = _as_q(Q, self.d)
+        Q, _, _ = _as_q(Q, self.d)
         nq = Q.shape[0]
         off = np.zeros(nq + 1, np.int64)
         self._ck(self._L.rpf_candidates_count(self._h, _p(Q, f64p), nq, t, _p(off, i64p)), "rpf_candidates_count")
@@ -226,24 +275,33 @@ class RPForest:
         return off, ids[: off[-1]]
 
     def knnBatch(self, Q, k, dedup=False):
-        Q, _ = _as_q(Q, self.d)
+        Q, _, ql = _as_q(Q, self.d)
         nq = Q.shape[0]
         dist = np.zeros((nq, k)); ids = np.zeros((nq, k), np.uint32); cnt = np.zeros(nq, np.int32)
-        self._ck(self._L.rpf_knn(self._h, _p(Q, f64p), nq, k, int(dedup), _p(dist, f64p), _p(ids, u32p), _p(cnt, i32p)), "rpf_knn")
+        if ql is None:
+            self._ck(self._L.rpf_knn(self._h, _p(Q, f64p), nq, k, int(dedup), _p(dist, f64p), _p(ids, u32p), _p(cnt, i32p)), "rpf_knn")
+        else:
+            self._ck(self._L.rpf_knn_s(self._h, _p(Q, f64p), _p(ql, i32p), nq, k, int(dedup), _p(dist, f64p), _p(ids, u32p), _p(cnt, i32p)), "rpf_knn_s")
         return dist, ids, cnt
 
     def recallSumBatch(self, Q, k):
-        Q, _ = _as_q(Q, self.d)
+        Q, _, ql = _as_q(Q, self.d)
         nq = Q.shape[0]
         r = np.zeros(nq)
-        self._ck(self._L.rpf_recall(self._h, _p(Q, f64p), nq, k, _p(r, f64p)), "rpf_recall")
+        if ql is None:
+            self._ck(self._L.rpf_recall(self._h, _p(Q, f64p), nq, k, _p(r, f64p)), "rpf_recall")
+        else:
+            self._ck(self._L.rpf_recall_s(self._h, _p(Q, f64p), _p(ql, i32p), nq, k, _p(r, f64p)), "rpf_recall_s")
         return r
 
     def bruteKnnBatch(self, Q, k):
-        Q, _ = _as_q(Q, self.d)
+        Q, _, ql = _as_q(Q, self.d)
         nq = Q.shape[0]
         dist = np.zeros((nq, k)); ids = np.zeros((nq, k), np.uint32)
-        self._ck(self._L.rpf_brute_knn(self._h, _p(Q, f64p), nq, k, _p(dist, f64p), _p(ids, u32p)), "rpf_brute_knn")
+        if ql is None:
+            self._ck(self._L.rpf_brute_knn(self._h, _p(Q, f64p), nq, k, _p(dist, f64p), _p(ids, u32p)), "rpf_brute_knn")
+        else:
+            self._ck(self._L.rpf_brute_knn_s(self._h, _p(Q, f64p), _p(ql, i32p), nq, k, _p(dist, f64p), _p(ids, u32p)), "rpf_brute_knn_s")
         return dist, ids
 
     def mergeTopk(self, dist, ids, cnt, dedup=False):
@@ -281,19 +339,29 @@ class RPForest:
 # ---------------------------------------------------------------------------------------------------------
 # the reference's function names
 # ---------------------------------------------------------------------------------------------------------
-def forestBatch(seed, maxd, minl, ntrees, pnz, dim, xs, *, hyperplanes=None, device=0, t_first=0, t_local=None, bottom_cap=None, options=None):
-    """forestBatch (Batch.hs:48-63).  `hyperplanes` = CSR (off, idx, val) drawn by the Haskell host overrides the
-    built-in sampler (bit-exact parity path).  t_first/t_local shard the trees for multi-GPU runs."""
+def _set_points(f, xs, dim):
+    if isinstance(xs, SparseRows):
+        if xs.d != dim:
+            raise ValueError("dataset must have dimension %d" % dim)
+        f.setPointsSparse(xs)
+        return
     xs = np.ascontiguousarray(xs, dtype=np.float64)
     if xs.ndim != 2 or xs.shape[1] != dim:
         raise ValueError("dataset must be n x %d" % dim)
+    f.setPoints(xs)
+
+
+def forestBatch(seed, maxd, minl, ntrees, pnz, dim, xs, *, hyperplanes=None, device=0, t_first=0, t_local=None, bottom_cap=None, options=None):
+    """forestBatch (Batch.hs:48-63).  `hyperplanes` = CSR (off, idx, val) drawn by the Haskell host overrides the
+    built-in sampler (bit-exact parity path).  t_first/t_local shard the trees for multi-GPU runs.
+    xs: n x dim float64 matrix (DVector points) or SparseRows (SVector points)."""
     t_local = ntrees - t_first if t_local is None else t_local
     f = RPForest(device)
     if bottom_cap is not None:
         f.setBottomCap(bottom_cap)
     for name, value in (options or {}).items():
         f.setOption(name, value)
-    f.setPoints(xs)
+    _set_points(f, xs, dim)
     if hyperplanes is not None:
         hp = hyperplanes if (t_first == 0 and t_local == ntrees) else slice_hyperplanes(hyperplanes, maxd, t_first, t_local)
         f.setHyperplanes(hp, t_local, maxd)
@@ -313,16 +381,13 @@ def forest(seed, maxd, minl, ntrees, chunksize, pnz, dim, xs, *, hyperplanes=Non
            bottom_cap=None, options=None):
     """forest (Conduit.hs:104-121): the rows of xs arrive in chunks of `chunksize` (the conduit's `chunksOf`), each chunk
     updates every tree (insertMulti, Internal.hs:243-255).  chunksize >= n is forestBatch."""
-    xs = np.ascontiguousarray(xs, dtype=np.float64)
-    if xs.ndim != 2 or xs.shape[1] != dim:
-        raise ValueError("dataset must be n x %d" % dim)
     t_local = ntrees - t_first if t_local is None else t_local
     f = RPForest(device)
     if bottom_cap is not None:
         f.setBottomCap(bottom_cap)
     for name, value in (options or {}).items():
         f.setOption(name, value)
-    f.setPoints(xs)
+    _set_points(f, xs, dim)
     if hyperplanes is not None:
         hp = hyperplanes if (t_first == 0 and t_local == ntrees) else slice_hyperplanes(hyperplanes, maxd, t_first, t_local)
         f.setHyperplanes(hp, t_local, maxd)
@@ -338,6 +403,14 @@ def tree(seed, maxd, minl, chunksize, pnz, dim, xs, **kw):
     return forest(seed, maxd, minl, 1, chunksize, pnz, dim, xs, **kw)
 
 
+def _q_for_call(q, d):
+    """One query vector / a batch (dense), or SparseRows (passed through): -> (queries, single?)"""
+    if isinstance(q, SparseRows):
+        return q, False
+    Q, single = _as_qd(q, d)
+    return Q, single
+
+
 def _need_l2(distf):
     if distf is not metricL2:
         raise RPForestError("only distf = metricL2 is implemented on the GPU path")
@@ -346,7 +419,7 @@ def _need_l2(distf):
 def knn(distf, k, tts, q):
     """knn (RPTree.hs:168-176): (distances, row ids) in increasing distance; duplicates across trees are kept."""
     _need_l2(distf)
-    Q, single = _as_q(q, tts.d)
+    Q, single = _q_for_call(q, tts.d)
     dist, ids, cnt = tts.knnBatch(Q, k, dedup=False)
     if single:
         return dist[0, : cnt[0]], ids[0, : cnt[0]]
@@ -356,7 +429,7 @@ def knn(distf, k, tts, q):
 def knnPQ(distf, k, tts, q):
     """knnPQ (RPTree.hs:181-194): one result per distinct distance."""
     _need_l2(distf)
-    Q, single = _as_q(q, tts.d)
+    Q, single = _q_for_call(q, tts.d)
     dist, ids, cnt = tts.knnBatch(Q, k, dedup=True)
     if single:
         return dist[0, : cnt[0]], ids[0, : cnt[0]]
@@ -365,7 +438,7 @@ def knnPQ(distf, k, tts, q):
 
 def candidates(tts, t, q):
     """candidates (RPTree.hs:293-314) of tree `t` of the forest for query q: row ids in the reference's order."""
-    Q, single = _as_q(q, tts.d)
+    Q, single = _q_for_call(q, tts.d)
     off, ids = tts.candidatesBatch(Q, t)
     if single:
         return ids
@@ -375,7 +448,7 @@ def candidates(tts, t, q):
 def recallWith(distf, tts, k, q):
     """recallWith (RPTree.hs:259-268): mean over the forest's trees of the per-tree candidate recall@k."""
     _need_l2(distf)
-    Q, single = _as_q(q, tts.d)
+    Q, single = _q_for_call(q, tts.d)
     r = tts.recallSumBatch(Q, k) / float(tts.ntrees)
     return float(r[0]) if single else r
 

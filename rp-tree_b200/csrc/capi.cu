@@ -281,6 +281,7 @@ void rpf_destroy(rpf_handle* h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     if (h->ownX && h->dX) cudaFree((void*)h->dX);
+    if (h->d_xlast) cudaFree(h->d_xlast);
     free_hp_dev(h); free_topo_dev(h); free_forest_dev(h);
     if (h->stream_plan && h->stream_plan_free) h->stream_plan_free(h->stream_plan);
     h->ws_free_all();
@@ -299,6 +300,7 @@ int rpf_set_points(rpf_handle* h, const double* X, int64_t n, int32_t d) {
     if (n < 0 || d < 1 || (n > 0 && !X)) return rpf_fail(h, RPF_ERR_ARG, "set_points: bad n/d/X");
     if (n >= (int64_t)1 << 31) return rpf_fail(h, RPF_ERR_UNSUPPORTED, "set_points: n must be < 2^31");
     RPF_SETDEV(h);
+    if (h->d_xlast) { cudaFree(h->d_xlast); h->d_xlast = nullptr; }
     double* p = nullptr;
     const size_t bytes = std::max<size_t>((size_t)n * d * 8, 16);
     if (h->ownX && h->dX && h->x_bytes == bytes) {
@@ -322,9 +324,89 @@ int rpf_set_points_device(rpf_handle* h, const double* X_dev, int64_t n, int32_t
     if (n < 0 || d < 1 || (n > 0 && !X_dev)) return rpf_fail(h, RPF_ERR_ARG, "set_points_device: bad n/d/X");
     if (n >= (int64_t)1 << 31) return rpf_fail(h, RPF_ERR_UNSUPPORTED, "set_points_device: n must be < 2^31");
     RPF_SETDEV(h);
+    if (h->d_xlast) { cudaFree(h->d_xlast); h->d_xlast = nullptr; }
     if (h->ownX && h->dX) cudaFree((void*)h->dX);
     free_forest_dev(h);
     h->dX = X_dev; h->ownX = false; h->n = n; h->d = d;
+    return RPF_OK;
+}
+
+// CSR rows -> dense n x d image (zero elsewhere) + last stored component per row
+__global__ void k_densify(const int64_t* __restrict__ off, const int32_t* __restrict__ idx, const double* __restrict__ val,
+                          int64_t n, int d, double* __restrict__ X, int32_t* __restrict__ xlast) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t a = off[i], b = off[i + 1];
+    for (int64_t q = a; q < b; ++q) X[i * d + idx[q]] = val[q];
+    xlast[i] = b > a ? idx[b - 1] : -1;
+}
+
+static int check_csr_rows(rpf_handle* h, int64_t n, int32_t d, const int64_t* off, const int32_t* idx, const char* what) {
+    if (off[0] != 0) return rpf_fail(h, RPF_ERR_ARG, std::string(what) + ": off[0] must be 0");
+    for (int64_t i = 0; i < n; ++i) {
+        if (off[i + 1] < off[i]) return rpf_fail(h, RPF_ERR_ARG, std::string(what) + ": offsets not monotone");
+        for (int64_t q = off[i]; q < off[i + 1]; ++q) {
+            if (idx[q] < 0 || idx[q] >= d) return rpf_fail(h, RPF_ERR_ARG, std::string(what) + ": component index out of range");
+            if (q > off[i] && idx[q] <= idx[q - 1]) return rpf_fail(h, RPF_ERR_ARG, std::string(what) + ": component indices must be strictly ascending per row");
+        }
+    }
+    return RPF_OK;
+}
+
+int rpf_set_points_sparse(rpf_handle* h, int64_t n, int32_t d, const int64_t* off, const int32_t* idx, const double* val) {
+    if (!h) return RPF_ERR_ARG;
+    if (n < 0 || d < 1 || !off || (off[n] > 0 && (!idx || !val))) return rpf_fail(h, RPF_ERR_ARG, "set_points_sparse: bad n/d/CSR");
+    if (n >= (int64_t)1 << 31) return rpf_fail(h, RPF_ERR_UNSUPPORTED, "set_points_sparse: n must be < 2^31");
+    int rc = check_csr_rows(h, n, d, off, idx, "set_points_sparse");
+    if (rc) return rc;
+    RPF_SETDEV(h);
+    if (h->d_xlast) { cudaFree(h->d_xlast); h->d_xlast = nullptr; }
+    if (h->ownX && h->dX) cudaFree((void*)h->dX);
+    h->dX = nullptr; h->ownX = false; h->x_bytes = 0;
+    free_forest_dev(h);
+    const int64_t nnz = off[n];
+    const size_t bytes = std::max<size_t>((size_t)n * d * 8, 16);
+    double* X = nullptr; int64_t* doff = nullptr; int32_t* didx = nullptr; double* dval = nullptr; int32_t* xl = nullptr;
+    cudaError_t e = cudaMalloc(&X, bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&xl, std::max<size_t>((size_t)n * 4, 16));
+    if (e == cudaSuccess) e = cudaMalloc(&doff, (size_t)(n + 1) * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&didx, std::max<size_t>((size_t)nnz * 4, 16));
+    if (e == cudaSuccess) e = cudaMalloc(&dval, std::max<size_t>((size_t)nnz * 8, 16));
+    if (e == cudaSuccess) e = cudaMemsetAsync(X, 0, bytes, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(doff, off, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess && nnz) e = cudaMemcpyAsync(didx, idx, (size_t)nnz * 4, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess && nnz) e = cudaMemcpyAsync(dval, val, (size_t)nnz * 8, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess && n > 0) {
+        k_densify<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(doff, didx, dval, n, d, X, xl);
+        ++h->launches;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (doff) cudaFree(doff);
+    if (didx) cudaFree(didx);
+    if (dval) cudaFree(dval);
+    if (e != cudaSuccess) {
+        if (X) cudaFree(X);
+        if (xl) cudaFree(xl);
+        return rpf_fail(h, e == cudaErrorMemoryAllocation ? RPF_ERR_NOMEM : RPF_ERR_CUDA, std::string("set_points_sparse: ") + cudaGetErrorString(e));
+    }
+    h->dX = X; h->ownX = true; h->x_bytes = bytes; h->n = n; h->d = d; h->d_xlast = xl;
+    return RPF_OK;
+}
+
+int rpf_points_are_sparse(const rpf_handle* h) { return h ? (h->d_xlast ? 1 : 0) : -1; }
+
+int rpf_densify_rows(int64_t nq, int32_t d, const int64_t* off, const int32_t* idx, const double* val, double* Q, int32_t* q_last) {
+    if (nq < 0 || d < 1 || !off || !Q) return RPF_ERR_ARG;
+    std::memset(Q, 0, (size_t)nq * d * 8);
+    for (int64_t i = 0; i < nq; ++i) {
+        if (off[i + 1] < off[i]) return RPF_ERR_ARG;
+        for (int64_t q = off[i]; q < off[i + 1]; ++q) {
+            if (idx[q] < 0 || idx[q] >= d || (q > off[i] && idx[q] <= idx[q - 1])) return RPF_ERR_ARG;
+            Q[i * d + idx[q]] = val[q];
+        }
+        if (q_last) q_last[i] = off[i + 1] > off[i] ? idx[off[i + 1] - 1] : -1;
+    }
     return RPF_OK;
 }
 
@@ -546,7 +628,18 @@ int rpf_knn(rpf_handle* h, const double* Q, int64_t nq, int32_t k, int32_t dedup
     if (nq < 0 || (nq > 0 && (!Q || !dist || !ids)) || k < 1 || k > 1024) return rpf_fail(h, RPF_ERR_ARG, "knn: bad arguments (1 <= k <= 1024)");
     RPF_SETDEV(h);
     h->call_begin();
-    int rc = rpf_knn_impl(h, Q, nq, k, dedup, dist, ids, count);
+    int rc = rpf_knn_impl(h, Q, nullptr, nq, k, dedup, dist, ids, count);
+    int rc2 = h->call_end();
+    return rc ? rc : rc2;
+}
+
+int rpf_knn_s(rpf_handle* h, const double* Q, const int32_t* q_last, int64_t nq, int32_t k, int32_t dedup, double* dist, uint32_t* ids, int32_t* count) {
+    if (!h) return RPF_ERR_ARG;
+    if (!h->built) return rpf_fail(h, RPF_ERR_STATE, "knn: forest not built");
+    if (nq < 0 || (nq > 0 && (!Q || !dist || !ids)) || k < 1 || k > 1024) return rpf_fail(h, RPF_ERR_ARG, "knn: bad arguments (1 <= k <= 1024)");
+    RPF_SETDEV(h);
+    h->call_begin();
+    int rc = rpf_knn_impl(h, Q, q_last, nq, k, dedup, dist, ids, count);
     int rc2 = h->call_end();
     return rc ? rc : rc2;
 }
@@ -557,7 +650,18 @@ int rpf_recall(rpf_handle* h, const double* Q, int64_t nq, int32_t k, double* re
     if (nq < 0 || (nq > 0 && (!Q || !recall_sum)) || k < 1 || k > 1024) return rpf_fail(h, RPF_ERR_ARG, "recall: bad arguments (1 <= k <= 1024)");
     RPF_SETDEV(h);
     h->call_begin();
-    int rc = rpf_recall_impl(h, Q, nq, k, recall_sum);
+    int rc = rpf_recall_impl(h, Q, nullptr, nq, k, recall_sum);
+    int rc2 = h->call_end();
+    return rc ? rc : rc2;
+}
+
+int rpf_recall_s(rpf_handle* h, const double* Q, const int32_t* q_last, int64_t nq, int32_t k, double* recall_sum) {
+    if (!h) return RPF_ERR_ARG;
+    if (!h->built) return rpf_fail(h, RPF_ERR_STATE, "recall: forest not built");
+    if (nq < 0 || (nq > 0 && (!Q || !recall_sum)) || k < 1 || k > 1024) return rpf_fail(h, RPF_ERR_ARG, "recall: bad arguments (1 <= k <= 1024)");
+    RPF_SETDEV(h);
+    h->call_begin();
+    int rc = rpf_recall_impl(h, Q, q_last, nq, k, recall_sum);
     int rc2 = h->call_end();
     return rc ? rc : rc2;
 }
@@ -568,7 +672,18 @@ int rpf_brute_knn(rpf_handle* h, const double* Q, int64_t nq, int32_t k, double*
     if (nq < 0 || (nq > 0 && (!Q || !dist || !ids)) || k < 1 || k > 1024) return rpf_fail(h, RPF_ERR_ARG, "brute_knn: bad arguments (1 <= k <= 1024)");
     RPF_SETDEV(h);
     h->call_begin();
-    int rc = rpf_brute_knn_impl(h, Q, nq, k, dist, ids);
+    int rc = rpf_brute_knn_impl(h, Q, nullptr, nq, k, dist, ids);
+    int rc2 = h->call_end();
+    return rc ? rc : rc2;
+}
+
+int rpf_brute_knn_s(rpf_handle* h, const double* Q, const int32_t* q_last, int64_t nq, int32_t k, double* dist, uint32_t* ids) {
+    if (!h) return RPF_ERR_ARG;
+    if (!h->dX) return rpf_fail(h, RPF_ERR_STATE, "brute_knn: call rpf_set_points first");
+    if (nq < 0 || (nq > 0 && (!Q || !dist || !ids)) || k < 1 || k > 1024) return rpf_fail(h, RPF_ERR_ARG, "brute_knn: bad arguments (1 <= k <= 1024)");
+    RPF_SETDEV(h);
+    h->call_begin();
+    int rc = rpf_brute_knn_impl(h, Q, q_last, nq, k, dist, ids);
     int rc2 = h->call_end();
     return rc ? rc : rc2;
 }

@@ -85,6 +85,7 @@ __device__ __forceinline__ void ld1024(const double* p, double* x) {
         : "l"(p));
 }
 // sqrt (sum_j (x_j - q_j)^2), left fold from 0, separate roundings (Internal.hs:403-406).
+// `d` may be a prefix length (SVector data: the reference's diffSD / diffSS stop at the sparse operand's last component).
 __device__ __forceinline__ double dist_exact(const double* __restrict__ row, const double* __restrict__ sq, int d, bool vec) {
     double acc = 0.0;
     if (vec) {
@@ -266,10 +267,23 @@ struct QArgs {
     const uint32_t* segs;
     const uint32_t* cnt;
     const uint32_t* order;     // knn only: CTA b answers query order[b] (queries grouped by their tree-0 leaf, see k_qorder_*)
+    const int32_t* xlast;      // SVector data only: index of each row's last stored component (-1: none); NULL for DVector data
+    const int32_t* qlast;      // SVector queries only: same per query; NULL for DVector queries
     double* dist;
     uint32_t* ids;
     int32_t* count;
 };
+
+// number of leading components the metric visits for data row `id` and query q:
+//   DVector data: all d (metricDDL2, Internal.hs:403-406)
+//   SVector data, DVector query: up to the row's last stored component (metricSDL2 / binSDD, Internal.hs:396-400,455-470)
+//   SVector data, SVector query: up to the smaller of the two last components (metricSSL2 / binSS, Internal.hs:389-393,432-453)
+__device__ __forceinline__ int metric_len(const QArgs& A, uint32_t id, int64_t q) {
+    if (!A.xlast) return A.d;
+    int m = __ldg(A.xlast + id);
+    if (A.qlast) m = min(m, __ldg(A.qlast + q));
+    return m + 1;
+}
 
 // slot sizes for query q into pre[0..nslots): slot = tt*S + j
 __device__ __forceinline__ void load_slots(const QArgs& A, int64_t q, int Tq, uint32_t* pre, int NT) {
@@ -319,7 +333,8 @@ __global__ void __launch_bounds__(KNN_NT) k_knn(QArgs A) {
             const int tt = slot / A.S;
             const uint32_t g = A.segs[(q * A.T + tt) * (int64_t)A.S + (slot % A.S)];
             const uint32_t id = A.perm[(int64_t)tt * A.n + A.nstart[g] + (c - pre[slot])];
-            const double dist = dist_exact(A.X + (int64_t)id * A.d, sq, A.d, A.vec);
+            const int len = metric_len(A, id, q);
+            const double dist = dist_exact(A.X + (int64_t)id * A.d, sq, len, A.vec && len == A.d);
             skey[nbest + j] = (ull)__double_as_longlong(dist);
             spos[nbest + j] = c;
             sid[nbest + j] = id;
@@ -624,7 +639,8 @@ __global__ void __launch_bounds__(KNN_NT) k_cand_fill(QArgs A, int Tq, int t_onl
 #define BF_NT 256
 // D[qi][i] = raw bits of dist(X[i], Q[q0+qi]);  thread per point, query tile in shared memory
 __global__ void __launch_bounds__(BF_NT) k_dist_all(const double* __restrict__ X, int64_t n, int d, const double* __restrict__ Q,
-                                                    int64_t q0, int nqt, ull* __restrict__ D, int vec) {
+                                                    int64_t q0, int nqt, ull* __restrict__ D, int vec,
+                                                    const int32_t* __restrict__ xlast, const int32_t* __restrict__ qlast) {
     extern __shared__ double sqt[];   // [BF_TQ][d]
     for (int e = threadIdx.x; e < nqt * d; e += BF_NT) sqt[e] = Q[q0 * d + e];
     __syncthreads();
@@ -634,7 +650,18 @@ __global__ void __launch_bounds__(BF_NT) k_dist_all(const double* __restrict__ X
     double acc[BF_TQ];
 #pragma unroll
     for (int qi = 0; qi < BF_TQ; ++qi) acc[qi] = 0.0;
-    if (vec) {
+    if (xlast) {          // SVector data: per (row, query) prefix length (see metric_len)
+        const int xl = xlast[i];
+        int len[BF_TQ];
+#pragma unroll
+        for (int qi = 0; qi < BF_TQ; ++qi) len[qi] = (qi < nqt ? (qlast ? min(xl, qlast[q0 + qi]) : xl) : -1) + 1;
+        for (int j = 0; j <= xl; ++j) {
+            const double x = __ldg(row + j);
+#pragma unroll
+            for (int qi = 0; qi < BF_TQ; ++qi)
+                if (j < len[qi]) { const double df = __dsub_rn(x, sqt[qi * d + j]); acc[qi] = __dadd_rn(acc[qi], __dmul_rn(df, df)); }
+        }
+    } else if (vec) {
         for (int j = 0; j < d; j += 4) {
             double x[4];
             ld256(row + j, x[0], x[1], x[2], x[3]);
@@ -829,8 +856,22 @@ __global__ void __launch_bounds__(KNN_NT) k_merge(int G, int64_t nq, int k, int 
 // shared front half of every query entry point: upload Q, project, descend (with retry on fork overflow)
 struct QState {
     double* dQ = nullptr; double* keysQ = nullptr; uint32_t* segs = nullptr; uint32_t* cnt = nullptr; uint32_t* maxcnt = nullptr;
+    const int32_t* dqlast = nullptr;
     int S = 2, Tq = 0;
 };
+
+// SVector queries: device copy of q_last (host), after checking it against the data representation
+static int upload_qlast(rpf_handle* h, const int32_t* q_last, int64_t nq, const int32_t** out) {
+    *out = nullptr;
+    if (!q_last) return RPF_OK;
+    if (!h->d_xlast) return rpf_fail(h, RPF_ERR_ARG, "SVector queries need SVector data (the reference has no Inner DVector SVector instance)");
+    for (int64_t i = 0; i < nq; ++i) if (q_last[i] < -1 || q_last[i] >= h->d) return rpf_fail(h, RPF_ERR_ARG, "q_last out of range");
+    int32_t* dq = (int32_t*)h->ws_get(WS_QLAST, (size_t)nq * 4);
+    if (!dq) return RPF_ERR_NOMEM;
+    RPF_CUDA(h, cudaMemcpyAsync(dq, q_last, (size_t)nq * 4, cudaMemcpyHostToDevice, h->stream));
+    *out = dq;
+    return RPF_OK;
+}
 
 static int run_descent(rpf_handle* h, const double* Q, int64_t nq, int t_only, QState& st) {
     const int L = h->topo.L_eff, T = h->T;
@@ -864,13 +905,16 @@ static QArgs make_qargs(rpf_handle* h, int64_t nq, const QState& st) {
     A.vec = (h->d % 4 == 0) && (((uintptr_t)h->dX & 31) == 0);
     A.X = h->dX; A.Q = st.dQ; A.perm = h->d_perm; A.nstart = h->d_node_start; A.nsize = h->d_node_size;
     A.segs = st.segs; A.cnt = st.cnt;
+    A.xlast = h->d_xlast; A.qlast = st.dqlast;
     return A;
 }
 
-int rpf_knn_impl(rpf_handle* h, const double* Q, int64_t nq, int k, int dedup, double* dist, uint32_t* ids, int32_t* count) {
+int rpf_knn_impl(rpf_handle* h, const double* Q, const int32_t* q_last, int64_t nq, int k, int dedup, double* dist, uint32_t* ids, int32_t* count) {
     if (nq == 0) return RPF_OK;
     QState st;
-    int rc = run_descent(h, Q, nq, -1, st);
+    int rc = upload_qlast(h, q_last, nq, &st.dqlast);
+    if (rc) return rc;
+    rc = run_descent(h, Q, nq, -1, st);
     if (rc) return rc;
     QWS(h, ddist, double, WS_OUT_D, (size_t)nq * k * 8);
     QWS(h, dids, uint32_t, WS_OUT_I, (size_t)nq * k * 4);
@@ -892,7 +936,7 @@ int rpf_knn_impl(rpf_handle* h, const double* Q, int64_t nq, int k, int dedup, d
     int rows = (int)std::min<size_t>(32, (size_t)(72 * 1024) / ((size_t)KT_STAGES * pitch));
     const size_t dyn_tma = (size_t)KT_STAGES * rows * pitch + (size_t)(KT_BUF + KT_SREG) * 16 + (size_t)2 * KT_BUF * 4 + tail;
     const bool use_tma = (h->d % 2 == 0) && rows >= 1 && k <= KT_BUF / 2 && dyn_tma <= 112 * 1024 && !h->force_simple_knn &&
-                         (((uintptr_t)h->dX & 15) == 0);
+                         (((uintptr_t)h->dX & 15) == 0) && !h->d_xlast;     // SVector data: per-candidate prefix lengths -> gather kernel
     if (use_tma) {
         RPF_CUDA(h, cudaFuncSetAttribute(k_knn_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_tma));
         RPF_CUDA(h, cudaFuncSetAttribute(k_knn_tma, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
@@ -942,7 +986,7 @@ int rpf_candidates_impl(rpf_handle* h, const double* Q, int64_t nq, int t, int64
 }
 
 // exact top-k of all n rows for queries dQ[0..nq) -> device arrays d_dist/d_ids (nq x k)
-static int brute_device(rpf_handle* h, const double* dQ, int64_t nq, int k, double* d_dist, uint32_t* d_ids) {
+static int brute_device(rpf_handle* h, const double* dQ, const int32_t* dqlast, int64_t nq, int k, double* d_dist, uint32_t* d_ids) {
     const int64_t n = h->n;
     const int d = h->d;
     if (n == 0) return rpf_fail(h, RPF_ERR_STATE, "brute_knn: no points");
@@ -953,19 +997,22 @@ static int brute_device(rpf_handle* h, const double* dQ, int64_t nq, int k, doub
     RPF_CUDA(h, cudaFuncSetAttribute(k_dist_all, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     for (int64_t q0 = 0; q0 < nq; q0 += BF_TQ) {
         const int nqt = (int)std::min<int64_t>(BF_TQ, nq - q0);
-        RPF_LAUNCH(h, PH_TRUTH, k_dist_all, (unsigned)((n + BF_NT - 1) / BF_NT), BF_NT, smem, h->dX, n, d, dQ, q0, nqt, D, vec);
+        RPF_LAUNCH(h, PH_TRUTH, k_dist_all, (unsigned)((n + BF_NT - 1) / BF_NT), BF_NT, smem, h->dX, n, d, dQ, q0, nqt, D, vec, h->d_xlast, dqlast);
         RPF_LAUNCH(h, PH_TRUTH, k_select_topk, (unsigned)nqt, 512, 0, D, n, k, q0, d_dist, d_ids);
     }
     return RPF_OK;
 }
 
-int rpf_brute_knn_impl(rpf_handle* h, const double* Q, int64_t nq, int k, double* dist, uint32_t* ids) {
+int rpf_brute_knn_impl(rpf_handle* h, const double* Q, const int32_t* q_last, int64_t nq, int k, double* dist, uint32_t* ids) {
     if (nq == 0) return RPF_OK;
+    const int32_t* dqlast = nullptr;
+    int rc0 = upload_qlast(h, q_last, nq, &dqlast);
+    if (rc0) return rc0;
     QWS(h, dQ, double, WS_Q, (size_t)nq * h->d * 8);
     QWS(h, dd, double, WS_TRUTH_D, (size_t)nq * k * 8);
     QWS(h, di, uint32_t, WS_TRUTH_I, (size_t)nq * k * 4);
     RPF_CUDA(h, cudaMemcpyAsync(dQ, Q, (size_t)nq * h->d * 8, cudaMemcpyHostToDevice, h->stream));
-    int rc = brute_device(h, dQ, nq, k, dd, di);
+    int rc = brute_device(h, dQ, dqlast, nq, k, dd, di);
     if (rc) return rc;
     RPF_CUDA(h, cudaMemcpyAsync(dist, dd, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, h->stream));
     RPF_CUDA(h, cudaMemcpyAsync(ids, di, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, h->stream));
@@ -973,15 +1020,17 @@ int rpf_brute_knn_impl(rpf_handle* h, const double* Q, int64_t nq, int k, double
     return RPF_OK;
 }
 
-int rpf_recall_impl(rpf_handle* h, const double* Q, int64_t nq, int k, double* recall_sum) {
+int rpf_recall_impl(rpf_handle* h, const double* Q, const int32_t* q_last, int64_t nq, int k, double* recall_sum) {
     if (nq == 0) return RPF_OK;
     QState st;
-    int rc = run_descent(h, Q, nq, -1, st);
+    int rc = upload_qlast(h, q_last, nq, &st.dqlast);
+    if (rc) return rc;
+    rc = run_descent(h, Q, nq, -1, st);
     if (rc) return rc;
     QWS(h, dd, double, WS_TRUTH_D, (size_t)nq * k * 8);
     QWS(h, di, uint32_t, WS_TRUTH_I, (size_t)nq * k * 4);
     QWS(h, dr, double, WS_RECALL, (size_t)nq * 8);
-    rc = brute_device(h, st.dQ, nq, k, dd, di);
+    rc = brute_device(h, st.dQ, st.dqlast, nq, k, dd, di);
     if (rc) return rc;
     QArgs A = make_qargs(h, nq, st);
     A.k = k;

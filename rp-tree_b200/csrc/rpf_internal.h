@@ -105,7 +105,7 @@ enum rpf_ws_slot {
     WS_NBDEV, WS_RANGE, WS_LVLPV, WS_HPPACK,
     WS_Q, WS_KEYSQ, WS_SEGS, WS_CNT, WS_MAXCNT, WS_OUT_D, WS_OUT_I, WS_OUT_C, WS_BF_D, WS_TRUTH_D, WS_TRUTH_I, WS_RECALL,
     WS_CANDCNT, WS_CANDOFF, WS_CANDOUT, WS_MRG_D, WS_MRG_I, WS_MRG_C, WS_QHIST, WS_QORDER,
-    WS_S_ARENA0, WS_S_ARENA1, WS_S_CPERM, WS_S_TMPN, WS_S_POOL,
+    WS_S_ARENA0, WS_S_ARENA1, WS_S_CPERM, WS_S_TMPN, WS_S_POOL, WS_QLAST,
     WS_COUNT
 };
 struct WsBuf { void* p = nullptr; size_t cap = 0; };
@@ -118,6 +118,7 @@ struct rpf_handle {
     // points
     int64_t n = 0; int d = 0;
     const double* dX = nullptr; bool ownX = false; size_t x_bytes = 0;
+    int32_t* d_xlast = nullptr;          // SVector data (rpf_set_points_sparse): last stored component of every row; else NULL
 
     // hyperplanes: CSR over (tree, level); host copy + device copy
     int T = 0, hpDepth = 0;
@@ -213,10 +214,10 @@ int rpf_project_launch(rpf_handle* h, int phase, const double* dX, int64_t n, in
 int rpf_upload_topology(rpf_handle* h);
 int rpf_build_stream_impl(rpf_handle* h, int maxDepth, int minLeaf, int64_t chunk);
 int rpf_project_queries(rpf_handle* h, const double* dQ, int64_t nq, double* d_keysQ);
-int rpf_knn_impl(rpf_handle* h, const double* Q, int64_t nq, int k, int dedup, double* dist, uint32_t* ids, int32_t* count);
+int rpf_knn_impl(rpf_handle* h, const double* Q, const int32_t* q_last, int64_t nq, int k, int dedup, double* dist, uint32_t* ids, int32_t* count);
 int rpf_candidates_impl(rpf_handle* h, const double* Q, int64_t nq, int t, int64_t* off_out, const int64_t* off_in, uint32_t* ids);
-int rpf_recall_impl(rpf_handle* h, const double* Q, int64_t nq, int k, double* recall_sum);
-int rpf_brute_knn_impl(rpf_handle* h, const double* Q, int64_t nq, int k, double* dist, uint32_t* ids);
+int rpf_recall_impl(rpf_handle* h, const double* Q, const int32_t* q_last, int64_t nq, int k, double* recall_sum);
+int rpf_brute_knn_impl(rpf_handle* h, const double* Q, const int32_t* q_last, int64_t nq, int k, double* dist, uint32_t* ids);
 int rpf_merge_impl(rpf_handle* h, int G, int64_t nq, int k, int dedup, const double* dist, const uint32_t* ids,
                    const int32_t* count, double* dist_out, uint32_t* ids_out, int32_t* count_out);
 

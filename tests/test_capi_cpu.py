@@ -73,3 +73,40 @@ def test_slice_hyperplanes(built):
     assert np.array_equal(np.concatenate([p[2] for p in parts]), hp[2])
     for p in parts:
         assert p[0][0] == 0 and len(p[0]) == 11 and p[0][-1] == len(p[1])
+
+
+@pytest.mark.parametrize("n,chunk,maxd,minl", [(1000, 100, 8, 10), (1000, 64, 10, 5), (5000, 50, 12, 8), (300, 7, 6, 3), (2000, 300, 4, 100),
+                                               (1000, 1, 5, 2), (1000, 3, 9, 1), (997, 101, 20, 6), (4096, 512, 12, 1), (500, 20, 7, 64),
+                                               (10000, 100, 14, 8), (3000, 999, 6, 40), (600, 50, 8, 0), (1000, 1000, 6, 10), (1000, 5000, 6, 10)])
+def test_streaming_plan_matches_oracle_chunked_shape(built, n, chunk, maxd, minl):
+    """The planner of the streaming build (sizes only, host) == the shape the oracle's chunked insert produces,
+    including the subtrees the reference drops when an empty piece reaches a Bin (Internal.hs:279)."""
+    import rp_tree_b200 as R
+    from oracle import orc
+    d = 3
+    X = np.random.default_rng(n + chunk).normal(size=(n, d))
+    hp = orc.gen_hyperplanes(1, 1, maxd, 1.0, d)
+    of = orc.Forest(X, hp, 1, maxd, minl, chunk=chunk)
+    e = of.export(0)
+    tp = R.topologyPlan(n, maxd, minl, chunk=chunk)
+    for k in ("child", "depth", "seg_start", "seg_size"):
+        assert np.array_equal(tp[k], e[k]), k
+    assert tp["points_lost"] == n - of.tree_size(0)
+
+
+def test_streaming_plan_rejects_oversized_resplit(built):
+    import rp_tree_b200 as R
+    with pytest.raises(R.RPForestError):
+        R.topologyPlan(30000, 4, 9000, chunk=6000)
+
+
+def test_densify_rows_helper(built):
+    import rp_tree_b200 as R
+    M = np.array([[0, 1.5, 0, -2.0], [0, 0, 0, 0], [3.0, 0, 0, 0]])
+    rows = R.SparseRows.fromDense(M)
+    assert rows.n == 3 and rows.d == 4 and list(rows.off) == [0, 2, 2, 3]
+    Q, last = rows.densify()
+    assert np.array_equal(Q, M) and list(last) == [3, -1, 0]
+    bad = R.SparseRows([0, 2], [2, 1], [1.0, 2.0], 4)        # indices not ascending
+    with pytest.raises(R.RPForestError):
+        bad.densify()

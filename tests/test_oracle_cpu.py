@@ -179,3 +179,45 @@ def test_golden_fixtures():
     d, i = f.knn(q, c["k"])
     assert i.tolist() == G["knn_ids"] and d.view(np.uint64).tolist() == G["knn_dist_bits"]
     assert f.recall(q, c["k"]) == G["recall"]
+
+
+def test_sparse_metrics_keep_the_reference_truncation_quirk():
+    """metricSSL2 / metricSDL2 (Internal.hs:389-400) go through binSS / binSDD (Internal.hs:432-470), which stop as soon as
+    EITHER operand is exhausted: components past the sparse operand's last stored index are dropped."""
+    from oracle import orc
+    # u = {1: 3, 4: 1}, v dense
+    ui, uv = np.array([1, 4], np.int32), np.array([3.0, 1.0])
+    v = np.array([1.0, 1.0, 2.0, 0.0, 5.0, 7.0, 7.0])
+    # visited positions 0..4: (0-1), (3-1), (0-2), (0-0), (1-5); positions 5, 6 are never reached
+    assert orc.metric_sd_l2(ui, uv, v) == np.sqrt(1.0 + 4.0 + 4.0 + 0.0 + 16.0)
+    # sparse-sparse: w = {0: 2, 1: 1, 6: 9}; the merge stops when u is exhausted (after index 4), so w's 6 is dropped
+    wi, wv = np.array([0, 1, 6], np.int32), np.array([2.0, 1.0, 9.0])
+    # emitted: (0: 0-2), (1: 3-1), (4: 1-0); then u is exhausted
+    assert orc.metric_ss_l2(ui, uv, wi, wv) == 3.0
+    assert orc.metric_ss_l2(wi, wv, ui, uv) == 3.0
+    # empty operand -> nothing emitted -> distance 0
+    e_i, e_v = np.zeros(0, np.int32), np.zeros(0)
+    assert orc.metric_ss_l2(e_i, e_v, wi, wv) == 0.0 and orc.metric_sd_l2(e_i, e_v, v) == 0.0
+
+
+def test_sparse_forest_equals_dense_forest_on_the_dense_image():
+    """innerSS over SVector points == innerSD over their dense image (missing components contribute exact zeros), so the
+    two forests have identical structure; only the metric differs."""
+    from oracle import orc
+    rng = np.random.default_rng(0)
+    n, d, T, maxd, minl = 600, 12, 3, 7, 8
+    M = rng.normal(size=(n, d)) * (rng.random((n, d)) < 0.3)
+    r, c = np.nonzero(M)
+    off = np.zeros(n + 1, np.int64); np.add.at(off, r + 1, 1); off = np.cumsum(off)
+    hp = orc.gen_hyperplanes(3, T, maxd, 0.5, d)
+    fs = orc.SparseForest((off, c.astype(np.int32), M[r, c]), d, hp, T, maxd, minl)
+    fd = orc.Forest(M, hp, T, maxd, minl)
+    for t in range(T):
+        a, b = fs.export(t), fd.export(t)
+        for k in a:
+            assert np.array_equal(a[k], b[k]), k
+    q = M[5] + 0.1
+    assert np.array_equal(fs.candidates(0, q), fd.candidates(0, q))
+    ds, _ = fs.knn(q, 5)
+    dd, _ = fd.knn(q, 5)
+    assert not np.array_equal(ds, dd)          # metricSDL2 ignores q's components past each row's last index
