@@ -136,6 +136,15 @@ int rpf_candidates(rpf_handle* h, const double* Q, int64_t nq, int32_t t, const 
  * sqrt(sum_j (x_j - q_j)^2), left-fold sum, correctly rounded squares (Internal.hs:403-406). */
 int rpf_knn(rpf_handle* h, const double* Q, int64_t nq, int32_t k, int32_t dedup,
             double* dist, uint32_t* ids, int32_t* count);
+/* knnH metricL2 k (RPTree.hs:199-217, candidatesH :318-341): the leaves the descent reaches are ranked by their margin
+ * priority (smallest margin distance met on the way down); leaves are taken in increasing priority and PREPENDED to the
+ * result while the running total stays <= k (the first non-empty one is always taken).  As in the reference the result
+ * is neither sorted by distance nor cut to k: count[q] <= cap entries per query, cap >= rpf_knn_h_capacity(h, k) =
+ * max(k, largest leaf).  q_last: NULL, or as in rpf_knn_s.  Order among leaves of EQUAL priority is an internal of the
+ * `heaps` package in the reference (unpinned); here: tree index, then leaf position. */
+int64_t rpf_knn_h_capacity(const rpf_handle* h, int32_t k);
+int rpf_knn_h(rpf_handle* h, const double* Q, const int32_t* q_last, int64_t nq, int32_t k, int64_t cap,
+              double* dist, uint32_t* ids, int32_t* count);
 /* recallWith metricL2 forest k q (RPTree.hs:259-282): mean over this handle's trees of
  * |candidates(t,q) /\ true-top-k| / k.  recall_sum[q] = SUM over local trees (divide by the global
  * tree count after reducing across GPUs). */

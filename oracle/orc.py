@@ -81,6 +81,10 @@ def lib():
         L.orc_candidates.argtypes = [C.c_void_p, C.c_int32, c_f64p, c_u32p, C.c_int64]
         L.orc_knn.restype = C.c_int64
         L.orc_knn.argtypes = [C.c_void_p, c_f64p, C.c_int32, C.c_int32, c_f64p, c_u32p]
+        L.orc_knn_h.restype = C.c_int64
+        L.orc_knn_h.argtypes = [C.c_void_p, c_f64p, C.c_int32, c_f64p, c_u32p, C.c_int64]
+        L.orc_knn_h_sq.restype = C.c_int64
+        L.orc_knn_h_sq.argtypes = [C.c_void_p, C.c_int64, c_i32p, c_f64p, C.c_int32, c_f64p, c_u32p, C.c_int64]
         L.orc_recall.restype = C.c_double
         L.orc_recall.argtypes = [C.c_void_p, c_f64p, C.c_int32]
         L.orc_brute_knn.argtypes = [c_f64p, C.c_int64, C.c_int32, c_f64p, C.c_int32, c_f64p, c_u32p]
@@ -231,6 +235,18 @@ class Forest:
     def recall(self, q, k):
         q = np.ascontiguousarray(q, np.float64)
         return lib().orc_recall(self.h, _p(q, c_f64p), k)
+
+    def knn_h(self, q, k):
+        """knnH: (distances, ids) in the reference's result order (not sorted by distance, not cut to k)."""
+        cap = max(k, self.n) + 1
+        dist = np.zeros(cap); ids = np.zeros(cap, np.uint32)
+        if isinstance(q, tuple):
+            nz, ii, vv = _sv(*q)
+            m = lib().orc_knn_h_sq(self.h, nz, _p(ii, c_i32p), _p(vv, c_f64p), k, _p(dist, c_f64p), _p(ids, c_u32p), cap)
+        else:
+            q = np.ascontiguousarray(q, np.float64)
+            m = lib().orc_knn_h(self.h, _p(q, c_f64p), k, _p(dist, c_f64p), _p(ids, c_u32p), cap)
+        return dist[:m], ids[:m]
 
 
 def _sv(idx, val):

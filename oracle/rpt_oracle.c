@@ -523,6 +523,62 @@ int64_t orc_knn_sq(const orc_forest* f, int64_t qnz, const int32_t* qidx, const 
     return knn_q(f, &r, k, dedup, dist, ids);
 }
 
+/* candidatesH, RPTree.hs:318-341: every reached Tip with its priority p (p0 = 1/0; left: p `min` dl, right: p `min` dr) */
+typedef struct { double p; const onode* tip; } hent;
+typedef struct { hent* e; int64_t n, cap; } hbuf;
+static void hbuf_push(hbuf* b, double p, const onode* tip) {
+    if (b->n == b->cap) { b->cap = b->cap * 2 + 16; b->e = (hent*)realloc(b->e, sizeof(hent) * (size_t)b->cap); }
+    b->e[b->n].p = p; b->e[b->n].tip = tip; ++b->n;
+}
+static void cand_h_go(const orc_forest* f, int32_t tree, int32_t lev, const onode* tt, const qref* x, double p, hbuf* out) {
+    if (!tt->is_bin) { hbuf_push(out, p, tt); return; }
+    int64_t hp = (int64_t)tree * f->maxd + lev;
+    double proj = query_proj(f, hp, x);
+    double dl = fabs(tt->mlo - proj), dr = fabs(tt->mhi - proj);
+    double pl = dmin(p, dl), pr = dmin(p, dr);
+    if (proj < tt->thr && dl > dr)      { cand_h_go(f, tree, lev + 1, tt->l, x, pl, out); cand_h_go(f, tree, lev + 1, tt->r, x, pr, out); }
+    else if (proj < tt->thr)            { cand_h_go(f, tree, lev + 1, tt->l, x, pl, out); }
+    else if (proj > tt->thr && dl < dr) { cand_h_go(f, tree, lev + 1, tt->l, x, pl, out); cand_h_go(f, tree, lev + 1, tt->r, x, pr, out); }
+    else                                { cand_h_go(f, tree, lev + 1, tt->r, x, pr, out); }
+}
+/* knnH, RPTree.hs:199-217: pop the union heap in increasing priority, prepend each popped leaf, stop at the first pop
+ * that would push the total past k once something has been taken.  The pop order among EQUAL priorities depends on the
+ * internals of the `heaps` package (skew-binomial heap; not in /root/reference): UNPINNED.  This restatement breaks such
+ * ties by (tree, leaf position left to right) -- the product documents and implements the same rule. */
+static int64_t knn_h_q(const orc_forest* f, const qref* q, int32_t k, double* dist, uint32_t* ids, int64_t cap) {
+    hbuf b = {0};
+    for (int32_t t = 0; t < f->T; ++t) cand_h_go(f, t, 0, f->roots[t], q, 1.0 / 0.0, &b);
+    /* stable insertion sort by priority (few entries) */
+    for (int64_t i = 1; i < b.n; ++i) {
+        hent v = b.e[i]; int64_t j = i;
+        while (j > 0 && cmp_double(v.p, b.e[j - 1].p) < 0) { b.e[j] = b.e[j - 1]; --j; }
+        b.e[j] = v;
+    }
+    int64_t n = 0, nacc = 0;
+    for (int64_t i = 0; i < b.n; ++i) {
+        int64_t ntot = n + b.e[i].tip->n;
+        if (ntot > k && n > 0) break;
+        n = ntot; nacc = i + 1;
+    }
+    /* acc = xsh_last <> ... <> xsh_first */
+    int64_t m = 0;
+    for (int64_t i = nacc - 1; i >= 0; --i)
+        for (int64_t e = 0; e < b.e[i].tip->n; ++e) {
+            if (m < cap) { ids[m] = b.e[i].tip->ids[e]; dist[m] = point_dist(f, b.e[i].tip->ids[e], q); }
+            ++m;
+        }
+    free(b.e);
+    return m;
+}
+int64_t orc_knn_h(const orc_forest* f, const double* q, int32_t k, double* dist, uint32_t* ids, int64_t cap) {
+    qref r = {q, 0, NULL, NULL};
+    return knn_h_q(f, &r, k, dist, ids, cap);
+}
+int64_t orc_knn_h_sq(const orc_forest* f, int64_t qnz, const int32_t* qidx, const double* qval, int32_t k, double* dist, uint32_t* ids, int64_t cap) {
+    qref r = {NULL, qnz, qidx, qval};
+    return knn_h_q(f, &r, k, dist, ids, cap);
+}
+
 static int cmp_u32(const void* a, const void* b) { uint32_t x = *(const uint32_t*)a, y = *(const uint32_t*)b; return x < y ? -1 : x > y; }
 
 /* recallWith / recallWith1, RPTree.hs:265-282.  `points tt` = leaves left to right; Data.List.sortBy is

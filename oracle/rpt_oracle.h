@@ -88,6 +88,11 @@ int64_t orc_knn(const orc_forest* f, const double* q, int32_t k, int32_t dedup, 
 int64_t orc_candidates_sq(const orc_forest* f, int32_t t, int64_t qnz, const int32_t* qidx, const double* qval, uint32_t* ids, int64_t cap);
 int64_t orc_knn_sq(const orc_forest* f, int64_t qnz, const int32_t* qidx, const double* qval, int32_t k, int32_t dedup, double* dist, uint32_t* ids);
 double  orc_recall_sq(const orc_forest* f, int64_t qnz, const int32_t* qidx, const double* qval, int32_t k);
+/* knnH (RPTree.hs:199-217) over candidatesH (RPTree.hs:318-341).  Returns the number of results (may exceed k: the
+ * first popped leaf is always taken whole); at most cap are written.  Ties between equal priorities: unpinned in the
+ * reference (heaps internals); here (tree, leaf position). */
+int64_t orc_knn_h(const orc_forest* f, const double* q, int32_t k, double* dist, uint32_t* ids, int64_t cap);
+int64_t orc_knn_h_sq(const orc_forest* f, int64_t qnz, const int32_t* qidx, const double* qval, int32_t k, double* dist, uint32_t* ids, int64_t cap);
 /* recallWith (RPTree.hs:265-282): mean over trees of |cands(t) n topk| / k; point identity = row id. */
 double  orc_recall(const orc_forest* f, const double* q, int32_t k);
 /* exact brute-force k nearest (stable by row id) -- used for forest-level recall */

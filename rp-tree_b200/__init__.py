@@ -7,11 +7,11 @@ plus tree-sharded multi-GPU plumbing (dist.py).  The directory name has a hyphen
 """
 from ._lib import RPForestError, lib, SO_PATH, SIGNATURES
 from .api import (RPForest, SparseRows, RPTreeConfig, metricL2, rpTreeCfg, sampleHyperplanes, topologyPlan, slice_hyperplanes,
-                  forestBatch, treeBatch, forest, tree, knn, knnPQ, candidates, recallWith, levels, leafSizes,
+                  forestBatch, treeBatch, forest, tree, knn, knnPQ, knnH, candidates, recallWith, levels, leafSizes,
                   treeSize, points)
 from . import _build
 from . import dist
 
 __all__ = ["RPForest", "SparseRows", "RPForestError", "RPTreeConfig", "metricL2", "rpTreeCfg", "sampleHyperplanes", "topologyPlan",
-           "slice_hyperplanes", "forestBatch", "treeBatch", "forest", "tree", "knn", "knnPQ", "candidates", "recallWith",
+           "slice_hyperplanes", "forestBatch", "treeBatch", "forest", "tree", "knn", "knnPQ", "knnH", "candidates", "recallWith",
            "levels", "leafSizes", "treeSize", "points", "lib", "SO_PATH", "SIGNATURES"]

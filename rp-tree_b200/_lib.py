@@ -50,6 +50,8 @@ SIGNATURES = {
     "rpf_candidates_count": (C.c_int, [H, f64p, C.c_int64, C.c_int32, i64p]),
     "rpf_candidates": (C.c_int, [H, f64p, C.c_int64, C.c_int32, i64p, u32p]),
     "rpf_knn": (C.c_int, [H, f64p, C.c_int64, C.c_int32, C.c_int32, f64p, u32p, i32p]),
+    "rpf_knn_h_capacity": (C.c_int64, [H, C.c_int32]),
+    "rpf_knn_h": (C.c_int, [H, f64p, i32p, C.c_int64, C.c_int32, C.c_int64, f64p, u32p, i32p]),
     "rpf_recall": (C.c_int, [H, f64p, C.c_int64, C.c_int32, f64p]),
     "rpf_brute_knn": (C.c_int, [H, f64p, C.c_int64, C.c_int32, f64p, u32p]),
     "rpf_merge_topk": (C.c_int, [H, C.c_int32, C.c_int64, C.c_int32, C.c_int32, f64p, u32p, i32p, f64p, u32p, i32p]),

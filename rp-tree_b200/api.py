@@ -8,7 +8,7 @@ Data points are rows of a float64 matrix (one DVector per row); the `Embed` payl
     treeBatch   seed maxd minl pnz dim xs             src/Data/RPTree/Batch.hs:29-41
     forest / tree (chunked conduit versions)          src/Data/RPTree/Conduit.hs:58-121
     rpTreeCfg minl n d                                src/Data/RPTree/Conduit.hs:132-141
-    knn / knnPQ distf k tts q                         src/Data/RPTree.hs:168-194
+    knn / knnPQ / knnH distf k tts q                  src/Data/RPTree.hs:168-217
     candidates tree q                                 src/Data/RPTree.hs:293-314
     recallWith distf tts k q                          src/Data/RPTree.hs:259-268
     treeSize / leafSizes / levels / points            src/Data/RPTree.hs:351-367, Internal.hs:199-208
@@ -284,6 +284,18 @@ class RPForest:
             self._ck(self._L.rpf_knn_s(self._h, _p(Q, f64p), _p(ql, i32p), nq, k, int(dedup), _p(dist, f64p), _p(ids, u32p), _p(cnt, i32p)), "rpf_knn_s")
         return dist, ids, cnt
 
+    def knnHBatch(self, Q, k):
+        """knnH for a batch: (dist, ids) nq x cap and cnt; row i holds cnt[i] results in the reference's order."""
+        Q, _, ql = _as_q(Q, self.d)
+        nq = Q.shape[0]
+        cap = int(self._L.rpf_knn_h_capacity(self._h, k))
+        if cap < 0:
+            raise RPForestError("rpf_knn_h_capacity: forest not built")
+        dist = np.zeros((nq, cap)); ids = np.zeros((nq, cap), np.uint32); cnt = np.zeros(nq, np.int32)
+        self._ck(self._L.rpf_knn_h(self._h, _p(Q, f64p), _p(ql, i32p) if ql is not None else None, nq, k, cap,
+                                   _p(dist, f64p), _p(ids, u32p), _p(cnt, i32p)), "rpf_knn_h")
+        return dist, ids, cnt
+
     def recallSumBatch(self, Q, k):
         Q, _, ql = _as_q(Q, self.d)
         nq = Q.shape[0]
@@ -431,6 +443,17 @@ def knnPQ(distf, k, tts, q):
     _need_l2(distf)
     Q, single = _q_for_call(q, tts.d)
     dist, ids, cnt = tts.knnBatch(Q, k, dedup=True)
+    if single:
+        return dist[0, : cnt[0]], ids[0, : cnt[0]]
+    return dist, ids, cnt
+
+
+def knnH(distf, k, tts, q):
+    """knnH (RPTree.hs:199-217): leaves in margin-priority order, accumulated while the total stays <= k.  Like the
+    reference the result is neither sorted by distance nor cut to k."""
+    _need_l2(distf)
+    Q, single = _q_for_call(q, tts.d)
+    dist, ids, cnt = tts.knnHBatch(Q, k)
     if single:
         return dist[0, : cnt[0]], ids[0, : cnt[0]]
     return dist, ids, cnt

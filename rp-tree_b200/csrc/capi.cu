@@ -644,6 +644,26 @@ int rpf_knn_s(rpf_handle* h, const double* Q, const int32_t* q_last, int64_t nq,
     return rc ? rc : rc2;
 }
 
+int64_t rpf_knn_h_capacity(const rpf_handle* h, int32_t k) {
+    if (!h || !h->built || k < 1) return -1;
+    uint32_t mx = 0;
+    const Topology& tp = h->topo;
+    for (int64_t g = 0; g < tp.nnodes(); ++g) if (tp.child[g] < 0) mx = std::max(mx, tp.size[g]);
+    return std::max<int64_t>(k, mx);
+}
+
+int rpf_knn_h(rpf_handle* h, const double* Q, const int32_t* q_last, int64_t nq, int32_t k, int64_t cap, double* dist, uint32_t* ids, int32_t* count) {
+    if (!h) return RPF_ERR_ARG;
+    if (!h->built) return rpf_fail(h, RPF_ERR_STATE, "knnH: forest not built");
+    if (nq < 0 || (nq > 0 && (!Q || !dist || !ids || !count)) || k < 1) return rpf_fail(h, RPF_ERR_ARG, "knnH: bad arguments");
+    if (cap < rpf_knn_h_capacity(h, k) || cap > 0x7fffffff) return rpf_fail(h, RPF_ERR_ARG, "knnH: cap must be >= rpf_knn_h_capacity(h, k)");
+    RPF_SETDEV(h);
+    h->call_begin();
+    int rc = rpf_knn_h_impl(h, Q, q_last, nq, k, (int)cap, dist, ids, count);
+    int rc2 = h->call_end();
+    return rc ? rc : rc2;
+}
+
 int rpf_recall(rpf_handle* h, const double* Q, int64_t nq, int32_t k, double* recall_sum) {
     if (!h) return RPF_ERR_ARG;
     if (!h->built) return rpf_fail(h, RPF_ERR_STATE, "recall: forest not built");

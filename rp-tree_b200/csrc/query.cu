@@ -27,10 +27,15 @@ __device__ __forceinline__ unsigned q_next_pow2(unsigned v) { return next_pow2_u
 // ---------------------------------------------------------------------------------------------------
 // One thread per (query, tree).  Emits the BFS ids of the reached leaves, left to right, into
 // segs[(q*Tq + tt)*S ..]; cnt holds the true count (may exceed S -> caller retries with a larger S).
+// PRIO (candidatesH, RPTree.hs:318-341): every reached leaf also gets its search priority = the smallest margin distance
+// met on the way down (p starts at +inf; going left p = min p dl, going right p = min p dr; Haskell's min x y = if x <= y
+// then x else y).
+template <bool PRIO>
 __global__ void k_traverse(const double* __restrict__ keysQ, int64_t nq, int T, int L, int64_t nn,
                            const int32_t* __restrict__ child, const int32_t* __restrict__ depth,
                            const double* __restrict__ thr, const double* __restrict__ mlo, const double* __restrict__ mhi,
-                           int S, int t_only, uint32_t* __restrict__ segs, uint32_t* __restrict__ cnt, uint32_t* __restrict__ maxcnt) {
+                           int S, int t_only, uint32_t* __restrict__ segs, uint32_t* __restrict__ cnt, uint32_t* __restrict__ maxcnt,
+                           double* __restrict__ prio) {
     const int Tq = t_only >= 0 ? 1 : T;
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= nq * Tq) return;
@@ -42,9 +47,12 @@ __global__ void k_traverse(const double* __restrict__ keysQ, int64_t nq, int T, 
     const double* mhi_t = mhi + (int64_t)t * nn;
     const double* kq = keysQ + (int64_t)t * L * nq + q;
     int stk[64];
+    double pstk[PRIO ? 64 : 1];
     int sp = 0, g = 0;
     uint32_t c = 0;
+    double p = __longlong_as_double(0x7ff0000000000000LL);
     uint32_t* out = segs + (q * Tq + tt) * (int64_t)S;
+    double* pout = PRIO ? prio + (q * Tq + tt) * (int64_t)S : nullptr;
     while (true) {
         int ch;
         while ((ch = __ldg(child + g)) >= 0) {
@@ -52,15 +60,17 @@ __global__ void k_traverse(const double* __restrict__ keysQ, int64_t nq, int T, 
             const double proj = kq[(int64_t)lev * nq];
             const double th = thr_t[g], lo = mlo_t[g], hi = mhi_t[g];
             const double dl = fabs(__dsub_rn(lo, proj)), dr = fabs(__dsub_rn(hi, proj));
-            if (proj < th && dl > dr) { stk[sp++] = ch + 1; g = ch; }
-            else if (proj < th) g = ch;
-            else if (proj > th && dl < dr) { stk[sp++] = ch + 1; g = ch; }
-            else g = ch + 1;
+            const double pl = (p <= dl) ? p : dl, pr = (p <= dr) ? p : dr;
+            if (proj < th && dl > dr) { if (PRIO) pstk[sp] = pr; stk[sp++] = ch + 1; g = ch; p = pl; }
+            else if (proj < th) { g = ch; p = pl; }
+            else if (proj > th && dl < dr) { if (PRIO) pstk[sp] = pr; stk[sp++] = ch + 1; g = ch; p = pl; }
+            else { g = ch + 1; p = pr; }
         }
-        if (c < (uint32_t)S) out[c] = (uint32_t)g;
+        if (c < (uint32_t)S) { out[c] = (uint32_t)g; if (PRIO) pout[c] = p; }
         ++c;
         if (sp == 0) break;
         g = stk[--sp];
+        if (PRIO) p = pstk[sp];
     }
     cnt[q * Tq + tt] = c;
     if (c > (uint32_t)S) atomicMax(maxcnt, c);
@@ -774,6 +784,69 @@ __global__ void __launch_bounds__(512) k_select_topk(const ull* __restrict__ D, 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// knnH (RPTree.hs:199-217): the reached leaves of all trees go into one min-heap keyed by their margin priority
+// (candidatesH); leaves are popped in increasing priority and PREPENDED to the result while the running total stays
+// <= k (the first non-empty pop is always taken).  The result is NOT sorted by distance and NOT cut to k -- it is what
+// the reference returns.  Order among EQUAL priorities is an internal of the `heaps` package (unpinned); here: tree
+// index, then leaf position left to right.
+// One CTA per query; up to HK_MAX reached leaves.
+// ---------------------------------------------------------------------------------------------------
+#define HK_NT 128
+#define HK_MAX 2048
+__global__ void __launch_bounds__(HK_NT) k_knn_h(QArgs A, const double* __restrict__ prio, int cap) {
+    __shared__ ull skey[HK_MAX];
+    __shared__ uint32_t spos[HK_MAX], sleaf[HK_MAX], soff[HK_MAX];
+    __shared__ unsigned s_m, s_total, s_nacc;
+    extern __shared__ unsigned char dyn[];
+    double* sq = (double*)dyn;
+    const int64_t q = blockIdx.x;
+    const int tid = threadIdx.x;
+    if (tid == 0) s_m = 0;
+    for (int j = tid; j < A.d; j += HK_NT) sq[j] = A.Q[q * A.d + j];
+    __syncthreads();
+    const unsigned nslots = (unsigned)A.T * A.S;
+    for (unsigned s = tid; s < nslots; s += HK_NT) {
+        const int tt = s / A.S, j = s % A.S;
+        if ((uint32_t)j < A.cnt[q * A.T + tt]) {
+            const unsigned p = atomicAdd(&s_m, 1u);
+            const int64_t e = (q * A.T + tt) * (int64_t)A.S + j;
+            skey[p] = (ull)__double_as_longlong(prio[e]);      // priorities are >= +0 or +inf: raw bits are order preserving
+            spos[p] = s;
+            sleaf[p] = A.segs[e];
+        }
+    }
+    __syncthreads();
+    const unsigned m = s_m;
+    sort3<HK_NT>(skey, spos, sleaf, m);                       // (priority, slot) ascending
+    if (tid == 0) {
+        // go acc n hh (RPTree.hs:207-217): stop at the first pop that would exceed k once something has been taken
+        unsigned n = 0, nacc = 0;
+        for (unsigned i = 0; i < m; ++i) {
+            const unsigned nels = A.nsize[sleaf[i]], ntot = n + nels;
+            if (ntot > (unsigned)A.k && n > 0) break;
+            soff[i] = n;                                         // elements taken before this leaf
+            n = ntot; nacc = i + 1;
+        }
+        s_total = n; s_nacc = nacc;
+    }
+    __syncthreads();
+    const unsigned total = s_total, nacc = s_nacc;
+    for (unsigned i = 0; i < nacc; ++i) {
+        const uint32_t g = sleaf[i], sz = A.nsize[g];
+        const int tt = spos[i] / A.S;
+        const unsigned base = total - soff[i] - sz;              // xsh <> acc: the latest pop comes first
+        for (unsigned e = tid; e < sz; e += HK_NT) {
+            if (base + e >= (unsigned)cap) continue;
+            const uint32_t id = A.perm[(int64_t)tt * A.n + A.nstart[g] + e];
+            const int len = metric_len(A, id, q);
+            A.dist[q * cap + base + e] = dist_exact(A.X + (int64_t)id * A.d, sq, len, A.vec && len == A.d);
+            A.ids[q * cap + base + e] = id;
+        }
+    }
+    if (tid == 0 && A.count) A.count[q] = (int32_t)min(total, (unsigned)cap);
+}
+
 // recallWith: per query, per tree: |candidates /\ truth| ; recall_sum = fold over trees of hits/k
 __global__ void __launch_bounds__(KNN_NT) k_recall(QArgs A, const uint32_t* __restrict__ truth, double* __restrict__ recall_sum) {
     __shared__ uint32_t part[KNN_NT + 1];
@@ -857,6 +930,8 @@ __global__ void __launch_bounds__(KNN_NT) k_merge(int G, int64_t nq, int k, int 
 struct QState {
     double* dQ = nullptr; double* keysQ = nullptr; uint32_t* segs = nullptr; uint32_t* cnt = nullptr; uint32_t* maxcnt = nullptr;
     const int32_t* dqlast = nullptr;
+    double* prio = nullptr;      // candidatesH priorities, parallel to segs (only when want_prio)
+    bool want_prio = false;
     int S = 2, Tq = 0;
 };
 
@@ -888,8 +963,15 @@ static int run_descent(rpf_handle* h, const double* Q, int64_t nq, int t_only, Q
         st.segs = segs;
         RPF_CUDA(h, cudaMemsetAsync(maxcnt, 0, 4, h->stream));
         const int64_t tot = nq * st.Tq;
-        RPF_LAUNCH(h, PH_Q_TRAVERSE, k_traverse, (unsigned)((tot + 127) / 128), 128, 0, keysQ, nq, T, L, h->topo.nnodes(),
-                   h->d_node_child, h->d_node_depth, h->d_thr, h->d_mlo, h->d_mhi, st.S, t_only, segs, cnt, maxcnt);
+        if (st.want_prio) {
+            QWS(h, prio, double, WS_PRIO, (size_t)nq * st.Tq * st.S * 8);
+            st.prio = prio;
+            RPF_LAUNCH(h, PH_Q_TRAVERSE, k_traverse<true>, (unsigned)((tot + 127) / 128), 128, 0, keysQ, nq, T, L, h->topo.nnodes(),
+                       h->d_node_child, h->d_node_depth, h->d_thr, h->d_mlo, h->d_mhi, st.S, t_only, segs, cnt, maxcnt, prio);
+        } else {
+            RPF_LAUNCH(h, PH_Q_TRAVERSE, k_traverse<false>, (unsigned)((tot + 127) / 128), 128, 0, keysQ, nq, T, L, h->topo.nnodes(),
+                       h->d_node_child, h->d_node_depth, h->d_thr, h->d_mlo, h->d_mhi, st.S, t_only, segs, cnt, maxcnt, (double*)nullptr);
+        }
         uint32_t mx = 0;
         RPF_CUDA(h, cudaMemcpyAsync(&mx, maxcnt, 4, cudaMemcpyDeviceToHost, h->stream));
         RPF_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -949,6 +1031,31 @@ int rpf_knn_impl(rpf_handle* h, const double* Q, const int32_t* q_last, int64_t 
     }
     RPF_CUDA(h, cudaMemcpyAsync(dist, ddist, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, h->stream));
     RPF_CUDA(h, cudaMemcpyAsync(ids, dids, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (count) RPF_CUDA(h, cudaMemcpyAsync(count, dcount, (size_t)nq * 4, cudaMemcpyDeviceToHost, h->stream));
+    RPF_CUDA(h, cudaStreamSynchronize(h->stream));
+    return RPF_OK;
+}
+
+int rpf_knn_h_impl(rpf_handle* h, const double* Q, const int32_t* q_last, int64_t nq, int k, int cap, double* dist, uint32_t* ids, int32_t* count) {
+    if (nq == 0) return RPF_OK;
+    QState st;
+    st.want_prio = true;
+    int rc = upload_qlast(h, q_last, nq, &st.dqlast);
+    if (rc) return rc;
+    rc = run_descent(h, Q, nq, -1, st);
+    if (rc) return rc;
+    if ((int64_t)h->T * st.S > HK_MAX) return rpf_fail(h, RPF_ERR_UNSUPPORTED, "knnH: more than 2048 leaf slots per query");
+    QWS(h, ddist, double, WS_OUT_D, (size_t)nq * cap * 8);
+    QWS(h, dids, uint32_t, WS_OUT_I, (size_t)nq * cap * 4);
+    QWS(h, dcount, int32_t, WS_OUT_C, (size_t)nq * 4);
+    QArgs A = make_qargs(h, nq, st);
+    A.k = k; A.dist = ddist; A.ids = dids; A.count = dcount;
+    const size_t dyn = (size_t)((h->d + 3) & ~3) * 8;
+    if (dyn > 160 * 1024) return rpf_fail(h, RPF_ERR_UNSUPPORTED, "knnH: dimension too large");
+    RPF_CUDA(h, cudaFuncSetAttribute(k_knn_h, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    RPF_LAUNCH(h, PH_Q_KNN, k_knn_h, (unsigned)nq, HK_NT, dyn, A, st.prio, cap);
+    RPF_CUDA(h, cudaMemcpyAsync(dist, ddist, (size_t)nq * cap * 8, cudaMemcpyDeviceToHost, h->stream));
+    RPF_CUDA(h, cudaMemcpyAsync(ids, dids, (size_t)nq * cap * 4, cudaMemcpyDeviceToHost, h->stream));
     if (count) RPF_CUDA(h, cudaMemcpyAsync(count, dcount, (size_t)nq * 4, cudaMemcpyDeviceToHost, h->stream));
     RPF_CUDA(h, cudaStreamSynchronize(h->stream));
     return RPF_OK;

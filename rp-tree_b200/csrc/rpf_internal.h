@@ -105,7 +105,7 @@ enum rpf_ws_slot {
     WS_NBDEV, WS_RANGE, WS_LVLPV, WS_HPPACK,
     WS_Q, WS_KEYSQ, WS_SEGS, WS_CNT, WS_MAXCNT, WS_OUT_D, WS_OUT_I, WS_OUT_C, WS_BF_D, WS_TRUTH_D, WS_TRUTH_I, WS_RECALL,
     WS_CANDCNT, WS_CANDOFF, WS_CANDOUT, WS_MRG_D, WS_MRG_I, WS_MRG_C, WS_QHIST, WS_QORDER,
-    WS_S_ARENA0, WS_S_ARENA1, WS_S_CPERM, WS_S_TMPN, WS_S_POOL, WS_QLAST,
+    WS_S_ARENA0, WS_S_ARENA1, WS_S_CPERM, WS_S_TMPN, WS_S_POOL, WS_QLAST, WS_PRIO,
     WS_COUNT
 };
 struct WsBuf { void* p = nullptr; size_t cap = 0; };
@@ -215,6 +215,7 @@ int rpf_upload_topology(rpf_handle* h);
 int rpf_build_stream_impl(rpf_handle* h, int maxDepth, int minLeaf, int64_t chunk);
 int rpf_project_queries(rpf_handle* h, const double* dQ, int64_t nq, double* d_keysQ);
 int rpf_knn_impl(rpf_handle* h, const double* Q, const int32_t* q_last, int64_t nq, int k, int dedup, double* dist, uint32_t* ids, int32_t* count);
+int rpf_knn_h_impl(rpf_handle* h, const double* Q, const int32_t* q_last, int64_t nq, int k, int cap, double* dist, uint32_t* ids, int32_t* count);
 int rpf_candidates_impl(rpf_handle* h, const double* Q, int64_t nq, int t, int64_t* off_out, const int64_t* off_in, uint32_t* ids);
 int rpf_recall_impl(rpf_handle* h, const double* Q, const int32_t* q_last, int64_t nq, int k, double* recall_sum);
 int rpf_brute_knn_impl(rpf_handle* h, const double* Q, const int32_t* q_last, int64_t nq, int k, double* dist, uint32_t* ids);

@@ -313,3 +313,24 @@ def test_profile_and_launch_count(built):
     prof = f.profile()
     assert prof["project"][1] >= 1 and prof["bottom"][1] >= 1
     assert f.lastDeviceMs() > 0 and f.launchCount() > 0
+
+
+@pytest.mark.parametrize("n,d,T,maxd,minl,pnz,kind,cap", QUERY_CASES[:4])
+def test_knnH_parity(built, n, d, T, maxd, minl, pnz, kind, cap):
+    """knnH (RPTree.hs:199-217): margin-priority leaf search.  Same leaves, same (reverse pop) order, bit-exact distances;
+    equal priorities are ordered by (tree, leaf position) on both sides (unpinned in the reference: heaps internals)."""
+    R, orc = _mods()
+    X, hp, f, of = _build_pair(n, d, T, maxd, minl, pnz, kind, cap)
+    rng = np.random.default_rng(23)
+    nq = 40
+    Q = X[rng.integers(0, n, size=nq)] + (0.05 * rng.normal(size=(nq, d)) if kind != "integer" else 0.0)
+    for k in (1, 10, 50, 200):
+        dist, ids, cnt = f.knnHBatch(Q, k)
+        for i in range(nq):
+            od, oi = of.knn_h(Q[i], k)
+            assert cnt[i] == len(oi), "count: k=%d q=%d: %d vs %d" % (k, i, cnt[i], len(oi))
+            assert np.array_equal(ids[i, :cnt[i]], oi), "ids: k=%d q=%d" % (k, i)
+            assert np.array_equal(bits(dist[i, :cnt[i]]), bits(od)), "distances: k=%d q=%d" % (k, i)
+    d1, i1 = R.knnH(R.metricL2, 10, f, Q[0])
+    od, oi = of.knn_h(Q[0], 10)
+    assert np.array_equal(i1, oi) and np.array_equal(bits(d1), bits(od))
