@@ -102,6 +102,8 @@ int rpf_build_chunked(rpf_handle* h, int32_t maxDepth, int32_t minLeaf, int64_t 
  * same for every tree.  Nodes are numbered in BFS order (level-major, left to right). */
 int64_t rpf_num_nodes(const rpf_handle* h);
 int32_t rpf_num_trees(const rpf_handle* h);
+int32_t rpf_hyperplane_depth(const rpf_handle* h);     /* hyperplanes stored per tree (>= maxDepth of the build) */
+int rpf_points_shape(const rpf_handle* h, int64_t* n, int32_t* d);
 /* child[g] = BFS id of the left child (right = +1) or -1 for a Tip; seg_start/seg_size = slice of perm
  * holding the points under node g.  Any pointer may be NULL. */
 int rpf_topology(const rpf_handle* h, int64_t* child, int32_t* depth, int64_t* seg_start, int64_t* seg_size);
@@ -123,6 +125,13 @@ int rpf_tree_export(rpf_handle* h, int32_t t, double* thr, double* mlo, double* 
 /* Whole forest in one call: thr/mlo/mhi[T][num_nodes], perm[T][n] (tree-major; any pointer may be NULL).
  * The copies run back to back on the engine's stream; pass page-locked buffers for full PCIe speed. */
 int rpf_forest_export(rpf_handle* h, double* thr, double* mlo, double* mhi, uint32_t* perm);
+
+/* ---- checkpoint (the engine-side counterpart of serialiseRPForest / deserialiseRPForest, Internal.hs:185-196) -------- */
+/* One flat little-endian file: hyperplanes, topology, thr/mlo/mhi, perm and -- with_points != 0 -- the data points
+ * (like the reference's serialised forest, which carries the Embed values in its leaves).  rpf_forest_load restores a
+ * queryable forest without rebuilding; a checkpoint without points needs the same points set on the handle first. */
+int rpf_forest_save(rpf_handle* h, const char* path, int32_t with_points);
+int rpf_forest_load(rpf_handle* h, const char* path);
 
 /* ---- queries --------------------------------------------------------------------------------------- */
 /* candidates (src/Data/RPTree.hs:293-314) for tree t (t >= 0) or for all trees concatenated tree-major

@@ -40,6 +40,8 @@ SIGNATURES = {
     "rpf_build_chunked": (C.c_int, [H, C.c_int32, C.c_int32, C.c_int64]),
     "rpf_num_nodes": (C.c_int64, [H]),
     "rpf_num_trees": (C.c_int32, [H]),
+    "rpf_hyperplane_depth": (C.c_int32, [H]),
+    "rpf_points_shape": (C.c_int, [H, i64p, i32p]),
     "rpf_topology": (C.c_int, [H, i64p, i32p, i64p, i64p]),
     "rpf_topology_plan": (C.c_int64, [C.c_int64, C.c_int32, C.c_int32, i64p, i32p, i64p, i64p]),
     "rpf_topology_plan_chunked": (C.c_int64, [C.c_int64, C.c_int32, C.c_int32, C.c_int64, i64p, i32p, i64p, i64p, i64p]),
@@ -47,6 +49,8 @@ SIGNATURES = {
     "rpf_leaf_order_exact": (C.c_int, [H]),
     "rpf_tree_export": (C.c_int, [H, C.c_int32, f64p, f64p, f64p, u32p]),
     "rpf_forest_export": (C.c_int, [H, f64p, f64p, f64p, u32p]),
+    "rpf_forest_save": (C.c_int, [H, C.c_char_p, C.c_int32]),
+    "rpf_forest_load": (C.c_int, [H, C.c_char_p]),
     "rpf_candidates_count": (C.c_int, [H, f64p, C.c_int64, C.c_int32, i64p]),
     "rpf_candidates": (C.c_int, [H, f64p, C.c_int64, C.c_int32, i64p, u32p]),
     "rpf_knn": (C.c_int, [H, f64p, C.c_int64, C.c_int32, C.c_int32, f64p, u32p, i32p]),

@@ -257,6 +257,23 @@ class RPForest:
                                            _p(out["perm"], u32p) if n else None), "rpf_forest_export")
         return out
 
+    def save(self, path, with_points=True):
+        """Checkpoint of the built forest (counterpart of serialiseRPForest, Internal.hs:185-190)."""
+        self._ck(self._L.rpf_forest_save(self._h, str(path).encode(), int(with_points)), "rpf_forest_save")
+
+    def load(self, path):
+        """Restore a checkpoint into this handle (counterpart of deserialiseRPForest, Internal.hs:192-196)."""
+        self._ck(self._L.rpf_forest_load(self._h, str(path).encode()), "rpf_forest_load")
+        self._topo = None
+        self.ntrees = int(self._L.rpf_num_trees(self._h))
+        tp = self.topology()
+        self.maxDepth = int(tp["depth"].max()) if len(tp["depth"]) else 0
+        n = C.c_int64(); d = C.c_int32()
+        self._L.rpf_points_shape(self._h, C.byref(n), C.byref(d))
+        self.n, self.d = n.value, d.value
+        self._hp_depth = int(self._L.rpf_hyperplane_depth(self._h))
+        self.ntrees_total = self.ntrees
+
     def leafOrderExact(self):
         return bool(self._L.rpf_leaf_order_exact(self._h))
 
@@ -421,6 +438,18 @@ def _q_for_call(q, d):
         return q, False
     Q, single = _as_qd(q, d)
     return Q, single
+
+
+def serialiseRPForest(tts, path, with_points=True):
+    """serialiseRPForest (Internal.hs:185-190) counterpart: writes the engine's flat checkpoint."""
+    tts.save(path, with_points)
+
+
+def deserialiseRPForest(path, device=0):
+    """deserialiseRPForest (Internal.hs:192-196) counterpart: a queryable forest from a checkpoint that carries its points."""
+    f = RPForest(device)
+    f.load(path)
+    return f
 
 
 def _need_l2(distf):

@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <cstdio>
 
 int rpf_fail(rpf_handle* h, int code, const std::string& msg) {
     if (h) h->err = msg;
@@ -253,6 +254,29 @@ int rpf_upload_topology(rpf_handle* h) {
     RPF_CUDA(h, cudaMemcpy(h->d_node_depth, tp.depth.data(), nn * 4, cudaMemcpyHostToDevice));
     return RPF_OK;
 }
+
+namespace {
+struct CkptHeader {
+    char magic[8];              // "RPFB200\0"
+    uint32_t version, flags;    // flags bit 0: points included, bit 1: SVector data (xlast present)
+    int64_t n, nn, hp_nnz, lost;
+    int32_t d, T, hpDepth, maxDepth, minLeaf, nlevels, L_eff, leaf_order_exact;
+};
+template <typename T> bool wr(FILE* f, const T* p, size_t n) { return n == 0 || fwrite(p, sizeof(T), n, f) == n; }
+template <typename T> bool rd(FILE* f, T* p, size_t n) { return n == 0 || fread(p, sizeof(T), n, f) == n; }
+template <typename T> bool wr_dev(FILE* f, const T* d, size_t n, std::vector<char>& tmp) {
+    if (n == 0) return true;
+    tmp.resize(n * sizeof(T));
+    if (cudaMemcpy(tmp.data(), d, n * sizeof(T), cudaMemcpyDeviceToHost) != cudaSuccess) return false;
+    return fwrite(tmp.data(), sizeof(T), n, f) == n;
+}
+template <typename T> bool rd_dev(FILE* f, T* d, size_t n, std::vector<char>& tmp) {
+    if (n == 0) return true;
+    tmp.resize(n * sizeof(T));
+    if (fread(tmp.data(), sizeof(T), n, f) != n) return false;
+    return cudaMemcpy(d, tmp.data(), n * sizeof(T), cudaMemcpyHostToDevice) == cudaSuccess;
+}
+}  // namespace
 
 extern "C" {
 
@@ -558,8 +582,105 @@ int rpf_build_chunked(rpf_handle* h, int32_t maxDepth, int32_t minLeaf, int64_t 
     return RPF_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// checkpoint: the device image of a built forest (serialiseRPForest / deserialiseRPForest, Internal.hs:185-196, store the
+// Haskell value as CBOR; a Haskell host still has that by rebuilding the value from rpf_forest_export.  This is the
+// engine-side equivalent: one flat little-endian file, restored without rebuilding.)
+// ---------------------------------------------------------------------------------------------------
+
+int rpf_forest_save(rpf_handle* h, const char* path, int32_t with_points) {
+    if (!h || !path) return RPF_ERR_ARG;
+    if (!h->built) return rpf_fail(h, RPF_ERR_STATE, "forest_save: forest not built");
+    RPF_SETDEV(h);
+    RPF_CUDA(h, cudaStreamSynchronize(h->stream));
+    FILE* f = fopen(path, "wb");
+    if (!f) return rpf_fail(h, RPF_ERR_ARG, std::string("forest_save: cannot open ") + path);
+    const Topology& tp = h->topo;
+    CkptHeader H{};
+    std::memcpy(H.magic, "RPFB200", 8);
+    H.version = 1; H.flags = (with_points ? 1u : 0u) | (h->d_xlast ? 2u : 0u);
+    H.n = h->n; H.nn = tp.nnodes(); H.hp_nnz = (int64_t)h->hp_idx.size(); H.lost = h->stream_lost;
+    H.d = h->d; H.T = h->T; H.hpDepth = h->hpDepth; H.maxDepth = tp.maxDepth; H.minLeaf = tp.minLeaf; H.nlevels = tp.nlevels; H.L_eff = tp.L_eff;
+    H.leaf_order_exact = h->leaf_order_exact ? 1 : 0;
+    std::vector<char> tmp;
+    const size_t nn = (size_t)H.nn, T = (size_t)H.T, n = (size_t)H.n;
+    bool ok = wr(f, &H, 1) && wr(f, h->hp_off.data(), h->hp_off.size()) && wr(f, h->hp_idx.data(), h->hp_idx.size()) &&
+              wr(f, h->hp_val.data(), h->hp_val.size()) && wr(f, tp.start.data(), nn) && wr(f, tp.size.data(), nn) &&
+              wr(f, tp.child.data(), nn) && wr(f, tp.depth.data(), nn) && wr(f, tp.level_off.data(), (size_t)tp.nlevels + 1) &&
+              wr(f, tp.lvl_maxsize.data(), (size_t)tp.nlevels) &&
+              wr_dev(f, h->d_thr, T * nn, tmp) && wr_dev(f, h->d_mlo, T * nn, tmp) && wr_dev(f, h->d_mhi, T * nn, tmp) &&
+              wr_dev(f, h->d_perm, T * n, tmp);
+    if (ok && with_points) {
+        ok = wr_dev(f, h->dX, n * (size_t)h->d, tmp);
+        if (ok && h->d_xlast) ok = wr_dev(f, h->d_xlast, n, tmp);
+    }
+    ok = (fclose(f) == 0) && ok;
+    if (!ok) return rpf_fail(h, RPF_ERR_CUDA, std::string("forest_save: write failed: ") + path);
+    return RPF_OK;
+}
+
+int rpf_forest_load(rpf_handle* h, const char* path) {
+    if (!h || !path) return RPF_ERR_ARG;
+    RPF_SETDEV(h);
+    RPF_CUDA(h, cudaStreamSynchronize(h->stream));
+    FILE* f = fopen(path, "rb");
+    if (!f) return rpf_fail(h, RPF_ERR_ARG, std::string("forest_load: cannot open ") + path);
+    CkptHeader H{};
+    auto fail = [&](const char* why) { fclose(f); h->built = false; return rpf_fail(h, RPF_ERR_ARG, std::string("forest_load: ") + why); };
+    if (!rd(f, &H, 1) || std::memcmp(H.magic, "RPFB200", 8) != 0 || H.version != 1) return fail("not a forest checkpoint");
+    if (H.n < 0 || H.nn < 1 || H.T < 1 || H.d < 1 || H.hpDepth < 0 || H.nlevels < 1 || H.hp_nnz < 0) return fail("corrupt header");
+    const bool has_points = H.flags & 1u, sparse = H.flags & 2u;
+    if (!has_points) {
+        if (!h->dX || h->n != H.n || h->d != H.d) return fail("the checkpoint carries no points: call rpf_set_points with the same data first");
+        if (sparse != (h->d_xlast != nullptr)) return fail("point representation (SVector / DVector) differs from the checkpoint's");
+    }
+    const size_t nn = (size_t)H.nn, T = (size_t)H.T, n = (size_t)H.n;
+    h->built = false;
+    h->T = H.T; h->hpDepth = H.hpDepth;
+    h->hp_off.resize((size_t)H.T * H.hpDepth + 1); h->hp_idx.resize((size_t)H.hp_nnz); h->hp_val.resize((size_t)H.hp_nnz);
+    Topology tp;
+    tp.n = H.n; tp.maxDepth = H.maxDepth; tp.minLeaf = H.minLeaf; tp.nlevels = H.nlevels; tp.L_eff = H.L_eff;
+    tp.start.resize(nn); tp.size.resize(nn); tp.child.resize(nn); tp.depth.resize(nn); tp.level_off.resize((size_t)H.nlevels + 1); tp.lvl_maxsize.resize((size_t)H.nlevels);
+    if (!(rd(f, h->hp_off.data(), h->hp_off.size()) && rd(f, h->hp_idx.data(), h->hp_idx.size()) && rd(f, h->hp_val.data(), h->hp_val.size()) &&
+          rd(f, tp.start.data(), nn) && rd(f, tp.size.data(), nn) && rd(f, tp.child.data(), nn) && rd(f, tp.depth.data(), nn) &&
+          rd(f, tp.level_off.data(), (size_t)H.nlevels + 1) && rd(f, tp.lvl_maxsize.data(), (size_t)H.nlevels)))
+        return fail("truncated file");
+    if (h->hp_off.back() != H.hp_nnz || tp.level_off.back() != H.nn) return fail("inconsistent tables");
+    if (has_points) {      // the data set travels with the forest: replace whatever the handle holds
+        if (h->d_xlast) { cudaFree(h->d_xlast); h->d_xlast = nullptr; }
+        if (h->ownX && h->dX) cudaFree((void*)h->dX);
+        h->dX = nullptr; h->ownX = false;
+        double* X = nullptr;
+        const size_t bytes = std::max<size_t>(n * (size_t)H.d * 8, 16);
+        if (cudaMalloc(&X, bytes) != cudaSuccess) { cudaGetLastError(); return fail("out of device memory"); }
+        h->dX = X; h->ownX = true; h->x_bytes = bytes; h->n = H.n; h->d = H.d;
+    }
+    int rc = upload_hyperplanes(h);      // also drops the previous forest arrays
+    if (rc) { fclose(f); return rc; }
+    h->topo = tp;
+    rc = rpf_upload_topology(h);
+    if (!rc) rc = rpf_alloc_forest(h, H.nn, H.n);
+    if (rc) { fclose(f); return rc; }
+    std::vector<char> tmp;
+    bool ok = rd_dev(f, h->d_thr, T * nn, tmp) && rd_dev(f, h->d_mlo, T * nn, tmp) && rd_dev(f, h->d_mhi, T * nn, tmp) && rd_dev(f, h->d_perm, T * n, tmp);
+    if (ok && has_points) {
+        ok = rd_dev(f, (double*)h->dX, n * (size_t)H.d, tmp);
+        if (ok && sparse) {
+            if (cudaMalloc(&h->d_xlast, std::max<size_t>(n * 4, 16)) != cudaSuccess) { cudaGetLastError(); return fail("out of device memory"); }
+            ok = rd_dev(f, h->d_xlast, n, tmp);
+        }
+    }
+    if (!ok) return fail("truncated file");
+    fclose(f);
+    h->stream_lost = H.lost; h->leaf_order_exact = H.leaf_order_exact != 0;
+    h->built = true;
+    return RPF_OK;
+}
+
 int64_t rpf_num_nodes(const rpf_handle* h) { return h ? h->topo.nnodes() : -1; }
 int32_t rpf_num_trees(const rpf_handle* h) { return h ? h->T : -1; }
+int32_t rpf_hyperplane_depth(const rpf_handle* h) { return h ? h->hpDepth : -1; }
+int rpf_points_shape(const rpf_handle* h, int64_t* n, int32_t* d) { if (!h) return RPF_ERR_ARG; if (n) *n = h->n; if (d) *d = h->d; return RPF_OK; }
 
 int rpf_topology(const rpf_handle* h, int64_t* child, int32_t* depth, int64_t* seg_start, int64_t* seg_size) {
     if (!h) return RPF_ERR_ARG;

@@ -844,6 +844,10 @@ __global__ void __launch_bounds__(HK_NT) k_knn_h(QArgs A, const double* __restri
             A.ids[q * cap + base + e] = id;
         }
     }
+    for (unsigned e = total + tid; e < (unsigned)cap; e += HK_NT) {          // unused tail of the row
+        A.dist[q * cap + e] = __longlong_as_double(0x7ff0000000000000LL);
+        A.ids[q * cap + e] = 0xffffffffu;
+    }
     if (tid == 0 && A.count) A.count[q] = (int32_t)min(total, (unsigned)cap);
 }
 

@@ -334,3 +334,40 @@ def test_knnH_parity(built, n, d, T, maxd, minl, pnz, kind, cap):
     d1, i1 = R.knnH(R.metricL2, 10, f, Q[0])
     od, oi = of.knn_h(Q[0], 10)
     assert np.array_equal(i1, oi) and np.array_equal(bits(d1), bits(od))
+
+
+@pytest.mark.parametrize("with_points", [True, False])
+@pytest.mark.parametrize("chunk", [None, 700])
+def test_checkpoint_round_trip(built, tmp_path, with_points, chunk):
+    """serialise / deserialise counterpart (Internal.hs:185-196): a restored forest answers exactly like the original."""
+    R, orc = _mods()
+    n, d, T, maxd, minl = 5000, 10, 3, 9, 12
+    X = make_data(n, d, 6)
+    hp = orc.gen_hyperplanes(8, T, maxd, 0.5, d)
+    f = R.forest(0, maxd, minl, T, chunk if chunk else n, 0.5, d, X, hyperplanes=hp)
+    path = tmp_path / "forest.rpf"
+    R.serialiseRPForest(f, path, with_points=with_points)
+    if with_points:
+        g = R.deserialiseRPForest(path)
+    else:
+        g = R.RPForest(0)
+        with pytest.raises(R.RPForestError, match="carries no points"):
+            g.load(path)
+        g.setPoints(X)
+        g.load(path)
+    assert g.ntrees == T and g.n == n and g.d == d and g.leafOrderExact() == f.leafOrderExact()
+    for t in range(T):
+        a, b = f.treeExport(t), g.treeExport(t)
+        for key in a:
+            assert np.array_equal(a[key], b[key]), key
+    Q = X[:20] + 0.01
+    for fn in (lambda h: h.knnBatch(Q, 7), lambda h: h.candidatesBatch(Q, -1), lambda h: h.knnHBatch(Q, 7)):
+        ra, rb = fn(f), fn(g)
+        for u, v in zip(ra, rb):
+            assert np.array_equal(u, v)
+    assert np.array_equal(f.recallSumBatch(Q, 5), g.recallSumBatch(Q, 5))
+    # a garbage file is refused
+    bad = tmp_path / "bad.rpf"
+    bad.write_bytes(b"not a checkpoint")
+    with pytest.raises(R.RPForestError):
+        g.load(bad)
