@@ -1,8 +1,8 @@
 {-# LANGUAGE ForeignFunctionInterface #-}
 {-# LANGUAGE BangPatterns #-}
 -- | Drop-in GPU back end for the hot path of "Data.RPTree" (rp-tree-0.7.1):
---   'forestBatch' / 'forest' -> 'candidates' / 'knn' / 'knnPQ' -> 'recallWith',
---   specialised to dense 'Double' data ('DVector') and 'metricL2'.
+--   'forestBatch' / 'forest' (streaming, any chunk size) -> 'candidates' / 'knn' / 'knnPQ' / 'knnH' -> 'recallWith',
+--   specialised to 'Double' data ('DVector' here; 'SVector' points go through 'setPointsSparse') and 'metricL2'.
 --
 -- Every function keeps the signature shape of its namesake in src/Data/RPTree.hs / Batch.hs / Conduit.hs and marshals to
 -- librpforest.so (include/rpforest.h).  The hyperplanes are drawn HERE, with the library's own
@@ -11,14 +11,15 @@
 --
 -- NOTE: written against the C ABI but NOT compiled in the authoring environment (no GHC there).
 module Data.RPTree.CUDA
-  ( GpuForest, forestBatch, treeBatch, forest, knn, knnPQ, candidates, recallWith, toRPForest, withDevice
+  ( GpuForest, forestBatch, treeBatch, forest, knn, knnPQ, knnH, candidates, recallWith, toRPForest, withDevice
+  , saveForest, setPointsSparse
   ) where
 
 import Control.Exception (throwIO, ErrorCall(..))
 import Control.Monad (replicateM, when, forM)
 import Data.Int (Int32, Int64)
 import Data.Word (Word32, Word64)
-import Foreign.C.String (CString, peekCString)
+import Foreign.C.String (CString, peekCString, withCString)
 import Foreign.C.Types (CInt(..), CDouble(..))
 import Foreign.ForeignPtr (ForeignPtr, newForeignPtr, withForeignPtr)
 import Foreign.Marshal.Alloc (alloca)
@@ -53,6 +54,10 @@ foreign import ccall safe "rpf_candidates_count"  c_candCnt  :: Ptr RpfHandle ->
 foreign import ccall safe "rpf_candidates"        c_cand     :: Ptr RpfHandle -> Ptr CDouble -> Int64 -> Int32 -> Ptr Int64 -> Ptr Word32 -> IO CInt
 foreign import ccall safe "rpf_knn"               c_knn      :: Ptr RpfHandle -> Ptr CDouble -> Int64 -> Int32 -> Int32 -> Ptr CDouble -> Ptr Word32 -> Ptr Int32 -> IO CInt
 foreign import ccall safe "rpf_recall"            c_recall   :: Ptr RpfHandle -> Ptr CDouble -> Int64 -> Int32 -> Ptr CDouble -> IO CInt
+foreign import ccall safe "rpf_knn_h_capacity"    c_knnHCap  :: Ptr RpfHandle -> Int32 -> IO Int64
+foreign import ccall safe "rpf_knn_h"             c_knnH     :: Ptr RpfHandle -> Ptr CDouble -> Ptr Int32 -> Int64 -> Int32 -> Int64 -> Ptr CDouble -> Ptr Word32 -> Ptr Int32 -> IO CInt
+foreign import ccall safe "rpf_set_points_sparse" c_setPtsS  :: Ptr RpfHandle -> Int64 -> Int32 -> Ptr Int64 -> Ptr Int32 -> Ptr CDouble -> IO CInt
+foreign import ccall safe "rpf_forest_save"       c_save     :: Ptr RpfHandle -> CString -> Int32 -> IO CInt
 
 -- | A forest living on one B200.  The payloads stay on the Haskell side, addressed by row number.
 data GpuForest x = GpuForest
@@ -109,7 +114,8 @@ forestBatch seed maxd minl ntrees pnz dim xs = unsafePerformIO (buildWith Nothin
 treeBatch :: Word64 -> Int -> Int -> Double -> Int -> V.Vector (Embed DVector Double x) -> GpuForest x
 treeBatch seed maxd minl = forestBatch seed maxd minl 1
 
--- | 'Data.RPTree.Conduit.forest' (Conduit.hs:104-121) after the source has been drained into a vector.
+-- | 'Data.RPTree.Conduit.forest' (Conduit.hs:104-121) after the source has been drained into a vector: the engine replays
+-- the conduit's @chunksOf chunksize@ fold itself (rpf_build_chunked), reproducing insert's Bin and Tip cases per chunk.
 forest :: Word64 -> Int -> Int -> Int -> Int -> Double -> Int -> V.Vector (Embed DVector Double x) -> IO (GpuForest x)
 forest seed maxd minl ntrees chunksize = buildWith (Just chunksize) seed maxd minl ntrees
 
@@ -131,6 +137,34 @@ knnWith dedup k gf q = unsafePerformIO $ withForeignPtr (gfHandle gf) $ \h -> qu
     ds <- peekArray m pd
     is <- peekArray m pi'
     pure $ V.fromList [ (realToFrac d, gfRows gf V.! fromIntegral i) | (d, i) <- zip ds is ]
+
+-- | 'Data.RPTree.knnH' with distf = metricL2 (RPTree.hs:199-217): whole leaves in margin-priority order, prepended
+-- while the running total stays <= k.  Not sorted by distance, not cut to k -- as in the reference.
+knnH :: Int -> GpuForest x -> DVector Double -> V.Vector (Double, Embed DVector Double x)
+knnH k gf q = unsafePerformIO $ withForeignPtr (gfHandle gf) $ \h -> queryPtr q $ \pq -> do
+  cap <- fromIntegral <$> c_knnHCap h (fromIntegral k)
+  allocaArray cap $ \pd -> allocaArray cap $ \pi' -> alloca $ \pc -> do
+    c_knnH h pq nullPtr 1 (fromIntegral k) (fromIntegral cap) pd pi' pc >>= check h "rpf_knn_h"
+    m <- fromIntegral <$> peek pc
+    ds <- peekArray m pd
+    is <- peekArray m pi'
+    pure $ V.fromList [ (realToFrac d, gfRows gf V.! fromIntegral i) | (d, i) <- zip ds is ]
+
+-- | Engine-side checkpoint (the CBOR form of 'serialiseRPForest' is still available through 'toRPForest').
+saveForest :: GpuForest x -> FilePath -> IO ()
+saveForest gf path = withForeignPtr (gfHandle gf) $ \h -> withCString path $ \p -> c_save h p 1 >>= check h "rpf_forest_save"
+
+-- | Data points as 'SVector's (Internal.hs:92-97): the (Int, Double) pairs are already SoA, so the rows go over as CSR.
+-- Distances then follow metricSDL2 / metricSSL2 (Internal.hs:389-400) including their early-stop behaviour.
+setPointsSparse :: Ptr RpfHandle -> Int -> V.Vector (SVector Double) -> IO ()
+setPointsSparse h dim svs =
+  withArray off $ \po -> withArray idx $ \pi' -> withArray val $ \pv ->
+    c_setPtsS h (fromIntegral (V.length svs)) (fromIntegral dim) po pi' pv >>= check h "rpf_set_points_sparse"
+  where
+    rows = map (VU.toList . svVec) (V.toList svs)
+    off  = scanl (+) 0 (map (fromIntegral . length) rows) :: [Int64]
+    idx  = concatMap (map (fromIntegral . fst)) rows :: [Int32]
+    val  = concatMap (map (realToFrac . snd)) rows :: [CDouble]
 
 -- | 'Data.RPTree.candidates' for tree @t@ of the forest (RPTree.hs:293-314).
 candidates :: GpuForest x -> Int -> DVector Double -> V.Vector (Embed DVector Double x)
