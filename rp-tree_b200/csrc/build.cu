@@ -1059,14 +1059,19 @@ __global__ void __launch_bounds__(NT) k_bottom3(BottomArgs A) {
     const bool root_internal = A.child[e0] >= 0;
     const bool unordered = A.s > 0 && !A.given_order;   // the slots do not arrive in the reference's order
 
-    for (uint32_t p = tid; p < P0; p += NT) sidx[p] = p < m ? perm[p] : 0u;
+    // Shared-memory layout: slot x of `w` and `sidx` lives at TI(x) = (x & 7) * NT + (x >> 3).  Thread t owns slots
+    // 8t .. 8t+7, i.e. TI = q * NT + t: every warp-wide access to "my q-th slot" touches 32 consecutive words (no bank
+    // conflicts; the linear layout made each of those a 4- to 16-way conflict -- 47 % of all wavefronts in ncu).
+    auto TI = [](unsigned x) -> unsigned { return (x & 7u) * NT + (x >> 3); };
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { const uint32_t p = 8u * tid + q; sidx[q * NT + tid] = p < m ? perm[p] : 0u; }
     __syncthreads();
 
     // composite order (key_{s-1}, ..., key_0, row id) of the whole node: only needed when the node arrives unordered
     // (s > 0) AND either it is a Tip itself or its first sort hits a tie in the top 48 key bits.
     auto composite_sort = [&]() {
         const ull* k1 = keys_t + (int64_t)(A.s - 1) * n;
-        for (uint32_t p = tid; p < m; p += NT) w[p] = k1[sidx[p]];
+        for (uint32_t p = tid; p < m; p += NT) w[p] = k1[sidx[TI(p)]];      // w is linear scratch inside this (rare) path
         __syncthreads();
         auto after = [&](ull ka, uint32_t ia, ull kb, uint32_t ib) -> bool {
             if (ka != kb) return ka > kb;
@@ -1083,8 +1088,8 @@ __global__ void __launch_bounds__(NT) k_bottom3(BottomArgs A) {
                 const unsigned blk = c >> (lk - 1), x = c & ((k >> 1) - 1);
                 const unsigned i = (blk << lk) + x, p = (blk << lk) + (k - 1 - x);
                 if (p < m) {
-                    const ull a = w[i], b = w[p]; const uint32_t ia = sidx[i], ib = sidx[p];
-                    if (after(a, ia, b, ib)) { w[i] = b; w[p] = a; sidx[i] = ib; sidx[p] = ia; }
+                    const ull a = w[i], b = w[p]; const uint32_t ia = sidx[TI(i)], ib = sidx[TI(p)];
+                    if (after(a, ia, b, ib)) { w[i] = b; w[p] = a; sidx[TI(i)] = ib; sidx[TI(p)] = ia; }
                 }
             }
             __syncthreads();
@@ -1093,8 +1098,8 @@ __global__ void __launch_bounds__(NT) k_bottom3(BottomArgs A) {
                 for (unsigned c = tid; c < half; c += NT) {
                     const unsigned i = ((c >> lj) << (lj + 1)) + (c & (j - 1)), p = i + j;
                     if (p < m) {
-                        const ull a = w[i], b = w[p]; const uint32_t ia = sidx[i], ib = sidx[p];
-                        if (after(a, ia, b, ib)) { w[i] = b; w[p] = a; sidx[i] = ib; sidx[p] = ia; }
+                        const ull a = w[i], b = w[p]; const uint32_t ia = sidx[TI(i)], ib = sidx[TI(p)];
+                        if (after(a, ia, b, ib)) { w[i] = b; w[p] = a; sidx[TI(i)] = ib; sidx[TI(p)] = ia; }
                     }
                 }
                 __syncthreads();
@@ -1103,7 +1108,7 @@ __global__ void __launch_bounds__(NT) k_bottom3(BottomArgs A) {
     };
 
     if (!root_internal) {        // the node is a Tip: its points must simply be in the reference's order
-        if (unordered) { composite_sort(); for (uint32_t p = tid; p < m; p += NT) perm[p] = sidx[p]; }
+        if (unordered) { composite_sort(); for (uint32_t p = tid; p < m; p += NT) perm[p] = sidx[TI(p)]; }
         return;
     }
     if (tid == 0) { t_sz[0][0] = (uint16_t)m; t_ps[0][0] = 0; t_gid[0][0] = e0; }
@@ -1120,14 +1125,14 @@ __global__ void __launch_bounds__(NT) k_bottom3(BottomArgs A) {
         const uint16_t* sz = t_sz[cur];
 
         // ---- gather keys into registers, build sort words, sort, store back in slot order
+        ull v[8];                                         // this thread's 8 sort words (kept in registers across the level)
         auto gather_and_sort = [&]() {
-            ull v[8];
             const unsigned e = x0 >> lpv;                 // all 8 slots share a segment when Pv >= 8
             if (Pv >= 8) {
                 const unsigned se = sz[e], i0 = x0 & (Pv - 1);
                 uint32_t ids[8];
-                const uint4 ia = *(const uint4*)(sidx + x0), ib = *(const uint4*)(sidx + x0 + 4);
-                ids[0] = ia.x; ids[1] = ia.y; ids[2] = ia.z; ids[3] = ia.w; ids[4] = ib.x; ids[5] = ib.y; ids[6] = ib.z; ids[7] = ib.w;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) ids[q] = sidx[q * NT + tid];
 #pragma unroll
                 for (int q = 0; q < 8; ++q) v[q] = (i0 + q < se) ? kl[ids[q]] : 0ull;      // 8 independent loads in flight
 #pragma unroll
@@ -1136,16 +1141,14 @@ __global__ void __launch_bounds__(NT) k_bottom3(BottomArgs A) {
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                     const unsigned x = x0 + q, eq = x >> lpv, i = x & (Pv - 1);
-                    v[q] = (i < sz[eq]) ? ((kl[sidx[x]] & ~0xffffull) | x) : W_SENT;
+                    v[q] = (i < sz[eq]) ? ((kl[sidx[q * NT + tid]] & ~0xffffull) | x) : W_SENT;
                 }
             }
             __syncthreads();                              // every thread has read sidx/w before w is reused
             sort_regs<NT>(v, w, Pv);
             __syncthreads();                              // other threads may still be reading the transposed staging
-            *(ulonglong2*)(w + x0) = make_ulonglong2(v[0], v[1]);
-            *(ulonglong2*)(w + x0 + 2) = make_ulonglong2(v[2], v[3]);
-            *(ulonglong2*)(w + x0 + 4) = make_ulonglong2(v[4], v[5]);
-            *(ulonglong2*)(w + x0 + 6) = make_ulonglong2(v[6], v[7]);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) w[q * NT + tid] = v[q];
             __syncthreads();
         };
         gather_and_sort();
@@ -1158,7 +1161,8 @@ __global__ void __launch_bounds__(NT) k_bottom3(BottomArgs A) {
                 const unsigned slot = x0 + q;
                 if (slot + 1 < P0) {
                     const unsigned e = slot >> lpv, i = slot & (Pv - 1);
-                    if (i + 1 < sz[e]) f |= ((w[slot] >> 16) == (w[slot + 1] >> 16));
+                    const ull nxt = q < 7 ? v[q < 7 ? q + 1 : 7] : w[tid + 1];          // slot + 1 = first slot of thread tid + 1
+                    if (i + 1 < sz[e]) f |= ((v[q] >> 16) == (nxt >> 16));
                 }
             }
             return __syncthreads_or(f);
@@ -1182,10 +1186,10 @@ __global__ void __launch_bounds__(NT) k_bottom3(BottomArgs A) {
                         if (slot + 1 < P0) {
                             const unsigned e = slot >> lpv, i = slot & (Pv - 1);
                             if (i + 1 < sz[e]) {
-                                const ull a = w[slot], b = w[slot + 1];
+                                const ull a = w[TI(slot)], b = w[TI(slot + 1)];
                                 if ((a >> 16) == (b >> 16)) {
-                                    const ull fa = kl[sidx[a & 0xffff]], fb = kl[sidx[b & 0xffff]];
-                                    if (fa > fb || (fa == fb && (a & 0xffff) > (b & 0xffff))) { w[slot] = b; w[slot + 1] = a; swapped = 1; }
+                                    const ull fa = kl[sidx[TI((unsigned)(a & 0xffff))]], fb = kl[sidx[TI((unsigned)(b & 0xffff))]];
+                                    if (fa > fb || (fa == fb && (a & 0xffff) > (b & 0xffff))) { w[TI(slot)] = b; w[TI(slot + 1)] = a; swapped = 1; }
                                 }
                             }
                         }
@@ -1194,6 +1198,8 @@ __global__ void __launch_bounds__(NT) k_bottom3(BottomArgs A) {
                 }
                 if (!__syncthreads_or(swapped)) break;
             }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = w[q * NT + tid];      // the registers follow the repaired order
         }
 
         // ---- thresholds / margins at the sorted positions (Internal.hs:496-503)
@@ -1201,7 +1207,7 @@ __global__ void __launch_bounds__(NT) k_bottom3(BottomArgs A) {
             const unsigned se = sz[e];
             if (!se) continue;
             const unsigned off = e << lpv, nh = se >> 1;
-            auto full = [&](unsigned slot) { return kl[sidx[w[slot] & 0xffff]]; };
+            auto full = [&](unsigned slot) { return kl[sidx[TI((unsigned)(w[TI(slot)] & 0xffff))]]; };
             const ull th = full(off + nh);
             ull ml, mh;
             if (se >= 3) { ml = full(off + nh - 1); mh = full(off + nh + 1); }
@@ -1240,13 +1246,13 @@ __global__ void __launch_bounds__(NT) k_bottom3(BottomArgs A) {
                 const unsigned e = slot >> lpv, i = slot & (Pv - 1), se = sz[e];
                 if (i < se) {
                     const unsigned nh = se >> 1;
-                    val[q] = sidx[w[slot] & 0xffff];
+                    val[q] = sidx[TI((unsigned)(v[q] & 0xffff))];
                     dst[q] = i < nh ? slot : (e << lpv) + (Pv >> 1) + (i - nh);
                 }
             }
             __syncthreads();
 #pragma unroll
-            for (int q = 0; q < 8; ++q) if (dst[q] != 0xffffffffu) sidx[dst[q]] = val[q];
+            for (int q = 0; q < 8; ++q) if (dst[q] != 0xffffffffu) sidx[TI(dst[q])] = val[q];
         }
         any_internal = __syncthreads_or(any_internal);
         if (!can_grow) break;      // unreachable for the shapes the host routes here
@@ -1258,7 +1264,7 @@ __global__ void __launch_bounds__(NT) k_bottom3(BottomArgs A) {
             for (int q = 0; q < 8; ++q) {
                 const unsigned slot = x0 + q;
                 const unsigned c = slot >> lpc, i = slot & (Pc - 1);
-                if (i < t_lsz[c]) perm[t_ps[nxt][c] + i] = sidx[slot];
+                if (i < t_lsz[c]) perm[t_ps[nxt][c] + i] = sidx[q * NT + tid];
             }
         }
         __syncthreads();
