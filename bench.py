@@ -131,6 +131,8 @@ def run_ours(args):
             raise SystemExit("launch with torchrun for --gpus > 1")
     dist = None
     if world > 1:
+        # NCCL writes its banner / debug lines to stdout by default; stdout is reserved for the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))

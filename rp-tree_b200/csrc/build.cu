@@ -30,13 +30,23 @@
 // fetched once (one 16-byte uniform load from the packed CSR) and feeds R independent mul/add chains.
 // Output row j corresponds to CSR row (t0 + j / L) * hpDepth + (j % L).
 // ORD: write order-preserving uint64 keys and track the per-row min/max (bin ranges of the top phase).
-template <int NT, int R, bool ORD>
-__global__ void __launch_bounds__(NT) k_project(const double* __restrict__ X, int64_t n, int d, int ld,
+template <int OFF>
+__device__ __forceinline__ double lds_f64_off(unsigned a) {
+    double x;
+    asm("ld.shared.f64 %0, [%1+%2];" : "=d"(x) : "r"(a), "n"(OFF));
+    return x;
+}
+
+// LD: compile-time row stride in doubles (0 = use the run-time ld): with it the R row addresses of a term are ONE add plus
+// immediate offsets.  hp_pack holds (value, byte offset of the component inside a row = 8 * idx).
+template <int NT, int R, bool ORD, int LD>
+__global__ void __launch_bounds__(NT) k_project(const double* __restrict__ X, int64_t n, int d, int ld_rt,
                                                  const int64_t* __restrict__ hp_off, const double2* __restrict__ hp_pack,
                                                  int t0, int L, int hpDepth, int H,
                                                  void* __restrict__ out, int64_t ostride, ull* __restrict__ kmin, ull* __restrict__ kmax) {
     constexpr int P = 32 * R, NW = NT / 32;
     extern __shared__ double xs[];
+    const int ld = LD ? LD : ld_rt;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int64_t i0 = (int64_t)blockIdx.x * P;
     const int rows = (int)min((int64_t)P, n - i0);
@@ -53,6 +63,10 @@ __global__ void __launch_bounds__(NT) k_project(const double* __restrict__ X, in
     unsigned rowaddr[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) rowaddr[r] = (unsigned)__cvta_generic_to_shared(xs + (size_t)(lane + 32 * r) * ld);
+    // The per-row key range only seeds the bin map of the top phase (keys outside it fall into the first / last bin, the
+    // exact select inside the median bin does the rest), so it is taken from every 8th tile: the warp reduction below
+    // costs about as much as four terms of the dot product.
+    const bool track = (blockIdx.x & 7) == 0;
     // write one output row (and fold its min/max) -- warp-uniform call
     auto emit = [&](int j, const double (&acc)[R]) {
         if (ORD) {
@@ -67,6 +81,7 @@ __global__ void __launch_bounds__(NT) k_project(const double* __restrict__ X, in
                     vmax = o > vmax ? o : vmax;
                 }
             }
+            if (!track) return;
             for (int off = 16; off > 0; off >>= 1) {
                 const ull a2 = __shfl_xor_sync(0xffffffffu, vmin, off), b2 = __shfl_xor_sync(0xffffffffu, vmax, off);
                 vmin = a2 < vmin ? a2 : vmin;
@@ -86,10 +101,19 @@ __global__ void __launch_bounds__(NT) k_project(const double* __restrict__ X, in
     };
     // one term of one hyperplane for this lane's R points: acc = val * x[idx] + acc  (separate roundings, right fold)
     auto term = [&](const double2 hv, double (&acc)[R]) {
-        const unsigned c = (unsigned)__double_as_longlong(hv.y) << 3;
+        const unsigned c = (unsigned)__double_as_longlong(hv.y);
         double x[R];
+        if constexpr (LD != 0) {
+            const unsigned a0 = rowaddr[0] + c;
+            x[0] = lds_f64_off<0>(a0);
+            if constexpr (R > 1) x[1] = lds_f64_off<1 * 32 * LD * 8>(a0);
+            if constexpr (R > 2) x[2] = lds_f64_off<2 * 32 * LD * 8>(a0);
+            if constexpr (R > 3) x[3] = lds_f64_off<3 * 32 * LD * 8>(a0);
+            static_assert(R <= 4, "extend the immediate-offset loads");
+        } else {
 #pragma unroll
-        for (int r = 0; r < R; ++r) asm("ld.shared.f64 %0, [%1];" : "=d"(x[r]) : "r"(rowaddr[r] + c));
+            for (int r = 0; r < R; ++r) asm("ld.shared.f64 %0, [%1];" : "=d"(x[r]) : "r"(rowaddr[r] + c));
+        }
 #pragma unroll
         for (int r = 0; r < R; ++r) acc[r] = __dadd_rn(__dmul_rn(hv.x, x[r]), acc[r]);
     };
@@ -109,14 +133,19 @@ __global__ void __launch_bounds__(NT) k_project(const double* __restrict__ X, in
         double accA[R], accB[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) { accA[r] = 0.0; accB[r] = 0.0; }
-        while (cA > 0 && cB > 0) {
-            const double2 a = __ldg(hA), b2 = __ldg(hB);
+        // the (value, offset) pair of the NEXT term is requested before the current term's loads and adds are issued
+        double2 a = cA > 0 ? __ldg(hA) : make_double2(0.0, 0.0), b2 = cB > 0 ? __ldg(hB) : make_double2(0.0, 0.0);
+        while (cA > 1 && cB > 1) {
+            const double2 an = __ldg(hA - 1), bn = __ldg(hB - 1);
             --hA; --hB; --cA; --cB;
             term(a, accA);
             term(b2, accB);
+            a = an; b2 = bn;
         }
-        while (cA > 0) { const double2 a = __ldg(hA); --hA; --cA; term(a, accA); }
-        while (cB > 0) { const double2 b2 = __ldg(hB); --hB; --cB; term(b2, accB); }
+        while (cA > 1) { const double2 an = __ldg(hA - 1); --hA; --cA; term(a, accA); a = an; }
+        while (cB > 1) { const double2 bn = __ldg(hB - 1); --hB; --cB; term(b2, accB); b2 = bn; }
+        if (cA > 0) term(a, accA);
+        if (cB > 0) term(b2, accB);
         emit(j, accA);
         if (hasB) emit(jB, accB);
     }
@@ -140,7 +169,7 @@ __global__ void __launch_bounds__(256) k_project_direct(const double* __restrict
         double acc = 0.0;
         for (int64_t q = e - 1; q >= s; --q) {
             const double2 hv = __ldg(hp_pack + q);
-            acc = __dadd_rn(__dmul_rn(hv.x, __ldg(xr + (int)__double_as_longlong(hv.y))), acc);
+            acc = __dadd_rn(__dmul_rn(hv.x, __ldg(xr + (int)(__double_as_longlong(hv.y) >> 3))), acc);
         }
         if (ORD) {
             const ull o = f2ord(acc);
@@ -161,11 +190,11 @@ __global__ void __launch_bounds__(256) k_project_direct(const double* __restrict
     }
 }
 
-template <int NT, int R, bool ORD>
+template <int NT, int R, bool ORD, int LD = 0>
 static int launch_project(rpf_handle* h, int phase, const double* dX, int64_t n, int t0, int L, int H, void* out, int64_t ostride, ull* kmin, ull* kmax) {
     const int d = h->d, ld = d | 1;
     const size_t smem = (size_t)32 * R * ld * sizeof(double);
-    auto kfn = k_project<NT, R, ORD>;
+    auto kfn = k_project<NT, R, ORD, LD>;
     RPF_CUDA(h, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t grid = (n + 32 * R - 1) / (32 * R);
     RPF_LAUNCH(h, phase, kfn, (unsigned)grid, NT, smem, dX, n, d, ld, h->d_hp_off, (const double2*)h->d_hp_pack, t0, L, h->hpDepth, H, out, ostride, kmin, kmax);
@@ -185,6 +214,9 @@ int rpf_project_launch(rpf_handle* h, int phase, const double* dX, int64_t n, in
     if (h->project_variant == 2 && 128 * row <= 140 * 1024)
         return ord ? launch_project<512, 4, true>(h, phase, dX, n, t0, L, H, out, ostride, kmin, kmax)
                    : launch_project<512, 4, false>(h, phase, dX, n, t0, L, H, out, ostride, kmin, kmax);
+    if (ld == 129)      // d = 128: compile-time row stride
+        return ord ? launch_project<1024, 4, true, 129>(h, phase, dX, n, t0, L, H, out, ostride, kmin, kmax)
+                   : launch_project<1024, 4, false, 129>(h, phase, dX, n, t0, L, H, out, ostride, kmin, kmax);
     if (128 * row <= 140 * 1024)
         return ord ? launch_project<1024, 4, true>(h, phase, dX, n, t0, L, H, out, ostride, kmin, kmax)
                    : launch_project<1024, 4, false>(h, phase, dX, n, t0, L, H, out, ostride, kmin, kmax);

@@ -229,8 +229,8 @@ static int upload_hyperplanes(rpf_handle* h) {
         std::vector<double> pack(nnz * 2);
         for (size_t q = 0; q < nnz; ++q) {
             pack[2 * q] = h->hp_val[q];
-            const int64_t ib = (int64_t)h->hp_idx[q];
-            std::memcpy(&pack[2 * q + 1], &ib, 8);      // index travels in the bit pattern of the second double
+            const int64_t ib = (int64_t)h->hp_idx[q] * 8;
+            std::memcpy(&pack[2 * q + 1], &ib, 8);      // byte offset of the component (8 * index) in the bit pattern of the second double
         }
         RPF_CUDA(h, cudaMemcpy(h->d_hp_pack, pack.data(), nnz * 16, cudaMemcpyHostToDevice));
     }
