@@ -381,14 +381,21 @@ struct TopArgs {
     NodeSel* sel;
     ull* cand;
     uint32_t* cand_total;
+    uint32_t* wl_cnt;                // [2] work-list lengths of this level: big median bins (k_top_finish), straddling ties (k_top_ties)
+    uint32_t* wl_big;                // [Tg * nnodes] entries t * nnodes + nl
+    uint32_t* wl_tie;
     ull* pivots;
     uint32_t* fill;
     uint32_t* perm;
     double *thr, *mlo, *mhi;
 };
 
-#define TOP_CH 32768      /* points per CTA in the streaming top-phase kernels */
+#ifndef TOP_CH
+#define TOP_CH 32768      /* points per CTA in the streaming top-phase kernels (<= 65535: 16-bit histogram counters) */
+#endif
+#ifndef TOP_NT
 #define TOP_NT 512
+#endif
 #define HBINS 32768       /* shared-memory histogram counters (16-bit, two per word; a CTA streams TOP_CH <= 65535 points) */
 #define HBINS_MAXNB 16384
 #define FIN_CAP 4096      /* in-bin sort capacity */
@@ -533,6 +540,39 @@ __global__ void __launch_bounds__(256) k_top_pick(TopArgs A) {
     }
 }
 
+// same, one WARP per (node, tree): the deep top levels have thousands of nodes with <= 256 bins each
+__global__ void __launch_bounds__(256) k_top_pick_warp(TopArgs A) {
+    const int lane = threadIdx.x & 31;
+    const int64_t item = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (item >= (int64_t)A.nnodes * A.Tg) return;
+    const int t = (int)(item / A.nnodes), nl = (int)(item % A.nnodes), g = A.node0 + nl;
+    if (A.child[g] < 0) return;
+    const uint32_t k = A.nsize[g] >> 1;
+    const uint32_t* hr = A.hist + (int64_t)t * A.HSZ + (int64_t)nl * A.NB;
+    const int per = (A.NB + 31) / 32;              // <= 8
+    const int b0 = lane * per, b1 = min(A.NB, b0 + per);
+    uint32_t loc[8], s = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { loc[j] = (b0 + j < b1) ? hr[b0 + j] : 0u; s += loc[j]; }
+    uint32_t incl = s;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += y; }
+    const uint32_t excl = incl - s;
+    if (k >= excl && k < incl) {
+        uint32_t c = excl;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (k < c + loc[j]) {
+                NodeSel& S = A.sel[(int64_t)t * A.NTOP + g];
+                S.sel_bin = b0 + j; S.below = c; S.cand_cnt = loc[j]; S.cand_fill = 0;
+                S.cand_off = atomicAdd(&A.cand_total[t], loc[j]);
+                break;
+            }
+            c += loc[j];
+        }
+    }
+}
+
 __global__ void __launch_bounds__(TOP_NT) k_top_compact(TopArgs A) {
     __shared__ int s_bin[SMEM_NODES];
     const int t = blockIdx.y, tid = threadIdx.x;
@@ -571,7 +611,10 @@ __global__ void __launch_bounds__(FW_WARPS * 32) k_top_finish_warp(TopArgs A) {
     if (A.child[g] < 0) return;
     NodeSel& S = A.sel[(int64_t)t * A.NTOP + g];
     const uint32_t c = S.cand_cnt, nh = A.nsize[g] >> 1, r = nh - S.below;
-    if (c > FW_MAX) return;
+    if (c > FW_MAX) {                             // rare: handed to k_top_finish through the work list
+        if (lane == 0) A.wl_big[atomicAdd(&A.wl_cnt[0], 1u)] = (uint32_t)item;
+        return;
+    }
     const ull* seg = A.cand + (int64_t)t * A.n + S.cand_off;
     ull v[8];
 #pragma unroll
@@ -593,22 +636,27 @@ __global__ void __launch_bounds__(FW_WARPS * 32) k_top_finish_warp(TopArgs A) {
         S.cless = S.below + lower; S.ceq = eq;
         S.tie_r = nh - S.cless;
         S.tie_depth = 0;
+        if (S.tie_r > 0) A.wl_tie[atomicAdd(&A.wl_cnt[1], 1u)] = (uint32_t)item;
         const bool need_pred = (S.cless == nh) && pred == ORD_NONE_LO;
         const bool need_succ = (S.cless + eq == nh + 1) && succ == ORD_NONE_HI;
         if (need_pred || need_succ) atomicOr(&A.track_any[t], 1u);
     }
 }
 
-// one CTA per (node, tree): exact order statistic inside the median bin (bins with more than FW_MAX keys)
+// exact order statistic inside the median bin for the bins with more than FW_MAX keys: the CTAs walk the work list
+// k_top_finish_warp filled (a grid of one CTA per node would spend the deep levels launching CTAs that return at once)
 __global__ void __launch_bounds__(512) k_top_finish(TopArgs A) {
     __shared__ ull buf[FIN_CAP];
     __shared__ uint32_t sh[264];
     __shared__ ull sh64[3];
-    const int t = blockIdx.y, nl = blockIdx.x, g = A.node0 + nl, tid = threadIdx.x;
-    if (A.child[g] < 0) return;
+    const int tid = threadIdx.x;
+    const uint32_t nwork = A.wl_cnt[0];
+    for (uint32_t wi = blockIdx.x; wi < nwork; wi += gridDim.x) {
+    const uint32_t item = A.wl_big[wi];
+    const int t = (int)(item / A.nnodes), nl = (int)(item % A.nnodes), g = A.node0 + nl;
+    __syncthreads();                              // shared buffers are reused from the previous work item
     NodeSel& S = A.sel[(int64_t)t * A.NTOP + g];
     const uint32_t c = S.cand_cnt, nh = A.nsize[g] >> 1, r = nh - S.below;
-    if (c <= FW_MAX) return;                      // small bins are finished by k_top_finish_warp (one warp per node)
     const ull* seg = A.cand + (int64_t)t * A.n + S.cand_off;
     ull thr, pred = ORD_NONE_LO, succ = ORD_NONE_HI;
     uint32_t lower, ceq;
@@ -648,11 +696,13 @@ __global__ void __launch_bounds__(512) k_top_finish(TopArgs A) {
         S.cless = S.below + lower; S.ceq = ceq;
         S.tie_r = nh - S.cless;      // tied points that must go left; > 0 => the split cuts through a tie
         S.tie_depth = 0;
+        if (S.tie_r > 0) A.wl_tie[atomicAdd(&A.wl_cnt[1], 1u)] = item;
         // sorted[nh-1] / sorted[nh+1] are taken from the bin's sorted keys; only when they fall outside the bin must
         // k_top_relabel track the nearest keys below / above the threshold over all points of the node
         const bool need_pred = (S.cless == nh) && pred == ORD_NONE_LO;
         const bool need_succ = (S.cless + ceq == nh + 1) && succ == ORD_NONE_HI;
         if (need_pred || need_succ) atomicOr(&A.track_any[t], 1u);
+    }
     }
 }
 
@@ -663,10 +713,13 @@ __global__ void __launch_bounds__(512) k_top_ties(TopArgs A) {
     __shared__ uint32_t sh[264];
     __shared__ ull sh64[1];
     __shared__ uint32_t cnt;
-    const int t = blockIdx.y, nl = blockIdx.x, g = A.node0 + nl, tid = threadIdx.x;
-    if (A.child[g] < 0) return;
+    const int tid = threadIdx.x;
+    const uint32_t nwork = A.wl_cnt[1];
+    for (uint32_t wi = blockIdx.x; wi < nwork; wi += gridDim.x) {
+    const uint32_t item = A.wl_tie[wi];
+    const int t = (int)(item / A.nnodes), nl = (int)(item % A.nnodes), g = A.node0 + nl;
+    __syncthreads();
     NodeSel& S = A.sel[(int64_t)t * A.NTOP + g];
-    if (S.tie_r == 0) return;
     const ull* keys_t = A.keys + (int64_t)t * A.L * A.ks;
     const ull* keys_l = keys_t + (int64_t)A.l * A.ks;
     const uint16_t* lab = A.label + (int64_t)t * A.n;
@@ -704,11 +757,15 @@ __global__ void __launch_bounds__(512) k_top_ties(TopArgs A) {
         __syncthreads();
     }
     if (tid == 0) S.tie_depth = depth;
+    }
 }
 
 // relabel every point of an internal level-l node to its child; track the keys adjacent to the threshold
 // (margins); at the last top level also scatter the points into the per-node segments of perm.
-__global__ void __launch_bounds__(TOP_NT) k_top_relabel(TopArgs A, int last) {
+#ifndef RELABEL_MINB
+#define RELABEL_MINB 2
+#endif
+__global__ void __launch_bounds__(TOP_NT, RELABEL_MINB) k_top_relabel(TopArgs A, int last) {
     __shared__ ull s_thr[SMEM_NODES], s_pred[SMEM_NODES], s_succ[SMEM_NODES];
     __shared__ uint32_t s_tie[SMEM_NODES];
     __shared__ uint32_t s_cnt[SCAT_MAX], s_base[SCAT_MAX];
@@ -1479,7 +1536,11 @@ int rpf_launch_job(rpf_handle* h, BuildJob& J, const JobPlan& P, const char* tab
         uint32_t* hist = (uint32_t*)h->ws_get(WS_HIST, (size_t)tg * HSZ * 4);
         NodeSel* sel = (NodeSel*)h->ws_get(WS_SEL, (size_t)tg * NTOP * sizeof(NodeSel));
         ull* cand = (ull*)h->ws_get(WS_CAND, (size_t)tg * n * 8);
-        uint32_t* cand_total = (uint32_t*)h->ws_get(WS_CANDTOT, (size_t)tg * 8);      // [tg] candidate totals + [tg] margin-tracking flags
+        uint32_t* cand_total = (uint32_t*)h->ws_get(WS_CANDTOT, (size_t)tg * 8 + 8);  // [tg] candidate totals + [tg] margin-tracking flags + 2 work-list lengths
+        uint32_t max_lvl_nodes = 1;
+        for (int l = 0; l < s_top; ++l) max_lvl_nodes = std::max<uint32_t>(max_lvl_nodes, (uint32_t)(P.level_off[l + 1] - P.level_off[l]));
+        uint32_t* wl = (uint32_t*)h->ws_get(WS_WORKLIST, (size_t)tg * max_lvl_nodes * 8);
+        if (!wl) return RPF_ERR_NOMEM;
         ull* pivots = (ull*)h->ws_get(WS_PIVOTS, (size_t)tg * NTOP * MAXTD * 8);
         uint32_t* fill = (uint32_t*)h->ws_get(WS_FILL, (size_t)tg * NTOP * 4);
         double* binlo = (double*)h->ws_get(WS_BINLO, (size_t)tg * J.Lk * 8);
@@ -1492,6 +1553,7 @@ int rpf_launch_job(rpf_handle* h, BuildJob& J, const JobPlan& P, const char* tab
         A.nsize = J.d_size; A.binlo = binlo; A.binscale = binscale;
         A.kmin = J.kmin; A.kmax = J.kmax; A.hist = hist; A.sel = sel;
         A.cand = cand; A.cand_total = cand_total; A.track_any = cand_total + tg; A.pivots = pivots;
+        A.wl_cnt = cand_total + 2 * tg; A.wl_big = wl; A.wl_tie = wl + (size_t)tg * max_lvl_nodes;
         A.fill = fill; A.perm = J.perm; A.thr = J.thr; A.mlo = J.mlo; A.mhi = J.mhi;
         RPF_CUDA(h, cudaFuncSetAttribute(k_top_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, HBINS * 2));
         RPF_LAUNCH(h, PH_MISC, k_bin_setup, (unsigned)((tg * J.Lk + 127) / 128), 128, 0, A, nbdev, s_top);
@@ -1508,15 +1570,17 @@ int rpf_launch_job(rpf_handle* h, BuildJob& J, const JobPlan& P, const char* tab
             all_top_internal = all_top_internal && A.all_internal;
             A.scatter_fast = (all_top_internal && 2 * A.nnodes <= SCAT_MAX) ? 1 : 0;
             RPF_CUDA(h, cudaMemsetAsync(hist, 0, (size_t)tg * HSZ * 4, h->stream));
-            RPF_CUDA(h, cudaMemsetAsync(cand_total, 0, (size_t)tg * 8, h->stream));
+            RPF_CUDA(h, cudaMemsetAsync(cand_total, 0, (size_t)tg * 8 + 8, h->stream));
             dim3 gs(nchunks, (unsigned)tg), gn((unsigned)A.nnodes, (unsigned)tg);
             const size_t hs = A.smem_hist ? ((size_t)A.nnodes * A.NB + 1) / 2 * 4 : 0;     // 16-bit counters
             RPF_LAUNCH(h, PH_TOP_HIST, k_top_hist, gs, TOP_NT, hs, A);
-            RPF_LAUNCH(h, PH_TOP_PICK, k_top_pick, gn, 256, 0, A);
+            if (A.NB <= 256) RPF_LAUNCH(h, PH_TOP_PICK, k_top_pick_warp, (unsigned)(((int64_t)A.nnodes * tg + 7) / 8), 256, 0, A);
+            else RPF_LAUNCH(h, PH_TOP_PICK, k_top_pick, gn, 256, 0, A);
             RPF_LAUNCH(h, PH_TOP_COMPACT, k_top_compact, gs, TOP_NT, 0, A);
             RPF_LAUNCH(h, PH_TOP_FINISH, k_top_finish_warp, (unsigned)(((int64_t)A.nnodes * tg + FW_WARPS - 1) / FW_WARPS), FW_WARPS * 32, 0, A);
-            RPF_LAUNCH(h, PH_TOP_FINISH, k_top_finish, gn, 512, 0, A);
-            RPF_LAUNCH(h, PH_TOP_TIES, k_top_ties, gn, 512, 0, A);
+            const unsigned gw = (unsigned)std::min<int64_t>((int64_t)A.nnodes * tg, 592);      // work-list walkers
+            RPF_LAUNCH(h, PH_TOP_FINISH, k_top_finish, gw, 512, 0, A);
+            RPF_LAUNCH(h, PH_TOP_TIES, k_top_ties, gw, 512, 0, A);
             RPF_LAUNCH(h, PH_TOP_RELABEL, k_top_relabel, gs, TOP_NT, 0, A, (int)(l == s_top - 1));
             RPF_LAUNCH(h, PH_MISC, k_top_finalize, (unsigned)((A.nnodes * tg + 127) / 128), 128, 0, A);
         }

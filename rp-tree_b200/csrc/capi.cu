@@ -78,16 +78,22 @@ int rpf_handle::stage_begin(size_t bytes) {
     if (S.pending) { cudaEventSynchronize(S.ev); S.pending = false; }      // the slot's previous upload has left host memory
     bytes += 4096;
     if (S.cap < bytes) {
-        // kernels of an earlier job may still read the old device block: cudaFree waits for them (growth is rare)
-        if (S.h) cudaFreeHost(S.h);
-        if (S.d) cudaFree(S.d);
-        S.h = nullptr; S.d = nullptr; S.cap = 0;
+        // Grow EVERY slot now (one burst of page-locked allocations on the first build of a shape) instead of one slot per
+        // call, which would put an allocation into each of the next RPF_STAGE_SLOTS builds.  Kernels of earlier jobs may
+        // still read the old device blocks: synchronise first (growth is rare).
+        cudaStreamSynchronize(stream);
         const size_t want = bytes + bytes / 4;
-        if (cudaMallocHost(&S.h, want) != cudaSuccess || cudaMalloc(&S.d, want) != cudaSuccess) {
-            cudaGetLastError();
-            return rpf_fail(this, RPF_ERR_NOMEM, "stage: allocation failed");
+        for (auto& Q : stage) {
+            if (Q.cap >= want) continue;
+            if (Q.h) cudaFreeHost(Q.h);
+            if (Q.d) cudaFree(Q.d);
+            Q.h = nullptr; Q.d = nullptr; Q.cap = 0; Q.pending = false;
+            if (cudaMallocHost(&Q.h, want) != cudaSuccess || cudaMalloc(&Q.d, want) != cudaSuccess) {
+                cudaGetLastError();
+                return rpf_fail(this, RPF_ERR_NOMEM, "stage: allocation failed");
+            }
+            Q.cap = want;
         }
-        S.cap = want;
     }
     stage_off = 0; stage_flushed = 0;
     return RPF_OK;
