@@ -21,6 +21,7 @@
 #include "rpf_device.cuh"
 #include <algorithm>
 #include <cstdio>
+#include <type_traits>
 
 // =====================================================================================================
 // K1  projections: key[h][i] = hp[h] . X[i]   (innerSD, right fold, no FMA)
@@ -268,40 +269,45 @@ __device__ void bitonic_keys(ull* buf, unsigned m) {
 // Thread t owns the 8 consecutive slots [8t, 8t+8) in registers.  Comparator distances 1,2,4 are register-to-register,
 // 8..128 are lane-to-lane shuffles inside the warp, >= 256 go through shared memory in a transposed layout
 // (slot x lives at (x & 7) * NT + (x >> 3), so consecutive threads touch consecutive words: no bank conflicts).
-__device__ __forceinline__ void ce_min_first(ull& a, ull& b) { if (a > b) { const ull t = a; a = b; b = t; } }
+template <typename W>
+__device__ __forceinline__ void ce_min_first(W& a, W& b) { if (a > b) { const W t = a; a = b; b = t; } }
 
-template <int K>
-__device__ __forceinline__ void flip_in(ull (&v)[8]) {      // mirror pairs inside blocks of K <= 8 registers
+template <int K, typename W>
+__device__ __forceinline__ void flip_in(W (&v)[8]) {      // mirror pairs inside blocks of K <= 8 registers
 #pragma unroll
     for (int e = 0; e < 8; ++e) { const int p = e ^ (K - 1); if (e < p) ce_min_first(v[e], v[p]); }
 }
-template <int J>
-__device__ __forceinline__ void half_in(ull (&v)[8]) {      // pairs (e, e+J), J in {1,2,4}
+template <int J, typename W>
+__device__ __forceinline__ void half_in(W (&v)[8]) {      // pairs (e, e+J), J in {1,2,4}
 #pragma unroll
     for (int e = 0; e < 8; ++e) if ((e & J) == 0) ce_min_first(v[e], v[e + J]);
 }
-__device__ __forceinline__ void flip_shfl(ull (&v)[8], unsigned g, unsigned lane) {   // block of g lanes (8g slots)
+template <typename W>
+__device__ __forceinline__ void flip_shfl(W (&v)[8], unsigned g, unsigned lane) {   // block of g lanes (8g slots)
     const bool lower = (lane & (g >> 1)) == 0;
-    ull o[8];
+    W o[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) o[e] = __shfl_xor_sync(0xffffffffu, v[7 - e], g - 1);
 #pragma unroll
     for (int e = 0; e < 8; ++e) { const bool lt = v[e] < o[e]; v[e] = (lt == lower) ? v[e] : o[e]; }
 }
-__device__ __forceinline__ void half_shfl(ull (&v)[8], unsigned jl, unsigned lane) {  // partner lane = lane ^ jl
+template <typename W>
+__device__ __forceinline__ void half_shfl(W (&v)[8], unsigned jl, unsigned lane) {  // partner lane = lane ^ jl
     const bool lower = (lane & jl) == 0;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-        const ull o = __shfl_xor_sync(0xffffffffu, v[e], jl);
+        const W o = __shfl_xor_sync(0xffffffffu, v[e], jl);
         const bool lt = v[e] < o;
         v[e] = (lt == lower) ? v[e] : o;
     }
 }
-__device__ __forceinline__ void tail_in(ull (&v)[8]) { half_in<4>(v); half_in<2>(v); half_in<1>(v); }
+template <typename W>
+__device__ __forceinline__ void tail_in(W (&v)[8]) { half_in<4>(v); half_in<2>(v); half_in<1>(v); }
 
-// sorts every aligned block of Pv slots (Pv a power of two, 2 <= Pv <= 8*NT) ascending; all threads must call
-template <int NT>
-__device__ void sort_regs(ull (&v)[8], ull* w, unsigned Pv) {
+// sorts every aligned block of Pv slots (Pv a power of two, 2 <= Pv <= 8*NT) ascending; all threads must call.
+// W = uint64 or uint32 sort words (the 32-bit form halves the compare / select / shuffle / shared-memory work).
+template <int NT, typename W>
+__device__ void sort_regs(W (&v)[8], W* w, unsigned Pv) {
     const unsigned tid = threadIdx.x, lane = tid & 31;
     flip_in<2>(v);
     if (Pv >= 4) { flip_in<4>(v); half_in<1>(v); }
@@ -324,7 +330,7 @@ __device__ void sort_regs(ull (&v)[8], ull* w, unsigned Pv) {
                 const unsigned blk = cc >> (lkt - 1), uo = cc & ((kt >> 1) - 1);
                 const unsigned u = (blk << lkt) + uo, up = (blk << lkt) + (kt - 1 - uo);
                 const unsigned ia = e * NT + u, ib = (7 - e) * NT + up;
-                const ull a = w[ia], b = w[ib];
+                const W a = w[ia], b = w[ib];
                 if (a > b) { w[ia] = b; w[ib] = a; }
             }
             __syncthreads();
@@ -334,7 +340,7 @@ __device__ void sort_regs(ull (&v)[8], ull* w, unsigned Pv) {
                     const unsigned e = c / (NT / 2), cc = c % (NT / 2);
                     const unsigned u = ((cc >> lj) << (lj + 1)) + (cc & (jt - 1));
                     const unsigned ia = e * NT + u, ib = ia + jt;
-                    const ull a = w[ia], b = w[ib];
+                    const W a = w[ia], b = w[ib];
                     if (a > b) { w[ia] = b; w[ib] = a; }
                 }
                 __syncthreads();
@@ -619,7 +625,7 @@ __global__ void __launch_bounds__(FW_WARPS * 32) k_top_finish_warp(TopArgs A) {
     ull v[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) { const uint32_t i = lane * 8 + e; v[e] = i < c ? seg[i] : 0xffffffffffffffffull; }
-    sort_regs<32>(v, nullptr, FW_MAX);
+    sort_regs<32, ull>(v, (ull*)nullptr, FW_MAX);
 #pragma unroll
     for (int e = 0; e < 8; ++e) buf[wi][lane * 8 + e] = v[e];
     __syncwarp();
@@ -1127,13 +1133,24 @@ __device__ __forceinline__ void bitonic_uniform(ull* w, unsigned nslots, unsigne
     }
 }
 
-template <int NT, int TAB>
+// Sort word W: uint64 = (top 48 key bits | 16-bit slot), or -- for P0 <= 2048 -- uint32 = (PB-bit key prefix | lp0-bit slot)
+// with the prefix taken from the key's position inside the (tree, level) key range.  Elements whose prefixes collide are
+// put in exact (full key, incoming slot) order by the neighbour fix-up below, so both forms give the same result; the
+// 32-bit form halves the compare/select, shuffle and shared-memory work of the network.
+template <int NT, int TAB, typename W>
 __global__ void __launch_bounds__(NT) k_bottom3(BottomArgs A) {
     constexpr unsigned P0 = 8 * NT;               // slots (>= node size), 8 per thread
     constexpr int lp0 = (NT == 32 ? 8 : NT == 64 ? 9 : NT == 128 ? 10 : NT == 256 ? 11 : NT == 512 ? 12 : 13);
+    constexpr bool W32 = sizeof(W) == 4;
+    constexpr int SB = W32 ? lp0 : 16;            // slot bits of a sort word
+    constexpr int PB = 32 - lp0;                  // key-prefix bits of a 32-bit word
+    constexpr unsigned SMASK = (1u << SB) - 1u;
+    constexpr W WSENT = (W)~(W)0;
+    static_assert(!W32 || lp0 <= 11, "32-bit sort words need at least 21 prefix bits");
     extern __shared__ unsigned char smraw[];
-    ull* w = (ull*)smraw;                         // [P0] sort words
-    uint32_t* sidx = (uint32_t*)(w + P0);         // [P0] row id held by each slot
+    W* w = (W*)smraw;                             // [P0] sort words (the block is sized for 8-byte words: composite_sort
+    ull* w64 = (ull*)smraw;                       //      uses it as linear uint64 scratch)
+    uint32_t* sidx = (uint32_t*)(w64 + P0);       // [P0] row id held by each slot
     __shared__ uint16_t t_sz[2][TAB];        // size of the segment if it splits at this level, else 0
     __shared__ uint16_t t_ps[2][TAB];        // offset of the segment inside this CTA's slice of perm
     __shared__ int32_t t_gid[2][TAB];        // BFS id
@@ -1160,7 +1177,7 @@ __global__ void __launch_bounds__(NT) k_bottom3(BottomArgs A) {
     // (s > 0) AND either it is a Tip itself or its first sort hits a tie in the top 48 key bits.
     auto composite_sort = [&]() {
         const ull* k1 = keys_t + (int64_t)(A.s - 1) * n;
-        for (uint32_t p = tid; p < m; p += NT) w[p] = k1[sidx[TI(p)]];      // w is linear scratch inside this (rare) path
+        for (uint32_t p = tid; p < m; p += NT) w64[p] = k1[sidx[TI(p)]];    // linear uint64 scratch inside this (rare) path
         __syncthreads();
         auto after = [&](ull ka, uint32_t ia, ull kb, uint32_t ib) -> bool {
             if (ka != kb) return ka > kb;
@@ -1177,8 +1194,8 @@ __global__ void __launch_bounds__(NT) k_bottom3(BottomArgs A) {
                 const unsigned blk = c >> (lk - 1), x = c & ((k >> 1) - 1);
                 const unsigned i = (blk << lk) + x, p = (blk << lk) + (k - 1 - x);
                 if (p < m) {
-                    const ull a = w[i], b = w[p]; const uint32_t ia = sidx[TI(i)], ib = sidx[TI(p)];
-                    if (after(a, ia, b, ib)) { w[i] = b; w[p] = a; sidx[TI(i)] = ib; sidx[TI(p)] = ia; }
+                    const ull a = w64[i], b = w64[p]; const uint32_t ia = sidx[TI(i)], ib = sidx[TI(p)];
+                    if (after(a, ia, b, ib)) { w64[i] = b; w64[p] = a; sidx[TI(i)] = ib; sidx[TI(p)] = ia; }
                 }
             }
             __syncthreads();
@@ -1187,8 +1204,8 @@ __global__ void __launch_bounds__(NT) k_bottom3(BottomArgs A) {
                 for (unsigned c = tid; c < half; c += NT) {
                     const unsigned i = ((c >> lj) << (lj + 1)) + (c & (j - 1)), p = i + j;
                     if (p < m) {
-                        const ull a = w[i], b = w[p]; const uint32_t ia = sidx[TI(i)], ib = sidx[TI(p)];
-                        if (after(a, ia, b, ib)) { w[i] = b; w[p] = a; sidx[TI(i)] = ib; sidx[TI(p)] = ia; }
+                        const ull a = w64[i], b = w64[p]; const uint32_t ia = sidx[TI(i)], ib = sidx[TI(p)];
+                        if (after(a, ia, b, ib)) { w64[i] = b; w64[p] = a; sidx[TI(i)] = ib; sidx[TI(p)] = ia; }
                     }
                 }
                 __syncthreads();
@@ -1214,27 +1231,46 @@ __global__ void __launch_bounds__(NT) k_bottom3(BottomArgs A) {
         const uint16_t* sz = t_sz[cur];
 
         // ---- gather keys into registers, build sort words, sort, store back in slot order
-        ull v[8];                                         // this thread's 8 sort words (kept in registers across the level)
+        W v[8];                                           // this thread's 8 sort words (kept in registers across the level)
+        // 32-bit words: prefix = position of the key's VALUE inside the (tree, level) key range, PB bits (monotone: every
+        // step below is monotone non-decreasing in the key).  A prefix taken from the key's bit pattern would spend
+        // almost all codes on magnitudes near zero, where no projections live.
+        double plo = 0.0, psc = 0.0;
+        if (W32 && A.kmin) {
+            plo = ord2f(A.kmin[t * A.L + l]);
+            const double wdt = ord2f(A.kmax[t * A.L + l]) - plo;
+            psc = (wdt > 0.0 && isfinite(wdt)) ? (double)((1u << PB) - 2u) / wdt : 0.0;
+            if (!isfinite(psc)) psc = 0.0;
+        }
+        auto make_word = [&](ull key, unsigned slot) -> W {
+            if (W32) {
+                const double pv = (ord2f(key) - plo) * psc;
+                unsigned p = pv > 0.0 ? (unsigned)fmin(pv, (double)((1u << PB) - 2u)) : 0u;
+                return (W)((p << SB) | slot);
+            }
+            return (W)((key & ~0xffffull) | slot);
+        };
         auto gather_and_sort = [&]() {
             const unsigned e = x0 >> lpv;                 // all 8 slots share a segment when Pv >= 8
             if (Pv >= 8) {
                 const unsigned se = sz[e], i0 = x0 & (Pv - 1);
                 uint32_t ids[8];
+                ull kk[8];
 #pragma unroll
                 for (int q = 0; q < 8; ++q) ids[q] = sidx[q * NT + tid];
 #pragma unroll
-                for (int q = 0; q < 8; ++q) v[q] = (i0 + q < se) ? kl[ids[q]] : 0ull;      // 8 independent loads in flight
+                for (int q = 0; q < 8; ++q) kk[q] = (i0 + q < se) ? kl[ids[q]] : 0ull;      // 8 independent loads in flight
 #pragma unroll
-                for (int q = 0; q < 8; ++q) v[q] = (i0 + q < se) ? ((v[q] & ~0xffffull) | (x0 + q)) : W_SENT;
+                for (int q = 0; q < 8; ++q) v[q] = (i0 + q < se) ? make_word(kk[q], x0 + q) : WSENT;
             } else {
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                     const unsigned x = x0 + q, eq = x >> lpv, i = x & (Pv - 1);
-                    v[q] = (i < sz[eq]) ? ((kl[sidx[q * NT + tid]] & ~0xffffull) | x) : W_SENT;
+                    v[q] = (i < sz[eq]) ? make_word(kl[sidx[q * NT + tid]], x) : WSENT;
                 }
             }
             __syncthreads();                              // every thread has read sidx/w before w is reused
-            sort_regs<NT>(v, w, Pv);
+            sort_regs<NT, W>(v, w, Pv);
             __syncthreads();                              // other threads may still be reading the transposed staging
 #pragma unroll
             for (int q = 0; q < 8; ++q) w[q * NT + tid] = v[q];
@@ -1242,7 +1278,7 @@ __global__ void __launch_bounds__(NT) k_bottom3(BottomArgs A) {
         };
         gather_and_sort();
 
-        // ---- ties in the top 48 bits: re-check with full keys
+        // ---- neighbours with equal key prefixes: re-check with the full keys
         auto tie_flag = [&]() -> int {
             int f = 0;
 #pragma unroll
@@ -1250,23 +1286,16 @@ __global__ void __launch_bounds__(NT) k_bottom3(BottomArgs A) {
                 const unsigned slot = x0 + q;
                 if (slot + 1 < P0) {
                     const unsigned e = slot >> lpv, i = slot & (Pv - 1);
-                    const ull nxt = q < 7 ? v[q < 7 ? q + 1 : 7] : w[tid + 1];          // slot + 1 = first slot of thread tid + 1
-                    if (i + 1 < sz[e]) f |= ((v[q] >> 16) == (nxt >> 16));
+                    const W nxt = q < 7 ? v[q < 7 ? q + 1 : 7] : w[tid + 1];            // slot + 1 = first slot of thread tid + 1
+                    if (i + 1 < sz[e]) f |= ((v[q] >> SB) == (nxt >> SB));
                 }
             }
             return __syncthreads_or(f);
         };
-        int flag = tie_flag();
-        if (flag && need_check_order) {
-            // the incoming slot order was arbitrary: establish the reference's order first, then redo this level
-            composite_sort();
-            need_check_order = false;
-            gather_and_sort();
-            flag = tie_flag();
-        }
-        need_check_order = false;
-        if (flag) {
-            // exact comparator on neighbours: (full key, incoming slot); odd-even transposition until stable
+        // exact comparator on neighbours with equal prefixes: (full key, incoming slot); odd-even transposition until
+        // stable.  Returns whether two compared elements had EQUAL full keys (only then does the incoming order matter).
+        auto fix_up = [&]() -> int {
+            int eqfull = 0;
             while (true) {
                 int swapped = 0;
                 for (int par = 0; par < 2; ++par) {
@@ -1275,10 +1304,12 @@ __global__ void __launch_bounds__(NT) k_bottom3(BottomArgs A) {
                         if (slot + 1 < P0) {
                             const unsigned e = slot >> lpv, i = slot & (Pv - 1);
                             if (i + 1 < sz[e]) {
-                                const ull a = w[TI(slot)], b = w[TI(slot + 1)];
-                                if ((a >> 16) == (b >> 16)) {
-                                    const ull fa = kl[sidx[TI((unsigned)(a & 0xffff))]], fb = kl[sidx[TI((unsigned)(b & 0xffff))]];
-                                    if (fa > fb || (fa == fb && (a & 0xffff) > (b & 0xffff))) { w[TI(slot)] = b; w[TI(slot + 1)] = a; swapped = 1; }
+                                const W a = w[TI(slot)], b = w[TI(slot + 1)];
+                                if ((a >> SB) == (b >> SB)) {
+                                    const unsigned sa = (unsigned)(a & SMASK), sb2 = (unsigned)(b & SMASK);
+                                    const ull fa = kl[sidx[TI(sa)]], fb = kl[sidx[TI(sb2)]];
+                                    eqfull |= (fa == fb);
+                                    if (fa > fb || (fa == fb && sa > sb2)) { w[TI(slot)] = b; w[TI(slot + 1)] = a; swapped = 1; }
                                 }
                             }
                         }
@@ -1287,16 +1318,27 @@ __global__ void __launch_bounds__(NT) k_bottom3(BottomArgs A) {
                 }
                 if (!__syncthreads_or(swapped)) break;
             }
+            return __syncthreads_or(eqfull);
+        };
+        if (tie_flag()) {
+            const int eqfull = fix_up();
+            if (eqfull && need_check_order) {
+                // equal keys, and the incoming slot order was arbitrary: establish the reference's order, redo the level
+                composite_sort();
+                gather_and_sort();
+                if (tie_flag()) fix_up();
+            }
 #pragma unroll
             for (int q = 0; q < 8; ++q) v[q] = w[q * NT + tid];      // the registers follow the repaired order
         }
+        need_check_order = false;
 
         // ---- thresholds / margins at the sorted positions (Internal.hs:496-503)
         for (unsigned e = tid; e < nseg; e += NT) {
             const unsigned se = sz[e];
             if (!se) continue;
             const unsigned off = e << lpv, nh = se >> 1;
-            auto full = [&](unsigned slot) { return kl[sidx[TI((unsigned)(w[TI(slot)] & 0xffff))]]; };
+            auto full = [&](unsigned slot) { return kl[sidx[TI((unsigned)(w[TI(slot)] & SMASK))]]; };
             const ull th = full(off + nh);
             ull ml, mh;
             if (se >= 3) { ml = full(off + nh - 1); mh = full(off + nh + 1); }
@@ -1335,7 +1377,7 @@ __global__ void __launch_bounds__(NT) k_bottom3(BottomArgs A) {
                 const unsigned e = slot >> lpv, i = slot & (Pv - 1), se = sz[e];
                 if (i < se) {
                     const unsigned nh = se >> 1;
-                    val[q] = sidx[TI((unsigned)(v[q] & 0xffff))];
+                    val[q] = sidx[TI((unsigned)(v[q] & SMASK))];
                     dst[q] = i < nh ? slot : (e << lpv) + (Pv >> 1) + (i - nh);
                 }
             }
@@ -1380,7 +1422,8 @@ template <int NT, int TAB>
 static int launch_bottom_fast(rpf_handle* h, const BottomArgs& B, int nnodes_s, int tg) {
     dim3 grid((unsigned)nnodes_s, (unsigned)tg);
     const size_t smem = (size_t)NT * 8 * 12;
-    auto kfn = k_bottom3<NT, TAB>;
+    typedef typename std::conditional<(NT <= 256), uint32_t, ull>::type W;      // <= 2048 slots: 32-bit sort words
+    auto kfn = h->bottom_words64 ? k_bottom3<NT, TAB, ull> : k_bottom3<NT, TAB, W>;
     RPF_CUDA(h, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     RPF_CUDA(h, cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     RPF_LAUNCH(h, PH_BOTTOM, kfn, grid, NT, smem, B);
@@ -1595,6 +1638,7 @@ int rpf_launch_job(rpf_handle* h, BuildJob& J, const JobPlan& P, const char* tab
         B.given_order = 0;
         B.keys = J.keys; B.perm = J.perm; B.child = J.d_child; B.nstart = J.d_start; B.nsize = J.d_size;
         B.range = range; B.lvl_pv = lvlpv; B.thr = J.thr; B.mlo = J.mlo; B.mhi = J.mhi;
+        B.kmin = J.kmin; B.kmax = J.kmax;
         int rc = rpf_bottom_launch(h, B, P.nnodes_s, tg, G.fast_bottom, P.maxsize_s, G.bottom_levels);
         if (rc) return rc;
     }

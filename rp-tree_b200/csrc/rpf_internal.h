@@ -143,6 +143,7 @@ struct rpf_handle {
     bool no_query_order = false;         // test/tuning hook: answer queries in input order (no locality grouping)
     bool force_simple_knn = false;       // test hook: per-thread gather knn kernel instead of the TMA ring
     bool force_generic_bottom = false;   // test hook: run the generic (entry-table) bottom kernel
+    bool bottom_words64 = false;         // test hook: 64-bit sort words in the fast bottom kernel even for <= 2048 slots
 
     // staging ring
     StageSlot stage[RPF_STAGE_SLOTS];
@@ -236,6 +237,8 @@ struct BottomArgs {
     const uint32_t* nsize;
     const int2* range;                   // [nodes at level s][nlb]: BFS id range of the descendants that split
     const uint32_t* lvl_pv;              // per level: next_pow2(max node size)
+    const ull* kmin;                     // [Tg][L] key range per (tree, level) (may be a sample's range, may be NULL):
+    const ull* kmax;                     //         seeds the key prefixes of 32-bit sort words
     double *thr, *mlo, *mhi;
 };
 int rpf_bottom_launch(rpf_handle* h, const BottomArgs& B, int nroots, int tg, bool fast, unsigned max_root, int levels);

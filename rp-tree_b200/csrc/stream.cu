@@ -653,6 +653,7 @@ int rpf_build_stream_impl(rpf_handle* h, int maxDepth, int minLeaf, int64_t chun
                     A.range = GL.off_rg == (size_t)-1 ? nullptr : (const int2*)(tab + GL.off_rg);
                     A.lvl_pv = GL.off_pv == (size_t)-1 ? nullptr : (const uint32_t*)(tab + GL.off_pv);
                     A.thr = rthr; A.mlo = rmlo; A.mhi = rmhi;
+                    A.kmin = kmin; A.kmax = kmax;                 // range of the current batch's keys (a sample is enough)
                     rc = rpf_bottom_launch(h, A, G.count, tg, G.fast, G.max_root, G.levels);
                     if (rc) return rc;
                 }

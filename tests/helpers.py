@@ -15,6 +15,10 @@ def make_data(n, d, seed, kind="gauss"):
     if kind == "dupes":             # exact duplicate rows
         base = rng.normal(size=(max(n // 4, 1), d))
         return base[rng.integers(0, len(base), size=n)]
+    if kind == "outlier":           # one huge point stretches every key range: nearly all keys share their leading bits
+        X = rng.normal(size=(n, d))
+        X[n // 3] *= 1e9
+        return X
     raise ValueError(kind)
 
 

@@ -21,8 +21,8 @@ def _build_pair(n, d, T, maxd, minl, pnz, kind="gauss", cap=None, seed=3, generi
     R, orc = _mods()
     X = make_data(n, d, seed, kind)
     hp = orc.gen_hyperplanes(1235137 + seed, T, maxd, pnz, d)
-    f = R.forestBatch(0, maxd, minl, T, pnz, d, X, hyperplanes=hp, bottom_cap=cap,
-                      options={"force_generic_bottom": 1} if generic else None)
+    opts = {"force_generic_bottom": 1} if generic is True else ({"bottom_words64": 1} if generic == "words64" else None)
+    f = R.forestBatch(0, maxd, minl, T, pnz, d, X, hyperplanes=hp, bottom_cap=cap, options=opts)
     of = orc.Forest(X, hp, T, maxd, minl)
     return X, hp, f, of
 
@@ -45,10 +45,12 @@ BUILD_CASES = [
     pytest.param(30000, 2, 4, 11, 11, 0.4, "gauss", 4096, id="cap4096-empty-hyperplanes"),
     pytest.param(3000, 1100, 2, 5, 40, 0.02, "gauss", 1024, id="large-d-direct-projection"),
     pytest.param(2500, 300, 2, 6, 20, 0.05, "gauss", 1024, id="d300-r1-tile"),
+    pytest.param(30000, 8, 3, 12, 8, 0.5, "outlier", 1024, id="one-outlier-collapses-key-prefixes"),
+    pytest.param(30000, 8, 3, 12, 8, 0.5, "outlier", 2048, id="one-outlier-collapses-key-prefixes-cap2048"),
 ]
 
 
-@pytest.mark.parametrize("generic", [False, True], ids=["fast-bottom", "generic-bottom"])
+@pytest.mark.parametrize("generic", [False, True, "words64"], ids=["fast-bottom", "generic-bottom", "fast-bottom-64bit-words"])
 @pytest.mark.parametrize("n,d,T,maxd,minl,pnz,kind,cap", BUILD_CASES)
 def test_build_parity(built, n, d, T, maxd, minl, pnz, kind, cap, generic):
     X, hp, f, of = _build_pair(n, d, T, maxd, minl, pnz, kind, cap, generic=generic)
