@@ -222,8 +222,8 @@ def run_ours(args):
     exp_bufs = {}
 
     def e2e_build():
-        g.setPoints(X)                                           # H2D n*d*8 from pinned host memory
-        g.build(maxd, W["min_leaf"])
+        g.buildFromHost(X, maxd, W["min_leaf"])                  # forestBatch from pinned host memory: H2D n*d*8 (row blocks, overlapped
+                                                                 # with the projection kernel) + build
         if not exp_bufs:                                         # page-locked result buffers, allocated once (first warm-up)
             nn_ = len(g.topology()["child"])
             for key in ("thr", "mlo", "mhi"):

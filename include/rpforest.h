@@ -87,6 +87,10 @@ int rpf_get_hyperplanes(const rpf_handle* h, int64_t* off, int32_t* idx, double*
 /* ---- build: forestBatch / treeBatch (Batch.hs:29-63) == createMulti/create/insert Tip-case
  *      (Internal.hs:217-240,287-297) with partitionAtMedian (Internal.hs:484-505) ---------------------- */
 int rpf_build(rpf_handle* h, int32_t maxDepth, int32_t minLeaf);
+/* forestBatch with the points still in HOST memory: rpf_set_points + rpf_build in one call; the upload runs in row blocks
+ * on a second stream and the projection kernel starts on the rows that have arrived (pass page-locked X for full PCIe
+ * speed).  Same result as rpf_set_points followed by rpf_build. */
+int rpf_build_from_host(rpf_handle* h, const double* X, int64_t n, int32_t d, int32_t maxDepth, int32_t minLeaf);
 /* forest / tree (Conduit.hs:58-121; insertMulti/insert, Internal.hs:243-297): the rows of X arrive in chunks of
  * `chunk` points, in row order.  chunk >= n is identical to rpf_build (one insert into an empty Tip).  chunk < n runs
  * the reference's streaming update per chunk: every Bin a chunk passes through gets thr' = (thr0 + thr)/2 and

@@ -37,6 +37,7 @@ SIGNATURES = {
     "rpf_rptree_cfg": (None, [C.c_int64, C.c_int64, C.c_int64, i64p, i64p, f64p]),
     "rpf_get_hyperplanes": (C.c_int, [H, i64p, i32p, f64p]),
     "rpf_build": (C.c_int, [H, C.c_int32, C.c_int32]),
+    "rpf_build_from_host": (C.c_int, [H, f64p, C.c_int64, C.c_int32, C.c_int32, C.c_int32]),
     "rpf_build_chunked": (C.c_int, [H, C.c_int32, C.c_int32, C.c_int64]),
     "rpf_num_nodes": (C.c_int64, [H]),
     "rpf_num_trees": (C.c_int32, [H]),

@@ -213,6 +213,16 @@ class RPForest:
         self._ck(self._L.rpf_get_hyperplanes(self._h, _p(off, i64p), _p(idx, i32p), _p(val, f64p)), "rpf_get_hyperplanes")
         return off, idx[:nnz], val[:nnz]
 
+    def buildFromHost(self, X, maxd, minl):
+        """setPoints + build in one call, the upload overlapped with the projection (rpf_build_from_host)."""
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        if X.ndim != 2:
+            raise ValueError("X must be n x d")
+        self._ck(self._L.rpf_build_from_host(self._h, _p(X, f64p), X.shape[0], X.shape[1], maxd, minl), "rpf_build_from_host")
+        self.n, self.d = X.shape
+        self.maxDepth, self.minLeaf = maxd, minl
+        self._topo = None
+
     def build(self, maxd, minl, chunk=None):
         if chunk is None:
             self._ck(self._L.rpf_build(self._h, maxd, minl), "rpf_build")
@@ -390,14 +400,24 @@ def forestBatch(seed, maxd, minl, ntrees, pnz, dim, xs, *, hyperplanes=None, dev
         f.setBottomCap(bottom_cap)
     for name, value in (options or {}).items():
         f.setOption(name, value)
-    _set_points(f, xs, dim)
+    dense = not isinstance(xs, SparseRows)
+    if dense:
+        xs = np.ascontiguousarray(xs, dtype=np.float64)
+        if xs.ndim != 2 or xs.shape[1] != dim:
+            raise ValueError("dataset must be n x %d" % dim)
+        f.d = dim                    # component range check of the hyperplanes
+    else:
+        _set_points(f, xs, dim)
     if hyperplanes is not None:
         hp = hyperplanes if (t_first == 0 and t_local == ntrees) else slice_hyperplanes(hyperplanes, maxd, t_first, t_local)
         f.setHyperplanes(hp, t_local, maxd)
     else:
         f.genHyperplanes(seed, ntrees, maxd, pnz, dim, t_first, t_local)
     f.t_first, f.ntrees_total = t_first, ntrees
-    f.build(maxd, minl)
+    if dense:
+        f.buildFromHost(xs, maxd, minl)      # upload overlapped with the projection
+    else:
+        f.build(maxd, minl)
     return f
 
 

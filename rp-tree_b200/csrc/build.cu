@@ -1660,10 +1660,12 @@ int rpf_run_job(rpf_handle* h, BuildJob& J) {
 
 #define WS(h, var, type, slot, bytes)                                   \
     type* var = (type*)(h)->ws_get((slot), (bytes));                    \
-    if (!var) return RPF_ERR_NOMEM;
+    if (!var) { (h)->tg_cached = 0; return RPF_ERR_NOMEM; }
 
-// forestBatch: the whole data set is one chunk (Batch.hs:48-63)
-int rpf_build_impl(rpf_handle* h) {
+// forestBatch: the whole data set is one chunk (Batch.hs:48-63).  hostX != NULL: the points still live in host memory
+// (h->dX is allocated but empty): they are uploaded in row blocks on a second stream while the projection kernel
+// already runs on the blocks that have arrived (the rest of the build needs all keys and follows on the engine's stream).
+int rpf_build_impl(rpf_handle* h, const double* hostX) {
     const Topology& tp = h->topo;
     const int64_t n = h->n, nn = tp.nnodes();
     const int T = h->T, L = tp.L_eff;
@@ -1680,24 +1682,54 @@ int rpf_build_impl(rpf_handle* h) {
     h->leaf_order_exact = G.order_exact;
 
     // ---- tree group size from the memory budget (free memory + what the workspace already holds)
-    size_t freeB = 0, totalB = 0;
-    RPF_CUDA(h, cudaMemGetInfo(&freeB, &totalB));
-    const size_t per_tree = (size_t)L * n * 8 + rpf_job_ws_per_tree(G, n);
-    const size_t budget = (size_t)((double)(freeB + h->ws_bytes) * 0.7);
-    if (per_tree > budget) return rpf_fail(h, RPF_ERR_NOMEM, "not enough device memory for one tree's keys");
-    const int Tg = (int)std::min<size_t>((size_t)T, std::max<size_t>(1, budget / per_tree));
+    int Tg;
+    if (h->tg_cached > 0 && h->tg_key_n == n && h->tg_key_L == L && h->tg_key_T == T) {
+        Tg = h->tg_cached;
+    } else {
+        size_t freeB = 0, totalB = 0;
+        RPF_CUDA(h, cudaMemGetInfo(&freeB, &totalB));
+        const size_t per_tree = (size_t)L * n * 8 + rpf_job_ws_per_tree(G, n);
+        const size_t budget = (size_t)((double)(freeB + h->ws_bytes) * 0.7);
+        if (per_tree > budget) return rpf_fail(h, RPF_ERR_NOMEM, "not enough device memory for one tree's keys");
+        Tg = (int)std::min<size_t>((size_t)T, std::max<size_t>(1, budget / per_tree));
+        h->tg_key_n = n; h->tg_key_L = L; h->tg_key_T = T; h->tg_cached = Tg;
+    }
 
     WS(h, keys, ull, WS_KEYS, (size_t)Tg * std::max(L, 1) * std::max<int64_t>(n, 1) * 8);
     WS(h, kmin, ull, WS_KMIN, (size_t)Tg * std::max(L, 1) * 8);
     WS(h, kmax, ull, WS_KMAX, (size_t)Tg * std::max(L, 1) * 8);
 
+    const bool pipelined = hostX && Tg == T && L > 0 && n > 0;
+    if (hostX && !pipelined && n > 0) {      // several tree groups (or nothing to project): plain upload first
+        RPF_CUDA(h, cudaMemcpyAsync((void*)h->dX, hostX, (size_t)n * h->d * 8, cudaMemcpyHostToDevice, h->stream));
+    }
     for (int t0 = 0; t0 < T; t0 += Tg) {
         const int tg = std::min(Tg, T - t0);
         if (L > 0 && n > 0) {   // K1
             RPF_CUDA(h, cudaMemsetAsync(kmin, 0xff, (size_t)tg * L * 8, h->stream));
             RPF_CUDA(h, cudaMemsetAsync(kmax, 0x00, (size_t)tg * L * 8, h->stream));
-            rc = rpf_project_launch(h, PH_PROJECT, h->dX, n, t0, tg, L, true, keys, n, kmin, kmax);
-            if (rc) return rc;
+            if (pipelined) {
+                if (!h->copy_stream) RPF_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+                const int NBLK = 8;
+                int64_t rows = (n + NBLK - 1) / NBLK;
+                rows = (rows + 4095) / 4096 * 4096;              // whole projection tiles, 32-byte aligned key columns
+                // the upload may only start once the engine's stream is done with the previous contents of dX
+                if (!h->copy_ev[0]) for (int i = 0; i <= NBLK; ++i) RPF_CUDA(h, cudaEventCreateWithFlags(&h->copy_ev[i], cudaEventDisableTiming));
+                RPF_CUDA(h, cudaEventRecord(h->copy_ev[NBLK], h->stream));
+                RPF_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->copy_ev[NBLK], 0));
+                int bi = 0;
+                for (int64_t r0 = 0; r0 < n; r0 += rows, ++bi) {
+                    const int64_t nr = std::min(rows, n - r0);
+                    RPF_CUDA(h, cudaMemcpyAsync((void*)(h->dX + r0 * h->d), hostX + r0 * h->d, (size_t)nr * h->d * 8, cudaMemcpyHostToDevice, h->copy_stream));
+                    RPF_CUDA(h, cudaEventRecord(h->copy_ev[bi], h->copy_stream));
+                    RPF_CUDA(h, cudaStreamWaitEvent(h->stream, h->copy_ev[bi], 0));
+                    rc = rpf_project_launch(h, PH_PROJECT, h->dX + r0 * h->d, nr, t0, tg, L, true, keys + r0, n, kmin, kmax);
+                    if (rc) return rc;
+                }
+            } else {
+                rc = rpf_project_launch(h, PH_PROJECT, h->dX, n, t0, tg, L, true, keys, n, kmin, kmax);
+                if (rc) return rc;
+            }
         }
         BuildJob J{};
         J.tp = &tp; J.d_start = h->d_node_start; J.d_size = h->d_node_size; J.d_child = h->d_node_child;

@@ -210,6 +210,7 @@ static void free_topo_dev(rpf_handle* h) {
     if (h->d_node_child) cudaFree(h->d_node_child);
     if (h->d_node_depth) cudaFree(h->d_node_depth);
     h->d_node_start = h->d_node_size = nullptr; h->d_node_child = h->d_node_depth = nullptr;
+    h->topo_dev_nn = 0; h->topo_dev_child.clear(); h->topo_dev_size.clear();
 }
 static void free_forest_dev(rpf_handle* h) {
     if (h->d_thr) cudaFree(h->d_thr);
@@ -248,8 +249,10 @@ static int upload_hyperplanes(rpf_handle* h) {
 // device copies of h->topo (start, size, child, depth per BFS node)
 int rpf_upload_topology(rpf_handle* h) {
     const Topology& tp = h->topo;
-    free_topo_dev(h);
     const size_t nn = (size_t)tp.nnodes();
+    // the device copy is kept while the shape stays the same (a rebuild of the same shape does no allocation and no copy)
+    if (h->d_node_start && h->topo_dev_nn == nn && h->topo_dev_child == tp.child && h->topo_dev_size == tp.size) return RPF_OK;
+    free_topo_dev(h);
     RPF_CUDA(h, cudaMalloc(&h->d_node_start, nn * 4));
     RPF_CUDA(h, cudaMalloc(&h->d_node_size, nn * 4));
     RPF_CUDA(h, cudaMalloc(&h->d_node_child, nn * 4));
@@ -258,6 +261,7 @@ int rpf_upload_topology(rpf_handle* h) {
     RPF_CUDA(h, cudaMemcpy(h->d_node_size, tp.size.data(), nn * 4, cudaMemcpyHostToDevice));
     RPF_CUDA(h, cudaMemcpy(h->d_node_child, tp.child.data(), nn * 4, cudaMemcpyHostToDevice));
     RPF_CUDA(h, cudaMemcpy(h->d_node_depth, tp.depth.data(), nn * 4, cudaMemcpyHostToDevice));
+    h->topo_dev_nn = nn; h->topo_dev_child = tp.child; h->topo_dev_size = tp.size;
     return RPF_OK;
 }
 
@@ -314,6 +318,8 @@ void rpf_destroy(rpf_handle* h) {
     if (h->d_xlast) cudaFree(h->d_xlast);
     free_hp_dev(h); free_topo_dev(h); free_forest_dev(h);
     if (h->stream_plan && h->stream_plan_free) h->stream_plan_free(h->stream_plan);
+    for (auto e : h->copy_ev) if (e) cudaEventDestroy(e);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     h->ws_free_all();
     h->stage_free_all();
     for (auto e : h->event_pool) cudaEventDestroy(e);
@@ -563,7 +569,39 @@ int rpf_build(rpf_handle* h, int32_t maxDepth, int32_t minLeaf) {
     h->built = false;
     h->stream_lost = 0;
     h->call_begin();
-    rc = rpf_build_impl(h);
+    rc = rpf_build_impl(h, nullptr);
+    int rc2 = h->call_end();
+    if (rc) return rc;
+    if (rc2) return rc2;
+    h->built = true;
+    return RPF_OK;
+}
+
+// forestBatch straight from host memory: rpf_set_points + rpf_build with the upload overlapped with the projection
+int rpf_build_from_host(rpf_handle* h, const double* X, int64_t n, int32_t d, int32_t maxDepth, int32_t minLeaf) {
+    if (!h) return RPF_ERR_ARG;
+    if (n < 0 || d < 1 || (n > 0 && !X)) return rpf_fail(h, RPF_ERR_ARG, "build_from_host: bad n/d/X");
+    if (n >= (int64_t)1 << 31) return rpf_fail(h, RPF_ERR_UNSUPPORTED, "build_from_host: n must be < 2^31");
+    RPF_SETDEV(h);
+    if (h->d_xlast) { cudaFree(h->d_xlast); h->d_xlast = nullptr; }
+    const size_t bytes = std::max<size_t>((size_t)n * d * 8, 16);
+    if (!(h->ownX && h->dX && h->x_bytes == bytes)) {
+        if (h->ownX && h->dX) cudaFree((void*)h->dX);
+        h->dX = nullptr; h->ownX = false;
+        free_forest_dev(h);
+        double* p = nullptr;
+        RPF_CUDA(h, cudaMalloc(&p, bytes));
+        h->dX = p; h->ownX = true; h->x_bytes = bytes;
+    }
+    h->n = n; h->d = d; h->built = false;
+    int rc = check_build_args(h, maxDepth, minLeaf);
+    if (rc) return rc;
+    build_topology(h->topo, h->n, maxDepth, minLeaf);
+    rc = rpf_upload_topology(h);
+    if (rc) return rc;
+    h->stream_lost = 0;
+    h->call_begin();
+    rc = rpf_build_impl(h, X);
     int rc2 = h->call_end();
     if (rc) return rc;
     if (rc2) return rc2;
@@ -867,7 +905,7 @@ int rpf_set_option(rpf_handle* h, const char* name, int64_t value) {
     if (s == "force_simple_knn") { h->force_simple_knn = value != 0; return RPF_OK; }
     if (s == "no_query_order") { h->no_query_order = value != 0; return RPF_OK; }
     if (s == "project_variant") { h->project_variant = (int)value; return RPF_OK; }
-    if (s == "release_workspace") { cudaStreamSynchronize(h->stream); h->ws_free_all(); return RPF_OK; }
+    if (s == "release_workspace") { cudaStreamSynchronize(h->stream); h->ws_free_all(); h->tg_cached = 0; return RPF_OK; }
     return rpf_fail(h, RPF_ERR_ARG, "unknown option " + s);
 }
 int rpf_set_bottom_cap(rpf_handle* h, int32_t cap) {
@@ -875,6 +913,7 @@ int rpf_set_bottom_cap(rpf_handle* h, int32_t cap) {
     if (cap != 256 && cap != 512 && cap != 1024 && cap != 2048 && cap != 4096 && cap != 8192)
         return rpf_fail(h, RPF_ERR_ARG, "bottom_cap must be a power of two in [256, 8192]");
     h->bottom_cap = cap;
+    h->tg_cached = 0;
     return RPF_OK;
 }
 

@@ -113,6 +113,8 @@ struct WsBuf { void* p = nullptr; size_t cap = 0; };
 struct rpf_handle {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // rpf_build_from_host: row-block uploads overlapped with the projection
+    cudaEvent_t copy_ev[9] = {nullptr};
     std::string err;
 
     // points
@@ -129,6 +131,9 @@ struct rpf_handle {
     // topology
     Topology topo;
     uint32_t* d_node_start = nullptr; uint32_t* d_node_size = nullptr; int32_t* d_node_child = nullptr; int32_t* d_node_depth = nullptr;
+    size_t topo_dev_nn = 0; std::vector<int32_t> topo_dev_child; std::vector<uint32_t> topo_dev_size;   // what the device copy holds
+    // tree-group size of the last batch build (cudaMemGetInfo is only asked again when the shape changes)
+    int64_t tg_key_n = -1; int tg_key_L = -1, tg_key_T = -1, tg_cached = 0;
 
     // forest
     bool built = false;
@@ -202,7 +207,7 @@ int rpf_fail(rpf_handle* h, int code, const std::string& msg);
     } while (0)
 
 // implemented in build.cu / stream.cu / query.cu
-int rpf_build_impl(rpf_handle* h);
+int rpf_build_impl(rpf_handle* h, const double* hostX);
 int rpf_alloc_forest(rpf_handle* h, int64_t nn, int64_t n);
 void rpf_job_geometry(const Topology& tp, int cap_cfg, int Lk, JobGeom& G);
 size_t rpf_job_ws_per_tree(const JobGeom& G, int64_t n);
