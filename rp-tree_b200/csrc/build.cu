@@ -625,7 +625,7 @@ __global__ void __launch_bounds__(FW_WARPS * 32) k_top_finish_warp(TopArgs A) {
     ull v[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) { const uint32_t i = lane * 8 + e; v[e] = i < c ? seg[i] : 0xffffffffffffffffull; }
-    sort_regs<32, ull>(v, (ull*)nullptr, FW_MAX);
+    sort_regs<32, ull>(v, (ull*)nullptr, max(8u, next_pow2_u32(c)));      // only the block that holds the c keys needs sorting
 #pragma unroll
     for (int e = 0; e < 8; ++e) buf[wi][lane * 8 + e] = v[e];
     __syncwarp();

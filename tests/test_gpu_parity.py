@@ -142,7 +142,7 @@ def test_candidates_knn_recall_parity(built, n, d, T, maxd, minl, pnz, kind, cap
                 assert np.array_equal(np.sort(got), np.sort(exp)), "candidate sets differ: tree %d query %d" % (t, i)
     # knn and knnPQ
     for dedup in (False, True):
-        for k in (1, 10, 37):
+        for k in (1, 10, 37, 100):
             dist, ids, cnt = f.knnBatch(Q, k, dedup=dedup)
             for i in range(nq):
                 od, oi = of.knn(Q[i], k, dedup=dedup)
