@@ -13,6 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PHASE = [("k_knn_tma", "q_knn"), ("k_knn", "q_knn"), ("k_project<", "project"), ("k_bottom", "bottom"), ("k_top_hist", "top_hist"),
          ("k_top_compact", "top_compact"), ("k_top_relabel", "top_relabel")]
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+TIME_MS = {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}
 
 
 def main(paths):
@@ -30,7 +31,7 @@ def main(paths):
             if ph == "project" and float(r[ir].replace(",", "")) * UNIT[units[ir]] < 1e8:
                 continue            # the query-projection launch of the same template
             b = float(r[ir].replace(",", "")) * UNIT[units[ir]] + float(r[iw].replace(",", "")) * UNIT[units[iw]]
-            acc.setdefault(ph, []).append((b, float(r[it].replace(",", "")), os.path.basename(path), name[:48]))
+            acc.setdefault(ph, []).append((b, float(r[it].replace(",", "")) * TIME_MS.get(units[it], 1.0), os.path.basename(path), name[:48]))
     res = {}
     for ph, lst in acc.items():
         res[ph] = dict(dram_bytes_per_launch=sum(x[0] for x in lst) / len(lst), launches_profiled=len(lst),
