@@ -1662,20 +1662,50 @@ int rpf_run_job(rpf_handle* h, BuildJob& J) {
     type* var = (type*)(h)->ws_get((slot), (bytes));                    \
     if (!var) { (h)->tg_cached = 0; return RPF_ERR_NOMEM; }
 
+// The plan of a batch build (geometry + device-resident tables) only depends on the shape: kept per handle.
+namespace {
+struct BatchPlan {
+    int64_t n = -1; int maxDepth = -1, minLeaf = -1, cap = -1, Lk = -1; bool force_generic = false;
+    JobPlan P; char* d_tab = nullptr;
+    ~BatchPlan() { if (d_tab) cudaFree(d_tab); }
+};
+void free_batch_plan(void* p) { delete (BatchPlan*)p; }
+}  // namespace
+
+static int get_batch_plan(rpf_handle* h, int L, BatchPlan** out) {
+    const Topology& tp = h->topo;
+    BatchPlan* B = (BatchPlan*)h->batch_plan;
+    if (B && B->n == tp.n && B->maxDepth == tp.maxDepth && B->minLeaf == tp.minLeaf && B->cap == h->bottom_cap && B->Lk == L &&
+        B->force_generic == h->force_generic_bottom && B->P.nn == tp.nnodes()) { *out = B; return RPF_OK; }
+    if (B) { cudaStreamSynchronize(h->stream); delete B; h->batch_plan = nullptr; }
+    ++h->cfg_epoch;
+    B = new BatchPlan();
+    B->n = tp.n; B->maxDepth = tp.maxDepth; B->minLeaf = tp.minLeaf; B->cap = h->bottom_cap; B->Lk = L; B->force_generic = h->force_generic_bottom;
+    TableBuf TB;
+    rpf_plan_job(tp, h->bottom_cap, L, h->force_generic_bottom, TB, B->P);
+    if (cudaMalloc(&B->d_tab, std::max<size_t>(TB.bytes.size(), 256)) != cudaSuccess ||
+        cudaMemcpy(B->d_tab, TB.bytes.data(), TB.bytes.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaGetLastError(); delete B;
+        return rpf_fail(h, RPF_ERR_NOMEM, "batch plan: device tables");
+    }
+    h->batch_plan = B; h->batch_plan_free = free_batch_plan;
+    *out = B;
+    return RPF_OK;
+}
+
 // forestBatch: the whole data set is one chunk (Batch.hs:48-63).  hostX != NULL: the points still live in host memory
 // (h->dX is allocated but empty): they are uploaded in row blocks on a second stream while the projection kernel
 // already runs on the blocks that have arrived (the rest of the build needs all keys and follows on the engine's stream).
+// A rebuild of an unchanged shape with the points resident replays the whole launch sequence as one CUDA graph.
 int rpf_build_impl(rpf_handle* h, const double* hostX) {
     const Topology& tp = h->topo;
     const int64_t n = h->n, nn = tp.nnodes();
     const int T = h->T, L = tp.L_eff;
 
     // ---- result arrays (kept across builds of the same shape)
+    const uint64_t ep_before = h->cfg_epoch;
     int rc = rpf_alloc_forest(h, nn, n);
     if (rc) return rc;
-    RPF_CUDA(h, cudaMemsetAsync(h->d_thr, 0, h->res_node_bytes, h->stream));
-    RPF_CUDA(h, cudaMemsetAsync(h->d_mlo, 0, h->res_node_bytes, h->stream));
-    RPF_CUDA(h, cudaMemsetAsync(h->d_mhi, 0, h->res_node_bytes, h->stream));
 
     JobGeom G;
     rpf_job_geometry(tp, h->bottom_cap, L, G);
@@ -1698,48 +1728,97 @@ int rpf_build_impl(rpf_handle* h, const double* hostX) {
     WS(h, keys, ull, WS_KEYS, (size_t)Tg * std::max(L, 1) * std::max<int64_t>(n, 1) * 8);
     WS(h, kmin, ull, WS_KMIN, (size_t)Tg * std::max(L, 1) * 8);
     WS(h, kmax, ull, WS_KMAX, (size_t)Tg * std::max(L, 1) * 8);
+    BatchPlan* BP = nullptr;
+    rc = get_batch_plan(h, L, &BP);
+    if (rc) return rc;
 
     const bool pipelined = hostX && Tg == T && L > 0 && n > 0;
-    if (hostX && !pipelined && n > 0) {      // several tree groups (or nothing to project): plain upload first
-        RPF_CUDA(h, cudaMemcpyAsync((void*)h->dX, hostX, (size_t)n * h->d * 8, cudaMemcpyHostToDevice, h->stream));
+    const bool graphable = h->use_graphs && !hostX && Tg == T && L > 0 && n > 0 && !h->profiling;
+    if (graphable && h->build_graph && h->graph_epoch == h->cfg_epoch) {
+        RPF_CUDA(h, cudaGraphLaunch(h->build_graph, h->stream));
+        h->launches += h->graph_launches;
+        h->phase_launches[PH_MISC] += h->graph_launches;
+        h->last_build_epoch = h->cfg_epoch;
+        return RPF_OK;
     }
-    for (int t0 = 0; t0 < T; t0 += Tg) {
-        const int tg = std::min(Tg, T - t0);
-        if (L > 0 && n > 0) {   // K1
-            RPF_CUDA(h, cudaMemsetAsync(kmin, 0xff, (size_t)tg * L * 8, h->stream));
-            RPF_CUDA(h, cudaMemsetAsync(kmax, 0x00, (size_t)tg * L * 8, h->stream));
-            if (pipelined) {
-                if (!h->copy_stream) RPF_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-                const int NBLK = 8;
-                int64_t rows = (n + NBLK - 1) / NBLK;
-                rows = (rows + 4095) / 4096 * 4096;              // whole projection tiles, 32-byte aligned key columns
-                // the upload may only start once the engine's stream is done with the previous contents of dX
-                if (!h->copy_ev[0]) for (int i = 0; i <= NBLK; ++i) RPF_CUDA(h, cudaEventCreateWithFlags(&h->copy_ev[i], cudaEventDisableTiming));
-                RPF_CUDA(h, cudaEventRecord(h->copy_ev[NBLK], h->stream));
-                RPF_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->copy_ev[NBLK], 0));
-                int bi = 0;
-                for (int64_t r0 = 0; r0 < n; r0 += rows, ++bi) {
-                    const int64_t nr = std::min(rows, n - r0);
-                    RPF_CUDA(h, cudaMemcpyAsync((void*)(h->dX + r0 * h->d), hostX + r0 * h->d, (size_t)nr * h->d * 8, cudaMemcpyHostToDevice, h->copy_stream));
-                    RPF_CUDA(h, cudaEventRecord(h->copy_ev[bi], h->copy_stream));
-                    RPF_CUDA(h, cudaStreamWaitEvent(h->stream, h->copy_ev[bi], 0));
-                    rc = rpf_project_launch(h, PH_PROJECT, h->dX + r0 * h->d, nr, t0, tg, L, true, keys + r0, n, kmin, kmax);
-                    if (rc) return rc;
+    if (h->build_graph) { cudaGraphExecDestroy(h->build_graph); h->build_graph = nullptr; }
+
+    // everything below only enqueues work on the engine's stream (no allocation once the workspace has its size)
+    auto enqueue = [&]() -> int {
+        RPF_CUDA(h, cudaMemsetAsync(h->d_thr, 0, h->res_node_bytes, h->stream));
+        RPF_CUDA(h, cudaMemsetAsync(h->d_mlo, 0, h->res_node_bytes, h->stream));
+        RPF_CUDA(h, cudaMemsetAsync(h->d_mhi, 0, h->res_node_bytes, h->stream));
+        if (hostX && !pipelined && n > 0)      // several tree groups (or nothing to project): plain upload first
+            RPF_CUDA(h, cudaMemcpyAsync((void*)h->dX, hostX, (size_t)n * h->d * 8, cudaMemcpyHostToDevice, h->stream));
+        for (int t0 = 0; t0 < T; t0 += Tg) {
+            const int tg = std::min(Tg, T - t0);
+            if (L > 0 && n > 0) {   // K1
+                RPF_CUDA(h, cudaMemsetAsync(kmin, 0xff, (size_t)tg * L * 8, h->stream));
+                RPF_CUDA(h, cudaMemsetAsync(kmax, 0x00, (size_t)tg * L * 8, h->stream));
+                if (pipelined) {
+                    if (!h->copy_stream) RPF_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+                    const int NBLK = 8;
+                    int64_t rows = (n + NBLK - 1) / NBLK;
+                    rows = (rows + 4095) / 4096 * 4096;              // whole projection tiles, 32-byte aligned key columns
+                    // the upload may only start once the engine's stream is done with the previous contents of dX
+                    if (!h->copy_ev[0]) for (int i = 0; i <= NBLK; ++i) RPF_CUDA(h, cudaEventCreateWithFlags(&h->copy_ev[i], cudaEventDisableTiming));
+                    RPF_CUDA(h, cudaEventRecord(h->copy_ev[NBLK], h->stream));
+                    RPF_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->copy_ev[NBLK], 0));
+                    int bi = 0;
+                    for (int64_t r0 = 0; r0 < n; r0 += rows, ++bi) {
+                        const int64_t nr = std::min(rows, n - r0);
+                        RPF_CUDA(h, cudaMemcpyAsync((void*)(h->dX + r0 * h->d), hostX + r0 * h->d, (size_t)nr * h->d * 8, cudaMemcpyHostToDevice, h->copy_stream));
+                        RPF_CUDA(h, cudaEventRecord(h->copy_ev[bi], h->copy_stream));
+                        RPF_CUDA(h, cudaStreamWaitEvent(h->stream, h->copy_ev[bi], 0));
+                        int rc2 = rpf_project_launch(h, PH_PROJECT, h->dX + r0 * h->d, nr, t0, tg, L, true, keys + r0, n, kmin, kmax);
+                        if (rc2) return rc2;
+                    }
+                } else {
+                    int rc2 = rpf_project_launch(h, PH_PROJECT, h->dX, n, t0, tg, L, true, keys, n, kmin, kmax);
+                    if (rc2) return rc2;
                 }
-            } else {
-                rc = rpf_project_launch(h, PH_PROJECT, h->dX, n, t0, tg, L, true, keys, n, kmin, kmax);
-                if (rc) return rc;
             }
+            BuildJob J{};
+            J.tp = &tp; J.d_start = h->d_node_start; J.d_size = h->d_node_size; J.d_child = h->d_node_child;
+            J.n = n; J.ks = n; J.ps = n; J.ns = nn; J.Lk = L;
+            J.keys = keys; J.kmin = kmin; J.kmax = kmax;
+            J.perm = h->d_perm + (int64_t)t0 * n; J.thr = h->d_thr; J.mlo = h->d_mlo; J.mhi = h->d_mhi;
+            J.gt0 = t0; J.tg = tg;
+            int rc2 = rpf_launch_job(h, J, BP->P, BP->d_tab);
+            if (rc2) return rc2;
         }
-        BuildJob J{};
-        J.tp = &tp; J.d_start = h->d_node_start; J.d_size = h->d_node_size; J.d_child = h->d_node_child;
-        J.n = n; J.ks = n; J.ps = n; J.ns = nn; J.Lk = L;
-        J.keys = keys; J.kmin = kmin; J.kmax = kmax;
-        J.perm = h->d_perm + (int64_t)t0 * n; J.thr = h->d_thr; J.mlo = h->d_mlo; J.mhi = h->d_mhi;
-        J.gt0 = t0; J.tg = tg;
-        rc = rpf_run_job(h, J);
-        if (rc) return rc;
+        return RPF_OK;
+    };
+
+    // second build of an unchanged configuration: capture the launch sequence, then run it as a graph from now on
+    const bool capture = graphable && h->last_build_epoch == h->cfg_epoch && ep_before == h->cfg_epoch;
+    if (capture) {
+        const int64_t l0 = h->launches;
+        int64_t pl[PH_COUNT];
+        for (int i = 0; i < PH_COUNT; ++i) pl[i] = h->phase_launches[i];
+        cudaGraph_t graph = nullptr;
+        h->capturing = true;
+        cudaError_t e = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal);
+        int rcq = e == cudaSuccess ? enqueue() : RPF_ERR_CUDA;
+        cudaError_t e2 = e == cudaSuccess ? cudaStreamEndCapture(h->stream, &graph) : e;
+        h->capturing = false;
+        cudaGraphExec_t exec = nullptr;
+        if (rcq == RPF_OK && e2 == cudaSuccess && graph && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
+            cudaGraphDestroy(graph);
+            h->build_graph = exec; h->graph_epoch = h->cfg_epoch; h->graph_launches = h->launches - l0;
+            RPF_CUDA(h, cudaGraphLaunch(h->build_graph, h->stream));
+            h->last_build_epoch = h->cfg_epoch;
+            return RPF_OK;
+        }
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        h->launches = l0;
+        for (int i = 0; i < PH_COUNT; ++i) h->phase_launches[i] = pl[i];
+        h->use_graphs = false;                 // capture is not possible in this environment: plain launches from now on
     }
+    rc = enqueue();
+    if (rc) return rc;
+    h->last_build_epoch = h->cfg_epoch;
     return RPF_OK;
 }
 
@@ -1750,6 +1829,7 @@ int rpf_alloc_forest(rpf_handle* h, int64_t nn, int64_t n) {
     if (h->res_node_bytes != node_bytes || h->res_perm_bytes != perm_bytes || !h->d_thr) {
         if (h->d_thr) { cudaFree(h->d_thr); cudaFree(h->d_mlo); cudaFree(h->d_mhi); cudaFree(h->d_perm); h->d_thr = h->d_mlo = h->d_mhi = nullptr; h->d_perm = nullptr; }
         h->res_node_bytes = h->res_perm_bytes = 0;
+        ++h->cfg_epoch;
         RPF_CUDA(h, cudaMalloc(&h->d_thr, node_bytes));
         RPF_CUDA(h, cudaMalloc(&h->d_mlo, node_bytes));
         RPF_CUDA(h, cudaMalloc(&h->d_mhi, node_bytes));

@@ -55,6 +55,8 @@ void* rpf_handle::ws_get(int slot, size_t bytes) {
     WsBuf& b = ws[slot];
     if (bytes < 16) bytes = 16;
     if (b.cap >= bytes) return b.p;
+    if (capturing) { err = "workspace growth during graph capture"; return nullptr; }
+    ++cfg_epoch;
     if (b.p) { cudaStreamSynchronize(stream); cudaFree(b.p); ws_bytes -= b.cap; b.p = nullptr; b.cap = 0; }
     size_t want = bytes + bytes / 16;          // a little slack so slowly growing requests do not thrash
     cudaError_t e = cudaMalloc(&b.p, want);
@@ -64,6 +66,7 @@ void* rpf_handle::ws_get(int slot, size_t bytes) {
     return b.p;
 }
 void rpf_handle::ws_free_all() {
+    ++cfg_epoch;
     for (int i = 0; i < WS_COUNT; ++i) if (ws[i].p) { cudaFree(ws[i].p); ws[i].p = nullptr; ws[i].cap = 0; }
     ws_bytes = 0;
 }
@@ -222,6 +225,7 @@ static void free_forest_dev(rpf_handle* h) {
 }
 
 static int upload_hyperplanes(rpf_handle* h) {
+    ++h->cfg_epoch;
     free_hp_dev(h);
     free_forest_dev(h);
     const size_t nrow = h->hp_off.size(), nnz = h->hp_idx.size();
@@ -253,6 +257,7 @@ int rpf_upload_topology(rpf_handle* h) {
     // the device copy is kept while the shape stays the same (a rebuild of the same shape does no allocation and no copy)
     if (h->d_node_start && h->topo_dev_nn == nn && h->topo_dev_child == tp.child && h->topo_dev_size == tp.size) return RPF_OK;
     free_topo_dev(h);
+    ++h->cfg_epoch;
     RPF_CUDA(h, cudaMalloc(&h->d_node_start, nn * 4));
     RPF_CUDA(h, cudaMalloc(&h->d_node_size, nn * 4));
     RPF_CUDA(h, cudaMalloc(&h->d_node_child, nn * 4));
@@ -318,6 +323,8 @@ void rpf_destroy(rpf_handle* h) {
     if (h->d_xlast) cudaFree(h->d_xlast);
     free_hp_dev(h); free_topo_dev(h); free_forest_dev(h);
     if (h->stream_plan && h->stream_plan_free) h->stream_plan_free(h->stream_plan);
+    if (h->build_graph) cudaGraphExecDestroy(h->build_graph);
+    if (h->batch_plan && h->batch_plan_free) h->batch_plan_free(h->batch_plan);
     for (auto e : h->copy_ev) if (e) cudaEventDestroy(e);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     h->ws_free_all();
@@ -336,6 +343,7 @@ int rpf_set_points(rpf_handle* h, const double* X, int64_t n, int32_t d) {
     if (n < 0 || d < 1 || (n > 0 && !X)) return rpf_fail(h, RPF_ERR_ARG, "set_points: bad n/d/X");
     if (n >= (int64_t)1 << 31) return rpf_fail(h, RPF_ERR_UNSUPPORTED, "set_points: n must be < 2^31");
     RPF_SETDEV(h);
+    ++h->cfg_epoch;
     if (h->d_xlast) { cudaFree(h->d_xlast); h->d_xlast = nullptr; }
     double* p = nullptr;
     const size_t bytes = std::max<size_t>((size_t)n * d * 8, 16);
@@ -360,6 +368,7 @@ int rpf_set_points_device(rpf_handle* h, const double* X_dev, int64_t n, int32_t
     if (n < 0 || d < 1 || (n > 0 && !X_dev)) return rpf_fail(h, RPF_ERR_ARG, "set_points_device: bad n/d/X");
     if (n >= (int64_t)1 << 31) return rpf_fail(h, RPF_ERR_UNSUPPORTED, "set_points_device: n must be < 2^31");
     RPF_SETDEV(h);
+    ++h->cfg_epoch;
     if (h->d_xlast) { cudaFree(h->d_xlast); h->d_xlast = nullptr; }
     if (h->ownX && h->dX) cudaFree((void*)h->dX);
     free_forest_dev(h);
@@ -396,6 +405,7 @@ int rpf_set_points_sparse(rpf_handle* h, int64_t n, int32_t d, const int64_t* of
     int rc = check_csr_rows(h, n, d, off, idx, "set_points_sparse");
     if (rc) return rc;
     RPF_SETDEV(h);
+    ++h->cfg_epoch;
     if (h->d_xlast) { cudaFree(h->d_xlast); h->d_xlast = nullptr; }
     if (h->ownX && h->dX) cudaFree((void*)h->dX);
     h->dX = nullptr; h->ownX = false; h->x_bytes = 0;
@@ -563,7 +573,10 @@ int rpf_build(rpf_handle* h, int32_t maxDepth, int32_t minLeaf) {
     int rc = check_build_args(h, maxDepth, minLeaf);
     if (rc) return rc;
     RPF_SETDEV(h);
-    build_topology(h->topo, h->n, maxDepth, minLeaf);
+    if (!(h->topo_key_n == h->n && h->topo_key_maxd == maxDepth && h->topo_key_minl == minLeaf)) {
+        build_topology(h->topo, h->n, maxDepth, minLeaf);
+        h->topo_key_n = h->n; h->topo_key_maxd = maxDepth; h->topo_key_minl = minLeaf;
+    }
     rc = rpf_upload_topology(h);
     if (rc) return rc;
     h->built = false;
@@ -583,6 +596,7 @@ int rpf_build_from_host(rpf_handle* h, const double* X, int64_t n, int32_t d, in
     if (n < 0 || d < 1 || (n > 0 && !X)) return rpf_fail(h, RPF_ERR_ARG, "build_from_host: bad n/d/X");
     if (n >= (int64_t)1 << 31) return rpf_fail(h, RPF_ERR_UNSUPPORTED, "build_from_host: n must be < 2^31");
     RPF_SETDEV(h);
+    ++h->cfg_epoch;
     if (h->d_xlast) { cudaFree(h->d_xlast); h->d_xlast = nullptr; }
     const size_t bytes = std::max<size_t>((size_t)n * d * 8, 16);
     if (!(h->ownX && h->dX && h->x_bytes == bytes)) {
@@ -596,7 +610,10 @@ int rpf_build_from_host(rpf_handle* h, const double* X, int64_t n, int32_t d, in
     h->n = n; h->d = d; h->built = false;
     int rc = check_build_args(h, maxDepth, minLeaf);
     if (rc) return rc;
-    build_topology(h->topo, h->n, maxDepth, minLeaf);
+    if (!(h->topo_key_n == h->n && h->topo_key_maxd == maxDepth && h->topo_key_minl == minLeaf)) {
+        build_topology(h->topo, h->n, maxDepth, minLeaf);
+        h->topo_key_n = h->n; h->topo_key_maxd = maxDepth; h->topo_key_minl = minLeaf;
+    }
     rc = rpf_upload_topology(h);
     if (rc) return rc;
     h->stream_lost = 0;
@@ -701,7 +718,7 @@ int rpf_forest_load(rpf_handle* h, const char* path) {
     }
     int rc = upload_hyperplanes(h);      // also drops the previous forest arrays
     if (rc) { fclose(f); return rc; }
-    h->topo = tp;
+    h->topo = tp; h->topo_key_n = -1;
     rc = rpf_upload_topology(h);
     if (!rc) rc = rpf_alloc_forest(h, H.nn, H.n);
     if (rc) { fclose(f); return rc; }
@@ -886,7 +903,7 @@ int rpf_merge_topk(rpf_handle* h, int32_t G, int64_t nq, int32_t k, int32_t dedu
 }
 
 double rpf_last_device_ms(const rpf_handle* h) { return h ? h->last_ms : -1.0; }
-int rpf_set_profiling(rpf_handle* h, int on) { if (!h) return RPF_ERR_ARG; h->profiling = on != 0; return RPF_OK; }
+int rpf_set_profiling(rpf_handle* h, int on) { if (!h) return RPF_ERR_ARG; h->profiling = on != 0; ++h->cfg_epoch; return RPF_OK; }
 int rpf_get_profile(const rpf_handle* h, double* ms, int64_t* launches, int cap) {
     if (!h) return RPF_ERR_ARG;
     for (int i = 0; i < PH_COUNT && i < cap; ++i) {
@@ -900,6 +917,8 @@ int64_t rpf_launch_count(const rpf_handle* h) { return h ? h->launches : -1; }
 int rpf_set_option(rpf_handle* h, const char* name, int64_t value) {
     if (!h || !name) return RPF_ERR_ARG;
     const std::string s(name);
+    ++h->cfg_epoch;
+    if (s == "cuda_graph") { h->use_graphs = value != 0; return RPF_OK; }
     if (s == "force_generic_bottom") { h->force_generic_bottom = value != 0; return RPF_OK; }
     if (s == "bottom_words64") { h->bottom_words64 = value != 0; return RPF_OK; }
     if (s == "force_simple_knn") { h->force_simple_knn = value != 0; return RPF_OK; }
@@ -914,6 +933,7 @@ int rpf_set_bottom_cap(rpf_handle* h, int32_t cap) {
         return rpf_fail(h, RPF_ERR_ARG, "bottom_cap must be a power of two in [256, 8192]");
     h->bottom_cap = cap;
     h->tg_cached = 0;
+    ++h->cfg_epoch;
     return RPF_OK;
 }
 

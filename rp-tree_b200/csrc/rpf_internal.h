@@ -159,6 +159,19 @@ struct rpf_handle {
     int stage_flush();
     void stage_free_all();
 
+    // Every mutation that can move a device buffer or change the build's shape bumps cfg_epoch; the cached batch plan /
+    // captured build graph are only replayed while the epoch they were made under is still current.
+    uint64_t cfg_epoch = 1;
+    uint64_t last_build_epoch = 0;        // epoch at the end of the previous batch build (0: none)
+    void* batch_plan = nullptr;           // build.cu: BatchPlan (job plan + device-resident tables of the current shape)
+    void (*batch_plan_free)(void*) = nullptr;
+    cudaGraphExec_t build_graph = nullptr;   // the whole batch build (memsets, projection, top and bottom phases) as one graph
+    uint64_t graph_epoch = 0;
+    int64_t graph_launches = 0;
+    bool capturing = false;
+    bool use_graphs = true;               // option "cuda_graph"
+    int64_t topo_key_n = -1; int topo_key_maxd = -1, topo_key_minl = -1;   // h->topo == build_topology(these)
+
     // workspace
     WsBuf ws[WS_COUNT];
     size_t ws_bytes = 0;

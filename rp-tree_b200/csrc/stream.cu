@@ -599,7 +599,7 @@ int rpf_build_stream_impl(rpf_handle* h, int maxDepth, int minLeaf, int64_t chun
     WSX(h, pool, double, WS_S_POOL, (size_t)Tg * (S->pool_nodes + 1) * 8 * 3);
 
     // ---- canonical result shape
-    h->topo = S->final_tp;
+    h->topo = S->final_tp; h->topo_key_n = -1;
     int rc = rpf_upload_topology(h);
     if (rc) return rc;
     const int64_t nn = h->topo.nnodes();
