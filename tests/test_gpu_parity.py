@@ -373,3 +373,35 @@ def test_checkpoint_round_trip(built, tmp_path, with_points, chunk):
     bad.write_bytes(b"not a checkpoint")
     with pytest.raises(R.RPForestError):
         g.load(bad)
+
+
+def test_repeated_builds_replay_the_graph_and_follow_new_data(built):
+    """From the third build of an unchanged configuration the launch sequence is replayed as a CUDA graph: every
+    rebuild must still equal the oracle, also after the points / hyperplanes / capacity changed in between."""
+    R, orc = _mods()
+    n, d, T, maxd, minl = 20000, 16, 3, 11, 16
+    hp = orc.gen_hyperplanes(5, T, maxd, 0.4, d)
+    f = R.RPForest(0)
+    f.setHyperplanes(hp, T, maxd)
+    for seed in (1, 2):
+        X = make_data(n, d, seed, "mixture")
+        f.setPoints(X)
+        of = orc.Forest(X, hp, T, maxd, minl)
+        exp = [of.export(t) for t in range(T)]
+        for rep in range(5):
+            f.build(maxd, minl)
+            for t in range(T):
+                assert not compare_tree(f.treeExport(t), exp[t]), "seed %d build %d tree %d" % (seed, rep, t)
+    # same points, other hyperplanes and another capacity: the cached plan / graph must not survive
+    hp2 = orc.gen_hyperplanes(6, T, maxd, 0.4, d)
+    f.setHyperplanes(hp2, T, maxd)
+    f.setBottomCap(256)
+    of = orc.Forest(X, hp2, T, maxd, minl)
+    for rep in range(4):
+        f.build(maxd, minl)
+        for t in range(T):
+            assert not compare_tree(f.treeExport(t), of.export(t)), "hp2 build %d tree %d" % (rep, t)
+    # graphs off gives the same result
+    f.setOption("cuda_graph", 0)
+    f.build(maxd, minl)
+    assert not compare_tree(f.treeExport(0), of.export(0))
