@@ -186,16 +186,13 @@ def run_ours(args):
     merger = f
 
     def knn_step():
-        """local knn over this rank's trees -> NCCL all-gather -> merge kernel.  Returns device ms + merged result."""
-        dd, ii, cc = f.knnBatch(Q, k, dedup=False)
-        ms = f.lastDeviceMs()
+        """local knn over this rank's trees -> NCCL all-gather of the device-resident lists over NVLink -> merge kernel.
+        Returns device ms (engine events for its two calls + torch events around the all-gather) and the merged result."""
         if dist is None:
-            return ms, (dd, ii, cc), 0.0
-        t0 = time.perf_counter()
-        D, I, Cn = R.dist.gather_topk(dd, ii, cc, device=dev)     # NCCL all-gather over NVLink
-        out = merger.mergeTopk(D, I, Cn, dedup=False)
-        ms += merger.lastDeviceMs()
-        return ms, out, (time.perf_counter() - t0) * 1e3
+            dd, ii, cc = f.knnBatch(Q, k, dedup=False)
+            return f.lastDeviceMs(), (dd, ii, cc), 0.0
+        out, ms, gather_ms = R.dist.knnShardedDevice(f, k, Q, dedup=False, device=dev, timed=True)
+        return ms + gather_ms, out, gather_ms
 
     # ---- warm-up
     for _ in range(args.warmup):
@@ -245,7 +242,7 @@ def run_ours(args):
     def e2e_knn():
         dd, ii, cc = g.knnBatch(Q, k)                            # H2D queries, D2H results
         if dist is not None:
-            D, I, Cn = R.dist.gather_topk(dd, ii, cc, device=dev)
+            D, I, Cn = R.dist.gather_topk(dd, ii, cc, device=dev)     # host-buffer form of the exchange (the e2e arm)
             g.mergeTopk(D, I, Cn)
 
     for _ in range(2):                                           # warm-up (workspace allocation)

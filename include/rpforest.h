@@ -181,6 +181,16 @@ int rpf_merge_topk(rpf_handle* h, int32_t G, int64_t nq, int32_t k, int32_t dedu
                    const double* dist, const uint32_t* ids, const int32_t* count,
                    double* dist_out, uint32_t* ids_out, int32_t* count_out);
 
+/* Device-resident form of the exchange: rpf_knn_dev leaves this rank's lists in caller-provided DEVICE buffers (nq x k
+ * doubles, nq x k uint32, nq int32 on this handle's device; complete when the call returns), the caller all-gathers them
+ * over NCCL / NVLink, and rpf_merge_topk_dev merges the gathered rank-major DEVICE lists; only the merged result
+ * crosses PCIe.  q_last as in rpf_knn_s (NULL for DVector queries). */
+int rpf_knn_dev(rpf_handle* h, const double* Q, const int32_t* q_last, int64_t nq, int32_t k, int32_t dedup,
+                double* dist_dev, uint32_t* ids_dev, int32_t* count_dev);
+int rpf_merge_topk_dev(rpf_handle* h, int32_t G, int64_t nq, int32_t k, int32_t dedup,
+                       const double* dist_dev, const uint32_t* ids_dev, const int32_t* count_dev,
+                       double* dist_out, uint32_t* ids_out, int32_t* count_out);
+
 /* ---- measurement hooks (CUDA events on the engine's own stream) ------------------------------------ */
 /* Device time in ms of the most recent rpf_build / rpf_knn / rpf_recall kernels (events on the stream
  * the kernels were launched on; excludes host<->device copies of the call's arguments). */

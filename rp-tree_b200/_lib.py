@@ -60,6 +60,8 @@ SIGNATURES = {
     "rpf_recall": (C.c_int, [H, f64p, C.c_int64, C.c_int32, f64p]),
     "rpf_brute_knn": (C.c_int, [H, f64p, C.c_int64, C.c_int32, f64p, u32p]),
     "rpf_merge_topk": (C.c_int, [H, C.c_int32, C.c_int64, C.c_int32, C.c_int32, f64p, u32p, i32p, f64p, u32p, i32p]),
+    "rpf_knn_dev": (C.c_int, [H, f64p, i32p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "rpf_merge_topk_dev": (C.c_int, [H, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, f64p, u32p, i32p]),
     "rpf_last_device_ms": (C.c_double, [H]),
     "rpf_set_profiling": (C.c_int, [H, C.c_int]),
     "rpf_get_profile": (C.c_int, [H, f64p, i64p, C.c_int]),

@@ -352,6 +352,20 @@ class RPForest:
                                         _p(od, f64p), _p(oi, u32p), _p(oc, i32p)), "rpf_merge_topk")
         return od, oi, oc
 
+    def knnBatchDevice(self, Q, k, dist_ptr, ids_ptr, cnt_ptr, dedup=False):
+        """knn whose (dist nq x k f64, ids nq x k u32, count nq i32) land in DEVICE buffers of the caller (raw pointers on
+        this forest's device); complete when the call returns."""
+        Q, _, ql = _as_q(Q, self.d)
+        self._ck(self._L.rpf_knn_dev(self._h, _p(Q, f64p), _p(ql, i32p) if ql is not None else None, Q.shape[0], k, int(dedup),
+                                     C.c_void_p(dist_ptr), C.c_void_p(ids_ptr), C.c_void_p(cnt_ptr)), "rpf_knn_dev")
+
+    def mergeTopkDevice(self, G, nq, k, dist_ptr, ids_ptr, cnt_ptr, dedup=False):
+        """Merge of gathered rank-major DEVICE lists (G x nq x k, G x nq x k, G x nq) -> merged host arrays."""
+        od = np.zeros((nq, k)); oi = np.zeros((nq, k), np.uint32); oc = np.zeros(nq, np.int32)
+        self._ck(self._L.rpf_merge_topk_dev(self._h, G, nq, k, int(dedup), C.c_void_p(dist_ptr), C.c_void_p(ids_ptr), C.c_void_p(cnt_ptr),
+                                            _p(od, f64p), _p(oi, u32p), _p(oc, i32p)), "rpf_merge_topk_dev")
+        return od, oi, oc
+
     # -- measurement
     def lastDeviceMs(self):
         return self._L.rpf_last_device_ms(self._h)

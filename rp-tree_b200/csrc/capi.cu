@@ -810,7 +810,7 @@ int rpf_knn(rpf_handle* h, const double* Q, int64_t nq, int32_t k, int32_t dedup
     if (nq < 0 || (nq > 0 && (!Q || !dist || !ids)) || k < 1 || k > 1024) return rpf_fail(h, RPF_ERR_ARG, "knn: bad arguments (1 <= k <= 1024)");
     RPF_SETDEV(h);
     h->call_begin();
-    int rc = rpf_knn_impl(h, Q, nullptr, nq, k, dedup, dist, ids, count);
+    int rc = rpf_knn_impl(h, Q, nullptr, nq, k, dedup, dist, ids, count, false);
     int rc2 = h->call_end();
     return rc ? rc : rc2;
 }
@@ -821,7 +821,7 @@ int rpf_knn_s(rpf_handle* h, const double* Q, const int32_t* q_last, int64_t nq,
     if (nq < 0 || (nq > 0 && (!Q || !dist || !ids)) || k < 1 || k > 1024) return rpf_fail(h, RPF_ERR_ARG, "knn: bad arguments (1 <= k <= 1024)");
     RPF_SETDEV(h);
     h->call_begin();
-    int rc = rpf_knn_impl(h, Q, q_last, nq, k, dedup, dist, ids, count);
+    int rc = rpf_knn_impl(h, Q, q_last, nq, k, dedup, dist, ids, count, false);
     int rc2 = h->call_end();
     return rc ? rc : rc2;
 }
@@ -897,7 +897,31 @@ int rpf_merge_topk(rpf_handle* h, int32_t G, int64_t nq, int32_t k, int32_t dedu
         return rpf_fail(h, RPF_ERR_ARG, "merge_topk: bad arguments");
     RPF_SETDEV(h);
     h->call_begin();
-    int rc = rpf_merge_impl(h, G, nq, k, dedup, dist, ids, count, dist_out, ids_out, count_out);
+    int rc = rpf_merge_impl(h, G, nq, k, dedup, dist, ids, count, dist_out, ids_out, count_out, false);
+    int rc2 = h->call_end();
+    return rc ? rc : rc2;
+}
+
+int rpf_knn_dev(rpf_handle* h, const double* Q, const int32_t* q_last, int64_t nq, int32_t k, int32_t dedup,
+                double* dist_dev, uint32_t* ids_dev, int32_t* count_dev) {
+    if (!h) return RPF_ERR_ARG;
+    if (!h->built) return rpf_fail(h, RPF_ERR_STATE, "knn: forest not built");
+    if (nq < 0 || (nq > 0 && (!Q || !dist_dev || !ids_dev || !count_dev)) || k < 1 || k > 1024) return rpf_fail(h, RPF_ERR_ARG, "knn_dev: bad arguments (1 <= k <= 1024)");
+    RPF_SETDEV(h);
+    h->call_begin();
+    int rc = rpf_knn_impl(h, Q, q_last, nq, k, dedup, dist_dev, ids_dev, count_dev, true);
+    int rc2 = h->call_end();
+    return rc ? rc : rc2;
+}
+
+int rpf_merge_topk_dev(rpf_handle* h, int32_t G, int64_t nq, int32_t k, int32_t dedup, const double* dist_dev, const uint32_t* ids_dev,
+                       const int32_t* count_dev, double* dist_out, uint32_t* ids_out, int32_t* count_out) {
+    if (!h) return RPF_ERR_ARG;
+    if (G < 1 || nq < 0 || k < 1 || k > 1024 || (nq > 0 && (!dist_dev || !ids_dev || !count_dev || !dist_out || !ids_out)))
+        return rpf_fail(h, RPF_ERR_ARG, "merge_topk_dev: bad arguments");
+    RPF_SETDEV(h);
+    h->call_begin();
+    int rc = rpf_merge_impl(h, G, nq, k, dedup, dist_dev, ids_dev, count_dev, dist_out, ids_out, count_out, true);
     int rc2 = h->call_end();
     return rc ? rc : rc2;
 }

@@ -995,16 +995,18 @@ static QArgs make_qargs(rpf_handle* h, int64_t nq, const QState& st) {
     return A;
 }
 
-int rpf_knn_impl(rpf_handle* h, const double* Q, const int32_t* q_last, int64_t nq, int k, int dedup, double* dist, uint32_t* ids, int32_t* count) {
+// out_dev: dist / ids / count are DEVICE buffers of the caller (multi-GPU exchange without a host round trip)
+int rpf_knn_impl(rpf_handle* h, const double* Q, const int32_t* q_last, int64_t nq, int k, int dedup, double* dist, uint32_t* ids, int32_t* count, bool out_dev) {
     if (nq == 0) return RPF_OK;
     QState st;
     int rc = upload_qlast(h, q_last, nq, &st.dqlast);
     if (rc) return rc;
     rc = run_descent(h, Q, nq, -1, st);
     if (rc) return rc;
-    QWS(h, ddist, double, WS_OUT_D, (size_t)nq * k * 8);
-    QWS(h, dids, uint32_t, WS_OUT_I, (size_t)nq * k * 4);
-    QWS(h, dcount, int32_t, WS_OUT_C, (size_t)nq * 4);
+    QWS(h, wdist, double, WS_OUT_D, (size_t)nq * k * 8);
+    QWS(h, wids, uint32_t, WS_OUT_I, (size_t)nq * k * 4);
+    QWS(h, wcount, int32_t, WS_OUT_C, (size_t)nq * 4);
+    double* ddist = out_dev ? dist : wdist; uint32_t* dids = out_dev ? ids : wids; int32_t* dcount = (out_dev && count) ? count : wcount;
     QArgs A = make_qargs(h, nq, st);
     A.k = k; A.dedup = dedup; A.dist = ddist; A.ids = dids; A.count = dcount;
     if (nq >= 64 && !h->no_query_order) {
@@ -1033,9 +1035,11 @@ int rpf_knn_impl(rpf_handle* h, const double* Q, const int32_t* q_last, int64_t 
         RPF_CUDA(h, cudaFuncSetAttribute(k_knn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
         RPF_LAUNCH(h, PH_Q_KNN, k_knn, (unsigned)nq, KNN_NT, dyn, A);
     }
-    RPF_CUDA(h, cudaMemcpyAsync(dist, ddist, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, h->stream));
-    RPF_CUDA(h, cudaMemcpyAsync(ids, dids, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, h->stream));
-    if (count) RPF_CUDA(h, cudaMemcpyAsync(count, dcount, (size_t)nq * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (!out_dev) {
+        RPF_CUDA(h, cudaMemcpyAsync(dist, ddist, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, h->stream));
+        RPF_CUDA(h, cudaMemcpyAsync(ids, dids, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, h->stream));
+        if (count) RPF_CUDA(h, cudaMemcpyAsync(count, dcount, (size_t)nq * 4, cudaMemcpyDeviceToHost, h->stream));
+    }
     RPF_CUDA(h, cudaStreamSynchronize(h->stream));
     return RPF_OK;
 }
@@ -1153,19 +1157,25 @@ int rpf_recall_impl(rpf_handle* h, const double* Q, const int32_t* q_last, int64
     return RPF_OK;
 }
 
+// in_dev: dist / ids / count (the gathered rank-major lists) already live on this handle's device
 int rpf_merge_impl(rpf_handle* h, int G, int64_t nq, int k, int dedup, const double* dist, const uint32_t* ids,
-                   const int32_t* count, double* dist_out, uint32_t* ids_out, int32_t* count_out) {
+                   const int32_t* count, double* dist_out, uint32_t* ids_out, int32_t* count_out, bool in_dev) {
     if (nq == 0) return RPF_OK;
     const size_t ne = (size_t)G * nq * k;
-    QWS(h, dd, double, WS_MRG_D, ne * 8);
-    QWS(h, di, uint32_t, WS_MRG_I, ne * 4);
-    QWS(h, dc, int32_t, WS_MRG_C, (size_t)G * nq * 4);
+    const double* dd; const uint32_t* di; const int32_t* dc;
+    if (in_dev) { dd = dist; di = ids; dc = count; }
+    else {
+        QWS(h, wd, double, WS_MRG_D, ne * 8);
+        QWS(h, wi, uint32_t, WS_MRG_I, ne * 4);
+        QWS(h, wc, int32_t, WS_MRG_C, (size_t)G * nq * 4);
+        RPF_CUDA(h, cudaMemcpyAsync(wd, dist, ne * 8, cudaMemcpyHostToDevice, h->stream));
+        RPF_CUDA(h, cudaMemcpyAsync(wi, ids, ne * 4, cudaMemcpyHostToDevice, h->stream));
+        RPF_CUDA(h, cudaMemcpyAsync(wc, count, (size_t)G * nq * 4, cudaMemcpyHostToDevice, h->stream));
+        dd = wd; di = wi; dc = wc;
+    }
     QWS(h, od, double, WS_OUT_D, (size_t)nq * k * 8);
     QWS(h, oi, uint32_t, WS_OUT_I, (size_t)nq * k * 4);
     QWS(h, oc, int32_t, WS_OUT_C, (size_t)nq * 4);
-    RPF_CUDA(h, cudaMemcpyAsync(dd, dist, ne * 8, cudaMemcpyHostToDevice, h->stream));
-    RPF_CUDA(h, cudaMemcpyAsync(di, ids, ne * 4, cudaMemcpyHostToDevice, h->stream));
-    RPF_CUDA(h, cudaMemcpyAsync(dc, count, (size_t)G * nq * 4, cudaMemcpyHostToDevice, h->stream));
     const size_t dynm = (size_t)KNN_BUF * 16;
     RPF_CUDA(h, cudaFuncSetAttribute(k_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dynm));
     RPF_LAUNCH(h, PH_MERGE, k_merge, (unsigned)nq, KNN_NT, dynm, G, nq, k, dedup, dd, di, dc, od, oi, oc);

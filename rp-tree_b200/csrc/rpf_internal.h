@@ -233,13 +233,13 @@ int rpf_project_launch(rpf_handle* h, int phase, const double* dX, int64_t n, in
 int rpf_upload_topology(rpf_handle* h);
 int rpf_build_stream_impl(rpf_handle* h, int maxDepth, int minLeaf, int64_t chunk);
 int rpf_project_queries(rpf_handle* h, const double* dQ, int64_t nq, double* d_keysQ);
-int rpf_knn_impl(rpf_handle* h, const double* Q, const int32_t* q_last, int64_t nq, int k, int dedup, double* dist, uint32_t* ids, int32_t* count);
+int rpf_knn_impl(rpf_handle* h, const double* Q, const int32_t* q_last, int64_t nq, int k, int dedup, double* dist, uint32_t* ids, int32_t* count, bool out_dev);
 int rpf_knn_h_impl(rpf_handle* h, const double* Q, const int32_t* q_last, int64_t nq, int k, int cap, double* dist, uint32_t* ids, int32_t* count);
 int rpf_candidates_impl(rpf_handle* h, const double* Q, int64_t nq, int t, int64_t* off_out, const int64_t* off_in, uint32_t* ids);
 int rpf_recall_impl(rpf_handle* h, const double* Q, const int32_t* q_last, int64_t nq, int k, double* recall_sum);
 int rpf_brute_knn_impl(rpf_handle* h, const double* Q, const int32_t* q_last, int64_t nq, int k, double* dist, uint32_t* ids);
 int rpf_merge_impl(rpf_handle* h, int G, int64_t nq, int k, int dedup, const double* dist, const uint32_t* ids,
-                   const int32_t* count, double* dist_out, uint32_t* ids_out, int32_t* count_out);
+                   const int32_t* count, double* dist_out, uint32_t* ids_out, int32_t* count_out, bool in_dev);
 
 // ---- bottom phase launch arguments (build.cu kernels; also filled by stream.cu for Tip re-splits) --------
 typedef unsigned long long ull;

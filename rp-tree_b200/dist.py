@@ -59,6 +59,40 @@ def knnSharded(forest, k, Q, dedup=False, group=None, device=None):
     return forest.mergeTopk(D, I, Cn, dedup=dedup)
 
 
+def knnShardedDevice(forest, k, Q, dedup=False, group=None, device=None, timed=False):
+    """Same result as knnSharded with the exchange kept on the devices: this rank's lists are written into CUDA tensors,
+    all-gathered over NCCL (NVLink), merged by the engine's merge kernel from the gathered device buffer; only the merged
+    nq x k result crosses PCIe.  Returns the merged lists; with timed=True also (device ms of the engine's two calls,
+    device ms of the all-gather from CUDA events on torch's stream)."""
+    import torch
+    dist = _dist()
+    world = dist.get_world_size(group)
+    Q = np.ascontiguousarray(Q, np.float64)
+    nq = Q.shape[0]
+    d = torch.empty((nq, k), dtype=torch.float64, device=device)
+    i = torch.empty((nq, k), dtype=torch.int32, device=device)
+    c = torch.empty((nq,), dtype=torch.int32, device=device)
+    gd = torch.empty((world, nq, k), dtype=torch.float64, device=device)
+    gi = torch.empty((world, nq, k), dtype=torch.int32, device=device)
+    gc = torch.empty((world, nq), dtype=torch.int32, device=device)
+    stream = torch.cuda.current_stream(device)
+    stream.synchronize()                                         # the buffers exist before the engine's stream writes them
+    forest.knnBatchDevice(Q, k, d.data_ptr(), i.data_ptr(), c.data_ptr(), dedup=dedup)
+    ms = forest.lastDeviceMs()
+    ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    dist.all_gather_into_tensor(gd, d, group=group)
+    dist.all_gather_into_tensor(gi, i, group=group)
+    dist.all_gather_into_tensor(gc, c, group=group)
+    ev1.record(stream)
+    stream.synchronize()                                         # gathered lists complete before the engine's stream reads them
+    out = forest.mergeTopkDevice(world, nq, k, gd.data_ptr(), gi.data_ptr(), gc.data_ptr(), dedup=dedup)
+    ms += forest.lastDeviceMs()
+    if timed:
+        return out, ms, ev0.elapsed_time(ev1)
+    return out
+
+
 def recallSharded(forest, k, Q, group=None, device=None):
     """recallWith (RPTree.hs:259-268): per-rank sums over local trees, all-reduced, divided by the forest size."""
     import torch

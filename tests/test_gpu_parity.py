@@ -405,3 +405,28 @@ def test_repeated_builds_replay_the_graph_and_follow_new_data(built):
     f.setOption("cuda_graph", 0)
     f.build(maxd, minl)
     assert not compare_tree(f.treeExport(0), of.export(0))
+
+
+def test_device_resident_exchange_equals_host_exchange(built):
+    """rpf_knn_dev + rpf_merge_topk_dev (lists stay on the device between the two calls, as in the NCCL exchange) give the
+    same merged result as rpf_knn + rpf_merge_topk with host lists."""
+    import torch
+    R, orc = _mods()
+    n, d, T, maxd, minl, pnz, k = 8000, 12, 8, 9, 12, 0.4, 10
+    X = make_data(n, d, 2, "mixture")
+    hp = orc.gen_hyperplanes(77, T, maxd, pnz, d)
+    whole = R.forestBatch(0, maxd, minl, T, pnz, d, X, hyperplanes=hp)
+    Q = X[:64] + 0.01
+    dev = torch.device("cuda", 0)
+    for dedup in (False, True):
+        wd, wi, wc = whole.knnBatch(Q, k, dedup=dedup)
+        G, per = 4, T // 4
+        gd = torch.empty((G, len(Q), k), dtype=torch.float64, device=dev)
+        gi = torch.empty((G, len(Q), k), dtype=torch.int32, device=dev)
+        gc = torch.empty((G, len(Q)), dtype=torch.int32, device=dev)
+        torch.cuda.synchronize()
+        for g in range(G):
+            sh = R.forestBatch(0, maxd, minl, T, pnz, d, X, hyperplanes=hp, t_first=g * per, t_local=per)
+            sh.knnBatchDevice(Q, k, gd[g].data_ptr(), gi[g].data_ptr(), gc[g].data_ptr(), dedup=dedup)
+        md, mi, mc = whole.mergeTopkDevice(G, len(Q), k, gd.data_ptr(), gi.data_ptr(), gc.data_ptr(), dedup=dedup)
+        assert np.array_equal(mc, wc) and np.array_equal(bits(md), bits(wd)) and np.array_equal(mi, wi)
