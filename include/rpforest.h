@@ -154,7 +154,8 @@ int rpf_knn(rpf_handle* h, const double* Q, int64_t nq, int32_t k, int32_t dedup
  * result while the running total stays <= k (the first non-empty one is always taken).  As in the reference the result
  * is neither sorted by distance nor cut to k: count[q] <= cap entries per query, cap >= rpf_knn_h_capacity(h, k) =
  * max(k, largest leaf).  q_last: NULL, or as in rpf_knn_s.  Order among leaves of EQUAL priority is an internal of the
- * `heaps` package in the reference (unpinned); here: tree index, then leaf position. */
+ * `heaps` package in the reference (unpinned); here: tree index, then leaf position.  Limit: trees x (most leaves one
+ * query reaches in one tree) <= 9216. */
 int64_t rpf_knn_h_capacity(const rpf_handle* h, int32_t k);
 int rpf_knn_h(rpf_handle* h, const double* Q, const int32_t* q_last, int64_t nq, int32_t k, int64_t cap,
               double* dist, uint32_t* ids, int32_t* count);

@@ -790,16 +790,18 @@ __global__ void __launch_bounds__(512) k_select_topk(const ull* __restrict__ D, 
 // <= k (the first non-empty pop is always taken).  The result is NOT sorted by distance and NOT cut to k -- it is what
 // the reference returns.  Order among EQUAL priorities is an internal of the `heaps` package (unpinned); here: tree
 // index, then leaf position left to right.
-// One CTA per query; up to HK_MAX reached leaves.
+// One CTA per query; the (tree, leaf) slots of a query (T * S of them, most unused) live in dynamic shared memory.
 // ---------------------------------------------------------------------------------------------------
 #define HK_NT 128
-#define HK_MAX 2048
-__global__ void __launch_bounds__(HK_NT) k_knn_h(QArgs A, const double* __restrict__ prio, int cap) {
-    __shared__ ull skey[HK_MAX];
-    __shared__ uint32_t spos[HK_MAX], sleaf[HK_MAX], soff[HK_MAX];
+#define HK_MAX 9216      /* slots: 20 bytes each next to the query vector */
+__global__ void __launch_bounds__(HK_NT) k_knn_h(QArgs A, const double* __restrict__ prio, int cap, int nslot_cap) {
     __shared__ unsigned s_m, s_total, s_nacc;
     extern __shared__ unsigned char dyn[];
-    double* sq = (double*)dyn;
+    ull* skey = (ull*)dyn;
+    double* sq = (double*)(skey + nslot_cap);
+    uint32_t* spos = (uint32_t*)(sq + ((A.d + 3) & ~3));
+    uint32_t* sleaf = spos + nslot_cap;
+    uint32_t* soff = sleaf + nslot_cap;
     const int64_t q = blockIdx.x;
     const int tid = threadIdx.x;
     if (tid == 0) s_m = 0;
@@ -1052,16 +1054,18 @@ int rpf_knn_h_impl(rpf_handle* h, const double* Q, const int32_t* q_last, int64_
     if (rc) return rc;
     rc = run_descent(h, Q, nq, -1, st);
     if (rc) return rc;
-    if ((int64_t)h->T * st.S > HK_MAX) return rpf_fail(h, RPF_ERR_UNSUPPORTED, "knnH: more than 2048 leaf slots per query");
+    const int64_t nslot = (int64_t)h->T * st.S;
+    if (nslot > HK_MAX) return rpf_fail(h, RPF_ERR_UNSUPPORTED, "knnH: more than 9216 (tree, leaf) slots per query");
     QWS(h, ddist, double, WS_OUT_D, (size_t)nq * cap * 8);
     QWS(h, dids, uint32_t, WS_OUT_I, (size_t)nq * cap * 4);
     QWS(h, dcount, int32_t, WS_OUT_C, (size_t)nq * 4);
     QArgs A = make_qargs(h, nq, st);
     A.k = k; A.dist = ddist; A.ids = dids; A.count = dcount;
-    const size_t dyn = (size_t)((h->d + 3) & ~3) * 8;
-    if (dyn > 160 * 1024) return rpf_fail(h, RPF_ERR_UNSUPPORTED, "knnH: dimension too large");
+    const int nslot_cap = (int)((nslot + 1) & ~(int64_t)1);
+    const size_t dyn = (size_t)((h->d + 3) & ~3) * 8 + (size_t)nslot_cap * 20;
+    if (dyn > 200 * 1024) return rpf_fail(h, RPF_ERR_UNSUPPORTED, "knnH: dimension / leaf slots too large for shared memory");
     RPF_CUDA(h, cudaFuncSetAttribute(k_knn_h, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-    RPF_LAUNCH(h, PH_Q_KNN, k_knn_h, (unsigned)nq, HK_NT, dyn, A, st.prio, cap);
+    RPF_LAUNCH(h, PH_Q_KNN, k_knn_h, (unsigned)nq, HK_NT, dyn, A, st.prio, cap, nslot_cap);
     RPF_CUDA(h, cudaMemcpyAsync(dist, ddist, (size_t)nq * cap * 8, cudaMemcpyDeviceToHost, h->stream));
     RPF_CUDA(h, cudaMemcpyAsync(ids, dids, (size_t)nq * cap * 4, cudaMemcpyDeviceToHost, h->stream));
     if (count) RPF_CUDA(h, cudaMemcpyAsync(count, dcount, (size_t)nq * 4, cudaMemcpyDeviceToHost, h->stream));

@@ -94,6 +94,15 @@ def test_streaming_plan_matches_oracle_chunked_shape(built, n, chunk, maxd, minl
     assert tp["points_lost"] == n - of.tree_size(0)
 
 
+def test_streaming_plan_keeps_every_point_at_the_reference_spec_shape(built):
+    """test/Data/RPTreeSpec.hs:87-92 asserts treeSize == n for `forest` with the rpTreeCfg parameters (n = 10000,
+    minLeaf = 20): the planner must not drop anything there."""
+    import rp_tree_b200 as R
+    cfg = R.rpTreeCfg(20, 10000, 2)
+    tp = R.topologyPlan(10000, cfg.fpMaxTreeDepth, 20, chunk=cfg.fpDataChunkSize)
+    assert tp["points_lost"] == 0 and tp["seg_size"][0] == 10000
+
+
 def test_streaming_plan_rejects_oversized_resplit(built):
     import rp_tree_b200 as R
     with pytest.raises(R.RPForestError):

@@ -430,3 +430,23 @@ def test_device_resident_exchange_equals_host_exchange(built):
             sh.knnBatchDevice(Q, k, gd[g].data_ptr(), gi[g].data_ptr(), gc[g].data_ptr(), dedup=dedup)
         md, mi, mc = whole.mergeTopkDevice(G, len(Q), k, gd.data_ptr(), gi.data_ptr(), gc.data_ptr(), dedup=dedup)
         assert np.array_equal(mc, wc) and np.array_equal(bits(md), bits(wd)) and np.array_equal(mi, wi)
+
+
+def test_reference_spec_conduit_shape(built):
+    """test/Data/RPTreeSpec.hs:87-107 through the engine: `forest` with the rpTreeCfg chunk size on the two-disc data keeps
+    every point in every tree (the reference's own assertion), and knn / knnPQ / knnH of the origin stay below 1."""
+    R, orc = _mods()
+    n, d, T, minl, k = 10000, 2, 10, 20, 5
+    rng = np.random.default_rng(1)
+    th = rng.uniform(0, 2 * np.pi, n); r = np.sqrt(rng.uniform(0, 1, n))
+    X = np.stack([r * np.cos(th), r * np.sin(th)], 1) + np.where(rng.uniform(size=(n, 1)) < 0.5, 0.0, 1.0) * np.array([2.0, 3.0])
+    cfg = R.rpTreeCfg(minl, n, d)
+    assert R.topologyPlan(n, cfg.fpMaxTreeDepth, minl, chunk=cfg.fpDataChunkSize)["points_lost"] == 0
+    f = R.forest(42, cfg.fpMaxTreeDepth, minl, T, cfg.fpDataChunkSize, 1.0, d, X)
+    assert R.treeSize(f) == n and f.pointsLost() == 0
+    for t in range(T):
+        assert np.array_equal(np.sort(R.points(f, t)[:n]), np.arange(n, dtype=np.uint32))
+    q = np.zeros(d)
+    for fn in (R.knn, R.knnPQ, R.knnH):
+        dist, ids = fn(R.metricL2, k, f, q)
+        assert len(dist) >= 1 and dist.max() < 1, fn.__name__
