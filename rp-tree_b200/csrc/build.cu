@@ -40,23 +40,31 @@ __device__ __forceinline__ double lds_f64_off(unsigned a) {
 
 // LD: compile-time row stride in doubles (0 = use the run-time ld): with it the R row addresses of a term are ONE add plus
 // immediate offsets.  hp_pack holds (value, byte offset of the component inside a row = 8 * idx).
+// Column blocks (rows too long for one tile, e.g. d = 768 / 960): a launch covers the columns [c0, c1) only.  The right fold
+// runs from the LAST nonzero to the first, so the host launches the blocks from the highest columns down; every launch
+// but the first resumes from the partial sum the previous one left in `out` (as a raw double), every launch but the
+// last stores the partial sum back, the last one stores the finished key.  The arithmetic -- order and roundings -- is
+// that of the single-tile kernel.  flags: bit 0 = first block of the fold (start from 0), bit 1 = last block.
 template <int NT, int R, bool ORD, int LD>
 __global__ void __launch_bounds__(NT) k_project(const double* __restrict__ X, int64_t n, int d, int ld_rt,
                                                  const int64_t* __restrict__ hp_off, const double2* __restrict__ hp_pack,
                                                  int t0, int L, int hpDepth, int H,
-                                                 void* __restrict__ out, int64_t ostride, ull* __restrict__ kmin, ull* __restrict__ kmax) {
+                                                 void* __restrict__ out, int64_t ostride, ull* __restrict__ kmin, ull* __restrict__ kmax,
+                                                 int c0, int c1, int flags) {
     constexpr int P = 32 * R, NW = NT / 32;
     extern __shared__ double xs[];
     const int ld = LD ? LD : ld_rt;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int64_t i0 = (int64_t)blockIdx.x * P;
     const int rows = (int)min((int64_t)P, n - i0);
+    const int dc = c1 - c0;
+    const bool blocked = dc != d, first = flags & 1, last = flags & 2;
     for (int r = w; r < P; r += NW) {
         if (r < rows) {
-            const double* src = X + (i0 + r) * (int64_t)d;
-            for (int c = lane; c < d; c += 32) xs[r * ld + c] = src[c];
+            const double* src = X + (i0 + r) * (int64_t)d + c0;
+            for (int c = lane; c < dc; c += 32) xs[r * ld + c] = src[c];
         } else {
-            for (int c = lane; c < d; c += 32) xs[r * ld + c] = 0.0;
+            for (int c = lane; c < dc; c += 32) xs[r * ld + c] = 0.0;
         }
     }
     __syncthreads();
@@ -70,7 +78,7 @@ __global__ void __launch_bounds__(NT) k_project(const double* __restrict__ X, in
     const bool track = (blockIdx.x & 7) == 0;
     // write one output row (and fold its min/max) -- warp-uniform call
     auto emit = [&](int j, const double (&acc)[R]) {
-        if (ORD) {
+        if (ORD && last) {
             ull vmin = ORD_NONE_HI, vmax = ORD_NONE_LO;
 #pragma unroll
             for (int r = 0; r < R; ++r) {
@@ -102,7 +110,7 @@ __global__ void __launch_bounds__(NT) k_project(const double* __restrict__ X, in
     };
     // one term of one hyperplane for this lane's R points: acc = val * x[idx] + acc  (separate roundings, right fold)
     auto term = [&](const double2 hv, double (&acc)[R]) {
-        const unsigned c = (unsigned)__double_as_longlong(hv.y);
+        const unsigned c = (unsigned)__double_as_longlong(hv.y) - 8u * (unsigned)c0;
         double x[R];
         if constexpr (LD != 0) {
             const unsigned a0 = rowaddr[0] + c;
@@ -128,12 +136,32 @@ __global__ void __launch_bounds__(NT) k_project(const double* __restrict__ X, in
         int64_t eA = hp_off[rowA + 1], eB = hp_off[rowB + 1];
         if (eA - sA > d) eA = sA + d;               // innerSD's `i >= nz2` guard (Internal.hs:376)
         if (eB - sB > d) eB = sB + d;
-        int cA = (int)(eA - sA), cB = hasB ? (int)(eB - sB) : 0;
+        int64_t bA = sA, bB = sB;                   // nonzeros of this column block: [bA, eA) / [bB, eB)
+        if (blocked) {
+            // component offsets (8 * idx) ascend inside a row: cut [s, e) down to the offsets in [8 c0, 8 c1)
+            auto lower = [&](int64_t lo, int64_t hi, long long key) {
+                while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (__double_as_longlong(__ldg(hp_pack + mid).y) < key) lo = mid + 1; else hi = mid; }
+                return lo;
+            };
+            eA = lower(sA, eA, 8ll * c1); bA = lower(sA, eA, 8ll * c0);
+            eB = lower(sB, eB, 8ll * c1); bB = lower(sB, eB, 8ll * c0);
+        }
+        int cA = (int)(eA - bA), cB = hasB ? (int)(eB - bB) : 0;
         const double2* hA = hp_pack + eA - 1;       // right fold: innermost (last) term first
         const double2* hB = hp_pack + eB - 1;
         double accA[R], accB[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) { accA[r] = 0.0; accB[r] = 0.0; }
+        if (!first) {                               // resume from the partial sums of the higher column blocks
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int64_t i = i0 + lane + 32 * r;
+                if (i < n) {
+                    accA[r] = ((const double*)out)[(int64_t)j * ostride + i];
+                    if (hasB) accB[r] = ((const double*)out)[(int64_t)jB * ostride + i];
+                }
+            }
+        }
         // the (value, offset) pair of the NEXT term is requested before the current term's loads and adds are issued
         double2 a = cA > 0 ? __ldg(hA) : make_double2(0.0, 0.0), b2 = cB > 0 ? __ldg(hB) : make_double2(0.0, 0.0);
         while (cA > 1 && cB > 1) {
@@ -191,14 +219,23 @@ __global__ void __launch_bounds__(256) k_project_direct(const double* __restrict
     }
 }
 
+// nblk column blocks of at most dcmax columns each, launched from the highest columns down (see k_project)
 template <int NT, int R, bool ORD, int LD = 0>
-static int launch_project(rpf_handle* h, int phase, const double* dX, int64_t n, int t0, int L, int H, void* out, int64_t ostride, ull* kmin, ull* kmax) {
-    const int d = h->d, ld = d | 1;
+static int launch_project(rpf_handle* h, int phase, const double* dX, int64_t n, int t0, int L, int H, void* out, int64_t ostride, ull* kmin, ull* kmax,
+                          int nblk = 1) {
+    const int d = h->d;
+    const int dcmax = (d + nblk - 1) / nblk, ld = dcmax | 1;
     const size_t smem = (size_t)32 * R * ld * sizeof(double);
     auto kfn = k_project<NT, R, ORD, LD>;
     RPF_CUDA(h, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t grid = (n + 32 * R - 1) / (32 * R);
-    RPF_LAUNCH(h, phase, kfn, (unsigned)grid, NT, smem, dX, n, d, ld, h->d_hp_off, (const double2*)h->d_hp_pack, t0, L, h->hpDepth, H, out, ostride, kmin, kmax);
+    for (int b = nblk - 1; b >= 0; --b) {
+        const int c0 = b * dcmax, c1 = std::min(d, c0 + dcmax);
+        if (c1 <= c0) continue;
+        const int flags = (b == nblk - 1 || c1 == d ? 1 : 0) | (b == 0 ? 2 : 0);
+        RPF_LAUNCH(h, phase, kfn, (unsigned)grid, NT, smem, dX, n, d, ld, h->d_hp_off, (const double2*)h->d_hp_pack, t0, L, h->hpDepth, H, out, ostride,
+                   kmin, kmax, c0, c1, flags);
+    }
     return RPF_OK;
 }
 
@@ -227,6 +264,14 @@ int rpf_project_launch(rpf_handle* h, int phase, const double* dX, int64_t n, in
     if (32 * row <= 110 * 1024)
         return ord ? launch_project<256, 1, true>(h, phase, dX, n, t0, L, H, out, ostride, kmin, kmax)
                    : launch_project<256, 1, false>(h, phase, dX, n, t0, L, H, out, ostride, kmin, kmax);
+    if (h->project_variant != 3) {
+        // long rows (d = 768, 960, ...): 64-point tiles over column blocks of <= ~270 columns, partial sums carried in `out`
+        int nblk = 2;
+        while ((size_t)64 * ((size_t)((d + nblk - 1) / nblk) | 1) * 8 > 140 * 1024) ++nblk;
+        if (nblk <= 64)
+            return ord ? launch_project<512, 2, true>(h, phase, dX, n, t0, L, H, out, ostride, kmin, kmax, nblk)
+                       : launch_project<512, 2, false>(h, phase, dX, n, t0, L, H, out, ostride, kmin, kmax, nblk);
+    }
     const int64_t grid = (n + 31) / 32;
     if (ord) {
         RPF_LAUNCH(h, phase, k_project_direct<true>, (unsigned)grid, 256, 0, dX, n, d, h->d_hp_off, (const double2*)h->d_hp_pack, t0, L, h->hpDepth, H, out, ostride, kmin, kmax);

@@ -45,6 +45,8 @@ BUILD_CASES = [
     pytest.param(30000, 2, 4, 11, 11, 0.4, "gauss", 4096, id="cap4096-empty-hyperplanes"),
     pytest.param(3000, 1100, 2, 5, 40, 0.02, "gauss", 1024, id="large-d-direct-projection"),
     pytest.param(2500, 300, 2, 6, 20, 0.05, "gauss", 1024, id="d300-r1-tile"),
+    pytest.param(4000, 960, 2, 7, 30, 0.1, "gauss", 1024, id="d960-column-blocked-projection"),
+    pytest.param(3000, 769, 2, 6, 30, 0.1, "mixture", 1024, id="d769-odd-column-blocks"),
     pytest.param(30000, 8, 3, 12, 8, 0.5, "outlier", 1024, id="one-outlier-collapses-key-prefixes"),
     pytest.param(30000, 8, 3, 12, 8, 0.5, "outlier", 2048, id="one-outlier-collapses-key-prefixes-cap2048"),
 ]
@@ -91,6 +93,22 @@ def test_all_points_in_every_tree(built):
     # knn of the origin is close (RPTreeSpec.hs:69-74 checks < 1 on its 2-cluster data; here: finds the true 1-NN region)
     dist, ids = R.knn(R.metricL2, 5, f, np.zeros(d))
     assert len(dist) == 5 and np.all(np.diff(dist) >= 0)
+
+
+def test_direct_projection_kernel_still_exact(built):
+    """The per-row fallback kernel (no shared-memory tile; selected here with project_variant = 3)."""
+    R, orc = _mods()
+    n, d, T, maxd, minl = 3000, 1100, 2, 5, 40
+    X = make_data(n, d, 3)
+    hp = orc.gen_hyperplanes(4, T, maxd, 0.02, d)
+    f = R.forestBatch(0, maxd, minl, T, 0.02, d, X, hyperplanes=hp, options={"project_variant": 3})
+    of = orc.Forest(X, hp, T, maxd, minl)
+    for t in range(T):
+        assert not compare_tree(f.treeExport(t), of.export(t))
+    Q = X[:8] + 0.01
+    off, ids = f.candidatesBatch(Q, -1)
+    for i in range(8):
+        assert np.array_equal(ids[off[i]:off[i + 1]], np.concatenate([of.candidates(t, Q[i]) for t in range(T)]))
 
 
 def test_projection_matches_oracle_fold_order(built):

@@ -11,6 +11,8 @@ X = bench.make_points(n, d, W["data_seed"], W["clusters"], W["sigma"])
 for T in [int(a) for a in sys.argv[1:]] or [4, 8, 16]:
     hp = R.sampleHyperplanes(W["forest_seed"], T, maxd, W["pnz"], d)
     f = R.RPForest(0); f.setHyperplanes(hp, T, maxd); f.setPoints(X)
+    if os.environ.get('RPF_PROJECT_VARIANT'):
+        f.setOption('project_variant', int(os.environ['RPF_PROJECT_VARIANT']))
     for i in range(4):
         f.build(maxd, W["min_leaf"])
     ms = f.lastDeviceMs()
