@@ -255,22 +255,26 @@ int rpf_project_launch(rpf_handle* h, int phase, const double* dX, int64_t n, in
     if (ld == 129)      // d = 128: compile-time row stride
         return ord ? launch_project<1024, 4, true, 129>(h, phase, dX, n, t0, L, H, out, ostride, kmin, kmax)
                    : launch_project<1024, 4, false, 129>(h, phase, dX, n, t0, L, H, out, ostride, kmin, kmax);
-    if (128 * row <= 140 * 1024)
-        return ord ? launch_project<1024, 4, true>(h, phase, dX, n, t0, L, H, out, ostride, kmin, kmax)
-                   : launch_project<1024, 4, false>(h, phase, dX, n, t0, L, H, out, ostride, kmin, kmax);
-    if (64 * row <= 110 * 1024)
-        return ord ? launch_project<256, 2, true>(h, phase, dX, n, t0, L, H, out, ostride, kmin, kmax)
-                   : launch_project<256, 2, false>(h, phase, dX, n, t0, L, H, out, ostride, kmin, kmax);
-    if (32 * row <= 110 * 1024)
-        return ord ? launch_project<256, 1, true>(h, phase, dX, n, t0, L, H, out, ostride, kmin, kmax)
-                   : launch_project<256, 1, false>(h, phase, dX, n, t0, L, H, out, ostride, kmin, kmax);
     if (h->project_variant != 3) {
-        // long rows (d = 768, 960, ...): 64-point tiles over column blocks of <= ~270 columns, partial sums carried in `out`
-        int nblk = 2;
-        while ((size_t)64 * ((size_t)((d + nblk - 1) / nblk) | 1) * 8 > 140 * 1024) ++nblk;
-        if (nblk <= 64)
-            return ord ? launch_project<512, 2, true>(h, phase, dX, n, t0, L, H, out, ostride, kmin, kmax, nblk)
-                       : launch_project<512, 2, false>(h, phase, dX, n, t0, L, H, out, ostride, kmin, kmax, nblk);
+        // 128-point tiles (4 points per lane); rows too long for one tile (d > 139: 200, 768, 960, ...) go in column
+        // blocks of <= 139 columns with the partial sums carried in `out`.  Tuning hooks: variant 4 / 6 = 32- / 64-point
+        // tiles (fewer, wider blocks) -- measured slower: 4 chains per lane matter more than the extra passes over `out`.
+        // (measured, 400 k points x 16 trees: d = 200: one 64-point tile 1.12 ms vs 128 x 2 blocks 1.62; d = 500: 128 x 4 blocks
+        //  3.85 ms vs 64 x 2 blocks 6.24; d = 960: 128 x 8 blocks 3.2 ms vs 64 x 4 blocks 6.0)
+        const bool one64 = (size_t)64 * row <= 140 * 1024;      // a single 64-point tile beats two passes of 128-point tiles
+        const int pts = h->project_variant == 4 ? 32 : ((h->project_variant == 6 || (h->project_variant == 0 && one64)) ? 64 : 128);
+        int nblk = 1;
+        while ((size_t)pts * ((size_t)((d + nblk - 1) / nblk) | 1) * 8 > 140 * 1024) ++nblk;
+        if (nblk <= 128) {
+            if (pts == 32)
+                return ord ? launch_project<256, 1, true>(h, phase, dX, n, t0, L, H, out, ostride, kmin, kmax, nblk)
+                           : launch_project<256, 1, false>(h, phase, dX, n, t0, L, H, out, ostride, kmin, kmax, nblk);
+            if (pts == 64)
+                return ord ? launch_project<512, 2, true>(h, phase, dX, n, t0, L, H, out, ostride, kmin, kmax, nblk)
+                           : launch_project<512, 2, false>(h, phase, dX, n, t0, L, H, out, ostride, kmin, kmax, nblk);
+            return ord ? launch_project<1024, 4, true>(h, phase, dX, n, t0, L, H, out, ostride, kmin, kmax, nblk)
+                       : launch_project<1024, 4, false>(h, phase, dX, n, t0, L, H, out, ostride, kmin, kmax, nblk);
+        }
     }
     const int64_t grid = (n + 31) / 32;
     if (ord) {
