@@ -46,6 +46,7 @@ foreign import ccall safe "rpf_last_error"        c_lastErr  :: Ptr RpfHandle ->
 foreign import ccall safe "rpf_set_points"        c_setPts   :: Ptr RpfHandle -> Ptr CDouble -> Int64 -> Int32 -> IO CInt
 foreign import ccall safe "rpf_set_hyperplanes"   c_setHp    :: Ptr RpfHandle -> Int32 -> Int32 -> Ptr Int64 -> Ptr Int32 -> Ptr CDouble -> IO CInt
 foreign import ccall safe "rpf_build"             c_build    :: Ptr RpfHandle -> Int32 -> Int32 -> IO CInt
+foreign import ccall safe "rpf_build_from_host"   c_buildH   :: Ptr RpfHandle -> Ptr CDouble -> Int64 -> Int32 -> Int32 -> Int32 -> IO CInt
 foreign import ccall safe "rpf_build_chunked"     c_buildCh  :: Ptr RpfHandle -> Int32 -> Int32 -> Int64 -> IO CInt
 foreign import ccall safe "rpf_num_nodes"         c_numNodes :: Ptr RpfHandle -> IO Int64
 foreign import ccall safe "rpf_topology"          c_topology :: Ptr RpfHandle -> Ptr Int64 -> Ptr Int32 -> Ptr Int64 -> Ptr Int64 -> IO CInt
@@ -97,12 +98,15 @@ buildWith chunk seed maxd minl ntrees pnz dim xs = withDevice 0 $ \fh -> withFor
         pure $ IM.fromList $ zip [0 ..] rvs
       (off, idx, val) = csrOf rvss
       buf = packRows xs
-  VS.unsafeWith buf $ \p -> c_setPts h p (fromIntegral (V.length xs)) (fromIntegral dim) >>= check h "rpf_set_points"
   withArray off $ \po -> withArray idx $ \pi' -> withArray val $ \pv ->
     c_setHp h (fromIntegral ntrees) (fromIntegral maxd) po pi' pv >>= check h "rpf_set_hyperplanes"
   case chunk of
-    Nothing -> c_build h (fromIntegral maxd) (fromIntegral minl) >>= check h "rpf_build"
-    Just c  -> c_buildCh h (fromIntegral maxd) (fromIntegral minl) (fromIntegral c) >>= check h "rpf_build_chunked"
+    -- batch: one call uploads the rows in blocks and projects them as they arrive
+    Nothing -> VS.unsafeWith buf $ \p ->
+                 c_buildH h p (fromIntegral (V.length xs)) (fromIntegral dim) (fromIntegral maxd) (fromIntegral minl) >>= check h "rpf_build_from_host"
+    Just c  -> do
+      VS.unsafeWith buf $ \p -> c_setPts h p (fromIntegral (V.length xs)) (fromIntegral dim) >>= check h "rpf_set_points"
+      c_buildCh h (fromIntegral maxd) (fromIntegral minl) (fromIntegral c) >>= check h "rpf_build_chunked"
   pure (GpuForest fh xs rvss ntrees maxd)
 
 -- | 'Data.RPTree.Batch.forestBatch' (Batch.hs:48-63).
