@@ -425,6 +425,8 @@ struct TopArgs {
     int64_t nn_all;                                                         // nodes per tree (stride of thr/mlo/mhi)
     const ull* keys;
     uint16_t* label;
+    uint16_t* pbin;                  // [Tg][n] bin of every point's key at the current level (written by k_top_hist): lets
+                                     // k_top_compact / k_top_relabel stream 2 bytes per point instead of the 8-byte key
     const int32_t* child;
     const uint32_t* nstart;
     const uint32_t* nsize;
@@ -533,6 +535,38 @@ __device__ __forceinline__ void stream_points(const TopArgs& A, const ull* __res
     }
 }
 
+// streaming access to (bin, label) of the points of one tree: 4 points per thread per step (two 8-byte loads), two steps in
+// flight; f(i, bin, node)
+template <typename F>
+__device__ __forceinline__ void stream_bins(const TopArgs& A, const uint16_t* __restrict__ pb, const uint16_t* lab, int64_t i0, int64_t i1, F&& f) {
+    if ((A.n & 3) == 0) {
+        const int64_t step = 4 * TOP_NT;
+        auto ld4 = [&](int64_t i, unsigned (&b)[4], int (&g)[4]) {
+            const uint2 q = *(const uint2*)(pb + i);
+            b[0] = q.x & 0xffff; b[1] = q.x >> 16; b[2] = q.y & 0xffff; b[3] = q.y >> 16;
+            if (A.haslab) { const uint2 r = *(const uint2*)(lab + i); g[0] = r.x & 0xffff; g[1] = r.x >> 16; g[2] = r.y & 0xffff; g[3] = r.y >> 16; }
+            else { g[0] = g[1] = g[2] = g[3] = 0; }
+        };
+        int64_t i = i0 + 4 * (int64_t)threadIdx.x;
+        for (; i + step < i1; i += 2 * step) {
+            unsigned ba[4], bb[4]; int ga[4], gb[4];
+            ld4(i, ba, ga); ld4(i + step, bb, gb);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) f(i + u, ba[u], ga[u]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) f(i + step + u, bb[u], gb[u]);
+        }
+        if (i < i1) {
+            unsigned ba[4]; int ga[4];
+            ld4(i, ba, ga);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) f(i + u, ba[u], ga[u]);
+        }
+    } else {
+        for (int64_t i = i0 + threadIdx.x; i < i1; i += TOP_NT) f(i, (unsigned)pb[i], A.haslab ? (int)lab[i] : 0);
+    }
+}
+
 __global__ void __launch_bounds__(TOP_NT) k_top_hist(TopArgs A) {
     extern __shared__ uint32_t sh[];
     const int t = blockIdx.y, tid = threadIdx.x;
@@ -546,14 +580,42 @@ __global__ void __launch_bounds__(TOP_NT) k_top_hist(TopArgs A) {
         for (int j = tid; j < (tot + 1) / 2; j += TOP_NT) sh[j] = 0;
         __syncthreads();
     }
-    stream_points(A, keys, lab, i0, i1, [&](int64_t, ull kv, int g) {
+    uint16_t* pb = A.pbin + (int64_t)t * A.n;
+    auto one = [&](ull kv, int g) -> unsigned {        // counts the point, returns its bin (0 when it sits in no splitting node)
         const int nl = node_of(A, g);
-        if (nl < 0) return;
+        if (nl < 0) return 0u;
         const int b = key_bin(kv, lo, sc, NB);
         const int j = nl * NB + b;
         if (A.smem_hist) atomicAdd(&sh[j >> 1], 1u << ((j & 1) << 4));
         else atomicAdd(&gh[j], 1u);
-    });
+        return (unsigned)b;
+    };
+    if (A.vec) {
+        const int64_t step = 4 * TOP_NT;
+        int64_t i = i0 + 4 * (int64_t)tid;
+        for (; i + step < i1; i += 2 * step) {
+            Pt4 a, b;
+            load_pt4(A, keys, lab, i, a);
+            load_pt4(A, keys, lab, i + step, b);
+            unsigned ba[4], bb[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) ba[u] = one(a.k[u], (int)a.g[u]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) bb[u] = one(b.k[u], (int)b.g[u]);
+            *(uint2*)(pb + i) = make_uint2(ba[0] | (ba[1] << 16), ba[2] | (ba[3] << 16));
+            *(uint2*)(pb + i + step) = make_uint2(bb[0] | (bb[1] << 16), bb[2] | (bb[3] << 16));
+        }
+        if (i < i1) {
+            Pt4 a;
+            load_pt4(A, keys, lab, i, a);
+            unsigned ba[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) ba[u] = one(a.k[u], (int)a.g[u]);
+            *(uint2*)(pb + i) = make_uint2(ba[0] | (ba[1] << 16), ba[2] | (ba[3] << 16));
+        }
+    } else {
+        for (int64_t i = i0 + tid; i < i1; i += TOP_NT) pb[i] = (uint16_t)one(keys[i], A.haslab ? (int)lab[i] : 0);
+    }
     if (A.smem_hist) {
         __syncthreads();
         for (int w2 = tid; w2 < (tot + 1) / 2; w2 += TOP_NT) {
@@ -642,14 +704,15 @@ __global__ void __launch_bounds__(TOP_NT) k_top_compact(TopArgs A) {
         __syncthreads();
     }
     ull* cand = A.cand + (int64_t)t * A.n;
-    stream_points(A, keys, lab, i0, i1, [&](int64_t, ull kv, int g) {
+    const uint16_t* pb = A.pbin + (int64_t)t * A.n;
+    (void)lo; (void)sc;
+    stream_bins(A, pb, lab, i0, i1, [&](int64_t i, unsigned b, int g) {
         const int nl = node_of(A, g);
         if (nl < 0) return;
-        const int b = key_bin(kv, lo, sc, A.NB);
         const int sb = cached ? s_bin[nl] : sel[nl].sel_bin;
-        if (b == sb) {
+        if ((int)b == sb) {                      // about one point in NB: only these keys are read
             const uint32_t pos = atomicAdd(&sel[nl].cand_fill, 1u);
-            cand[sel[nl].cand_off + pos] = kv;
+            cand[sel[nl].cand_off + pos] = keys[i];
         }
     });
 }
@@ -823,6 +886,7 @@ __global__ void __launch_bounds__(512) k_top_ties(TopArgs A) {
 __global__ void __launch_bounds__(TOP_NT, RELABEL_MINB) k_top_relabel(TopArgs A, int last) {
     __shared__ ull s_thr[SMEM_NODES], s_pred[SMEM_NODES], s_succ[SMEM_NODES];
     __shared__ uint32_t s_tie[SMEM_NODES];
+    __shared__ uint16_t s_sbin[SMEM_NODES];
     __shared__ uint32_t s_cnt[SCAT_MAX], s_base[SCAT_MAX];
     const int t = blockIdx.y, tid = threadIdx.x;
     const int64_t i0 = (int64_t)blockIdx.x * TOP_CH, i1 = min(A.n, i0 + TOP_CH);
@@ -836,6 +900,7 @@ __global__ void __launch_bounds__(TOP_NT, RELABEL_MINB) k_top_relabel(TopArgs A,
     if (cached) {
         for (int j = tid; j < A.nnodes; j += TOP_NT) {
             s_thr[j] = sel[j].thr; s_pred[j] = sel[j].pred; s_succ[j] = sel[j].succ; s_tie[j] = sel[j].tie_r;
+            s_sbin[j] = (uint16_t)sel[j].sel_bin;
         }
     }
     __syncthreads();
@@ -894,7 +959,67 @@ __global__ void __launch_bounds__(TOP_NT, RELABEL_MINB) k_top_relabel(TopArgs A,
         }
         return g;
     };
-    if (A.vec) {
+    // fast path: the side of the split follows from the point's BIN unless it sits in the median bin (monotone binning:
+    // bin < median bin => key < thr, bin > median bin => key > thr), so only ~1 key in NB is read
+    const uint16_t* pb = A.pbin + (int64_t)t * A.n;
+    auto relabel_bin = [&](int64_t i, unsigned b, int g) -> int {
+        const int nl = g - A.node0;
+        if ((unsigned)nl < (unsigned)A.nnodes) {
+            const unsigned sb = s_sbin[nl];
+            bool left = b < sb;
+            if (b == sb) {
+                const ull kv = keys[i], thr = s_thr[nl];
+                left = kv < thr;
+                if (kv == thr && s_tie[nl] > 0) {   // composite compare against the tie pivot (rare)
+                    const int td = sel[nl].tie_depth;
+                    const ull* piv = A.pivots + ((int64_t)t * A.NTOP + g) * A.MAXTD;
+                    for (int j = 0; j < td; ++j) {
+                        const int lvl = A.l - 1 - j;
+                        const ull kq = lvl >= 0 ? keys_t[(int64_t)lvl * A.ks + i] : (ull)i;
+                        const ull pv = piv[j];
+                        if (kq != pv) { left = kq < pv; break; }
+                    }
+                }
+            }
+            g = A.child0 + 2 * nl + (left ? 0 : 1);
+        }
+        if (last) {
+            if (sf) atomicAdd(&s_cnt[g - A.child0], 1u);
+            else { const uint32_t pos = atomicAdd(&fill[g], 1u); perm[A.nstart[g] + pos] = (uint32_t)i; }
+        }
+        return g;
+    };
+    if (fast && (A.n & 3) == 0) {
+        const int64_t step = 4 * TOP_NT;
+        auto ld4 = [&](int64_t i, unsigned (&b)[4], int (&g)[4]) {
+            const uint2 q = *(const uint2*)(pb + i);
+            b[0] = q.x & 0xffff; b[1] = q.x >> 16; b[2] = q.y & 0xffff; b[3] = q.y >> 16;
+            if (A.haslab) { const uint2 r = *(const uint2*)(lab + i); g[0] = r.x & 0xffff; g[1] = r.x >> 16; g[2] = r.y & 0xffff; g[3] = r.y >> 16; }
+            else { g[0] = g[1] = g[2] = g[3] = 0; }
+        };
+        int64_t i = i0 + 4 * (int64_t)tid;
+        for (; i + step < i1; i += 2 * step) {
+            unsigned ba[4], bb[4]; int ia[4], ib[4];
+            ld4(i, ba, ia); ld4(i + step, bb, ib);
+            uint32_t ga[4], gb[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) ga[u] = (uint32_t)relabel_bin(i + u, ba[u], ia[u]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) gb[u] = (uint32_t)relabel_bin(i + step + u, bb[u], ib[u]);
+            *(uint2*)(lab + i) = make_uint2(ga[0] | (ga[1] << 16), ga[2] | (ga[3] << 16));
+            *(uint2*)(lab + i + step) = make_uint2(gb[0] | (gb[1] << 16), gb[2] | (gb[3] << 16));
+        }
+        if (i < i1) {
+            unsigned ba[4]; int ia[4];
+            ld4(i, ba, ia);
+            uint32_t ga[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) ga[u] = (uint32_t)relabel_bin(i + u, ba[u], ia[u]);
+            *(uint2*)(lab + i) = make_uint2(ga[0] | (ga[1] << 16), ga[2] | (ga[3] << 16));
+        }
+    } else if (fast) {
+        for (int64_t i = i0 + tid; i < i1; i += TOP_NT) lab[i] = (uint16_t)relabel_bin(i, (unsigned)pb[i], A.haslab ? (int)lab[i] : 0);
+    } else if (A.vec) {
         const int64_t step = 4 * TOP_NT;
         int64_t i = i0 + 4 * (int64_t)tid;
         for (; i + step < i1; i += 2 * step) {
@@ -934,7 +1059,7 @@ __global__ void __launch_bounds__(TOP_NT, RELABEL_MINB) k_top_relabel(TopArgs A,
             const uint32_t pos = s_base[j] + atomicAdd(&s_cnt[j], 1u);
             perm[A.nstart[g] + pos] = (uint32_t)i;
         };
-        if (A.vec) {
+        if ((A.n & 3) == 0 && (fast || A.vec)) {
             for (int64_t i = i0 + 4 * (int64_t)tid; i < i1; i += 4 * TOP_NT) {
                 const uint2 q = *(const uint2*)(lab + i);          // labels written by this same thread above
                 place(i, (int)(q.x & 0xffff)); place(i + 1, (int)(q.x >> 16)); place(i + 2, (int)(q.y & 0xffff)); place(i + 3, (int)(q.y >> 16));
@@ -1556,7 +1681,7 @@ void rpf_job_geometry(const Topology& tp, int cap_cfg, int Lk, JobGeom& G) {
     }
 }
 size_t rpf_job_ws_per_tree(const JobGeom& G, int64_t n) {
-    return (G.s_top > 0 ? (size_t)n * 10 : 0) + (size_t)G.HSZ * 4 + (size_t)G.NTOP * (sizeof(NodeSel) + 4 + (size_t)G.MAXTD * 8) + 4096;
+    return (G.s_top > 0 ? (size_t)n * 12 : 0) + (size_t)G.HSZ * 4 + (size_t)G.NTOP * (sizeof(NodeSel) + 4 + (size_t)G.MAXTD * 8) + 4096;
 }
 
 // Host half of a job: geometry, per-level flags and the device tables (bottom-phase ranges, histogram shapes) appended
@@ -1625,6 +1750,7 @@ int rpf_launch_job(rpf_handle* h, BuildJob& J, const JobPlan& P, const char* tab
 
     if (s_top > 0) {
         uint16_t* label = (uint16_t*)h->ws_get(WS_LABEL, (size_t)tg * n * 2);
+        uint16_t* pbin = (uint16_t*)h->ws_get(WS_PBIN, (size_t)tg * n * 2);
         uint32_t* hist = (uint32_t*)h->ws_get(WS_HIST, (size_t)tg * HSZ * 4);
         NodeSel* sel = (NodeSel*)h->ws_get(WS_SEL, (size_t)tg * NTOP * sizeof(NodeSel));
         ull* cand = (ull*)h->ws_get(WS_CAND, (size_t)tg * n * 8);
@@ -1637,11 +1763,11 @@ int rpf_launch_job(rpf_handle* h, BuildJob& J, const JobPlan& P, const char* tab
         uint32_t* fill = (uint32_t*)h->ws_get(WS_FILL, (size_t)tg * NTOP * 4);
         double* binlo = (double*)h->ws_get(WS_BINLO, (size_t)tg * J.Lk * 8);
         double* binscale = (double*)h->ws_get(WS_BINSC, (size_t)tg * J.Lk * 8);
-        if (!label || !hist || !sel || !cand || !cand_total || !pivots || !fill || !binlo || !binscale) return RPF_ERR_NOMEM;
+        if (!label || !pbin || !hist || !sel || !cand || !cand_total || !pivots || !fill || !binlo || !binscale) return RPF_ERR_NOMEM;
         TopArgs A{};
         A.n = n; A.ks = J.ks; A.ps = J.ps; A.Tg = tg; A.L = J.Lk; A.NTOP = (int)NTOP; A.HSZ = (int)HSZ; A.MAXTD = MAXTD; A.gt0 = J.gt0; A.nn_all = J.ns;
         A.vec = ((n & 3) == 0 && (J.ks & 3) == 0 && ((uintptr_t)J.keys & 31) == 0) ? 1 : 0;
-        A.keys = J.keys; A.label = label; A.child = J.d_child; A.nstart = J.d_start;
+        A.keys = J.keys; A.label = label; A.pbin = pbin; A.child = J.d_child; A.nstart = J.d_start;
         A.nsize = J.d_size; A.binlo = binlo; A.binscale = binscale;
         A.kmin = J.kmin; A.kmax = J.kmax; A.hist = hist; A.sel = sel;
         A.cand = cand; A.cand_total = cand_total; A.track_any = cand_total + tg; A.pivots = pivots;

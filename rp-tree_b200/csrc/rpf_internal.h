@@ -105,7 +105,7 @@ enum rpf_ws_slot {
     WS_NBDEV, WS_RANGE, WS_LVLPV, WS_HPPACK,
     WS_Q, WS_KEYSQ, WS_SEGS, WS_CNT, WS_MAXCNT, WS_OUT_D, WS_OUT_I, WS_OUT_C, WS_BF_D, WS_TRUTH_D, WS_TRUTH_I, WS_RECALL,
     WS_CANDCNT, WS_CANDOFF, WS_CANDOUT, WS_MRG_D, WS_MRG_I, WS_MRG_C, WS_QHIST, WS_QORDER,
-    WS_S_ARENA0, WS_S_ARENA1, WS_S_CPERM, WS_S_TMPN, WS_S_POOL, WS_QLAST, WS_PRIO, WS_WORKLIST,
+    WS_S_ARENA0, WS_S_ARENA1, WS_S_CPERM, WS_S_TMPN, WS_S_POOL, WS_QLAST, WS_PRIO, WS_WORKLIST, WS_PBIN,
     WS_COUNT
 };
 struct WsBuf { void* p = nullptr; size_t cap = 0; };
