@@ -410,7 +410,8 @@ struct NodeSel {
     int32_t sel_bin;
     uint32_t below, cand_off, cand_cnt, cand_fill, cless, ceq, tie_r;
     int32_t tie_depth;
-    int32_t pad_;
+    uint16_t lo_bin, hi_bin;         // nearest non-empty bins below / above the median bin when sorted[nh-1] / sorted[nh+1]
+                                     // lie outside it (0xffff: not needed); read by the lean relabel kernels
 };
 
 struct TopArgs {
@@ -463,6 +464,31 @@ __device__ __forceinline__ int key_bin(ull o, double lo, double sc, int NB) {
     double v = (ord2f(o) - lo) * sc;
     int b = (int)v;
     return b < 0 ? 0 : (b >= NB ? NB - 1 : b);
+}
+
+// Called by one whole warp.  When the margin neighbours sorted[nh-1] / sorted[nh+1] lie outside the median bin they are
+// the largest key of the nearest non-empty bin below / the smallest key of the nearest non-empty bin above (monotone
+// binning): find those bins in the node's histogram so that the relabel pass only reads the keys of these bins.
+__device__ __forceinline__ void warp_track_bins(const TopArgs& A, NodeSel& S, int t, int nl, bool need_pred, bool need_succ) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t* hr = A.hist + (int64_t)t * A.HSZ + (int64_t)nl * A.NB;
+    const int sb = S.sel_bin;
+    int lo = 0xffff, hi = 0xffff;
+    if (need_pred) {
+        for (int b0 = sb - 1; b0 >= 0; b0 -= 32) {
+            const int b = b0 - lane;
+            const unsigned m = __ballot_sync(0xffffffffu, b >= 0 && hr[b] != 0);
+            if (m) { lo = b0 - (__ffs(m) - 1); break; }
+        }
+    }
+    if (need_succ) {
+        for (int b0 = sb + 1; b0 < A.NB; b0 += 32) {
+            const int b = b0 + lane;
+            const unsigned m = __ballot_sync(0xffffffffu, b < A.NB && hr[b] != 0);
+            if (m) { hi = b0 + (__ffs(m) - 1); break; }
+        }
+    }
+    if (lane == 0) { S.lo_bin = (uint16_t)lo; S.hi_bin = (uint16_t)hi; }
 }
 
 // per (tree, level): linear bin map from the key range
@@ -746,19 +772,21 @@ __global__ void __launch_bounds__(FW_WARPS * 32) k_top_finish_warp(TopArgs A) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) { const uint32_t i = lane * 8 + e; if (i < c) { lt += v[e] < thr; eq += v[e] == thr; } }
     for (int off = 16; off > 0; off >>= 1) { lt += __shfl_xor_sync(0xffffffffu, lt, off); eq += __shfl_xor_sync(0xffffffffu, eq, off); }
+    const uint32_t lower = lt, upper = lt + eq;
+    const ull pred = lower > 0 ? buf[wi][lower - 1] : ORD_NONE_LO;
+    const ull succ = upper < c ? buf[wi][upper] : ORD_NONE_HI;
+    const uint32_t cless = S.below + lower;
+    const bool need_pred = (cless == nh) && pred == ORD_NONE_LO;
+    const bool need_succ = (cless + eq == nh + 1) && succ == ORD_NONE_HI;
     if (lane == 0) {
-        const uint32_t lower = lt, upper = lt + eq;
-        const ull pred = lower > 0 ? buf[wi][lower - 1] : ORD_NONE_LO;
-        const ull succ = upper < c ? buf[wi][upper] : ORD_NONE_HI;
         S.thr = thr; S.pred = pred; S.succ = succ;
-        S.cless = S.below + lower; S.ceq = eq;
-        S.tie_r = nh - S.cless;
+        S.cless = cless; S.ceq = eq;
+        S.tie_r = nh - cless;
         S.tie_depth = 0;
-        if (S.tie_r > 0) A.wl_tie[atomicAdd(&A.wl_cnt[1], 1u)] = (uint32_t)item;
-        const bool need_pred = (S.cless == nh) && pred == ORD_NONE_LO;
-        const bool need_succ = (S.cless + eq == nh + 1) && succ == ORD_NONE_HI;
+        if (nh > cless) A.wl_tie[atomicAdd(&A.wl_cnt[1], 1u)] = (uint32_t)item;
         if (need_pred || need_succ) atomicOr(&A.track_any[t], 1u);
     }
+    warp_track_bins(A, S, t, nl, need_pred, need_succ);
 }
 
 // exact order statistic inside the median bin for the bins with more than FW_MAX keys: the CTAs walk the work list
@@ -809,18 +837,20 @@ __global__ void __launch_bounds__(512) k_top_finish(TopArgs A) {
         __syncthreads();
         pred = sh64[1]; succ = sh64[2];
     }
+    // sorted[nh-1] / sorted[nh+1] are taken from the bin's sorted keys; only when they fall outside the bin must
+    // k_top_relabel track the nearest keys below / above the threshold (they sit in the nearest non-empty bins)
+    const uint32_t cless = S.below + lower;
+    const bool need_pred = (cless == nh) && pred == ORD_NONE_LO;
+    const bool need_succ = (cless + ceq == nh + 1) && succ == ORD_NONE_HI;
     if (tid == 0) {
         S.thr = thr; S.pred = pred; S.succ = succ;
-        S.cless = S.below + lower; S.ceq = ceq;
-        S.tie_r = nh - S.cless;      // tied points that must go left; > 0 => the split cuts through a tie
+        S.cless = cless; S.ceq = ceq;
+        S.tie_r = nh - cless;        // tied points that must go left; > 0 => the split cuts through a tie
         S.tie_depth = 0;
-        if (S.tie_r > 0) A.wl_tie[atomicAdd(&A.wl_cnt[1], 1u)] = item;
-        // sorted[nh-1] / sorted[nh+1] are taken from the bin's sorted keys; only when they fall outside the bin must
-        // k_top_relabel track the nearest keys below / above the threshold over all points of the node
-        const bool need_pred = (S.cless == nh) && pred == ORD_NONE_LO;
-        const bool need_succ = (S.cless + ceq == nh + 1) && succ == ORD_NONE_HI;
+        if (nh > cless) A.wl_tie[atomicAdd(&A.wl_cnt[1], 1u)] = item;
         if (need_pred || need_succ) atomicOr(&A.track_any[t], 1u);
     }
+    if (tid < 32) warp_track_bins(A, S, t, nl, need_pred, need_succ);
     }
 }
 
@@ -1074,6 +1104,297 @@ __global__ void __launch_bounds__(TOP_NT, RELABEL_MINB) k_top_relabel(TopArgs A,
             if (s_pred[j] > sel[j].pred) atomicMax(&sel[j].pred, s_pred[j]);
             if (s_succ[j] < sel[j].succ) atomicMin(&sel[j].succ, s_succ[j]);
         }
+    }
+}
+
+// ---- lean top-phase kernels --------------------------------------------------------------------------------------
+// Used when the level's nodes all split, fit the shared-memory tables (<= SMEM_NODES) and n % 8 == 0 (16-byte rows of
+// 2-byte bins / labels).  They stream 8 points per load (one 16-byte load of bins + one of labels, every load of a CTA
+// chunk in flight at once) and touch an 8-byte key only for a point in the median bin or in a margin-tracking bin
+// (NodeSel::lo_bin / hi_bin), so no level has to fall back to streaming the keys.
+struct LeanTabs { ull thr[SMEM_NODES]; uint16_t sbin[SMEM_NODES], lob[SMEM_NODES], hib[SMEM_NODES]; };
+
+__device__ __forceinline__ void lean_load_tabs(const TopArgs& A, const NodeSel* sel, LeanTabs& T, int nthreads) {
+    for (int j = threadIdx.x; j < A.nnodes; j += nthreads) {
+        T.thr[j] = sel[j].thr;
+        T.sbin[j] = (uint16_t)sel[j].sel_bin; T.lob[j] = sel[j].lo_bin; T.hib[j] = sel[j].hi_bin;
+    }
+}
+
+// Sides of the split for 8 consecutive points i..i+7 (bins b, local node indices nl; nl outside [0, nnodes) = the point
+// does not sit in a node of this level).  Bit u of the result: point u goes to the RIGHT child.  The bin decides unless
+// the point sits in the median bin; the keys of median-bin and margin-tracking-bin points are fetched together (all
+// loads issued before the first use: one memory latency per 8 points instead of one per hit).
+__device__ __forceinline__ unsigned lean_sides8(const TopArgs& A, NodeSel* sel, const LeanTabs& T, const ull* __restrict__ keys,
+                                                const ull* __restrict__ keys_t, int t, int64_t i, const unsigned (&b)[8], const int (&nl)[8]) {
+    unsigned right = 0, kind = 0;               // kind: 2 bits per point (1 median bin, 2 tracked bin below, 3 tracked bin above)
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        if ((unsigned)nl[u] < (unsigned)A.nnodes) {
+            const unsigned sb = T.sbin[nl[u]];
+            if (b[u] >= sb) right |= 1u << u;
+            const unsigned k = b[u] == sb ? 1u : (b[u] == T.lob[nl[u]] ? 2u : (b[u] == T.hib[nl[u]] ? 3u : 0u));
+            kind |= k << (2 * u);
+        }
+    }
+    if (kind == 0) return right;
+    ull kv[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) kv[u] = ((kind >> (2 * u)) & 3u) ? __ldg(keys + i + u) : 0ull;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const unsigned k = (kind >> (2 * u)) & 3u;
+        if (k == 1u) {
+            const ull thr = T.thr[nl[u]];
+            bool left = kv[u] < thr;
+            if (kv[u] == thr && sel[nl[u]].tie_r > 0) {   // composite compare against the tie pivot (rare)
+                const int td = sel[nl[u]].tie_depth;
+                const ull* piv = A.pivots + ((int64_t)t * A.NTOP + A.node0 + nl[u]) * A.MAXTD;
+                for (int j = 0; j < td; ++j) {
+                    const int lvl = A.l - 1 - j;
+                    const ull kq = lvl >= 0 ? keys_t[(int64_t)lvl * A.ks + i + u] : (ull)(i + u);
+                    const ull pv = piv[j];
+                    if (kq != pv) { left = kq < pv; break; }
+                }
+            }
+            if (left) right &= ~(1u << u);
+        } else if (k == 2u) {                   // every key of a lower bin is < thr; the largest one is sorted[nh-1]
+            if (kv[u] > *(volatile ull*)&sel[nl[u]].pred) atomicMax(&sel[nl[u]].pred, kv[u]);
+        } else if (k == 3u) {
+            if (kv[u] < *(volatile ull*)&sel[nl[u]].succ) atomicMin(&sel[nl[u]].succ, kv[u]);
+        }
+    }
+    return right;
+}
+
+__device__ __forceinline__ void unpack8(const uint4 q, unsigned (&v)[8]) {
+    v[0] = q.x & 0xffff; v[1] = q.x >> 16; v[2] = q.y & 0xffff; v[3] = q.y >> 16;
+    v[4] = q.z & 0xffff; v[5] = q.z >> 16; v[6] = q.w & 0xffff; v[7] = q.w >> 16;
+}
+__device__ __forceinline__ uint4 pack8(const unsigned (&g)[8]) {
+    return make_uint4(g[0] | (g[1] << 16), g[2] | (g[3] << 16), g[4] | (g[5] << 16), g[6] | (g[7] << 16));
+}
+
+// relabel (levels before the last top level): 6 bytes of traffic per point
+#define LEAN_IT (TOP_CH / (8 * TOP_NT))
+#ifndef LEAN_G
+#define LEAN_G 2          /* 16-byte load pairs in flight per thread */
+#endif
+__global__ void __launch_bounds__(TOP_NT, 2) k_top_relabel_lean(TopArgs A) {
+    __shared__ LeanTabs T;
+    const int t = blockIdx.y, tid = threadIdx.x;
+    const int64_t i0 = (int64_t)blockIdx.x * TOP_CH, i1 = min(A.n, i0 + TOP_CH);
+    const ull* keys_t = A.keys + (int64_t)t * A.L * A.ks;
+    const ull* keys = keys_t + (int64_t)A.l * A.ks;
+    uint16_t* lab = A.label + (int64_t)t * A.n;
+    const uint16_t* pb = A.pbin + (int64_t)t * A.n;
+    NodeSel* sel = A.sel + (int64_t)t * A.NTOP + A.node0;
+    lean_load_tabs(A, sel, T, TOP_NT);
+    __syncthreads();
+    for (int it0 = 0; it0 < LEAN_IT; it0 += LEAN_G) {
+        uint4 qb[LEAN_G], ql[LEAN_G];
+#pragma unroll
+        for (int k = 0; k < LEAN_G; ++k) {
+            const int64_t i = i0 + ((int64_t)(it0 + k) * TOP_NT + tid) * 8;
+            if (i < i1) {
+                qb[k] = __ldcs((const uint4*)(pb + i));
+                ql[k] = A.haslab ? *(const uint4*)(lab + i) : make_uint4(0, 0, 0, 0);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < LEAN_G; ++k) {
+            const int64_t i = i0 + ((int64_t)(it0 + k) * TOP_NT + tid) * 8;
+            if (i < i1) {
+                unsigned b[8], g[8];
+                int nl[8];
+                unpack8(qb[k], b); unpack8(ql[k], g);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) nl[u] = (int)g[u] - A.node0;
+                const unsigned right = lean_sides8(A, sel, T, keys, keys_t, t, i, b, nl);
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    if ((unsigned)nl[u] < (unsigned)A.nnodes) g[u] = A.child0 + 2 * nl[u] + ((right >> u) & 1u);
+                *(uint4*)(lab + i) = pack8(g);
+            }
+        }
+    }
+}
+
+// last top level: children instead of labels, and the points are placed into their child's slice of perm.  The CTA's
+// chunk is bucketed by child in shared memory first, so a warp writes runs of consecutive perm entries (full sectors)
+// instead of 32 scattered 4-byte stores.  Order inside a slice is irrelevant: the bottom phase sorts it.
+#ifndef SCAT_NT
+#define SCAT_NT 512
+#endif
+#ifndef SCAT_CH
+#define SCAT_CH 16384     /* points per CTA: 64 KB staging buffer, two CTAs per SM */
+#endif
+#define SCAT_IT (SCAT_CH / (8 * SCAT_NT))
+#define SCAT_PER (SCAT_MAX / SCAT_NT)
+__global__ void __launch_bounds__(SCAT_NT, 2) k_top_scatter_lean(TopArgs A) {
+    extern __shared__ uint32_t s_stage[];                       // [SCAT_CH] (child << 15) | local point index
+    __shared__ LeanTabs T;
+    __shared__ uint32_t s_cnt[SCAT_MAX], s_off[SCAT_MAX], s_dst[SCAT_MAX];
+    __shared__ uint32_t s_wsum[32];
+    const int t = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int64_t i0 = (int64_t)blockIdx.x * SCAT_CH, i1 = min(A.n, i0 + SCAT_CH);
+    const ull* keys_t = A.keys + (int64_t)t * A.L * A.ks;
+    const ull* keys = keys_t + (int64_t)A.l * A.ks;
+    const uint16_t* lab = A.label + (int64_t)t * A.n;
+    const uint16_t* pb = A.pbin + (int64_t)t * A.n;
+    NodeSel* sel = A.sel + (int64_t)t * A.NTOP + A.node0;
+    const int nch = 2 * A.nnodes;
+    uint4 qb[SCAT_IT], ql[SCAT_IT];
+#pragma unroll
+    for (int it = 0; it < SCAT_IT; ++it) {
+        const int64_t i = i0 + ((int64_t)it * SCAT_NT + tid) * 8;
+        if (i < i1) {
+            qb[it] = __ldcs((const uint4*)(pb + i));
+            ql[it] = A.haslab ? __ldcs((const uint4*)(lab + i)) : make_uint4(0, 0, 0, 0);
+        }
+    }
+    lean_load_tabs(A, sel, T, SCAT_NT);
+    for (int j = tid; j < nch; j += SCAT_NT) s_cnt[j] = 0;
+    if (tid < 32) s_wsum[tid] = 0;
+    __syncthreads();
+    // pass 1: child of every point (kept in registers, 16 bits each), per-child counts of this chunk
+    uint32_t cj[SCAT_IT][4];
+#pragma unroll
+    for (int it = 0; it < SCAT_IT; ++it) {
+        const int64_t i = i0 + ((int64_t)it * SCAT_NT + tid) * 8;
+        if (i < i1) {
+            unsigned b[8], g[8];
+            int nl[8];
+            unpack8(qb[it], b); unpack8(ql[it], g);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) nl[u] = (int)g[u] - A.node0;       // scatter_fast: every point sits in a node of this level
+            const unsigned right = lean_sides8(A, sel, T, keys, keys_t, t, i, b, nl);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                g[u] = min(2u * (unsigned)nl[u] + ((right >> u) & 1u), (unsigned)(nch - 1));
+                atomicAdd(&s_cnt[g[u]], 1u);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) cj[it][u] = g[2 * u] | (g[2 * u + 1] << 16);
+        }
+    }
+    __syncthreads();
+    // exclusive scan of the counts (SCAT_PER consecutive children per thread); reserve the chunk's range in every child's slice
+    {
+        uint32_t c[SCAT_PER], s = 0;
+#pragma unroll
+        for (int e = 0; e < SCAT_PER; ++e) { const int j = SCAT_PER * tid + e; c[e] = j < nch ? s_cnt[j] : 0u; s += c[e]; }
+        uint32_t incl = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+        if (lane == 31) s_wsum[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            uint32_t w = s_wsum[lane], wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += y; }
+            s_wsum[lane] = wi - w;
+        }
+        __syncthreads();
+        uint32_t ex = s_wsum[wid] + incl - s;
+        uint32_t* fill = A.fill + (int64_t)t * A.NTOP;
+#pragma unroll
+        for (int e = 0; e < SCAT_PER; ++e) {
+            const int j = SCAT_PER * tid + e;
+            if (j < nch) {
+                s_off[j] = ex;
+                s_dst[j] = A.nstart[A.child0 + j] + (c[e] ? atomicAdd(&fill[A.child0 + j], c[e]) : 0u) - ex;
+                s_cnt[j] = 0;
+            }
+            ex += c[e];
+        }
+    }
+    __syncthreads();
+    // pass 2: bucket the chunk by child
+#pragma unroll
+    for (int it = 0; it < SCAT_IT; ++it) {
+        const int64_t i = i0 + ((int64_t)it * SCAT_NT + tid) * 8;
+        if (i < i1) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const unsigned j = (cj[it][u >> 1] >> ((u & 1) << 4)) & 0xffffu;
+                const uint32_t slot = s_off[j] + atomicAdd(&s_cnt[j], 1u);
+                s_stage[slot] = (j << 15) | (uint32_t)((it * SCAT_NT + tid) * 8 + u);
+            }
+        }
+    }
+    __syncthreads();
+    // pass 3: consecutive threads write consecutive entries of a child's slice
+    uint32_t* perm = A.perm + (int64_t)t * A.ps;
+    const int npts = (int)(i1 - i0);
+    for (int sl = tid; sl < npts; sl += SCAT_NT) {
+        const uint32_t e = s_stage[sl];
+        perm[s_dst[e >> 15] + sl] = (uint32_t)i0 + (e & 0x7fffu);
+    }
+}
+
+// gather the median bins' keys: the chunk's hits are listed in shared memory, every node's range is reserved with one
+// atomic per (CTA, node), then all keys are fetched at once (no atomic -> store chain inside the streaming loop)
+#define CL_CAP 8192
+__global__ void __launch_bounds__(TOP_NT, 3) k_top_compact_lean(TopArgs A) {
+    __shared__ uint16_t s_sbin[SMEM_NODES];
+    __shared__ uint32_t s_cnt[SMEM_NODES], s_base[SMEM_NODES];
+    extern __shared__ uint32_t s_list[];                         // [CL_CAP] (node << 15) | local point index
+    uint16_t* s_rank = (uint16_t*)(s_list + CL_CAP);             // [CL_CAP] position among the chunk's hits of that node
+    __shared__ uint32_t s_n;
+    const int t = blockIdx.y, tid = threadIdx.x;
+    const int64_t i0 = (int64_t)blockIdx.x * TOP_CH, i1 = min(A.n, i0 + TOP_CH);
+    const ull* keys = A.keys + ((int64_t)t * A.L + A.l) * A.ks;
+    const uint16_t* lab = A.label + (int64_t)t * A.n;
+    const uint16_t* pb = A.pbin + (int64_t)t * A.n;
+    NodeSel* sel = A.sel + (int64_t)t * A.NTOP + A.node0;
+    ull* cand = A.cand + (int64_t)t * A.n;
+    for (int j = tid; j < A.nnodes; j += TOP_NT) { s_sbin[j] = (uint16_t)sel[j].sel_bin; s_cnt[j] = 0; }
+    if (tid == 0) s_n = 0;
+    __syncthreads();
+    for (int it0 = 0; it0 < LEAN_IT; it0 += LEAN_G) {
+        uint4 qb[LEAN_G], ql[LEAN_G];
+#pragma unroll
+        for (int k = 0; k < LEAN_G; ++k) {
+            const int64_t i = i0 + ((int64_t)(it0 + k) * TOP_NT + tid) * 8;
+            if (i < i1) {
+                qb[k] = *(const uint4*)(pb + i);
+                ql[k] = A.haslab ? *(const uint4*)(lab + i) : make_uint4(0, 0, 0, 0);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < LEAN_G; ++k) {
+            const int64_t i = i0 + ((int64_t)(it0 + k) * TOP_NT + tid) * 8;
+            if (i < i1) {
+                unsigned b[8], g[8];
+                unpack8(qb[k], b); unpack8(ql[k], g);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int nl = (int)g[u] - A.node0;
+                    if ((unsigned)nl < (unsigned)A.nnodes && b[u] == s_sbin[nl]) {
+                        const uint32_t q = atomicAdd(&s_n, 1u);
+                        if (q < CL_CAP) {
+                            s_rank[q] = (uint16_t)atomicAdd(&s_cnt[nl], 1u);
+                            s_list[q] = ((uint32_t)nl << 15) | (uint32_t)(((it0 + k) * TOP_NT + tid) * 8 + u);
+                        } else {                             // list full (a chunk dominated by median-bin points)
+                            const uint32_t pos = atomicAdd(&sel[nl].cand_fill, 1u);
+                            cand[sel[nl].cand_off + pos] = keys[i + u];
+                        }
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int j = tid; j < A.nnodes; j += TOP_NT) {
+        const uint32_t c = s_cnt[j];
+        if (c) s_base[j] = sel[j].cand_off + atomicAdd(&sel[j].cand_fill, c);
+    }
+    __syncthreads();
+    const uint32_t nq = min(s_n, (uint32_t)CL_CAP);
+    for (uint32_t q = tid; q < nq; q += TOP_NT) {
+        const uint32_t e = s_list[q];
+        cand[s_base[e >> 15] + s_rank[q]] = keys[i0 + (e & 0x7fffu)];
     }
 }
 
@@ -1774,6 +2095,8 @@ int rpf_launch_job(rpf_handle* h, BuildJob& J, const JobPlan& P, const char* tab
         A.wl_cnt = cand_total + 2 * tg; A.wl_big = wl; A.wl_tie = wl + (size_t)tg * max_lvl_nodes;
         A.fill = fill; A.perm = J.perm; A.thr = J.thr; A.mlo = J.mlo; A.mhi = J.mhi;
         RPF_CUDA(h, cudaFuncSetAttribute(k_top_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, HBINS * 2));
+        RPF_CUDA(h, cudaFuncSetAttribute(k_top_compact_lean, cudaFuncAttributeMaxDynamicSharedMemorySize, CL_CAP * 6));
+        RPF_CUDA(h, cudaFuncSetAttribute(k_top_scatter_lean, cudaFuncAttributeMaxDynamicSharedMemorySize, SCAT_CH * 4));
         RPF_LAUNCH(h, PH_MISC, k_bin_setup, (unsigned)((tg * J.Lk + 127) / 128), 128, 0, A, nbdev, s_top);
         RPF_CUDA(h, cudaMemsetAsync(fill, 0, (size_t)tg * NTOP * 4, h->stream));
         if (P.nroots > 1) RPF_LAUNCH(h, PH_MISC, k_label_roots, (unsigned)((n + 255) / 256), 256, 0, label, n, tg, J.d_start, P.nroots);
@@ -1794,12 +2117,19 @@ int rpf_launch_job(rpf_handle* h, BuildJob& J, const JobPlan& P, const char* tab
             RPF_LAUNCH(h, PH_TOP_HIST, k_top_hist, gs, TOP_NT, hs, A);
             if (A.NB <= 256) RPF_LAUNCH(h, PH_TOP_PICK, k_top_pick_warp, (unsigned)(((int64_t)A.nnodes * tg + 7) / 8), 256, 0, A);
             else RPF_LAUNCH(h, PH_TOP_PICK, k_top_pick, gn, 256, 0, A);
-            RPF_LAUNCH(h, PH_TOP_COMPACT, k_top_compact, gs, TOP_NT, 0, A);
+            // lean kernels (16-byte rows of bins / labels, shared-memory node tables): see k_top_relabel_lean
+            const bool lean = h->lean_top && (n & 7) == 0 && A.nnodes <= SMEM_NODES && A.all_internal;
+            const bool last = l == s_top - 1;
+            if (lean) RPF_LAUNCH(h, PH_TOP_COMPACT, k_top_compact_lean, gs, TOP_NT, CL_CAP * 6, A);
+            else RPF_LAUNCH(h, PH_TOP_COMPACT, k_top_compact, gs, TOP_NT, 0, A);
             RPF_LAUNCH(h, PH_TOP_FINISH, k_top_finish_warp, (unsigned)(((int64_t)A.nnodes * tg + FW_WARPS - 1) / FW_WARPS), FW_WARPS * 32, 0, A);
             const unsigned gw = (unsigned)std::min<int64_t>((int64_t)A.nnodes * tg, 592);      // work-list walkers
             RPF_LAUNCH(h, PH_TOP_FINISH, k_top_finish, gw, 512, 0, A);
             RPF_LAUNCH(h, PH_TOP_TIES, k_top_ties, gw, 512, 0, A);
-            RPF_LAUNCH(h, PH_TOP_RELABEL, k_top_relabel, gs, TOP_NT, 0, A, (int)(l == s_top - 1));
+            if (lean && !last) RPF_LAUNCH(h, PH_TOP_RELABEL, k_top_relabel_lean, gs, TOP_NT, 0, A);
+            else if (lean && A.scatter_fast)
+                RPF_LAUNCH(h, PH_TOP_RELABEL, k_top_scatter_lean, dim3((unsigned)((n + SCAT_CH - 1) / SCAT_CH), (unsigned)tg), SCAT_NT, (size_t)SCAT_CH * 4, A);
+            else RPF_LAUNCH(h, PH_TOP_RELABEL, k_top_relabel, gs, TOP_NT, 0, A, (int)last);
             RPF_LAUNCH(h, PH_MISC, k_top_finalize, (unsigned)((A.nnodes * tg + 127) / 128), 128, 0, A);
         }
     } else {

@@ -147,6 +147,7 @@ struct rpf_handle {
     int project_variant = 0;             // tuning hook: 0 = 1024 threads x 4 points/lane, 1 = 1024 x 2 (two CTAs/SM), 2 = 512 x 4
     bool no_query_order = false;         // test/tuning hook: answer queries in input order (no locality grouping)
     bool force_simple_knn = false;       // test hook: per-thread gather knn kernel instead of the TMA ring
+    bool lean_top = true;                // option "lean_top": 0 = generic top-phase compact / relabel kernels only (test hook)
     bool force_generic_bottom = false;   // test hook: run the generic (entry-table) bottom kernel
     bool bottom_words64 = false;         // test hook: 64-bit sort words in the fast bottom kernel even for <= 2048 slots
 

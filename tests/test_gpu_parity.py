@@ -66,6 +66,41 @@ def test_build_parity(built, n, d, T, maxd, minl, pnz, kind, cap, generic):
         assert order
 
 
+GENERIC_TOP_CASES = [c for c in BUILD_CASES if c.id in (
+    "top4-bottom", "top7-cap256", "integer-data-massive-ties", "duplicate-rows", "cap4096-integer-ties",
+    "one-outlier-collapses-key-prefixes", "cap8192-top4")]
+
+
+@pytest.mark.parametrize("n,d,T,maxd,minl,pnz,kind,cap", GENERIC_TOP_CASES)
+def test_build_parity_generic_top_kernels(built, n, d, T, maxd, minl, pnz, kind, cap):
+    """n % 8 == 0 selects the lean top-phase kernels (k_top_compact_lean / k_top_relabel_lean / k_top_scatter_lean);
+    option lean_top = 0 keeps the generic streaming kernels covered on the same shapes."""
+    R, orc = _mods()
+    X = make_data(n, d, 3, kind)
+    hp = orc.gen_hyperplanes(1235137 + 3, T, maxd, pnz, d)
+    f = R.forestBatch(0, maxd, minl, T, pnz, d, X, hyperplanes=hp, bottom_cap=cap, options={"lean_top": 0})
+    of = orc.Forest(X, hp, T, maxd, minl)
+    for t in range(T):
+        bad = compare_tree(f.treeExport(t), of.export(t), check_order=f.leafOrderExact())
+        assert not bad, "tree %d: %s" % (t, bad)
+
+
+@pytest.mark.parametrize("n", [65536 + 8, 32768, 98304 + 4096])
+def test_lean_top_chunk_edges(built, n):
+    """chunk boundaries of the lean kernels (32768-point chunks: exact multiples, an 8-point tail, a partial chunk),
+    clustered keys that overflow the per-chunk hit list of k_top_compact_lean (integer data) and a wide forest."""
+    R, orc = _mods()
+    for kind, d, T in (("mixture", 12, 5), ("integer", 3, 2)):
+        maxd, minl, pnz = 11, 12, 0.5
+        X = make_data(n, d, 17, kind)
+        hp = orc.gen_hyperplanes(77, T, maxd, pnz, d)
+        f = R.forestBatch(0, maxd, minl, T, pnz, d, X, hyperplanes=hp, bottom_cap=512)
+        of = orc.Forest(X, hp, T, maxd, minl)
+        for t in range(T):
+            bad = compare_tree(f.treeExport(t), of.export(t), check_order=f.leafOrderExact())
+            assert not bad, "%s n=%d tree %d: %s" % (kind, n, t, bad)
+
+
 @pytest.mark.parametrize("n", [0, 1, 2, 3, 4, 5])
 def test_tiny_inputs(built, n):
     R, orc = _mods()

@@ -19,6 +19,8 @@ hp = R.sampleHyperplanes(W["forest_seed"], T, maxd, W["pnz"], d)
 f = R.RPForest(0)
 if os.environ.get("RPF_PROJECT_VARIANT"):
     f.setOption("project_variant", int(os.environ["RPF_PROJECT_VARIANT"]))
+if os.environ.get("RPF_LEAN_TOP"):
+    f.setOption("lean_top", int(os.environ["RPF_LEAN_TOP"]))
 if os.environ.get("RPF_BOTTOM_CAP"):
     f.setBottomCap(int(os.environ["RPF_BOTTOM_CAP"]))
 f.setHyperplanes(hp, T, maxd)
