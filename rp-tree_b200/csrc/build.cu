@@ -417,6 +417,7 @@ struct NodeSel {
 struct TopArgs {
     int64_t n;                       // points of this job (labels, cand are [Tg][n])
     int64_t ks, ps;                  // element stride between key rows / between the trees' slices of perm
+    int ch;                          // points per CTA of the streaming kernels (8192 .. TOP_CH: small tree groups use small chunks to fill the SMs)
     int vec;                         // key rows and labels are 32-byte / 8-byte aligned: 4-point vector accesses allowed
     int haslab;                      // labels are valid (level > 0, or a job with several roots); else every point sits in node 0
     int Tg, L, l, node0, nnodes, NTOP, NB, HSZ, MAXTD, smem_hist, gt0;   // gt0: global tree id of the group's first tree
@@ -596,7 +597,7 @@ __device__ __forceinline__ void stream_bins(const TopArgs& A, const uint16_t* __
 __global__ void __launch_bounds__(TOP_NT) k_top_hist(TopArgs A) {
     extern __shared__ uint32_t sh[];
     const int t = blockIdx.y, tid = threadIdx.x;
-    const int64_t i0 = (int64_t)blockIdx.x * TOP_CH, i1 = min(A.n, i0 + TOP_CH);
+    const int64_t i0 = (int64_t)blockIdx.x * A.ch, i1 = min(A.n, i0 + A.ch);
     const ull* keys = A.keys + ((int64_t)t * A.L + A.l) * A.ks;
     const uint16_t* lab = A.label + (int64_t)t * A.n;
     const double lo = A.binlo[t * A.L + A.l], sc = A.binscale[t * A.L + A.l];
@@ -652,33 +653,49 @@ __global__ void __launch_bounds__(TOP_NT) k_top_hist(TopArgs A) {
     }
 }
 
-// one CTA per (node, tree): find the bin holding rank nh = size/2
+// one CTA per (node, tree): find the bin holding rank nh = size/2.  Thread j sums a contiguous range of bins, a
+// shuffle scan over the 256 partial sums names the range that covers the rank, warp 0 then scans that range.
 __global__ void __launch_bounds__(256) k_top_pick(TopArgs A) {
-    __shared__ uint32_t part[256];
-    __shared__ uint32_t excl[257];
-    const int t = blockIdx.y, nl = blockIdx.x, g = A.node0 + nl, tid = threadIdx.x;
+    __shared__ uint32_t wsum[8];
+    __shared__ uint32_t own[2];
+    const int t = blockIdx.y, nl = blockIdx.x, g = A.node0 + nl, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (A.child[g] < 0) return;
     const uint32_t k = A.nsize[g] >> 1;
     const uint32_t* hr = A.hist + (int64_t)t * A.HSZ + (int64_t)nl * A.NB;
     const int per = (A.NB + 255) / 256;
     const int b0 = tid * per, b1 = min(A.NB, b0 + per);
     uint32_t s = 0;
+#pragma unroll 8
     for (int b = b0; b < b1; ++b) s += hr[b];
-    part[tid] = s;
+    uint32_t incl = s;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += y; }
+    if (lane == 31) wsum[wid] = incl;
+    if (tid == 0) { own[0] = 0; own[1] = 0; }
     __syncthreads();
-    if (tid == 0) { uint32_t c = 0; for (int j = 0; j < 256; ++j) { excl[j] = c; c += part[j]; } excl[256] = c; }
+    uint32_t wofs = 0;
+    for (int j = 0; j < wid; ++j) wofs += wsum[j];
+    const uint32_t excl = wofs + incl - s;
+    if (k >= excl && k < excl + s) { own[0] = (uint32_t)b0; own[1] = excl; }     // exactly one thread
     __syncthreads();
-    if (k >= excl[tid] && k < excl[tid] + part[tid]) {
-        uint32_t c = excl[tid];
-        for (int b = b0; b < b1; ++b) {
-            uint32_t hb = hr[b];
-            if (k < c + hb) {
+    if (wid == 0) {
+        const int ob0 = (int)own[0], ob1 = min(A.NB, ob0 + per);
+        uint32_t c = own[1];
+        for (int base = ob0; base < ob1; base += 32) {
+            const int b = base + lane;
+            const uint32_t hb = b < ob1 ? hr[b] : 0u;
+            uint32_t in2 = hb;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, in2, off); if (lane >= off) in2 += y; }
+            const uint32_t ex2 = c + in2 - hb;
+            const bool hit = hb > 0 && k >= ex2 && k < ex2 + hb;
+            if (hit) {
                 NodeSel& S = A.sel[(int64_t)t * A.NTOP + g];
-                S.sel_bin = b; S.below = c; S.cand_cnt = hb; S.cand_fill = 0;
+                S.sel_bin = b; S.below = ex2; S.cand_cnt = hb; S.cand_fill = 0;
                 S.cand_off = atomicAdd(&A.cand_total[t], hb);
-                break;
             }
-            c += hb;
+            if (__any_sync(0xffffffffu, hit)) break;
+            c += __shfl_sync(0xffffffffu, in2, 31);
         }
     }
 }
@@ -719,7 +736,7 @@ __global__ void __launch_bounds__(256) k_top_pick_warp(TopArgs A) {
 __global__ void __launch_bounds__(TOP_NT) k_top_compact(TopArgs A) {
     __shared__ int s_bin[SMEM_NODES];
     const int t = blockIdx.y, tid = threadIdx.x;
-    const int64_t i0 = (int64_t)blockIdx.x * TOP_CH, i1 = min(A.n, i0 + TOP_CH);
+    const int64_t i0 = (int64_t)blockIdx.x * A.ch, i1 = min(A.n, i0 + A.ch);
     const ull* keys = A.keys + ((int64_t)t * A.L + A.l) * A.ks;
     const uint16_t* lab = A.label + (int64_t)t * A.n;
     const double lo = A.binlo[t * A.L + A.l], sc = A.binscale[t * A.L + A.l];
@@ -919,7 +936,7 @@ __global__ void __launch_bounds__(TOP_NT, RELABEL_MINB) k_top_relabel(TopArgs A,
     __shared__ uint16_t s_sbin[SMEM_NODES];
     __shared__ uint32_t s_cnt[SCAT_MAX], s_base[SCAT_MAX];
     const int t = blockIdx.y, tid = threadIdx.x;
-    const int64_t i0 = (int64_t)blockIdx.x * TOP_CH, i1 = min(A.n, i0 + TOP_CH);
+    const int64_t i0 = (int64_t)blockIdx.x * A.ch, i1 = min(A.n, i0 + A.ch);
     const ull* keys_t = A.keys + (int64_t)t * A.L * A.ks;
     const ull* keys = keys_t + (int64_t)A.l * A.ks;
     uint16_t* lab = A.label + (int64_t)t * A.n;
@@ -1176,14 +1193,14 @@ __device__ __forceinline__ uint4 pack8(const unsigned (&g)[8]) {
 }
 
 // relabel (levels before the last top level): 6 bytes of traffic per point
-#define LEAN_IT (TOP_CH / (8 * TOP_NT))
+#define LEAN_IT (A.ch / (8 * TOP_NT))       /* A.ch is a multiple of 8 * TOP_NT * LEAN_G */
 #ifndef LEAN_G
 #define LEAN_G 2          /* 16-byte load pairs in flight per thread */
 #endif
 __global__ void __launch_bounds__(TOP_NT, 2) k_top_relabel_lean(TopArgs A) {
     __shared__ LeanTabs T;
     const int t = blockIdx.y, tid = threadIdx.x;
-    const int64_t i0 = (int64_t)blockIdx.x * TOP_CH, i1 = min(A.n, i0 + TOP_CH);
+    const int64_t i0 = (int64_t)blockIdx.x * A.ch, i1 = min(A.n, i0 + A.ch);
     const ull* keys_t = A.keys + (int64_t)t * A.L * A.ks;
     const ull* keys = keys_t + (int64_t)A.l * A.ks;
     uint16_t* lab = A.label + (int64_t)t * A.n;
@@ -1343,7 +1360,7 @@ __global__ void __launch_bounds__(TOP_NT, 3) k_top_compact_lean(TopArgs A) {
     uint16_t* s_rank = (uint16_t*)(s_list + CL_CAP);             // [CL_CAP] position among the chunk's hits of that node
     __shared__ uint32_t s_n;
     const int t = blockIdx.y, tid = threadIdx.x;
-    const int64_t i0 = (int64_t)blockIdx.x * TOP_CH, i1 = min(A.n, i0 + TOP_CH);
+    const int64_t i0 = (int64_t)blockIdx.x * A.ch, i1 = min(A.n, i0 + A.ch);
     const ull* keys = A.keys + ((int64_t)t * A.L + A.l) * A.ks;
     const uint16_t* lab = A.label + (int64_t)t * A.n;
     const uint16_t* pb = A.pbin + (int64_t)t * A.n;
@@ -2100,7 +2117,12 @@ int rpf_launch_job(rpf_handle* h, BuildJob& J, const JobPlan& P, const char* tab
         RPF_LAUNCH(h, PH_MISC, k_bin_setup, (unsigned)((tg * J.Lk + 127) / 128), 128, 0, A, nbdev, s_top);
         RPF_CUDA(h, cudaMemsetAsync(fill, 0, (size_t)tg * NTOP * 4, h->stream));
         if (P.nroots > 1) RPF_LAUNCH(h, PH_MISC, k_label_roots, (unsigned)((n + 255) / 256), 256, 0, label, n, tg, J.d_start, P.nroots);
-        const unsigned nchunks = (unsigned)((n + TOP_CH - 1) / TOP_CH);
+        // chunk per CTA: the full TOP_CH amortises the shared-memory histogram flush best; a small tree group (the shard
+        // of an 8-GPU run holds 4 trees) takes smaller chunks so that every streaming kernel still launches >= 2 CTAs per SM
+        int ch = TOP_CH;
+        while (ch > 8192 && ((n + ch - 1) / ch) * tg < 2 * 148) ch >>= 1;
+        A.ch = ch;
+        const unsigned nchunks = (unsigned)((n + ch - 1) / ch);
         bool all_top_internal = true;
         for (int l = 0; l < s_top; ++l) {
             A.l = l; A.node0 = (int)P.level_off[l]; A.nnodes = (int)(P.level_off[l + 1] - P.level_off[l]);
@@ -2130,8 +2152,10 @@ int rpf_launch_job(rpf_handle* h, BuildJob& J, const JobPlan& P, const char* tab
             else if (lean && A.scatter_fast)
                 RPF_LAUNCH(h, PH_TOP_RELABEL, k_top_scatter_lean, dim3((unsigned)((n + SCAT_CH - 1) / SCAT_CH), (unsigned)tg), SCAT_NT, (size_t)SCAT_CH * 4, A);
             else RPF_LAUNCH(h, PH_TOP_RELABEL, k_top_relabel, gs, TOP_NT, 0, A, (int)last);
-            RPF_LAUNCH(h, PH_MISC, k_top_finalize, (unsigned)((A.nnodes * tg + 127) / 128), 128, 0, A);
         }
+        // thr / margins of every top-phase node in one launch (NodeSel entries are per node and stay valid)
+        A.node0 = 0; A.nnodes = (int)P.level_off[s_top];
+        RPF_LAUNCH(h, PH_MISC, k_top_finalize, (unsigned)(((int64_t)A.nnodes * tg + 127) / 128), 128, 0, A);
     } else {
         const int64_t tot = n * tg;
         RPF_LAUNCH(h, PH_MISC, k_iota_perm, (unsigned)((tot + 255) / 256), 256, 0, J.perm, n, J.ps, tg);
