@@ -110,9 +110,9 @@ def algorithmic_bytes(W, tlocal, L, s_top, C_mean):
     n, d = W["n"], W["d"]
     return {
         "project": 8 * d * n + 8 * tlocal * L * n,                     # read X once, write every (tree, level) key
-        "top_hist": tlocal * n * (8 + 2),                              # key + label
-        "top_compact": tlocal * n * (8 + 2),
-        "top_relabel": tlocal * n * (8 + 2 + 2),                       # + label write
+        "top_hist": tlocal * n * (8 + 2 + 2),                          # key + label read, 2-byte bin write
+        "top_compact": tlocal * n * (2 + 2),                           # bin + label (keys only for the median bin)
+        "top_relabel": tlocal * n * (2 + 2 + 2),                       # bin + label read, label write
         "bottom": tlocal * n * (4 + 4 + 8 * (L - s_top) + (8 if s_top > 0 else 0)),   # perm r/w + one key per bottom level
         "q_knn": W["nq"] * (C_mean * (8 * d + 4) + 8 * d + 12 * W["k"]),
     }

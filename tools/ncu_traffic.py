@@ -11,7 +11,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PHASE = [("k_knn_tma", "q_knn"), ("k_knn", "q_knn"), ("k_project<", "project"), ("k_bottom", "bottom"), ("k_top_hist", "top_hist"),
-         ("k_top_compact", "top_compact"), ("k_top_relabel", "top_relabel")]
+         ("k_top_compact", "top_compact"), ("k_top_relabel", "top_relabel"), ("k_top_scatter", "top_relabel")]
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
 TIME_MS = {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}
 
