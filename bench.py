@@ -229,9 +229,14 @@ def run_ours(args):
 
     exp_bufs = {}
 
+    rp = R.dist.ReplicatedPoints(dev) if dist is not None else None
+
     def e2e_build():
-        g.buildFromHost(X, maxd, W["min_leaf"])                  # forestBatch from pinned host memory: H2D n*d*8 (row blocks, overlapped
+        if dist is None:
+            g.buildFromHost(X, maxd, W["min_leaf"])              # forestBatch from pinned host memory: H2D n*d*8 (row blocks, overlapped
                                                                  # with the projection kernel) + build
+        else:                                                    # N GPUs: each rank uploads n/N rows over its own PCIe link, NCCL
+            R.dist.buildFromHostSharded(g, rp, Xp, maxd, W["min_leaf"])   # all-gather over NVLink replicates them, then the build
         if not exp_bufs:                                         # page-locked result buffers, allocated once (first warm-up)
             nn_ = len(g.topology()["child"])
             for key in ("thr", "mlo", "mhi"):
@@ -366,8 +371,11 @@ def run_ours(args):
             "build_ms": build_ms, "knn_ms": knn_ms, "knn_queries_per_s": nq / (knn_ms * 1e-3),
             "recall_at_10_recallWith": recall_ref_def, "recall_at_10_forest": forest_recall, "recall_queries": ns,
             "candidates_per_query": C_mean, "stream_build": stream,
-            "e2e": {"value": n / e2e_build_s, "unit": "points/s", "h2d_bytes_per_step": int(n * d * 8 + len(hp[1]) * 12 + len(hp[0]) * 8),
-                    "d2h_bytes_per_step": int(t_local * (nn * 24 + n * 4)), "build_s": e2e_build_s,
+            "e2e": {"value": n / e2e_build_s, "unit": "points/s",
+                    "h2d_bytes_per_step": int(n * d * 8 + world * (len(hp[1]) * 12 + len(hp[0]) * 8)),     # all ranks together
+                    "d2h_bytes_per_step": int(world * t_local * (nn * 24 + n * 4)), "build_s": e2e_build_s,
+                    "upload": ("one H2D of the n x d points (row blocks overlapped with the projection)" if world == 1 else
+                               "row-sharded: n/%d rows per rank over its own PCIe link + NCCL all-gather over NVLink" % world),
                     "knn_queries_per_s": nq / e2e_knn_s, "knn_s": e2e_knn_s,
                     "knn_h2d_bytes": int(nq * d * 8), "knn_d2h_bytes": int(nq * k * 12 + nq * 4)},
             "gpu_launches": int(launches), "wall_ms_per_step": wall_ms,

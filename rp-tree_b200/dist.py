@@ -3,7 +3,9 @@ CPU tests).  Trees are independent (createMulti maps over the IntMap of trees, s
 folds the per-tree candidates in ascending tree order, src/Data/RPTree.hs:176), so the forest is partitioned in
 CONTIGUOUS blocks of trees, the data is replicated, the build needs no communication, and a query needs exactly one
 exchange: an all-gather of the per-rank (dist, id, count) top-k lists followed by the engine's merge kernel
-(rpf_merge_topk).  Contiguous blocks make (rank, position) order equal to the reference's tree order, so the merged
+(rpf_merge_topk).  Getting the replicated data onto the GPUs is the other exchange: every rank uploads only its row block
+over its own PCIe link and the blocks are all-gathered over NVLink (ReplicatedPoints), instead of every rank pulling
+the whole n x d matrix through the host.  Contiguous blocks make (rank, position) order equal to the reference's tree order, so the merged
 result is identical to the single-GPU result, ties included.
 """
 import numpy as np
@@ -101,3 +103,69 @@ def recallSharded(forest, k, Q, group=None, device=None):
     r = torch.from_numpy(forest.recallSumBatch(Q, k)).to(dev)
     dist.all_reduce(r, group=group)
     return r.cpu().numpy() / float(forest.ntrees_total)
+
+
+def shard_rows(n, world, rank):
+    """Equal row blocks for the all-gather of the replicated points: (rows per rank, first row, rows of this rank)."""
+    per = (n + world - 1) // world
+    r0 = min(rank * per, n)
+    return per, r0, max(0, min(n, r0 + per) - r0)
+
+
+def gather_rows(full, block, group=None):
+    """All-gather equal row blocks into `full` (world*per x d); `block` may alias full[rank*per:(rank+1)*per] (in place)."""
+    dist = _dist()
+    if dist.get_backend(group) == "nccl":
+        dist.all_gather_into_tensor(full, block, group=group)
+    else:                                                        # gloo (CPU tests): list form
+        import torch
+        world = dist.get_world_size(group)
+        parts = [torch.empty_like(block) for _ in range(world)]
+        dist.all_gather(parts, block.clone(), group=group)
+        per = block.shape[0]
+        for r, p in enumerate(parts):
+            full[r * per:(r + 1) * per].copy_(p)
+
+
+class ReplicatedPoints:
+    """Device-resident replica of the host data set, filled by a row-sharded upload: rank r copies rows
+    [r*per, (r+1)*per) from (pinned) host memory over its own PCIe link, then the blocks are all-gathered over NCCL
+    (NVLink / NVSwitch) so that every GPU holds all n rows.  H2D traffic per rank is n*d*8 / world bytes instead of
+    n*d*8.  The buffer is kept across calls (one allocation per shape)."""
+
+    def __init__(self, device, group=None):
+        self.device, self.group = device, group
+        self.buf = None
+        self.n = self.d = 0
+
+    def upload(self, X):
+        """X: n x d float64 host array or CPU tensor (ideally pinned), identical on every rank.  Returns (device pointer, n, d)."""
+        import torch
+        dist = _dist()
+        world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        if not isinstance(X, torch.Tensor):
+            X = torch.from_numpy(np.ascontiguousarray(X, np.float64))
+        n, d = X.shape
+        per, r0, rl = shard_rows(n, world, rank)
+        if self.buf is None or self.buf.shape != (world * per, d):
+            self.buf = torch.empty((world * per, d), dtype=torch.float64, device=self.device)
+        mine = self.buf[rank * per:(rank + 1) * per]
+        if rl > 0:
+            mine[:rl].copy_(X[r0:r0 + rl], non_blocking=True)
+        if rl < per:
+            mine[rl:].zero_()
+        gather_rows(self.buf, mine, group=self.group)
+        if self.buf.is_cuda:
+            torch.cuda.current_stream(self.buf.device).synchronize()   # complete before the engine's stream reads it
+        self.n, self.d = n, d
+        return self.buf.data_ptr(), n, d
+
+
+def buildFromHostSharded(forest, points, X, maxd, minl):
+    """forestBatch on this rank's trees from HOST data: row-sharded upload + NVLink all-gather (ReplicatedPoints), then
+    the batch build on the borrowed device replica.  Same forest as forest.buildFromHost(X, ...), bit for bit."""
+    ptr, n, d = points.upload(X)
+    if getattr(forest, "_borrowed_points", None) != (ptr, n, d):
+        forest.setPointsDevice(ptr, n, d)
+        forest._borrowed_points = (ptr, n, d)
+    forest.build(maxd, minl)

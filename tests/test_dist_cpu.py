@@ -100,3 +100,52 @@ def test_world2_gloo_gather_and_merge(built):
         p.join(timeout=60)
     for rank, ok, msg in res:
         assert ok, "rank %d failed: %s" % (rank, msg)
+
+
+def _rows_worker(rank, world, port, q):
+    try:
+        import torch
+        import torch.distributed as dist
+        import rp_tree_b200 as R
+        dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+        ok = True
+        for n in (1001, 64, 3):
+            X = np.random.default_rng(3).normal(size=(n, 5))
+            rp = R.dist.ReplicatedPoints(torch.device("cpu"))
+            ptr, nn, d = rp.upload(X)
+            ok &= (nn, d) == (n, 5) and ptr == rp.buf.data_ptr()
+            ok &= np.array_equal(rp.buf[:n].numpy().view(np.uint64), X.view(np.uint64))
+        dist.barrier()
+        dist.destroy_process_group()
+        q.put((rank, bool(ok), ""))
+    except Exception:  # pragma: no cover
+        import traceback
+        q.put((rank, False, traceback.format_exc()))
+
+
+def test_shard_rows_cover_all_rows():
+    import rp_tree_b200 as R
+    for n in (0, 1, 7, 1000, 1001):
+        for world in (1, 2, 3, 8):
+            rows = []
+            for r in range(world):
+                per, r0, rl = R.dist.shard_rows(n, world, r)
+                assert rl <= per
+                rows += list(range(r0, r0 + rl))
+            assert rows == list(range(n))
+
+
+def test_world2_gloo_row_sharded_replica(built):
+    """ReplicatedPoints: each rank contributes its row block, every rank ends up with the whole matrix (bit-identical)."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_rows_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, ok, msg in res:
+        assert ok, "rank %d failed: %s" % (rank, msg)
