@@ -245,10 +245,10 @@ def run_ours(args):
         return g.forestExport(exp_bufs)                          # D2H: thr/mlo/mhi + perm of every local tree, one call
 
     def e2e_knn():
-        dd, ii, cc = g.knnBatch(Q, k)                            # H2D queries, D2H results
-        if dist is not None:
-            D, I, Cn = R.dist.gather_topk(dd, ii, cc, device=dev)     # host-buffer form of the exchange (the e2e arm)
-            g.mergeTopk(D, I, Cn)
+        if dist is None:
+            g.knnBatch(Q, k)                                     # H2D queries, D2H results
+        else:                                                    # H2D queries; per-rank lists stay on the device, NCCL all-gather,
+            R.dist.knnShardedDevice(g, k, Q, dedup=False, device=dev)   # merge kernel; D2H of the merged nq x k result only
 
     for _ in range(2):                                           # warm-up (workspace allocation)
         e2e_build(); e2e_knn()

@@ -203,7 +203,8 @@ int rpf_get_profile(const rpf_handle* h, double* ms, int64_t* launches, int cap)
 const char* rpf_phase_name(int i);
 /* Total kernel launches issued by this handle since creation. */
 int64_t rpf_launch_count(const rpf_handle* h);
-/* Named options: "force_generic_bottom" (0/1: use the generic bottom-phase kernel; test hook),
+/* Named options: "lean_top" (0/1, default 1: 0 = generic top-phase compact / relabel kernels only; test hook),
+ * "force_generic_bottom" (0/1: use the generic bottom-phase kernel; test hook),
  * "release_workspace" (free the cached device workspace now). */
 int rpf_set_option(rpf_handle* h, const char* name, int64_t value);
 /* Tuning knob: bottom-phase shared-memory capacity in points (256, 1024, 4096 or 8192). */
