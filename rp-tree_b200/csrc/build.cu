@@ -71,7 +71,8 @@ __global__ void __launch_bounds__(NT) k_project(const double* __restrict__ X, in
     // 32-bit shared-window addresses of this lane's R rows (one IADD + LDS per term instead of 64-bit pointer math)
     unsigned rowaddr[R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) rowaddr[r] = (unsigned)__cvta_generic_to_shared(xs + (size_t)(lane + 32 * r) * ld);
+    for (int r = 0; r < R; ++r) rowaddr[r] = (unsigned)__cvta_generic_to_shared(xs + (size_t)(lane + 32 * r) * ld) - 8u * (unsigned)c0;
+    // (the packed CSR stores byte offsets 8 * idx from column 0; the tile starts at column c0)
     // The per-row key range only seeds the bin map of the top phase (keys outside it fall into the first / last bin, the
     // exact select inside the median bin does the rest), so it is taken from every 8th tile: the warp reduction below
     // costs about as much as four terms of the dot product.
@@ -110,7 +111,7 @@ __global__ void __launch_bounds__(NT) k_project(const double* __restrict__ X, in
     };
     // one term of one hyperplane for this lane's R points: acc = val * x[idx] + acc  (separate roundings, right fold)
     auto term = [&](const double2 hv, double (&acc)[R]) {
-        const unsigned c = (unsigned)__double_as_longlong(hv.y) - 8u * (unsigned)c0;
+        const unsigned c = (unsigned)__double_as_longlong(hv.y);
         double x[R];
         if constexpr (LD != 0) {
             const unsigned a0 = rowaddr[0] + c;
@@ -127,11 +128,13 @@ __global__ void __launch_bounds__(NT) k_project(const double* __restrict__ X, in
         for (int r = 0; r < R; ++r) acc[r] = __dadd_rn(__dmul_rn(hv.x, x[r]), acc[r]);
     };
     // two hyperplanes per warp in flight (2R independent accumulate chains per lane)
+    const unsigned magicL = 0xffffffffu / (unsigned)L + 1u;      // j / L = umulhi(j, magicL) for j * L < 2^32 (L > 1)
+    auto csr_row = [&](int j) { const int q = L > 1 ? (int)__umulhi((unsigned)j, magicL) : j; return (t0 + q) * hpDepth + (j - q * L); };
     for (int j = w; j < H; j += 2 * NW) {          // warp-uniform
         const int jB = j + NW;
         const bool hasB = jB < H;
-        const int rowA = (t0 + j / L) * hpDepth + (j % L);
-        const int rowB = hasB ? (t0 + jB / L) * hpDepth + (jB % L) : rowA;
+        const int rowA = csr_row(j);
+        const int rowB = hasB ? csr_row(jB) : rowA;
         const int64_t sA = hp_off[rowA], sB = hp_off[rowB];
         int64_t eA = hp_off[rowA + 1], eB = hp_off[rowB + 1];
         if (eA - sA > d) eA = sA + d;               // innerSD's `i >= nz2` guard (Internal.hs:376)
@@ -164,6 +167,17 @@ __global__ void __launch_bounds__(NT) k_project(const double* __restrict__ X, in
         }
         // the (value, offset) pair of the NEXT term is requested before the current term's loads and adds are issued
         double2 a = cA > 0 ? __ldg(hA) : make_double2(0.0, 0.0), b2 = cB > 0 ? __ldg(hB) : make_double2(0.0, 0.0);
+        // two terms per stream and iteration: the consumed pair's registers are reloaded with the term after next
+        // (no register rotation, half the loop control per term)
+        while (cA > 2 && cB > 2) {
+            const double2 a1 = __ldg(hA - 1), b1 = __ldg(hB - 1);
+            term(a, accA);
+            term(b2, accB);
+            a = __ldg(hA - 2); b2 = __ldg(hB - 2);
+            term(a1, accA);
+            term(b1, accB);
+            hA -= 2; hB -= 2; cA -= 2; cB -= 2;
+        }
         while (cA > 1 && cB > 1) {
             const double2 an = __ldg(hA - 1), bn = __ldg(hB - 1);
             --hA; --hB; --cA; --cB;

@@ -946,6 +946,7 @@ int rpf_set_option(rpf_handle* h, const char* name, int64_t value) {
     if (s == "lean_top") { h->lean_top = value != 0; return RPF_OK; }
     if (s == "force_generic_bottom") { h->force_generic_bottom = value != 0; return RPF_OK; }
     if (s == "bottom_words64") { h->bottom_words64 = value != 0; return RPF_OK; }
+    if (s == "force_simple_topk") { h->force_simple_topk = value != 0; return RPF_OK; }
     if (s == "force_simple_knn") { h->force_simple_knn = value != 0; return RPF_OK; }
     if (s == "no_query_order") { h->no_query_order = value != 0; return RPF_OK; }
     if (s == "project_variant") { h->project_variant = (int)value; return RPF_OK; }

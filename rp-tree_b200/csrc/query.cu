@@ -698,14 +698,16 @@ __global__ void __launch_bounds__(BF_NT) k_dist_all(const double* __restrict__ X
 }
 
 // One CTA per query of the tile: k smallest of D[qi][0..n) ordered by (distance, row id)
+// (the general path: nine passes over the n distances; `need` != NULL: only the queries flagged by k_topk_final)
 __global__ void __launch_bounds__(512) k_select_topk(const ull* __restrict__ D, int64_t n, int k, int64_t q0,
-                                                     double* __restrict__ dist, uint32_t* __restrict__ ids) {
+                                                     double* __restrict__ dist, uint32_t* __restrict__ ids, const uint32_t* __restrict__ need) {
     __shared__ uint32_t sh[260];
     __shared__ ull s_pref;
     __shared__ ull skey[1024];
     __shared__ uint32_t sidv[1024];
     __shared__ unsigned s_cnt, s_cnt_eq;
     const int qi = blockIdx.x, tid = threadIdx.x;
+    if (need && need[qi] == 0) return;
     const ull* Dq = D + (int64_t)qi * n;
     const uint32_t kk = (uint32_t)min((int64_t)k, n);
     // radix select of rank kk-1
@@ -781,6 +783,80 @@ __global__ void __launch_bounds__(512) k_select_topk(const ull* __restrict__ D, 
         const bool ok = i < kk;
         dist[(q0 + qi) * k + i] = ok ? __longlong_as_double((long long)skey[i]) : __longlong_as_double(0x7ff0000000000000LL);
         ids[(q0 + qi) * k + i] = ok ? sidv[i] : 0xffffffffu;
+    }
+}
+
+// ---- fast exact top-k: one pass over the distances instead of nine ---------------------------------------------
+// tau = the kk-th smallest of a strided SAMPLE of the query's distances is an upper bound of the kk-th smallest of all n,
+// so every member of the exact top-k (by (distance, row id)) passes the filter v <= tau; with S samples about kk * n / S
+// rows pass.  The survivors are sorted by (distance, row id) in shared memory.  A query whose survivors exceed the
+// buffer (adversarial distributions) is flagged and answered by k_select_topk.
+#define TK_CAP 8192       /* survivors per query (96 KB of shared memory in k_topk_final) */
+__global__ void __launch_bounds__(512) k_topk_tau(const ull* __restrict__ D, int64_t n, int kk, int64_t S, int64_t stride,
+                                                  ull* __restrict__ tau, uint32_t* __restrict__ cnt, uint32_t* __restrict__ need) {
+    __shared__ uint32_t sh[264];
+    __shared__ ull sh64[1];
+    const int qi = blockIdx.x;
+    const ull* Dq = D + (int64_t)qi * n;
+    uint32_t cl, ce;
+    const ull t = cta_radix_select<512>((uint32_t)S, (uint32_t)(kk - 1), [&](uint32_t i) { return Dq[(int64_t)i * stride]; }, sh, sh64, cl, ce);
+    if (threadIdx.x == 0) { tau[qi] = t; cnt[qi] = 0; need[qi] = 0; }
+}
+__global__ void __launch_bounds__(512) k_topk_filter(const ull* __restrict__ D, int64_t n, const ull* __restrict__ tau,
+                                                     ull* __restrict__ cv, uint32_t* __restrict__ ci, uint32_t* __restrict__ cnt) {
+    const int qi = blockIdx.y;
+    const ull* Dq = D + (int64_t)qi * n;
+    const ull t = tau[qi];
+    const int64_t base = (int64_t)blockIdx.x * (512 * 16) + threadIdx.x;
+    ull v[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) { const int64_t i = base + e * 512; v[e] = i < n ? __ldcs(Dq + i) : ~0ull; }
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+        const int64_t i = base + e * 512;
+        if (i < n && v[e] <= t) {
+            const uint32_t p = atomicAdd(&cnt[qi], 1u);
+            if (p < TK_CAP) { cv[(int64_t)qi * TK_CAP + p] = v[e]; ci[(int64_t)qi * TK_CAP + p] = (uint32_t)i; }
+        }
+    }
+}
+__global__ void __launch_bounds__(512) k_topk_final(const ull* __restrict__ cv, const uint32_t* __restrict__ ci, const uint32_t* __restrict__ cnt,
+                                                    int kk, int k, int64_t q0, double* __restrict__ dist, uint32_t* __restrict__ ids,
+                                                    uint32_t* __restrict__ need) {
+    extern __shared__ ull tk_key[];                       // [Pv] keys, then [Pv] row ids
+    const int qi = blockIdx.x, tid = threadIdx.x;
+    const unsigned m = cnt[qi];
+    if (m > TK_CAP) { if (tid == 0) need[qi] = 1; return; }
+    const unsigned Pv = q_next_pow2(m < 2 ? 2 : m), half = Pv >> 1;
+    uint32_t* tk_id = (uint32_t*)(tk_key + Pv);
+    for (unsigned i = tid; i < Pv; i += 512) {
+        tk_key[i] = i < m ? cv[(int64_t)qi * TK_CAP + i] : ~0ull;
+        tk_id[i] = i < m ? ci[(int64_t)qi * TK_CAP + i] : 0xffffffffu;
+    }
+    __syncthreads();
+    for (unsigned kq = 2; kq <= Pv; kq <<= 1) {           // bitonic network on (distance, row id)
+        const int lk = q_ilog2(kq);
+        for (unsigned c = tid; c < half; c += 512) {
+            const unsigned blk = c >> (lk - 1), w = c & ((kq >> 1) - 1);
+            const unsigned i = (blk << lk) + w, p = (blk << lk) + (kq - 1 - w);
+            ull a = tk_key[i], b = tk_key[p]; uint32_t ia = tk_id[i], ib = tk_id[p];
+            if (a > b || (a == b && ia > ib)) { tk_key[i] = b; tk_key[p] = a; tk_id[i] = ib; tk_id[p] = ia; }
+        }
+        __syncthreads();
+        for (unsigned j = kq >> 2; j > 0; j >>= 1) {
+            const int lj = q_ilog2(j);
+            for (unsigned c = tid; c < half; c += 512) {
+                const unsigned i = ((c >> lj) << (lj + 1)) + (c & (j - 1)), p = i + j;
+                ull a = tk_key[i], b = tk_key[p]; uint32_t ia = tk_id[i], ib = tk_id[p];
+                if (a > b || (a == b && ia > ib)) { tk_key[i] = b; tk_key[p] = a; tk_id[i] = ib; tk_id[p] = ia; }
+            }
+            __syncthreads();
+        }
+    }
+    for (unsigned i = tid; i < (unsigned)k; i += 512) {
+        const bool ok = i < (unsigned)kk;
+        dist[(q0 + qi) * k + i] = ok ? __longlong_as_double((long long)tk_key[i]) : __longlong_as_double(0x7ff0000000000000LL);
+        ids[(q0 + qi) * k + i] = ok ? tk_id[i] : 0xffffffffu;
     }
 }
 
@@ -1114,10 +1190,31 @@ static int brute_device(rpf_handle* h, const double* dQ, const int32_t* dqlast, 
     const size_t smem = (size_t)BF_TQ * d * 8;
     if (smem > 160 * 1024) return rpf_fail(h, RPF_ERR_UNSUPPORTED, "brute_knn: dimension too large");
     RPF_CUDA(h, cudaFuncSetAttribute(k_dist_all, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // sampled-threshold select (k_topk_*): needs a sample much larger than k and much smaller than n
+    const int kk = (int)std::min<int64_t>(k, n);
+    const int64_t S = std::min<int64_t>(n, std::max<int64_t>(65536, 256 * (int64_t)kk));
+    const int64_t stride = n / S;
+    const bool fast = !h->force_simple_topk && kk >= 1 && n >= 4 * S;
+    ull* cv = nullptr; uint32_t* ci = nullptr; ull* tau = nullptr; uint32_t *cnt = nullptr, *need = nullptr;
+    if (fast) {
+        cv = (ull*)h->ws_get(WS_BF_CV, (size_t)BF_TQ * TK_CAP * 8);
+        ci = (uint32_t*)h->ws_get(WS_BF_CI, (size_t)BF_TQ * TK_CAP * 4);
+        tau = (ull*)h->ws_get(WS_BF_AUX, (size_t)BF_TQ * 16);
+        if (!cv || !ci || !tau) return RPF_ERR_NOMEM;
+        cnt = (uint32_t*)(tau + BF_TQ); need = cnt + BF_TQ;
+        RPF_CUDA(h, cudaFuncSetAttribute(k_topk_final, cudaFuncAttributeMaxDynamicSharedMemorySize, TK_CAP * 12));
+    }
     for (int64_t q0 = 0; q0 < nq; q0 += BF_TQ) {
         const int nqt = (int)std::min<int64_t>(BF_TQ, nq - q0);
         RPF_LAUNCH(h, PH_TRUTH, k_dist_all, (unsigned)((n + BF_NT - 1) / BF_NT), BF_NT, smem, h->dX, n, d, dQ, q0, nqt, D, vec, h->d_xlast, dqlast);
-        RPF_LAUNCH(h, PH_TRUTH, k_select_topk, (unsigned)nqt, 512, 0, D, n, k, q0, d_dist, d_ids);
+        if (fast) {
+            RPF_LAUNCH(h, PH_TRUTH, k_topk_tau, (unsigned)nqt, 512, 0, D, n, kk, S, stride, tau, cnt, need);
+            RPF_LAUNCH(h, PH_TRUTH, k_topk_filter, dim3((unsigned)((n + 512 * 16 - 1) / (512 * 16)), (unsigned)nqt), 512, 0, D, n, tau, cv, ci, cnt);
+            RPF_LAUNCH(h, PH_TRUTH, k_topk_final, (unsigned)nqt, 512, (size_t)TK_CAP * 12, cv, ci, cnt, kk, k, q0, d_dist, d_ids, need);
+            RPF_LAUNCH(h, PH_TRUTH, k_select_topk, (unsigned)nqt, 512, 0, D, n, k, q0, d_dist, d_ids, need);     // flagged queries only
+        } else {
+            RPF_LAUNCH(h, PH_TRUTH, k_select_topk, (unsigned)nqt, 512, 0, D, n, k, q0, d_dist, d_ids, (const uint32_t*)nullptr);
+        }
     }
     return RPF_OK;
 }

@@ -105,7 +105,7 @@ enum rpf_ws_slot {
     WS_NBDEV, WS_RANGE, WS_LVLPV, WS_HPPACK,
     WS_Q, WS_KEYSQ, WS_SEGS, WS_CNT, WS_MAXCNT, WS_OUT_D, WS_OUT_I, WS_OUT_C, WS_BF_D, WS_TRUTH_D, WS_TRUTH_I, WS_RECALL,
     WS_CANDCNT, WS_CANDOFF, WS_CANDOUT, WS_MRG_D, WS_MRG_I, WS_MRG_C, WS_QHIST, WS_QORDER,
-    WS_S_ARENA0, WS_S_ARENA1, WS_S_CPERM, WS_S_TMPN, WS_S_POOL, WS_QLAST, WS_PRIO, WS_WORKLIST, WS_PBIN,
+    WS_S_ARENA0, WS_S_ARENA1, WS_S_CPERM, WS_S_TMPN, WS_S_POOL, WS_QLAST, WS_PRIO, WS_WORKLIST, WS_PBIN, WS_BF_CV, WS_BF_CI, WS_BF_AUX,
     WS_COUNT
 };
 struct WsBuf { void* p = nullptr; size_t cap = 0; };
@@ -146,6 +146,7 @@ struct rpf_handle {
     size_t res_node_bytes = 0, res_perm_bytes = 0;
     int project_variant = 0;             // tuning hook: 0 = 1024 threads x 4 points/lane, 1 = 1024 x 2 (two CTAs/SM), 2 = 512 x 4
     bool no_query_order = false;         // test/tuning hook: answer queries in input order (no locality grouping)
+    bool force_simple_topk = false;      // test hook: brute-force truth through the nine-pass radix select only
     bool force_simple_knn = false;       // test hook: per-thread gather knn kernel instead of the TMA ring
     bool lean_top = true;                // option "lean_top": 0 = generic top-phase compact / relabel kernels only (test hook)
     bool force_generic_bottom = false;   // test hook: run the generic (entry-table) bottom kernel

@@ -503,3 +503,34 @@ def test_reference_spec_conduit_shape(built):
     for fn in (R.knn, R.knnPQ, R.knnH):
         dist, ids = fn(R.metricL2, k, f, q)
         assert len(dist) >= 1 and dist.max() < 1, fn.__name__
+
+
+@pytest.mark.parametrize("kind", ["gauss", "all-equal", "sorted-far-first"])
+def test_brute_force_topk_sampled_threshold_path(built, kind):
+    """n >= 4 * 65536 rows select the truth top-k through k_topk_tau / k_topk_filter / k_topk_final (one pass over the
+    distances, threshold from a strided sample); results must equal the nine-pass radix select (option
+    force_simple_topk) and the oracle.  `all-equal` (every distance identical: all rows pass the filter) and
+    `sorted-far-first` exercise the overflow flag -> k_select_topk fallback and the (distance, row id) tie order."""
+    R, orc = _mods()
+    n, d = 300_000, 4
+    rng = np.random.default_rng(8)
+    if kind == "gauss":
+        X = rng.normal(size=(n, d))
+    elif kind == "all-equal":
+        X = np.ones((n, d))
+    else:                                   # few distinct distances, many ties
+        X = np.repeat(rng.integers(0, 3, size=(n, 1)).astype(np.float64), d, axis=1)
+    Q = rng.normal(size=(11, d))
+    hp = orc.gen_hyperplanes(3, 1, 2, 1.0, d)
+    f = R.RPForest(0)
+    f.setHyperplanes(hp, 1, 2); f.setPoints(X); f.build(2, 1000)
+    for k in (1, 10, 100):
+        f.setOption("force_simple_topk", 0)
+        fd, fi = f.bruteKnnBatch(Q, k)
+        f.setOption("force_simple_topk", 1)
+        sd, si = f.bruteKnnBatch(Q, k)
+        assert np.array_equal(bits(fd), bits(sd)) and np.array_equal(fi, si), (kind, k)
+        for i in (0, 10):
+            od, oi = orc.brute_knn(X, Q[i], k)
+            assert np.array_equal(bits(fd[i]), bits(od)) and np.array_equal(fi[i], oi), (kind, k, i)
+    f.close()
