@@ -2131,12 +2131,30 @@ int rpf_launch_job(rpf_handle* h, BuildJob& J, const JobPlan& P, const char* tab
         RPF_LAUNCH(h, PH_MISC, k_bin_setup, (unsigned)((tg * J.Lk + 127) / 128), 128, 0, A, nbdev, s_top);
         RPF_CUDA(h, cudaMemsetAsync(fill, 0, (size_t)tg * NTOP * 4, h->stream));
         if (P.nroots > 1) RPF_LAUNCH(h, PH_MISC, k_label_roots, (unsigned)((n + 255) / 256), 256, 0, label, n, tg, J.d_start, P.nroots);
-        // chunk per CTA: the full TOP_CH amortises the shared-memory histogram flush best; a small tree group (the shard
-        // of an 8-GPU run holds 4 trees) takes smaller chunks so that every streaming kernel still launches >= 2 CTAs per SM
-        int ch = TOP_CH;
-        while (ch > 8192 && ((n + ch - 1) / ch) * tg < 2 * 148) ch >>= 1;
-        A.ch = ch;
-        const unsigned nchunks = (unsigned)((n + ch - 1) / ch);
+        // Chunk per CTA, chosen per kernel class.  The streaming kernels do uniform work per CTA, so a launch takes
+        // ceil(CTAs / resident CTAs) waves of (chunk + fixed per-CTA cost: histogram zero / flush, table loads); a 32-tree
+        // group at 32 768 points per CTA runs 2.2 waves of the histogram kernel (the third wave is a quarter full), a
+        // 4-tree shard of an 8-GPU run would not even fill the SMs once.  Candidates: multiples of 8192 up to TOP_CH.
+        auto pick_chunk = [&](int resident_per_sm, int fixed, int forced) {
+            if (forced >= 8192 && forced <= TOP_CH && forced % 8192 == 0) return forced;
+            int best = TOP_CH; double best_cost = 1e300;
+            for (int ch = TOP_CH; ch >= 8192; ch -= 8192) {
+                const int64_t ctas = ((n + ch - 1) / ch) * tg;
+                const int64_t waves = (ctas + 148 * resident_per_sm - 1) / (148 * resident_per_sm);
+                const double cost = (double)waves * (ch + fixed);
+                if (cost < best_cost * 0.98) { best_cost = cost; best = ch; }      // prefer the larger chunk on near ties
+            }
+            return best;
+        };
+        // (measured at 32 trees: the histogram kernel prefers the largest chunk -- its flush of 32 768 counters per CTA
+        // outweighs the partial last wave: 0.99 ms at 32 768, 1.02 at 24 576, 1.09 at 16 384 -- so it only shrinks the
+        // chunk to reach 2 CTAs per SM; compact / relabel gain 3-5 % from the wave model)
+        int ch_hist = TOP_CH;
+        while (ch_hist > 8192 && ((n + ch_hist - 1) / ch_hist) * tg < 2 * 148) ch_hist >>= 1;
+        if (h->top_chunk[0] >= 8192 && h->top_chunk[0] <= TOP_CH && h->top_chunk[0] % 8192 == 0) ch_hist = h->top_chunk[0];
+        const int ch_compact = pick_chunk(3, 2048, h->top_chunk[1]);
+        const int ch_relabel = pick_chunk(2, 2048, h->top_chunk[2]);
+        auto grid_for = [&](int ch) { return dim3((unsigned)((n + ch - 1) / ch), (unsigned)tg); };
         bool all_top_internal = true;
         for (int l = 0; l < s_top; ++l) {
             A.l = l; A.node0 = (int)P.level_off[l]; A.nnodes = (int)(P.level_off[l + 1] - P.level_off[l]);
@@ -2148,24 +2166,27 @@ int rpf_launch_job(rpf_handle* h, BuildJob& J, const JobPlan& P, const char* tab
             A.scatter_fast = (all_top_internal && 2 * A.nnodes <= SCAT_MAX) ? 1 : 0;
             RPF_CUDA(h, cudaMemsetAsync(hist, 0, (size_t)tg * HSZ * 4, h->stream));
             RPF_CUDA(h, cudaMemsetAsync(cand_total, 0, (size_t)tg * 8 + 8, h->stream));
-            dim3 gs(nchunks, (unsigned)tg), gn((unsigned)A.nnodes, (unsigned)tg);
+            dim3 gn((unsigned)A.nnodes, (unsigned)tg);
             const size_t hs = A.smem_hist ? ((size_t)A.nnodes * A.NB + 1) / 2 * 4 : 0;     // 16-bit counters
-            RPF_LAUNCH(h, PH_TOP_HIST, k_top_hist, gs, TOP_NT, hs, A);
+            A.ch = ch_hist;
+            RPF_LAUNCH(h, PH_TOP_HIST, k_top_hist, grid_for(ch_hist), TOP_NT, hs, A);
             if (A.NB <= 256) RPF_LAUNCH(h, PH_TOP_PICK, k_top_pick_warp, (unsigned)(((int64_t)A.nnodes * tg + 7) / 8), 256, 0, A);
             else RPF_LAUNCH(h, PH_TOP_PICK, k_top_pick, gn, 256, 0, A);
             // lean kernels (16-byte rows of bins / labels, shared-memory node tables): see k_top_relabel_lean
             const bool lean = h->lean_top && (n & 7) == 0 && A.nnodes <= SMEM_NODES && A.all_internal;
             const bool last = l == s_top - 1;
-            if (lean) RPF_LAUNCH(h, PH_TOP_COMPACT, k_top_compact_lean, gs, TOP_NT, CL_CAP * 6, A);
-            else RPF_LAUNCH(h, PH_TOP_COMPACT, k_top_compact, gs, TOP_NT, 0, A);
+            A.ch = ch_compact;
+            if (lean) RPF_LAUNCH(h, PH_TOP_COMPACT, k_top_compact_lean, grid_for(ch_compact), TOP_NT, CL_CAP * 6, A);
+            else RPF_LAUNCH(h, PH_TOP_COMPACT, k_top_compact, grid_for(ch_compact), TOP_NT, 0, A);
             RPF_LAUNCH(h, PH_TOP_FINISH, k_top_finish_warp, (unsigned)(((int64_t)A.nnodes * tg + FW_WARPS - 1) / FW_WARPS), FW_WARPS * 32, 0, A);
             const unsigned gw = (unsigned)std::min<int64_t>((int64_t)A.nnodes * tg, 592);      // work-list walkers
             RPF_LAUNCH(h, PH_TOP_FINISH, k_top_finish, gw, 512, 0, A);
             RPF_LAUNCH(h, PH_TOP_TIES, k_top_ties, gw, 512, 0, A);
-            if (lean && !last) RPF_LAUNCH(h, PH_TOP_RELABEL, k_top_relabel_lean, gs, TOP_NT, 0, A);
+            A.ch = ch_relabel;
+            if (lean && !last) RPF_LAUNCH(h, PH_TOP_RELABEL, k_top_relabel_lean, grid_for(ch_relabel), TOP_NT, 0, A);
             else if (lean && A.scatter_fast)
                 RPF_LAUNCH(h, PH_TOP_RELABEL, k_top_scatter_lean, dim3((unsigned)((n + SCAT_CH - 1) / SCAT_CH), (unsigned)tg), SCAT_NT, (size_t)SCAT_CH * 4, A);
-            else RPF_LAUNCH(h, PH_TOP_RELABEL, k_top_relabel, gs, TOP_NT, 0, A, (int)last);
+            else RPF_LAUNCH(h, PH_TOP_RELABEL, k_top_relabel, grid_for(ch_relabel), TOP_NT, 0, A, (int)last);
         }
         // thr / margins of every top-phase node in one launch (NodeSel entries are per node and stay valid)
         A.node0 = 0; A.nnodes = (int)P.level_off[s_top];

@@ -943,6 +943,9 @@ int rpf_set_option(rpf_handle* h, const char* name, int64_t value) {
     const std::string s(name);
     ++h->cfg_epoch;
     if (s == "cuda_graph") { h->use_graphs = value != 0; return RPF_OK; }
+    if (s == "top_chunk_hist") { h->top_chunk[0] = (int)value; return RPF_OK; }
+    if (s == "top_chunk_compact") { h->top_chunk[1] = (int)value; return RPF_OK; }
+    if (s == "top_chunk_relabel") { h->top_chunk[2] = (int)value; return RPF_OK; }
     if (s == "lean_top") { h->lean_top = value != 0; return RPF_OK; }
     if (s == "force_generic_bottom") { h->force_generic_bottom = value != 0; return RPF_OK; }
     if (s == "bottom_words64") { h->bottom_words64 = value != 0; return RPF_OK; }

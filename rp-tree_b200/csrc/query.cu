@@ -1192,7 +1192,7 @@ static int brute_device(rpf_handle* h, const double* dQ, const int32_t* dqlast, 
     RPF_CUDA(h, cudaFuncSetAttribute(k_dist_all, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // sampled-threshold select (k_topk_*): needs a sample much larger than k and much smaller than n
     const int kk = (int)std::min<int64_t>(k, n);
-    const int64_t S = std::min<int64_t>(n, std::max<int64_t>(65536, 256 * (int64_t)kk));
+    const int64_t S = std::min<int64_t>(n, std::max<int64_t>(16384, 256 * (int64_t)kk));    // ~ kk * n / S survivors per query
     const int64_t stride = n / S;
     const bool fast = !h->force_simple_topk && kk >= 1 && n >= 4 * S;
     ull* cv = nullptr; uint32_t* ci = nullptr; ull* tau = nullptr; uint32_t *cnt = nullptr, *need = nullptr;

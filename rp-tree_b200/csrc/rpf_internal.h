@@ -148,6 +148,7 @@ struct rpf_handle {
     bool no_query_order = false;         // test/tuning hook: answer queries in input order (no locality grouping)
     bool force_simple_topk = false;      // test hook: brute-force truth through the nine-pass radix select only
     bool force_simple_knn = false;       // test hook: per-thread gather knn kernel instead of the TMA ring
+    int top_chunk[3] = {0, 0, 0};        // tuning hook: points per CTA of the top-phase hist / compact / relabel kernels (0 = chosen per launch)
     bool lean_top = true;                // option "lean_top": 0 = generic top-phase compact / relabel kernels only (test hook)
     bool force_generic_bottom = false;   // test hook: run the generic (entry-table) bottom kernel
     bool bottom_words64 = false;         // test hook: 64-bit sort words in the fast bottom kernel even for <= 2048 slots

@@ -21,6 +21,9 @@ if os.environ.get("RPF_PROJECT_VARIANT"):
     f.setOption("project_variant", int(os.environ["RPF_PROJECT_VARIANT"]))
 if os.environ.get("RPF_LEAN_TOP"):
     f.setOption("lean_top", int(os.environ["RPF_LEAN_TOP"]))
+if os.environ.get("RPF_TOP_CH"):       # "hist,compact,relabel" points per CTA
+    for name, v in zip(("top_chunk_hist", "top_chunk_compact", "top_chunk_relabel"), os.environ["RPF_TOP_CH"].split(",")):
+        f.setOption(name, int(v))
 if os.environ.get("RPF_BOTTOM_CAP"):
     f.setBottomCap(int(os.environ["RPF_BOTTOM_CAP"]))
 f.setHyperplanes(hp, T, maxd)
