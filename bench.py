@@ -242,7 +242,9 @@ def run_ours(args):
             for key in ("thr", "mlo", "mhi"):
                 exp_bufs[key] = torch.empty((t_local, nn_), dtype=torch.float64, pin_memory=True).numpy()
             exp_bufs["perm"] = torch.empty((t_local, n), dtype=torch.int32, pin_memory=True).numpy().view(np.uint32)
-        return g.forestExport(exp_bufs)                          # D2H: thr/mlo/mhi + perm of every local tree, one call
+            if dist is None:
+                g.setExportSink(exp_bufs)                        # later builds stream the forest into these buffers while they run
+        return g.forestExport(exp_bufs)                          # D2H: thr/mlo/mhi + perm of every local tree (streamed or one call)
 
     def e2e_knn():
         if dist is None:

@@ -129,6 +129,13 @@ int rpf_tree_export(rpf_handle* h, int32_t t, double* thr, double* mlo, double* 
 /* Whole forest in one call: thr/mlo/mhi[T][num_nodes], perm[T][n] (tree-major; any pointer may be NULL).
  * The copies run back to back on the engine's stream; pass page-locked buffers for full PCIe speed. */
 int rpf_forest_export(rpf_handle* h, double* thr, double* mlo, double* mhi, uint32_t* perm);
+/* Export sink: host buffers (same shapes as rpf_forest_export's, ideally page-locked; perm must be non-NULL, NULLs clear
+ * the sink) that rpf_build_from_host fills WHILE it builds -- the bottom phase runs in tree groups and every group's
+ * slice of perm is downloaded on a second stream as soon as it is final -- so the RPForest value forestBatch returns
+ * (Batch.hs:48-63) is on the host ~2 ms after the last kernel instead of after a separate 153 MB download.
+ * rpf_forest_export with exactly these pointers then only waits for the stream.  The buffers must stay valid until the
+ * sink is cleared or the handle destroyed; their content is undefined between a build and the matching export. */
+int rpf_set_export_sink(rpf_handle* h, double* thr, double* mlo, double* mhi, uint32_t* perm);
 
 /* ---- checkpoint (the engine-side counterpart of serialiseRPForest / deserialiseRPForest, Internal.hs:185-196) -------- */
 /* One flat little-endian file: hyperplanes, topology, thr/mlo/mhi, perm and -- with_points != 0 -- the data points

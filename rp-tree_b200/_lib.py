@@ -50,6 +50,7 @@ SIGNATURES = {
     "rpf_leaf_order_exact": (C.c_int, [H]),
     "rpf_tree_export": (C.c_int, [H, C.c_int32, f64p, f64p, f64p, u32p]),
     "rpf_forest_export": (C.c_int, [H, f64p, f64p, f64p, u32p]),
+    "rpf_set_export_sink": (C.c_int, [H, f64p, f64p, f64p, u32p]),
     "rpf_forest_save": (C.c_int, [H, C.c_char_p, C.c_int32]),
     "rpf_forest_load": (C.c_int, [H, C.c_char_p]),
     "rpf_candidates_count": (C.c_int, [H, f64p, C.c_int64, C.c_int32, i64p]),

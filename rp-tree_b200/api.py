@@ -267,6 +267,17 @@ class RPForest:
                                            _p(out["perm"], u32p) if n else None), "rpf_forest_export")
         return out
 
+    def setExportSink(self, out):
+        """Register `out` (dict of thr/mlo/mhi [T][nodes] float64 and perm [T][n] uint32, ideally page-locked; None clears)
+        as the buffers buildFromHost streams the forest into while it builds; forestExport(out) then only waits."""
+        if out is None:
+            self._ck(self._L.rpf_set_export_sink(self._h, None, None, None, None), "rpf_set_export_sink")
+            self._sink = None
+            return
+        self._sink = out                     # keeps the arrays alive
+        self._ck(self._L.rpf_set_export_sink(self._h, _p(out["thr"], f64p), _p(out["mlo"], f64p), _p(out["mhi"], f64p),
+                                             _p(out["perm"], u32p)), "rpf_set_export_sink")
+
     def save(self, path, with_points=True):
         """Checkpoint of the built forest (counterpart of serialiseRPForest, Internal.hs:185-190)."""
         self._ck(self._L.rpf_forest_save(self._h, str(path).encode(), int(with_points)), "rpf_forest_save")

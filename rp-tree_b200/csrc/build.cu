@@ -2203,8 +2203,25 @@ int rpf_launch_job(rpf_handle* h, BuildJob& J, const JobPlan& P, const char* tab
         B.keys = J.keys; B.perm = J.perm; B.child = J.d_child; B.nstart = J.d_start; B.nsize = J.d_size;
         B.range = range; B.lvl_pv = lvlpv; B.thr = J.thr; B.mlo = J.mlo; B.mhi = J.mhi;
         B.kmin = J.kmin; B.kmax = J.kmax;
-        int rc = rpf_bottom_launch(h, B, P.nnodes_s, tg, G.fast_bottom, P.maxsize_s, G.bottom_levels);
-        if (rc) return rc;
+        // With an export sink the trees go through the bottom phase in groups: a group's slice of perm is final when its
+        // launch ends, so its D2H runs on the download stream while the next group is still sorting.
+        const int groups = (J.stream_to_sink && h->sink_perm && J.ps == n && tg >= 8) ? 8 : 1;
+        for (int gi = 0; gi < groups; ++gi) {
+            const int ta = (int)((int64_t)tg * gi / groups), tb = (int)((int64_t)tg * (gi + 1) / groups);
+            if (tb <= ta) continue;
+            BottomArgs Bg = B;
+            Bg.keys += (int64_t)ta * J.Lk * J.ks; Bg.perm += (int64_t)ta * J.ps; Bg.gt0 += ta;
+            if (Bg.kmin) { Bg.kmin += (int64_t)ta * J.Lk; Bg.kmax += (int64_t)ta * J.Lk; }
+            int rc = rpf_bottom_launch(h, Bg, P.nnodes_s, tb - ta, G.fast_bottom, P.maxsize_s, G.bottom_levels);
+            if (rc) return rc;
+            if (groups > 1) {
+                RPF_CUDA(h, cudaEventRecord(h->sink_ev[gi], h->stream));
+                RPF_CUDA(h, cudaStreamWaitEvent(h->d2h_stream, h->sink_ev[gi], 0));
+                RPF_CUDA(h, cudaMemcpyAsync(h->sink_perm + (int64_t)(J.gt0 + ta) * n, J.perm + (int64_t)ta * J.ps, (size_t)(tb - ta) * n * 4,
+                                            cudaMemcpyDeviceToHost, h->d2h_stream));
+            }
+        }
+        if (groups > 1) h->sink_perm_streamed = true;
     }
     return RPF_OK;
 }
@@ -2297,6 +2314,14 @@ int rpf_build_impl(rpf_handle* h, const double* hostX) {
     if (rc) return rc;
 
     const bool pipelined = hostX && Tg == T && L > 0 && n > 0;
+    // export sink: only the host-data build streams into it (never captured into the build graph)
+    const bool sink = hostX && h->sink_perm != nullptr;
+    h->sink_pending = false; h->sink_perm_streamed = false;
+    if (h->d2h_stream) RPF_CUDA(h, cudaStreamSynchronize(h->d2h_stream));   // a previous build's download is complete before its source is rewritten
+    if (sink) {
+        if (!h->d2h_stream) RPF_CUDA(h, cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
+        if (!h->sink_ev[0]) for (auto& e : h->sink_ev) RPF_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
     const bool graphable = h->use_graphs && !hostX && Tg == T && L > 0 && n > 0 && !h->profiling;
     if (graphable && h->build_graph && h->graph_epoch == h->cfg_epoch) {
         RPF_CUDA(h, cudaGraphLaunch(h->build_graph, h->stream));
@@ -2348,8 +2373,21 @@ int rpf_build_impl(rpf_handle* h, const double* hostX) {
             J.keys = keys; J.kmin = kmin; J.kmax = kmax;
             J.perm = h->d_perm + (int64_t)t0 * n; J.thr = h->d_thr; J.mlo = h->d_mlo; J.mhi = h->d_mhi;
             J.gt0 = t0; J.tg = tg;
+            J.stream_to_sink = sink;
             int rc2 = rpf_launch_job(h, J, BP->P, BP->d_tab);
             if (rc2) return rc2;
+        }
+        if (sink) {     // node arrays (and perm, unless the job streamed it group by group) once everything is final
+            RPF_CUDA(h, cudaEventRecord(h->sink_ev[8], h->stream));
+            RPF_CUDA(h, cudaStreamWaitEvent(h->d2h_stream, h->sink_ev[8], 0));
+            const size_t nb = (size_t)T * (size_t)nn * 8;
+            if (h->sink_thr && nb) RPF_CUDA(h, cudaMemcpyAsync(h->sink_thr, h->d_thr, nb, cudaMemcpyDeviceToHost, h->d2h_stream));
+            if (h->sink_mlo && nb) RPF_CUDA(h, cudaMemcpyAsync(h->sink_mlo, h->d_mlo, nb, cudaMemcpyDeviceToHost, h->d2h_stream));
+            if (h->sink_mhi && nb) RPF_CUDA(h, cudaMemcpyAsync(h->sink_mhi, h->d_mhi, nb, cudaMemcpyDeviceToHost, h->d2h_stream));
+            if (!h->sink_perm_streamed && n > 0)
+                RPF_CUDA(h, cudaMemcpyAsync(h->sink_perm, h->d_perm, (size_t)T * n * 4, cudaMemcpyDeviceToHost, h->d2h_stream));
+            RPF_CUDA(h, cudaEventRecord(h->sink_ev[9], h->d2h_stream));
+            h->sink_pending = true;
         }
         return RPF_OK;
     };

@@ -327,6 +327,8 @@ void rpf_destroy(rpf_handle* h) {
     if (h->batch_plan && h->batch_plan_free) h->batch_plan_free(h->batch_plan);
     for (auto e : h->copy_ev) if (e) cudaEventDestroy(e);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    for (auto e : h->sink_ev) if (e) cudaEventDestroy(e);
+    if (h->d2h_stream) { cudaStreamSynchronize(h->d2h_stream); cudaStreamDestroy(h->d2h_stream); }
     h->ws_free_all();
     h->stage_free_all();
     for (auto e : h->event_pool) cudaEventDestroy(e);
@@ -772,6 +774,10 @@ int rpf_forest_export(rpf_handle* h, double* thr, double* mlo, double* mhi, uint
     if (!h) return RPF_ERR_ARG;
     if (!h->built) return rpf_fail(h, RPF_ERR_STATE, "forest_export: forest not built");
     RPF_SETDEV(h);
+    if (h->sink_pending && perm == h->sink_perm && thr == h->sink_thr && mlo == h->sink_mlo && mhi == h->sink_mhi) {
+        RPF_CUDA(h, cudaEventSynchronize(h->sink_ev[9]));        // the build streamed the forest into these buffers already
+        return RPF_OK;
+    }
     // the device arrays are already [T][nodes] / [T][n]: four straight copies on the engine's stream, one sync
     const size_t nb = (size_t)h->T * (size_t)h->topo.nnodes() * 8, pb = (size_t)h->T * (size_t)h->n * 4;
     if (thr && nb) RPF_CUDA(h, cudaMemcpyAsync(thr, h->d_thr, nb, cudaMemcpyDeviceToHost, h->stream));
@@ -779,6 +785,15 @@ int rpf_forest_export(rpf_handle* h, double* thr, double* mlo, double* mhi, uint
     if (mhi && nb) RPF_CUDA(h, cudaMemcpyAsync(mhi, h->d_mhi, nb, cudaMemcpyDeviceToHost, h->stream));
     if (perm && pb) RPF_CUDA(h, cudaMemcpyAsync(perm, h->d_perm, pb, cudaMemcpyDeviceToHost, h->stream));
     RPF_CUDA(h, cudaStreamSynchronize(h->stream));
+    return RPF_OK;
+}
+
+int rpf_set_export_sink(rpf_handle* h, double* thr, double* mlo, double* mhi, uint32_t* perm) {
+    if (!h) return RPF_ERR_ARG;
+    RPF_SETDEV(h);
+    if (h->d2h_stream) RPF_CUDA(h, cudaStreamSynchronize(h->d2h_stream));
+    h->sink_thr = thr; h->sink_mlo = mlo; h->sink_mhi = mhi; h->sink_perm = perm;
+    h->sink_pending = false;
     return RPF_OK;
 }
 

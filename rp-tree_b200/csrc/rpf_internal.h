@@ -63,6 +63,7 @@ struct BuildJob {
     uint32_t* perm = nullptr;                   // [tg][ps] out: point ids 0..n-1, leaves left to right
     double *thr = nullptr, *mlo = nullptr, *mhi = nullptr;   // [..][ns] out, indexed (gt0 + t) * ns + node
     int gt0 = 0, tg = 0;
+    bool stream_to_sink = false;                // batch build from host with an export sink: copy perm per bottom tree group
     bool order_exact = true;                    // out: every leaf is in the reference's order
 };
 struct JobGeom {
@@ -115,6 +116,13 @@ struct rpf_handle {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;   // rpf_build_from_host: row-block uploads overlapped with the projection
     cudaEvent_t copy_ev[9] = {nullptr};
+    // export sink (rpf_set_export_sink): host buffers the forest is streamed into while rpf_build_from_host still runs --
+    // the bottom phase is launched in tree groups and every group's slice of perm starts its D2H as soon as it is final
+    double *sink_thr = nullptr, *sink_mlo = nullptr, *sink_mhi = nullptr; uint32_t* sink_perm = nullptr;
+    cudaStream_t d2h_stream = nullptr;
+    cudaEvent_t sink_ev[10] = {nullptr};  // [0..7] bottom groups, [8] whole build, [9] sink complete
+    bool sink_pending = false;            // the sink holds (or is receiving) the forest of the last build
+    bool sink_perm_streamed = false;      // set by the job when it issued the perm copies itself
     std::string err;
 
     // points

@@ -534,3 +534,44 @@ def test_brute_force_topk_sampled_threshold_path(built, kind):
             od, oi = orc.brute_knn(X, Q[i], k)
             assert np.array_equal(bits(fd[i]), bits(od)) and np.array_equal(fi[i], oi), (kind, k, i)
     f.close()
+
+
+@pytest.mark.parametrize("T,cap", [(8, 256), (16, 1024), (3, 256)])
+def test_export_sink_streams_the_same_forest(built, T, cap):
+    """rpf_set_export_sink: buildFromHost downloads perm per bottom-phase tree group while the build runs; the sink must
+    hold exactly what a plain forestExport returns (and the oracle's trees), also across repeated builds and for forests
+    too small to be split (T < 8)."""
+    import torch
+    R, orc = _mods()
+    n, d, maxd, minl, pnz = 24000, 12, 11, 10, 0.4
+    X = make_data(n, d, 21, "mixture")
+    hp = orc.gen_hyperplanes(31, T, maxd, pnz, d)
+    f = R.RPForest(0)
+    f.setHyperplanes(hp, T, maxd)
+    if cap:
+        f.setBottomCap(cap)
+    f.buildFromHost(X, maxd, minl)
+    ref = f.forestExport()
+    nn = ref["thr"].shape[1]
+    sink = {k: torch.zeros((T, nn), dtype=torch.float64, pin_memory=True).numpy() for k in ("thr", "mlo", "mhi")}
+    sink["perm"] = torch.zeros((T, n), dtype=torch.int32, pin_memory=True).numpy().view(np.uint32)
+    f.setExportSink(sink)
+    for rep in range(2):
+        for a in sink.values():
+            a[...] = 0
+        f.buildFromHost(X, maxd, minl)
+        out = f.forestExport(sink)
+        assert out is sink
+        for key in ("thr", "mlo", "mhi"):
+            assert np.array_equal(bits(sink[key]), bits(ref[key])), (key, rep)
+        assert np.array_equal(sink["perm"], ref["perm"]), rep
+    other = f.forestExport()                       # different buffers: the plain download still works with a sink set
+    assert np.array_equal(other["perm"], ref["perm"])
+    f.build(maxd, minl)                            # resident-data build: no streaming, export copies
+    again = f.forestExport(sink)
+    assert np.array_equal(again["perm"], ref["perm"]) and np.array_equal(bits(again["thr"]), bits(ref["thr"]))
+    f.setExportSink(None)
+    of = orc.Forest(X, hp, T, maxd, minl)
+    for t in range(T):
+        assert not compare_tree(f.treeExport(t), of.export(t))
+    f.close()
