@@ -2346,7 +2346,7 @@ int rpf_build_impl(rpf_handle* h, const double* hostX) {
                 RPF_CUDA(h, cudaMemsetAsync(kmax, 0x00, (size_t)tg * L * 8, h->stream));
                 if (pipelined) {
                     if (!h->copy_stream) RPF_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-                    const int NBLK = 8;
+                    const int NBLK = 16;
                     int64_t rows = (n + NBLK - 1) / NBLK;
                     rows = (rows + 4095) / 4096 * 4096;              // whole projection tiles, 32-byte aligned key columns
                     // the upload may only start once the engine's stream is done with the previous contents of dX

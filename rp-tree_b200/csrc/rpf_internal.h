@@ -115,7 +115,7 @@ struct rpf_handle {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;   // rpf_build_from_host: row-block uploads overlapped with the projection
-    cudaEvent_t copy_ev[9] = {nullptr};
+    cudaEvent_t copy_ev[17] = {nullptr};  // one per upload block + the "previous contents of dX are no longer read" event
     // export sink (rpf_set_export_sink): host buffers the forest is streamed into while rpf_build_from_host still runs --
     // the bottom phase is launched in tree groups and every group's slice of perm starts its D2H as soon as it is final
     double *sink_thr = nullptr, *sink_mlo = nullptr, *sink_mhi = nullptr; uint32_t* sink_perm = nullptr;
