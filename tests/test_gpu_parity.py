@@ -575,3 +575,22 @@ def test_export_sink_streams_the_same_forest(built, T, cap):
     for t in range(T):
         assert not compare_tree(f.treeExport(t), of.export(t))
     f.close()
+
+
+@pytest.mark.parametrize("lean", [1, 0], ids=["lean-then-generic-levels", "generic-levels-only"])
+def test_top_phase_beyond_1024_nodes_per_level(built, lean):
+    """600k points with bottom_cap 256: the top phase runs 12 levels, the last ones with 2048 nodes per tree -- more than
+    the lean kernels' shared-memory tables (1024) and than the shared-memory histogram (512: global-atomic histogram) --
+    so one build mixes lean levels, generic levels and both histogram forms.  Integer-valued columns add straddling ties."""
+    R, orc = _mods()
+    n, d, T, maxd, minl, pnz = 600_000, 4, 2, 13, 100, 0.75
+    rng = np.random.default_rng(5)
+    X = rng.normal(size=(n, d))
+    X[:, 1] = np.round(X[:, 1] * 3)
+    hp = orc.gen_hyperplanes(41, T, maxd, pnz, d)
+    f = R.forestBatch(0, maxd, minl, T, pnz, d, X, hyperplanes=hp, bottom_cap=256, options={"lean_top": lean})
+    assert f.leafOrderExact()
+    of = orc.Forest(X, hp, T, maxd, minl)
+    for t in range(T):
+        bad = compare_tree(f.treeExport(t), of.export(t))
+        assert not bad, "tree %d: %s" % (t, bad)
