@@ -128,15 +128,23 @@ def gather_rows(full, block, group=None):
 
 
 class ReplicatedPoints:
-    """Device-resident replica of the host data set, filled by a row-sharded upload: rank r copies rows
-    [r*per, (r+1)*per) from (pinned) host memory over its own PCIe link, then the blocks are all-gathered over NCCL
-    (NVLink / NVSwitch) so that every GPU holds all n rows.  H2D traffic per rank is n*d*8 / world bytes instead of
-    n*d*8.  The buffer is kept across calls (one allocation per shape)."""
+    """Device-resident replica of the host data set, filled by a row-sharded upload: the rows are cut into `slices`
+    contiguous slices; inside slice s rank r copies ITS sub-block of rows from (pinned) host memory over its own PCIe
+    link, and the sub-blocks of a slice are all-gathered in place over NCCL (NVLink / NVSwitch) -- the all-gather of slice s
+    overlaps the PCIe upload of slice s+1 (uploads on a side stream, one event per slice).  Every GPU ends up with all n
+    rows; H2D traffic per rank is n*d*8 / world bytes instead of n*d*8.  The buffer is kept across calls."""
 
-    def __init__(self, device, group=None):
-        self.device, self.group = device, group
+    def __init__(self, device, group=None, slices=4):
+        self.device, self.group, self.slices = device, group, max(1, int(slices))
         self.buf = None
         self.n = self.d = 0
+        self._copy_stream = None
+
+    def layout(self, n, world):
+        """(rows per slice, rows per rank inside a slice, number of slices): slice s covers rows [s*S, (s+1)*S)."""
+        nsl = max(1, min(self.slices, n // max(world * 1024, 1)))       # no slicing for small inputs
+        sub = (n + nsl * world - 1) // (nsl * world)
+        return sub * world, sub, nsl
 
     def upload(self, X):
         """X: n x d float64 host array or CPU tensor (ideally pinned), identical on every rank.  Returns (device pointer, n, d)."""
@@ -146,17 +154,41 @@ class ReplicatedPoints:
         if not isinstance(X, torch.Tensor):
             X = torch.from_numpy(np.ascontiguousarray(X, np.float64))
         n, d = X.shape
-        per, r0, rl = shard_rows(n, world, rank)
-        if self.buf is None or self.buf.shape != (world * per, d):
-            self.buf = torch.empty((world * per, d), dtype=torch.float64, device=self.device)
-        mine = self.buf[rank * per:(rank + 1) * per]
-        if rl > 0:
-            mine[:rl].copy_(X[r0:r0 + rl], non_blocking=True)
-        if rl < per:
-            mine[rl:].zero_()
-        gather_rows(self.buf, mine, group=self.group)
-        if self.buf.is_cuda:
-            torch.cuda.current_stream(self.buf.device).synchronize()   # complete before the engine's stream reads it
+        S, sub, nsl = self.layout(n, world)
+        if self.buf is None or self.buf.shape != (nsl * S, d):
+            self.buf = torch.empty((nsl * S, d), dtype=torch.float64, device=self.device)
+        cuda = self.buf.is_cuda
+        if cuda and self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.buf.device)
+        main = torch.cuda.current_stream(self.buf.device) if cuda else None
+        if cuda:
+            self._copy_stream.wait_stream(main)                  # the previous contents are no longer read
+        events = []
+        for s in range(nsl):                                     # this rank's sub-block of every slice: PCIe, side stream
+            r0 = s * S + rank * sub
+            rl = max(0, min(n, r0 + sub) - r0)
+            mine = self.buf[r0:r0 + sub]
+            if cuda:
+                with torch.cuda.stream(self._copy_stream):
+                    if rl > 0:
+                        mine[:rl].copy_(X[r0:r0 + rl], non_blocking=True)
+                    if rl < sub:
+                        mine[rl:].zero_()
+                    ev = torch.cuda.Event()
+                    ev.record(self._copy_stream)
+                events.append(ev)
+            else:
+                if rl > 0:
+                    mine[:rl].copy_(X[r0:r0 + rl])
+                if rl < sub:
+                    mine[rl:].zero_()
+        for s in range(nsl):                                     # slice by slice: NVLink all-gather as soon as the slice is up
+            if cuda:
+                main.wait_event(events[s])
+            r0 = s * S + rank * sub
+            gather_rows(self.buf[s * S:(s + 1) * S], self.buf[r0:r0 + sub], group=self.group)
+        if cuda:
+            main.synchronize()                                   # complete before the engine's stream reads it
         self.n, self.d = n, d
         return self.buf.data_ptr(), n, d
 

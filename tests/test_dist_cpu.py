@@ -109,9 +109,11 @@ def _rows_worker(rank, world, port, q):
         import rp_tree_b200 as R
         dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
         ok = True
-        for n in (1001, 64, 3):
+        for n, slices in ((1001, 4), (64, 4), (3, 1), (10000, 4), (8200, 3), (4097, 2)):
             X = np.random.default_rng(3).normal(size=(n, 5))
-            rp = R.dist.ReplicatedPoints(torch.device("cpu"))
+            rp = R.dist.ReplicatedPoints(torch.device("cpu"), slices=slices)
+            S, sub, nsl = rp.layout(n, world)
+            ok &= nsl * S >= n and S == sub * world and (nsl == 1 or n >= world * 1024 * nsl)
             ptr, nn, d = rp.upload(X)
             ok &= (nn, d) == (n, 5) and ptr == rp.buf.data_ptr()
             ok &= np.array_equal(rp.buf[:n].numpy().view(np.uint64), X.view(np.uint64))
