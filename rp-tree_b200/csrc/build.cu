@@ -1140,8 +1140,8 @@ __global__ void __launch_bounds__(TOP_NT, RELABEL_MINB) k_top_relabel(TopArgs A,
 
 // ---- lean top-phase kernels --------------------------------------------------------------------------------------
 // Used when the level's nodes all split, fit the shared-memory tables (<= SMEM_NODES) and n % 8 == 0 (16-byte rows of
-// 2-byte bins / labels).  They stream 8 points per load (one 16-byte load of bins + one of labels, every load of a CTA
-// chunk in flight at once) and touch an 8-byte key only for a point in the median bin or in a margin-tracking bin
+// 2-byte bins / labels).  They stream 8 points per load (one 16-byte load of bins + one of labels, LEAN_G such pairs in
+// flight per thread) and touch an 8-byte key only for a point in the median bin or in a margin-tracking bin
 // (NodeSel::lo_bin / hi_bin), so no level has to fall back to streaming the keys.
 struct LeanTabs { ull thr[SMEM_NODES]; uint16_t sbin[SMEM_NODES], lob[SMEM_NODES], hib[SMEM_NODES]; };
 
