@@ -220,7 +220,7 @@ static void free_forest_dev(rpf_handle* h) {
     if (h->d_mlo) cudaFree(h->d_mlo);
     if (h->d_mhi) cudaFree(h->d_mhi);
     if (h->d_perm) cudaFree(h->d_perm);
-    h->d_thr = h->d_mlo = h->d_mhi = nullptr; h->d_perm = nullptr; h->built = false;
+    h->d_thr = h->d_mlo = h->d_mhi = nullptr; h->d_perm = nullptr; h->built = false; h->sink_pending = false;
     h->res_node_bytes = h->res_perm_bytes = 0;
 }
 
@@ -351,7 +351,7 @@ int rpf_set_points(rpf_handle* h, const double* X, int64_t n, int32_t d) {
     const size_t bytes = std::max<size_t>((size_t)n * d * 8, 16);
     if (h->ownX && h->dX && h->x_bytes == bytes) {
         p = (double*)h->dX;                       // same footprint: reuse the device buffer
-        h->built = false;
+        h->built = false; h->sink_pending = false;
     } else {
         if (h->ownX && h->dX) cudaFree((void*)h->dX);
         h->dX = nullptr; h->ownX = false;
@@ -581,7 +581,7 @@ int rpf_build(rpf_handle* h, int32_t maxDepth, int32_t minLeaf) {
     }
     rc = rpf_upload_topology(h);
     if (rc) return rc;
-    h->built = false;
+    h->built = false; h->sink_pending = false;
     h->stream_lost = 0;
     h->call_begin();
     rc = rpf_build_impl(h, nullptr);
@@ -609,7 +609,7 @@ int rpf_build_from_host(rpf_handle* h, const double* X, int64_t n, int32_t d, in
         RPF_CUDA(h, cudaMalloc(&p, bytes));
         h->dX = p; h->ownX = true; h->x_bytes = bytes;
     }
-    h->n = n; h->d = d; h->built = false;
+    h->n = n; h->d = d; h->built = false; h->sink_pending = false;
     int rc = check_build_args(h, maxDepth, minLeaf);
     if (rc) return rc;
     if (!(h->topo_key_n == h->n && h->topo_key_maxd == maxDepth && h->topo_key_minl == minLeaf)) {
@@ -635,7 +635,7 @@ int rpf_build_chunked(rpf_handle* h, int32_t maxDepth, int32_t minLeaf, int64_t 
     int rc = check_build_args(h, maxDepth, minLeaf);
     if (rc) return rc;
     RPF_SETDEV(h);
-    h->built = false;
+    h->built = false; h->sink_pending = false;
     h->call_begin();
     rc = rpf_build_stream_impl(h, maxDepth, minLeaf, chunk);     // sets h->topo and the device topology itself
     int rc2 = h->call_end();
@@ -689,7 +689,7 @@ int rpf_forest_load(rpf_handle* h, const char* path) {
     FILE* f = fopen(path, "rb");
     if (!f) return rpf_fail(h, RPF_ERR_ARG, std::string("forest_load: cannot open ") + path);
     CkptHeader H{};
-    auto fail = [&](const char* why) { fclose(f); h->built = false; return rpf_fail(h, RPF_ERR_ARG, std::string("forest_load: ") + why); };
+    auto fail = [&](const char* why) { fclose(f); h->built = false; h->sink_pending = false; return rpf_fail(h, RPF_ERR_ARG, std::string("forest_load: ") + why); };
     if (!rd(f, &H, 1) || std::memcmp(H.magic, "RPFB200", 8) != 0 || H.version != 1) return fail("not a forest checkpoint");
     if (H.n < 0 || H.nn < 1 || H.T < 1 || H.d < 1 || H.hpDepth < 0 || H.nlevels < 1 || H.hp_nnz < 0) return fail("corrupt header");
     const bool has_points = H.flags & 1u, sparse = H.flags & 2u;
@@ -698,7 +698,7 @@ int rpf_forest_load(rpf_handle* h, const char* path) {
         if (sparse != (h->d_xlast != nullptr)) return fail("point representation (SVector / DVector) differs from the checkpoint's");
     }
     const size_t nn = (size_t)H.nn, T = (size_t)H.T, n = (size_t)H.n;
-    h->built = false;
+    h->built = false; h->sink_pending = false;
     h->T = H.T; h->hpDepth = H.hpDepth;
     h->hp_off.resize((size_t)H.T * H.hpDepth + 1); h->hp_idx.resize((size_t)H.hp_nnz); h->hp_val.resize((size_t)H.hp_nnz);
     Topology tp;

@@ -570,6 +570,13 @@ def test_export_sink_streams_the_same_forest(built, T, cap):
     f.build(maxd, minl)                            # resident-data build: no streaming, export copies
     again = f.forestExport(sink)
     assert np.array_equal(again["perm"], ref["perm"]) and np.array_equal(bits(again["thr"]), bits(ref["thr"]))
+    f.buildFromHost(X, maxd, minl)                 # the sink holds this forest ...
+    f.forestExport(sink)
+    f.build(maxd, minl, chunk=5000)                # ... and must not be taken for the streamed one built afterwards
+    fresh = f.forestExport()
+    stale = f.forestExport(sink)
+    assert np.array_equal(stale["perm"], fresh["perm"]) and np.array_equal(bits(stale["thr"]), bits(fresh["thr"]))
+    f.build(maxd, minl)
     f.setExportSink(None)
     of = orc.Forest(X, hp, T, maxd, minl)
     for t in range(T):
