@@ -57,6 +57,8 @@ def lib():
         L.orc_gen_hyperplanes.argtypes = [C.c_uint64, C.c_int32, C.c_int32, C.c_double, C.c_int32, c_i64p, c_i32p, c_f64p]
         L.orc_forest_new.restype = C.c_void_p
         L.orc_forest_new.argtypes = [c_f64p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_i64p, c_i32p, c_f64p]
+        L.orc_forest_new_mt.restype = C.c_void_p
+        L.orc_forest_new_mt.argtypes = [c_f64p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_i64p, c_i32p, c_f64p, C.c_int32]
         L.orc_forest_new_chunked.restype = C.c_void_p
         L.orc_forest_new_chunked.argtypes = [c_f64p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64, c_i64p, c_i32p, c_f64p]
         L.orc_forest_new_sparse.restype = C.c_void_p
@@ -87,6 +89,8 @@ def lib():
         L.orc_knn_h_sq.argtypes = [C.c_void_p, C.c_int64, c_i32p, c_f64p, C.c_int32, c_f64p, c_u32p, C.c_int64]
         L.orc_recall.restype = C.c_double
         L.orc_recall.argtypes = [C.c_void_p, c_f64p, C.c_int32]
+        L.orc_recall_shared.restype = C.c_double
+        L.orc_recall_shared.argtypes = [C.c_void_p, c_f64p, C.c_int32]
         L.orc_brute_knn.argtypes = [c_f64p, C.c_int64, C.c_int32, c_f64p, C.c_int32, c_f64p, c_u32p]
         L.orc_set_use_pow.argtypes = [C.c_int]
         _LIB = L
@@ -182,7 +186,7 @@ def gen_hyperplanes(seed, T, maxd, pnz, dim):
 class Forest:
     """Oracle forest built with forestBatch semantics (chunk=None) or forest/conduit semantics (chunk=int)."""
 
-    def __init__(self, X, hp, T, maxd, minl, chunk=None):
+    def __init__(self, X, hp, T, maxd, minl, chunk=None, threads=1):
         self.X = np.ascontiguousarray(X, np.float64)
         self.n, self.d = self.X.shape
         off, idx, val = hp
@@ -191,7 +195,10 @@ class Forest:
         self.val = np.ascontiguousarray(val if len(val) else np.zeros(1), np.float64)
         self.T, self.maxd, self.minl = T, maxd, minl
         L = lib()
-        if chunk is None:
+        if chunk is None and threads > 1:
+            self.h = L.orc_forest_new_mt(_p(self.X, c_f64p), self.n, self.d, T, maxd, minl,
+                                         _p(self.off, c_i64p), _p(self.idx, c_i32p), _p(self.val, c_f64p), threads)
+        elif chunk is None:
             self.h = L.orc_forest_new(_p(self.X, c_f64p), self.n, self.d, T, maxd, minl,
                                       _p(self.off, c_i64p), _p(self.idx, c_i32p), _p(self.val, c_f64p))
         else:
@@ -235,6 +242,11 @@ class Forest:
     def recall(self, q, k):
         q = np.ascontiguousarray(q, np.float64)
         return lib().orc_recall(self.h, _p(q, c_f64p), k)
+
+    def recall_shared(self, q, k):
+        """recall() with the brute-force distances evaluated once per query instead of once per tree (same value)."""
+        q = np.ascontiguousarray(q, np.float64)
+        return lib().orc_recall_shared(self.h, _p(q, c_f64p), k)
 
     def knn_h(self, q, k):
         """knnH: (distances, ids) in the reference's result order (not sorted by distance, not cut to k)."""
@@ -312,6 +324,15 @@ class SparseForest(Forest):
             return Forest.recall(self, q, k)
         nz, ii, vv = _sv(*q)
         return lib().orc_recall_sq(self.h, nz, _p(ii, c_i32p), _p(vv, c_f64p), k)
+
+
+def slice_hyperplanes(hp, maxd, t_first, t_local):
+    """CSR rows of trees [t_first, t_first + t_local) of a forest-wide hyperplane set, re-based to offset 0."""
+    off, idx, val = hp
+    a, b = t_first * maxd, (t_first + t_local) * maxd
+    lo, hi = int(off[a]), int(off[b])
+    return (np.ascontiguousarray(off[a:b + 1] - off[a], np.int64), np.ascontiguousarray(idx[lo:hi], np.int32),
+            np.ascontiguousarray(val[lo:hi], np.float64))
 
 
 def brute_knn(X, q, k):

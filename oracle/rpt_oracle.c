@@ -8,6 +8,7 @@
  */
 #include "rpt_oracle.h"
 #include <stdlib.h>
+#include <pthread.h>
 #include <string.h>
 #include <math.h>
 
@@ -415,6 +416,41 @@ orc_forest* orc_forest_new_sparse(int64_t n, int32_t d, const int64_t* sp_off, c
     free(ids);
     return f;
 }
+/* The same forest with the independent trees built on `nthreads` host threads (createMulti is a map over the IntMap of
+ * trees, Internal.hs:234-240; the reference itself is single threaded -- this exists so that the CPU arm of the benchmark
+ * can use every host core).  Result identical to orc_forest_new. */
+typedef struct { orc_forest* f; const uint32_t* ids; int32_t t0, t1, step; } mt_job;
+static void* mt_run(void* arg) {
+    mt_job* j = (mt_job*)arg;
+    for (int32_t t = j->t0; t < j->t1; t += j->step)
+        j->f->roots[t] = insert_loop(j->f, t, 0, tip_new(NULL, 0), j->ids, j->f->n);
+    return NULL;
+}
+orc_forest* orc_forest_new_mt(const double* X, int64_t n, int32_t d, int32_t T, int32_t maxd, int32_t minl,
+                              const int64_t* hp_off, const int32_t* hp_idx, const double* hp_val, int32_t nthreads) {
+    orc_forest* f = (orc_forest*)calloc(1, sizeof(orc_forest));
+    f->X = X; f->n = n; f->d = d; f->T = T; f->maxd = maxd; f->minl = minl;
+    int64_t nhp = (int64_t)T * maxd, nnz = hp_off[nhp];
+    f->hp_off = (int64_t*)malloc(sizeof(int64_t) * (size_t)(nhp + 1));
+    memcpy(f->hp_off, hp_off, sizeof(int64_t) * (size_t)(nhp + 1));
+    f->hp_idx = (int32_t*)malloc(sizeof(int32_t) * (size_t)(nnz > 0 ? nnz : 1));
+    f->hp_val = (double*)malloc(sizeof(double) * (size_t)(nnz > 0 ? nnz : 1));
+    if (nnz > 0) { memcpy(f->hp_idx, hp_idx, sizeof(int32_t) * (size_t)nnz); memcpy(f->hp_val, hp_val, sizeof(double) * (size_t)nnz); }
+    f->roots = (onode**)calloc((size_t)T, sizeof(onode*));
+    uint32_t* ids = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)(n > 0 ? n : 1));
+    for (int64_t i = 0; i < n; ++i) ids[i] = (uint32_t)i;
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > T) nthreads = T;
+    pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * (size_t)nthreads);
+    mt_job* jobs = (mt_job*)malloc(sizeof(mt_job) * (size_t)nthreads);
+    for (int32_t i = 0; i < nthreads; ++i) {
+        jobs[i].f = f; jobs[i].ids = ids; jobs[i].t0 = i; jobs[i].t1 = T; jobs[i].step = nthreads;
+        pthread_create(&th[i], NULL, mt_run, &jobs[i]);
+    }
+    for (int32_t i = 0; i < nthreads; ++i) pthread_join(th[i], NULL);
+    free(th); free(jobs); free(ids);
+    return f;
+}
 orc_forest* orc_forest_new(const double* X, int64_t n, int32_t d, int32_t T, int32_t maxd, int32_t minl,
                            const int64_t* hp_off, const int32_t* hp_idx, const double* hp_val) {
     return orc_forest_new_chunked(X, n, d, T, maxd, minl, n > 0 ? n : 1, hp_off, hp_idx, hp_val);
@@ -623,6 +659,58 @@ static double recall_q(const orc_forest* f, const qref* q, int32_t k) {
     return sum / (double)f->T;
 }
 
+/* recallWith with the brute-force distances evaluated ONCE instead of once per tree (same value as recall_q).  In a batch
+ * forest every tree holds all n rows, so the per-tree truth sets of RPTree.hs:279 differ only in how a tie AT the k-th
+ * distance is cut (each tree's own leaf order); when such a tie exists, or a tree does not hold all rows (streaming build
+ * with dropped subtrees), the query is answered by recall_q itself. */
+static double recall_shared_q(const orc_forest* f, const qref* q, int32_t k) {
+    int64_t n = f->n;
+    if (n < 1 || k < 1) return recall_q(f, q, k);
+    for (int32_t t = 0; t < f->T; ++t) if (count_points(f->roots[t]) != n) return recall_q(f, q, k);
+    double* dd = (double*)malloc(sizeof(double) * (size_t)n);
+    for (int64_t i = 0; i < n; ++i) dd[i] = point_dist(f, (uint32_t)i, q);
+    int64_t kk = n < k ? n : k;
+    /* k-th smallest distance: keep the kk smallest seen so far in a sorted buffer */
+    double* best = (double*)malloc(sizeof(double) * (size_t)kk);
+    int64_t nb = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        double v = dd[i];
+        if (nb == kk && !(v < best[kk - 1])) continue;
+        int64_t p = nb < kk ? nb++ : kk - 1;
+        while (p > 0 && v < best[p - 1]) { best[p] = best[p - 1]; --p; }
+        best[p] = v;
+    }
+    double tau = best[kk - 1];
+    free(best);
+    int64_t nle = 0;
+    for (int64_t i = 0; i < n; ++i) if (dd[i] <= tau) ++nle;
+    if (nle != kk) { free(dd); return recall_q(f, q, k); }          /* tie across the cut: tree order decides */
+    uint32_t* top = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)kk);
+    int64_t m = 0;
+    for (int64_t i = 0; i < n; ++i) if (dd[i] <= tau) top[m++] = (uint32_t)i;   /* ascending row id */
+    free(dd);
+    double sum = 0.0;
+    for (int32_t t = 0; t < f->T; ++t) {
+        idbuf b = {0};
+        cand_go(f, t, 0, f->roots[t], q, &b);
+        if (b.n > 0) qsort(b.ids, (size_t)b.n, sizeof(uint32_t), cmp_u32);
+        int64_t hit = 0, i = 0, j = 0;
+        uint32_t last = 0; int have_last = 0;
+        while (i < b.n && j < kk) {
+            if (b.ids[i] < top[j]) ++i;
+            else if (b.ids[i] > top[j]) ++j;
+            else { if (!have_last || last != top[j]) { ++hit; last = top[j]; have_last = 1; } ++i; ++j; }
+        }
+        sum = sum + (double)hit / (double)k;
+        free(b.ids);
+    }
+    free(top);
+    return sum / (double)f->T;
+}
+double orc_recall_shared(const orc_forest* f, const double* q, int32_t k) {
+    qref r = {q, 0, NULL, NULL};
+    return recall_shared_q(f, &r, k);
+}
 double orc_recall(const orc_forest* f, const double* q, int32_t k) {
     qref r = {q, 0, NULL, NULL};
     return recall_q(f, &r, k);

@@ -69,6 +69,9 @@ orc_forest* orc_forest_new_chunked(const double* X, int64_t n, int32_t d, int32_
 orc_forest* orc_forest_new_sparse(int64_t n, int32_t d, const int64_t* sp_off, const int32_t* sp_idx, const double* sp_val,
                                   int32_t T, int32_t maxd, int32_t minl, int64_t chunk,
                                   const int64_t* hp_off, const int32_t* hp_idx, const double* hp_val);
+/* orc_forest_new with the (independent) trees built on nthreads host threads; identical result. */
+orc_forest* orc_forest_new_mt(const double* X, int64_t n, int32_t d, int32_t T, int32_t maxd, int32_t minl,
+                              const int64_t* hp_off, const int32_t* hp_idx, const double* hp_val, int32_t nthreads);
 void orc_forest_free(orc_forest* f);
 
 /* Canonical flat export of tree t: nodes in BFS (level-major, left-to-right) order.
@@ -95,6 +98,9 @@ int64_t orc_knn_h(const orc_forest* f, const double* q, int32_t k, double* dist,
 int64_t orc_knn_h_sq(const orc_forest* f, int64_t qnz, const int32_t* qidx, const double* qval, int32_t k, double* dist, uint32_t* ids, int64_t cap);
 /* recallWith (RPTree.hs:265-282): mean over trees of |cands(t) n topk| / k; point identity = row id. */
 double  orc_recall(const orc_forest* f, const double* q, int32_t k);
+/* same value, brute-force distances evaluated once instead of once per tree (falls back to orc_recall's path when a
+ * distance tie straddles rank k or a tree does not hold every row) -- makes full-size recall checks affordable */
+double  orc_recall_shared(const orc_forest* f, const double* q, int32_t k);
 /* exact brute-force k nearest (stable by row id) -- used for forest-level recall */
 void    orc_brute_knn(const double* X, int64_t n, int32_t d, const double* q, int32_t k, double* dist, uint32_t* ids);
 /* use libm pow(x,2.0) instead of x*x for the squared terms (GHC `** 2`, Internal.hs:404). default 0 */

@@ -682,62 +682,143 @@ int rpf_forest_save(rpf_handle* h, const char* path, int32_t with_points) {
     return RPF_OK;
 }
 
-int rpf_forest_load(rpf_handle* h, const char* path) {
-    if (!h || !path) return RPF_ERR_ARG;
-    RPF_SETDEV(h);
-    RPF_CUDA(h, cudaStreamSynchronize(h->stream));
+// every id in perm must be a row number (< n) or the "dropped slot" marker of a streaming build
+__global__ void k_check_perm(const uint32_t* __restrict__ perm, size_t cnt, uint32_t n, int* __restrict__ bad) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    int b = 0;
+    for (; i < cnt; i += stride) { const uint32_t v = perm[i]; if (v >= n && v != 0xffffffffu) b = 1; }
+    if (b) *bad = 1;
+}
+
+// Everything a query kernel later indexes with is validated here, BEFORE the handle is touched (deserialiseRPForest
+// returns Left on malformed input, Internal.hs:191-196): table sizes against the file length, CSR offsets, component
+// indices, the BFS topology, and -- on the device -- the row ids of perm.
+static int forest_load_impl(rpf_handle* h, const char* path) {
     FILE* f = fopen(path, "rb");
     if (!f) return rpf_fail(h, RPF_ERR_ARG, std::string("forest_load: cannot open ") + path);
+    struct Closer { FILE* f; ~Closer() { if (f) fclose(f); } } closer{f};     // also on an exception (bad_alloc)
     CkptHeader H{};
-    auto fail = [&](const char* why) { fclose(f); h->built = false; h->sink_pending = false; return rpf_fail(h, RPF_ERR_ARG, std::string("forest_load: ") + why); };
+    auto fail = [&](const char* why) { return rpf_fail(h, RPF_ERR_ARG, std::string("forest_load: ") + why); };
     if (!rd(f, &H, 1) || std::memcmp(H.magic, "RPFB200", 8) != 0 || H.version != 1) return fail("not a forest checkpoint");
-    if (H.n < 0 || H.nn < 1 || H.T < 1 || H.d < 1 || H.hpDepth < 0 || H.nlevels < 1 || H.hp_nnz < 0) return fail("corrupt header");
+    if (H.n < 0 || H.n >= ((int64_t)1 << 31) || H.nn < 1 || H.nn >= ((int64_t)1 << 31) || H.T < 1 || H.d < 1 || H.hpDepth < 0 ||
+        H.hpDepth > 4096 || H.nlevels < 1 || H.nlevels > 64 || H.hp_nnz < 0 || H.lost < 0 || H.maxDepth < 0 || H.minLeaf < 0 || (H.flags & ~3u))
+        return fail("corrupt header");
     const bool has_points = H.flags & 1u, sparse = H.flags & 2u;
+    // the header fixes the file length exactly; nothing below allocates more than the file holds
+    const long here = ftell(f);
+    if (fseek(f, 0, SEEK_END) != 0) return fail("cannot seek");
+    const long flen = ftell(f);
+    if (here < 0 || flen < 0 || fseek(f, here, SEEK_SET) != 0) return fail("cannot seek");
+    const unsigned __int128 nn = (unsigned __int128)H.nn, T = (unsigned __int128)H.T, n = (unsigned __int128)H.n, d = (unsigned __int128)H.d;
+    unsigned __int128 want = (unsigned __int128)here + (T * (unsigned __int128)H.hpDepth + 1) * 8 + (unsigned __int128)H.hp_nnz * 12 +
+                             nn * 16 + ((unsigned __int128)H.nlevels + 1) * 8 + (unsigned __int128)H.nlevels * 4 + T * nn * 24 + T * n * 4;
+    if (has_points) want += n * d * 8 + (sparse ? n * 4 : 0);
+    if (want != (unsigned __int128)flen) return fail("file length does not match the header (truncated or corrupt)");
     if (!has_points) {
         if (!h->dX || h->n != H.n || h->d != H.d) return fail("the checkpoint carries no points: call rpf_set_points with the same data first");
         if (sparse != (h->d_xlast != nullptr)) return fail("point representation (SVector / DVector) differs from the checkpoint's");
     }
-    const size_t nn = (size_t)H.nn, T = (size_t)H.T, n = (size_t)H.n;
-    h->built = false; h->sink_pending = false;
-    h->T = H.T; h->hpDepth = H.hpDepth;
-    h->hp_off.resize((size_t)H.T * H.hpDepth + 1); h->hp_idx.resize((size_t)H.hp_nnz); h->hp_val.resize((size_t)H.hp_nnz);
+    const size_t snn = (size_t)H.nn, sT = (size_t)H.T, sn = (size_t)H.n;
+    std::vector<int64_t> hp_off((size_t)H.T * H.hpDepth + 1); std::vector<int32_t> hp_idx((size_t)H.hp_nnz); std::vector<double> hp_val((size_t)H.hp_nnz);
     Topology tp;
-    tp.n = H.n; tp.maxDepth = H.maxDepth; tp.minLeaf = H.minLeaf; tp.nlevels = H.nlevels; tp.L_eff = H.L_eff;
-    tp.start.resize(nn); tp.size.resize(nn); tp.child.resize(nn); tp.depth.resize(nn); tp.level_off.resize((size_t)H.nlevels + 1); tp.lvl_maxsize.resize((size_t)H.nlevels);
-    if (!(rd(f, h->hp_off.data(), h->hp_off.size()) && rd(f, h->hp_idx.data(), h->hp_idx.size()) && rd(f, h->hp_val.data(), h->hp_val.size()) &&
-          rd(f, tp.start.data(), nn) && rd(f, tp.size.data(), nn) && rd(f, tp.child.data(), nn) && rd(f, tp.depth.data(), nn) &&
+    tp.n = H.n; tp.maxDepth = H.maxDepth; tp.minLeaf = H.minLeaf; tp.nlevels = H.nlevels;
+    tp.start.resize(snn); tp.size.resize(snn); tp.child.resize(snn); tp.depth.resize(snn); tp.level_off.resize((size_t)H.nlevels + 1); tp.lvl_maxsize.resize((size_t)H.nlevels);
+    if (!(rd(f, hp_off.data(), hp_off.size()) && rd(f, hp_idx.data(), hp_idx.size()) && rd(f, hp_val.data(), hp_val.size()) &&
+          rd(f, tp.start.data(), snn) && rd(f, tp.size.data(), snn) && rd(f, tp.child.data(), snn) && rd(f, tp.depth.data(), snn) &&
           rd(f, tp.level_off.data(), (size_t)H.nlevels + 1) && rd(f, tp.lvl_maxsize.data(), (size_t)H.nlevels)))
         return fail("truncated file");
-    if (h->hp_off.back() != H.hp_nnz || tp.level_off.back() != H.nn) return fail("inconsistent tables");
+    // hyperplanes: CSR rows over (tree, level)
+    if (hp_off[0] != 0 || hp_off.back() != H.hp_nnz) return fail("hyperplane offsets do not match the header");
+    for (size_t r = 0; r + 1 < hp_off.size(); ++r) if (hp_off[r + 1] < hp_off[r]) return fail("hyperplane offsets not monotone");
+    for (int32_t q : hp_idx) if (q < 0 || q >= H.d) return fail("hyperplane component index out of range");
+    // topology: BFS numbering, level table, segments inside perm
+    if (tp.level_off[0] != 0 || tp.level_off.back() != H.nn) return fail("level table does not match the node count");
+    for (int l = 0; l < H.nlevels; ++l) if (tp.level_off[l + 1] <= tp.level_off[l]) return fail("level table not increasing");
+    int L_eff = 0;
+    for (int l = 0; l < H.nlevels; ++l) {
+        uint32_t mx = 0;
+        for (int64_t g = tp.level_off[l]; g < tp.level_off[l + 1]; ++g) {
+            if (tp.depth[g] != l) return fail("node depth does not match its level");
+            if ((uint64_t)tp.start[g] + tp.size[g] > (uint64_t)H.n) return fail("node segment outside the point array");
+            mx = std::max(mx, tp.size[g]);
+            const int32_t c = tp.child[g];
+            if (c == -1) continue;
+            if (l + 1 >= H.nlevels || c < tp.level_off[l + 1] || (int64_t)c + 1 >= tp.level_off[l + 2]) return fail("child id outside the next level");
+            if (l >= H.hpDepth) return fail("internal node deeper than the stored hyperplanes");
+            if ((uint64_t)tp.size[c] + tp.size[c + 1] > (uint64_t)tp.size[g] || tp.start[c] < tp.start[g] ||
+                (uint64_t)tp.start[c + 1] + tp.size[c + 1] > (uint64_t)tp.start[g] + tp.size[g])
+                return fail("child segments outside the parent's");
+            L_eff = l + 1;
+        }
+        tp.lvl_maxsize[l] = mx;          // derived, not trusted: sizes shared-memory buffers of the query kernels
+    }
+    tp.L_eff = L_eff;
+    if (H.lost > H.n) return fail("corrupt header");
+
+    // ---- the file is sane: now replace the handle's state
+    h->built = false; h->sink_pending = false;
+    ++h->cfg_epoch;
+    h->T = H.T; h->hpDepth = H.hpDepth;
+    h->hp_off.swap(hp_off); h->hp_idx.swap(hp_idx); h->hp_val.swap(hp_val);
+    auto fail_reset = [&](int code, const char* why) {      // the previous forest is gone; leave a consistent "not built" handle
+        h->built = false; h->sink_pending = false;
+        return rpf_fail(h, code, std::string("forest_load: ") + why);
+    };
     if (has_points) {      // the data set travels with the forest: replace whatever the handle holds
         if (h->d_xlast) { cudaFree(h->d_xlast); h->d_xlast = nullptr; }
         if (h->ownX && h->dX) cudaFree((void*)h->dX);
-        h->dX = nullptr; h->ownX = false;
+        h->dX = nullptr; h->ownX = false; h->n = 0; h->x_bytes = 0;
         double* X = nullptr;
-        const size_t bytes = std::max<size_t>(n * (size_t)H.d * 8, 16);
-        if (cudaMalloc(&X, bytes) != cudaSuccess) { cudaGetLastError(); return fail("out of device memory"); }
+        const size_t bytes = std::max<size_t>(sn * (size_t)H.d * 8, 16);
+        if (cudaMalloc(&X, bytes) != cudaSuccess) { cudaGetLastError(); return fail_reset(RPF_ERR_NOMEM, "out of device memory"); }
         h->dX = X; h->ownX = true; h->x_bytes = bytes; h->n = H.n; h->d = H.d;
     }
     int rc = upload_hyperplanes(h);      // also drops the previous forest arrays
-    if (rc) { fclose(f); return rc; }
+    if (rc) return rc;
     h->topo = tp; h->topo_key_n = -1;
     rc = rpf_upload_topology(h);
     if (!rc) rc = rpf_alloc_forest(h, H.nn, H.n);
-    if (rc) { fclose(f); return rc; }
+    if (rc) return rc;
     std::vector<char> tmp;
-    bool ok = rd_dev(f, h->d_thr, T * nn, tmp) && rd_dev(f, h->d_mlo, T * nn, tmp) && rd_dev(f, h->d_mhi, T * nn, tmp) && rd_dev(f, h->d_perm, T * n, tmp);
+    bool ok = rd_dev(f, h->d_thr, sT * snn, tmp) && rd_dev(f, h->d_mlo, sT * snn, tmp) && rd_dev(f, h->d_mhi, sT * snn, tmp) && rd_dev(f, h->d_perm, sT * sn, tmp);
     if (ok && has_points) {
-        ok = rd_dev(f, (double*)h->dX, n * (size_t)H.d, tmp);
+        ok = rd_dev(f, (double*)h->dX, sn * (size_t)H.d, tmp);
         if (ok && sparse) {
-            if (cudaMalloc(&h->d_xlast, std::max<size_t>(n * 4, 16)) != cudaSuccess) { cudaGetLastError(); return fail("out of device memory"); }
-            ok = rd_dev(f, h->d_xlast, n, tmp);
+            if (cudaMalloc(&h->d_xlast, std::max<size_t>(sn * 4, 16)) != cudaSuccess) { cudaGetLastError(); return fail_reset(RPF_ERR_NOMEM, "out of device memory"); }
+            ok = rd_dev(f, h->d_xlast, sn, tmp);
         }
     }
-    if (!ok) return fail("truncated file");
-    fclose(f);
+    if (!ok) return fail_reset(RPF_ERR_ARG, "truncated file");
+    if (sT * sn > 0) {
+        int* bad = (int*)h->ws_get(WS_MAXCNT, 16);
+        if (!bad) return RPF_ERR_NOMEM;
+        RPF_CUDA(h, cudaMemsetAsync(bad, 0, 4, h->stream));
+        k_check_perm<<<1184, 256, 0, h->stream>>>(h->d_perm, sT * sn, (uint32_t)H.n, bad);
+        ++h->launches;
+        int hb = 0;
+        RPF_CUDA(h, cudaMemcpyAsync(&hb, bad, 4, cudaMemcpyDeviceToHost, h->stream));
+        RPF_CUDA(h, cudaStreamSynchronize(h->stream));
+        if (hb) return rpf_fail(h, RPF_ERR_ARG, "forest_load: perm holds a row id >= n");
+    }
     h->stream_lost = H.lost; h->leaf_order_exact = H.leaf_order_exact != 0;
     h->built = true;
     return RPF_OK;
+}
+
+int rpf_forest_load(rpf_handle* h, const char* path) {
+    if (!h || !path) return RPF_ERR_ARG;
+    RPF_SETDEV(h);
+    RPF_CUDA(h, cudaStreamSynchronize(h->stream));
+    try {
+        return forest_load_impl(h, path);
+    } catch (const std::bad_alloc&) {
+        h->built = false; h->sink_pending = false;
+        return rpf_fail(h, RPF_ERR_NOMEM, "forest_load: out of host memory");
+    } catch (const std::exception& e) {
+        h->built = false; h->sink_pending = false;
+        return rpf_fail(h, RPF_ERR_ARG, std::string("forest_load: ") + e.what());
+    }
 }
 
 int64_t rpf_num_nodes(const rpf_handle* h) { return h ? h->topo.nnodes() : -1; }

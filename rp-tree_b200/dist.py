@@ -12,10 +12,10 @@ import numpy as np
 
 
 def shard_trees(ntrees, world, rank):
-    """Contiguous block of trees owned by `rank`: (t_first, t_local)."""
-    per = (ntrees + world - 1) // world
-    t_first = min(rank * per, ntrees)
-    return t_first, max(0, min(ntrees, t_first + per) - t_first)
+    """Contiguous block of trees owned by `rank`: (t_first, t_local).  Balanced: the first ntrees % world ranks hold one
+    tree more, so every rank owns at least one tree whenever ntrees >= world (contiguous blocks keep the merge order)."""
+    base, rem = divmod(ntrees, world)
+    return rank * base + min(rank, rem), base + (1 if rank < rem else 0)
 
 
 def _dist():
@@ -47,9 +47,9 @@ def forestBatchSharded(seed, maxd, minl, ntrees, pnz, dim, xs, *, hyperplanes=No
     from .api import forestBatch
     dist = _dist()
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    t_first, t_local = shard_trees(ntrees, world, rank)
-    if t_local == 0:
+    if ntrees < world:                        # the same verdict on every rank, before any collective
         raise ValueError("more ranks (%d) than trees (%d)" % (world, ntrees))
+    t_first, t_local = shard_trees(ntrees, world, rank)
     return forestBatch(seed, maxd, minl, ntrees, pnz, dim, xs, hyperplanes=hyperplanes, device=device,
                        t_first=t_first, t_local=t_local, bottom_cap=bottom_cap)
 

@@ -426,6 +426,50 @@ def test_checkpoint_round_trip(built, tmp_path, with_points, chunk):
     bad.write_bytes(b"not a checkpoint")
     with pytest.raises(R.RPForestError):
         g.load(bad)
+    # ... and so is a truncated, padded or internally corrupt one (deserialiseRPForest returns Left, Internal.hs:191-196):
+    # nothing a query kernel indexes with may come from the file unchecked
+    raw = bytearray(path.read_bytes())
+    nn = len(f.topology()["child"])
+    hdr = 80                                            # CkptHeader
+    o_hpoff = hdr
+    o_hpidx = o_hpoff + (T * maxd + 1) * 8
+    nnz = len(hp[1])
+    o_start = o_hpidx + nnz * 12
+    o_child = o_start + nn * 8
+    o_perm = o_child + nn * 8 + (int(f.topology()["depth"].max()) + 2) * 8 + (int(f.topology()["depth"].max()) + 1) * 4 + T * nn * 24
+
+    def variant(name, mutate):
+        b = bytearray(raw)
+        b = mutate(b) or b
+        q = tmp_path / (name + ".rpf")
+        q.write_bytes(bytes(b))
+        return q
+
+    def put(b, off, val, fmt):
+        import struct
+        b[off:off + struct.calcsize(fmt)] = struct.pack(fmt, val)
+
+    cases = {
+        "truncated": lambda b: b[:-100],
+        "padded": lambda b: b + b"\0" * 8,
+        "hp_index": lambda b: put(b, o_hpidx + 4 * (nnz // 2), d + 3, "<i"),
+        "hp_offset": lambda b: put(b, o_hpoff + 8 * 3, 10 ** 9, "<q"),
+        "child": lambda b: put(b, o_child + 4 * 1, nn + 7, "<i"),
+        "segment": lambda b: put(b, o_start + 4 * (nn - 1), n + 1, "<I"),
+        "perm_row": lambda b: put(b, o_perm + 4 * 17, n + 5, "<I"),
+        "header_T": lambda b: put(b, 8 + 8 + 32 + 4, 10 ** 6, "<i"),
+    }
+    for name, mut in cases.items():
+        q = variant(name, mut)
+        with pytest.raises(R.RPForestError):
+            g.load(q)
+    # the handle is still usable after the refusals
+    if with_points:
+        g.load(path)
+    else:
+        g.setPoints(X)
+        g.load(path)
+    assert np.array_equal(g.knnBatch(Q, 7)[1], f.knnBatch(Q, 7)[1])
 
 
 def test_repeated_builds_replay_the_graph_and_follow_new_data(built):
