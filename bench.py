@@ -25,19 +25,41 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = dict(name="configs[1]: synthetic SIFT-like 1Mx128 fp64, 32 trees, pnz 0.1, 10k queries k=10",
-                n=1_000_000, d=128, ntrees=32, pnz=0.1, min_leaf=64, nq=10_000, k=10,
-                data_seed=1234, query_seed=4321, forest_seed=1235137, clusters=256, sigma=0.25)
+_COMMON = dict(data_seed=1234, query_seed=4321, forest_seed=1235137, clusters=256, sigma=0.25, pnz=0.1, min_leaf=64)
+CONFIGS = {   # BASELINE.json configs[1..4]; configs[0] (MNIST) is the reference's own CPU case (data file absent from the checkout)
+    "c2": dict(_COMMON, name="configs[1]: synthetic SIFT-like 1Mx128 fp64, 32 trees, pnz 0.1, 10k queries k=10",
+               n=1_000_000, d=128, ntrees=32, nq=10_000, k=10),
+    "c3": dict(_COMMON, name="configs[2]: synthetic GIST-like 1Mx960 fp64, 64 trees, pnz 0.1, 100k queries k=10",
+               n=1_000_000, d=960, ntrees=64, nq=100_000, k=10),
+    "c4": dict(_COMMON, name="configs[3]: synthetic 768-d embeddings, 5M points, 128 trees sharded across the GPUs, 100k queries k=10",
+               n=5_000_000, d=768, ntrees=128, nq=100_000, k=10),
+    "c5": dict(_COMMON, name="configs[4]: synthetic Deep1B-like 10Mx96, 256 trees, 1M queries k=100",
+               n=10_000_000, d=96, ntrees=256, nq=1_000_000, k=100),
+}
+WORKLOAD = CONFIGS["c2"]          # the headline configuration (the one BASELINE.json's metric is quoted on)
+GEN_BLOCK = 16384                 # rows per independently seeded block: any rank can generate any row range
 
 
-def make_points(n, d, seed, clusters, sigma, center_seed=99):
-    """Clustered Gaussian mixture: centres ~ N(0,1)^d, points = centre + N(0, sigma^2)^d."""
+def make_rows(n, d, seed, clusters, sigma, r0=0, r1=None, out=None, center_seed=99):
+    """Rows [r0, r1) of the clustered Gaussian mixture: centres ~ N(0,1)^d, points = centre + N(0, sigma^2)^d.
+    Block b of GEN_BLOCK rows is drawn from its own generator seeded (seed, b), so a row range is the same on every rank."""
+    r1 = n if r1 is None else r1
     cen = np.random.default_rng(center_seed).normal(size=(clusters, d))
-    rng = np.random.default_rng(seed)
-    X = rng.normal(size=(n, d))
-    X *= sigma
-    X += cen[rng.integers(0, clusters, size=n)]
+    X = np.empty((r1 - r0, d)) if out is None else out
+    for b in range(r0 // GEN_BLOCK, (max(r1, r0 + 1) - 1) // GEN_BLOCK + 1):
+        lo, hi = b * GEN_BLOCK, min(n, (b + 1) * GEN_BLOCK)
+        rng = np.random.default_rng([seed, b])
+        blk = rng.normal(size=(hi - lo, d))
+        blk *= sigma
+        blk += cen[rng.integers(0, clusters, size=hi - lo)]
+        a, z = max(lo, r0), min(hi, r1)
+        if z > a:
+            X[a - r0:z - r0] = blk[a - lo:z - lo]
     return X
+
+
+def make_points(n, d, seed, clusters, sigma):
+    return make_rows(n, d, seed, clusters, sigma)
 
 
 def config_dict(W, maxd, gpus):
@@ -140,7 +162,7 @@ def run_ours(args):
     import torch
     import rp_tree_b200 as R
 
-    W = WORKLOAD
+    W = CONFIGS[args.config]
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -148,41 +170,31 @@ def run_ours(args):
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch with torchrun for --gpus > 1")
     dist = None
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
     if world > 1:
+        # torch.distributed is only the launcher-side plumbing here (barrier, max over ranks, handing the NCCL id to the
+        # ranks); every data-path exchange runs inside the engine on its own communicator (rpf_comm_init_rank).
         # NCCL writes its banner / debug lines to stdout by default; stdout is reserved for the one JSON line
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
-        # ... and the version banner ignores NCCL_DEBUG_FILE: point fd 1 at stderr while the communicator comes up
         sys.stdout.flush()
         saved_stdout = os.dup(1)
         os.dup2(2, 1)
         try:
-            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.init_process_group("nccl", device_id=dev)
             dist.barrier()
             torch.cuda.synchronize()
         finally:
             sys.stdout.flush()
             os.dup2(saved_stdout, 1)
             os.close(saved_stdout)
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
 
     n, d, T, k, nq = W["n"], W["d"], W["ntrees"], W["k"], W["nq"]
     cfg = R.rpTreeCfg(W["min_leaf"], n, d)
     maxd = cfg.fpMaxTreeDepth
+    assert T >= world, "more ranks than trees"
     t_first, t_local = R.dist.shard_trees(T, world, rank)
-    assert t_local > 0, "more ranks than trees"
-
-    # synthetic inputs in PINNED host memory (so the e2e H2D is a real DMA)
-    Xp = torch.empty((n, d), dtype=torch.float64, pin_memory=True)
-    X = Xp.numpy()
-    X[:] = make_points(n, d, W["data_seed"], W["clusters"], W["sigma"])
-    Qp = torch.empty((nq, d), dtype=torch.float64, pin_memory=True)
-    Q = Qp.numpy()
-    Q[:] = make_points(nq, d, W["query_seed"], W["clusters"], W["sigma"])
-    hp_all = R.sampleHyperplanes(W["forest_seed"], T, maxd, W["pnz"], d)
-    hp = slice_hp(hp_all, maxd, t_first, t_local)
 
     def barrier():
         if dist is not None:
@@ -196,26 +208,53 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    f = R.RPForest(local_rank)
-    if os.environ.get("RPF_BOTTOM_CAP"):
-        f.setBottomCap(int(os.environ["RPF_BOTTOM_CAP"]))
-    f.setHyperplanes(hp, t_local, maxd)
-    f.setPoints(X)                      # resident in HBM before the timed region (the `value` arm)
-    merger = f
+    def new_forest():
+        f_ = R.RPForest(local_rank)
+        if os.environ.get("RPF_BOTTOM_CAP"):
+            f_.setBottomCap(int(os.environ["RPF_BOTTOM_CAP"]))
+        if world > 1:                                  # the engine's own communicator: id made on rank 0, handed out once
+            uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+            if rank == 0:
+                uid = torch.frombuffer(bytearray(R.RPForest.commUniqueId()), dtype=torch.uint8).to(dev)
+            dist.broadcast(uid, 0)
+            f_.commInitRank(world, rank, bytes(uid.cpu().numpy().tobytes()))
+        f_.setHyperplanes(hp, t_local, maxd)
+        return f_
 
-    def knn_step():
-        """local knn over this rank's trees -> NCCL all-gather of the device-resident lists over NVLink -> merge kernel.
-        Returns device ms (engine events for its two calls + torch events around the all-gather) and the merged result."""
-        if dist is None:
-            dd, ii, cc = f.knnBatch(Q, k, dedup=False)
-            return f.lastDeviceMs(), (dd, ii, cc), 0.0
-        out, ms, gather_ms = R.dist.knnShardedDevice(f, k, Q, dedup=False, device=dev, timed=True)
-        return ms + gather_ms, out, gather_ms
+    # synthetic inputs.  Small enough (or one GPU): the whole matrix in PINNED host memory on every rank (so the e2e H2D is a
+    # real DMA).  Large multi-GPU configurations: every rank generates and holds only the rows it uploads (rpf_set_points on
+    # a communicator rank reads rows [r*per, (r+1)*per) only); the e2e arm is then not run.
+    full_host = world == 1 or n * d * 8 <= 2.2e9
+    per = -(-n // world)
+    r0, r1 = (0, n) if full_host else (min(n, rank * per), min(n, (rank + 1) * per))
+    Xp = torch.empty((r1 - r0, d), dtype=torch.float64, pin_memory=full_host)
+    X = Xp.numpy()
+    make_rows(n, d, W["data_seed"], W["clusters"], W["sigma"], r0, r1, out=X)
+    Qp = torch.empty((nq, d), dtype=torch.float64, pin_memory=True)
+    Q = Qp.numpy()
+    make_rows(nq, d, W["query_seed"], W["clusters"], W["sigma"], out=Q)
+    hp_all = R.sampleHyperplanes(W["forest_seed"], T, maxd, W["pnz"], d)
+    hp = slice_hp(hp_all, maxd, t_first, t_local)
+
+    f = new_forest()
+    if full_host:
+        f.setPoints(X)                  # resident in HBM before the timed region (the `value` arm); N > 1: row-sharded upload + all-gather
+    else:
+        f.setPointsRaw(X.ctypes.data - r0 * d * 8, n, d)
+    kout = (torch.empty((nq, k), dtype=torch.float64, pin_memory=True).numpy(),
+            torch.empty((nq, k), dtype=torch.int32, pin_memory=True).numpy().view(np.uint32),
+            torch.empty((nq,), dtype=torch.int32, pin_memory=True).numpy())
+
+    def knn_step(forest):
+        """knn over the whole forest: local top-k on this rank's trees; N > 1: ONE packed NCCL all-gather over NVLink and the
+        merge kernel, all inside rpf_knn on the engine's stream.  Device ms from the engine's events around the whole call."""
+        forest.knnBatch(Q, k, dedup=False, out=kout)
+        return forest.lastDeviceMs()
 
     # ---- warm-up
     for _ in range(args.warmup):
         f.build(maxd, W["min_leaf"])
-        knn_step()
+        knn_step(f)
 
     # ---- timed: device-resident arm
     lc0 = f.launchCount()
@@ -227,8 +266,7 @@ def run_ours(args):
     for _ in range(args.steps):
         f.build(maxd, W["min_leaf"])
         b_ms.append(f.lastDeviceMs())
-        ms, merged, _ = knn_step()
-        q_ms.append(ms)
+        q_ms.append(knn_step(f))
     barrier()
     wall_ms = (time.perf_counter() - t_wall0) * 1e3 / args.steps
     clocks = cs.stop()
@@ -236,78 +274,75 @@ def run_ours(args):
     build_ms = allmax(float(np.mean(b_ms)))
     knn_ms = allmax(float(np.mean(q_ms)))
 
-    # ---- timed: e2e arm -- host (pinned) buffers through the public API; every step copies the points H2D, builds, and
-    # reads the forest back D2H; the query step copies the queries H2D and the results D2H (+ NCCL gather / merge)
-    e2e_b, e2e_q = [], []
-    g = R.RPForest(local_rank)
-    if os.environ.get("RPF_BOTTOM_CAP"):
-        g.setBottomCap(int(os.environ["RPF_BOTTOM_CAP"]))
-    g.setHyperplanes(hp, t_local, maxd)
-    nn = None
+    # ---- timed: e2e arm -- host (pinned) buffers through the public API; every step copies the points H2D (N > 1: 1/N of
+    # every row block per rank + NVLink all-gather, overlapped with the projection), builds, and streams the forest back D2H
+    # (export sink); the query step copies the queries H2D and the merged results D2H
+    e2e = None
+    nn = len(f.topology()["child"])
+    if full_host:
+        e2e_b, e2e_q = [], []
+        g = new_forest()
+        exp_bufs = {key: torch.empty((t_local, nn), dtype=torch.float64, pin_memory=True).numpy() for key in ("thr", "mlo", "mhi")}
+        exp_bufs["perm"] = torch.empty((t_local, n), dtype=torch.int32, pin_memory=True).numpy().view(np.uint32)
+        g.setExportSink(exp_bufs)                                # builds stream the forest into these buffers while they run
 
-    exp_bufs = {}
+        def e2e_build():
+            g.buildFromHost(X, maxd, W["min_leaf"])              # forestBatch from pinned host memory
+            return g.forestExport(exp_bufs)                      # waits for the streamed download (thr/mlo/mhi + perm of every local tree)
 
-    rp = R.dist.ReplicatedPoints(dev) if dist is not None else None
-
-    def e2e_build():
-        if dist is None:
-            g.buildFromHost(X, maxd, W["min_leaf"])              # forestBatch from pinned host memory: H2D n*d*8 (row blocks, overlapped
-                                                                 # with the projection kernel) + build
-        else:                                                    # N GPUs: each rank uploads n/N rows over its own PCIe link, NCCL
-            R.dist.buildFromHostSharded(g, rp, Xp, maxd, W["min_leaf"])   # all-gather over NVLink replicates them, then the build
-        if not exp_bufs:                                         # page-locked result buffers, allocated once (first warm-up)
-            nn_ = len(g.topology()["child"])
-            for key in ("thr", "mlo", "mhi"):
-                exp_bufs[key] = torch.empty((t_local, nn_), dtype=torch.float64, pin_memory=True).numpy()
-            exp_bufs["perm"] = torch.empty((t_local, n), dtype=torch.int32, pin_memory=True).numpy().view(np.uint32)
-            if dist is None:
-                g.setExportSink(exp_bufs)                        # later builds stream the forest into these buffers while they run
-        return g.forestExport(exp_bufs)                          # D2H: thr/mlo/mhi + perm of every local tree (streamed or one call)
-
-    def e2e_knn():
-        if dist is None:
-            g.knnBatch(Q, k)                                     # H2D queries, D2H results
-        else:                                                    # H2D queries; per-rank lists stay on the device, NCCL all-gather,
-            R.dist.knnShardedDevice(g, k, Q, dedup=False, device=dev)   # merge kernel; D2H of the merged nq x k result only
-
-    for _ in range(2):                                           # warm-up (workspace allocation)
-        e2e_build(); e2e_knn()
-    for _ in range(args.steps):
-        barrier()
-        t0 = time.perf_counter()
-        exp = e2e_build()
-        barrier()
-        e2e_b.append(time.perf_counter() - t0)
-        nn = exp["thr"].shape[1]
-        t0 = time.perf_counter()
-        e2e_knn()
-        barrier()
-        e2e_q.append(time.perf_counter() - t0)
-    g.close()
-    if rank == 0:
-        print("per-step build device ms: %s | e2e build s: %s | e2e knn s: %s" % (
-            [round(x, 3) for x in b_ms], [round(x, 4) for x in e2e_b], [round(x, 4) for x in e2e_q]), file=sys.stderr)
-    e2e_build_s = allmax(float(np.mean(e2e_b)))
-    e2e_knn_s = allmax(float(np.mean(e2e_q)))
+        for _ in range(2):                                       # warm-up (workspace allocation)
+            e2e_build(); knn_step(g)
+        for _ in range(args.steps):
+            barrier()
+            t0 = time.perf_counter()
+            e2e_build()
+            barrier()
+            e2e_b.append(time.perf_counter() - t0)
+            t0 = time.perf_counter()
+            knn_step(g)
+            barrier()
+            e2e_q.append(time.perf_counter() - t0)
+        g.close()
+        if rank == 0:
+            print("per-step build device ms: %s | e2e build s: %s | e2e knn s: %s" % (
+                [round(x, 3) for x in b_ms], [round(x, 4) for x in e2e_b], [round(x, 4) for x in e2e_q]), file=sys.stderr)
+        e2e_build_s = allmax(float(np.mean(e2e_b)))
+        e2e_knn_s = allmax(float(np.mean(e2e_q)))
+        e2e = {"value": n / e2e_build_s, "unit": "points/s",
+               "h2d_bytes_per_step": int(n * d * 8 + world * (len(hp[1]) * 12 + len(hp[0]) * 8)),     # all ranks together
+               "d2h_bytes_per_step": int(T * (nn * 24 + n * 4)), "build_s": e2e_build_s,
+               "upload": ("one H2D of the n x d points (row blocks overlapped with the projection)" if world == 1 else
+                          "row-sharded: 1/%d of every row block per rank over its own PCIe link + in-engine NCCL all-gather over NVLink, "
+                          "overlapped with the projection" % world),
+               "knn_queries_per_s": nq / e2e_knn_s, "knn_s": e2e_knn_s,
+               "knn_h2d_bytes": int(world * nq * d * 8), "knn_d2h_bytes": int(world * (nq * k * 12 + nq * 4))}
 
     # ---- per-kernel profile (separate pass: event pairs around every launch) -> roofline of the dominant kernel
     f.setProfiling(True)
     f.build(maxd, W["min_leaf"])
     prof = f.profile()
-    f.knnBatch(Q, k)
+    f.knnBatch(Q, k, out=kout)
     prof_q = f.profile()
     f.setProfiling(False)
-    for name in ("q_project", "q_traverse", "q_knn"):
-        prof[name] = prof_q[name]
-    off, _ = f.candidatesBatch(Q[:512], -1)
-    C_mean = float(off[-1]) / 512.0
+    for name in ("q_project", "q_traverse", "q_knn", "merge"):
+        if name in prof_q:
+            prof[name] = prof_q[name]
+    # candidates per query over the WHOLE forest (local trees of every rank added up): the re-rank's algorithmic bytes
+    qs = min(512, nq)
+    off, _ = f.candidatesBatch(Q[:qs], -1)
+    c_local = float(off[-1]) / qs
+    C_mean = c_local
+    if dist is not None:
+        t = torch.tensor([c_local], dtype=torch.float64, device=dev)
+        dist.all_reduce(t)
+        C_mean = float(t.item())
     tp = f.topology()
     L = int(tp["depth"][tp["child"] >= 0].max()) + 1
     cap = int(os.environ.get("RPF_BOTTOM_CAP", "1024"))      # engine default (rpf_set_bottom_cap)
     lvl_max = [int(tp["seg_size"][tp["depth"] == l].max()) for l in range(int(tp["depth"].max()) + 1)]
     s_top = next((l for l, m in enumerate(lvl_max) if m <= cap), len(lvl_max))
     s_top = min(s_top, L)
-    ab = algorithmic_bytes(W, t_local, L, s_top, C_mean)
+    ab = algorithmic_bytes(W, t_local, L, s_top, c_local)    # per-rank kernels: this rank's trees / candidates
     kern = {kname: v for kname, v in prof.items() if v[1] > 0 and kname in ab}
     traffic_tab = {}
     for tf in ("r02_traffic.json", "r01_traffic.json"):      # DRAM bytes per launch from the committed `ncu --set full` captures
@@ -317,6 +352,8 @@ def run_ours(args):
             break
         except Exception:
             pass
+    if args.config != "c2" or world != 1:
+        traffic_tab = {}                                     # the captures were taken on configs[1] at one GPU
 
     def kernel_roofline(kname):
         """Roofline record of one kernel class.  top_* entries of `ab` are bytes per level launch (every launch streams all
@@ -342,42 +379,34 @@ def run_ours(args):
     bk = {kname: v for kname, v in kern.items() if not kname.startswith("q_")}
     bdom = max(bk, key=lambda kname: bk[kname][0])
     roofline = kernel_roofline(bdom)
-    if bdom == "project":
-        roofline["note"] = "k_project is bound by the shared-memory pipe (z*n*T*L*8 B of LDS traffic), not by DRAM: DESIGN.md 4.1"
     roofline_knn_kernel = kernel_roofline("q_knn") if "q_knn" in kern else None
     roofline_build_kernels = {kname: kernel_roofline(kname) for kname in bk}
     build_bytes = 8 * d * n + t_local * L * n * 24
     knn_bytes = ab["q_knn"]
     phases = {kname: dict(ms=round(v[0], 3), launches=v[1]) for kname, v in prof.items() if v[1] > 0}
 
-    # ---- quality: recallWith (reference definition) and forest-level recall@10 on a query sample (untimed)
+    # ---- quality: recallWith (reference definition) and forest-level recall@k on a query sample (untimed)
     ns = 64
-    rs = f.recallSumBatch(Q[:ns], k)
-    if dist is not None:
-        t = torch.from_numpy(rs).to(dev)
-        dist.all_reduce(t)
-        rs = t.cpu().numpy()
-    recall_ref_def = float(np.mean(rs / T))
+    recall_ref_def = float(np.mean(f.recallSumBatch(Q[:ns], k) / T))       # N > 1: forest-wide sums, reduced inside the engine
     bd, bi = f.bruteKnnBatch(Q[:ns], k)
     pd_, pi_, pc_ = f.knnBatch(Q[:ns], k, dedup=True)
-    if dist is not None:
-        D, I, Cn = R.dist.gather_topk(pd_, pi_, pc_, device=dev)
-        pd_, pi_, pc_ = f.mergeTopk(D, I, Cn, dedup=True)
     forest_recall = float(np.mean([len(set(pi_[i, :pc_[i]].tolist()) & set(bi[i].tolist())) / k for i in range(ns)]))
 
     # ---- streaming build (`forest` with the rpTreeCfg chunk size, Conduit.hs:104-141): reported beside the batch build
-    chunk = cfg.fpDataChunkSize
-    t0 = time.perf_counter()
-    f.build(maxd, W["min_leaf"], chunk=chunk)                    # first call: plans the 100 chunks on the host
-    stream_first_ms = (time.perf_counter() - t0) * 1e3
-    s_ms = []
-    for _ in range(3):
-        f.build(maxd, W["min_leaf"], chunk=chunk)
-        s_ms.append(f.lastDeviceMs())
-    stream_ms = allmax(float(np.mean(s_ms)))
-    stream = {"chunk": int(chunk), "chunks": int(-(-n // chunk)), "device_ms": stream_ms, "points_per_s": n / (stream_ms * 1e-3),
-              "first_call_ms_incl_host_plan": stream_first_ms, "points_lost_by_reference_rule": f.pointsLost()}
-    f.build(maxd, W["min_leaf"])
+    stream = None
+    if args.config == "c2":
+        chunk = cfg.fpDataChunkSize
+        t0 = time.perf_counter()
+        f.build(maxd, W["min_leaf"], chunk=chunk)                    # first call: plans the 100 chunks on the host
+        stream_first_ms = (time.perf_counter() - t0) * 1e3
+        s_ms = []
+        for _ in range(3):
+            f.build(maxd, W["min_leaf"], chunk=chunk)
+            s_ms.append(f.lastDeviceMs())
+        stream_ms = allmax(float(np.mean(s_ms)))
+        stream = {"chunk": int(chunk), "chunks": int(-(-n // chunk)), "device_ms": stream_ms, "points_per_s": n / (stream_ms * 1e-3),
+                  "first_call_ms_incl_host_plan": stream_first_ms, "points_lost_by_reference_rule": f.pointsLost()}
+        f.build(maxd, W["min_leaf"])
 
     out = None
     if rank == 0:
@@ -387,16 +416,12 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": build_ms + knn_ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config_dict(W, maxd, world), "trees_per_gpu": t_local,
+            "multi_gpu": None if world == 1 else "rpf_comm_init_rank: NCCL communicator owned by the engine (C ABI); exchanges inside rpf_set_points / rpf_build_from_host / rpf_knn / rpf_recall",
             "build_ms": build_ms, "knn_ms": knn_ms, "knn_queries_per_s": nq / (knn_ms * 1e-3),
-            "recall_at_10_recallWith": recall_ref_def, "recall_at_10_forest": forest_recall, "recall_queries": ns,
+            "recall_at_k_recallWith": recall_ref_def, "recall_at_k_forest": forest_recall, "recall_queries": ns,
             "candidates_per_query": C_mean, "stream_build": stream,
-            "e2e": {"value": n / e2e_build_s, "unit": "points/s",
-                    "h2d_bytes_per_step": int(n * d * 8 + world * (len(hp[1]) * 12 + len(hp[0]) * 8)),     # all ranks together
-                    "d2h_bytes_per_step": int(world * t_local * (nn * 24 + n * 4)), "build_s": e2e_build_s,
-                    "upload": ("one H2D of the n x d points (row blocks overlapped with the projection)" if world == 1 else
-                               "row-sharded: n/%d rows per rank over its own PCIe link + NCCL all-gather over NVLink" % world),
-                    "knn_queries_per_s": nq / e2e_knn_s, "knn_s": e2e_knn_s,
-                    "knn_h2d_bytes": int(nq * d * 8), "knn_d2h_bytes": int(nq * k * 12 + nq * 4)},
+            "e2e": e2e if e2e is not None else {"value": None, "unit": "points/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
+                                                "note": "not measured: at this configuration every rank's host holds only the rows it uploads"},
             "gpu_launches": int(launches), "wall_ms_per_step": wall_ms,
             "roofline": roofline, "roofline_knn_kernel": roofline_knn_kernel, "roofline_build_kernels": roofline_build_kernels,
             "roofline_build": dict(bound="hbm", achieved=round(build_bytes / (build_ms * 1e-3) / 1e9, 1), peak=peak, unit="GB/s",
@@ -409,7 +434,7 @@ def run_ours(args):
             # CPU leg (rank 0, N=1 only): the oracle builds the whole forest on all host threads, answers a query sample, and
             # is the CHECKER of the GPU results on that sample (knn ids / distance bits, recallWith within 0.005)
             threads = min(os.cpu_count() or 1, T)
-            cb, (ores, orec) = cpu_baseline(X, Q, hp_all, W, maxd, threads, full_forest=True)
+            cb, (ores, orec) = cpu_baseline(X, Q, hp_all, W, maxd, threads, full_forest=True, nq_knn=args.cpu_queries)
             gd, gi, gc = f.knnBatch(Q[:len(ores)], k)
             for i, (od, oi) in enumerate(ores):
                 assert np.array_equal(gi[i, :gc[i]], oi) and np.array_equal(gd[i, :gc[i]].view(np.uint64), od.view(np.uint64)), \
@@ -421,6 +446,7 @@ def run_ours(args):
             assert cb["recall_abs_diff"] <= 0.005, "recallWith@%d differs from the oracle by %g" % (k, cb["recall_abs_diff"])
             out["cpu_baseline"] = cb
     barrier()
+    f.close()
     if dist is not None:
         dist.destroy_process_group()
     if out is not None:
@@ -487,7 +513,7 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle import orc
-    W = WORKLOAD
+    W = CONFIGS[args.config]
     n, d, T = W["n"], W["d"], W["ntrees"]
     maxd = orc.rptree_cfg(W["min_leaf"], n, d)[0]
     X = make_points(n, d, W["data_seed"], W["clusters"], W["sigma"])
@@ -499,7 +525,7 @@ def run_reference(args):
         cb, _ = cpu_baseline(X, Q, hp_all, W, maxd, threads, full_forest=False)
         if i >= args.warmup:
             vals.append(cb)
-    full, _ = cpu_baseline(X, Q, hp_all, W, maxd, threads, full_forest=True)   # untimed for `value`: whole forest once + the query legs
+    full, _ = cpu_baseline(X, Q, hp_all, W, maxd, threads, full_forest=True, nq_knn=args.cpu_queries)   # untimed for `value`: whole forest once + the query legs
     v = float(np.mean([c["value"] for c in vals]))
     cb = dict(full)
     cb.update({"value": v, "seconds": float(np.mean([c["seconds"] for c in vals])), "full_forest_points_per_s": full["value"],
@@ -511,7 +537,7 @@ def run_reference(args):
            "steps": len(vals), "warmup": args.warmup, "ms_per_step": float(np.mean([c["seconds"] for c in vals])) * 1e3,
            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": config_dict(W, maxd, args.gpus),
-           "knn_queries_per_s": full["knn_queries_per_s"], "recall_at_10_recallWith": full["recall_oracle"],
+           "knn_queries_per_s": full["knn_queries_per_s"], "recall_at_k_recallWith": full["recall_oracle"],
            "cpu_baseline": cb,
            "e2e": {"value": v, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "note": "reference = C port of the Haskell algorithm (no GHC toolchain in this image), trees spread over all host threads "
@@ -525,7 +551,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS), help="BASELINE.json configuration (c2 = configs[1], the headline)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-queries", type=int, default=10000, help="queries answered by the CPU knn leg (and checked against the GPU)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

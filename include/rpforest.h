@@ -37,12 +37,40 @@ typedef enum {
 } rpf_status;
 
 /* ---- lifecycle ---------------------------------------------------------------------------------- */
-/* Creates an engine bound to CUDA device `device` (owns a stream and all device buffers). */
+/* Creates an engine bound to CUDA device `device` (owns a stream and all device buffers).  Replaces nothing in the
+ * reference (pure values, GC-owned); the handle is what the shim's RPForest value wraps. */
 int  rpf_create(rpf_handle** out, int device);
 void rpf_destroy(rpf_handle* h);
 const char* rpf_last_error(const rpf_handle* h);
 /* ABI version of this header. */
 int  rpf_abi_version(void);
+
+/* ---- multi-GPU: trees sharded in contiguous blocks over W GPUs, data replicated ---------------------
+ * createMulti maps over the IntMap of trees (Internal.hs:234-240), knn folds per-tree candidates in ascending tree order
+ * (RPTree.hs:174-176), recallWith is a mean over trees (RPTree.hs:265-268): trees are independent, so GPU r builds and
+ * queries trees [t0_r, t0_r + T_r) and the results equal the single-GPU results bit for bit.  The handle owns one NCCL
+ * communicator per GPU (libnccl.so.2 is loaded on first use); all exchanges run inside the engine on its own streams:
+ *   points  -- every GPU uploads 1/W of each row block over its own PCIe link, NVLink all-gather, projection overlapped;
+ *   knn     -- per-GPU top-k lists -> ONE packed all-gather -> merge kernel ((distance, GPU, position) = tree order);
+ *   recall  -- brute-force truth sharded by query, all-gather, per-GPU hit sums added in GPU (= tree) order.
+ *
+ * (1) ONE process, n GPUs (what a Haskell host uses): rpf_create_multi.  The returned handle is accepted by every entry
+ *     point of this header with the single-GPU meaning: rpf_set_hyperplanes takes the WHOLE forest and shards it,
+ *     rpf_tree_export(t) takes the forest-wide tree index, rpf_forest_export fills [T][..] arrays in tree order, rpf_knn /
+ *     rpf_recall return forest-wide results (recall_sum = sum over ALL trees).  One host thread per GPU issues the work.
+ *     Not available on such a handle: rpf_set_points_device, rpf_knn_h, rpf_knn_dev / rpf_merge_topk(_dev);
+ *     rpf_forest_save / _load write / read one file per GPU (path + ".gpu<r>of<n>").  n_gpus == 1 == rpf_create.
+ * (2) one process per GPU (SPMD, e.g. torchrun): every process creates its own handle with rpf_create, then joins with
+ *     rpf_comm_init_rank BEFORE setting points (id: 128 bytes from rpf_comm_unique_id on one rank, distributed by the
+ *     caller).  Each rank passes only ITS trees to rpf_set_hyperplanes (contiguous blocks in rank order) and ALL ranks
+ *     call rpf_set_points / rpf_build_from_host / rpf_knn / rpf_recall collectively with the same arguments; every rank
+ *     receives the forest-wide knn / recall result.  rpf_set_points reads only rows [r*per, (r+1)*per), per = ceil(n/W),
+ *     of X on rank r (the other rows need not be valid memory); rpf_build_from_host reads 1/W of every row block. */
+int rpf_create_multi(rpf_handle** out, const int* gpu_ids, int n_gpus);
+int rpf_comm_unique_id(void* id128);
+int rpf_comm_init_rank(rpf_handle* h, int32_t world, int32_t rank, const void* id128);
+/* GPUs behind this handle: n of rpf_create_multi, world of rpf_comm_init_rank, else 1. */
+int rpf_num_gpus(const rpf_handle* h);
 
 /* ---- data: V.Vector (Embed DVector Double x)  (src/Data/RPTree/Internal.hs:56-63,122-126) -------- */
 /* X: n x d row-major doubles (one DVector per row).  Copied to the device; caller keeps ownership. */
@@ -169,7 +197,7 @@ int rpf_knn_h(rpf_handle* h, const double* Q, const int32_t* q_last, int64_t nq,
 /* recallWith metricL2 forest k q (RPTree.hs:259-282): mean over this handle's trees of
  * |candidates(t,q) /\ true-top-k| / k.  recall_sum[q] = SUM over local trees (divide by the global
  * tree count after reducing across GPUs). */
-int rpf_recall(rpf_handle* h, const double* Q, int64_t nq, int32_t k, double* recall_sum);
+int rpf_recall(rpf_handle* h, const double* Q, int64_t nq, int32_t k, double* recall_sum);   /* multi-GPU handle / communicator rank: sum over ALL trees */
 /* Exact brute-force k nearest rows (ties by row id): ground truth for forest-level recall. */
 int rpf_brute_knn(rpf_handle* h, const double* Q, int64_t nq, int32_t k, double* dist, uint32_t* ids);
 

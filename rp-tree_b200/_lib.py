@@ -19,6 +19,10 @@ H = C.c_void_p
 # name -> (restype, argtypes); mirrors include/rpforest.h one to one
 SIGNATURES = {
     "rpf_create": (C.c_int, [C.POINTER(H), C.c_int]),
+    "rpf_create_multi": (C.c_int, [C.POINTER(H), i32p, C.c_int]),
+    "rpf_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "rpf_comm_init_rank": (C.c_int, [H, C.c_int32, C.c_int32, C.c_void_p]),
+    "rpf_num_gpus": (C.c_int, [H]),
     "rpf_destroy": (None, [H]),
     "rpf_last_error": (C.c_char_p, [H]),
     "rpf_abi_version": (C.c_int, []),

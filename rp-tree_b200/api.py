@@ -142,13 +142,24 @@ class RPForest:
     Wraps one `rpf_handle`.  `t_first` is the global index of this shard's first tree (multi-GPU sharding).
     """
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, devices=None):
+        """device: one CUDA device (rpf_create).  devices=[g0, g1, ...]: ONE handle over several GPUs of this process
+        (rpf_create_multi): trees sharded in contiguous blocks, data replicated, NCCL exchanges inside the engine -- every
+        method below keeps its single-GPU meaning."""
         self._L = lib()
         self._h = H()
-        rc = self._L.rpf_create(C.byref(self._h), device)
+        if devices is not None and len(devices) > 1:
+            ids = np.ascontiguousarray(devices, np.int32)
+            rc = self._L.rpf_create_multi(C.byref(self._h), _p(ids, i32p), len(ids))
+            device = int(ids[0])
+        else:
+            if devices is not None:
+                device = int(devices[0])
+            rc = self._L.rpf_create(C.byref(self._h), device)
         if rc != 0:
             self._h = None
-            raise RPForestError("rpf_create failed (rc=%d): no usable CUDA device %d -- the engine has no CPU fallback" % (rc, device))
+            raise RPForestError("rpf_create failed (rc=%d): no usable CUDA device %r -- the engine has no CPU fallback" % (
+                rc, devices if devices is not None else device))
         self.device = device
         self.n = 0; self.d = 0; self.ntrees = 0; self.maxDepth = 0; self.minLeaf = 0
         self.t_first = 0; self.ntrees_total = 0
@@ -170,22 +181,50 @@ class RPForest:
         except Exception:
             pass
 
+    # -- multi-GPU
+    @staticmethod
+    def commUniqueId():
+        """128-byte NCCL id (rpf_comm_unique_id): create on one rank, hand to every rank's commInitRank."""
+        buf = C.create_string_buffer(128)
+        rc = lib().rpf_comm_unique_id(buf)
+        if rc != 0:
+            raise RPForestError("rpf_comm_unique_id failed (rc=%d): NCCL not available" % rc)
+        return buf.raw
+
+    def commInitRank(self, world, rank, uid):
+        """One process per GPU: make this handle rank `rank` of a `world`-rank tree-sharded forest (before setPoints).
+        From then on setPoints / buildFromHost / knnBatch / recallSumBatch are collective and forest-wide."""
+        buf = C.create_string_buffer(bytes(uid), 128)
+        self._ck(self._L.rpf_comm_init_rank(self._h, world, rank, buf), "rpf_comm_init_rank")
+
+    def numGpus(self):
+        return int(self._L.rpf_num_gpus(self._h))
+
     # -- build
     def setPoints(self, X):
         X = np.ascontiguousarray(X, dtype=np.float64)
         if X.ndim != 2:
             raise ValueError("X must be n x d")
+        self._borrowed_points = None          # dist.buildFromHostSharded's cache: the handle owns its points again
         self._ck(self._L.rpf_set_points(self._h, _p(X, f64p), X.shape[0], X.shape[1]), "rpf_set_points")
         self.n, self.d = X.shape
 
     def setPointsSparse(self, rows):
         """Data points as SVectors (Embed SVector Double x): rows is a SparseRows."""
+        self._borrowed_points = None
         self._ck(self._L.rpf_set_points_sparse(self._h, rows.n, rows.d, _p(rows.off, i64p), _p(rows.idx, i32p), _p(rows.val, f64p)),
                  "rpf_set_points_sparse")
         self.n, self.d = rows.n, rows.d
 
     def pointsAreSparse(self):
         return bool(self._L.rpf_points_are_sparse(self._h))
+
+    def setPointsRaw(self, addr, n, d):
+        """rpf_set_points with a raw host address for row 0 (rank of a communicator: only this rank's rows
+        [r*per, (r+1)*per), per = ceil(n/world), are read, so `addr` may be a virtual base whose other rows are unmapped)."""
+        self._borrowed_points = None
+        self._ck(self._L.rpf_set_points(self._h, C.cast(C.c_void_p(addr), f64p), n, d), "rpf_set_points")
+        self.n, self.d = n, d
 
     def setPointsDevice(self, ptr, n, d):
         self._ck(self._L.rpf_set_points_device(self._h, C.c_void_p(ptr), n, d), "rpf_set_points_device")
@@ -218,6 +257,7 @@ class RPForest:
         X = np.ascontiguousarray(X, dtype=np.float64)
         if X.ndim != 2:
             raise ValueError("X must be n x d")
+        self._borrowed_points = None
         self._ck(self._L.rpf_build_from_host(self._h, _p(X, f64p), X.shape[0], X.shape[1], maxd, minl), "rpf_build_from_host")
         self.n, self.d = X.shape
         self.maxDepth, self.minLeaf = maxd, minl
@@ -284,6 +324,7 @@ class RPForest:
 
     def load(self, path):
         """Restore a checkpoint into this handle (counterpart of deserialiseRPForest, Internal.hs:192-196)."""
+        self._borrowed_points = None
         self._ck(self._L.rpf_forest_load(self._h, str(path).encode()), "rpf_forest_load")
         self._topo = None
         self.ntrees = int(self._L.rpf_num_trees(self._h))
@@ -312,10 +353,17 @@ class RPForest:
         self._ck(self._L.rpf_candidates(self._h, _p(Q, f64p), nq, t, _p(off, i64p), _p(ids, u32p)), "rpf_candidates")
         return off, ids[: off[-1]]
 
-    def knnBatch(self, Q, k, dedup=False):
+    def knnBatch(self, Q, k, dedup=False, out=None):
+        """knn / knnPQ for a batch: (dist nq x k, ids nq x k, count nq).  `out` may hold preallocated (ideally page-locked)
+        arrays of those shapes.  On a multi-GPU handle / communicator rank the result covers the whole forest."""
         Q, _, ql = _as_q(Q, self.d)
         nq = Q.shape[0]
-        dist = np.zeros((nq, k)); ids = np.zeros((nq, k), np.uint32); cnt = np.zeros(nq, np.int32)
+        if out is None:
+            dist = np.zeros((nq, k)); ids = np.zeros((nq, k), np.uint32); cnt = np.zeros(nq, np.int32)
+        else:
+            dist, ids, cnt = out
+            assert dist.shape == (nq, k) and dist.dtype == np.float64 and ids.shape == (nq, k) and ids.dtype == np.uint32
+            assert cnt.shape == (nq,) and cnt.dtype == np.int32
         if ql is None:
             self._ck(self._L.rpf_knn(self._h, _p(Q, f64p), nq, k, int(dedup), _p(dist, f64p), _p(ids, u32p), _p(cnt, i32p)), "rpf_knn")
         else:

@@ -2274,6 +2274,24 @@ static int get_batch_plan(rpf_handle* h, int L, BatchPlan** out) {
     return RPF_OK;
 }
 
+// Rows [r0, r0 + nr) of the host matrix -> dX on `stream`.  Single GPU: one H2D copy.  Rank R of a W-rank tree-sharded
+// forest (data replicated): this rank copies only ITS 1/W sub-block over its own PCIe link and the sub-blocks are
+// all-gathered in place over NCCL / NVLink (the last sub-block may spill past row r0 + nr: dX carries x_pad_rows spare rows,
+// and a later block overwrites its own range afterwards on the same stream).
+int rpf_upload_rows(rpf_handle* h, const double* hostX, int64_t r0, int64_t nr, cudaStream_t stream) {
+    const int W = rpf_comm_world(h), R = rpf_comm_rank(h);
+    const size_t rb = (size_t)h->d * 8;
+    if (W <= 1) {
+        RPF_CUDA(h, cudaMemcpyAsync((void*)(h->dX + r0 * h->d), hostX + r0 * h->d, (size_t)nr * rb, cudaMemcpyHostToDevice, stream));
+        return RPF_OK;
+    }
+    const int64_t sub = (nr + W - 1) / W;
+    if (h->x_pad_rows < W) return rpf_fail(h, RPF_ERR_STATE, "upload_rows: point buffer has no all-gather padding");
+    const int64_t a = std::min(nr, R * sub), b = std::min(nr, a + sub);
+    if (b > a) RPF_CUDA(h, cudaMemcpyAsync((void*)(h->dX + (r0 + a) * h->d), hostX + (r0 + a) * h->d, (size_t)(b - a) * rb, cudaMemcpyHostToDevice, stream));
+    return rpf_comm_allgather(h, (void*)(h->dX + r0 * h->d), (size_t)sub * rb, stream);
+}
+
 // forestBatch: the whole data set is one chunk (Batch.hs:48-63).  hostX != NULL: the points still live in host memory
 // (h->dX is allocated but empty): they are uploaded in row blocks on a second stream while the projection kernel
 // already runs on the blocks that have arrived (the rest of the build needs all keys and follows on the engine's stream).
@@ -2337,8 +2355,10 @@ int rpf_build_impl(rpf_handle* h, const double* hostX) {
         RPF_CUDA(h, cudaMemsetAsync(h->d_thr, 0, h->res_node_bytes, h->stream));
         RPF_CUDA(h, cudaMemsetAsync(h->d_mlo, 0, h->res_node_bytes, h->stream));
         RPF_CUDA(h, cudaMemsetAsync(h->d_mhi, 0, h->res_node_bytes, h->stream));
-        if (hostX && !pipelined && n > 0)      // several tree groups (or nothing to project): plain upload first
-            RPF_CUDA(h, cudaMemcpyAsync((void*)h->dX, hostX, (size_t)n * h->d * 8, cudaMemcpyHostToDevice, h->stream));
+        if (hostX && !pipelined && n > 0) {    // several tree groups (or nothing to project): plain upload first
+            int rcu = rpf_upload_rows(h, hostX, 0, n, h->stream);
+            if (rcu) return rcu;
+        }
         for (int t0 = 0; t0 < T; t0 += Tg) {
             const int tg = std::min(Tg, T - t0);
             if (L > 0 && n > 0) {   // K1
@@ -2356,7 +2376,8 @@ int rpf_build_impl(rpf_handle* h, const double* hostX) {
                     int bi = 0;
                     for (int64_t r0 = 0; r0 < n; r0 += rows, ++bi) {
                         const int64_t nr = std::min(rows, n - r0);
-                        RPF_CUDA(h, cudaMemcpyAsync((void*)(h->dX + r0 * h->d), hostX + r0 * h->d, (size_t)nr * h->d * 8, cudaMemcpyHostToDevice, h->copy_stream));
+                        int rcu = rpf_upload_rows(h, hostX, r0, nr, h->copy_stream);   // rank of a sharded forest: 1/W of the block over PCIe + NVLink all-gather
+                        if (rcu) return rcu;
                         RPF_CUDA(h, cudaEventRecord(h->copy_ev[bi], h->copy_stream));
                         RPF_CUDA(h, cudaStreamWaitEvent(h->stream, h->copy_ev[bi], 0));
                         int rc2 = rpf_project_launch(h, PH_PROJECT, h->dX + r0 * h->d, nr, t0, tg, L, true, keys + r0, n, kmin, kmax);

@@ -250,6 +250,27 @@ static int upload_hyperplanes(rpf_handle* h) {
 
 #define RPF_SETDEV(h) RPF_CUDA(h, cudaSetDevice((h)->device))
 
+// group parent (rpf_create_multi, multi.cu): every entry point forwards to the per-GPU sub-handles
+int rpfg_set_hyperplanes(rpf_handle* h, int32_t T, int32_t maxDepth, const int64_t* off, const int32_t* idx, const double* val);
+int rpfg_after_gen_hyperplanes(rpf_handle* h);
+int rpfg_set_points(rpf_handle* h, const double* X, int64_t n, int32_t d);
+int rpfg_set_points_sparse(rpf_handle* h, int64_t n, int32_t d, const int64_t* off, const int32_t* idx, const double* val);
+int rpfg_build(rpf_handle* h, int32_t maxDepth, int32_t minLeaf, int64_t chunk);
+int rpfg_build_from_host(rpf_handle* h, const double* X, int64_t n, int32_t d, int32_t maxDepth, int32_t minLeaf);
+int rpfg_tree_export(rpf_handle* h, int32_t t, double* thr, double* mlo, double* mhi, uint32_t* perm);
+int rpfg_forest_export(rpf_handle* h, double* thr, double* mlo, double* mhi, uint32_t* perm);
+int rpfg_set_export_sink(rpf_handle* h, double* thr, double* mlo, double* mhi, uint32_t* perm);
+int rpfg_knn(rpf_handle* h, const double* Q, const int32_t* q_last, int64_t nq, int32_t k, int32_t dedup, double* dist, uint32_t* ids, int32_t* count);
+int rpfg_recall(rpf_handle* h, const double* Q, const int32_t* q_last, int64_t nq, int32_t k, double* recall_sum);
+int rpfg_brute_knn(rpf_handle* h, const double* Q, const int32_t* q_last, int64_t nq, int32_t k, double* dist, uint32_t* ids);
+int rpfg_candidates(rpf_handle* h, const double* Q, int64_t nq, int32_t t, int64_t* off_out, const int64_t* off_in, uint32_t* ids);
+int rpfg_forest_save(rpf_handle* h, const char* path, int32_t with_points);
+int rpfg_forest_load(rpf_handle* h, const char* path);
+int rpfg_set_option(rpf_handle* h, const char* name, int64_t value, bool is_cap);
+int rpfg_set_profiling(rpf_handle* h, int on);
+int rpfg_get_profile(const rpf_handle* h, double* ms, int64_t* launches, int cap);
+int64_t rpfg_launch_count(const rpf_handle* h);
+
 // device copies of h->topo (start, size, child, depth per BFS node)
 int rpf_upload_topology(rpf_handle* h) {
     const Topology& tp = h->topo;
@@ -317,6 +338,7 @@ int rpf_create(rpf_handle** out, int device) {
 
 void rpf_destroy(rpf_handle* h) {
     if (!h) return;
+    if (h->group) { rpf_group_free(h); delete h; return; }
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     if (h->ownX && h->dX) cudaFree((void*)h->dX);
@@ -335,6 +357,7 @@ void rpf_destroy(rpf_handle* h) {
     if (h->ev_begin) cudaEventDestroy(h->ev_begin);
     if (h->ev_end) cudaEventDestroy(h->ev_end);
     cudaStreamDestroy(h->stream);
+    rpf_comm_free(h);
     delete h;
 }
 
@@ -344,11 +367,13 @@ int rpf_set_points(rpf_handle* h, const double* X, int64_t n, int32_t d) {
     if (!h) return RPF_ERR_ARG;
     if (n < 0 || d < 1 || (n > 0 && !X)) return rpf_fail(h, RPF_ERR_ARG, "set_points: bad n/d/X");
     if (n >= (int64_t)1 << 31) return rpf_fail(h, RPF_ERR_UNSUPPORTED, "set_points: n must be < 2^31");
+    if (h->group) return rpfg_set_points(h, X, n, d);
     RPF_SETDEV(h);
     ++h->cfg_epoch;
     if (h->d_xlast) { cudaFree(h->d_xlast); h->d_xlast = nullptr; }
     double* p = nullptr;
-    const size_t bytes = std::max<size_t>((size_t)n * d * 8, 16);
+    const int64_t pad = rpf_comm_world(h) > 1 ? rpf_comm_world(h) : 0;      // spill rows of the in-place all-gather
+    const size_t bytes = std::max<size_t>((size_t)(n + pad) * d * 8, 16);
     if (h->ownX && h->dX && h->x_bytes == bytes) {
         p = (double*)h->dX;                       // same footprint: reuse the device buffer
         h->built = false; h->sink_pending = false;
@@ -359,9 +384,15 @@ int rpf_set_points(rpf_handle* h, const double* X, int64_t n, int32_t d) {
         RPF_CUDA(h, cudaMalloc(&p, bytes));
         h->x_bytes = bytes;
     }
-    if (n > 0) RPF_CUDA(h, cudaMemcpyAsync(p, X, (size_t)n * d * 8, cudaMemcpyHostToDevice, h->stream));
-    RPF_CUDA(h, cudaStreamSynchronize(h->stream));
-    h->dX = p; h->ownX = true; h->n = n; h->d = d;
+    h->dX = p; h->ownX = true; h->n = n; h->d = d; h->x_pad_rows = pad;
+    // rank of a tree-sharded forest: only rows [rank * per, (rank + 1) * per), per = ceil(n / world), are read from X; the
+    // rest arrives over NVLink (rpf_upload_rows)
+    int rcu = n > 0 ? rpf_upload_rows(h, X, 0, n, h->stream) : RPF_OK;
+    if (!rcu && cudaStreamSynchronize(h->stream) != cudaSuccess) rcu = rpf_fail(h, RPF_ERR_CUDA, std::string("set_points: ") + cudaGetErrorString(cudaGetLastError()));
+    if (rcu) {           // no half-filled buffer is left behind
+        cudaFree(p); h->dX = nullptr; h->ownX = false; h->n = 0; h->x_bytes = 0;
+        return rcu;
+    }
     return RPF_OK;
 }
 
@@ -369,12 +400,13 @@ int rpf_set_points_device(rpf_handle* h, const double* X_dev, int64_t n, int32_t
     if (!h) return RPF_ERR_ARG;
     if (n < 0 || d < 1 || (n > 0 && !X_dev)) return rpf_fail(h, RPF_ERR_ARG, "set_points_device: bad n/d/X");
     if (n >= (int64_t)1 << 31) return rpf_fail(h, RPF_ERR_UNSUPPORTED, "set_points_device: n must be < 2^31");
+    if (h->group) return rpf_fail(h, RPF_ERR_UNSUPPORTED, "set_points_device: a multi-GPU handle replicates the points itself (rpf_set_points)");
     RPF_SETDEV(h);
     ++h->cfg_epoch;
     if (h->d_xlast) { cudaFree(h->d_xlast); h->d_xlast = nullptr; }
     if (h->ownX && h->dX) cudaFree((void*)h->dX);
     free_forest_dev(h);
-    h->dX = X_dev; h->ownX = false; h->n = n; h->d = d;
+    h->dX = X_dev; h->ownX = false; h->n = n; h->d = d; h->x_pad_rows = 0;
     return RPF_OK;
 }
 
@@ -406,6 +438,7 @@ int rpf_set_points_sparse(rpf_handle* h, int64_t n, int32_t d, const int64_t* of
     if (n >= (int64_t)1 << 31) return rpf_fail(h, RPF_ERR_UNSUPPORTED, "set_points_sparse: n must be < 2^31");
     int rc = check_csr_rows(h, n, d, off, idx, "set_points_sparse");
     if (rc) return rc;
+    if (h->group) return rpfg_set_points_sparse(h, n, d, off, idx, val);
     RPF_SETDEV(h);
     ++h->cfg_epoch;
     if (h->d_xlast) { cudaFree(h->d_xlast); h->d_xlast = nullptr; }
@@ -438,7 +471,7 @@ int rpf_set_points_sparse(rpf_handle* h, int64_t n, int32_t d, const int64_t* of
         if (xl) cudaFree(xl);
         return rpf_fail(h, e == cudaErrorMemoryAllocation ? RPF_ERR_NOMEM : RPF_ERR_CUDA, std::string("set_points_sparse: ") + cudaGetErrorString(e));
     }
-    h->dX = X; h->ownX = true; h->x_bytes = bytes; h->n = n; h->d = d; h->d_xlast = xl;
+    h->dX = X; h->ownX = true; h->x_bytes = bytes; h->n = n; h->d = d; h->d_xlast = xl; h->x_pad_rows = 0;
     return RPF_OK;
 }
 
@@ -461,12 +494,13 @@ int rpf_densify_rows(int64_t nq, int32_t d, const int64_t* off, const int32_t* i
 int rpf_set_hyperplanes(rpf_handle* h, int32_t T, int32_t maxDepth, const int64_t* off, const int32_t* idx, const double* val) {
     if (!h) return RPF_ERR_ARG;
     if (T < 1 || maxDepth < 0 || !off) return rpf_fail(h, RPF_ERR_ARG, "set_hyperplanes: bad T/maxDepth/off");
-    RPF_SETDEV(h);
+    if (!h->group) RPF_SETDEV(h);
     const int64_t nrow = (int64_t)T * maxDepth;
     const int64_t nnz = off[nrow];
     if (off[0] != 0 || nnz < 0 || (nnz > 0 && (!idx || !val))) return rpf_fail(h, RPF_ERR_ARG, "set_hyperplanes: bad CSR");
     for (int64_t r = 0; r < nrow; ++r) if (off[r + 1] < off[r]) return rpf_fail(h, RPF_ERR_ARG, "set_hyperplanes: offsets not monotone");
     if (h->d > 0) for (int64_t q = 0; q < nnz; ++q) if (idx[q] < 0 || idx[q] >= h->d) return rpf_fail(h, RPF_ERR_ARG, "set_hyperplanes: component index out of range");
+    if (h->group) return rpfg_set_hyperplanes(h, T, maxDepth, off, idx, val);
     h->T = T; h->hpDepth = maxDepth;
     h->hp_off.assign(off, off + nrow + 1);
     h->hp_idx.assign(idx, idx + nnz);
@@ -479,7 +513,7 @@ int rpf_gen_hyperplanes(rpf_handle* h, uint64_t seed, int32_t T_total, int32_t m
     if (!h) return RPF_ERR_ARG;
     if (T_total < 1 || maxDepth < 0 || d < 1 || t_first < 0 || T_local < 1 || t_first + T_local > T_total)
         return rpf_fail(h, RPF_ERR_ARG, "gen_hyperplanes: bad arguments");
-    RPF_SETDEV(h);
+    if (!h->group) RPF_SETDEV(h);
     // One sequential generator for the whole forest: tree-major, level-major, component-minor; per component
     // one uniform (bernoulli p = u < p) and, on a hit, one more for the normal (Gen.hs:183-195).
     SMGen g = mk_smgen(seed);
@@ -499,6 +533,7 @@ int rpf_gen_hyperplanes(rpf_handle* h, uint64_t seed, int32_t T_total, int32_t m
     }
     h->hp_off.push_back((int64_t)h->hp_idx.size());
     h->T = T_local; h->hpDepth = maxDepth;
+    if (h->group) return rpfg_after_gen_hyperplanes(h);
     return upload_hyperplanes(h);
 }
 
@@ -572,6 +607,7 @@ static int check_build_args(rpf_handle* h, int32_t maxDepth, int32_t minLeaf) {
 
 int rpf_build(rpf_handle* h, int32_t maxDepth, int32_t minLeaf) {
     if (!h) return RPF_ERR_ARG;
+    if (h->group) return rpfg_build(h, maxDepth, minLeaf, 0);
     int rc = check_build_args(h, maxDepth, minLeaf);
     if (rc) return rc;
     RPF_SETDEV(h);
@@ -597,19 +633,28 @@ int rpf_build_from_host(rpf_handle* h, const double* X, int64_t n, int32_t d, in
     if (!h) return RPF_ERR_ARG;
     if (n < 0 || d < 1 || (n > 0 && !X)) return rpf_fail(h, RPF_ERR_ARG, "build_from_host: bad n/d/X");
     if (n >= (int64_t)1 << 31) return rpf_fail(h, RPF_ERR_UNSUPPORTED, "build_from_host: n must be < 2^31");
+    if (h->group) return rpfg_build_from_host(h, X, n, d, maxDepth, minLeaf);
+    // validate against the NEW shape before the handle's state is touched
+    if (h->T < 1) return rpf_fail(h, RPF_ERR_STATE, "build: call rpf_set_hyperplanes / rpf_gen_hyperplanes first");
+    if (maxDepth < 0 || minLeaf < 0) return rpf_fail(h, RPF_ERR_ARG, "build: maxDepth and minLeaf must be >= 0");
+    if (maxDepth > h->hpDepth) return rpf_fail(h, RPF_ERR_ARG, "build: maxDepth exceeds the number of hyperplanes per tree");
+    if (maxDepth > 62) return rpf_fail(h, RPF_ERR_UNSUPPORTED, "build: maxDepth > 62");
+    for (int32_t q : h->hp_idx) if (q < 0 || q >= d) return rpf_fail(h, RPF_ERR_ARG, "build: hyperplane component index out of range");
     RPF_SETDEV(h);
     ++h->cfg_epoch;
     if (h->d_xlast) { cudaFree(h->d_xlast); h->d_xlast = nullptr; }
-    const size_t bytes = std::max<size_t>((size_t)n * d * 8, 16);
+    const int64_t pad = rpf_comm_world(h) > 1 ? rpf_comm_world(h) : 0;      // spill rows of the in-place all-gather
+    const size_t bytes = std::max<size_t>((size_t)(n + pad) * d * 8, 16);
+    h->built = false; h->sink_pending = false;
     if (!(h->ownX && h->dX && h->x_bytes == bytes)) {
         if (h->ownX && h->dX) cudaFree((void*)h->dX);
-        h->dX = nullptr; h->ownX = false;
+        h->dX = nullptr; h->ownX = false; h->n = 0; h->x_bytes = 0;     // "no points" until the new buffer exists
         free_forest_dev(h);
         double* p = nullptr;
         RPF_CUDA(h, cudaMalloc(&p, bytes));
         h->dX = p; h->ownX = true; h->x_bytes = bytes;
     }
-    h->n = n; h->d = d; h->built = false; h->sink_pending = false;
+    h->n = n; h->d = d; h->x_pad_rows = pad;
     int rc = check_build_args(h, maxDepth, minLeaf);
     if (rc) return rc;
     if (!(h->topo_key_n == h->n && h->topo_key_maxd == maxDepth && h->topo_key_minl == minLeaf)) {
@@ -622,8 +667,11 @@ int rpf_build_from_host(rpf_handle* h, const double* X, int64_t n, int32_t d, in
     h->call_begin();
     rc = rpf_build_impl(h, X);
     int rc2 = h->call_end();
-    if (rc) return rc;
-    if (rc2) return rc2;
+    if (rc || rc2) {     // the buffer may hold a partial upload: a later rpf_build must not run on it
+        if (h->ownX && h->dX) cudaFree((void*)h->dX);
+        h->dX = nullptr; h->ownX = false; h->n = 0; h->x_bytes = 0;
+        return rc ? rc : rc2;
+    }
     h->built = true;
     return RPF_OK;
 }
@@ -631,6 +679,7 @@ int rpf_build_from_host(rpf_handle* h, const double* X, int64_t n, int32_t d, in
 int rpf_build_chunked(rpf_handle* h, int32_t maxDepth, int32_t minLeaf, int64_t chunk) {
     if (!h) return RPF_ERR_ARG;
     if (chunk < 1) return rpf_fail(h, RPF_ERR_ARG, "build_chunked: chunk must be >= 1");
+    if (h->group) return rpfg_build(h, maxDepth, minLeaf, chunk);
     if (chunk >= h->n) return rpf_build(h, maxDepth, minLeaf);   // one chunk == insert into an empty Tip == forestBatch
     int rc = check_build_args(h, maxDepth, minLeaf);
     if (rc) return rc;
@@ -654,6 +703,7 @@ int rpf_build_chunked(rpf_handle* h, int32_t maxDepth, int32_t minLeaf, int64_t 
 int rpf_forest_save(rpf_handle* h, const char* path, int32_t with_points) {
     if (!h || !path) return RPF_ERR_ARG;
     if (!h->built) return rpf_fail(h, RPF_ERR_STATE, "forest_save: forest not built");
+    if (h->group) return rpfg_forest_save(h, path, with_points);
     RPF_SETDEV(h);
     RPF_CUDA(h, cudaStreamSynchronize(h->stream));
     FILE* f = fopen(path, "wb");
@@ -808,6 +858,7 @@ static int forest_load_impl(rpf_handle* h, const char* path) {
 
 int rpf_forest_load(rpf_handle* h, const char* path) {
     if (!h || !path) return RPF_ERR_ARG;
+    if (h->group) return rpfg_forest_load(h, path);
     RPF_SETDEV(h);
     RPF_CUDA(h, cudaStreamSynchronize(h->stream));
     try {
@@ -841,6 +892,7 @@ int rpf_topology(const rpf_handle* h, int64_t* child, int32_t* depth, int64_t* s
 int rpf_tree_export(rpf_handle* h, int32_t t, double* thr, double* mlo, double* mhi, uint32_t* perm) {
     if (!h) return RPF_ERR_ARG;
     if (!h->built) return rpf_fail(h, RPF_ERR_STATE, "tree_export: forest not built");
+    if (h->group) return rpfg_tree_export(h, t, thr, mlo, mhi, perm);
     if (t < 0 || t >= h->T) return rpf_fail(h, RPF_ERR_ARG, "tree_export: tree index out of range");
     RPF_SETDEV(h);
     const size_t nn = (size_t)h->topo.nnodes();
@@ -854,6 +906,7 @@ int rpf_tree_export(rpf_handle* h, int32_t t, double* thr, double* mlo, double* 
 int rpf_forest_export(rpf_handle* h, double* thr, double* mlo, double* mhi, uint32_t* perm) {
     if (!h) return RPF_ERR_ARG;
     if (!h->built) return rpf_fail(h, RPF_ERR_STATE, "forest_export: forest not built");
+    if (h->group) return rpfg_forest_export(h, thr, mlo, mhi, perm);
     RPF_SETDEV(h);
     if (h->sink_pending && perm == h->sink_perm && thr == h->sink_thr && mlo == h->sink_mlo && mhi == h->sink_mhi) {
         RPF_CUDA(h, cudaEventSynchronize(h->sink_ev[9]));        // the build streamed the forest into these buffers already
@@ -871,6 +924,7 @@ int rpf_forest_export(rpf_handle* h, double* thr, double* mlo, double* mhi, uint
 
 int rpf_set_export_sink(rpf_handle* h, double* thr, double* mlo, double* mhi, uint32_t* perm) {
     if (!h) return RPF_ERR_ARG;
+    if (h->group) return rpfg_set_export_sink(h, thr, mlo, mhi, perm);
     RPF_SETDEV(h);
     if (h->d2h_stream) RPF_CUDA(h, cudaStreamSynchronize(h->d2h_stream));
     h->sink_thr = thr; h->sink_mlo = mlo; h->sink_mhi = mhi; h->sink_perm = perm;
@@ -882,6 +936,7 @@ int rpf_candidates_count(rpf_handle* h, const double* Q, int64_t nq, int32_t t, 
     if (!h) return RPF_ERR_ARG;
     if (!h->built) return rpf_fail(h, RPF_ERR_STATE, "candidates: forest not built");
     if (nq < 0 || (nq > 0 && !Q) || !off_out || t < -1 || t >= h->T) return rpf_fail(h, RPF_ERR_ARG, "candidates_count: bad arguments");
+    if (h->group) return rpfg_candidates(h, Q, nq, t, off_out, nullptr, nullptr);
     RPF_SETDEV(h);
     h->call_begin();
     int rc = rpf_candidates_impl(h, Q, nq, t, off_out, nullptr, nullptr);
@@ -893,6 +948,7 @@ int rpf_candidates(rpf_handle* h, const double* Q, int64_t nq, int32_t t, const 
     if (!h) return RPF_ERR_ARG;
     if (!h->built) return rpf_fail(h, RPF_ERR_STATE, "candidates: forest not built");
     if (nq < 0 || (nq > 0 && !Q) || !off || t < -1 || t >= h->T) return rpf_fail(h, RPF_ERR_ARG, "candidates: bad arguments");
+    if (h->group) return rpfg_candidates(h, Q, nq, t, nullptr, off, ids);
     RPF_SETDEV(h);
     h->call_begin();
     int rc = rpf_candidates_impl(h, Q, nq, t, nullptr, off, ids);
@@ -904,6 +960,7 @@ int rpf_knn(rpf_handle* h, const double* Q, int64_t nq, int32_t k, int32_t dedup
     if (!h) return RPF_ERR_ARG;
     if (!h->built) return rpf_fail(h, RPF_ERR_STATE, "knn: forest not built");
     if (nq < 0 || (nq > 0 && (!Q || !dist || !ids)) || k < 1 || k > 1024) return rpf_fail(h, RPF_ERR_ARG, "knn: bad arguments (1 <= k <= 1024)");
+    if (h->group) return rpfg_knn(h, Q, nullptr, nq, k, dedup, dist, ids, count);
     RPF_SETDEV(h);
     h->call_begin();
     int rc = rpf_knn_impl(h, Q, nullptr, nq, k, dedup, dist, ids, count, false);
@@ -915,6 +972,7 @@ int rpf_knn_s(rpf_handle* h, const double* Q, const int32_t* q_last, int64_t nq,
     if (!h) return RPF_ERR_ARG;
     if (!h->built) return rpf_fail(h, RPF_ERR_STATE, "knn: forest not built");
     if (nq < 0 || (nq > 0 && (!Q || !dist || !ids)) || k < 1 || k > 1024) return rpf_fail(h, RPF_ERR_ARG, "knn: bad arguments (1 <= k <= 1024)");
+    if (h->group) return rpfg_knn(h, Q, q_last, nq, k, dedup, dist, ids, count);
     RPF_SETDEV(h);
     h->call_begin();
     int rc = rpf_knn_impl(h, Q, q_last, nq, k, dedup, dist, ids, count, false);
@@ -935,6 +993,8 @@ int rpf_knn_h(rpf_handle* h, const double* Q, const int32_t* q_last, int64_t nq,
     if (!h->built) return rpf_fail(h, RPF_ERR_STATE, "knnH: forest not built");
     if (nq < 0 || (nq > 0 && (!Q || !dist || !ids || !count)) || k < 1) return rpf_fail(h, RPF_ERR_ARG, "knnH: bad arguments");
     if (cap < rpf_knn_h_capacity(h, k) || cap > 0x7fffffff) return rpf_fail(h, RPF_ERR_ARG, "knnH: cap must be >= rpf_knn_h_capacity(h, k)");
+    if (h->group || rpf_comm_world(h) > 1)
+        return rpf_fail(h, RPF_ERR_UNSUPPORTED, "knnH: the margin-priority search ranks the leaves of ALL trees in one heap; not sharded across GPUs yet");
     RPF_SETDEV(h);
     h->call_begin();
     int rc = rpf_knn_h_impl(h, Q, q_last, nq, k, (int)cap, dist, ids, count);
@@ -946,6 +1006,7 @@ int rpf_recall(rpf_handle* h, const double* Q, int64_t nq, int32_t k, double* re
     if (!h) return RPF_ERR_ARG;
     if (!h->built) return rpf_fail(h, RPF_ERR_STATE, "recall: forest not built");
     if (nq < 0 || (nq > 0 && (!Q || !recall_sum)) || k < 1 || k > 1024) return rpf_fail(h, RPF_ERR_ARG, "recall: bad arguments (1 <= k <= 1024)");
+    if (h->group) return rpfg_recall(h, Q, nullptr, nq, k, recall_sum);
     RPF_SETDEV(h);
     h->call_begin();
     int rc = rpf_recall_impl(h, Q, nullptr, nq, k, recall_sum);
@@ -957,6 +1018,7 @@ int rpf_recall_s(rpf_handle* h, const double* Q, const int32_t* q_last, int64_t 
     if (!h) return RPF_ERR_ARG;
     if (!h->built) return rpf_fail(h, RPF_ERR_STATE, "recall: forest not built");
     if (nq < 0 || (nq > 0 && (!Q || !recall_sum)) || k < 1 || k > 1024) return rpf_fail(h, RPF_ERR_ARG, "recall: bad arguments (1 <= k <= 1024)");
+    if (h->group) return rpfg_recall(h, Q, q_last, nq, k, recall_sum);
     RPF_SETDEV(h);
     h->call_begin();
     int rc = rpf_recall_impl(h, Q, q_last, nq, k, recall_sum);
@@ -966,6 +1028,7 @@ int rpf_recall_s(rpf_handle* h, const double* Q, const int32_t* q_last, int64_t 
 
 int rpf_brute_knn(rpf_handle* h, const double* Q, int64_t nq, int32_t k, double* dist, uint32_t* ids) {
     if (!h) return RPF_ERR_ARG;
+    if (h->group) return rpfg_brute_knn(h, Q, nullptr, nq, k, dist, ids);
     if (!h->dX) return rpf_fail(h, RPF_ERR_STATE, "brute_knn: call rpf_set_points first");
     if (nq < 0 || (nq > 0 && (!Q || !dist || !ids)) || k < 1 || k > 1024) return rpf_fail(h, RPF_ERR_ARG, "brute_knn: bad arguments (1 <= k <= 1024)");
     RPF_SETDEV(h);
@@ -977,6 +1040,7 @@ int rpf_brute_knn(rpf_handle* h, const double* Q, int64_t nq, int32_t k, double*
 
 int rpf_brute_knn_s(rpf_handle* h, const double* Q, const int32_t* q_last, int64_t nq, int32_t k, double* dist, uint32_t* ids) {
     if (!h) return RPF_ERR_ARG;
+    if (h->group) return rpfg_brute_knn(h, Q, q_last, nq, k, dist, ids);
     if (!h->dX) return rpf_fail(h, RPF_ERR_STATE, "brute_knn: call rpf_set_points first");
     if (nq < 0 || (nq > 0 && (!Q || !dist || !ids)) || k < 1 || k > 1024) return rpf_fail(h, RPF_ERR_ARG, "brute_knn: bad arguments (1 <= k <= 1024)");
     RPF_SETDEV(h);
@@ -991,6 +1055,7 @@ int rpf_merge_topk(rpf_handle* h, int32_t G, int64_t nq, int32_t k, int32_t dedu
     if (!h) return RPF_ERR_ARG;
     if (G < 1 || nq < 0 || k < 1 || k > 1024 || (nq > 0 && (!dist || !ids || !count || !dist_out || !ids_out)))
         return rpf_fail(h, RPF_ERR_ARG, "merge_topk: bad arguments");
+    if (h->group) return rpf_fail(h, RPF_ERR_UNSUPPORTED, "merge_topk: a multi-GPU handle merges inside rpf_knn");
     RPF_SETDEV(h);
     h->call_begin();
     int rc = rpf_merge_impl(h, G, nq, k, dedup, dist, ids, count, dist_out, ids_out, count_out, false);
@@ -1003,6 +1068,7 @@ int rpf_knn_dev(rpf_handle* h, const double* Q, const int32_t* q_last, int64_t n
     if (!h) return RPF_ERR_ARG;
     if (!h->built) return rpf_fail(h, RPF_ERR_STATE, "knn: forest not built");
     if (nq < 0 || (nq > 0 && (!Q || !dist_dev || !ids_dev || !count_dev)) || k < 1 || k > 1024) return rpf_fail(h, RPF_ERR_ARG, "knn_dev: bad arguments (1 <= k <= 1024)");
+    if (h->group) return rpf_fail(h, RPF_ERR_UNSUPPORTED, "knn_dev: a multi-GPU handle exchanges and merges inside rpf_knn");
     RPF_SETDEV(h);
     h->call_begin();
     int rc = rpf_knn_impl(h, Q, q_last, nq, k, dedup, dist_dev, ids_dev, count_dev, true);
@@ -1015,6 +1081,7 @@ int rpf_merge_topk_dev(rpf_handle* h, int32_t G, int64_t nq, int32_t k, int32_t 
     if (!h) return RPF_ERR_ARG;
     if (G < 1 || nq < 0 || k < 1 || k > 1024 || (nq > 0 && (!dist_dev || !ids_dev || !count_dev || !dist_out || !ids_out)))
         return rpf_fail(h, RPF_ERR_ARG, "merge_topk_dev: bad arguments");
+    if (h->group) return rpf_fail(h, RPF_ERR_UNSUPPORTED, "merge_topk_dev: a multi-GPU handle merges inside rpf_knn");
     RPF_SETDEV(h);
     h->call_begin();
     int rc = rpf_merge_impl(h, G, nq, k, dedup, dist_dev, ids_dev, count_dev, dist_out, ids_out, count_out, true);
@@ -1023,9 +1090,10 @@ int rpf_merge_topk_dev(rpf_handle* h, int32_t G, int64_t nq, int32_t k, int32_t 
 }
 
 double rpf_last_device_ms(const rpf_handle* h) { return h ? h->last_ms : -1.0; }
-int rpf_set_profiling(rpf_handle* h, int on) { if (!h) return RPF_ERR_ARG; h->profiling = on != 0; ++h->cfg_epoch; return RPF_OK; }
+int rpf_set_profiling(rpf_handle* h, int on) { if (!h) return RPF_ERR_ARG; if (h->group) return rpfg_set_profiling(h, on); h->profiling = on != 0; ++h->cfg_epoch; return RPF_OK; }
 int rpf_get_profile(const rpf_handle* h, double* ms, int64_t* launches, int cap) {
     if (!h) return RPF_ERR_ARG;
+    if (h->group) return rpfg_get_profile(h, ms, launches, cap);
     for (int i = 0; i < PH_COUNT && i < cap; ++i) {
         if (ms) ms[i] = h->phase_ms[i];
         if (launches) launches[i] = h->phase_launches[i];
@@ -1033,9 +1101,10 @@ int rpf_get_profile(const rpf_handle* h, double* ms, int64_t* launches, int cap)
     return PH_COUNT;
 }
 const char* rpf_phase_name(int i) { return (i >= 0 && i < PH_COUNT) ? kPhaseNames[i] : ""; }
-int64_t rpf_launch_count(const rpf_handle* h) { return h ? h->launches : -1; }
+int64_t rpf_launch_count(const rpf_handle* h) { return h ? (h->group ? rpfg_launch_count(h) : h->launches) : -1; }
 int rpf_set_option(rpf_handle* h, const char* name, int64_t value) {
     if (!h || !name) return RPF_ERR_ARG;
+    if (h->group) return rpfg_set_option(h, name, value, false);
     const std::string s(name);
     ++h->cfg_epoch;
     if (s == "cuda_graph") { h->use_graphs = value != 0; return RPF_OK; }
@@ -1056,6 +1125,7 @@ int rpf_set_bottom_cap(rpf_handle* h, int32_t cap) {
     if (!h) return RPF_ERR_ARG;
     if (cap != 256 && cap != 512 && cap != 1024 && cap != 2048 && cap != 4096 && cap != 8192)
         return rpf_fail(h, RPF_ERR_ARG, "bottom_cap must be a power of two in [256, 8192]");
+    if (h->group) return rpfg_set_option(h, "", cap, true);
     h->bottom_cap = cap;
     h->tg_cached = 0;
     ++h->cfg_epoch;

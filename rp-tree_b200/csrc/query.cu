@@ -962,9 +962,12 @@ __global__ void __launch_bounds__(KNN_NT) k_recall(QArgs A, const uint32_t* __re
     }
 }
 
-// multi-GPU merge: G rank-major lists of up to k (dist, id) per query -> global top-k by (dist, rank, position)
+// multi-GPU merge: G rank-major lists of up to k (dist, id) per query -> global top-k by (dist, rank, position).
+// Rank g's lists start at dist + g * sd, ids + g * si, count + g * sc (elements): three rank-major arrays (sd = si = nq * k,
+// sc = nq) or the packed per-rank chunks of the in-engine NCCL exchange.
 __global__ void __launch_bounds__(KNN_NT) k_merge(int G, int64_t nq, int k, int dedup, const double* __restrict__ dist,
                                                   const uint32_t* __restrict__ ids, const int32_t* __restrict__ count,
+                                                  int64_t sd, int64_t si, int64_t sc,
                                                   double* __restrict__ dist_out, uint32_t* __restrict__ ids_out, int32_t* __restrict__ count_out) {
     extern __shared__ unsigned char dyn[];
     ull* skey = (ull*)dyn;
@@ -979,11 +982,11 @@ __global__ void __launch_bounds__(KNN_NT) k_merge(int G, int64_t nq, int k, int 
         const int g1 = min(G, g0 + (int)per);
         unsigned m = 0;
         for (int g = g0; g < g1; ++g) {
-            const unsigned c = (unsigned)count[(int64_t)g * nq + q];
+            const unsigned c = (unsigned)count[(int64_t)g * sc + q];
             for (unsigned j = tid; j < c; j += KNN_NT) {
-                skey[nbest + m + j] = (ull)__double_as_longlong(dist[((int64_t)g * nq + q) * k + j]);
+                skey[nbest + m + j] = (ull)__double_as_longlong(dist[(int64_t)g * sd + q * k + j]);
                 spos[nbest + m + j] = (uint32_t)(g * k + j);
-                sid[nbest + m + j] = ids[((int64_t)g * nq + q) * k + j];
+                sid[nbest + m + j] = ids[(int64_t)g * si + q * k + j];
             }
             m += c;
         }
@@ -999,6 +1002,15 @@ __global__ void __launch_bounds__(KNN_NT) k_merge(int G, int64_t nq, int k, int 
         ids_out[q * k + i] = ok ? sid[i] : 0xffffffffu;
     }
     if (tid == 0 && count_out) count_out[q] = (int32_t)nbest;
+}
+
+// recall sums of the ranks (rank-major [G][stride]) added in rank order = tree order (left fold, like the reference's sum)
+__global__ void k_sum_ranks(const double* __restrict__ part, int G, int64_t stride, int64_t nq, double* __restrict__ out) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    double s = 0.0;
+    for (int g = 0; g < G; ++g) s = s + part[(int64_t)g * stride + q];
+    out[q] = s;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1085,6 +1097,21 @@ int rpf_knn_impl(rpf_handle* h, const double* Q, const int32_t* q_last, int64_t 
     QWS(h, wids, uint32_t, WS_OUT_I, (size_t)nq * k * 4);
     QWS(h, wcount, int32_t, WS_OUT_C, (size_t)nq * 4);
     double* ddist = out_dev ? dist : wdist; uint32_t* dids = out_dev ? ids : wids; int32_t* dcount = (out_dev && count) ? count : wcount;
+    // rank of a tree-sharded forest (rpf_comm_init_rank / rpf_create_multi): the local lists are written straight into this
+    // rank's chunk of ONE packed exchange buffer [dist | ids | count], all-gathered in place over NCCL on the engine's
+    // stream (no host synchronisation in between), and merged by k_merge in (distance, rank, position) order -- which is
+    // the reference's tree order because the ranks hold contiguous blocks of trees (RPTree.hs:174-176)
+    const int W = out_dev ? 1 : rpf_comm_world(h);
+    char* xbuf = nullptr; size_t chunk = 0, off_i = 0, off_c = 0;
+    if (W > 1) {
+        off_i = ((size_t)nq * k * 8 + 15) & ~(size_t)15;
+        off_c = off_i + (((size_t)nq * k * 4 + 15) & ~(size_t)15);
+        chunk = off_c + (((size_t)nq * 4 + 15) & ~(size_t)15);
+        xbuf = (char*)h->ws_get(WS_MRG_D, chunk * W);
+        if (!xbuf) return RPF_ERR_NOMEM;
+        char* mine = xbuf + (size_t)rpf_comm_rank(h) * chunk;
+        ddist = (double*)mine; dids = (uint32_t*)(mine + off_i); dcount = (int32_t*)(mine + off_c);
+    }
     QArgs A = make_qargs(h, nq, st);
     A.k = k; A.dedup = dedup; A.dist = ddist; A.ids = dids; A.count = dcount;
     if (nq >= 64 && !h->no_query_order) {
@@ -1113,7 +1140,18 @@ int rpf_knn_impl(rpf_handle* h, const double* Q, const int32_t* q_last, int64_t 
         RPF_CUDA(h, cudaFuncSetAttribute(k_knn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
         RPF_LAUNCH(h, PH_Q_KNN, k_knn, (unsigned)nq, KNN_NT, dyn, A);
     }
-    if (!out_dev) {
+    if (W > 1) {
+        int rcx = rpf_comm_allgather(h, xbuf, chunk, h->stream);
+        if (rcx) return rcx;
+        if (dist) {      // ranks that want the result (all of them in a multi-process job, rank 0 of an in-process group)
+            const size_t dynm = (size_t)KNN_BUF * 16;
+            RPF_CUDA(h, cudaFuncSetAttribute(k_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dynm));
+            RPF_LAUNCH(h, PH_MERGE, k_merge, (unsigned)nq, KNN_NT, dynm, W, nq, k, dedup, (const double*)xbuf, (const uint32_t*)(xbuf + off_i),
+                       (const int32_t*)(xbuf + off_c), (int64_t)(chunk / 8), (int64_t)(chunk / 4), (int64_t)(chunk / 4), wdist, wids, wcount);
+            ddist = wdist; dids = wids; dcount = wcount;
+        }
+    }
+    if (!out_dev && dist) {
         RPF_CUDA(h, cudaMemcpyAsync(dist, ddist, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, h->stream));
         RPF_CUDA(h, cudaMemcpyAsync(ids, dids, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, h->stream));
         if (count) RPF_CUDA(h, cudaMemcpyAsync(count, dcount, (size_t)nq * 4, cudaMemcpyDeviceToHost, h->stream));
@@ -1243,17 +1281,34 @@ int rpf_recall_impl(rpf_handle* h, const double* Q, const int32_t* q_last, int64
     if (rc) return rc;
     rc = run_descent(h, Q, nq, -1, st);
     if (rc) return rc;
-    QWS(h, dd, double, WS_TRUTH_D, (size_t)nq * k * 8);
-    QWS(h, di, uint32_t, WS_TRUTH_I, (size_t)nq * k * 4);
-    QWS(h, dr, double, WS_RECALL, (size_t)nq * 8);
-    rc = brute_device(h, st.dQ, st.dqlast, nq, k, dd, di);
-    if (rc) return rc;
+    // Rank of a tree-sharded forest: the brute-force truth (the expensive part: n x d per query) is computed for a 1/W
+    // slice of the queries per rank and all-gathered; every rank then counts the hits of ITS trees and the per-rank sums
+    // are added in rank (= tree) order, so recall_sum is the sum over the WHOLE forest (RPTree.hs:265-268).
+    const int W = rpf_comm_world(h), R = rpf_comm_rank(h);
+    const int64_t per = (nq + W - 1) / W;
+    QWS(h, dd, double, WS_TRUTH_D, (size_t)per * W * k * 8);
+    QWS(h, di, uint32_t, WS_TRUTH_I, (size_t)per * W * k * 4);
+    const size_t res_n = (size_t)per * W;      // >= nq
+    QWS(h, dr, double, WS_RECALL, (res_n + (W > 1 ? (size_t)W * res_n : 0)) * 8);   // result, then W > 1: [W][res_n] per-rank sums
+    double* part = dr + res_n;
+    double* mine = W > 1 ? part + (size_t)R * res_n : dr;
+    const int64_t q0 = std::min<int64_t>(nq, R * per), q1 = std::min<int64_t>(nq, q0 + per);
+    if (q1 > q0) {
+        rc = brute_device(h, st.dQ + q0 * h->d, st.dqlast ? st.dqlast + q0 : nullptr, q1 - q0, k, dd + q0 * k, di + q0 * k);
+        if (rc) return rc;
+    }
+    if (W > 1) { rc = rpf_comm_allgather(h, di, (size_t)per * k * 4, h->stream); if (rc) return rc; }
     QArgs A = make_qargs(h, nq, st);
     A.k = k;
     const size_t dyn = ((size_t)h->T * st.S + 1) * 4 + (size_t)h->T * 4;
     RPF_CUDA(h, cudaFuncSetAttribute(k_recall, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(dyn, 1024)));
-    RPF_LAUNCH(h, PH_RECALL, k_recall, (unsigned)nq, KNN_NT, dyn, A, di, dr);
-    RPF_CUDA(h, cudaMemcpyAsync(recall_sum, dr, (size_t)nq * 8, cudaMemcpyDeviceToHost, h->stream));
+    RPF_LAUNCH(h, PH_RECALL, k_recall, (unsigned)nq, KNN_NT, dyn, A, di, mine);
+    if (W > 1) {
+        rc = rpf_comm_allgather(h, part, res_n * 8, h->stream);
+        if (rc) return rc;
+        RPF_LAUNCH(h, PH_RECALL, k_sum_ranks, (unsigned)((nq + 255) / 256), 256, 0, part, W, (int64_t)res_n, nq, dr);
+    }
+    if (recall_sum) RPF_CUDA(h, cudaMemcpyAsync(recall_sum, dr, (size_t)nq * 8, cudaMemcpyDeviceToHost, h->stream));
     RPF_CUDA(h, cudaStreamSynchronize(h->stream));
     return RPF_OK;
 }
@@ -1279,7 +1334,7 @@ int rpf_merge_impl(rpf_handle* h, int G, int64_t nq, int k, int dedup, const dou
     QWS(h, oc, int32_t, WS_OUT_C, (size_t)nq * 4);
     const size_t dynm = (size_t)KNN_BUF * 16;
     RPF_CUDA(h, cudaFuncSetAttribute(k_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dynm));
-    RPF_LAUNCH(h, PH_MERGE, k_merge, (unsigned)nq, KNN_NT, dynm, G, nq, k, dedup, dd, di, dc, od, oi, oc);
+    RPF_LAUNCH(h, PH_MERGE, k_merge, (unsigned)nq, KNN_NT, dynm, G, nq, k, dedup, dd, di, dc, nq * k, nq * k, nq, od, oi, oc);
     RPF_CUDA(h, cudaMemcpyAsync(dist_out, od, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, h->stream));
     RPF_CUDA(h, cudaMemcpyAsync(ids_out, oi, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, h->stream));
     if (count_out) RPF_CUDA(h, cudaMemcpyAsync(count_out, oc, (size_t)nq * 4, cudaMemcpyDeviceToHost, h->stream));

@@ -111,8 +111,14 @@ enum rpf_ws_slot {
 };
 struct WsBuf { void* p = nullptr; size_t cap = 0; };
 
+struct RpfComm;     // multi.cu: this handle is one rank of a tree-sharded forest (NCCL communicator + rank / world)
+struct RpfGroup;    // multi.cu: this handle is the in-process parent of one sub-handle per GPU (rpf_create_multi)
+
 struct rpf_handle {
     int device = 0;
+    RpfComm* comm = nullptr;
+    RpfGroup* group = nullptr;
+    int64_t x_pad_rows = 0;              // rows allocated behind row n of dX (the in-place all-gather of the last row block may spill)
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;   // rpf_build_from_host: row-block uploads overlapped with the projection
     cudaEvent_t copy_ev[17] = {nullptr};  // one per upload block + the "previous contents of dX are no longer read" event
@@ -251,6 +257,18 @@ int rpf_recall_impl(rpf_handle* h, const double* Q, const int32_t* q_last, int64
 int rpf_brute_knn_impl(rpf_handle* h, const double* Q, const int32_t* q_last, int64_t nq, int k, double* dist, uint32_t* ids);
 int rpf_merge_impl(rpf_handle* h, int G, int64_t nq, int k, int dedup, const double* dist, const uint32_t* ids,
                    const int32_t* count, double* dist_out, uint32_t* ids_out, int32_t* count_out, bool in_dev);
+
+// ---- multi-GPU (multi.cu) ---------------------------------------------------------------------------
+// rank / world of a handle (0 / 1 without a communicator)
+int rpf_comm_rank(const rpf_handle* h);
+int rpf_comm_world(const rpf_handle* h);
+void rpf_comm_free(rpf_handle* h);
+// in-place all-gather on `stream`: every rank contributed `bytes` bytes at buf + rank * bytes
+int rpf_comm_allgather(rpf_handle* h, void* buf, size_t bytes, cudaStream_t stream);
+// the rows rank r supplies to a row-sharded upload of n rows: [r * per, min(n, (r + 1) * per)), per = ceil(n / world)
+int rpf_upload_rows(rpf_handle* h, const double* hostX, int64_t r0, int64_t nr, cudaStream_t stream);   // build.cu
+// group parent (rpf_create_multi): every public entry point forwards here when h->group is set
+void rpf_group_free(rpf_handle* h);
 
 // ---- bottom phase launch arguments (build.cu kernels; also filled by stream.cu for Tip re-splits) --------
 typedef unsigned long long ull;

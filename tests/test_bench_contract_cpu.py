@@ -10,12 +10,25 @@ sys.path.insert(0, ROOT)
 
 
 def test_reference_arm_prints_one_json_line(built):
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
-                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    # run bench.py as __main__ and then look at what the process loaded: the reference arm must run on the oracle alone --
+    # neither the product package nor librpforest.so may be in the process (the driver records the loaded .so files)
+    prog = ("import sys, runpy\n"
+            "sys.argv = ['bench.py', '--impl', 'reference', '--steps', '1', '--warmup', '0']\n"
+            "runpy.run_path(%r, run_name='__main__')\n"
+            "maps = open('/proc/self/maps').read()\n"
+            "assert 'librpforest' not in maps, 'the reference arm loaded the product library'\n"
+            "assert 'liborc' in maps\n"
+            "assert not any(m.startswith('rp_tree_b200') or m.startswith('rp-tree_b200') for m in sys.modules), 'product package imported'\n"
+            % os.path.join(ROOT, "bench.py"))
+    out = subprocess.run([sys.executable, "-c", prog], capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.strip()]
     assert len(lines) == 1
     j = json.loads(lines[0])
+    import bench
+    maxd = j["config"]["max_depth"]
+    assert j["config"] == bench.config_dict(bench.WORKLOAD, maxd, 1), "both arms must print the same config dict"
+    assert j["cpu_baseline"]["knn_queries_per_s"] > 0 and 0 <= j["cpu_baseline"]["recall_oracle"] <= 1
     for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
                 "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert key in j, key
