@@ -11,6 +11,7 @@ from .api import (RPForest, SparseRows, RPTreeConfig, metricL2, rpTreeCfg, sampl
                   treeSize, points, serialiseRPForest, deserialiseRPForest)
 from . import _build
 from . import dist
+from . import idx
 
 __all__ = ["RPForest", "SparseRows", "RPForestError", "RPTreeConfig", "metricL2", "rpTreeCfg", "sampleHyperplanes", "topologyPlan",
            "slice_hyperplanes", "forestBatch", "treeBatch", "forest", "tree", "knn", "knnPQ", "knnH", "candidates", "recallWith",

@@ -119,3 +119,31 @@ def test_densify_rows_helper(built):
     bad = R.SparseRows([0, 2], [2, 1], [1.0, 2.0], 4)        # indices not ascending
     with pytest.raises(R.RPForestError):
         bad.densify()
+
+
+def _write_idx3(path, img):
+    import struct
+    with open(path, "wb") as fh:
+        fh.write(bytes([0, 0, 8, 3]) + struct.pack(">3I", *img.shape) + img.tobytes())
+
+
+def test_idx_loader_cpu_roundtrip(tmp_path):
+    """IDX3 ubyte file -> SVectors of the nonzero pixels / 255 (`mnist`, bench/time/Main.hs:113-125); no GPU needed."""
+    import rp_tree_b200 as R
+    rng = np.random.default_rng(0)
+    img = (rng.integers(0, 256, size=(37, 6, 5)) * (rng.random((37, 6, 5)) < 0.3)).astype(np.uint8)
+    p = tmp_path / "train-images-idx3-ubyte"
+    _write_idx3(p, img)
+    rows = R.idx.mnistSparse(p, 20)
+    assert rows.n == 20 and rows.d == 30
+    flat = img.reshape(37, -1)[:20]
+    for i in range(20):
+        a, b = rows.off[i], rows.off[i + 1]
+        nzc = np.flatnonzero(flat[i])
+        assert np.array_equal(rows.idx[a:b], nzc) and np.array_equal(rows.val[a:b], flat[i, nzc] / 255.0)
+    with pytest.raises(ValueError):
+        bad = tmp_path / "bad"
+        bad.write_bytes(b"\x00\x00\x0d\x03" + b"\x00" * 12)
+        R.idx.read_idx_ubyte(bad)
+
+

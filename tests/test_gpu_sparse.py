@@ -99,3 +99,43 @@ def test_sparse_points_reject_malformed_rows(built):
         f.setPointsSparse(R.SparseRows([0, 2], [3, 1], [1.0, 2.0], 5))
     with pytest.raises(R.RPForestError, match="range"):
         f.setPointsSparse(R.SparseRows([0, 1], [7], [1.0], 5))
+
+
+def _write_idx3(path, img):
+    import struct
+    with open(path, "wb") as fh:
+        fh.write(bytes([0, 0, 8, 3]) + struct.pack(">3I", *img.shape) + img.tobytes())
+
+
+@pytest.mark.gpu
+def test_c1_mnist_like_single_tree(built, tmp_path):
+    """BASELINE configs[0] shape: 784-d MNIST-like IDX file -> single RPTree build + knn k=10, checked against the oracle
+    (massive ties at 0: most pixels are background)."""
+    import rp_tree_b200 as R
+    from oracle import orc
+    rng = np.random.default_rng(5)
+    n = 3000
+    img = np.zeros((n, 28, 28), np.uint8)
+    for i in range(n):                                  # blobs of ink on a black background
+        cx, cy, r = rng.integers(6, 22), rng.integers(6, 22), rng.integers(2, 6)
+        yy, xx = np.ogrid[:28, :28]
+        m = (yy - cy) ** 2 + (xx - cx) ** 2 <= r * r
+        img[i][m] = rng.integers(1, 256, size=int(m.sum()))
+    p = tmp_path / "train-images-idx3-ubyte"
+    _write_idx3(p, img)
+    rows = R.idx.mnistSparse(p)
+    d, minl, k = 784, 10, 10
+    cfg = R.rpTreeCfg(minl, n, d)
+    maxd = cfg.fpMaxTreeDepth
+    hp = orc.gen_hyperplanes(1235137, 1, maxd, cfg.fpProjNzDensity, d)
+    f = R.RPForest(0)
+    f.setHyperplanes(hp, 1, maxd)
+    f.setPointsSparse(rows)
+    f.build(maxd, minl)
+    of = orc.SparseForest((rows.off, rows.idx, rows.val), d, hp, 1, maxd, minl)
+    assert not compare_tree(f.treeExport(0), of.export(0))
+    Qd, _ = rows.densify()
+    dist, ids, cnt = f.knnBatch(Qd[:24], k)
+    for i in range(24):
+        od, oi = of.knn(Qd[i], k)
+        assert np.array_equal(ids[i, :cnt[i]], oi) and np.array_equal(bits(dist[i, :cnt[i]]), bits(od))
