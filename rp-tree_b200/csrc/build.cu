@@ -45,29 +45,17 @@ __device__ __forceinline__ double lds_f64_off(unsigned a) {
 // but the first resumes from the partial sum the previous one left in `out` (as a raw double), every launch but the
 // last stores the partial sum back, the last one stores the finished key.  The arithmetic -- order and roundings -- is
 // that of the single-tile kernel.  flags: bit 0 = first block of the fold (start from 0), bit 1 = last block.
+// The fold of one staged tile: xs holds the P = 32 * R points i0 .. i0 + P - 1 (columns [c0, c1), row stride ld doubles).
 template <int NT, int R, bool ORD, int LD>
-__global__ void __launch_bounds__(NT) k_project(const double* __restrict__ X, int64_t n, int d, int ld_rt,
-                                                 const int64_t* __restrict__ hp_off, const double2* __restrict__ hp_pack,
-                                                 int t0, int L, int hpDepth, int H,
-                                                 void* __restrict__ out, int64_t ostride, ull* __restrict__ kmin, ull* __restrict__ kmax,
-                                                 int c0, int c1, int flags) {
-    constexpr int P = 32 * R, NW = NT / 32;
-    extern __shared__ double xs[];
-    const int ld = LD ? LD : ld_rt;
+__device__ __forceinline__ void project_fold(const double* xs, const int ld, const int64_t i0, const int64_t n, const int d,
+                                             const int64_t* __restrict__ hp_off, const double2* __restrict__ hp_pack,
+                                             const int t0, const int L, const int hpDepth, const int H,
+                                             void* __restrict__ out, const int64_t ostride, ull* __restrict__ kmin, ull* __restrict__ kmax,
+                                             const int c0, const int c1, const int flags, const bool track) {
+    constexpr int NW = NT / 32;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    const int64_t i0 = (int64_t)blockIdx.x * P;
-    const int rows = (int)min((int64_t)P, n - i0);
     const int dc = c1 - c0;
     const bool blocked = dc != d, first = flags & 1, last = flags & 2;
-    for (int r = w; r < P; r += NW) {
-        if (r < rows) {
-            const double* src = X + (i0 + r) * (int64_t)d + c0;
-            for (int c = lane; c < dc; c += 32) xs[r * ld + c] = src[c];
-        } else {
-            for (int c = lane; c < dc; c += 32) xs[r * ld + c] = 0.0;
-        }
-    }
-    __syncthreads();
     // 32-bit shared-window addresses of this lane's R rows (one IADD + LDS per term instead of 64-bit pointer math)
     unsigned rowaddr[R];
 #pragma unroll
@@ -75,8 +63,7 @@ __global__ void __launch_bounds__(NT) k_project(const double* __restrict__ X, in
     // (the packed CSR stores byte offsets 8 * idx from column 0; the tile starts at column c0)
     // The per-row key range only seeds the bin map of the top phase (keys outside it fall into the first / last bin, the
     // exact select inside the median bin does the rest), so it is taken from every 8th tile: the warp reduction below
-    // costs about as much as four terms of the dot product.
-    const bool track = (blockIdx.x & 7) == 0;
+    // costs about as much as four terms of the dot product.  (`track`: chosen by the caller.)
     // write one output row (and fold its min/max) -- warp-uniform call
     auto emit = [&](int j, const double (&acc)[R]) {
         if (ORD && last) {
@@ -194,6 +181,80 @@ __global__ void __launch_bounds__(NT) k_project(const double* __restrict__ X, in
     }
 }
 
+template <int NT, int R, bool ORD, int LD>
+__global__ void __launch_bounds__(NT) k_project(const double* __restrict__ X, int64_t n, int d, int ld_rt,
+                                                 const int64_t* __restrict__ hp_off, const double2* __restrict__ hp_pack,
+                                                 int t0, int L, int hpDepth, int H,
+                                                 void* __restrict__ out, int64_t ostride, ull* __restrict__ kmin, ull* __restrict__ kmax,
+                                                 int c0, int c1, int flags) {
+    constexpr int P = 32 * R, NW = NT / 32;
+    extern __shared__ double xs[];
+    const int ld = LD ? LD : ld_rt;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int64_t i0 = (int64_t)blockIdx.x * P;
+    const int rows = (int)min((int64_t)P, n - i0);
+    const int dc = c1 - c0;
+    for (int r = w; r < P; r += NW) {
+        if (r < rows) {
+            const double* src = X + (i0 + r) * (int64_t)d + c0;
+            for (int c = lane; c < dc; c += 32) xs[r * ld + c] = src[c];
+        } else {
+            for (int c = lane; c < dc; c += 32) xs[r * ld + c] = 0.0;
+        }
+    }
+    __syncthreads();
+    project_fold<NT, R, ORD, LD>(xs, ld, i0, n, d, hp_off, hp_pack, t0, L, hpDepth, H, out, ostride, kmin, kmax, c0, c1, flags,
+                                 (blockIdx.x & 7) == 0);
+}
+
+// Pipelined form for rows that fit one tile twice (d <= ~145 at 96 points, d <= ~107 at 128 points): persistent CTAs walk
+// the tiles with a stride of gridDim.x; while the warps fold tile i out of one shared-memory buffer, the rows of tile i + 1
+// stream into the other one with asynchronous 8-byte copies (cp.async -> LDGSTS; the odd row stride that keeps the column
+// gathers conflict-free rules out 16-byte bulk copies), so the HBM read of X overlaps the fold instead of preceding it.
+// At small tree groups (the shard of an 8-GPU run: a few dozen hyperplanes) the load IS most of the kernel.
+template <int NT, int R, bool ORD, int LD>
+__global__ void __launch_bounds__(NT, 1) k_project_pipe(const double* __restrict__ X, int64_t n, int d, int ld_rt,
+                                                         const int64_t* __restrict__ hp_off, const double2* __restrict__ hp_pack,
+                                                         int t0, int L, int hpDepth, int H,
+                                                         void* __restrict__ out, int64_t ostride, ull* __restrict__ kmin, ull* __restrict__ kmax,
+                                                         int64_t ntiles) {
+    constexpr int P = 32 * R, NW = NT / 32;
+    extern __shared__ double xs[];
+    const int ld = LD ? LD : ld_rt;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const size_t bufsz = (size_t)P * ld;                       // doubles per buffer
+    auto stage = [&](int64_t tile, int b) {                    // rows of `tile` -> buffer b (rows past n: zero fill)
+        const int64_t i0 = tile * P;
+        double* dst = xs + (size_t)b * bufsz;
+        for (int r = w; r < P; r += NW) {
+            const bool live = i0 + r < n;
+            const double* src = X + (live ? (i0 + r) : 0) * (int64_t)d;
+            const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + (size_t)r * ld);
+            const unsigned nb = live ? 8u : 0u;                 // src-size 0: the 8 bytes are written as zeros
+            for (int c = lane; c < d; c += 32)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" :: "r"(sa + 8u * (unsigned)c), "l"(src + c), "r"(nb) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    int64_t tile = blockIdx.x;
+    if (tile >= ntiles) return;
+    stage(tile, 0);
+    int b = 0;
+    for (; tile < ntiles; tile += gridDim.x, b ^= 1) {
+        const int64_t nxt = tile + gridDim.x;
+        if (nxt < ntiles) {
+            stage(nxt, b ^ 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();                                        // every thread's copies of this tile have landed
+        project_fold<NT, R, ORD, LD>(xs + (size_t)b * bufsz, ld, tile * P, n, d, hp_off, hp_pack, t0, L, hpDepth, H, out, ostride,
+                                     kmin, kmax, 0, d, 3, (tile & 7) == 0);
+        __syncthreads();                                        // buffer b is free for the tile after next
+    }
+}
+
 // Fallback for very large d (tile does not fit shared memory): same arithmetic, rows read through L1/L2.
 template <bool ORD>
 __global__ void __launch_bounds__(256) k_project_direct(const double* __restrict__ X, int64_t n, int d,
@@ -253,6 +314,21 @@ static int launch_project(rpf_handle* h, int phase, const double* dX, int64_t n,
     return RPF_OK;
 }
 
+template <int NT, int R, bool ORD, int LD = 0>
+static int launch_project_pipe(rpf_handle* h, int phase, const double* dX, int64_t n, int t0, int L, int H, void* out, int64_t ostride, ull* kmin, ull* kmax) {
+    const int d = h->d, ld = d | 1;
+    const size_t smem = (size_t)2 * 32 * R * ld * sizeof(double);
+    auto kfn = k_project_pipe<NT, R, ORD, LD>;
+    RPF_CUDA(h, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t ntiles = (n + 32 * R - 1) / (32 * R);
+    static int nsm = 0;
+    if (!nsm) { cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device); if (nsm <= 0) nsm = 148; }
+    const int64_t grid = std::min<int64_t>(ntiles, nsm);
+    RPF_LAUNCH(h, phase, kfn, (unsigned)grid, NT, smem, dX, n, d, ld, h->d_hp_off, (const double2*)h->d_hp_pack, t0, L, h->hpDepth, H, out, ostride,
+               kmin, kmax, ntiles);
+    return RPF_OK;
+}
+
 // out row j (= tree-in-group * L + level) starts at out + j * ostride; point i of dX lands at column i
 int rpf_project_launch(rpf_handle* h, int phase, const double* dX, int64_t n, int t0, int Tg, int L, bool ord, void* out,
                        int64_t ostride, ull* kmin, ull* kmax) {
@@ -266,6 +342,19 @@ int rpf_project_launch(rpf_handle* h, int phase, const double* dX, int64_t n, in
     if (h->project_variant == 2 && 128 * row <= 140 * 1024)
         return ord ? launch_project<512, 4, true>(h, phase, dX, n, t0, L, H, out, ostride, kmin, kmax)
                    : launch_project<512, 4, false>(h, phase, dX, n, t0, L, H, out, ostride, kmin, kmax);
+    // rows short enough for two tiles in shared memory: the pipelined kernel (variant 7 = the single-buffer kernels below)
+    if (h->project_variant == 0 && n >= 4096) {
+        const size_t lim = 225 * 1024;
+        if (ld == 129)
+            return ord ? launch_project_pipe<1024, 3, true, 129>(h, phase, dX, n, t0, L, H, out, ostride, kmin, kmax)
+                       : launch_project_pipe<1024, 3, false, 129>(h, phase, dX, n, t0, L, H, out, ostride, kmin, kmax);
+        if ((size_t)2 * 128 * row <= lim)
+            return ord ? launch_project_pipe<1024, 4, true>(h, phase, dX, n, t0, L, H, out, ostride, kmin, kmax)
+                       : launch_project_pipe<1024, 4, false>(h, phase, dX, n, t0, L, H, out, ostride, kmin, kmax);
+        if ((size_t)2 * 96 * row <= lim)
+            return ord ? launch_project_pipe<1024, 3, true>(h, phase, dX, n, t0, L, H, out, ostride, kmin, kmax)
+                       : launch_project_pipe<1024, 3, false>(h, phase, dX, n, t0, L, H, out, ostride, kmin, kmax);
+    }
     if (ld == 129)      // d = 128: compile-time row stride
         return ord ? launch_project<1024, 4, true, 129>(h, phase, dX, n, t0, L, H, out, ostride, kmin, kmax)
                    : launch_project<1024, 4, false, 129>(h, phase, dX, n, t0, L, H, out, ostride, kmin, kmax);
