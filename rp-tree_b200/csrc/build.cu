@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(NT) k_project(const double* __restrict__ X, in
                                                  const int64_t* __restrict__ hp_off, const double2* __restrict__ hp_pack,
                                                  int t0, int L, int hpDepth, int H,
                                                  void* __restrict__ out, int64_t ostride, ull* __restrict__ kmin, ull* __restrict__ kmax,
-                                                 int c0, int c1, int flags) {
+                                                 int c0, int c1, int flags, int pf_ahead) {
     constexpr int P = 32 * R, NW = NT / 32;
     extern __shared__ double xs[];
     const int ld = LD ? LD : ld_rt;
@@ -194,6 +194,17 @@ __global__ void __launch_bounds__(NT) k_project(const double* __restrict__ X, in
     const int64_t i0 = (int64_t)blockIdx.x * P;
     const int rows = (int)min((int64_t)P, n - i0);
     const int dc = c1 - c0;
+    if (pf_ahead > 0 && tid == 0) {
+        // the tile a later wave will stage (its rows are contiguous in X): pulled into L2 now, so that CTA's load phase
+        // -- during which its SM does nothing else -- is served from L2 instead of HBM
+        const int64_t j0 = i0 + (int64_t)pf_ahead * P;
+        if (j0 + P <= n) {
+            const double* pf = X + j0 * (int64_t)d;
+            const unsigned bytes = (unsigned)((size_t)P * d * 8);
+            if ((((uintptr_t)pf) & 15) == 0 && (bytes & 15) == 0)
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(pf), "r"(bytes) : "memory");
+        }
+    }
     for (int r = w; r < P; r += NW) {
         if (r < rows) {
             const double* src = X + (i0 + r) * (int64_t)d + c0;
@@ -308,8 +319,12 @@ static int launch_project(rpf_handle* h, int phase, const double* dX, int64_t n,
         const int c0 = b * dcmax, c1 = std::min(d, c0 + dcmax);
         if (c1 <= c0) continue;
         const int flags = (b == nblk - 1 || c1 == d ? 1 : 0) | (b == 0 ? 2 : 0);
+        // whole-row tiles: prefetch the tile `resident CTAs` ahead into L2 (option project_prefetch: 0 = off)
+        int occ = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, NT, smem);
+        const int pf = (nblk == 1 && h->project_prefetch) ? std::max(1, occ) * 148 : 0;
         RPF_LAUNCH(h, phase, kfn, (unsigned)grid, NT, smem, dX, n, d, ld, h->d_hp_off, (const double2*)h->d_hp_pack, t0, L, h->hpDepth, H, out, ostride,
-                   kmin, kmax, c0, c1, flags);
+                   kmin, kmax, c0, c1, flags, pf);
     }
     return RPF_OK;
 }
@@ -343,7 +358,11 @@ int rpf_project_launch(rpf_handle* h, int phase, const double* dX, int64_t n, in
         return ord ? launch_project<512, 4, true>(h, phase, dX, n, t0, L, H, out, ostride, kmin, kmax)
                    : launch_project<512, 4, false>(h, phase, dX, n, t0, L, H, out, ostride, kmin, kmax);
     // rows short enough for two tiles in shared memory: the pipelined kernel (variant 7 = the single-buffer kernels below)
-    if (h->project_variant == 0 && n >= 4096) {
+    // (measured at 1M x 128: at 448 hyperplanes the two 96-point buffers leave 30 KB of L1 for the 92 KB of packed
+    //  hyperplanes and the fold slows down more than the overlap gains -- 2.92 vs 2.54 ms; with few hyperplanes, e.g. the
+    //  4-tree shard of an 8-GPU run, the load dominates and the pipeline wins)
+    const bool want_pipe = h->project_variant == 8 || (h->project_variant == 0 && H <= h->project_pipe_maxh);
+    if (want_pipe && n >= 4096) {
         const size_t lim = 225 * 1024;
         if (ld == 129)
             return ord ? launch_project_pipe<1024, 3, true, 129>(h, phase, dX, n, t0, L, H, out, ostride, kmin, kmax)
@@ -1721,6 +1740,7 @@ __global__ void __launch_bounds__(NT) k_bottom(BottomArgs A) {
 // transposition, so the result is exactly Merge.sortBy (comparing snd) (Internal.hs:504-512).
 // No entry tables, no bounds checks and no payload in the network: 2 LDS.64 + compare + 2 STS.64 per comparator.
 #define BOT2_TAB 512        /* segment-table entries of the default instance: subtrees of <= 9 splitting levels */
+#define BOT2_TAB_SHALLOW 32 /* shallow instance (<= 5 splitting levels, the usual batch build): 0.6 KB of tables instead of 9 KB per CTA */
 #define BOT2_TAB_DEEP 1024  /* deep instance (streaming chunk trees, minLeaf 0/1 chains): <= 10 splitting levels */
 #define W_SENT 0xffffffffffffffffull
 
@@ -1752,8 +1772,11 @@ __device__ __forceinline__ void bitonic_uniform(ull* w, unsigned nslots, unsigne
 // with the prefix taken from the key's position inside the (tree, level) key range.  Elements whose prefixes collide are
 // put in exact (full key, incoming slot) order by the neighbour fix-up below, so both forms give the same result; the
 // 32-bit form halves the compare/select, shuffle and shared-memory work of the network.
+#ifndef RPF_BOT_MINB128
+#define RPF_BOT_MINB128 10     /* resident CTAs per SM asked of the 128-thread instance (caps it at 48 registers) */
+#endif
 template <int NT, int TAB, typename W>
-__global__ void __launch_bounds__(NT) k_bottom3(BottomArgs A) {
+__global__ void __launch_bounds__(NT, (NT == 128 ? RPF_BOT_MINB128 : 1)) k_bottom3(BottomArgs A) {
     constexpr unsigned P0 = 8 * NT;               // slots (>= node size), 8 per thread
     constexpr int lp0 = (NT == 32 ? 8 : NT == 64 ? 9 : NT == 128 ? 10 : NT == 256 ? 11 : NT == 512 ? 12 : 13);
     constexpr bool W32 = sizeof(W) == 4;
@@ -2056,9 +2079,10 @@ int rpf_bottom_launch(rpf_handle* h, const BottomArgs& B, int nroots, int tg, bo
         unsigned slots = std::max(256u, next_pow2_host(std::max(max_root, 1u)));
         while (levels > 0 && (slots >> levels) == 0) slots <<= 1;          // slots >= 2^levels
         if (slots > 8192 || levels > rpf_bottom_fast_levels()) return rpf_fail(h, RPF_ERR_ARG, "internal: subtree too deep for the fast bottom kernel");
-        const bool deep = levels > 9;
+        const bool deep = levels > 9, shallow = levels <= 5;
 #define RPF_BOT_CASE(SL, NT_)                                                                                         \
-        case SL: return deep ? launch_bottom_fast<NT_, BOT2_TAB_DEEP>(h, B, nroots, tg) : launch_bottom_fast<NT_, BOT2_TAB>(h, B, nroots, tg);
+        case SL: return deep ? launch_bottom_fast<NT_, BOT2_TAB_DEEP>(h, B, nroots, tg)                              \
+                             : (shallow ? launch_bottom_fast<NT_, BOT2_TAB_SHALLOW>(h, B, nroots, tg) : launch_bottom_fast<NT_, BOT2_TAB>(h, B, nroots, tg));
         switch (slots) {
             RPF_BOT_CASE(256, 32)
             RPF_BOT_CASE(512, 64)
@@ -2190,21 +2214,29 @@ int rpf_launch_job(rpf_handle* h, BuildJob& J, const JobPlan& P, const char* tab
     const int* nbdev = (const int*)(tab + P.off_nb);
 
     if (s_top > 0) {
-        uint16_t* label = (uint16_t*)h->ws_get(WS_LABEL, (size_t)tg * n * 2);
-        uint16_t* pbin = (uint16_t*)h->ws_get(WS_PBIN, (size_t)tg * n * 2);
-        uint32_t* hist = (uint32_t*)h->ws_get(WS_HIST, (size_t)tg * HSZ * 4);
-        NodeSel* sel = (NodeSel*)h->ws_get(WS_SEL, (size_t)tg * NTOP * sizeof(NodeSel));
-        ull* cand = (ull*)h->ws_get(WS_CAND, (size_t)tg * n * 8);
-        uint32_t* cand_total = (uint32_t*)h->ws_get(WS_CANDTOT, (size_t)tg * 8 + 8);  // [tg] candidate totals + [tg] margin-tracking flags + 2 work-list lengths
+        // workspace: slice ws_part of ws_parts equal slices (one per concurrent branch), each sized for tgw trees
+        const int tgw = J.ws_tg > 0 ? J.ws_tg : tg;
+        bool ws_ok = true;
+        auto WSP = [&](int slot, size_t bytes) -> char* {
+            const size_t one = (bytes + 255) & ~(size_t)255;
+            char* b = (char*)h->ws_get(slot, one * (size_t)J.ws_parts);
+            if (!b) { ws_ok = false; return nullptr; }
+            return b + one * (size_t)J.ws_part;
+        };
         uint32_t max_lvl_nodes = 1;
         for (int l = 0; l < s_top; ++l) max_lvl_nodes = std::max<uint32_t>(max_lvl_nodes, (uint32_t)(P.level_off[l + 1] - P.level_off[l]));
-        uint32_t* wl = (uint32_t*)h->ws_get(WS_WORKLIST, (size_t)tg * max_lvl_nodes * 8);
-        if (!wl) return RPF_ERR_NOMEM;
-        ull* pivots = (ull*)h->ws_get(WS_PIVOTS, (size_t)tg * NTOP * MAXTD * 8);
-        uint32_t* fill = (uint32_t*)h->ws_get(WS_FILL, (size_t)tg * NTOP * 4);
-        double* binlo = (double*)h->ws_get(WS_BINLO, (size_t)tg * J.Lk * 8);
-        double* binscale = (double*)h->ws_get(WS_BINSC, (size_t)tg * J.Lk * 8);
-        if (!label || !pbin || !hist || !sel || !cand || !cand_total || !pivots || !fill || !binlo || !binscale) return RPF_ERR_NOMEM;
+        uint16_t* label = (uint16_t*)WSP(WS_LABEL, (size_t)tgw * n * 2);
+        uint16_t* pbin = (uint16_t*)WSP(WS_PBIN, (size_t)tgw * n * 2);
+        uint32_t* hist = (uint32_t*)WSP(WS_HIST, (size_t)tgw * HSZ * 4);
+        NodeSel* sel = (NodeSel*)WSP(WS_SEL, (size_t)tgw * NTOP * sizeof(NodeSel));
+        ull* cand = (ull*)WSP(WS_CAND, (size_t)tgw * n * 8);
+        uint32_t* cand_total = (uint32_t*)WSP(WS_CANDTOT, (size_t)tgw * 8 + 8);  // [tg] candidate totals + [tg] margin-tracking flags + 2 work-list lengths
+        uint32_t* wl = (uint32_t*)WSP(WS_WORKLIST, (size_t)tgw * max_lvl_nodes * 8);
+        ull* pivots = (ull*)WSP(WS_PIVOTS, (size_t)tgw * NTOP * MAXTD * 8);
+        uint32_t* fill = (uint32_t*)WSP(WS_FILL, (size_t)tgw * NTOP * 4);
+        double* binlo = (double*)WSP(WS_BINLO, (size_t)tgw * J.Lk * 8);
+        double* binscale = (double*)WSP(WS_BINSC, (size_t)tgw * J.Lk * 8);
+        if (!ws_ok) return RPF_ERR_NOMEM;
         TopArgs A{};
         A.n = n; A.ks = J.ks; A.ps = J.ps; A.Tg = tg; A.L = J.Lk; A.NTOP = (int)NTOP; A.HSZ = (int)HSZ; A.MAXTD = MAXTD; A.gt0 = J.gt0; A.nn_all = J.ns;
         A.vec = ((n & 3) == 0 && (J.ks & 3) == 0 && ((uintptr_t)J.keys & 31) == 0) ? 1 : 0;
@@ -2294,7 +2326,8 @@ int rpf_launch_job(rpf_handle* h, BuildJob& J, const JobPlan& P, const char* tab
         B.kmin = J.kmin; B.kmax = J.kmax;
         // With an export sink the trees go through the bottom phase in groups: a group's slice of perm is final when its
         // launch ends, so its D2H runs on the download stream while the next group is still sorting.
-        const int groups = (J.stream_to_sink && h->sink_perm && J.ps == n && tg >= 8) ? 8 : 1;
+        const bool to_sink = J.stream_to_sink && h->sink_perm && J.ps == n;
+        const int groups = to_sink ? std::max(1, std::min(J.sink_groups, tg)) : 1;
         for (int gi = 0; gi < groups; ++gi) {
             const int ta = (int)((int64_t)tg * gi / groups), tb = (int)((int64_t)tg * (gi + 1) / groups);
             if (tb <= ta) continue;
@@ -2303,14 +2336,14 @@ int rpf_launch_job(rpf_handle* h, BuildJob& J, const JobPlan& P, const char* tab
             if (Bg.kmin) { Bg.kmin += (int64_t)ta * J.Lk; Bg.kmax += (int64_t)ta * J.Lk; }
             int rc = rpf_bottom_launch(h, Bg, P.nnodes_s, tb - ta, G.fast_bottom, P.maxsize_s, G.bottom_levels);
             if (rc) return rc;
-            if (groups > 1) {
-                RPF_CUDA(h, cudaEventRecord(h->sink_ev[gi], h->stream));
-                RPF_CUDA(h, cudaStreamWaitEvent(h->d2h_stream, h->sink_ev[gi], 0));
+            if (to_sink) {
+                RPF_CUDA(h, cudaEventRecord(h->sink_ev[J.sink_ev0 + gi], h->stream));
+                RPF_CUDA(h, cudaStreamWaitEvent(h->d2h_stream, h->sink_ev[J.sink_ev0 + gi], 0));
                 RPF_CUDA(h, cudaMemcpyAsync(h->sink_perm + (int64_t)(J.gt0 + ta) * n, J.perm + (int64_t)ta * J.ps, (size_t)(tb - ta) * n * 4,
                                             cudaMemcpyDeviceToHost, h->d2h_stream));
             }
         }
-        if (groups > 1) h->sink_perm_streamed = true;
+        if (to_sink) h->sink_perm_streamed = true;
     }
     return RPF_OK;
 }
@@ -2439,6 +2472,15 @@ int rpf_build_impl(rpf_handle* h, const double* hostX) {
     }
     if (h->build_graph) { cudaGraphExecDestroy(h->build_graph); h->build_graph = nullptr; }
 
+    // concurrent branches per tree group (see rpf_handle::branch_stream): off while profiling (per-kernel event pairs want
+    // one stream) and for tiny inputs
+    int NB = 1;
+    if (!h->profiling && h->branches != 1 && Tg >= 2 && n >= 65536 && L > 0)
+        NB = h->branches >= 2 ? std::min(h->branches, RPF_MAX_BRANCH) : (Tg >= 16 ? 2 : std::min(Tg, RPF_MAX_BRANCH));
+    if (NB > 1 && !h->branch_stream[0]) {
+        for (int b = 0; b < RPF_MAX_BRANCH; ++b) RPF_CUDA(h, cudaStreamCreateWithFlags(&h->branch_stream[b], cudaStreamNonBlocking));
+        for (int b = 0; b <= RPF_MAX_BRANCH; ++b) RPF_CUDA(h, cudaEventCreateWithFlags(&h->branch_ev[b], cudaEventDisableTiming));
+    }
     // everything below only enqueues work on the engine's stream (no allocation once the workspace has its size)
     auto enqueue = [&]() -> int {
         RPF_CUDA(h, cudaMemsetAsync(h->d_thr, 0, h->res_node_bytes, h->stream));
@@ -2472,20 +2514,50 @@ int rpf_build_impl(rpf_handle* h, const double* hostX) {
                         int rc2 = rpf_project_launch(h, PH_PROJECT, h->dX + r0 * h->d, nr, t0, tg, L, true, keys + r0, n, kmin, kmax);
                         if (rc2) return rc2;
                     }
-                } else {
-                    int rc2 = rpf_project_launch(h, PH_PROJECT, h->dX, n, t0, tg, L, true, keys, n, kmin, kmax);
-                    if (rc2) return rc2;
                 }
             }
-            BuildJob J{};
-            J.tp = &tp; J.d_start = h->d_node_start; J.d_size = h->d_node_size; J.d_child = h->d_node_child;
-            J.n = n; J.ks = n; J.ps = n; J.ns = nn; J.Lk = L;
-            J.keys = keys; J.kmin = kmin; J.kmax = kmax;
-            J.perm = h->d_perm + (int64_t)t0 * n; J.thr = h->d_thr; J.mlo = h->d_mlo; J.mhi = h->d_mhi;
-            J.gt0 = t0; J.tg = tg;
-            J.stream_to_sink = sink;
-            int rc2 = rpf_launch_job(h, J, BP->P, BP->d_tab);
-            if (rc2) return rc2;
+            // the trees [ta, tb) of the group as one job
+            auto job = [&](int ta, int tb, int part, int parts, int ws_tg) -> int {
+                BuildJob J{};
+                J.tp = &tp; J.d_start = h->d_node_start; J.d_size = h->d_node_size; J.d_child = h->d_node_child;
+                J.n = n; J.ks = n; J.ps = n; J.ns = nn; J.Lk = L;
+                J.keys = keys + (int64_t)ta * L * n; J.kmin = kmin + (int64_t)ta * L; J.kmax = kmax + (int64_t)ta * L;
+                J.perm = h->d_perm + (int64_t)(t0 + ta) * n; J.thr = h->d_thr; J.mlo = h->d_mlo; J.mhi = h->d_mhi;
+                J.gt0 = t0 + ta; J.tg = tb - ta;
+                J.stream_to_sink = sink;
+                J.ws_part = part; J.ws_parts = parts; J.ws_tg = ws_tg;
+                J.sink_groups = std::max(1, 8 / parts); J.sink_ev0 = part * J.sink_groups;
+                return rpf_launch_job(h, J, BP->P, BP->d_tab);
+            };
+            if (L > 0 && n > 0 && !pipelined) {       // one pass over X for all trees of the group
+                int rc2 = rpf_project_launch(h, PH_PROJECT, h->dX, n, t0, tg, L, true, keys, n, kmin, kmax);
+                if (rc2) return rc2;
+            }
+            if (NB <= 1 || tg < 2) {
+                int rc2 = job(0, tg, 0, 1, 0);
+                if (rc2) return rc2;
+            } else {
+                // concurrent branches: contiguous parts of the group, each with its top and bottom phase on its own stream;
+                // forked from / joined on the engine's stream (captured into the build graph like everything else)
+                const int nb = std::min(NB, tg), per = (tg + nb - 1) / nb;
+                cudaStream_t main = h->stream;
+                RPF_CUDA(h, cudaEventRecord(h->branch_ev[RPF_MAX_BRANCH], main));
+                int rcb = RPF_OK, used = 0;
+                for (int b = 0; b < nb && rcb == RPF_OK; ++b) {
+                    const int ta = b * per, tb = std::min(tg, ta + per);
+                    if (tb <= ta) break;
+                    ++used;
+                    h->stream = h->branch_stream[b];
+                    cudaError_t e = cudaStreamWaitEvent(h->stream, h->branch_ev[RPF_MAX_BRANCH], 0);
+                    if (e != cudaSuccess) { rcb = rpf_fail(h, RPF_ERR_CUDA, std::string("branch fork: ") + cudaGetErrorString(e)); break; }
+                    rcb = job(ta, tb, b, nb, per);
+                    if (rcb == RPF_OK && cudaEventRecord(h->branch_ev[b], h->stream) != cudaSuccess) rcb = rpf_fail(h, RPF_ERR_CUDA, "branch join: event record");
+                }
+                h->stream = main;
+                for (int b = 0; b < used; ++b)       // always rejoin (a capture must end with every forked stream joined)
+                    if (cudaStreamWaitEvent(main, h->branch_ev[b], 0) != cudaSuccess && rcb == RPF_OK) rcb = rpf_fail(h, RPF_ERR_CUDA, "branch join: wait");
+                if (rcb) return rcb;
+            }
         }
         if (sink) {     // node arrays (and perm, unless the job streamed it group by group) once everything is final
             RPF_CUDA(h, cudaEventRecord(h->sink_ev[8], h->stream));

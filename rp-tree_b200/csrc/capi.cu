@@ -347,6 +347,8 @@ void rpf_destroy(rpf_handle* h) {
     if (h->stream_plan && h->stream_plan_free) h->stream_plan_free(h->stream_plan);
     if (h->build_graph) cudaGraphExecDestroy(h->build_graph);
     if (h->batch_plan && h->batch_plan_free) h->batch_plan_free(h->batch_plan);
+    for (auto e : h->branch_ev) if (e) cudaEventDestroy(e);
+    for (auto st : h->branch_stream) if (st) cudaStreamDestroy(st);
     for (auto e : h->copy_ev) if (e) cudaEventDestroy(e);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     for (auto e : h->sink_ev) if (e) cudaEventDestroy(e);
@@ -1118,6 +1120,9 @@ int rpf_set_option(rpf_handle* h, const char* name, int64_t value) {
     if (s == "force_simple_knn") { h->force_simple_knn = value != 0; return RPF_OK; }
     if (s == "no_query_order") { h->no_query_order = value != 0; return RPF_OK; }
     if (s == "project_variant") { h->project_variant = (int)value; return RPF_OK; }
+    if (s == "project_prefetch") { h->project_prefetch = (int)value; return RPF_OK; }
+    if (s == "project_pipe_maxh") { h->project_pipe_maxh = (int)value; return RPF_OK; }
+    if (s == "branches") { h->branches = (int)value; h->tg_cached = 0; return RPF_OK; }
     if (s == "release_workspace") { cudaStreamSynchronize(h->stream); h->ws_free_all(); h->tg_cached = 0; return RPF_OK; }
     return rpf_fail(h, RPF_ERR_ARG, "unknown option " + s);
 }

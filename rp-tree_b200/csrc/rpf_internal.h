@@ -64,6 +64,10 @@ struct BuildJob {
     double *thr = nullptr, *mlo = nullptr, *mhi = nullptr;   // [..][ns] out, indexed (gt0 + t) * ns + node
     int gt0 = 0, tg = 0;
     bool stream_to_sink = false;                // batch build from host with an export sink: copy perm per bottom tree group
+    int sink_ev0 = 0, sink_groups = 8;          // ... using the handle's events sink_ev[sink_ev0 .. sink_ev0 + sink_groups)
+    // concurrent branches (rpf_build_impl): this job uses slice ws_part of ws_parts equal workspace slices, each sized
+    // for ws_tg trees (0: tg)
+    int ws_part = 0, ws_parts = 1, ws_tg = 0;
     bool order_exact = true;                    // out: every leaf is in the reference's order
 };
 struct JobGeom {
@@ -97,6 +101,7 @@ struct JobPlan {
 // host -> device table staging: tables are written into page-locked memory and travel with one async copy per flush,
 // so planning the next job overlaps the kernels of the previous one (no stream synchronisation in the build loop)
 #define RPF_STAGE_SLOTS 8
+#define RPF_MAX_BRANCH 4
 struct StageSlot { char* h = nullptr; char* d = nullptr; size_t cap = 0; cudaEvent_t ev = nullptr; bool pending = false; };
 
 
@@ -120,6 +125,12 @@ struct rpf_handle {
     RpfGroup* group = nullptr;
     int64_t x_pad_rows = 0;              // rows allocated behind row n of dX (the in-place all-gather of the last row block may spill)
     cudaStream_t stream = nullptr;
+    // Batch build: the trees of a group are independent, so the group is cut into up to RPF_MAX_BRANCH contiguous parts whose
+    // top / bottom phases run as concurrent branches on these streams (joined on `stream`): the many small kernels of one
+    // branch (median pick / finish / ties) and the partial last waves of its big ones are filled by the other branches.
+    cudaStream_t branch_stream[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t branch_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // [0..3] branch done, [4] fork point
+    int branches = 0;                     // option "branches": 0 = chosen per build, 1 = off, 2..4 = forced
     cudaStream_t copy_stream = nullptr;   // rpf_build_from_host: row-block uploads overlapped with the projection
     cudaEvent_t copy_ev[17] = {nullptr};  // one per upload block + the "previous contents of dX are no longer read" event
     // export sink (rpf_set_export_sink): host buffers the forest is streamed into while rpf_build_from_host still runs --
@@ -158,6 +169,8 @@ struct rpf_handle {
     void* stream_plan = nullptr;         // cached plan of the last streaming build shape (stream.cu: StreamPlanAll)
     void (*stream_plan_free)(void*) = nullptr;
     size_t res_node_bytes = 0, res_perm_bytes = 0;
+    int project_prefetch = 1;            // option: L2 prefetch of a later tile in the single-buffer projection kernel
+    int project_pipe_maxh = 128;         // option: the pipelined projection kernel is used up to this many hyperplanes per launch
     int project_variant = 0;             // tuning hook: 0 = 1024 threads x 4 points/lane, 1 = 1024 x 2 (two CTAs/SM), 2 = 512 x 4
     bool no_query_order = false;         // test/tuning hook: answer queries in input order (no locality grouping)
     bool force_simple_topk = false;      // test hook: brute-force truth through the nine-pass radix select only
