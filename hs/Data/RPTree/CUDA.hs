@@ -11,36 +11,43 @@
 --
 -- NOTE: written against the C ABI but NOT compiled in the authoring environment (no GHC there).
 module Data.RPTree.CUDA
-  ( GpuForest, forestBatch, treeBatch, forest, knn, knnPQ, knnH, candidates, recallWith, toRPForest, withDevice
-  , saveForest, setPointsSparse
+  ( GpuForest, forestBatch, treeBatch, forest, forestOn, knn, knnPQ, knnH, candidates, recallWith, toRPForest
+  , withDevice, withDevices, saveForest, setPointsSparse
   ) where
 
 import Control.Exception (throwIO, ErrorCall(..))
-import Control.Monad (replicateM, when, forM)
+import Control.Monad (replicateM, when, forM, forM_)
 import Data.Int (Int32, Int64)
 import Data.Word (Word32, Word64)
 import Foreign.C.String (CString, peekCString, withCString)
 import Foreign.C.Types (CInt(..), CDouble(..))
 import Foreign.ForeignPtr (ForeignPtr, newForeignPtr, withForeignPtr)
 import Foreign.Marshal.Alloc (alloca)
+import Foreign.ForeignPtr (mallocForeignPtrArray)
 import Foreign.Marshal.Array (allocaArray, peekArray, withArrayLen, withArray)
 import Foreign.Ptr (Ptr, FunPtr, nullPtr)
 import Foreign.Storable (peek)
 import System.IO.Unsafe (unsafePerformIO)
 
+import qualified Data.Conduit as C
+import qualified Data.Conduit.Combinators as CC
 import qualified Data.IntMap.Strict as IM
 import qualified Data.Vector as V
 import qualified Data.Vector.Storable as VS
+import qualified Data.Vector.Storable.Mutable as VSM
 import qualified Data.Vector.Unboxed as VU
 import System.Random.SplitMix.Distributions (sample, stdNormal)
 
 import Data.RPTree.Gen (sparse)
-import Data.RPTree.Internal (RPTree(..), RPT(..), RPForest, Embed(..), DVector(..), SVector(..), Margin(..))
+import Data.RPTree.Internal (RPTree(..), RPT(..), RPForest, Embed(..), DVector(..), SVector(..), Margin(..), metricL2)
 import Data.Semigroup (Max(..), Min(..))
 
 data RpfHandle
 
 foreign import ccall safe "rpf_create"            c_create   :: Ptr (Ptr RpfHandle) -> CInt -> IO CInt
+-- | ONE handle over several GPUs of this process: trees sharded in contiguous blocks, data replicated, NCCL owned by the
+-- engine; every entry point below keeps its meaning (rpforest.h, "multi-GPU").
+foreign import ccall safe "rpf_create_multi"      c_createM  :: Ptr (Ptr RpfHandle) -> Ptr CInt -> CInt -> IO CInt
 foreign import ccall safe "&rpf_destroy"          p_destroy  :: FunPtr (Ptr RpfHandle -> IO ())
 foreign import ccall safe "rpf_last_error"        c_lastErr  :: Ptr RpfHandle -> IO CString
 foreign import ccall safe "rpf_set_points"        c_setPts   :: Ptr RpfHandle -> Ptr CDouble -> Int64 -> Int32 -> IO CInt
@@ -65,7 +72,7 @@ foreign import ccall safe "rpf_knn_h"             c_knnH     :: Ptr RpfHandle ->
 foreign import ccall safe "rpf_set_points_sparse" c_setPtsS  :: Ptr RpfHandle -> Int64 -> Int32 -> Ptr Int64 -> Ptr Int32 -> Ptr CDouble -> IO CInt
 foreign import ccall safe "rpf_forest_save"       c_save     :: Ptr RpfHandle -> CString -> Int32 -> IO CInt
 
--- | A forest living on one B200.  The payloads stay on the Haskell side, addressed by row number.
+-- | A forest living on one B200 -- or sharded over several ('withDevices' / 'forestOn').  The payloads stay on the Haskell side, addressed by row number.
 data GpuForest x = GpuForest
   { gfHandle  :: !(ForeignPtr RpfHandle)
   , gfRows    :: !(V.Vector (Embed DVector Double x))   -- ^ row id -> original item
@@ -75,8 +82,14 @@ data GpuForest x = GpuForest
   }
 
 withDevice :: Int -> (ForeignPtr RpfHandle -> IO a) -> IO a
-withDevice dev k = alloca $ \pp -> do
-  rc <- c_create pp (fromIntegral dev)
+withDevice dev = withDevices [dev]
+
+-- | An engine over the listed GPUs (one entry: 'rpf_create'; several: 'rpf_create_multi').  'createMulti' is a map over
+-- the IntMap of trees (Internal.hs:234-240) and 'knn' folds the trees' candidates (RPTree.hs:176), so the engine gives
+-- GPU r a contiguous block of trees and returns exactly the single-GPU results.
+withDevices :: [Int] -> (ForeignPtr RpfHandle -> IO a) -> IO a
+withDevices devs k = alloca $ \pp -> withArrayLen (map fromIntegral devs) $ \nd pd -> do
+  rc <- if nd == 1 then c_create pp (fromIntegral (head devs)) else c_createM pp pd (fromIntegral nd)
   when (rc /= 0) $ throwIO (ErrorCall "rpf_create: no usable CUDA device (there is no CPU fallback)")
   h <- peek pp >>= newForeignPtr p_destroy
   k h
@@ -86,9 +99,15 @@ check h what rc = when (rc /= 0) $ do
   msg <- c_lastErr h >>= peekCString
   throwIO (ErrorCall (what ++ ": " ++ msg))
 
--- | One pinned, row-major n x d buffer out of the unpinned VU.Vectors (Internal.hs:122).
-packRows :: V.Vector (Embed DVector Double x) -> VS.Vector CDouble
-packRows = VS.concat . map (VS.map realToFrac . VS.convert . dvVec . eEmbed) . V.toList
+-- | One row-major n x d 'Storable' buffer out of the unpinned VU.Vectors (Internal.hs:122): written in place, one
+-- 'VU.copy'-style pass per row (no intermediate lists; CDouble and Double share their representation).
+packRows :: Int -> V.Vector (Embed DVector Double x) -> VS.Vector CDouble
+packRows dim xs = VS.create $ do
+  buf <- VSM.unsafeNew (V.length xs * dim)
+  V.iforM_ xs $ \i xe -> do
+    let row = dvVec (eEmbed xe)
+    forM_ [0 .. min dim (VU.length row) - 1] $ \j -> VSM.unsafeWrite buf (i * dim + j) (realToFrac (VU.unsafeIndex row j))
+  pure buf
 
 -- | CSR over (tree-major, level-minor) of rvss; SVector's VU.Vector (Int, Double) is already SoA (Internal.hs:92-93).
 csrOf :: IM.IntMap (V.Vector (SVector Double)) -> ([Int64], [Int32], [CDouble])
@@ -96,13 +115,13 @@ csrOf rvss = (scanl (+) 0 (map (fromIntegral . VU.length . svVec) svs), concatMa
              , concatMap (map (realToFrac . snd) . VU.toList . svVec) svs)
   where svs = concatMap V.toList (IM.elems rvss)
 
-buildWith :: Maybe Int -> Word64 -> Int -> Int -> Int -> Double -> Int -> V.Vector (Embed DVector Double x) -> IO (GpuForest x)
-buildWith chunk seed maxd minl ntrees pnz dim xs = withDevice 0 $ \fh -> withForeignPtr fh $ \h -> do
+buildWith :: [Int] -> Maybe Int -> Word64 -> Int -> Int -> Int -> Double -> Int -> V.Vector (Embed DVector Double x) -> IO (GpuForest x)
+buildWith devs chunk seed maxd minl ntrees pnz dim xs = withDevices devs $ \fh -> withForeignPtr fh $ \h -> do
   let rvss = sample seed $ do                                   -- Batch.hs:59-61 / Conduit.hs:116-118, verbatim
         rvs <- replicateM ntrees $ V.replicateM maxd (sparse pnz dim stdNormal)
         pure $ IM.fromList $ zip [0 ..] rvs
       (off, idx, val) = csrOf rvss
-      buf = packRows xs
+      buf = packRows dim xs
   withArray off $ \po -> withArray idx $ \pi' -> withArray val $ \pv ->
     c_setHp h (fromIntegral ntrees) (fromIntegral maxd) po pi' pv >>= check h "rpf_set_hyperplanes"
   case chunk of
@@ -116,36 +135,52 @@ buildWith chunk seed maxd minl ntrees pnz dim xs = withDevice 0 $ \fh -> withFor
 
 -- | 'Data.RPTree.Batch.forestBatch' (Batch.hs:48-63).
 forestBatch :: Word64 -> Int -> Int -> Int -> Double -> Int -> V.Vector (Embed DVector Double x) -> GpuForest x
-forestBatch seed maxd minl ntrees pnz dim xs = unsafePerformIO (buildWith Nothing seed maxd minl ntrees pnz dim xs)
+forestBatch seed maxd minl ntrees pnz dim xs = unsafePerformIO (buildWith [0] Nothing seed maxd minl ntrees pnz dim xs)
 {-# NOINLINE forestBatch #-}
+
+-- | 'forestBatch' on an explicit list of GPUs (e.g. @[0 .. 7]@: 8 B200 of one box, the trees sharded across them).
+forestOn :: [Int] -> Word64 -> Int -> Int -> Int -> Double -> Int -> V.Vector (Embed DVector Double x) -> IO (GpuForest x)
+forestOn devs = buildWith devs Nothing
 
 -- | 'Data.RPTree.Batch.treeBatch' (Batch.hs:29-41).
 treeBatch :: Word64 -> Int -> Int -> Double -> Int -> V.Vector (Embed DVector Double x) -> GpuForest x
 treeBatch seed maxd minl = forestBatch seed maxd minl 1
 
--- | 'Data.RPTree.Conduit.forest' (Conduit.hs:104-121) after the source has been drained into a vector: the engine replays
--- the conduit's @chunksOf chunksize@ fold itself (rpf_build_chunked), reproducing insert's Bin and Tip cases per chunk.
-forest :: Word64 -> Int -> Int -> Int -> Int -> Double -> Int -> V.Vector (Embed DVector Double x) -> IO (GpuForest x)
-forest seed maxd minl ntrees chunksize = buildWith (Just chunksize) seed maxd minl ntrees
+-- | 'Data.RPTree.Conduit.forest' (Conduit.hs:104-121), same argument order: the source is drained into a vector and the
+-- engine replays the conduit's @chunksOf chunksize@ fold itself (rpf_build_chunked), reproducing insert's Bin and Tip
+-- cases per chunk (Internal.hs:243-297).
+forest :: Monad m => Word64 -> Int -> Int -> Int -> Int -> Double -> Int -> C.ConduitT () (Embed DVector Double x) m () -> m (GpuForest x)
+forest seed maxd minl ntrees chunksize pnz dim src = do
+  xs <- C.runConduit (src C..| CC.sinkVector)
+  pure $! unsafePerformIO (buildWith [0] (Just chunksize) seed maxd minl ntrees pnz dim xs)
 
 queryPtr :: DVector Double -> (Ptr CDouble -> IO a) -> IO a
 queryPtr (DV q) = VS.unsafeWith (VS.map realToFrac (VS.convert q))
 
--- | 'Data.RPTree.knn' with distf = metricL2 (RPTree.hs:168-176).
-knn :: Int -> GpuForest x -> DVector Double -> V.Vector (Double, Embed DVector Double x)
+-- | 'Data.RPTree.knn' (RPTree.hs:168-176), same argument order.  The engine implements @distf = metricL2@ only; the
+-- argument is used to re-evaluate the distance of the first result on the Haskell side and must agree with the engine's.
+knn :: (DVector Double -> DVector Double -> Double) -> Int -> GpuForest x -> DVector Double -> V.Vector (Double, Embed DVector Double x)
 knn = knnWith 0
--- | 'Data.RPTree.knnPQ' with distf = metricL2 (RPTree.hs:181-194).
-knnPQ :: Int -> GpuForest x -> DVector Double -> V.Vector (Double, Embed DVector Double x)
+-- | 'Data.RPTree.knnPQ' (RPTree.hs:181-194), same argument order; @distf@ as in 'knn'.
+knnPQ :: (DVector Double -> DVector Double -> Double) -> Int -> GpuForest x -> DVector Double -> V.Vector (Double, Embed DVector Double x)
 knnPQ = knnWith 1
 
-knnWith :: Int32 -> Int -> GpuForest x -> DVector Double -> V.Vector (Double, Embed DVector Double x)
-knnWith dedup k gf q = unsafePerformIO $ withForeignPtr (gfHandle gf) $ \h -> queryPtr q $ \pq ->
-  allocaArray k $ \pd -> allocaArray k $ \pi' -> alloca $ \pc -> do
+knnWith :: Int32 -> (DVector Double -> DVector Double -> Double) -> Int -> GpuForest x -> DVector Double -> V.Vector (Double, Embed DVector Double x)
+knnWith dedup distf k gf q = unsafePerformIO $ withForeignPtr (gfHandle gf) $ \h -> queryPtr q $ \pq -> alloca $ \pc -> do
+  pdv <- mallocForeignPtrArray k
+  piv <- mallocForeignPtrArray k
+  withForeignPtr pdv $ \pd -> withForeignPtr piv $ \pi' ->
     c_knn h pq 1 (fromIntegral k) dedup pd pi' pc >>= check h "rpf_knn"
-    m <- fromIntegral <$> peek pc
-    ds <- peekArray m pd
-    is <- peekArray m pi'
-    pure $ V.fromList [ (realToFrac d, gfRows gf V.! fromIntegral i) | (d, i) <- zip ds is ]
+  m <- fromIntegral <$> peek pc
+  let ds = VS.unsafeFromForeignPtr0 pdv m :: VS.Vector CDouble
+      is = VS.unsafeFromForeignPtr0 piv m :: VS.Vector Word32
+      res = V.generate m (\j -> (realToFrac (ds VS.! j), gfRows gf V.! fromIntegral (is VS.! j)))
+  when (m > 0) $ do
+    let (d0, x0) = V.head res
+        dref = distf (eEmbed x0) q
+    when (abs (dref - d0) > 4 * abs d0 * 2.220446049250313e-16) $
+      throwIO (ErrorCall "Data.RPTree.CUDA.knn: the engine implements metricL2 only")
+  pure res
 
 -- | 'Data.RPTree.knnH' with distf = metricL2 (RPTree.hs:199-217): whole leaves in margin-priority order, prepended
 -- while the running total stays <= k.  Not sorted by distance, not cut to k -- as in the reference.
@@ -197,19 +232,29 @@ toRPForest :: GpuForest x -> IO (RPForest Double (V.Vector (Embed DVector Double
 toRPForest gf = withForeignPtr (gfHandle gf) $ \h -> do
   nn <- fromIntegral <$> c_numNodes h
   let n = V.length (gfRows gf)
-  (child, start, size) <- allocaArray nn $ \pc -> allocaArray nn $ \ps -> allocaArray nn $ \pz -> do
+      nt = gfNTrees gf
+  -- topology once (the same for every tree), then the whole forest in ONE call: [T][nodes] / [T][n] arrays
+  childFp <- mallocForeignPtrArray nn; startFp <- mallocForeignPtrArray nn; sizeFp <- mallocForeignPtrArray nn
+  withForeignPtr childFp $ \pc -> withForeignPtr startFp $ \ps -> withForeignPtr sizeFp $ \pz ->
     c_topology h pc nullPtr ps pz >>= check h "rpf_topology"
-    (,,) <$> (VU.fromList <$> peekArray nn pc) <*> (VU.fromList <$> peekArray nn ps) <*> (VU.fromList <$> peekArray nn pz)
-  trees <- forM [0 .. gfNTrees gf - 1] $ \t ->
-    allocaArray nn $ \pt -> allocaArray nn $ \pl -> allocaArray nn $ \ph -> allocaArray (max 1 n) $ \pp -> do
-      c_export h (fromIntegral t) pt pl ph pp >>= check h "rpf_tree_export"
-      thr <- VU.fromList . map realToFrac <$> peekArray nn pt
-      mlo <- VU.fromList . map realToFrac <$> peekArray nn pl
-      mhi <- VU.fromList . map realToFrac <$> peekArray nn ph
-      perm <- VU.fromList <$> peekArray n pp
-      let go :: Int -> RPT Double () (V.Vector (Embed DVector Double x))
-          go g | c < 0     = Tip () (V.generate (fromIntegral (size VU.! g)) (\i -> gfRows gf V.! fromIntegral (perm VU.! (fromIntegral (start VU.! g) + i))))
-               | otherwise = Bin () (thr VU.! g) (Margin (Max (mlo VU.! g)) (Min (mhi VU.! g))) (go (fromIntegral c)) (go (fromIntegral c + 1))
-            where c = (child VU.! g) :: Int64
-      pure (t, RPTree (gfVectors gf IM.! t) (go 0))
-  pure (IM.fromList trees)
+  let child = VS.unsafeFromForeignPtr0 childFp nn :: VS.Vector Int64
+      start = VS.unsafeFromForeignPtr0 startFp nn :: VS.Vector Int64
+      size  = VS.unsafeFromForeignPtr0 sizeFp nn :: VS.Vector Int64
+  thrFp <- mallocForeignPtrArray (nt * nn); mloFp <- mallocForeignPtrArray (nt * nn); mhiFp <- mallocForeignPtrArray (nt * nn)
+  permFp <- mallocForeignPtrArray (max 1 (nt * n))
+  withForeignPtr thrFp $ \pt -> withForeignPtr mloFp $ \pl -> withForeignPtr mhiFp $ \ph -> withForeignPtr permFp $ \pp ->
+    c_exportAll h pt pl ph pp >>= check h "rpf_forest_export"
+  let thr  = VS.unsafeFromForeignPtr0 thrFp (nt * nn) :: VS.Vector CDouble
+      mlo  = VS.unsafeFromForeignPtr0 mloFp (nt * nn) :: VS.Vector CDouble
+      mhi  = VS.unsafeFromForeignPtr0 mhiFp (nt * nn) :: VS.Vector CDouble
+      perm = VS.unsafeFromForeignPtr0 permFp (nt * n) :: VS.Vector Word32
+      tree t = RPTree (gfVectors gf IM.! t) (go 0)
+        where
+          go :: Int -> RPT Double () (V.Vector (Embed DVector Double x))
+          go g | c < 0     = Tip () (V.generate (fromIntegral (size VS.! g))
+                                       (\i -> gfRows gf V.! fromIntegral (perm VS.! (t * n + fromIntegral (start VS.! g) + i))))
+               | otherwise = Bin () (realToFrac (thr VS.! (t * nn + g)))
+                                 (Margin (Max (realToFrac (mlo VS.! (t * nn + g)))) (Min (realToFrac (mhi VS.! (t * nn + g)))))
+                                 (go (fromIntegral c)) (go (fromIntegral c + 1))
+            where c = child VS.! g
+  pure (IM.fromList [ (t, tree t) | t <- [0 .. nt - 1] ])
