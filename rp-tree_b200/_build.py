@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "librpforest.so")
-SOURCES = ["capi.cu", "build.cu", "stream.cu", "query.cu", "multi.cu"]
+SOURCES = ["capi.cu", "build.cu", "stream.cu", "query.cu", "multi.cu", "rerank.cu"]
 HEADERS = [os.path.join(CSRC, "rpf_internal.h"), os.path.join(HERE, "..", "include", "rpforest.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default"]

@@ -2400,7 +2400,7 @@ static int get_batch_plan(rpf_handle* h, int L, BatchPlan** out) {
 // forest (data replicated): this rank copies only ITS 1/W sub-block over its own PCIe link and the sub-blocks are
 // all-gathered in place over NCCL / NVLink (the last sub-block may spill past row r0 + nr: dX carries x_pad_rows spare rows,
 // and a later block overwrites its own range afterwards on the same stream).
-int rpf_upload_rows(rpf_handle* h, const double* hostX, int64_t r0, int64_t nr, cudaStream_t stream) {
+int rpf_upload_rows(rpf_handle* h, const double* hostX, int64_t r0, int64_t nr, cudaStream_t stream, cudaStream_t gather_stream, cudaEvent_t up_ev) {
     const int W = rpf_comm_world(h), R = rpf_comm_rank(h);
     const size_t rb = (size_t)h->d * 8;
     if (W <= 1) {
@@ -2411,6 +2411,11 @@ int rpf_upload_rows(rpf_handle* h, const double* hostX, int64_t r0, int64_t nr, 
     if (h->x_pad_rows < W) return rpf_fail(h, RPF_ERR_STATE, "upload_rows: point buffer has no all-gather padding");
     const int64_t a = std::min(nr, R * sub), b = std::min(nr, a + sub);
     if (b > a) RPF_CUDA(h, cudaMemcpyAsync((void*)(h->dX + (r0 + a) * h->d), hostX + (r0 + a) * h->d, (size_t)(b - a) * rb, cudaMemcpyHostToDevice, stream));
+    if (gather_stream && gather_stream != stream) {      // PCIe copies and NVLink all-gathers on separate streams: block b + 1
+        RPF_CUDA(h, cudaEventRecord(up_ev, stream));     // crosses PCIe while block b is being gathered
+        RPF_CUDA(h, cudaStreamWaitEvent(gather_stream, up_ev, 0));
+        stream = gather_stream;
+    }
     return rpf_comm_allgather(h, (void*)(h->dX + r0 * h->d), (size_t)sub * rb, stream);
 }
 
@@ -2504,12 +2509,19 @@ int rpf_build_impl(rpf_handle* h, const double* hostX) {
                     if (!h->copy_ev[0]) for (int i = 0; i <= NBLK; ++i) RPF_CUDA(h, cudaEventCreateWithFlags(&h->copy_ev[i], cudaEventDisableTiming));
                     RPF_CUDA(h, cudaEventRecord(h->copy_ev[NBLK], h->stream));
                     RPF_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->copy_ev[NBLK], 0));
+                    const bool multi = rpf_comm_world(h) > 1;
+                    if (multi && !h->gather_stream) {
+                        RPF_CUDA(h, cudaStreamCreateWithFlags(&h->gather_stream, cudaStreamNonBlocking));
+                        for (auto& e : h->up_ev) RPF_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                    }
+                    cudaStream_t gs = multi ? h->gather_stream : h->copy_stream;
                     int bi = 0;
                     for (int64_t r0 = 0; r0 < n; r0 += rows, ++bi) {
                         const int64_t nr = std::min(rows, n - r0);
-                        int rcu = rpf_upload_rows(h, hostX, r0, nr, h->copy_stream);   // rank of a sharded forest: 1/W of the block over PCIe + NVLink all-gather
+                        // rank of a sharded forest: 1/W of the block over PCIe (copy stream), NVLink all-gather (gather stream)
+                        int rcu = rpf_upload_rows(h, hostX, r0, nr, h->copy_stream, gs, multi ? h->up_ev[bi] : nullptr);
                         if (rcu) return rcu;
-                        RPF_CUDA(h, cudaEventRecord(h->copy_ev[bi], h->copy_stream));
+                        RPF_CUDA(h, cudaEventRecord(h->copy_ev[bi], gs));
                         RPF_CUDA(h, cudaStreamWaitEvent(h->stream, h->copy_ev[bi], 0));
                         int rc2 = rpf_project_launch(h, PH_PROJECT, h->dX + r0 * h->d, nr, t0, tg, L, true, keys + r0, n, kmin, kmax);
                         if (rc2) return rc2;

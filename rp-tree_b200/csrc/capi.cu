@@ -351,6 +351,8 @@ void rpf_destroy(rpf_handle* h) {
     for (auto st : h->branch_stream) if (st) cudaStreamDestroy(st);
     for (auto e : h->copy_ev) if (e) cudaEventDestroy(e);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    for (auto e : h->up_ev) if (e) cudaEventDestroy(e);
+    if (h->gather_stream) cudaStreamDestroy(h->gather_stream);
     for (auto e : h->sink_ev) if (e) cudaEventDestroy(e);
     if (h->d2h_stream) { cudaStreamSynchronize(h->d2h_stream); cudaStreamDestroy(h->d2h_stream); }
     h->ws_free_all();
@@ -1120,6 +1122,7 @@ int rpf_set_option(rpf_handle* h, const char* name, int64_t value) {
     if (s == "force_simple_knn") { h->force_simple_knn = value != 0; return RPF_OK; }
     if (s == "no_query_order") { h->no_query_order = value != 0; return RPF_OK; }
     if (s == "project_variant") { h->project_variant = (int)value; return RPF_OK; }
+    if (s == "rerank_gemm") { h->rerank_gemm = (int)value; return RPF_OK; }
     if (s == "project_prefetch") { h->project_prefetch = (int)value; return RPF_OK; }
     if (s == "project_pipe_maxh") { h->project_pipe_maxh = (int)value; return RPF_OK; }
     if (s == "branches") { h->branches = (int)value; h->tg_cached = 0; return RPF_OK; }

@@ -1004,6 +1004,70 @@ __global__ void __launch_bounds__(KNN_NT) k_merge(int G, int64_t nq, int k, int 
     if (tid == 0 && count_out) count_out[q] = (int32_t)nbest;
 }
 
+// The same merge without a sort, for dedup = 0: every rank's list is already ordered by (distance, position), so the place
+// of element (g, j) in the merged order is j + sum over the other lists of the number of their elements that precede it --
+// all elements with a smaller distance, and on equal distances those of LOWER ranks (rank order = tree order,
+// RPTree.hs:174-176).  Two binary searches per (element, other list) in shared memory; one CTA per query.
+#define MR_NT 128
+__global__ void __launch_bounds__(MR_NT) k_merge_rank(int G, int64_t nq, int k, const double* __restrict__ dist,
+                                                      const uint32_t* __restrict__ ids, const int32_t* __restrict__ count,
+                                                      int64_t sd, int64_t si, int64_t sc,
+                                                      double* __restrict__ dist_out, uint32_t* __restrict__ ids_out, int32_t* __restrict__ count_out) {
+    extern __shared__ unsigned char dyn[];
+    ull* sk = (ull*)dyn;                         // [G][k] distance bits (non-negative doubles: bit order == value order)
+    int* scnt = (int*)(sk + (size_t)G * k);      // [G]
+    const int64_t q = blockIdx.x;
+    const int tid = threadIdx.x;
+    for (int g = tid; g < G; g += MR_NT) scnt[g] = min(k, max(0, count[(int64_t)g * sc + q]));
+    __syncthreads();
+    for (int e = tid; e < G * k; e += MR_NT) {
+        const int g = e / k, j = e % k;
+        sk[e] = j < scnt[g] ? (ull)__double_as_longlong(dist[(int64_t)g * sd + q * k + j]) : ~0ull;
+    }
+    __syncthreads();
+    int total = 0;
+    for (int g = 0; g < G; ++g) total += scnt[g];
+    const int nres = min(total, k);
+    for (int e = tid; e < G * k; e += MR_NT) {
+        const int g = e / k, j = e % k;
+        if (j >= scnt[g]) continue;
+        const ull key = sk[e];
+        int rank = j;
+        for (int g2 = 0; g2 < G && rank < k; ++g2) {
+            if (g2 == g) continue;
+            const ull* l = sk + (size_t)g2 * k;
+            int lo = 0, hi = scnt[g2];
+            if (g2 < g) { while (lo < hi) { const int mid = (lo + hi) >> 1; if (l[mid] <= key) lo = mid + 1; else hi = mid; } }   // # <= key
+            else        { while (lo < hi) { const int mid = (lo + hi) >> 1; if (l[mid] <  key) lo = mid + 1; else hi = mid; } }   // # <  key
+            rank += lo;
+        }
+        if (rank < k) {
+            dist_out[q * k + rank] = __longlong_as_double((long long)key);
+            ids_out[q * k + rank] = ids[(int64_t)g * si + q * k + j];
+        }
+    }
+    for (int i = nres + tid; i < k; i += MR_NT) {
+        dist_out[q * k + i] = __longlong_as_double(0x7ff0000000000000LL);
+        ids_out[q * k + i] = 0xffffffffu;
+    }
+    if (tid == 0 && count_out) count_out[q] = nres;
+}
+
+// both merges behind one launch site
+static int launch_merge(rpf_handle* h, int G, int64_t nq, int k, int dedup, const double* dd, const uint32_t* di, const int32_t* dc,
+                        int64_t sd, int64_t si, int64_t sc, double* od, uint32_t* oi, int32_t* oc) {
+    const size_t dynr = (size_t)G * k * 8 + (size_t)G * 4 + 16;
+    if (!dedup && dynr <= 96 * 1024) {
+        RPF_CUDA(h, cudaFuncSetAttribute(k_merge_rank, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dynr));
+        RPF_LAUNCH(h, PH_MERGE, k_merge_rank, (unsigned)nq, MR_NT, dynr, G, nq, k, dd, di, dc, sd, si, sc, od, oi, oc);
+        return RPF_OK;
+    }
+    const size_t dynm = (size_t)KNN_BUF * 16;
+    RPF_CUDA(h, cudaFuncSetAttribute(k_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dynm));
+    RPF_LAUNCH(h, PH_MERGE, k_merge, (unsigned)nq, KNN_NT, dynm, G, nq, k, dedup, dd, di, dc, sd, si, sc, od, oi, oc);
+    return RPF_OK;
+}
+
 // recall sums of the ranks (rank-major [G][stride]) added in rank order = tree order (left fold, like the reference's sum)
 __global__ void k_sum_ranks(const double* __restrict__ part, int G, int64_t stride, int64_t nq, double* __restrict__ out) {
     const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1114,7 +1178,18 @@ int rpf_knn_impl(rpf_handle* h, const double* Q, const int32_t* q_last, int64_t 
     }
     QArgs A = make_qargs(h, nq, st);
     A.k = k; A.dedup = dedup; A.dist = ddist; A.ids = dids; A.count = dcount;
-    if (nq >= 64 && !h->no_query_order) {
+    // long rows, many queries per leaf: leaf-grouped GEMM on the FP64 tensor cores selects, exact recompute of the survivors
+    // (rerank.cu); the few queries it cannot settle (massive distance ties) go through the gather kernel below
+    unsigned grid_q = (unsigned)nq;
+    bool run_gather = true;
+    if (rpf_rerank_gemm_wanted(h, nq, k, dedup)) {
+        uint32_t nfb = 0;
+        int rcg = rpf_rerank_gemm(h, st.dQ, nq, st.S, st.segs, st.cnt, k, ddist, dids, dcount, &nfb);
+        if (rcg) return rcg;
+        run_gather = nfb > 0;
+        grid_q = nfb;
+        A.order = (const uint32_t*)h->ws[WS_RR_FB].p;
+    } else if (nq >= 64 && !h->no_query_order) {
         QWS(h, qhist, uint32_t, WS_QHIST, (size_t)QO_BUCKETS * 4);
         QWS(h, qorder, uint32_t, WS_QORDER, (size_t)nq * 4);
         RPF_CUDA(h, cudaMemsetAsync(qhist, 0, (size_t)QO_BUCKETS * 4, h->stream));
@@ -1130,24 +1205,24 @@ int rpf_knn_impl(rpf_handle* h, const double* Q, const int32_t* q_last, int64_t 
     const size_t dyn_tma = (size_t)KT_STAGES * rows * pitch + (size_t)(KT_BUF + KT_SREG) * 16 + (size_t)2 * KT_BUF * 4 + tail;
     const bool use_tma = (h->d % 2 == 0) && rows >= 1 && k <= KT_BUF / 2 && dyn_tma <= 112 * 1024 && !h->force_simple_knn &&
                          (((uintptr_t)h->dX & 15) == 0) && !h->d_xlast;     // SVector data: per-candidate prefix lengths -> gather kernel
-    if (use_tma) {
+    if (!run_gather) {
+    } else if (use_tma) {
         RPF_CUDA(h, cudaFuncSetAttribute(k_knn_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_tma));
         RPF_CUDA(h, cudaFuncSetAttribute(k_knn_tma, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        RPF_LAUNCH(h, PH_Q_KNN, k_knn_tma, (unsigned)nq, KT_NT, dyn_tma, A, rows, pitch);
+        RPF_LAUNCH(h, PH_Q_KNN, k_knn_tma, grid_q, KT_NT, dyn_tma, A, rows, pitch);
     } else {
         const size_t dyn = (size_t)(KNN_BUF + KNN_SREG) * 16 + tail;
         if (dyn > 200 * 1024) return rpf_fail(h, RPF_ERR_UNSUPPORTED, "knn: d / tree count too large for the query kernel's shared memory");
         RPF_CUDA(h, cudaFuncSetAttribute(k_knn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-        RPF_LAUNCH(h, PH_Q_KNN, k_knn, (unsigned)nq, KNN_NT, dyn, A);
+        RPF_LAUNCH(h, PH_Q_KNN, k_knn, grid_q, KNN_NT, dyn, A);
     }
     if (W > 1) {
         int rcx = rpf_comm_allgather(h, xbuf, chunk, h->stream);
         if (rcx) return rcx;
         if (dist) {      // ranks that want the result (all of them in a multi-process job, rank 0 of an in-process group)
-            const size_t dynm = (size_t)KNN_BUF * 16;
-            RPF_CUDA(h, cudaFuncSetAttribute(k_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dynm));
-            RPF_LAUNCH(h, PH_MERGE, k_merge, (unsigned)nq, KNN_NT, dynm, W, nq, k, dedup, (const double*)xbuf, (const uint32_t*)(xbuf + off_i),
-                       (const int32_t*)(xbuf + off_c), (int64_t)(chunk / 8), (int64_t)(chunk / 4), (int64_t)(chunk / 4), wdist, wids, wcount);
+            int rcm = launch_merge(h, W, nq, k, dedup, (const double*)xbuf, (const uint32_t*)(xbuf + off_i), (const int32_t*)(xbuf + off_c),
+                                   (int64_t)(chunk / 8), (int64_t)(chunk / 4), (int64_t)(chunk / 4), wdist, wids, wcount);
+            if (rcm) return rcm;
             ddist = wdist; dids = wids; dcount = wcount;
         }
     }
@@ -1332,9 +1407,8 @@ int rpf_merge_impl(rpf_handle* h, int G, int64_t nq, int k, int dedup, const dou
     QWS(h, od, double, WS_OUT_D, (size_t)nq * k * 8);
     QWS(h, oi, uint32_t, WS_OUT_I, (size_t)nq * k * 4);
     QWS(h, oc, int32_t, WS_OUT_C, (size_t)nq * 4);
-    const size_t dynm = (size_t)KNN_BUF * 16;
-    RPF_CUDA(h, cudaFuncSetAttribute(k_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dynm));
-    RPF_LAUNCH(h, PH_MERGE, k_merge, (unsigned)nq, KNN_NT, dynm, G, nq, k, dedup, dd, di, dc, nq * k, nq * k, nq, od, oi, oc);
+    int rcm = launch_merge(h, G, nq, k, dedup, dd, di, dc, nq * k, nq * k, nq, od, oi, oc);
+    if (rcm) return rcm;
     RPF_CUDA(h, cudaMemcpyAsync(dist_out, od, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, h->stream));
     RPF_CUDA(h, cudaMemcpyAsync(ids_out, oi, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, h->stream));
     if (count_out) RPF_CUDA(h, cudaMemcpyAsync(count_out, oc, (size_t)nq * 4, cudaMemcpyDeviceToHost, h->stream));

@@ -112,6 +112,7 @@ enum rpf_ws_slot {
     WS_Q, WS_KEYSQ, WS_SEGS, WS_CNT, WS_MAXCNT, WS_OUT_D, WS_OUT_I, WS_OUT_C, WS_BF_D, WS_TRUTH_D, WS_TRUTH_I, WS_RECALL,
     WS_CANDCNT, WS_CANDOFF, WS_CANDOUT, WS_MRG_D, WS_MRG_I, WS_MRG_C, WS_QHIST, WS_QORDER,
     WS_S_ARENA0, WS_S_ARENA1, WS_S_CPERM, WS_S_TMPN, WS_S_POOL, WS_QLAST, WS_PRIO, WS_WORKLIST, WS_PBIN, WS_BF_CV, WS_BF_CI, WS_BF_AUX,
+    WS_RR_LEAVES, WS_RR_XN, WS_RR_QN, WS_RR_HIST, WS_RR_START, WS_RR_CC, WS_RR_QOFF, WS_RR_AUX, WS_RR_FB, WS_RR_ENTQ, WS_RR_ENTD, WS_RR_DAP,
     WS_COUNT
 };
 struct WsBuf { void* p = nullptr; size_t cap = 0; };
@@ -133,6 +134,8 @@ struct rpf_handle {
     int branches = 0;                     // option "branches": 0 = chosen per build, 1 = off, 2..4 = forced
     cudaStream_t copy_stream = nullptr;   // rpf_build_from_host: row-block uploads overlapped with the projection
     cudaEvent_t copy_ev[17] = {nullptr};  // one per upload block + the "previous contents of dX are no longer read" event
+    cudaStream_t gather_stream = nullptr; // communicator rank: the NVLink all-gathers of the row blocks (PCIe copies stay on copy_stream)
+    cudaEvent_t up_ev[16] = {nullptr};    // block b's PCIe part has landed
     // export sink (rpf_set_export_sink): host buffers the forest is streamed into while rpf_build_from_host still runs --
     // the bottom phase is launched in tree groups and every group's slice of perm starts its D2H as soon as it is final
     double *sink_thr = nullptr, *sink_mlo = nullptr, *sink_mhi = nullptr; uint32_t* sink_perm = nullptr;
@@ -169,6 +172,8 @@ struct rpf_handle {
     void* stream_plan = nullptr;         // cached plan of the last streaming build shape (stream.cu: StreamPlanAll)
     void (*stream_plan_free)(void*) = nullptr;
     size_t res_node_bytes = 0, res_perm_bytes = 0;
+    int rerank_gemm = 1;                 // option: leaf-grouped FP64 tensor-core re-rank (rerank.cu): 0 = never, 1 = when it pays (d >= 512,
+                                         //         >= 2 queries per leaf), 2 = whenever applicable (tests)
     int project_prefetch = 1;            // option: L2 prefetch of a later tile in the single-buffer projection kernel
     int project_pipe_maxh = 128;         // option: the pipelined projection kernel is used up to this many hyperplanes per launch
     int project_variant = 0;             // tuning hook: 0 = 1024 threads x 4 points/lane, 1 = 1024 x 2 (two CTAs/SM), 2 = 512 x 4
@@ -271,6 +276,11 @@ int rpf_brute_knn_impl(rpf_handle* h, const double* Q, const int32_t* q_last, in
 int rpf_merge_impl(rpf_handle* h, int G, int64_t nq, int k, int dedup, const double* dist, const uint32_t* ids,
                    const int32_t* count, double* dist_out, uint32_t* ids_out, int32_t* count_out, bool in_dev);
 
+// ---- leaf-grouped tensor-core re-rank (rerank.cu) ------------------------------------------------------------
+bool rpf_rerank_gemm_wanted(const rpf_handle* h, int64_t nq, int k, int dedup);
+int rpf_rerank_gemm(rpf_handle* h, const double* dQ, int64_t nq, int S, const uint32_t* segs, const uint32_t* cnt, int k,
+                    double* ddist, uint32_t* dids, int32_t* dcount, uint32_t* n_fallback);
+
 // ---- multi-GPU (multi.cu) ---------------------------------------------------------------------------
 // rank / world of a handle (0 / 1 without a communicator)
 int rpf_comm_rank(const rpf_handle* h);
@@ -279,7 +289,8 @@ void rpf_comm_free(rpf_handle* h);
 // in-place all-gather on `stream`: every rank contributed `bytes` bytes at buf + rank * bytes
 int rpf_comm_allgather(rpf_handle* h, void* buf, size_t bytes, cudaStream_t stream);
 // the rows rank r supplies to a row-sharded upload of n rows: [r * per, min(n, (r + 1) * per)), per = ceil(n / world)
-int rpf_upload_rows(rpf_handle* h, const double* hostX, int64_t r0, int64_t nr, cudaStream_t stream);   // build.cu
+int rpf_upload_rows(rpf_handle* h, const double* hostX, int64_t r0, int64_t nr, cudaStream_t stream,
+                    cudaStream_t gather_stream = nullptr, cudaEvent_t up_ev = nullptr);   // build.cu
 // group parent (rpf_create_multi): every public entry point forwards here when h->group is set
 void rpf_group_free(rpf_handle* h);
 

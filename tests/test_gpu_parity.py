@@ -645,3 +645,43 @@ def test_top_phase_beyond_1024_nodes_per_level(built, lean):
     for t in range(T):
         bad = compare_tree(f.treeExport(t), of.export(t))
         assert not bad, "tree %d: %s" % (t, bad)
+
+
+@pytest.mark.parametrize("n,d,T,minl,kind,nq", [
+    (30000, 64, 6, 32, "mixture", 900),      # ~1 query per leaf and tree
+    (8000, 128, 5, 48, "gauss", 3000),       # many queries per leaf: several passes of 32 queries per (tree, leaf)
+    (5000, 20, 3, 64, "dupes", 400),         # exact duplicate rows: massive distance ties -> some queries fall back to the gather kernel
+    (4000, 36, 4, 16, "integer", 500),       # ties everywhere, forks
+    (300, 8, 2, 64, "gauss", 50),            # the whole data set is a handful of leaves
+])
+def test_leaf_grouped_tensor_core_rerank_equals_gather_path_and_oracle(built, n, d, T, minl, kind, nq):
+    """rerank.cu: (tree, leaf)-grouped FP64 DMMA GEMM selects, survivors recomputed in the reference's arithmetic.  The
+    result must be identical -- ids, distance bits, tie order, counts -- to the gather kernel and to the oracle."""
+    R, orc = _mods()
+    maxd = R.rpTreeCfg(minl, n, d).fpMaxTreeDepth
+    X = make_data(n, d, 21, kind)
+    hp = orc.gen_hyperplanes(4242, T, maxd, 0.4, d)
+    rng = np.random.default_rng(3)
+    Q = np.concatenate([X[rng.integers(0, n, nq // 2)] + 0.01 * rng.normal(size=(nq // 2, d)), make_data(nq - nq // 2, d, 22, kind)])
+    f = R.RPForest(0)
+    f.setHyperplanes(hp, T, maxd); f.setPoints(X); f.build(maxd, minl)
+    of = orc.Forest(X, hp, T, maxd, minl)
+    for k in (1, 10, 37, 100):
+        f.setOption("rerank_gemm", 0)
+        d0, i0, c0 = f.knnBatch(Q, k)
+        f.setOption("rerank_gemm", 2)
+        d1, i1, c1 = f.knnBatch(Q, k)
+        assert np.array_equal(c0, c1), k
+        for i in range(nq):
+            assert np.array_equal(i0[i, :c0[i]], i1[i, :c1[i]]), (k, i)
+            assert np.array_equal(bits(d0[i, :c0[i]]), bits(d1[i, :c1[i]])), (k, i)
+        for i in range(0, nq, max(1, nq // 40)):
+            od, oi = of.knn(Q[i], k)
+            assert np.array_equal(i1[i, :c1[i]], oi) and np.array_equal(bits(d1[i, :c1[i]]), bits(od)), (k, i)
+    # knnPQ (dedup) is not regrouped: same answers with the option on
+    f.setOption("rerank_gemm", 2)
+    da, ia, ca = f.knnBatch(Q[:64], 10, dedup=True)
+    f.setOption("rerank_gemm", 0)
+    db, ib, cb = f.knnBatch(Q[:64], 10, dedup=True)
+    assert np.array_equal(ia, ib) and np.array_equal(ca, cb)
+    f.close()
