@@ -266,6 +266,152 @@ __global__ void __launch_bounds__(NT, 1) k_project_pipe(const double* __restrict
     }
 }
 
+// Long rows (d > one tile: 768, 960, ...).  The column-blocked launches of k_project carry every partial sum through the key
+// array (2 x 8 bytes per key and block: at 1M x 960 x 64 trees that is 100 GB next to 7.7 GB of X).  Here the partial sums
+// never leave the registers: a warp OWNS up to HPW hyperplanes for the whole tile (HPW x R accumulators per lane), the tile's
+// columns arrive in chunks of PW_KC from the HIGHEST columns down (the right fold's order) through a double-buffered
+// cp.async pipeline that runs across tiles (persistent CTAs), and for every chunk the warp folds the chunk's terms of each of
+// its hyperplanes onto the accumulator it already holds -- same order, same roundings as the single-tile kernel.
+// ctab[row * (nch + 1) + c] = number of nonzeros of CSR row `row` with column < c * PW_KC (host-built, rpf_project_launch).
+// A launch covers the H output rows jbase .. jbase + H - 1 (H <= NW * HPW); more hyperplanes take more launches (X re-read).
+#define PW_KC 128
+template <int NT, int R, int HPW, bool ORD>
+__global__ void __launch_bounds__(NT, 1) k_project_wide(const double* __restrict__ X, int64_t n, int d,
+                                                         const int64_t* __restrict__ hp_off, const double2* __restrict__ hp_pack,
+                                                         const int32_t* __restrict__ ctab, int nch, int t0, int L, int hpDepth, int jbase, int H,
+                                                         void* __restrict__ out, int64_t ostride, ull* __restrict__ kmin, ull* __restrict__ kmax,
+                                                         int64_t ntiles) {
+    constexpr int P = 32 * R, NW = NT / 32, LD = PW_KC + 1;
+    static_assert(HPW % 2 == 0, "hyperplanes are folded in pairs");
+    extern __shared__ double xs[];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    constexpr size_t bufsz = (size_t)P * LD;
+    auto stage = [&](int64_t tile, int cc, int b) {            // columns [cc * KC, ..) of the rows of `tile` -> buffer b
+        const int64_t i0 = tile * P;
+        const int c0 = cc * PW_KC, dc = min(PW_KC, d - c0);
+        double* dst = xs + (size_t)b * bufsz;
+        for (int r = w; r < P; r += NW) {
+            const bool live = i0 + r < n;
+            const double* src = X + (live ? (i0 + r) : 0) * (int64_t)d + c0;
+            const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + (size_t)r * LD);
+            const unsigned nb = live ? 8u : 0u;
+            for (int c = lane; c < dc; c += 32)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" :: "r"(sa + 8u * (unsigned)c), "l"(src + c), "r"(nb) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    const unsigned magicL = 0xffffffffu / (unsigned)L + 1u;
+    auto csr_row = [&](int j) { const int q = L > 1 ? (int)__umulhi((unsigned)j, magicL) : j; return (t0 + q) * hpDepth + (j - q * L); };
+    int64_t tile = blockIdx.x;
+    if (tile >= ntiles) return;
+    stage(tile, nch - 1, 0);
+    int b = 0;
+    for (; tile < ntiles; tile += gridDim.x) {
+        double acc[HPW][R];
+#pragma unroll
+        for (int s2 = 0; s2 < HPW; ++s2)
+#pragma unroll
+            for (int r = 0; r < R; ++r) acc[s2][r] = 0.0;
+        for (int cc = nch - 1; cc >= 0; --cc, b ^= 1) {
+            // next stage: the chunk below, or the top chunk of this CTA's next tile
+            const bool more = cc > 0 || tile + gridDim.x < ntiles;
+            if (more) {
+                if (cc > 0) stage(tile, cc - 1, b ^ 1); else stage(tile + gridDim.x, nch - 1, b ^ 1);
+                asm volatile("cp.async.wait_group 1;" ::: "memory");
+            } else {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+            }
+            __syncthreads();
+            const unsigned a0 = (unsigned)__cvta_generic_to_shared(xs + (size_t)b * bufsz + (size_t)lane * LD) - 8u * (unsigned)(cc * PW_KC);
+            auto term = [&](const double2 hv, double (&ac)[R]) {
+                const unsigned a = a0 + (unsigned)__double_as_longlong(hv.y);
+                double x[R];
+                x[0] = lds_f64_off<0>(a);
+                if constexpr (R > 1) x[1] = lds_f64_off<1 * 32 * LD * 8>(a);
+                if constexpr (R > 2) x[2] = lds_f64_off<2 * 32 * LD * 8>(a);
+                if constexpr (R > 3) x[3] = lds_f64_off<3 * 32 * LD * 8>(a);
+                static_assert(R <= 4, "extend the immediate-offset loads");
+#pragma unroll
+                for (int r = 0; r < R; ++r) ac[r] = __dadd_rn(__dmul_rn(hv.x, x[r]), ac[r]);
+            };
+#pragma unroll
+            for (int jj = 0; jj < HPW / 2; ++jj) {
+                const int jA = jj * NW + w, jB = (jj + HPW / 2) * NW + w;        // output rows of this warp inside the pass
+                if (jA >= H) continue;                                           // warp-uniform
+                const bool hasB = jB < H;
+                const int rowA = csr_row(jbase + jA), rowB = hasB ? csr_row(jbase + jB) : rowA;
+                const int32_t* tA = ctab + (int64_t)rowA * (nch + 1) + cc;
+                const int32_t* tB = ctab + (int64_t)rowB * (nch + 1) + cc;
+                const int lA = __ldg(tA), lB = __ldg(tB);
+                int cA = __ldg(tA + 1) - lA, cB = hasB ? __ldg(tB + 1) - lB : 0;
+                const double2* hA = hp_pack + hp_off[rowA] + lA + cA - 1;       // right fold: last term of the chunk first
+                const double2* hB = hp_pack + hp_off[rowB] + lB + cB - 1;
+                double2 a = cA > 0 ? __ldg(hA) : make_double2(0.0, 0.0), b2 = cB > 0 ? __ldg(hB) : make_double2(0.0, 0.0);
+                while (cA > 2 && cB > 2) {
+                    const double2 a1 = __ldg(hA - 1), b1 = __ldg(hB - 1);
+                    term(a, acc[jj]);
+                    term(b2, acc[jj + HPW / 2]);
+                    a = __ldg(hA - 2); b2 = __ldg(hB - 2);
+                    term(a1, acc[jj]);
+                    term(b1, acc[jj + HPW / 2]);
+                    hA -= 2; hB -= 2; cA -= 2; cB -= 2;
+                }
+                while (cA > 1 && cB > 1) {
+                    const double2 an = __ldg(hA - 1), bn = __ldg(hB - 1);
+                    --hA; --hB; --cA; --cB;
+                    term(a, acc[jj]);
+                    term(b2, acc[jj + HPW / 2]);
+                    a = an; b2 = bn;
+                }
+                while (cA > 1) { const double2 an = __ldg(hA - 1); --hA; --cA; term(a, acc[jj]); a = an; }
+                while (cB > 1) { const double2 bn = __ldg(hB - 1); --hB; --cB; term(b2, acc[jj + HPW / 2]); b2 = bn; }
+                if (cA > 0) term(a, acc[jj]);
+                if (cB > 0) term(b2, acc[jj + HPW / 2]);
+            }
+            __syncthreads();                                    // buffer b is free for the stage after next
+        }
+        // ---- the finished keys of this tile
+        const int64_t i0 = tile * P;
+        const bool track = (tile & 7) == 0;
+#pragma unroll
+        for (int s2 = 0; s2 < HPW; ++s2) {
+            const int j = s2 * NW + w;
+            if (j >= H) continue;
+            const int jo = jbase + j;
+            if (ORD) {
+                ull vmin = ORD_NONE_HI, vmax = ORD_NONE_LO;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const int64_t i = i0 + lane + 32 * r;
+                    if (i < n) {
+                        const ull o = f2ord(acc[s2][r]);
+                        ((ull*)out)[(int64_t)jo * ostride + i] = o;
+                        vmin = o < vmin ? o : vmin;
+                        vmax = o > vmax ? o : vmax;
+                    }
+                }
+                if (track) {
+                    for (int off = 16; off > 0; off >>= 1) {
+                        const ull a2 = __shfl_xor_sync(0xffffffffu, vmin, off), b3 = __shfl_xor_sync(0xffffffffu, vmax, off);
+                        vmin = a2 < vmin ? a2 : vmin;
+                        vmax = b3 > vmax ? b3 : vmax;
+                    }
+                    if (lane == 0 && vmin != ORD_NONE_HI) {
+                        if (vmin < kmin[jo]) atomicMin(&kmin[jo], vmin);
+                        if (vmax > kmax[jo]) atomicMax(&kmax[jo], vmax);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const int64_t i = i0 + lane + 32 * r;
+                    if (i < n) ((double*)out)[(int64_t)jo * ostride + i] = acc[s2][r];
+                }
+            }
+        }
+    }
+}
+
 // Fallback for very large d (tile does not fit shared memory): same arithmetic, rows read through L1/L2.
 template <bool ORD>
 __global__ void __launch_bounds__(256) k_project_direct(const double* __restrict__ X, int64_t n, int d,
@@ -344,6 +490,46 @@ static int launch_project_pipe(rpf_handle* h, int phase, const double* dX, int64
     return RPF_OK;
 }
 
+// long rows: chunk table (per CSR row: nonzeros below every PW_KC column boundary), built once per hyperplane set and d
+static int ensure_chunk_table(rpf_handle* h, int nch) {
+    if (h->d_hp_chunk && h->hp_chunk_d == h->d && h->hp_chunk_rows == (int64_t)h->hp_off.size() - 1) return RPF_OK;
+    if (h->capturing) return rpf_fail(h, RPF_ERR_STATE, "projection chunk table missing during graph capture");
+    const int64_t rows = (int64_t)h->hp_off.size() - 1;
+    std::vector<int32_t> tab((size_t)rows * (nch + 1));
+    for (int64_t r = 0; r < rows; ++r) {
+        int64_t q = h->hp_off[r];
+        const int64_t e = std::min(h->hp_off[r + 1], h->hp_off[r] + (int64_t)h->d);     // innerSD's `i >= nz2` guard (Internal.hs:376)
+        for (int c = 0; c <= nch; ++c) {
+            while (q < e && h->hp_idx[q] < c * PW_KC) ++q;
+            tab[(size_t)r * (nch + 1) + c] = (int32_t)((c == nch ? e : q) - h->hp_off[r]);
+        }
+    }
+    if (h->d_hp_chunk) { cudaStreamSynchronize(h->stream); cudaFree(h->d_hp_chunk); h->d_hp_chunk = nullptr; }
+    RPF_CUDA(h, cudaMalloc(&h->d_hp_chunk, std::max<size_t>(tab.size() * 4, 16)));
+    RPF_CUDA(h, cudaMemcpy(h->d_hp_chunk, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
+    h->hp_chunk_d = h->d; h->hp_chunk_rows = rows;
+    return RPF_OK;
+}
+
+template <int NT, int R, int HPW, bool ORD>
+static int launch_project_wide(rpf_handle* h, int phase, const double* dX, int64_t n, int t0, int L, int H, void* out, int64_t ostride, ull* kmin, ull* kmax) {
+    const int d = h->d, nch = (d + PW_KC - 1) / PW_KC;
+    int rc = ensure_chunk_table(h, nch);
+    if (rc) return rc;
+    const size_t smem = (size_t)2 * 32 * R * (PW_KC + 1) * sizeof(double);
+    auto kfn = k_project_wide<NT, R, HPW, ORD>;
+    RPF_CUDA(h, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t ntiles = (n + 32 * R - 1) / (32 * R);
+    const int64_t grid = std::min<int64_t>(ntiles, 148);
+    const int per = (NT / 32) * HPW;
+    // balanced passes (e.g. 896 hyperplanes at 288 per pass: 4 x 224 instead of 3 x 288 + 32)
+    const int npass = (H + per - 1) / per, hp = (H + npass - 1) / npass;
+    for (int j0 = 0; j0 < H; j0 += hp)
+        RPF_LAUNCH(h, phase, kfn, (unsigned)grid, NT, smem, dX, n, d, h->d_hp_off, (const double2*)h->d_hp_pack, (const int32_t*)h->d_hp_chunk, nch,
+                   t0, L, h->hpDepth, j0, std::min(hp, H - j0), out, ostride, kmin, kmax, ntiles);
+    return RPF_OK;
+}
+
 // out row j (= tree-in-group * L + level) starts at out + j * ostride; point i of dX lands at column i
 int rpf_project_launch(rpf_handle* h, int phase, const double* dX, int64_t n, int t0, int Tg, int L, bool ord, void* out,
                        int64_t ostride, ull* kmin, ull* kmax) {
@@ -377,6 +563,10 @@ int rpf_project_launch(rpf_handle* h, int phase, const double* dX, int64_t n, in
     if (ld == 129)      // d = 128: compile-time row stride
         return ord ? launch_project<1024, 4, true, 129>(h, phase, dX, n, t0, L, H, out, ostride, kmin, kmax)
                    : launch_project<1024, 4, false, 129>(h, phase, dX, n, t0, L, H, out, ostride, kmin, kmax);
+    // long rows: register-accumulator kernel (variant 9 = the column-blocked launches below instead)
+    if ((h->project_variant == 0 || h->project_variant == 5) && (size_t)64 * row > 140 * 1024 && n >= 2048)
+        return ord ? launch_project_wide<512, 2, 18, true>(h, phase, dX, n, t0, L, H, out, ostride, kmin, kmax)
+                   : launch_project_wide<512, 2, 18, false>(h, phase, dX, n, t0, L, H, out, ostride, kmin, kmax);
     if (h->project_variant != 3) {
         // 128-point tiles (4 points per lane); rows too long for one tile (d > 139: 200, 768, 960, ...) go in column
         // blocks of <= 139 columns with the partial sums carried in `out`.  Tuning hooks: variant 4 / 6 = 32- / 64-point
@@ -562,6 +752,8 @@ struct TopArgs {
     NodeSel* sel;
     ull* cand;
     uint32_t* cand_total;
+    uint32_t* done;                  // [Tg] CTAs of k_top_hist that finished the tree (NULL: separate pick kernels)
+    int fused_finish;                // k_top_finish_all instead of finish_warp -> finish -> ties
     uint32_t* wl_cnt;                // [2] work-list lengths of this level: big median bins (k_top_finish), straddling ties (k_top_ties)
     uint32_t* wl_big;                // [Tg * nnodes] entries t * nnodes + nl
     uint32_t* wl_tie;
@@ -716,6 +908,9 @@ __device__ __forceinline__ void stream_bins(const TopArgs& A, const uint16_t* __
     }
 }
 
+template <int NT> __device__ void pick_node_block(const TopArgs& A, int t, int nl, uint32_t* wsum, uint32_t* own);
+__device__ __forceinline__ void pick_node_warp(const TopArgs& A, int t, int nl);
+
 __global__ void __launch_bounds__(TOP_NT) k_top_hist(TopArgs A) {
     extern __shared__ uint32_t sh[];
     const int t = blockIdx.y, tid = threadIdx.x;
@@ -773,25 +968,37 @@ __global__ void __launch_bounds__(TOP_NT) k_top_hist(TopArgs A) {
             if (v >> 16) atomicAdd(&gh[2 * w2 + 1], v >> 16);
         }
     }
+    if (!A.done) return;
+    // ---- fused pick: the CTA that completes the tree's histogram (ticket counter) locates every node's median bin right
+    // away -- one launch and one kernel-boundary less per level
+    __shared__ uint32_t s_last;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(&A.done[t], 1u) == gridDim.x - 1) ? 1u : 0u;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int nl = tid >> 5; nl < A.nnodes; nl += TOP_NT / 32) pick_node_warp(A, t, nl);      // 16 nodes at a time
 }
 
-// one CTA per (node, tree): find the bin holding rank nh = size/2.  Thread j sums a contiguous range of bins, a
-// shuffle scan over the 256 partial sums names the range that covers the rank, warp 0 then scans that range.
-__global__ void __launch_bounds__(256) k_top_pick(TopArgs A) {
-    __shared__ uint32_t wsum[8];
-    __shared__ uint32_t own[2];
-    const int t = blockIdx.y, nl = blockIdx.x, g = A.node0 + nl, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (A.child[g] < 0) return;
+// Median bin of node (t, nl): the bin holding rank nh = size/2.  All NT threads of the CTA call it; thread j sums a contiguous
+// range of bins, a shuffle scan over the partial sums names the range that covers the rank, warp 0 then scans that range.
+// (__ldcg: the counters were written by other CTAs' atomics -- read them where the atomics landed, in L2.)
+template <int NT>
+__device__ void pick_node_block(const TopArgs& A, int t, int nl, uint32_t* wsum /*[NT/32]*/, uint32_t* own /*[2]*/) {
+    const int g = A.node0 + nl, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (A.child[g] < 0) return;                    // block-uniform
     const uint32_t k = A.nsize[g] >> 1;
     const uint32_t* hr = A.hist + (int64_t)t * A.HSZ + (int64_t)nl * A.NB;
-    const int per = (A.NB + 255) / 256;
-    const int b0 = tid * per, b1 = min(A.NB, b0 + per);
+    const int per = (A.NB + NT - 1) / NT;
+    const int b0 = min(A.NB, tid * per), b1 = min(A.NB, b0 + per);
     uint32_t s = 0;
 #pragma unroll 8
-    for (int b = b0; b < b1; ++b) s += hr[b];
+    for (int b = b0; b < b1; ++b) s += __ldcg(hr + b);
     uint32_t incl = s;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += y; }
+    __syncthreads();                               // scratch reuse across calls
     if (lane == 31) wsum[wid] = incl;
     if (tid == 0) { own[0] = 0; own[1] = 0; }
     __syncthreads();
@@ -805,7 +1012,7 @@ __global__ void __launch_bounds__(256) k_top_pick(TopArgs A) {
         uint32_t c = own[1];
         for (int base = ob0; base < ob1; base += 32) {
             const int b = base + lane;
-            const uint32_t hb = b < ob1 ? hr[b] : 0u;
+            const uint32_t hb = b < ob1 ? __ldcg(hr + b) : 0u;
             uint32_t in2 = hb;
 #pragma unroll
             for (int off = 1; off < 32; off <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, in2, off); if (lane >= off) in2 += y; }
@@ -821,38 +1028,42 @@ __global__ void __launch_bounds__(256) k_top_pick(TopArgs A) {
         }
     }
 }
-
-// same, one WARP per (node, tree): the deep top levels have thousands of nodes with <= 256 bins each
-__global__ void __launch_bounds__(256) k_top_pick_warp(TopArgs A) {
-    const int lane = threadIdx.x & 31;
-    const int64_t item = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (item >= (int64_t)A.nnodes * A.Tg) return;
-    const int t = (int)(item / A.nnodes), nl = (int)(item % A.nnodes), g = A.node0 + nl;
+// same, one WARP per (node, tree): the deep top levels have thousands of nodes.  The warp walks the node's bins in chunks
+// of 32 (one coalesced load + one shuffle scan per chunk, the next chunk's load already in flight) with a running prefix.
+__device__ __forceinline__ void pick_node_warp(const TopArgs& A, int t, int nl) {
+    const int lane = threadIdx.x & 31, g = A.node0 + nl;
     if (A.child[g] < 0) return;
     const uint32_t k = A.nsize[g] >> 1;
     const uint32_t* hr = A.hist + (int64_t)t * A.HSZ + (int64_t)nl * A.NB;
-    const int per = (A.NB + 31) / 32;              // <= 8
-    const int b0 = lane * per, b1 = min(A.NB, b0 + per);
-    uint32_t loc[8], s = 0;
+    uint32_t c = 0;
+    uint32_t nxt = lane < A.NB ? __ldcg(hr + lane) : 0u;
+    for (int base = 0; base < A.NB; base += 32) {
+        const uint32_t hb = nxt;
+        const int bn = base + 32 + lane;
+        nxt = bn < A.NB ? __ldcg(hr + bn) : 0u;
+        uint32_t in2 = hb;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { loc[j] = (b0 + j < b1) ? hr[b0 + j] : 0u; s += loc[j]; }
-    uint32_t incl = s;
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += y; }
-    const uint32_t excl = incl - s;
-    if (k >= excl && k < incl) {
-        uint32_t c = excl;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            if (k < c + loc[j]) {
-                NodeSel& S = A.sel[(int64_t)t * A.NTOP + g];
-                S.sel_bin = b0 + j; S.below = c; S.cand_cnt = loc[j]; S.cand_fill = 0;
-                S.cand_off = atomicAdd(&A.cand_total[t], loc[j]);
-                break;
-            }
-            c += loc[j];
+        for (int off = 1; off < 32; off <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, in2, off); if (lane >= off) in2 += y; }
+        const uint32_t ex2 = c + in2 - hb;
+        const bool hit = hb > 0 && k >= ex2 && k < ex2 + hb;
+        if (hit) {
+            NodeSel& S = A.sel[(int64_t)t * A.NTOP + g];
+            S.sel_bin = base + lane; S.below = ex2; S.cand_cnt = hb; S.cand_fill = 0;
+            S.cand_off = atomicAdd(&A.cand_total[t], hb);
         }
+        if (__any_sync(0xffffffffu, hit)) break;
+        c += __shfl_sync(0xffffffffu, in2, 31);
     }
+}
+__global__ void __launch_bounds__(256) k_top_pick(TopArgs A) {
+    __shared__ uint32_t wsum[8];
+    __shared__ uint32_t own[2];
+    pick_node_block<256>(A, blockIdx.y, blockIdx.x, wsum, own);
+}
+__global__ void __launch_bounds__(256) k_top_pick_warp(TopArgs A) {
+    const int64_t item = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (item >= (int64_t)A.nnodes * A.Tg) return;
+    pick_node_warp(A, (int)(item / A.nnodes), (int)(item % A.nnodes));
 }
 
 __global__ void __launch_bounds__(TOP_NT) k_top_compact(TopArgs A) {
@@ -882,38 +1093,33 @@ __global__ void __launch_bounds__(TOP_NT) k_top_compact(TopArgs A) {
     });
 }
 
-// one WARP per (node, tree) whose median bin holds <= 256 keys: register-blocked bitonic sort, no block barriers
+// one WARP per (node, tree) whose median bin holds <= 256 keys: register-blocked bitonic sort, no block barriers.
+// Returns bit 0: the bin is larger (CTA-wide path needed), bit 1: a tie straddles the split (lexicographic select needed).
 #define FW_MAX 256
 #define FW_WARPS 8
-__global__ void __launch_bounds__(FW_WARPS * 32) k_top_finish_warp(TopArgs A) {
-    __shared__ ull buf[FW_WARPS][FW_MAX];
-    const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
-    const int64_t item = (int64_t)blockIdx.x * FW_WARPS + wi;
-    if (item >= (int64_t)A.nnodes * A.Tg) return;
+__device__ __forceinline__ unsigned top_finish_small(const TopArgs& A, uint32_t item, ull* bufw /*[FW_MAX], this warp's*/) {
+    const int lane = threadIdx.x & 31;
     const int t = (int)(item / A.nnodes), nl = (int)(item % A.nnodes), g = A.node0 + nl;
-    if (A.child[g] < 0) return;
+    if (A.child[g] < 0) return 0u;
     NodeSel& S = A.sel[(int64_t)t * A.NTOP + g];
     const uint32_t c = S.cand_cnt, nh = A.nsize[g] >> 1, r = nh - S.below;
-    if (c > FW_MAX) {                             // rare: handed to k_top_finish through the work list
-        if (lane == 0) A.wl_big[atomicAdd(&A.wl_cnt[0], 1u)] = (uint32_t)item;
-        return;
-    }
+    if (c > FW_MAX) return 1u;
     const ull* seg = A.cand + (int64_t)t * A.n + S.cand_off;
     ull v[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) { const uint32_t i = lane * 8 + e; v[e] = i < c ? seg[i] : 0xffffffffffffffffull; }
     sort_regs<32, ull>(v, (ull*)nullptr, max(8u, next_pow2_u32(c)));      // only the block that holds the c keys needs sorting
 #pragma unroll
-    for (int e = 0; e < 8; ++e) buf[wi][lane * 8 + e] = v[e];
+    for (int e = 0; e < 8; ++e) bufw[lane * 8 + e] = v[e];
     __syncwarp();
-    const ull thr = buf[wi][r];
+    const ull thr = bufw[r];
     uint32_t lt = 0, eq = 0;
 #pragma unroll
     for (int e = 0; e < 8; ++e) { const uint32_t i = lane * 8 + e; if (i < c) { lt += v[e] < thr; eq += v[e] == thr; } }
     for (int off = 16; off > 0; off >>= 1) { lt += __shfl_xor_sync(0xffffffffu, lt, off); eq += __shfl_xor_sync(0xffffffffu, eq, off); }
     const uint32_t lower = lt, upper = lt + eq;
-    const ull pred = lower > 0 ? buf[wi][lower - 1] : ORD_NONE_LO;
-    const ull succ = upper < c ? buf[wi][upper] : ORD_NONE_HI;
+    const ull pred = lower > 0 ? bufw[lower - 1] : ORD_NONE_LO;
+    const ull succ = upper < c ? bufw[upper] : ORD_NONE_HI;
     const uint32_t cless = S.below + lower;
     const bool need_pred = (cless == nh) && pred == ORD_NONE_LO;
     const bool need_succ = (cless + eq == nh + 1) && succ == ORD_NONE_HI;
@@ -922,22 +1128,28 @@ __global__ void __launch_bounds__(FW_WARPS * 32) k_top_finish_warp(TopArgs A) {
         S.cless = cless; S.ceq = eq;
         S.tie_r = nh - cless;
         S.tie_depth = 0;
-        if (nh > cless) A.wl_tie[atomicAdd(&A.wl_cnt[1], 1u)] = (uint32_t)item;
         if (need_pred || need_succ) atomicOr(&A.track_any[t], 1u);
     }
     warp_track_bins(A, S, t, nl, need_pred, need_succ);
+    __syncwarp();
+    return nh > cless ? 2u : 0u;
+}
+__global__ void __launch_bounds__(FW_WARPS * 32) k_top_finish_warp(TopArgs A) {
+    __shared__ ull buf[FW_WARPS][FW_MAX];
+    const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+    const int64_t item = (int64_t)blockIdx.x * FW_WARPS + wi;
+    if (item >= (int64_t)A.nnodes * A.Tg) return;
+    const unsigned f = top_finish_small(A, (uint32_t)item, buf[wi]);
+    if (lane == 0) {
+        if (f & 1u) A.wl_big[atomicAdd(&A.wl_cnt[0], 1u)] = (uint32_t)item;      // rare: handed to k_top_finish through the work list
+        if (f & 2u) A.wl_tie[atomicAdd(&A.wl_cnt[1], 1u)] = (uint32_t)item;
+    }
 }
 
-// exact order statistic inside the median bin for the bins with more than FW_MAX keys: the CTAs walk the work list
-// k_top_finish_warp filled (a grid of one CTA per node would spend the deep levels launching CTAs that return at once)
-__global__ void __launch_bounds__(512) k_top_finish(TopArgs A) {
-    __shared__ ull buf[FIN_CAP];
-    __shared__ uint32_t sh[264];
-    __shared__ ull sh64[3];
+// exact order statistic inside the median bin for a bin with more than FW_MAX keys; all 512 threads of the CTA.
+// Returns (to every thread) whether a tie straddles the split.
+__device__ bool top_finish_big(const TopArgs& A, uint32_t item, ull* buf /*[FIN_CAP]*/, uint32_t* sh /*[264]*/, ull* sh64 /*[3]*/) {
     const int tid = threadIdx.x;
-    const uint32_t nwork = A.wl_cnt[0];
-    for (uint32_t wi = blockIdx.x; wi < nwork; wi += gridDim.x) {
-    const uint32_t item = A.wl_big[wi];
     const int t = (int)(item / A.nnodes), nl = (int)(item % A.nnodes), g = A.node0 + nl;
     __syncthreads();                              // shared buffers are reused from the previous work item
     NodeSel& S = A.sel[(int64_t)t * A.NTOP + g];
@@ -986,24 +1198,29 @@ __global__ void __launch_bounds__(512) k_top_finish(TopArgs A) {
         S.cless = cless; S.ceq = ceq;
         S.tie_r = nh - cless;        // tied points that must go left; > 0 => the split cuts through a tie
         S.tie_depth = 0;
-        if (nh > cless) A.wl_tie[atomicAdd(&A.wl_cnt[1], 1u)] = item;
         if (need_pred || need_succ) atomicOr(&A.track_any[t], 1u);
     }
     if (tid < 32) warp_track_bins(A, S, t, nl, need_pred, need_succ);
+    return nh > cless;
+}
+// the CTAs walk the work list k_top_finish_warp filled (a grid of one CTA per node would spend the deep levels launching
+// CTAs that return at once)
+__global__ void __launch_bounds__(512) k_top_finish(TopArgs A) {
+    __shared__ ull buf[FIN_CAP];
+    __shared__ uint32_t sh[264];
+    __shared__ ull sh64[3];
+    const uint32_t nwork = A.wl_cnt[0];
+    for (uint32_t wi = blockIdx.x; wi < nwork; wi += gridDim.x) {
+        const uint32_t item = A.wl_big[wi];
+        if (top_finish_big(A, item, buf, sh, sh64) && threadIdx.x == 0) A.wl_tie[atomicAdd(&A.wl_cnt[1], 1u)] = item;
     }
 }
 
-// one CTA per (node, tree): only does work when a tie straddles the split.  Finds the composite pivot
-// (key_{l-1}, key_{l-2}, ..., key_0, row id) such that exactly tie_r tied points are lexicographically below it:
-// this is the order the reference's stable merge sort leaves tied points in (Internal.hs:504-512).
-__global__ void __launch_bounds__(512) k_top_ties(TopArgs A) {
-    __shared__ uint32_t sh[264];
-    __shared__ ull sh64[1];
-    __shared__ uint32_t cnt;
+// Only does work when a tie straddles the split.  Finds the composite pivot (key_{l-1}, key_{l-2}, ..., key_0, row id) such
+// that exactly tie_r tied points are lexicographically below it: this is the order the reference's stable merge sort
+// leaves tied points in (Internal.hs:504-512).  All 512 threads of the CTA.
+__device__ void top_ties_item(const TopArgs& A, uint32_t item, uint32_t* sh /*[264]*/, ull* sh64 /*[1]*/, uint32_t* cnt) {
     const int tid = threadIdx.x;
-    const uint32_t nwork = A.wl_cnt[1];
-    for (uint32_t wi = blockIdx.x; wi < nwork; wi += gridDim.x) {
-    const uint32_t item = A.wl_tie[wi];
     const int t = (int)(item / A.nnodes), nl = (int)(item % A.nnodes), g = A.node0 + nl;
     __syncthreads();
     NodeSel& S = A.sel[(int64_t)t * A.NTOP + g];
@@ -1013,14 +1230,14 @@ __global__ void __launch_bounds__(512) k_top_ties(TopArgs A) {
     const ull thr = S.thr;
     uint32_t* la = (uint32_t*)(A.cand + (int64_t)t * A.n) + 2 * (int64_t)A.nstart[g];
     uint32_t* lb = la + A.nsize[g];
-    if (tid == 0) cnt = 0;
+    if (tid == 0) *cnt = 0;
     __syncthreads();
     for (int64_t i = tid; i < A.n; i += 512) {
         int gi = A.haslab ? (int)lab[i] : 0;
-        if (gi == g && keys_l[i] == thr) { uint32_t p = atomicAdd(&cnt, 1u); la[p] = (uint32_t)i; }
+        if (gi == g && keys_l[i] == thr) { uint32_t p = atomicAdd(cnt, 1u); la[p] = (uint32_t)i; }
     }
     __syncthreads();
-    uint32_t c = cnt, rr = S.tie_r;
+    uint32_t c = *cnt, rr = S.tie_r;
     int depth = 0;
     ull* piv = A.pivots + ((int64_t)t * A.NTOP + g) * A.MAXTD;
     while (true) {
@@ -1032,19 +1249,55 @@ __global__ void __launch_bounds__(512) k_top_ties(TopArgs A) {
         ++depth;
         const uint32_t r2 = rr - cl;
         if (r2 == 0 || lvl < 0) break;
-        if (tid == 0) cnt = 0;
+        if (tid == 0) *cnt = 0;
         __syncthreads();
         for (uint32_t i = tid; i < c; i += 512) {
             uint32_t id = la[i];
-            if (kk[id] == pv) { uint32_t p = atomicAdd(&cnt, 1u); lb[p] = id; }
+            if (kk[id] == pv) { uint32_t p = atomicAdd(cnt, 1u); lb[p] = id; }
         }
         __syncthreads();
-        c = cnt; rr = r2;
+        c = *cnt; rr = r2;
         uint32_t* tmp = la; la = lb; lb = tmp;
         __syncthreads();
     }
     if (tid == 0) S.tie_depth = depth;
+}
+__global__ void __launch_bounds__(512) k_top_ties(TopArgs A) {
+    __shared__ uint32_t sh[264];
+    __shared__ ull sh64[1];
+    __shared__ uint32_t cnt;
+    const uint32_t nwork = A.wl_cnt[1];
+    for (uint32_t wi = blockIdx.x; wi < nwork; wi += gridDim.x) top_ties_item(A, A.wl_tie[wi], sh, sh64, &cnt);
+}
+
+// finish_warp -> finish -> ties of one level in ONE launch: the 16 warps of a CTA each settle one node (median bin <= 256
+// keys: the usual case); the nodes of the CTA that need the CTA-wide sort / the tie select (rare) are then taken by the
+// whole CTA, one after the other.  Replaces three launches -- two of them fixed-size grids that mostly found empty work
+// lists -- per level.
+#define FA_WARPS 16
+__global__ void __launch_bounds__(FA_WARPS * 32) k_top_finish_all(TopArgs A) {
+    __shared__ ull buf[FIN_CAP];                          // phase 1: [FA_WARPS][FW_MAX]; phase 2: the CTA-wide sort buffer
+    __shared__ uint32_t sh[264];
+    __shared__ ull sh64[3];
+    __shared__ uint32_t cnt;
+    __shared__ uint32_t s_flag[FA_WARPS];
+    static_assert(FA_WARPS * FW_MAX <= FIN_CAP, "phase-1 buffers alias the CTA-wide sort buffer");
+    const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+    const int64_t total = (int64_t)A.nnodes * A.Tg, item0 = (int64_t)blockIdx.x * FA_WARPS;
+    unsigned f = 0;
+    if (item0 + wi < total) f = top_finish_small(A, (uint32_t)(item0 + wi), buf + (size_t)wi * FW_MAX);
+    if (lane == 0) s_flag[wi] = f;
+    __syncthreads();
+    for (int w2 = 0; w2 < FA_WARPS; ++w2) {
+        if (s_flag[w2] & 1u) {                            // block-uniform
+            const bool tie = top_finish_big(A, (uint32_t)(item0 + w2), buf, sh, sh64);
+            __syncthreads();
+            if (threadIdx.x == 0) s_flag[w2] = tie ? 2u : 0u;
+            __syncthreads();
+        }
     }
+    for (int w2 = 0; w2 < FA_WARPS; ++w2)
+        if (s_flag[w2] & 2u) top_ties_item(A, (uint32_t)(item0 + w2), sh, sh64, &cnt);
 }
 
 // relabel every point of an internal level-l node to its child; track the keys adjacent to the threshold
@@ -2230,7 +2483,7 @@ int rpf_launch_job(rpf_handle* h, BuildJob& J, const JobPlan& P, const char* tab
         uint32_t* hist = (uint32_t*)WSP(WS_HIST, (size_t)tgw * HSZ * 4);
         NodeSel* sel = (NodeSel*)WSP(WS_SEL, (size_t)tgw * NTOP * sizeof(NodeSel));
         ull* cand = (ull*)WSP(WS_CAND, (size_t)tgw * n * 8);
-        uint32_t* cand_total = (uint32_t*)WSP(WS_CANDTOT, (size_t)tgw * 8 + 8);  // [tg] candidate totals + [tg] margin-tracking flags + 2 work-list lengths
+        uint32_t* cand_total = (uint32_t*)WSP(WS_CANDTOT, (size_t)tgw * 12 + 8);  // [tg] candidate totals + [tg] margin-tracking flags + 2 work-list lengths + [tg] hist tickets
         uint32_t* wl = (uint32_t*)WSP(WS_WORKLIST, (size_t)tgw * max_lvl_nodes * 8);
         ull* pivots = (ull*)WSP(WS_PIVOTS, (size_t)tgw * NTOP * MAXTD * 8);
         uint32_t* fill = (uint32_t*)WSP(WS_FILL, (size_t)tgw * NTOP * 4);
@@ -2245,6 +2498,8 @@ int rpf_launch_job(rpf_handle* h, BuildJob& J, const JobPlan& P, const char* tab
         A.kmin = J.kmin; A.kmax = J.kmax; A.hist = hist; A.sel = sel;
         A.cand = cand; A.cand_total = cand_total; A.track_any = cand_total + tg; A.pivots = pivots;
         A.wl_cnt = cand_total + 2 * tg; A.wl_big = wl; A.wl_tie = wl + (size_t)tg * max_lvl_nodes;
+        uint32_t* done = cand_total + 2 * tg + 2;
+        A.fused_finish = (h->fused_top & 2) ? 1 : 0;
         A.fill = fill; A.perm = J.perm; A.thr = J.thr; A.mlo = J.mlo; A.mhi = J.mhi;
         RPF_CUDA(h, cudaFuncSetAttribute(k_top_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, HBINS * 2));
         RPF_CUDA(h, cudaFuncSetAttribute(k_top_compact_lean, cudaFuncAttributeMaxDynamicSharedMemorySize, CL_CAP * 6));
@@ -2286,23 +2541,35 @@ int rpf_launch_job(rpf_handle* h, BuildJob& J, const JobPlan& P, const char* tab
             all_top_internal = all_top_internal && A.all_internal;
             A.scatter_fast = (all_top_internal && 2 * A.nnodes <= SCAT_MAX) ? 1 : 0;
             RPF_CUDA(h, cudaMemsetAsync(hist, 0, (size_t)tg * HSZ * 4, h->stream));
-            RPF_CUDA(h, cudaMemsetAsync(cand_total, 0, (size_t)tg * 8 + 8, h->stream));
+            RPF_CUDA(h, cudaMemsetAsync(cand_total, 0, (size_t)tg * 12 + 8, h->stream));
             dim3 gn((unsigned)A.nnodes, (unsigned)tg);
             const size_t hs = A.smem_hist ? ((size_t)A.nnodes * A.NB + 1) / 2 * 4 : 0;     // 16-bit counters
             A.ch = ch_hist;
+            // pick fused into the histogram kernel where ONE CTA settles a tree's level quickly (>= 16 nodes: one warp per
+            // node); the first levels have a handful of nodes with up to 16384 bins each and keep their own pick launch
+            // (measured, profiles/r02_top_fusion_sweep.txt: the ticket's __threadfence also waits for the CTA's streaming bin
+            //  stores; with >= 16 trees per job other CTAs hide that and the fusion gains 0.15 ms at 32 trees, with 4 trees it
+            //  costs 0.13 ms -- so it is only used for large jobs)
+            A.done = ((h->fused_top & 1) && A.nnodes >= 16 && tg >= 16) ? done : nullptr;
             RPF_LAUNCH(h, PH_TOP_HIST, k_top_hist, grid_for(ch_hist), TOP_NT, hs, A);
-            if (A.NB <= 256) RPF_LAUNCH(h, PH_TOP_PICK, k_top_pick_warp, (unsigned)(((int64_t)A.nnodes * tg + 7) / 8), 256, 0, A);
-            else RPF_LAUNCH(h, PH_TOP_PICK, k_top_pick, gn, 256, 0, A);
+            if (!A.done) {
+                if (A.NB <= 256) RPF_LAUNCH(h, PH_TOP_PICK, k_top_pick_warp, (unsigned)(((int64_t)A.nnodes * tg + 7) / 8), 256, 0, A);
+                else RPF_LAUNCH(h, PH_TOP_PICK, k_top_pick, gn, 256, 0, A);
+            }
             // lean kernels (16-byte rows of bins / labels, shared-memory node tables): see k_top_relabel_lean
             const bool lean = h->lean_top && (n & 7) == 0 && A.nnodes <= SMEM_NODES && A.all_internal;
             const bool last = l == s_top - 1;
             A.ch = ch_compact;
             if (lean) RPF_LAUNCH(h, PH_TOP_COMPACT, k_top_compact_lean, grid_for(ch_compact), TOP_NT, CL_CAP * 6, A);
             else RPF_LAUNCH(h, PH_TOP_COMPACT, k_top_compact, grid_for(ch_compact), TOP_NT, 0, A);
-            RPF_LAUNCH(h, PH_TOP_FINISH, k_top_finish_warp, (unsigned)(((int64_t)A.nnodes * tg + FW_WARPS - 1) / FW_WARPS), FW_WARPS * 32, 0, A);
-            const unsigned gw = (unsigned)std::min<int64_t>((int64_t)A.nnodes * tg, 592);      // work-list walkers
-            RPF_LAUNCH(h, PH_TOP_FINISH, k_top_finish, gw, 512, 0, A);
-            RPF_LAUNCH(h, PH_TOP_TIES, k_top_ties, gw, 512, 0, A);
+            if (A.fused_finish) {
+                RPF_LAUNCH(h, PH_TOP_FINISH, k_top_finish_all, (unsigned)(((int64_t)A.nnodes * tg + FA_WARPS - 1) / FA_WARPS), FA_WARPS * 32, 0, A);
+            } else {
+                RPF_LAUNCH(h, PH_TOP_FINISH, k_top_finish_warp, (unsigned)(((int64_t)A.nnodes * tg + FW_WARPS - 1) / FW_WARPS), FW_WARPS * 32, 0, A);
+                const unsigned gw = (unsigned)std::min<int64_t>((int64_t)A.nnodes * tg, 592);      // work-list walkers
+                RPF_LAUNCH(h, PH_TOP_FINISH, k_top_finish, gw, 512, 0, A);
+                RPF_LAUNCH(h, PH_TOP_TIES, k_top_ties, gw, 512, 0, A);
+            }
             A.ch = ch_relabel;
             if (lean && !last) RPF_LAUNCH(h, PH_TOP_RELABEL, k_top_relabel_lean, grid_for(ch_relabel), TOP_NT, 0, A);
             else if (lean && A.scatter_fast)

@@ -205,6 +205,8 @@ static void free_hp_dev(rpf_handle* h) {
     if (h->d_hp_idx) cudaFree(h->d_hp_idx);
     if (h->d_hp_val) cudaFree(h->d_hp_val);
     if (h->d_hp_pack) cudaFree(h->d_hp_pack);
+    if (h->d_hp_chunk) cudaFree(h->d_hp_chunk);
+    h->d_hp_chunk = nullptr; h->hp_chunk_rows = 0;
     h->d_hp_off = nullptr; h->d_hp_idx = nullptr; h->d_hp_val = nullptr; h->d_hp_pack = nullptr;
 }
 static void free_topo_dev(rpf_handle* h) {
@@ -1122,6 +1124,7 @@ int rpf_set_option(rpf_handle* h, const char* name, int64_t value) {
     if (s == "force_simple_knn") { h->force_simple_knn = value != 0; return RPF_OK; }
     if (s == "no_query_order") { h->no_query_order = value != 0; return RPF_OK; }
     if (s == "project_variant") { h->project_variant = (int)value; return RPF_OK; }
+    if (s == "fused_top") { h->fused_top = (int)value; return RPF_OK; }
     if (s == "rerank_gemm") { h->rerank_gemm = (int)value; return RPF_OK; }
     if (s == "project_prefetch") { h->project_prefetch = (int)value; return RPF_OK; }
     if (s == "project_pipe_maxh") { h->project_pipe_maxh = (int)value; return RPF_OK; }

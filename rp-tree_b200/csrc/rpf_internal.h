@@ -155,6 +155,7 @@ struct rpf_handle {
     std::vector<int64_t> hp_off; std::vector<int32_t> hp_idx; std::vector<double> hp_val;
     int64_t* d_hp_off = nullptr; int32_t* d_hp_idx = nullptr; double* d_hp_val = nullptr;
     void* d_hp_pack = nullptr;   // (val, idx) pairs, 16 bytes each, CSR order
+    int32_t* d_hp_chunk = nullptr; int hp_chunk_d = 0; int64_t hp_chunk_rows = 0;   // long rows: nonzeros per column chunk (k_project_wide)
 
     // topology
     Topology topo;
@@ -172,6 +173,8 @@ struct rpf_handle {
     void* stream_plan = nullptr;         // cached plan of the last streaming build shape (stream.cu: StreamPlanAll)
     void (*stream_plan_free)(void*) = nullptr;
     size_t res_node_bytes = 0, res_perm_bytes = 0;
+    int fused_top = 1;                   // option, bits: 1 = median-bin pick fused into the histogram kernel (jobs of >= 16 trees), 2 = one
+                                         //         finish kernel per level instead of finish_warp -> finish -> ties (measured slower: off)
     int rerank_gemm = 1;                 // option: leaf-grouped FP64 tensor-core re-rank (rerank.cu): 0 = never, 1 = when it pays (d >= 512,
                                          //         >= 2 queries per leaf), 2 = whenever applicable (tests)
     int project_prefetch = 1;            // option: L2 prefetch of a later tile in the single-buffer projection kernel

@@ -685,3 +685,27 @@ def test_leaf_grouped_tensor_core_rerank_equals_gather_path_and_oracle(built, n,
     db, ib, cb = f.knnBatch(Q[:64], 10, dedup=True)
     assert np.array_equal(ia, ib) and np.array_equal(ca, cb)
     f.close()
+
+
+@pytest.mark.parametrize("opts", [{"project_variant": 9}, {"fused_top": 0}, {"branches": 1}, {"branches": 4, "fused_top": 3}],
+                         ids=["column-blocked-projection", "seven-launch-top-chain", "no-branches", "four-branches"])
+def test_build_variants_give_the_same_forest(built, opts):
+    """A/B hooks of the build: the column-blocked projection (k_project with partial sums in the key array) instead of the
+    register-accumulator kernel for long rows, the unfused top-phase launch chain, the number of concurrent branches."""
+    R, orc = _mods()
+    for (n, d, T, minl, kind) in [(70000, 960 if "project_variant" in opts else 24, 3 if "project_variant" in opts else 6, 16, "mixture"),
+                                  (66000, 12, 5, 8, "integer")]:
+        if "project_variant" in opts and d != 960:
+            continue
+        maxd = R.rpTreeCfg(minl, n, d).fpMaxTreeDepth
+        X = make_data(n, d, 11, kind)
+        hp = orc.gen_hyperplanes(99, T, maxd, 0.3 if d < 100 else 0.05, d)
+        f = R.forestBatch(0, maxd, minl, T, 0.3, d, X, hyperplanes=hp, options=opts)
+        g = R.forestBatch(0, maxd, minl, T, 0.3, d, X, hyperplanes=hp)
+        a, b = f.forestExport(), g.forestExport()
+        for key in ("thr", "mlo", "mhi"):
+            assert np.array_equal(bits(a[key]), bits(b[key])), (opts, key)
+        assert np.array_equal(a["perm"], b["perm"]), opts
+        of = orc.Forest(X, R.slice_hyperplanes(hp, maxd, 0, 1), 1, maxd, minl)
+        assert not compare_tree(f.treeExport(0), of.export(0))
+        f.close(); g.close()

@@ -24,10 +24,9 @@ for T in (32, 4):
     f.setHyperplanes(hp, T, maxd)
     f.setPoints(X)
     ref = None
-    for br, pv, pf in itertools.product((1, 2, 4), (7, 1, 2), (0, 1)):
-        if (pv != 7 and (br != 1 or T != 4)) or (br != 1 and pf != (1 if T == 4 else 0)):
-            continue
-        f.setOption("branches", br); f.setOption("project_variant", pv); f.setOption("project_prefetch", pf)
+    for br, fu in itertools.product((2,), (0, 1, 2, 3)):
+        pv, pf = 0, 1
+        f.setOption("branches", br); f.setOption("fused_top", fu)
         ms = []
         for i in range(8):
             f.build(maxd, W["min_leaf"])
@@ -39,7 +38,8 @@ for T in (32, 4):
             ref = sig
         assert sig == ref, "result changed with the options"
         f.setProfiling(True); f.build(maxd, W["min_leaf"]); prof = f.profile(); f.setProfiling(False)
-        rows.append(dict(T=T, branches=br, project_variant=pv, prefetch=pf, build_ms=round(float(np.mean(ms)), 3),
-                         project_ms=round(prof["project"][0], 3)))
+        rows.append(dict(T=T, branches=br, fused_top=fu, build_ms=round(float(np.mean(ms)), 3),
+                         project_ms=round(prof["project"][0], 3), top_ms=round(sum(v[0] for k, v in prof.items() if k.startswith("top_")), 3),
+                         launches=sum(v[1] for v in prof.values())))
         print(json.dumps(rows[-1]), flush=True)
     f.close()
