@@ -563,8 +563,11 @@ int rpf_project_launch(rpf_handle* h, int phase, const double* dX, int64_t n, in
     if (ld == 129)      // d = 128: compile-time row stride
         return ord ? launch_project<1024, 4, true, 129>(h, phase, dX, n, t0, L, H, out, ostride, kmin, kmax)
                    : launch_project<1024, 4, false, 129>(h, phase, dX, n, t0, L, H, out, ostride, kmin, kmax);
-    // long rows: register-accumulator kernel (variant 9 = the column-blocked launches below instead)
-    if ((h->project_variant == 0 || h->project_variant == 5) && (size_t)64 * row > 140 * 1024 && n >= 2048)
+    // long rows: register-accumulator kernel -- tuning hook only (variant 5).  Measured at 1M x 960 x 64 trees: 82.7 ms against
+    // 57.5 ms for the column-blocked launches below: with 2 points per lane and 16 warps per SM it keeps half as many
+    // accumulate chains in flight, and the shared-memory gathers -- the real bound of this fold -- are hidden less well;
+    // the 100 GB of partial sums the blocked launches move through HBM cost less than that.
+    if (h->project_variant == 5 && (size_t)64 * row > 140 * 1024 && n >= 2048)
         return ord ? launch_project_wide<512, 2, 18, true>(h, phase, dX, n, t0, L, H, out, ostride, kmin, kmax)
                    : launch_project_wide<512, 2, 18, false>(h, phase, dX, n, t0, L, H, out, ostride, kmin, kmax);
     if (h->project_variant != 3) {

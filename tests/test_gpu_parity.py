@@ -687,11 +687,11 @@ def test_leaf_grouped_tensor_core_rerank_equals_gather_path_and_oracle(built, n,
     f.close()
 
 
-@pytest.mark.parametrize("opts", [{"project_variant": 9}, {"fused_top": 0}, {"branches": 1}, {"branches": 4, "fused_top": 3}],
-                         ids=["column-blocked-projection", "seven-launch-top-chain", "no-branches", "four-branches"])
+@pytest.mark.parametrize("opts", [{"project_variant": 5}, {"fused_top": 3}, {"branches": 1}, {"branches": 4, "fused_top": 0}],
+                         ids=["register-accumulator-projection", "fused-top-chain", "no-branches", "four-branches"])
 def test_build_variants_give_the_same_forest(built, opts):
-    """A/B hooks of the build: the column-blocked projection (k_project with partial sums in the key array) instead of the
-    register-accumulator kernel for long rows, the unfused top-phase launch chain, the number of concurrent branches."""
+    """A/B hooks of the build: the register-accumulator projection kernel for long rows (k_project_wide) instead of the
+    column-blocked launches, the fused top-phase kernels, the number of concurrent branches."""
     R, orc = _mods()
     for (n, d, T, minl, kind) in [(70000, 960 if "project_variant" in opts else 24, 3 if "project_variant" in opts else 6, 16, "mixture"),
                                   (66000, 12, 5, 8, "integer")]:
