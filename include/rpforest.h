@@ -127,6 +127,22 @@ int rpf_build_from_host(rpf_handle* h, const double* X, int64_t n, int32_t d, in
  * Bin replaces that subtree by an empty Tip (Internal.hs:279), dropping its points -- see rpf_points_lost.
  * Limits: a Tip that must be re-split may hold at most 8192 points (minLeaf <= 4095 in practice). */
 int rpf_build_chunked(rpf_handle* h, int32_t maxDepth, int32_t minLeaf, int64_t chunk);
+/* The same fold, driven by the caller AS THE CHUNKS ARRIVE (Conduit.hs:157-176: `chunksOf n .| foldl insertMulti im0`;
+ * one rpf_insert_chunk == one insertMulti, Internal.hs:243-255).  Neither n nor the number of chunks is known in advance
+ * and the chunks may have any sizes (the reference's chunksOf gives equal chunks and a shorter last one).
+ *   rpf_insert_begin : every tree = `Tip () mempty` (Conduit.hs:166-168); needs the hyperplanes (rpf_set_hyperplanes /
+ *                      rpf_gen_hyperplanes); replaces the handle's points and forest.
+ *   rpf_insert_chunk : X_chunk = m x d row-major HOST rows; they get the row ids n_so_far .. n_so_far + m - 1.  After every
+ *                      call the handle holds a complete forest over all rows inserted so far -- every query / export /
+ *                      checkpoint entry point works between chunks -- identical to rpf_build_chunked over the same rows
+ *                      with the same chunk boundaries.  m = 0 is a no-op chunk.
+ *   rpf_insert_end   : closes the session (frees the per-level key store); points and forest stay, as after a build.
+ * Any other call that replaces the points or the hyperplanes closes the session and discards its points; rpf_build /
+ * rpf_build_chunked / rpf_build_from_host are refused (RPF_ERR_STATE) while a session is open.
+ * Same limit as rpf_build_chunked (a Tip that re-splits holds <= 8192 points); on that error the session is closed. */
+int rpf_insert_begin(rpf_handle* h, int32_t d, int32_t maxDepth, int32_t minLeaf);
+int rpf_insert_chunk(rpf_handle* h, const double* X_chunk, int64_t m);
+int rpf_insert_end(rpf_handle* h);
 
 /* ---- result structure: RPT Bin/Tip (Internal.hs:139-148) as flat arrays ---------------------------- */
 /* The topology (which nodes exist, their sizes) is a pure function of (n, minLeaf, maxDepth) because the

@@ -7,12 +7,12 @@ plus tree-sharded multi-GPU plumbing (dist.py).  The directory name has a hyphen
 """
 from ._lib import RPForestError, lib, SO_PATH, SIGNATURES
 from .api import (RPForest, SparseRows, RPTreeConfig, metricL2, rpTreeCfg, sampleHyperplanes, topologyPlan, slice_hyperplanes,
-                  forestBatch, treeBatch, forest, tree, knn, knnPQ, knnH, candidates, recallWith, levels, leafSizes,
+                  forestBatch, treeBatch, forest, tree, chunksOf, knn, knnPQ, knnH, candidates, recallWith, levels, leafSizes,
                   treeSize, points, serialiseRPForest, deserialiseRPForest)
 from . import _build
 from . import dist
 from . import idx
 
 __all__ = ["RPForest", "SparseRows", "RPForestError", "RPTreeConfig", "metricL2", "rpTreeCfg", "sampleHyperplanes", "topologyPlan",
-           "slice_hyperplanes", "forestBatch", "treeBatch", "forest", "tree", "knn", "knnPQ", "knnH", "candidates", "recallWith",
+           "slice_hyperplanes", "forestBatch", "treeBatch", "forest", "tree", "chunksOf", "knn", "knnPQ", "knnH", "candidates", "recallWith",
            "levels", "leafSizes", "treeSize", "points", "serialiseRPForest", "deserialiseRPForest", "lib", "SO_PATH", "SIGNATURES"]

@@ -43,6 +43,9 @@ SIGNATURES = {
     "rpf_build": (C.c_int, [H, C.c_int32, C.c_int32]),
     "rpf_build_from_host": (C.c_int, [H, f64p, C.c_int64, C.c_int32, C.c_int32, C.c_int32]),
     "rpf_build_chunked": (C.c_int, [H, C.c_int32, C.c_int32, C.c_int64]),
+    "rpf_insert_begin": (C.c_int, [H, C.c_int32, C.c_int32, C.c_int32]),
+    "rpf_insert_chunk": (C.c_int, [H, f64p, C.c_int64]),
+    "rpf_insert_end": (C.c_int, [H]),
     "rpf_num_nodes": (C.c_int64, [H]),
     "rpf_num_trees": (C.c_int32, [H]),
     "rpf_hyperplane_depth": (C.c_int32, [H]),

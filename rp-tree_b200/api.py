@@ -271,6 +271,27 @@ class RPForest:
         self.maxDepth, self.minLeaf = maxd, minl
         self._topo = None
 
+    # -- incremental build: the fold of Conduit.hs:157-176, one insertMulti per call
+    def insertBegin(self, d, maxd, minl):
+        """Every tree = `Tip () mempty` (rpf_insert_begin); the hyperplanes must be set."""
+        self._borrowed_points = None
+        self._ck(self._L.rpf_insert_begin(self._h, d, maxd, minl), "rpf_insert_begin")
+        self.n, self.d = 0, d
+        self.maxDepth, self.minLeaf = maxd, minl
+        self._topo = None
+
+    def insertChunk(self, Xc):
+        """insertMulti (Internal.hs:243-255) of one chunk of rows into every tree; the forest is queryable afterwards."""
+        Xc = np.ascontiguousarray(Xc, dtype=np.float64)
+        if Xc.ndim != 2 or (self.d and Xc.shape[0] and Xc.shape[1] != self.d):
+            raise ValueError("chunk must be m x %d" % self.d)
+        self._ck(self._L.rpf_insert_chunk(self._h, _p(Xc, f64p), Xc.shape[0]), "rpf_insert_chunk")
+        self.n += Xc.shape[0]
+        self._topo = None
+
+    def insertEnd(self):
+        self._ck(self._L.rpf_insert_end(self._h), "rpf_insert_end")
+
     # -- structure
     def topology(self):
         if self._topo is None:
@@ -509,15 +530,43 @@ def forest(seed, maxd, minl, ntrees, chunksize, pnz, dim, xs, *, hyperplanes=Non
         f.setBottomCap(bottom_cap)
     for name, value in (options or {}).items():
         f.setOption(name, value)
-    _set_points(f, xs, dim)
+    source = not isinstance(xs, (np.ndarray, SparseRows, list, tuple))     # a conduit-like source: rows arrive one at a time
+    if not source:
+        _set_points(f, xs, dim)
     if hyperplanes is not None:
         hp = hyperplanes if (t_first == 0 and t_local == ntrees) else slice_hyperplanes(hyperplanes, maxd, t_first, t_local)
         f.setHyperplanes(hp, t_local, maxd)
     else:
         f.genHyperplanes(seed, ntrees, maxd, pnz, dim, t_first, t_local)
     f.t_first, f.ntrees_total = t_first, ntrees
-    f.build(maxd, minl, chunk=chunksize)
+    if source:
+        # `src .| chunksOf n .| foldl insertMulti`: n is unknown until the source is exhausted
+        f.insertBegin(dim, maxd, minl)
+        for chunk in chunksOf(chunksize, xs, dim):
+            f.insertChunk(chunk)
+        f.insertEnd()
+    else:
+        f.build(maxd, minl, chunk=chunksize)
     return f
+
+
+def chunksOf(n, src, dim):
+    """chunkedAccum's `C.chunksOf n` (Conduit.hs:168-176): groups a stream of rows (1-d arrays, or 2-d blocks of rows) into n x dim chunks, last one shorter."""
+    buf = np.empty((n, dim), np.float64)
+    fill = 0
+    for item in src:
+        rows = np.asarray(item, np.float64)
+        rows = rows.reshape(1, dim) if rows.ndim == 1 else rows
+        a = 0
+        while a < rows.shape[0]:
+            take = min(n - fill, rows.shape[0] - a)
+            buf[fill:fill + take] = rows[a:a + take]
+            fill += take; a += take
+            if fill == n:
+                yield buf.copy()
+                fill = 0
+    if fill:
+        yield buf[:fill].copy()
 
 
 def tree(seed, maxd, minl, chunksize, pnz, dim, xs, **kw):

@@ -343,6 +343,7 @@ void rpf_destroy(rpf_handle* h) {
     if (h->group) { rpf_group_free(h); delete h; return; }
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    rpf_insert_drop(h);
     if (h->ownX && h->dX) cudaFree((void*)h->dX);
     if (h->d_xlast) cudaFree(h->d_xlast);
     free_hp_dev(h); free_topo_dev(h); free_forest_dev(h);
@@ -375,6 +376,7 @@ int rpf_set_points(rpf_handle* h, const double* X, int64_t n, int32_t d) {
     if (n >= (int64_t)1 << 31) return rpf_fail(h, RPF_ERR_UNSUPPORTED, "set_points: n must be < 2^31");
     if (h->group) return rpfg_set_points(h, X, n, d);
     RPF_SETDEV(h);
+    rpf_insert_drop(h);
     ++h->cfg_epoch;
     if (h->d_xlast) { cudaFree(h->d_xlast); h->d_xlast = nullptr; }
     double* p = nullptr;
@@ -408,6 +410,7 @@ int rpf_set_points_device(rpf_handle* h, const double* X_dev, int64_t n, int32_t
     if (n >= (int64_t)1 << 31) return rpf_fail(h, RPF_ERR_UNSUPPORTED, "set_points_device: n must be < 2^31");
     if (h->group) return rpf_fail(h, RPF_ERR_UNSUPPORTED, "set_points_device: a multi-GPU handle replicates the points itself (rpf_set_points)");
     RPF_SETDEV(h);
+    rpf_insert_drop(h);
     ++h->cfg_epoch;
     if (h->d_xlast) { cudaFree(h->d_xlast); h->d_xlast = nullptr; }
     if (h->ownX && h->dX) cudaFree((void*)h->dX);
@@ -446,6 +449,7 @@ int rpf_set_points_sparse(rpf_handle* h, int64_t n, int32_t d, const int64_t* of
     if (rc) return rc;
     if (h->group) return rpfg_set_points_sparse(h, n, d, off, idx, val);
     RPF_SETDEV(h);
+    rpf_insert_drop(h);
     ++h->cfg_epoch;
     if (h->d_xlast) { cudaFree(h->d_xlast); h->d_xlast = nullptr; }
     if (h->ownX && h->dX) cudaFree((void*)h->dX);
@@ -507,6 +511,7 @@ int rpf_set_hyperplanes(rpf_handle* h, int32_t T, int32_t maxDepth, const int64_
     for (int64_t r = 0; r < nrow; ++r) if (off[r + 1] < off[r]) return rpf_fail(h, RPF_ERR_ARG, "set_hyperplanes: offsets not monotone");
     if (h->d > 0) for (int64_t q = 0; q < nnz; ++q) if (idx[q] < 0 || idx[q] >= h->d) return rpf_fail(h, RPF_ERR_ARG, "set_hyperplanes: component index out of range");
     if (h->group) return rpfg_set_hyperplanes(h, T, maxDepth, off, idx, val);
+    rpf_insert_drop(h);
     h->T = T; h->hpDepth = maxDepth;
     h->hp_off.assign(off, off + nrow + 1);
     h->hp_idx.assign(idx, idx + nnz);
@@ -538,6 +543,7 @@ int rpf_gen_hyperplanes(rpf_handle* h, uint64_t seed, int32_t T_total, int32_t m
         }
     }
     h->hp_off.push_back((int64_t)h->hp_idx.size());
+    if (!h->group) rpf_insert_drop(h);
     h->T = T_local; h->hpDepth = maxDepth;
     if (h->group) return rpfg_after_gen_hyperplanes(h);
     return upload_hyperplanes(h);
@@ -614,6 +620,7 @@ static int check_build_args(rpf_handle* h, int32_t maxDepth, int32_t minLeaf) {
 int rpf_build(rpf_handle* h, int32_t maxDepth, int32_t minLeaf) {
     if (!h) return RPF_ERR_ARG;
     if (h->group) return rpfg_build(h, maxDepth, minLeaf, 0);
+    if (h->insert_session) return rpf_fail(h, RPF_ERR_STATE, "build: an insert session is open (rpf_insert_end first)");
     int rc = check_build_args(h, maxDepth, minLeaf);
     if (rc) return rc;
     RPF_SETDEV(h);
@@ -640,6 +647,7 @@ int rpf_build_from_host(rpf_handle* h, const double* X, int64_t n, int32_t d, in
     if (n < 0 || d < 1 || (n > 0 && !X)) return rpf_fail(h, RPF_ERR_ARG, "build_from_host: bad n/d/X");
     if (n >= (int64_t)1 << 31) return rpf_fail(h, RPF_ERR_UNSUPPORTED, "build_from_host: n must be < 2^31");
     if (h->group) return rpfg_build_from_host(h, X, n, d, maxDepth, minLeaf);
+    if (h->insert_session) return rpf_fail(h, RPF_ERR_STATE, "build: an insert session is open (rpf_insert_end first)");
     // validate against the NEW shape before the handle's state is touched
     if (h->T < 1) return rpf_fail(h, RPF_ERR_STATE, "build: call rpf_set_hyperplanes / rpf_gen_hyperplanes first");
     if (maxDepth < 0 || minLeaf < 0) return rpf_fail(h, RPF_ERR_ARG, "build: maxDepth and minLeaf must be >= 0");
@@ -686,6 +694,7 @@ int rpf_build_chunked(rpf_handle* h, int32_t maxDepth, int32_t minLeaf, int64_t 
     if (!h) return RPF_ERR_ARG;
     if (chunk < 1) return rpf_fail(h, RPF_ERR_ARG, "build_chunked: chunk must be >= 1");
     if (h->group) return rpfg_build(h, maxDepth, minLeaf, chunk);
+    if (h->insert_session) return rpf_fail(h, RPF_ERR_STATE, "build: an insert session is open (rpf_insert_end first)");
     if (chunk >= h->n) return rpf_build(h, maxDepth, minLeaf);   // one chunk == insert into an empty Tip == forestBatch
     int rc = check_build_args(h, maxDepth, minLeaf);
     if (rc) return rc;
@@ -698,6 +707,50 @@ int rpf_build_chunked(rpf_handle* h, int32_t maxDepth, int32_t minLeaf, int64_t 
     if (rc2) return rc2;
     h->built = true;
     return RPF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// incremental insert (stream.cu): forest = foldl insertMulti over the chunks as they arrive (Conduit.hs:157-176)
+// ---------------------------------------------------------------------------------------------------
+int rpf_insert_begin(rpf_handle* h, int32_t d, int32_t maxDepth, int32_t minLeaf) {
+    if (!h) return RPF_ERR_ARG;
+    if (h->group) return rpf_fail(h, RPF_ERR_UNSUPPORTED, "insert: not available on a multi-GPU handle (use one handle per tree shard)");
+    if (d < 1) return rpf_fail(h, RPF_ERR_ARG, "insert_begin: d must be >= 1");
+    if (h->T < 1) return rpf_fail(h, RPF_ERR_STATE, "insert_begin: call rpf_set_hyperplanes / rpf_gen_hyperplanes first");
+    if (maxDepth < 0 || minLeaf < 0) return rpf_fail(h, RPF_ERR_ARG, "insert_begin: maxDepth and minLeaf must be >= 0");
+    if (maxDepth > h->hpDepth) return rpf_fail(h, RPF_ERR_ARG, "insert_begin: maxDepth exceeds the number of hyperplanes per tree");
+    if (maxDepth > 62) return rpf_fail(h, RPF_ERR_UNSUPPORTED, "insert_begin: maxDepth > 62");
+    for (int32_t q : h->hp_idx) if (q < 0 || q >= d) return rpf_fail(h, RPF_ERR_ARG, "insert_begin: hyperplane component index out of range");
+    if (rpf_comm_world(h) > 1) return rpf_fail(h, RPF_ERR_UNSUPPORTED, "insert: every rank inserts the full chunk itself; detach the communicator first");
+    RPF_SETDEV(h);
+    free_forest_dev(h);
+    return rpf_insert_begin_impl(h, d, maxDepth, minLeaf);
+}
+
+int rpf_insert_chunk(rpf_handle* h, const double* X_chunk, int64_t m) {
+    if (!h) return RPF_ERR_ARG;
+    if (!h->insert_session) return rpf_fail(h, RPF_ERR_STATE, "insert_chunk: call rpf_insert_begin first");
+    if (m < 0 || (m > 0 && !X_chunk)) return rpf_fail(h, RPF_ERR_ARG, "insert_chunk: bad m / X_chunk");
+    if (m == 0) return RPF_OK;
+    RPF_SETDEV(h);
+    h->sink_pending = false;
+    h->call_begin();
+    int rc = rpf_insert_chunk_impl(h, X_chunk, m);
+    int rc2 = h->call_end();
+    if (rc || rc2) {
+        rpf_insert_drop(h);                        // the device state no longer matches the planner's
+        h->built = false;
+        return rc ? rc : rc2;
+    }
+    h->built = true;
+    return RPF_OK;
+}
+
+int rpf_insert_end(rpf_handle* h) {
+    if (!h) return RPF_ERR_ARG;
+    if (!h->insert_session) return RPF_OK;
+    RPF_SETDEV(h);
+    return rpf_insert_end_impl(h);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -866,6 +919,7 @@ int rpf_forest_load(rpf_handle* h, const char* path) {
     if (!h || !path) return RPF_ERR_ARG;
     if (h->group) return rpfg_forest_load(h, path);
     RPF_SETDEV(h);
+    rpf_insert_drop(h);
     RPF_CUDA(h, cudaStreamSynchronize(h->stream));
     try {
         return forest_load_impl(h, path);

@@ -170,6 +170,8 @@ struct rpf_handle {
     uint32_t* d_perm = nullptr;                                       // [T][n]
     bool leaf_order_exact = true;
     int64_t stream_lost = 0;             // points dropped by the reference's empty-piece rule during a streaming build
+    void* insert_session = nullptr;      // stream.cu: InsertSession of rpf_insert_begin / rpf_insert_chunk (owns dX while it lives)
+    void (*insert_session_free)(void*) = nullptr;
     void* stream_plan = nullptr;         // cached plan of the last streaming build shape (stream.cu: StreamPlanAll)
     void (*stream_plan_free)(void*) = nullptr;
     size_t res_node_bytes = 0, res_perm_bytes = 0;
@@ -270,6 +272,10 @@ int rpf_project_launch(rpf_handle* h, int phase, const double* dX, int64_t n, in
                        int64_t ostride, unsigned long long* kmin, unsigned long long* kmax);
 int rpf_upload_topology(rpf_handle* h);
 int rpf_build_stream_impl(rpf_handle* h, int maxDepth, int minLeaf, int64_t chunk);
+int rpf_insert_begin_impl(rpf_handle* h, int d, int maxDepth, int minLeaf);
+int rpf_insert_chunk_impl(rpf_handle* h, const double* Xc, int64_t m);
+int rpf_insert_end_impl(rpf_handle* h);
+void rpf_insert_drop(rpf_handle* h);      // closes an insert session (every other way of setting points / building calls it)
 int rpf_project_queries(rpf_handle* h, const double* dQ, int64_t nq, double* d_keysQ);
 int rpf_knn_impl(rpf_handle* h, const double* Q, const int32_t* q_last, int64_t nq, int k, int dedup, double* dist, uint32_t* ids, int32_t* count, bool out_dev);
 int rpf_knn_h_impl(rpf_handle* h, const double* Q, const int32_t* q_last, int64_t nq, int k, int cap, double* dist, uint32_t* ids, int32_t* count);

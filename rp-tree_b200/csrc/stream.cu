@@ -407,6 +407,32 @@ struct StreamPlanAll {
 };
 void free_stream_plan(void* p) { delete (StreamPlanAll*)p; }
 
+// levels / kernel choice of one group of re-split roots (same depth); rg / pv: tables of the generic bottom kernel
+void size_group(const ChunkPlan& P, RtGroup& G, bool force_generic, std::vector<int2>& rg, std::vector<uint32_t>& pv) {
+    int maxrel = 0;                   // depth of the deepest descendant below this group's roots
+    std::vector<int32_t> fr, nx;
+    pv.assign((size_t)G.depth, 1);
+    for (int e = 0; e < G.count; ++e) fr.push_back(G.first + e);
+    for (int rl = 0; !fr.empty(); ++rl) {
+        uint32_t mx = 1; nx.clear();
+        for (int32_t g : fr) { mx = std::max(mx, P.rt_size[g]); if (P.rt_child[g] >= 0) { nx.push_back(P.rt_child[g]); nx.push_back(P.rt_child[g] + 1); } }
+        uint32_t p2 = 1; while (p2 < mx) p2 <<= 1;
+        pv.push_back(p2);              // next_pow2(max size) at absolute level G.depth + rl
+        if (!nx.empty()) maxrel = rl + 1;
+        fr.swap(nx);
+    }
+    G.nlb = std::max(1, maxrel + 1);
+    G.levels = maxrel;
+    G.fast = maxrel <= rpf_bottom_fast_levels() && !force_generic;
+    if (G.fast) {
+        unsigned slots = 256; while (slots < G.max_root) slots <<= 1;
+        while (maxrel > 0 && (slots >> maxrel) == 0) slots <<= 1;
+        if (slots > 8192) G.fast = false;
+    }
+    rg.clear();
+    if (!G.fast) make_ranges(P.rt_child, G.first, G.count, G.nlb, rg);
+}
+
 // Plans every chunk (sequentially: the shape after chunk c depends on chunks < c) and groups the chunks into batches
 // whose descents run as ONE job: the routing of a chunk depends only on the tree SHAPE the chunk finds, which the
 // planner knows, never on the thresholds or leaf contents earlier chunks produced.
@@ -445,30 +471,10 @@ bool build_stream_plan(StreamPlanAll& S, std::string& err) {
             S.max_nnrt = std::max<int64_t>(S.max_nnrt, C.nnrt);
             for (RtGroup& G : P.groups) {
                 RtGroupL GL;
-                int maxrel = 0;                   // depth of the deepest descendant below this group's roots
-                std::vector<int32_t> fr, nx;
-                std::vector<uint32_t> pv((size_t)G.depth, 1);
-                for (int e = 0; e < G.count; ++e) fr.push_back(G.first + e);
-                for (int rl = 0; !fr.empty(); ++rl) {
-                    uint32_t mx = 1; nx.clear();
-                    for (int32_t g : fr) { mx = std::max(mx, P.rt_size[g]); if (P.rt_child[g] >= 0) { nx.push_back(P.rt_child[g]); nx.push_back(P.rt_child[g] + 1); } }
-                    uint32_t p2 = 1; while (p2 < mx) p2 <<= 1;
-                    pv.push_back(p2);              // next_pow2(max size) at absolute level G.depth + rl
-                    if (!nx.empty()) maxrel = rl + 1;
-                    fr.swap(nx);
-                }
-                G.nlb = std::max(1, maxrel + 1);
-                G.levels = maxrel;
-                G.fast = maxrel <= rpf_bottom_fast_levels() && !S.force_generic;
-                if (G.fast) {
-                    unsigned slots = 256; while (slots < G.max_root) slots <<= 1;
-                    while (maxrel > 0 && (slots >> maxrel) == 0) slots <<= 1;
-                    if (slots > 8192) G.fast = false;
-                }
+                std::vector<int2> rg; std::vector<uint32_t> pv;
+                size_group(P, G, S.force_generic, rg, pv);
                 GL.g = G;
                 if (!G.fast) {
-                    std::vector<int2> rg;
-                    make_ranges(P.rt_child, G.first, G.count, G.nlb, rg);
                     GL.off_rg = S.TB.put(rg.data(), rg.size() * sizeof(int2));
                     GL.off_pv = S.TB.put(pv.data(), pv.size() * 4);
                 }
@@ -671,6 +677,252 @@ int rpf_build_stream_impl(rpf_handle* h, int maxDepth, int minLeaf, int64_t chun
         for (int t = 0; t < tg; ++t)
             RPF_CUDA(h, cudaMemcpyAsync(h->d_perm + (int64_t)(t0 + t) * n, arena_old + (int64_t)t * n, (size_t)n * 4, cudaMemcpyDeviceToDevice, h->stream));
     }
+    return RPF_OK;
+}
+
+// =====================================================================================================
+// true incremental insert: the forest is a fold over the chunks AS THEY ARRIVE
+//   forest src = src .| chunksOf n .| foldl (insertMulti ...) im0        Conduit.hs:157-176
+//   insertMulti maxd minl rvss tts xs = per tree: insert ... tt xs       Internal.hs:243-255
+// rpf_insert_begin makes every tree `Tip () mempty`; every rpf_insert_chunk is ONE insertMulti: the chunk is uploaded,
+// projected, descends through the Bins it finds (thr' = (thr0 + thr)/2, margin' = margin0 <> margin), is prepended to the
+// Tips it reaches, and Tips that outgrow minLeaf split -- the per-chunk half of rpf_build_stream_impl, with the planner
+// (sizes only) kept alive between calls instead of replaying a known n.  After every call the handle holds a complete,
+// queryable forest over all points inserted so far.  Chunks may have any sizes; neither n nor the chunk count is known
+// in advance (per-point arrays grow geometrically).
+// =====================================================================================================
+namespace {
+struct InsertSession {
+    StreamPlanner SP; ChunkPlan P;
+    int maxDepth = 0, minLeaf = 0, Lk = 1, d = 0, T = 0;
+    int64_t n = 0, cap = 0;
+    double* X = nullptr;                 // [cap][d]
+    ull* keys = nullptr;                 // [T][Lk][cap]
+    uint32_t* arena[2] = {nullptr, nullptr};   // [T][cap]: leaf contents, left to right (slots past the kept points: 0xffffffff)
+    int cur = 0; bool order_exact = true;
+    double* pool = nullptr; size_t pool_cap = 0;     // thr | mlo | mhi, each [pool_cap][T] (node-major)
+    ~InsertSession() {
+        if (X) cudaFree(X);
+        if (keys) cudaFree(keys);
+        if (arena[0]) cudaFree(arena[0]);
+        if (arena[1]) cudaFree(arena[1]);
+        if (pool) cudaFree(pool);
+    }
+};
+void free_insert_session(void* p) { delete (InsertSession*)p; }
+}  // namespace
+
+void rpf_insert_drop(rpf_handle* h) {
+    if (!h->insert_session) return;
+    cudaStreamSynchronize(h->stream);
+    InsertSession* S = (InsertSession*)h->insert_session;
+    if (h->dX == S->X) { h->dX = nullptr; h->ownX = false; h->n = 0; h->x_bytes = 0; h->built = false; }
+    if (h->insert_session_free) h->insert_session_free(h->insert_session);
+    h->insert_session = nullptr;
+}
+
+// closes the session but keeps what it built: the points become the handle's own (as after rpf_set_points) and the forest
+// stays queryable; the key store, the arenas and the node pool are released
+int rpf_insert_end_impl(rpf_handle* h) {
+    InsertSession* S = (InsertSession*)h->insert_session;
+    if (!S) return RPF_OK;
+    RPF_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (S->X) { h->dX = S->X; h->ownX = true; h->x_bytes = std::max<size_t>((size_t)S->cap * S->d * 8, 16); h->n = S->n; h->x_pad_rows = 0; S->X = nullptr; }
+    else { h->dX = nullptr; h->ownX = false; h->x_bytes = 0; h->n = 0; }
+    if (h->insert_session_free) h->insert_session_free(h->insert_session);
+    h->insert_session = nullptr;
+    ++h->cfg_epoch;
+    return RPF_OK;
+}
+
+int rpf_insert_begin_impl(rpf_handle* h, int d, int maxDepth, int minLeaf) {
+    rpf_insert_drop(h);
+    if (h->d_xlast) { cudaFree(h->d_xlast); h->d_xlast = nullptr; }
+    if (h->ownX && h->dX) cudaFree((void*)h->dX);
+    h->dX = nullptr; h->ownX = false; h->x_bytes = 0; h->n = 0; h->d = d; h->x_pad_rows = 0;
+    h->built = false; h->sink_pending = false;
+    ++h->cfg_epoch;
+    InsertSession* S = new InsertSession();
+    S->maxDepth = maxDepth; S->minLeaf = minLeaf; S->Lk = std::max(maxDepth, 1); S->d = d; S->T = h->T;
+    S->SP.begin(0, maxDepth, minLeaf);
+    h->insert_session = S; h->insert_session_free = free_insert_session;
+    // the empty forest: one empty Tip per tree
+    h->stream_lost = 0;
+    S->SP.n = 0;
+    std::vector<int32_t> pool_of;
+    S->SP.final_topology(h->topo, pool_of);
+    h->topo_key_n = -1;
+    int rc = rpf_upload_topology(h);
+    if (!rc) rc = rpf_alloc_forest(h, h->topo.nnodes(), 0);
+    if (rc) return rc;
+    h->built = true;
+    return RPF_OK;
+}
+
+// grows a [rows][cap] device array to [rows][ncap], keeping the first `used` elements of every row
+template <typename E>
+static int grow_rows(rpf_handle* h, E** buf, size_t rows, int64_t cap, int64_t ncap, int64_t used, int fill) {
+    E* nb = nullptr;
+    if (cudaMalloc(&nb, std::max<size_t>(rows * (size_t)ncap * sizeof(E), 16)) != cudaSuccess) { cudaGetLastError(); return rpf_fail(h, RPF_ERR_NOMEM, "insert: out of device memory"); }
+    if (fill >= 0) RPF_CUDA(h, cudaMemsetAsync(nb, fill, rows * (size_t)ncap * sizeof(E), h->stream));
+    if (*buf && used > 0)
+        RPF_CUDA(h, cudaMemcpy2DAsync(nb, (size_t)ncap * sizeof(E), *buf, (size_t)cap * sizeof(E), (size_t)used * sizeof(E), rows, cudaMemcpyDeviceToDevice, h->stream));
+    if (*buf) { RPF_CUDA(h, cudaStreamSynchronize(h->stream)); cudaFree(*buf); }
+    *buf = nb;
+    return RPF_OK;
+}
+
+int rpf_insert_chunk_impl(rpf_handle* h, const double* Xc, int64_t m) {
+    InsertSession* S = (InsertSession*)h->insert_session;
+    const int T = S->T, Lk = S->Lk, d = S->d;
+    const int64_t n0 = S->n, n1 = n0 + m;
+    if (n1 >= ((int64_t)1 << 31)) return rpf_fail(h, RPF_ERR_UNSUPPORTED, "insert: more than 2^31 - 1 points");
+    // ---- plan on sizes alone (the planner's state is the shape of the tree so far)
+    ChunkPlan& P = S->P;
+    S->SP.n = n1;
+    if (!S->SP.plan_chunk(m, P)) {
+        const std::string e = S->SP.err;
+        rpf_insert_drop(h);                      // the planner's state is no longer the device's
+        return rpf_fail(h, RPF_ERR_UNSUPPORTED, e + " (the insert session was closed)");
+    }
+    ++h->cfg_epoch;
+    h->built = false;
+    // ---- capacity of the per-point arrays
+    if (n1 > S->cap) {
+        const int64_t ncap = ((std::max<int64_t>({n1, 2 * S->cap, 65536}) + 255) / 256) * 256;
+        int rc = grow_rows<double>(h, &S->X, 1, S->cap * d, ncap * d, n0 * d, -1);
+        if (!rc) rc = grow_rows<ull>(h, &S->keys, (size_t)T * Lk, S->cap, ncap, n0, -1);
+        if (!rc) rc = grow_rows<uint32_t>(h, &S->arena[0], (size_t)T, S->cap, ncap, n0, 0xff);
+        if (!rc) rc = grow_rows<uint32_t>(h, &S->arena[1], (size_t)T, S->cap, ncap, n0, 0xff);
+        if (rc) return rc;
+        S->cap = ncap;
+    }
+    const int64_t cap = S->cap;
+    if (S->SP.pool.size() + 1 > S->pool_cap) {
+        const size_t npc = std::max<size_t>(2 * S->pool_cap, S->SP.pool.size() + 1024);
+        double* np = nullptr;
+        if (cudaMalloc(&np, npc * T * 24) != cudaSuccess) { cudaGetLastError(); return rpf_fail(h, RPF_ERR_NOMEM, "insert: out of device memory"); }
+        for (int a = 0; a < 3 && S->pool; ++a)
+            RPF_CUDA(h, cudaMemcpyAsync(np + (size_t)a * npc * T, S->pool + (size_t)a * S->pool_cap * T, S->pool_cap * T * 8, cudaMemcpyDeviceToDevice, h->stream));
+        if (S->pool) { RPF_CUDA(h, cudaStreamSynchronize(h->stream)); cudaFree(S->pool); }
+        S->pool = np; S->pool_cap = npc;
+    }
+    double* pthr = S->pool; double* pmlo = pthr + S->pool_cap * T; double* pmhi = pmlo + S->pool_cap * T;
+    h->dX = S->X; h->ownX = false; h->n = n0; h->d = d;
+    if (m > 0) RPF_CUDA(h, cudaMemcpyAsync(S->X + n0 * d, Xc, (size_t)m * d * 8, cudaMemcpyHostToDevice, h->stream));
+
+    // ---- everything the device needs to know about this chunk, in ONE slot of the staging ring (a second stage_begin
+    //      inside this call could grow the ring and move the first slot's device block)
+    const int64_t nnct = P.ct.nnodes(), nnrt = (int64_t)P.rt_size.size();
+    std::vector<int32_t> pool_of;
+    S->SP.final_topology(h->topo, pool_of);       // canonical shape of the forest AFTER this chunk (sizes only)
+    h->topo.n = n1; h->topo_key_n = -1;
+    TableBuf JT; JobPlan JP;
+    if (m > 0) rpf_plan_job(P.ct, h->bottom_cap, Lk, h->force_generic_bottom, JT, JP);
+    std::vector<std::vector<int2>> rgs(P.groups.size()); std::vector<std::vector<uint32_t>> pvs(P.groups.size());
+    size_t tab_bytes = (size_t)nnct * 12 + P.upd_g.size() * 8 + P.copies.size() * sizeof(TipCopy) + (size_t)nnrt * 12 + P.rt_upd_g.size() * 8 +
+                       pool_of.size() * 4 + JT.bytes.size() + 64 * 256;
+    for (size_t i = 0; i < P.groups.size(); ++i) {
+        size_group(P, P.groups[i], h->force_generic_bottom, rgs[i], pvs[i]);
+        tab_bytes += rgs[i].size() * sizeof(int2) + pvs[i].size() * 4 + 512;
+    }
+    int rc = h->stage_begin(tab_bytes);
+    if (rc) return rc;
+    const uint32_t* d_start = h->stage_put(P.ct.start.data(), P.ct.start.size());
+    const uint32_t* d_size = h->stage_put(P.ct.size.data(), P.ct.size.size());
+    const int32_t* d_child = h->stage_put(P.ct.child.data(), P.ct.child.size());
+    const int32_t* d_upd_g = h->stage_put(P.upd_g.data(), P.upd_g.size());
+    const int32_t* d_upd_u = h->stage_put(P.upd_u.data(), P.upd_u.size());
+    const TipCopy* d_copies = h->stage_put(P.copies.data(), P.copies.size());
+    const uint32_t* d_rt_start = h->stage_put(P.rt_start.data(), P.rt_start.size());
+    const uint32_t* d_rt_size = h->stage_put(P.rt_size.data(), P.rt_size.size());
+    const int32_t* d_rt_child = h->stage_put(P.rt_child.data(), P.rt_child.size());
+    const int32_t* d_rt_upd_g = h->stage_put(P.rt_upd_g.data(), P.rt_upd_g.size());
+    const int32_t* d_rt_upd_u = h->stage_put(P.rt_upd_u.data(), P.rt_upd_u.size());
+    const int32_t* d_pool_of = h->stage_put(pool_of.data(), pool_of.size());
+    const char* d_jtab = (const char*)h->stage_put_raw(JT.bytes.data(), JT.bytes.size());
+    std::vector<const int2*> d_rg(P.groups.size(), nullptr); std::vector<const uint32_t*> d_pv(P.groups.size(), nullptr);
+    bool ok = d_start && d_size && d_child && d_upd_g && d_upd_u && d_copies && d_rt_start && d_rt_size && d_rt_child && d_rt_upd_g && d_rt_upd_u &&
+              d_pool_of && d_jtab;
+    for (size_t i = 0; i < P.groups.size(); ++i)
+        if (!P.groups[i].fast) {
+            d_rg[i] = h->stage_put(rgs[i].data(), rgs[i].size()); d_pv[i] = h->stage_put(pvs[i].data(), pvs[i].size());
+            ok = ok && d_rg[i] && d_pv[i];
+        }
+    if (!ok) return rpf_fail(h, RPF_ERR_NOMEM, h->err);
+    rc = h->stage_flush();
+    if (rc) return rc;
+
+    WSX(h, kmin, ull, WS_KMIN, (size_t)T * Lk * 8);
+    WSX(h, kmax, ull, WS_KMAX, (size_t)T * Lk * 8);
+    WSX(h, cperm, uint32_t, WS_S_CPERM, (size_t)T * std::max<int64_t>(m, 1) * 4);
+    WSX(h, tmpn, double, WS_S_TMPN, (size_t)T * (nnct + nnrt + 2) * 8 * 3);
+    double* cthr = tmpn; double* cmlo = cthr + (size_t)T * nnct; double* cmhi = cmlo + (size_t)T * nnct;
+    double* rthr = cmhi + (size_t)T * nnct; double* rmlo = rthr + (size_t)T * nnrt; double* rmhi = rmlo + (size_t)T * nnrt;
+    uint32_t* arena_old = S->arena[S->cur]; uint32_t* arena_new = S->arena[S->cur ^ 1];
+    if (m > 0) {
+        // ---- 1. keys of the chunk's points, appended to the persistent key store
+        RPF_CUDA(h, cudaMemsetAsync(kmin, 0xff, (size_t)T * Lk * 8, h->stream));
+        RPF_CUDA(h, cudaMemsetAsync(kmax, 0x00, (size_t)T * Lk * 8, h->stream));
+        if (S->maxDepth > 0) {
+            rc = rpf_project_launch(h, PH_PROJECT, S->X + n0 * d, m, 0, T, Lk, true, S->keys + n0, cap, kmin, kmax);
+            if (rc) return rc;
+        }
+        // ---- 2. the chunk descends through the Bins of the tree it finds
+        BuildJob J{};
+        J.tp = &P.ct; J.d_start = d_start; J.d_size = d_size; J.d_child = d_child;
+        J.n = m; J.ks = cap; J.ps = m; J.ns = nnct; J.Lk = Lk;
+        J.keys = S->keys + n0; J.kmin = kmin; J.kmax = kmax;
+        J.perm = cperm; J.thr = cthr; J.mlo = cmlo; J.mhi = cmhi; J.gt0 = 0; J.tg = T;
+        rc = rpf_launch_job(h, J, JP, d_jtab);
+        if (rc) return rc;
+        // ---- 3. thr' = (thr0 + thr) / 2, margin' = margin0 <> margin (or plain set for the first chunk of an empty tree)
+        if (!P.upd_g.empty()) {
+            const int64_t tot = (int64_t)P.upd_g.size() * T;
+            RPF_LAUNCH(h, PH_STREAM, k_pool_update, (unsigned)((tot + 255) / 256), 256, 0, d_upd_g, d_upd_u, (int)P.upd_g.size(), T, nnct,
+                       cthr, cmlo, cmhi, pthr, pmlo, pmhi, P.ct_set ? 0 : 1);
+        }
+    }
+    // ---- 4. Tip contents: piece ++ old, in the new left-to-right layout
+    RPF_CUDA(h, cudaMemsetAsync(arena_new, 0xff, (size_t)T * cap * 4, h->stream));
+    if (!P.copies.empty() && P.kept > 0)
+        RPF_LAUNCH(h, PH_STREAM_CONCAT, k_tip_concat, dim3((unsigned)((P.kept + 255) / 256), (unsigned)((T + 7) / 8)), 256, 0, d_copies, (int)P.copies.size(), T,
+                   (uint32_t)P.kept, cperm, (int64_t)m, (uint32_t)n0, arena_old, arena_new, cap);
+    // ---- 5. Tips that outgrew minLeaf split in place
+    for (size_t i = 0; i < P.groups.size(); ++i) {
+        const RtGroup& G = P.groups[i];
+        BottomArgs A{};
+        A.ks = cap; A.ps = cap; A.nn_all = nnrt; A.L = Lk; A.s = G.depth; A.nlb = G.nlb; A.gt0 = 0; A.first_gid = G.first;
+        A.given_order = 1;
+        A.keys = S->keys; A.perm = arena_new; A.child = d_rt_child; A.nstart = d_rt_start; A.nsize = d_rt_size;
+        A.range = d_rg[i]; A.lvl_pv = d_pv[i];
+        A.thr = rthr; A.mlo = rmlo; A.mhi = rmhi;
+        A.kmin = m > 0 ? kmin : nullptr; A.kmax = m > 0 ? kmax : nullptr;
+        rc = rpf_bottom_launch(h, A, G.count, T, G.fast, G.max_root, G.levels);
+        if (rc) return rc;
+    }
+    if (!P.rt_upd_g.empty()) {
+        const int64_t tot = (int64_t)P.rt_upd_g.size() * T;
+        RPF_LAUNCH(h, PH_STREAM, k_pool_update, (unsigned)((tot + 255) / 256), 256, 0, d_rt_upd_g, d_rt_upd_u, (int)P.rt_upd_g.size(), T, nnrt,
+                   rthr, rmlo, rmhi, pthr, pmlo, pmhi, 0);
+    }
+    S->cur ^= 1;
+    S->n = n1;
+
+    // ---- canonical forest over everything inserted so far
+    h->n = n1;
+    h->stream_lost = S->SP.lost;
+    if (m > 0 && !JP.G.order_exact) S->order_exact = false;
+    h->leaf_order_exact = S->order_exact;
+    rc = rpf_upload_topology(h);
+    if (rc) return rc;
+    const int64_t nn = h->topo.nnodes();
+    rc = rpf_alloc_forest(h, nn, n1);
+    if (rc) return rc;
+    RPF_LAUNCH(h, PH_STREAM, k_pool_export, (unsigned)((nn * T + 255) / 256), 256, 0, d_pool_of, h->d_node_child, nn, T, 0,
+               pthr, pmlo, pmhi, h->d_thr, h->d_mlo, h->d_mhi);
+    if (n1 > 0)
+        RPF_CUDA(h, cudaMemcpy2DAsync(h->d_perm, (size_t)n1 * 4, S->arena[S->cur], (size_t)cap * 4, (size_t)n1 * 4, T, cudaMemcpyDeviceToDevice, h->stream));
     return RPF_OK;
 }
 

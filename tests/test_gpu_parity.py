@@ -347,6 +347,112 @@ def test_streaming_rebuild_and_batch_on_same_handle(built):
             assert not compare_tree(f.treeExport(t), of.export(t)), "chunk=%r tree %d" % (chunk, t)
 
 
+INSERT_CASES = [
+    # n, d, T, maxd, minl, chunk, pnz, kind, cap
+    pytest.param(1000, 8, 3, 8, 10, 100, 0.5, "gauss", None, id="small-chunks"),
+    pytest.param(10007, 12, 3, 10, 12, 1001, 0.4, "gauss", 256, id="ragged-chunks-top-phase-cap256"),
+    pytest.param(3000, 4, 2, 6, 40, 999, 0.7, "gauss", None, id="tiny-last-chunk-wipes-tree"),
+    pytest.param(500, 3, 2, 7, 64, 20, 1.0, "gauss", None, id="chunks-accumulate-in-root-tip"),
+    pytest.param(10001, 6, 3, 10, 10, 2500, 0.5, "integer", 256, id="one-point-last-chunk-ties"),
+    pytest.param(40000, 16, 2, 12, 32, 4000, 0.3, "mixture", 1024, id="ten-chunks-top-phase"),
+]
+
+
+@pytest.mark.parametrize("n,d,T,maxd,minl,chunk,pnz,kind,cap", INSERT_CASES)
+def test_incremental_insert_equals_fold_after_every_chunk(built, n, d, T, maxd, minl, chunk, pnz, kind, cap):
+    """rpf_insert_begin / rpf_insert_chunk: the forest after EVERY chunk equals the oracle's chunked insert over the rows seen
+    so far (Conduit.hs:157-176: the fold's accumulator after each `insertMulti`, Internal.hs:243-255) -- neither n nor the
+    number of chunks is known to the engine in advance -- and it answers queries between chunks."""
+    R, orc = _mods()
+    X = make_data(n, d, 21, kind)
+    hp = orc.gen_hyperplanes(99, T, maxd, pnz, d)
+    f = R.RPForest(0)
+    if cap is not None:
+        f.setBottomCap(cap)
+    f.setHyperplanes(hp, T, maxd)
+    f.insertBegin(d, maxd, minl)
+    assert f.topology()["child"].tolist() == [-1] and f.topology()["seg_size"].tolist() == [0]      # Tip () mempty
+    nchunks = (n + chunk - 1) // chunk
+    check_at = {1, 2, nchunks // 2, nchunks - 1, nchunks}
+    rng = np.random.default_rng(5)
+    for c in range(nchunks):
+        f.insertChunk(X[c * chunk:(c + 1) * chunk])
+        seen = min(n, (c + 1) * chunk)
+        if c + 1 not in check_at:
+            continue
+        of = orc.Forest(X[:seen], hp, T, maxd, minl, chunk=chunk)
+        assert f.pointsLost() == seen - of.tree_size(0)
+        problems = []
+        for t in range(T):
+            problems += ["after chunk %d tree %d: %s" % (c + 1, t, b) for b in compare_tree(f.treeExport(t), of.export(t))]
+        assert not problems, "\n".join(problems[:20])
+        assert f.leafOrderExact()
+        Q = X[rng.integers(0, seen, size=8)] + (0.05 * rng.normal(size=(8, d)) if kind != "integer" else 0.0)
+        dist, idk, cnt = f.knnBatch(Q, 5)
+        for i in range(len(Q)):
+            od, oi = of.knn(Q[i], 5)
+            assert cnt[i] == len(od) and np.array_equal(bits(dist[i, :cnt[i]]), bits(od))
+            if kind in ("gauss", "mixture"):
+                assert np.array_equal(idk[i, :cnt[i]], oi)
+    f.insertEnd()
+    # closed session: the forest and the points stay
+    of = orc.Forest(X, hp, T, maxd, minl, chunk=chunk)
+    for t in range(T):
+        assert not compare_tree(f.treeExport(t), of.export(t))
+    # ... and the handle is an ordinary one again
+    f.build(maxd, minl)
+    ob = orc.Forest(X, hp, T, maxd, minl)
+    for t in range(T):
+        assert not compare_tree(f.treeExport(t), ob.export(t))
+
+
+def test_incremental_insert_from_a_row_source(built):
+    """`forest` fed by a generator of single rows (the conduit source of Conduit.hs:104-121) == `forest` over the matrix;
+    unequal chunk sizes are accepted by rpf_insert_chunk (the oracle has no counterpart: checked for shape + membership)."""
+    R, orc = _mods()
+    n, d, T, maxd, minl, chunk = 2503, 6, 3, 9, 8, 250
+    X = make_data(n, d, 3)
+    hp = orc.gen_hyperplanes(7, T, maxd, 0.5, d)
+    f = R.forest(0, maxd, minl, T, chunk, 0.5, d, (row for row in X), hyperplanes=hp)
+    of = orc.Forest(X, hp, T, maxd, minl, chunk=chunk)
+    assert f.n == n
+    for t in range(T):
+        assert not compare_tree(f.treeExport(t), of.export(t))
+    g = R.RPForest(0)
+    g.setHyperplanes(hp, T, maxd)
+    g.insertBegin(d, maxd, minl)
+    a = 0
+    for m in (700, 3, 0, 1200, 600):
+        g.insertChunk(X[a:a + m]); a += m
+    assert a == n and g.n == n
+    tp = g.topology()
+    assert tp["seg_size"][0] + g.pointsLost() == n
+    e = g.treeExport(0)
+    kept = e["perm"][:tp["seg_size"][0]]
+    assert len(np.unique(kept)) == len(kept) and kept.max() < n
+
+
+def test_incremental_insert_state_errors(built):
+    R, orc = _mods()
+    d, T, maxd = 4, 2, 5
+    hp = orc.gen_hyperplanes(5, T, maxd, 1.0, d)
+    f = R.RPForest(0)
+    with pytest.raises(R.RPForestError, match="hyperplanes"):
+        f.insertBegin(d, maxd, 4)
+    f.setHyperplanes(hp, T, maxd)
+    with pytest.raises(R.RPForestError, match="insert_begin"):
+        f.insertChunk(np.zeros((3, d)))
+    f.insertBegin(d, maxd, 4)
+    f.insertChunk(make_data(100, d, 1))
+    with pytest.raises(R.RPForestError, match="insert session"):
+        f.build(maxd, 4)
+    f.setPoints(make_data(50, d, 2))               # replaces the points: the session is gone
+    with pytest.raises(R.RPForestError, match="insert_begin"):
+        f.insertChunk(np.zeros((3, d)))
+    f.build(maxd, 4)
+    assert f.topology()["seg_size"][0] == 50
+
+
 def test_streaming_unsupported_shape_reports(built):
     """A Tip of more than 8192 points that must be re-split is outside the streaming path's limits."""
     R, orc = _mods()
