@@ -21,6 +21,7 @@
 #include "rpf_device.cuh"
 #include <algorithm>
 #include <cstdio>
+#include <cstring>
 #include <type_traits>
 
 // =====================================================================================================
@@ -530,6 +531,269 @@ static int launch_project_wide(rpf_handle* h, int phase, const double* dX, int64
     return RPF_OK;
 }
 
+// =====================================================================================================
+// K1t  projections, transposed tile + fold program (the default for rows that fit one tile)
+// =====================================================================================================
+// What bounds this fold is shared-memory bandwidth: 8 bytes per (point, term) cannot be avoided (the sparsity pattern is
+// run-time data, so the x values cannot sit in registers) -- 1.23 ms of the LDS pipe at configs[1].  k_project spends 35 warp
+// instructions per 128-point term on it (ncu: 1.57e9 instructions for 4.5e7 warp-terms) although its inner loop has 17.5:
+// the rest is per-hyperplane control (CSR offsets, tail loops for unequal pair lengths, 64-bit address arithmetic and
+// bounds checks in the store of the keys), paid once per ~13 terms.  Here
+//   * the tile is stored TRANSPOSED, xs[column][point] (row of P points = 8P bytes, the 16-byte point pairs XOR-swizzled
+//     with the column's low bits so the transposing stores of the loader are conflict-free too): the x values of a term
+//     arrive as 16-byte loads of two points each instead of 8-byte ones, and no padding column is needed (128 x 128
+//     doubles = 128 KB exactly: the carve-out leaves 124 KB of L1 for the program);
+//   * the host turns the hyperplanes of a launch into a FOLD PROGRAM: output rows sorted by their number of nonzeros and
+//     paired; both streams of a pair padded to the same even length with (0.0, column 0) terms -- exact: the fold's
+//     accumulator is never -0 (it starts at +0 and RN addition gives -0 only for (-0) + (-0)), so adding 0.0 * x = +-0
+//     leaves every bit of it unchanged for finite x -- and stored interleaved, 48 bytes per iteration (2 terms of each
+//     stream: four values + four packed smem offsets), so the inner loop has no tails, no per-stream pointer and 3 uniform
+//     loads per 4 terms; the pairs are dealt to the warps in serpentine order (equal work per warp, no run-time balancing);
+//   * keys are stored as 16-byte pairs from a precomputed row pointer; bounds checks only in the last tile.
+// Arithmetic: acc = fl(fl(val * x) + acc) from the LAST nonzero to the first, as innerSD (Internal.hs:369-382) -- the same
+// operations in the same order as k_project; the results are bit-identical (tests: both kernels against the oracle).
+struct ProjProg {
+    int t0 = 0, H = 0, L = 0, hpDepth = 0, d = 0, P = 0, NW = 0;
+    int jpw = 0;                        // jobs (pairs of output rows) per warp
+    int4* d_jobs = nullptr;             // [NW][jpw]: (first 16-byte unit of the pair's terms, iterations, row A, row B); row < 0: none
+    uint4* d_terms = nullptr;
+    size_t term_bytes = 0;
+    ~ProjProg() { if (d_jobs) cudaFree(d_jobs); if (d_terms) cudaFree(d_terms); }
+};
+struct ProjProgCache { std::vector<ProjProg*> v; ~ProjProgCache() { for (auto* p : v) delete p; } };
+static void free_proj_progs(void* p) { delete (ProjProgCache*)p; }
+
+static int get_proj_prog(rpf_handle* h, int t0, int H, int L, int P, int NW, ProjProg** out) {
+    if (!h->proj_progs) { h->proj_progs = new ProjProgCache(); h->proj_progs_free = free_proj_progs; }
+    ProjProgCache* C = (ProjProgCache*)h->proj_progs;
+    for (ProjProg* q : C->v)
+        if (q->t0 == t0 && q->H == H && q->L == L && q->hpDepth == h->hpDepth && q->d == h->d && q->P == P && q->NW == NW) { *out = q; return RPF_OK; }
+    if (h->capturing) return rpf_fail(h, RPF_ERR_STATE, "projection program missing during graph capture");
+    if (C->v.size() >= 32) { cudaStreamSynchronize(h->stream); for (auto* q : C->v) delete q; C->v.clear(); }
+    const int d = h->d;
+    struct Row { int j; int64_t s; int cnt; };
+    std::vector<Row> rows((size_t)H);
+    for (int j = 0; j < H; ++j) {
+        const int64_t r = (int64_t)(t0 + j / L) * h->hpDepth + (j % L);
+        const int64_t s0 = h->hp_off[r], e0 = std::min(h->hp_off[r + 1], s0 + (int64_t)d);      // innerSD's `i >= nz2` guard (Internal.hs:376)
+        rows[j] = Row{j, s0, (int)(e0 - s0)};
+    }
+    std::stable_sort(rows.begin(), rows.end(), [](const Row& a, const Row& b) { return a.cnt > b.cnt; });
+    const int npairs = (H + 1) / 2;
+    const int jpw = (npairs + NW - 1) / NW;
+    std::vector<int4> jobs((size_t)NW * jpw, make_int4(0, 0, -1, -1));
+    std::vector<uint4> terms;
+    const unsigned rowb = (unsigned)P * 8u;
+    auto enc = [&](int c) { return (unsigned)c * rowb + (((unsigned)c & 7u) << 4); };
+    for (int q = 0; q < npairs; ++q) {
+        const Row& A = rows[2 * q];
+        const bool hasB = 2 * q + 1 < H;
+        const Row B = hasB ? rows[2 * q + 1] : Row{-1, 0, 0};
+        const int niter = (std::max(A.cnt, B.cnt) + 1) / 2;
+        const int g = q / NW, i = q % NW, w = (g & 1) ? NW - 1 - i : i;            // serpentine deal
+        jobs[(size_t)w * jpw + g] = make_int4((int)terms.size(), niter, A.j, B.j);
+        auto val = [&](const Row& R, int k) { return k < R.cnt ? h->hp_val[R.s + R.cnt - 1 - k] : 0.0; };     // fold order: last nonzero first
+        auto rec = [&](const Row& R, int k) { return k < R.cnt ? enc(h->hp_idx[R.s + R.cnt - 1 - k]) : enc(0); };
+        for (int it = 0; it < niter; ++it) {
+            // 48 bytes per iteration: [A_k0, A_k1] [B_k0, B_k1] [recA_k0, recA_k1] [recB_k0, recB_k1] -- a lane of half-warp s reads
+            // its stream's 16 bytes of values at +16 s and its 8 bytes of offsets at +32 + 8 s
+            const int k0 = 2 * it, k1 = k0 + 1;
+            const double v4[4] = {val(A, k0), val(A, k1), val(B, k0), val(B, k1)};
+            uint4 u0, u1;
+            std::memcpy(&u0, &v4[0], 16); std::memcpy(&u1, &v4[2], 16);
+            terms.push_back(u0); terms.push_back(u1);
+            terms.push_back(make_uint4(rec(A, k0), rec(A, k1), rec(B, k0), rec(B, k1)));
+        }
+    }
+    ProjProg* Q = new ProjProg();
+    Q->t0 = t0; Q->H = H; Q->L = L; Q->hpDepth = h->hpDepth; Q->d = d; Q->P = P; Q->NW = NW; Q->jpw = jpw;
+    Q->term_bytes = terms.size() * sizeof(uint4);
+    if (cudaMalloc(&Q->d_jobs, jobs.size() * sizeof(int4)) != cudaSuccess || cudaMalloc(&Q->d_terms, std::max<size_t>(Q->term_bytes, 64)) != cudaSuccess ||
+        cudaMemcpy(Q->d_jobs, jobs.data(), jobs.size() * sizeof(int4), cudaMemcpyHostToDevice) != cudaSuccess ||
+        (Q->term_bytes && cudaMemcpy(Q->d_terms, terms.data(), Q->term_bytes, cudaMemcpyHostToDevice) != cudaSuccess)) {
+        cudaGetLastError(); delete Q;
+        return rpf_fail(h, RPF_ERR_NOMEM, "projection program: device tables");
+    }
+    C->v.push_back(Q);
+    *out = Q;
+    return RPF_OK;
+}
+
+__device__ __forceinline__ double2 lds_f64x2(unsigned a) {
+    double2 v;
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ double ldg_stream_f64(const double* p) {
+    double v;
+    asm("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+
+template <int NT, int R, bool ORD, int MINB>
+__global__ void __launch_bounds__(NT, MINB) k_project_t(const double* __restrict__ X, int64_t n, int d,
+                                                         const int4* __restrict__ jobs, int jpw, const uint4* __restrict__ terms,
+                                                         void* __restrict__ out, int64_t ostride, ull* __restrict__ kmin, ull* __restrict__ kmax,
+                                                         int pf_ahead) {
+    static_assert(R == 2 || R == 4, "tile of 64 or 128 points");
+    constexpr int P = 32 * R, NW = NT / 32;
+    constexpr int K = R;                                           // 16-byte point pairs per lane: a half-warp covers the tile
+    constexpr unsigned ROWB = P * 8;                               // bytes of one tile row (one column, P points)
+    extern __shared__ double xs_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    // the swizzle XORs address bits 4..6: the tile base must not carry into them
+    const unsigned base = ((unsigned)__cvta_generic_to_shared(xs_raw) + 511u) & ~511u;
+    const int64_t i0 = (int64_t)blockIdx.x * P;
+    if (pf_ahead > 0 && tid == 0) {
+        // the tile a later wave will stage (its rows are contiguous in X) is pulled into L2 now
+        const int64_t j0 = i0 + (int64_t)pf_ahead * P;
+        if (j0 + P <= n) {
+            const double* pf = X + j0 * (int64_t)d;
+            const unsigned bytes = (unsigned)((size_t)P * d * 8);
+            if ((((uintptr_t)pf) & 15) == 0 && (bytes & 15) == 0)
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(pf), "r"(bytes) : "memory");
+        }
+    }
+    // ---- stage the tile transposed: rows (2q, 2q+1) of X -> one 16-byte pair per column
+    for (int q = w; q < P / 2; q += NW) {
+        const int64_t r0 = i0 + 2 * q;
+        const bool l0 = r0 < n, l1 = r0 + 1 < n;
+        const double* s0 = X + (l0 ? r0 : 0) * (int64_t)d;
+        const double* s1 = X + (l1 ? r0 + 1 : 0) * (int64_t)d;
+        for (int c0 = lane; c0 < d; c0 += 128) {
+            double v0[4], v1[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int c = c0 + 32 * u;
+                v0[u] = (c < d && l0) ? ldg_stream_f64(s0 + c) : 0.0;
+                v1[u] = (c < d && l1) ? ldg_stream_f64(s1 + c) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int c = c0 + 32 * u;
+                if (c < d) {
+                    const unsigned a = base + (unsigned)c * ROWB + ((unsigned)(q ^ (c & 7)) << 4);
+                    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" :: "r"(a), "d"(v0[u]), "d"(v1[u]) : "memory");
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // Half-warp s = lane >> 4 folds stream s of the warp's current pair of output rows; lane m = lane & 15 of it carries the
+    // point pairs m, m + 16, ... (points 2m, 2m+1, 2m+32, 2m+33, ...).  The (value, offset) words of a term are then fetched
+    // by 16 lanes, not 32: the LSU writes back lanes x bytes whatever the address pattern, so a warp-uniform 16-byte load
+    // costs four 128-byte wavefronts of the same data pipe the x gathers saturate (ncu of the first version, every lane
+    // loading both streams' terms: 3 wavefronts per term next to the 8 of the x values, pipe 92 % busy).
+    const int sgrp = lane >> 4, m = lane & 15;
+    const unsigned m16 = (unsigned)m << 4;
+    const bool full = i0 + P <= n;
+    const bool al16 = ((((uintptr_t)out) | ((uintptr_t)ostride << 3)) & 15) == 0;
+    const bool track = ORD && (blockIdx.x & 7) == 0;               // the key range only seeds bin maps: every 8th tile is enough
+    const int4* jw = jobs + (size_t)w * jpw;
+    for (int k = 0; k < jpw; ++k) {                                // warp-uniform
+        const int4 jb = __ldg(jw + k);
+        if (jb.z < 0) break;
+        double acc[2 * K];
+#pragma unroll
+        for (int r = 0; r < 2 * K; ++r) acc[r] = 0.0;
+        auto term = [&](const double v, const unsigned rec) {
+            const unsigned a = (rec ^ m16) + base;
+            double2 x[K];
+#pragma unroll
+            for (int q = 0; q < K; ++q) x[q] = lds_f64x2(a + 256u * q);
+#pragma unroll
+            for (int q = 0; q < K; ++q) {
+                acc[2 * q] = __dadd_rn(__dmul_rn(v, x[q].x), acc[2 * q]);
+                acc[2 * q + 1] = __dadd_rn(__dmul_rn(v, x[q].y), acc[2 * q + 1]);
+            }
+        };
+        int it = jb.y;
+        if (it > 0) {
+            const char* tp = (const char*)(terms + jb.x) + 16 * sgrp;      // this half-warp's values; its offsets: + 32 - 8 s
+            const int ro = 32 - 8 * sgrp;
+            double2 v = __ldg((const double2*)tp);
+            uint2 rc = __ldg((const uint2*)(tp + ro));
+            while (true) {
+                // the next iteration's words are requested before this one's loads and adds are issued
+                const char* tn = tp + (it > 1 ? 48 : 0);
+                const double2 nv = __ldg((const double2*)tn);
+                const uint2 nr = __ldg((const uint2*)(tn + ro));
+                term(v.x, rc.x);
+                term(v.y, rc.y);
+                if (--it == 0) break;
+                tp = tn; v = nv; rc = nr;
+            }
+        }
+        // ---- this half-warp's output row: points i0 + 2m + 32q (+1)
+        const int j = sgrp ? jb.w : jb.z;
+        if (j < 0) continue;                                           // odd row count: the last pair has no second stream
+        if (ORD) {
+            ull o[2 * K];
+#pragma unroll
+            for (int r = 0; r < 2 * K; ++r) o[r] = f2ord(acc[r]);
+            ull* row = (ull*)out + (int64_t)j * ostride + i0 + 2 * m;
+            if (full && al16) {
+#pragma unroll
+                for (int q = 0; q < K; ++q) *reinterpret_cast<ulonglong2*>(row + 32 * q) = make_ulonglong2(o[2 * q], o[2 * q + 1]);
+            } else {
+#pragma unroll
+                for (int r = 0; r < 2 * K; ++r) {
+                    const int off = (r >> 1) * 32 + (r & 1);
+                    if (i0 + 2 * m + off < n) row[off] = o[r];
+                }
+            }
+            if (track) {
+                ull vmin = ORD_NONE_HI, vmax = ORD_NONE_LO;
+#pragma unroll
+                for (int r = 0; r < 2 * K; ++r) {
+                    const int off = (r >> 1) * 32 + (r & 1);
+                    if (i0 + 2 * m + off < n) { vmin = o[r] < vmin ? o[r] : vmin; vmax = o[r] > vmax ? o[r] : vmax; }
+                }
+                const unsigned hm = sgrp ? 0xffff0000u : 0x0000ffffu;
+                for (int off = 8; off > 0; off >>= 1) {
+                    const ull a2 = __shfl_xor_sync(hm, vmin, off), b2 = __shfl_xor_sync(hm, vmax, off);
+                    vmin = a2 < vmin ? a2 : vmin;
+                    vmax = b2 > vmax ? b2 : vmax;
+                }
+                if (m == 0 && vmin != ORD_NONE_HI) {
+                    if (vmin < kmin[j]) atomicMin(&kmin[j], vmin);
+                    if (vmax > kmax[j]) atomicMax(&kmax[j], vmax);
+                }
+            }
+        } else {
+            double* row = (double*)out + (int64_t)j * ostride + i0 + 2 * m;
+            if (full && al16) {
+#pragma unroll
+                for (int q = 0; q < K; ++q) *reinterpret_cast<double2*>(row + 32 * q) = make_double2(acc[2 * q], acc[2 * q + 1]);
+            } else {
+#pragma unroll
+                for (int r = 0; r < 2 * K; ++r) {
+                    const int off = (r >> 1) * 32 + (r & 1);
+                    if (i0 + 2 * m + off < n) row[off] = acc[r];
+                }
+            }
+        }
+    }
+}
+
+template <int NT, int R, bool ORD, int MINB>
+static int launch_project_t(rpf_handle* h, int phase, const double* dX, int64_t n, int t0, int L, int H, void* out, int64_t ostride, ull* kmin, ull* kmax) {
+    constexpr int P = 32 * R;
+    ProjProg* Q = nullptr;
+    int rc = get_proj_prog(h, t0, H, L, P, NT / 32, &Q);
+    if (rc) return rc;
+    const size_t smem = (size_t)h->d * P * 8 + 512;
+    auto kfn = k_project_t<NT, R, ORD, MINB>;
+    RPF_CUDA(h, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t grid = (n + P - 1) / P;
+    int occ = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, NT, smem);
+    const int pf = h->project_prefetch ? std::max(1, occ) * 148 : 0;
+    RPF_LAUNCH(h, phase, kfn, (unsigned)grid, NT, smem, dX, n, h->d, (const int4*)Q->d_jobs, Q->jpw, (const uint4*)Q->d_terms, out, ostride, kmin, kmax, pf);
+    return RPF_OK;
+}
+
 // out row j (= tree-in-group * L + level) starts at out + j * ostride; point i of dX lands at column i
 int rpf_project_launch(rpf_handle* h, int phase, const double* dX, int64_t n, int t0, int Tg, int L, bool ord, void* out,
                        int64_t ostride, ull* kmin, ull* kmax) {
@@ -537,6 +801,21 @@ int rpf_project_launch(rpf_handle* h, int phase, const double* dX, int64_t n, in
     const int H = Tg * L;
     if (n <= 0 || H <= 0) return RPF_OK;
     const size_t row = (size_t)ld * 8;
+    // transposed tile + fold program: whole rows in one tile (variant 7 / 8 and 1..6: the earlier kernels, kept as test hooks)
+    if (h->project_variant == 0 || h->project_variant >= 10) {
+        const int v = h->project_variant;
+        const bool fitA = (size_t)d * 1024 + 512 <= 164 * 1024, fitB = (size_t)d * 512 + 512 <= 200 * 1024;
+        const int pick = v >= 10 ? v : (fitA && H > h->project_pipe_maxh ? 10 : (fitB ? 11 : 0));
+        if (pick == 10 && fitA)
+            return ord ? launch_project_t<1024, 4, true, 1>(h, phase, dX, n, t0, L, H, out, ostride, kmin, kmax)
+                       : launch_project_t<1024, 4, false, 1>(h, phase, dX, n, t0, L, H, out, ostride, kmin, kmax);
+        if (pick == 11 && fitB)
+            return ord ? launch_project_t<512, 2, true, 2>(h, phase, dX, n, t0, L, H, out, ostride, kmin, kmax)
+                       : launch_project_t<512, 2, false, 2>(h, phase, dX, n, t0, L, H, out, ostride, kmin, kmax);
+        if (pick == 12 && fitB)
+            return ord ? launch_project_t<256, 2, true, 3>(h, phase, dX, n, t0, L, H, out, ostride, kmin, kmax)
+                       : launch_project_t<256, 2, false, 3>(h, phase, dX, n, t0, L, H, out, ostride, kmin, kmax);
+    }
     if (h->project_variant == 1 && 64 * row <= 110 * 1024)
         return ord ? launch_project<1024, 2, true>(h, phase, dX, n, t0, L, H, out, ostride, kmin, kmax)
                    : launch_project<1024, 2, false>(h, phase, dX, n, t0, L, H, out, ostride, kmin, kmax);

@@ -207,6 +207,8 @@ static void free_hp_dev(rpf_handle* h) {
     if (h->d_hp_pack) cudaFree(h->d_hp_pack);
     if (h->d_hp_chunk) cudaFree(h->d_hp_chunk);
     h->d_hp_chunk = nullptr; h->hp_chunk_rows = 0;
+    if (h->proj_progs && h->proj_progs_free) { cudaStreamSynchronize(h->stream); h->proj_progs_free(h->proj_progs); }
+    h->proj_progs = nullptr;
     h->d_hp_off = nullptr; h->d_hp_idx = nullptr; h->d_hp_val = nullptr; h->d_hp_pack = nullptr;
 }
 static void free_topo_dev(rpf_handle* h) {

@@ -156,6 +156,8 @@ struct rpf_handle {
     int64_t* d_hp_off = nullptr; int32_t* d_hp_idx = nullptr; double* d_hp_val = nullptr;
     void* d_hp_pack = nullptr;   // (val, idx) pairs, 16 bytes each, CSR order
     int32_t* d_hp_chunk = nullptr; int hp_chunk_d = 0; int64_t hp_chunk_rows = 0;   // long rows: nonzeros per column chunk (k_project_wide)
+    void* proj_progs = nullptr;          // build.cu: ProjProgCache, fold programs of k_project_t per (tree group, levels, d, tile)
+    void (*proj_progs_free)(void*) = nullptr;
 
     // topology
     Topology topo;
