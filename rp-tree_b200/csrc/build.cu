@@ -2329,6 +2329,7 @@ __global__ void __launch_bounds__(NT, (NT == 128 ? RPF_BOT_MINB128 : 1)) k_botto
     __shared__ int32_t t_gid[2][TAB];        // BFS id
     __shared__ uint16_t t_lsz[TAB];          // size if the segment just became a Tip (to be emitted), else 0
     const int t = blockIdx.y, tid = threadIdx.x;
+    if (A.only && !A.only[(size_t)t * gridDim.x + blockIdx.x]) return;      // second pass of k_bottom4: flagged nodes only
     const int e0 = A.first_gid + blockIdx.x;
     const uint32_t m = A.nsize[e0], start = A.nstart[e0];
     if (m == 0) return;
@@ -2408,17 +2409,20 @@ __global__ void __launch_bounds__(NT, (NT == 128 ? RPF_BOT_MINB128 : 1)) k_botto
         // 32-bit words: prefix = position of the key's VALUE inside the (tree, level) key range, PB bits (monotone: every
         // step below is monotone non-decreasing in the key).  A prefix taken from the key's bit pattern would spend
         // almost all codes on magnitudes near zero, where no projections live.
-        double plo = 0.0, psc = 0.0;
+        // (the difference is taken in fp64 -- keys far from zero keep their resolution -- the scaling in fp32: a 24-bit mantissa
+        //  against <= 24 prefix bits, 3 instructions instead of an fp64 multiply, compare / select and fp64 -> int conversion)
+        double plo = 0.0; float pscf = 0.f;
         if (W32 && A.kmin) {
             plo = ord2f(A.kmin[t * A.L + l]);
             const double wdt = ord2f(A.kmax[t * A.L + l]) - plo;
-            psc = (wdt > 0.0 && isfinite(wdt)) ? (double)((1u << PB) - 2u) / wdt : 0.0;
-            if (!isfinite(psc)) psc = 0.0;
+            const double psc = (wdt > 0.0 && isfinite(wdt)) ? (double)((1u << PB) - 2u) / wdt : 0.0;
+            pscf = isfinite(psc) ? __double2float_rz(psc) : 0.f;
+            if (!isfinite(pscf)) pscf = 0.f;
         }
         auto make_word = [&](ull key, unsigned slot) -> W {
             if (W32) {
-                const double pv = (ord2f(key) - plo) * psc;
-                unsigned p = pv > 0.0 ? (unsigned)fmin(pv, (double)((1u << PB) - 2u)) : 0u;
+                const float fv = __double2float_rz(ord2f(key) - plo) * pscf;
+                const unsigned p = min(__float2uint_rz(fv), (1u << PB) - 2u);      // the conversion saturates: negative (and NaN) -> 0
                 return (W)((p << SB) | slot);
             }
             return (W)((key & ~0xffffull) | slot);
@@ -2578,6 +2582,331 @@ __global__ void __launch_bounds__(NT, (NT == 128 ? RPF_BOT_MINB128 : 1)) k_botto
 }
 
 // =====================================================================================================
+// k_bottom4: one WARP owns a level-s node (<= 1024 points) and its subtree -- no block barriers at all
+// =====================================================================================================
+// What k_bottom3 pays for is a full sort of every segment at every level (164 network stages for the four bottom levels of
+// configs[1], ~270 thread instructions per point and level, 3.7 barrier stalls per issue).  The reference only needs
+//   * at a level whose children all split again: the elements of rank nh-1, nh, nh+1 of the stable sort (threshold and margin,
+//     Internal.hs:496-501) and WHICH elements go left -- the order inside a child matters only as the tie-break of a later
+//     sort, i.e. only if two full keys are equal later on;
+//   * at a level where Tips form: the sorted order (it is the Tip's content order).
+// The warp keeps three 1024-entry arrays in shared memory: the row ids in slot order (two buffers, ping-pong) and the level's
+// 32-bit sort words (22-bit prefix = position of the key's value in the (tree, level) key range | 10-bit slot, as in
+// k_bottom3).  A segment of Pv = 1024 >> j slots at relative depth j is read in chunks of 128 slots, four consecutive slots
+// per lane (one 16-byte load).
+//   select level (Pv >= 256): bisection on the prefix for the class of rank nh -- 22 steps, each one compare-and-count pass
+//     over the words + one REDUX per segment, the segments of the level interleaved -- then the median / predecessor / successor
+//     words by REDUX.MIN/MAX and a ballot compaction of the row ids into the children's slots.  Exact iff the prefix classes of
+//     ranks nh-1, nh, nh+1 are singletons (different prefixes order like the full keys: the map is monotone) -- checked.
+//   sort level (Pv <= 128): bitonic network per 128-slot chunk (distances 1, 2 in registers, 4 .. 64 by shuffles); neighbours
+//     with equal prefixes are put in full-key order afterwards.
+// Anything else -- a prefix class with several members where it matters, equal FULL keys (the reference's incoming order is
+// needed, which the select levels do not keep), a node that is a Tip itself but arrives unordered, segments of fewer than 3
+// points, Tips larger than 64 points -- sets the node's `redo` flag after putting the row ids of the unfinished segments back
+// into their ranges of perm (the node's slice is again a permutation of its points); k_bottom3 then runs on the flagged nodes
+// only and, being exact on any input, produces the same forest.
+#define B4_WPC 4
+struct B4Warp {
+    uint32_t ids[2][1024];
+    uint32_t words[1024];
+    int32_t gid[2][32];
+    uint16_t sz[2][32], ps[2][32], lsz[32];
+};
+
+__global__ void __launch_bounds__(B4_WPC * 32, 4) k_bottom4(BottomArgs A, uint8_t* __restrict__ redo, int nroots) {
+    extern __shared__ __align__(16) unsigned char b4raw[];
+    constexpr unsigned PAD = 0xffffffffu, FULL = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int node = blockIdx.x * B4_WPC + (int)wib, t = blockIdx.y;
+    if (node >= nroots) return;
+    B4Warp& S = ((B4Warp*)b4raw)[wib];
+    const int e0 = A.first_gid + node;
+    const uint32_t m = A.nsize[e0], start = A.nstart[e0];
+    if (m == 0) return;
+    const int64_t n = A.ks;
+    const ull* keys_t = A.keys + (int64_t)t * A.L * n;
+    uint32_t* perm = A.perm + (int64_t)t * A.ps + start;
+    uint8_t* flag = redo + (size_t)t * nroots + node;
+    if (A.child[e0] < 0) {                       // the node is a Tip: only its order may be open (k_bottom3 knows how)
+        if (A.s > 0 && lane == 0) *flag = 1;
+        return;
+    }
+    for (unsigned x = lane; x < 1024u; x += 32) S.ids[0][x] = x < m ? perm[x] : 0u;
+    if (lane == 0) { S.sz[0][0] = (uint16_t)m; S.ps[0][0] = 0; S.gid[0][0] = e0; }
+    __syncwarp();
+    uint32_t* words = S.words;
+    const unsigned lt = (1u << lane) - 1u;
+    int cur = 0, rc = 1;
+    for (int J = 0; J < 5 && rc == 1; ++J) {
+        const int nseg = 1 << J, lpv = 10 - J, l = A.s + J, nxt = cur ^ 1;
+        const unsigned Pv = 1024u >> J;
+        const ull* kl = keys_t + (int64_t)l * n;
+        const uint16_t* sz = S.sz[cur];
+        const uint32_t* ids = S.ids[cur];
+        uint32_t* idn = S.ids[nxt];
+        // ---- children tables (sizes only)
+        int anyint = 0, anytip = 0, bail = 0;
+        if (lane < 2u * nseg) {
+            const unsigned c = lane, e = c >> 1, psz = sz[e];
+            uint16_t csz = 0, lsz = 0, cps = 0; int32_t cg = -1;
+            if (psz) {
+                const unsigned nh = psz >> 1, s2 = (c & 1) ? psz - nh : nh;
+                cps = (uint16_t)(S.ps[cur][e] + ((c & 1) ? nh : 0));
+                cg = A.child[S.gid[cur][e]] + (int)(c & 1);
+                if (A.child[cg] >= 0) { csz = (uint16_t)s2; anyint = 1; } else { lsz = (uint16_t)s2; anytip = 1; }
+                if (psz < 3) bail = 1;
+            }
+            S.sz[nxt][c] = csz; S.ps[nxt][c] = cps; S.gid[nxt][c] = cg; S.lsz[c] = lsz;
+        }
+        anyint = __any_sync(FULL, anyint); anytip = __any_sync(FULL, anytip); bail = __any_sync(FULL, bail);
+        const bool do_sort = anytip || Pv <= 128;
+        if (do_sort && Pv > 128) bail = 1;        // Tips of more than 64 points: k_bottom3
+        __syncwarp();
+        if (!bail) {
+            // ---- sort words of the level: prefix = floor((key - lo) * scale), the difference in fp64 (keys far from zero keep
+            //      their resolution), the scaling in fp32 (24-bit mantissa against 22 prefix bits); every step is monotone
+            const double plo = ord2f(A.kmin[t * A.L + l]);
+            float scf = 0.f;
+            {
+                const double wdt = ord2f(A.kmax[t * A.L + l]) - plo;
+                const double sc = (wdt > 0.0 && isfinite(wdt)) ? (double)((1u << 22) - 2u) / wdt : 0.0;
+                scf = isfinite(sc) ? __double2float_rz(sc) : 0.f;
+                if (!isfinite(scf)) scf = 0.f;
+            }
+#pragma unroll 1
+            for (unsigned c = 0; c < 8; c += 2) {             // 8 key gathers in flight per lane
+                uint4 idv[2]; ull kk[8]; bool ok[8];
+#pragma unroll
+                for (int h2 = 0; h2 < 2; ++h2) idv[h2] = *reinterpret_cast<const uint4*>(ids + 128u * (c + h2) + 4u * lane);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const unsigned x = 128u * (c + (q >> 2)) + 4u * lane + (q & 3);
+                    const uint32_t id = (q & 3) == 0 ? idv[q >> 2].x : (q & 3) == 1 ? idv[q >> 2].y : (q & 3) == 2 ? idv[q >> 2].z : idv[q >> 2].w;
+                    ok[q] = (x & (Pv - 1u)) < sz[x >> lpv];
+                    kk[q] = ok[q] ? kl[id] : ~0ull;
+                }
+                uint32_t wv[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const unsigned x = 128u * (c + (q >> 2)) + 4u * lane + (q & 3);
+                    const float fv = __double2float_rz(ord2f(kk[q]) - plo) * scf;
+                    const unsigned p = min(__float2uint_rz(fv), (1u << 22) - 2u);      // the conversion saturates: negative (and NaN) -> 0
+                    wv[q] = ok[q] ? ((p << 10) | x) : PAD;
+                }
+#pragma unroll
+                for (int h2 = 0; h2 < 2; ++h2)
+                    *reinterpret_cast<uint4*>(words + 128u * (c + h2) + 4u * lane) = make_uint4(wv[4 * h2], wv[4 * h2 + 1], wv[4 * h2 + 2], wv[4 * h2 + 3]);
+            }
+            __syncwarp();
+        }
+        if (!bail && !do_sort) {
+            // ================= select level: nseg <= 4 segments of cps = Pv / 128 >= 2 chunks each
+            const unsigned cps = Pv >> 7;
+            unsigned lo[4], hi[4], cl[4], chi[4], nhv[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { const unsigned se = e < nseg ? sz[e] : 0u; lo[e] = 0u; hi[e] = (1u << 22) - 1u; cl[e] = 0u; chi[e] = se; nhv[e] = se >> 1; }
+#pragma unroll 1
+            for (int it = 0; it < 22; ++it) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    if (e < nseg) {
+                        const unsigned mid = (lo[e] + hi[e]) >> 1, lim = mid << 10;
+                        unsigned c0 = 0, c1 = 0;
+                        const uint4* wp = reinterpret_cast<const uint4*>(words + (unsigned)e * Pv) + lane;
+#pragma unroll 2
+                        for (unsigned q = 0; q < cps; ++q) {
+                            const uint4 v = wp[32u * q];
+                            c0 += (v.x < lim) + (v.z < lim);
+                            c1 += (v.y < lim) + (v.w < lim);
+                        }
+                        const unsigned c = __reduce_add_sync(FULL, c0 + c1);
+                        if (c <= nhv[e]) { lo[e] = mid; cl[e] = c; } else { hi[e] = mid; chi[e] = c; }
+                    }
+                }
+            }
+            unsigned medw[4], predw[4], succw[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                medw[e] = PAD; predw[e] = 0u; succw[e] = PAD;
+                if (e < nseg && sz[e]) {
+                    const unsigned lim0 = lo[e] << 10, lim1 = (lo[e] + 1u) << 10;
+                    unsigned a = PAD, b = 0u, c2 = PAD;
+                    const uint4* wp = reinterpret_cast<const uint4*>(words + (unsigned)e * Pv) + lane;
+#pragma unroll 2
+                    for (unsigned q = 0; q < cps; ++q) {
+                        const uint4 v = wp[32u * q];
+                        const unsigned vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            a = min(a, vv[u] >= lim0 ? vv[u] : PAD);
+                            b = max(b, vv[u] < lim0 ? vv[u] : 0u);
+                            c2 = min(c2, vv[u] >= lim1 ? vv[u] : PAD);
+                        }
+                    }
+                    medw[e] = __reduce_min_sync(FULL, a); predw[e] = __reduce_max_sync(FULL, b); succw[e] = __reduce_min_sync(FULL, c2);
+                    // singleton prefix classes at ranks nh-1, nh, nh+1
+                    const unsigned limp = predw[e] & ~1023u, lims = (succw[e] | 1023u) + 1u;
+                    unsigned cp = 0, cs = 0;
+#pragma unroll 2
+                    for (unsigned q = 0; q < cps; ++q) {
+                        const uint4 v = wp[32u * q];
+                        cp += (v.x < limp) + (v.y < limp) + (v.z < limp) + (v.w < limp);
+                        cs += (v.x < lims) + (v.y < lims) + (v.z < lims) + (v.w < lims);
+                    }
+                    cp = __reduce_add_sync(FULL, cp); cs = __reduce_add_sync(FULL, cs);
+                    if (chi[e] - cl[e] != 1u || cl[e] != nhv[e] || succw[e] == PAD || cp + 1u != cl[e] || cs != chi[e] + 1u) bail = 1;
+                }
+            }
+            if (!bail) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    if (e < nseg && sz[e]) {
+                        if (lane == 0) {
+                            const int64_t o = (int64_t)(A.gt0 + t) * A.nn_all + S.gid[cur][e];
+                            A.thr[o] = ord2f(kl[ids[medw[e] & 1023u]]);
+                            A.mlo[o] = ord2f(kl[ids[predw[e] & 1023u]]);
+                            A.mhi[o] = ord2f(kl[ids[succw[e] & 1023u]]);
+                        }
+                        unsigned baseL = (unsigned)e * Pv, baseR = (unsigned)e * Pv + Pv / 2;
+                        const uint4* wp = reinterpret_cast<const uint4*>(words + (unsigned)e * Pv) + lane;
+                        const uint4* ip = reinterpret_cast<const uint4*>(ids + (unsigned)e * Pv) + lane;
+                        const unsigned mw = medw[e];
+#pragma unroll 1
+                        for (unsigned q = 0; q < cps; ++q) {
+                            const uint4 v = wp[32u * q], iv = ip[32u * q];
+                            const unsigned vv[4] = {v.x, v.y, v.z, v.w}, ii[4] = {iv.x, iv.y, iv.z, iv.w};
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const bool valid = vv[u] != PAD, isL = vv[u] < mw;
+                                const unsigned bL = __ballot_sync(FULL, isL), bR = __ballot_sync(FULL, valid && !isL);
+                                const unsigned dst = isL ? baseL + __popc(bL & lt) : baseR + __popc(bR & lt);
+                                if (valid) idn[dst] = ii[u];
+                                baseL += __popc(bL); baseR += __popc(bR);
+                            }
+                        }
+                    }
+                }
+            }
+        } else if (!bail) {
+            // ================= sort level: every aligned block of Pv <= 128 slots ascending, one 128-slot chunk at a time
+#pragma unroll 1
+            for (unsigned c = 0; c < 8; ++c) {
+                const uint4 v = *reinterpret_cast<const uint4*>(words + 128u * c + 4u * lane);
+                if (__all_sync(FULL, v.x == PAD)) continue;                  // chunk without elements (real elements come first)
+                unsigned w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (unsigned k = 2; k <= 128; k <<= 1) {
+                    if (k <= Pv) {
+#pragma unroll
+                        for (unsigned j = k >> 1; j >= 1; j >>= 1) {
+                            if (j >= 4) {
+                                const unsigned lj = j >> 2;
+                                const bool lower = (lane & lj) == 0, asc = k == Pv || ((4u * lane) & k) == 0;
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) {
+                                    const unsigned o = __shfl_xor_sync(FULL, w4[u], lj);
+                                    w4[u] = (asc == lower) ? min(w4[u], o) : max(w4[u], o);
+                                }
+                            } else {
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) {
+                                    const int u2 = u ^ (int)j;
+                                    if (u < u2) {
+                                        const bool asc = k == Pv || ((4u * lane + u) & k) == 0;
+                                        const unsigned a = w4[u], b = w4[u2];
+                                        w4[u] = asc ? min(a, b) : max(a, b);
+                                        w4[u2] = asc ? max(a, b) : min(a, b);
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+                // the row ids in sorted order, left / right halves at the children's slots; tie candidates flagged
+                const unsigned nx0 = __shfl_down_sync(FULL, w4[0], 1);
+                int tie = 0;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const unsigned x = 128u * c + 4u * lane + u, e = x >> lpv, i = x & (Pv - 1u), se = sz[e], nh = se >> 1;
+                    if (i < se) idn[i < nh ? x : e * Pv + Pv / 2 + (i - nh)] = ids[w4[u] & 1023u];
+                    const unsigned nx = u < 3 ? w4[u < 3 ? u + 1 : 3] : (lane < 31 ? nx0 : PAD);
+                    if (i + 1u < se && (w4[u] >> 10) == (nx >> 10)) tie = 1;
+                }
+                // the sorted words go back (the fix-up below finds the tie positions in them)
+                *reinterpret_cast<uint4*>(words + 128u * c + 4u * lane) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+                if (tie) bail = 2;                                           // (2: not a bail yet)
+            }
+            __syncwarp();
+            if (__any_sync(FULL, bail == 2)) {
+                // neighbours with equal prefixes: their order is decided by the full keys (a swap exchanges two elements of the
+                // SAME prefix, so the tie positions stay what they are); equal FULL keys need the reference's incoming order
+                bail = 0;
+                auto slot_of = [&](unsigned e, unsigned i, unsigned se) { const unsigned nh = se >> 1; return i < nh ? e * Pv + i : e * Pv + Pv / 2 + (i - nh); };
+                for (int guard = 0; guard < 128 && !bail; ++guard) {
+                    int swapped = 0;
+                    for (int par = 0; par < 2; ++par) {
+                        for (unsigned x = 2u * lane + (unsigned)par; x + 1u < 1024u; x += 64u) {
+                            const unsigned e = x >> lpv, i = x & (Pv - 1u), se = sz[e];
+                            if (i + 1u < se && (words[x] >> 10) == (words[x + 1u] >> 10)) {
+                                const unsigned sa = slot_of(e, i, se), sb = slot_of(e, i + 1u, se);
+                                const uint32_t ia = idn[sa], ib = idn[sb];
+                                const ull fa = kl[ia], fb = kl[ib];
+                                if (fa == fb) bail = 1;
+                                else if (fa > fb) { idn[sa] = ib; idn[sb] = ia; swapped = 1; }
+                            }
+                        }
+                        __syncwarp();
+                    }
+                    bail = __any_sync(FULL, bail);
+                    if (!__any_sync(FULL, swapped)) break;
+                }
+            }
+            if (!bail) {
+                if (lane < (unsigned)nseg && sz[lane]) {
+                    const unsigned e = lane, se = sz[e], nh = se >> 1, oL = e * Pv, oR = e * Pv + Pv / 2;
+                    const ull th = kl[idn[oR]];
+                    const ull ml = kl[idn[oL + nh - 1]], mh = kl[idn[oR + 1]];      // se >= 3 (checked above)
+                    const int64_t o = (int64_t)(A.gt0 + t) * A.nn_all + S.gid[cur][e];
+                    A.thr[o] = ord2f(th); A.mlo[o] = ord2f(ml); A.mhi[o] = ord2f(mh);
+                }
+            } else {
+                // the segments' row ids sit in idn (sorted by prefix): hand them back from there
+                for (int e = 0; e < nseg; ++e) {
+                    const unsigned se = sz[e], nh = se >> 1;
+                    for (unsigned i = lane; i < se; i += 32) perm[S.ps[cur][e] + i] = idn[i < nh ? (unsigned)e * Pv + i : (unsigned)e * Pv + Pv / 2 + (i - nh)];
+                }
+                rc = 2;
+                break;
+            }
+        }
+        bail = __any_sync(FULL, bail);
+        if (bail) {
+            // the unfinished segments' row ids go back to their ranges of perm: the slice is a permutation of the node's points again
+            for (int e = 0; e < nseg; ++e)
+                for (unsigned i = lane; i < sz[e]; i += 32) perm[S.ps[cur][e] + i] = ids[(unsigned)e * Pv + i];
+            rc = 2;
+            break;
+        }
+        __syncwarp();
+        // ---- children that are Tips: final
+        if (anytip) {
+            for (int c = 0; c < 2 * nseg; ++c) {
+                const unsigned ls = S.lsz[c];
+                for (unsigned i = lane; i < ls; i += 32) perm[S.ps[nxt][c] + i] = idn[(unsigned)c * (Pv / 2) + i];
+            }
+        }
+        __syncwarp();
+        cur = nxt;
+        rc = anyint ? 1 : 0;
+    }
+    if (rc == 1) {                               // deeper than five levels (the host never routes such a subtree here): hand back what is left
+        for (int e = 0; e < 32; ++e)
+            for (unsigned i = lane; i < S.sz[cur][e]; i += 32) perm[S.ps[cur][e] + i] = S.ids[cur][(unsigned)e * 32u + i];
+    }
+    if (rc != 0 && lane == 0) *flag = 1;         // tie / tiny segment (rc 2)
+}
+
+// =====================================================================================================
 // host orchestration
 // =====================================================================================================
 static unsigned next_pow2_host(unsigned v) { unsigned p = 1; while (p < v) p <<= 1; return p; }
@@ -2615,6 +2944,19 @@ int rpf_bottom_launch(rpf_handle* h, const BottomArgs& B, int nroots, int tg, bo
         while (levels > 0 && (slots >> levels) == 0) slots <<= 1;          // slots >= 2^levels
         if (slots > 8192 || levels > rpf_bottom_fast_levels()) return rpf_fail(h, RPF_ERR_ARG, "internal: subtree too deep for the fast bottom kernel");
         const bool deep = levels > 9, shallow = levels <= 5;
+        BottomArgs B2 = B;
+        if (h->bottom_select && slots == 1024 && levels >= 1 && levels <= 5 && !B.given_order && B.kmin && B.kmax && !B.only) {
+            // warp-per-node select / partition kernel first; k_bottom3 below then only runs the nodes it flagged
+            uint8_t* redo = (uint8_t*)h->ws_get(WS_BOT_REDO, (size_t)std::max(h->T, B.gt0 + tg) * nroots);
+            if (!redo) return rpf_fail(h, RPF_ERR_NOMEM, h->err);
+            redo += (size_t)B.gt0 * nroots;                                 // concurrent branches work on disjoint trees
+            RPF_CUDA(h, cudaMemsetAsync(redo, 0, (size_t)tg * nroots, h->stream));
+            const size_t smem4 = sizeof(B4Warp) * B4_WPC;
+            RPF_CUDA(h, cudaFuncSetAttribute(k_bottom4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
+            RPF_LAUNCH(h, PH_BOTTOM, k_bottom4, dim3((unsigned)((nroots + B4_WPC - 1) / B4_WPC), (unsigned)tg), B4_WPC * 32, smem4, B, redo, nroots);
+            B2.only = redo;
+        }
+        const BottomArgs& B = B2;
 #define RPF_BOT_CASE(SL, NT_)                                                                                         \
         case SL: return deep ? launch_bottom_fast<NT_, BOT2_TAB_DEEP>(h, B, nroots, tg)                              \
                              : (shallow ? launch_bottom_fast<NT_, BOT2_TAB_SHALLOW>(h, B, nroots, tg) : launch_bottom_fast<NT_, BOT2_TAB>(h, B, nroots, tg));

@@ -348,6 +348,8 @@ void rpf_destroy(rpf_handle* h) {
     rpf_insert_drop(h);
     if (h->ownX && h->dX) cudaFree((void*)h->dX);
     if (h->d_xlast) cudaFree(h->d_xlast);
+    if (h->dX32) cudaFree(h->dX32);
+    if (h->d_xmax) cudaFree(h->d_xmax);
     free_hp_dev(h); free_topo_dev(h); free_forest_dev(h);
     if (h->stream_plan && h->stream_plan_free) h->stream_plan_free(h->stream_plan);
     if (h->build_graph) cudaGraphExecDestroy(h->build_graph);
@@ -1177,9 +1179,11 @@ int rpf_set_option(rpf_handle* h, const char* name, int64_t value) {
     if (s == "force_generic_bottom") { h->force_generic_bottom = value != 0; return RPF_OK; }
     if (s == "bottom_words64") { h->bottom_words64 = value != 0; return RPF_OK; }
     if (s == "force_simple_topk") { h->force_simple_topk = value != 0; return RPF_OK; }
+    if (s == "knn_filter32") { h->knn_filter32 = (int)value; return RPF_OK; }
     if (s == "force_simple_knn") { h->force_simple_knn = value != 0; return RPF_OK; }
     if (s == "no_query_order") { h->no_query_order = value != 0; return RPF_OK; }
     if (s == "project_variant") { h->project_variant = (int)value; return RPF_OK; }
+    if (s == "bottom_select") { h->bottom_select = (int)value; return RPF_OK; }
     if (s == "fused_top") { h->fused_top = (int)value; return RPF_OK; }
     if (s == "rerank_gemm") { h->rerank_gemm = (int)value; return RPF_OK; }
     if (s == "project_prefetch") { h->project_prefetch = (int)value; return RPF_OK; }

@@ -282,6 +282,10 @@ struct QArgs {
     double* dist;
     uint32_t* ids;
     int32_t* count;
+    const float* X32;          // k_knn_f32: fp32 image of X (row i at X32 + i * d)
+    const double* xmax;        // k_knn_f32: [1] largest row norm of X
+    uint8_t* fb;               // k_knn_f32: [nq] set when the query must be answered by the exact kernel
+    const uint8_t* only;       // k_knn_tma as the second pass: answer only the queries whose flag is set
 };
 
 // number of leading components the metric visits for data row `id` and query q:
@@ -460,6 +464,7 @@ __global__ void __launch_bounds__(KT_NT) k_knn_tma(QArgs A, int rows_per_stage, 
     double* sq = (double*)(cid + 2 * KT_BUF);
     uint32_t* pre = (uint32_t*)(sq + ((A.d + 3) & ~3));
     const int64_t q = A.order ? (int64_t)A.order[blockIdx.x] : (int64_t)blockIdx.x;
+    if (A.only && !A.only[q]) return;                                            // second pass of k_knn_f32: flagged queries only
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned nslots = (unsigned)A.T * A.S;
     const int R = rows_per_stage;
@@ -569,6 +574,248 @@ __global__ void __launch_bounds__(KT_NT) k_knn_tma(QArgs A, int rows_per_stage, 
         A.ids[q * k + i] = ok ? sid[i] : 0xffffffffu;
     }
     if (tid == 0 && A.count) A.count[q] = (int32_t)nbest;
+}
+
+
+// ---------------------------------------------------------------------------------------------------
+// knn with an fp32 FILTER pass in front of the exact re-rank.
+// k_knn_tma moves 8d bytes per candidate and is bound by how many rows fit the shared-memory ring (two 32-row stages per CTA:
+// ~90 KB in flight per SM against ~2 us of latency = 45 GB/s per SM).  The reference's answer only needs the exact distance
+// of the FEW candidates that can be among the k nearest.  So: (A) every candidate row is streamed from an fp32 image of X
+// (half the bytes, twice the rows in flight, four ring stages) and gets an approximate distance d~ in fp32 arithmetic;
+// with u = 2^-24, |d~ - d| <= delta d + eta for delta = 2 (d + 8) u, eta = 4 u (|q| + max|x|) + 2^-70 sqrt(d)  (rounding of x and
+// q to fp32, of the differences, of the d-term sum, of the square root; underflow of squares) -- a 2x over-estimate of the
+// standard bounds.  If tau~ is the k-th smallest d~ seen so far, every candidate of the exact top-k has
+// d~ <= tau~ (1 + 4 delta) + 4 eta; the others are dropped.  (B) the survivors (k plus whatever lies within the margin: a
+// handful) get their 8d-byte rows staged and the exact distance of metricDDL2 (Internal.hs:403-406: left to right,
+// separate roundings), and the final order is the (distance, position in the reference's concatenation order) sort of
+// k_knn_tma -- same ids, same distance bits, same tie order.  Queries with more than KT_SREG survivors (duplicate rows,
+// integer data) or non-finite / huge norms are flagged and answered by k_knn_tma in a second launch.
+// ---------------------------------------------------------------------------------------------------
+#define KF_STAGES 4
+#define KF_NPROD 3
+__global__ void k_x32_convert(const double* __restrict__ X, int64_t n, int d, float* __restrict__ X32, ull* __restrict__ xmax_bits) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    double best = 0.0;
+    for (int64_t i = w; i < n; i += nw) {
+        double s = 0.0;
+        for (int j = lane; j < d; j += 32) { const double x = X[i * d + j]; X32[i * d + j] = __double2float_rn(x); s += x * x; }
+        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        s = sqrt(s);
+        if (!(s <= 1e300)) s = __longlong_as_double(0x7ff0000000000000LL);      // NaN / Inf rows: the filter is not used
+        best = fmax(best, s);
+    }
+    if (lane == 0) atomicMax(xmax_bits, (ull)__double_as_longlong(best));
+}
+
+__global__ void __launch_bounds__(KT_NT) k_knn_f32(QArgs A, int rows_per_stage, int pitch32, int pitch64, int nb_exact) {
+    __shared__ uint32_t part[KT_NT + 1];
+    __shared__ unsigned s_n, s_nsurv;
+    __shared__ uint32_t sh[264];
+    __shared__ ull sh64;
+    __shared__ double s_thr, s_qn;
+    __shared__ __align__(8) uint64_t full_bar[KF_STAGES], empty_bar[KF_STAGES], xbar;
+    extern __shared__ __align__(16) unsigned char dyn[];
+    unsigned char* stage_buf = dyn;                                              // phase A: [KF_STAGES][rows][pitch32]; phase B: [nb_exact][pitch64]
+    const size_t stage_bytes = (size_t)KF_STAGES * rows_per_stage * pitch32;   // >= nb_exact * pitch64 (host)
+    ull* skey = (ull*)(dyn + ((stage_bytes + 15) & ~(size_t)15));
+    ull* rkey = skey + KT_BUF;
+    uint32_t* spos = (uint32_t*)(rkey + KT_SREG);
+    uint32_t* sid = spos + KT_BUF;
+    uint32_t* rpos = sid + KT_BUF;
+    uint32_t* rid = rpos + KT_SREG;
+    uint32_t* cid = rid + KT_SREG;                                               // [2][KT_BUF] row ids of the current / next chunk
+    double* sq = (double*)(cid + 2 * KT_BUF);
+    float* sqf = (float*)(sq + ((A.d + 3) & ~3));
+    uint32_t* pre = (uint32_t*)(sqf + ((A.d + 3) & ~3));
+    const int64_t q = A.order ? (int64_t)A.order[blockIdx.x] : (int64_t)blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned nslots = (unsigned)A.T * A.S;
+    const int R = rows_per_stage;
+    const uint32_t row_bytes = (uint32_t)A.d * 4u;
+
+    if (tid == 0) {
+        for (int s2 = 0; s2 < KF_STAGES; ++s2) { mbar_init(&full_bar[s2], KF_NPROD); mbar_init(&empty_bar[s2], 1); }
+        mbar_init(&xbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        s_nsurv = 0; s_thr = __longlong_as_double(0x7ff0000000000000LL);
+    }
+    for (int j = tid; j < A.d; j += KT_NT) { const double v = A.Q[q * A.d + j]; sq[j] = v; sqf[j] = __double2float_rn(v); }
+    load_slots(A, q, A.T, pre, KT_NT);
+    slot_prefix<KT_NT>(pre, nslots, part);
+    if (warp == 0) {                                                             // |q|
+        double s = 0.0;
+        for (int j = lane; j < A.d; j += 32) s += sq[j] * sq[j];
+        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        if (lane == 0) s_qn = sqrt(s);
+    }
+    __syncthreads();
+    const uint32_t C = pre[nslots];
+    const unsigned k = (unsigned)A.k, CHK = KT_BUF - KT_SREG;                   // a chunk's survivors always fit next to the kept front
+    const double xm = *A.xmax, qn = s_qn;
+    if (!(xm < 1e18) || !(qn < 1e18)) {                                          // fp32 would overflow: exact kernel
+        if (tid == 0) A.fb[q] = 1;
+        return;
+    }
+    const double delta = 2.0 * (double)(A.d + 8) * 5.9604644775390625e-8;       // 2 (d + 8) u
+    const double eta = 4.0 * 5.9604644775390625e-8 * (qn + xm) + 8.470329472543003e-22 * sqrt((double)A.d);
+    auto resolve = [&](uint32_t base, unsigned m, uint32_t* dst, unsigned r, unsigned nthr) {
+        for (unsigned j0 = r; j0 < m; j0 += 4 * nthr) {          // four independent segs -> perm chains in flight per thread
+            const uint32_t* src[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const unsigned j = j0 + u * nthr;
+                src[u] = nullptr;
+                if (j < m) {
+                    const uint32_t c = base + j;
+                    const unsigned slot = find_slot(pre, nslots, c);
+                    const int tt = slot / A.S;
+                    const uint32_t g = A.segs[(q * A.T + tt) * (int64_t)A.S + (slot % A.S)];
+                    src[u] = A.perm + (int64_t)tt * A.n + A.nstart[g] + (c - pre[slot]);
+                }
+            }
+            uint32_t v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = src[u] ? __ldg(src[u]) : 0u;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) if (src[u]) dst[j0 + u * nthr] = v[u];
+        }
+    };
+    resolve(0, min((uint32_t)CHK, C), cid, tid, KT_NT);
+    __syncthreads();
+    // ================= phase A: approximate distances of all candidates; survivors = (fp32 bits of d~ << 32, position, row id)
+    uint32_t uses = 0;
+    int cb = 0;
+    for (uint32_t base = 0; base < C; base += CHK, cb ^= 1) {
+        const unsigned m = min((uint32_t)CHK, C - base);
+        const unsigned ntiles = (m + R - 1) / R;
+        const uint32_t nbase = base + CHK;
+        const unsigned next_m = nbase < C ? min((uint32_t)CHK, C - nbase) : 0u;
+        const uint32_t* ids = cid + cb * KT_BUF;
+        if (warp < KF_NPROD) {
+            // ---- producers: warp p issues the rows p, p + NPROD, ... of every tile (lane l: row l * NPROD + p)
+            for (unsigned ti = 0; ti < ntiles; ++ti) {
+                const uint32_t u = uses + ti, st = u % KF_STAGES, round = u / KF_STAGES;
+                if (round > 0) mbar_wait(&empty_bar[st], (round - 1) & 1);
+                const unsigned nrows = min((unsigned)R, m - ti * R);
+                const unsigned rloc = (unsigned)lane * KF_NPROD + (unsigned)warp;
+                const bool valid = rloc < nrows;
+                const uint32_t id = valid ? ids[ti * R + rloc] : 0u;
+                const unsigned mine = nrows > (unsigned)warp ? (nrows - (unsigned)warp + KF_NPROD - 1) / KF_NPROD : 0u;
+                if (lane == 0) {
+                    if (mine) mbar_arrive_expect_tx(&full_bar[st], mine * row_bytes);
+                    else mbar_arrive(&full_bar[st]);
+                }
+                __syncwarp();
+                if (valid) bulk_g2s(stage_buf + ((size_t)st * R + rloc) * pitch32, A.X32 + (int64_t)id * A.d, row_bytes, &full_bar[st]);
+            }
+        } else if (warp < KF_NPROD + KF_STAGES) {
+            // ---- consumer of stage warp - NPROD: one lane per staged row, fp32, four partial sums
+            const uint32_t st = warp - KF_NPROD;
+            const float thr = (float)s_thr;                                      // (rounded up below: s_thr holds a float value)
+            const int d4 = A.d >> 2;
+            for (unsigned ti = 0; ti < ntiles; ++ti) {
+                const uint32_t u = uses + ti;
+                if (u % KF_STAGES != st) continue;
+                mbar_wait(&full_bar[st], (u / KF_STAGES) & 1);
+                const unsigned j = ti * R + lane;
+                if (lane < R && j < m) {
+                    const float4* row = (const float4*)(stage_buf + ((size_t)st * R + lane) * pitch32);
+                    const float4* qf = (const float4*)sqf;
+                    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 4
+                    for (int jj = 0; jj < d4; ++jj) {
+                        const float4 x = row[jj], y = qf[jj];
+                        const float t0 = x.x - y.x, t1 = x.y - y.y, t2 = x.z - y.z, t3 = x.w - y.w;
+                        a0 = fmaf(t0, t0, a0); a1 = fmaf(t1, t1, a1); a2 = fmaf(t2, t2, a2); a3 = fmaf(t3, t3, a3);
+                    }
+                    const float da = sqrtf((a0 + a1) + (a2 + a3));
+                    if (da <= thr) {
+                        const unsigned p = atomicAdd(&s_nsurv, 1u);
+                        skey[p] = (ull)__float_as_uint(da) << 32; spos[p] = base + j; sid[p] = ids[j];
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty_bar[st]);
+            }
+        } else if (next_m) {
+            resolve(nbase, next_m, cid + (cb ^ 1) * KT_BUF, (unsigned)tid - 32u * (KF_NPROD + KF_STAGES), (unsigned)KT_NT - 32u * (KF_NPROD + KF_STAGES));
+        }
+        uses += ntiles;
+        __syncthreads();
+        const unsigned nsurv = s_nsurv;
+        if (next_m == 0 || nsurv + next_m > KT_BUF) {
+            // tau~ = k-th smallest approximate distance so far (4 radix passes: the keys are 32-bit); keep what lies within the margin
+            if (nsurv > k) {
+                uint32_t cl, ce;
+                const ull v = cta_radix_select<KT_NT, 4>(nsurv, k - 1, [&](uint32_t i) { return skey[i]; }, sh, &sh64, cl, ce);
+                const double tau = (double)__uint_as_float((unsigned)(v >> 32));
+                const float thr2 = __double2float_ru(tau * (1.0 + 4.0 * delta) + 4.0 * eta);
+                if (tid == 0) s_n = 0;
+                __syncthreads();
+                const ull tb = (ull)__float_as_uint(thr2) << 32;
+                for (unsigned i = tid; i < nsurv; i += KT_NT) {
+                    const ull kv = skey[i];
+                    if (kv <= tb) { const unsigned p = atomicAdd(&s_n, 1u); if (p < KT_SREG) { rkey[p] = kv; rpos[p] = spos[i]; rid[p] = sid[i]; } }
+                }
+                __syncthreads();
+                const unsigned cnt = s_n;
+                if (cnt > KT_SREG) {                                             // too many candidates within the margin: exact kernel
+                    if (tid == 0) A.fb[q] = 1;
+                    return;
+                }
+                for (unsigned i = tid; i < cnt; i += KT_NT) { skey[i] = rkey[i]; spos[i] = rpos[i]; sid[i] = rid[i]; }
+                if (tid == 0) { s_nsurv = cnt; s_thr = (double)thr2; }
+                __syncthreads();
+            }
+        }
+    }
+    // ================= phase B: exact distances of the survivors, then the reference's (distance, position) order
+    const unsigned ns = s_nsurv;
+    if (ns > KT_SREG) { if (tid == 0) A.fb[q] = 1; return; }
+    const uint32_t row_bytes64 = (uint32_t)A.d * 8u;
+    uint32_t xphase = 0;
+    for (unsigned b0 = 0; b0 < ns; b0 += (unsigned)nb_exact, xphase ^= 1) {
+        const unsigned nb = min((unsigned)nb_exact, ns - b0);
+        __syncthreads();                                                         // the buffer's previous readers are done
+        if (warp == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            if (lane == 0) mbar_arrive_expect_tx(&xbar, nb * row_bytes64);
+            __syncwarp();
+            for (unsigned r = lane; r < nb; r += 32) bulk_g2s(stage_buf + (size_t)r * pitch64, A.X + (int64_t)sid[b0 + r] * A.d, row_bytes64, &xbar);
+        }
+        mbar_wait(&xbar, xphase);
+        if ((unsigned)tid < nb) {
+            const double acc = row_dist2((const double2*)(stage_buf + (size_t)tid * pitch64), (const double2*)sq, A.d >> 1);
+            skey[b0 + tid] = (ull)__double_as_longlong(__dsqrt_rn(acc));
+        }
+    }
+    __syncthreads();
+    const unsigned nbest = topk_front<KT_NT, KT_SREG>(skey, spos, sid, ns, k, 0, rkey, rpos, rid, sh, &sh64, &s_n);
+    for (unsigned i = tid; i < k; i += KT_NT) {
+        const bool ok = i < nbest;
+        A.dist[q * k + i] = ok ? __longlong_as_double((long long)skey[i]) : __longlong_as_double(0x7ff0000000000000LL);
+        A.ids[q * k + i] = ok ? sid[i] : 0xffffffffu;
+    }
+    if (tid == 0 && A.count) A.count[q] = (int32_t)nbest;
+}
+
+// fp32 image of X + largest row norm, rebuilt when the points changed
+static int ensure_x32(rpf_handle* h) {
+    if (h->dX32 && h->x32_src == h->dX && h->x32_n == h->n && h->x32_d == h->d && h->x32_epoch == h->cfg_epoch) return RPF_OK;
+    const size_t bytes = std::max<size_t>((size_t)h->n * h->d * 4, 16);
+    if (!h->dX32 || h->x32_bytes < bytes) {
+        if (h->dX32) { cudaStreamSynchronize(h->stream); cudaFree(h->dX32); h->dX32 = nullptr; h->x32_bytes = 0; }
+        if (cudaMalloc(&h->dX32, bytes) != cudaSuccess) { cudaGetLastError(); return 1; }      // no room: the caller uses the exact kernel
+        h->x32_bytes = bytes;
+    }
+    if (!h->d_xmax && cudaMalloc(&h->d_xmax, 16) != cudaSuccess) { cudaGetLastError(); return 1; }
+    RPF_CUDA(h, cudaMemsetAsync(h->d_xmax, 0, 8, h->stream));
+    RPF_LAUNCH(h, PH_Q_PROJECT, k_x32_convert, 148 * 8, 256, 0, h->dX, h->n, h->d, h->dX32, (ull*)h->d_xmax);
+    h->x32_src = h->dX; h->x32_n = h->n; h->x32_d = h->d; h->x32_epoch = h->cfg_epoch;
+    return RPF_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1205,6 +1452,25 @@ int rpf_knn_impl(rpf_handle* h, const double* Q, const int32_t* q_last, int64_t 
     const size_t dyn_tma = (size_t)KT_STAGES * rows * pitch + (size_t)(KT_BUF + KT_SREG) * 16 + (size_t)2 * KT_BUF * 4 + tail;
     const bool use_tma = (h->d % 2 == 0) && rows >= 1 && k <= KT_BUF / 2 && dyn_tma <= 112 * 1024 && !h->force_simple_knn &&
                          (((uintptr_t)h->dX & 15) == 0) && !h->d_xlast;     // SVector data: per-candidate prefix lengths -> gather kernel
+    // fp32 filter pass + exact re-rank of the survivors (plain knn, whole-forest batches); queries it flags, and every other
+    // case, go through the exact TMA kernel
+    const int pitch32 = h->d * 4 + 16;
+    const int rows32 = (int)std::min<size_t>(32, (size_t)(72 * 1024) / ((size_t)KF_STAGES * pitch32));
+    const int nb_exact = rows32 >= 1 ? (int)std::min<size_t>(KT_NT, ((size_t)KF_STAGES * rows32 * pitch32) / (size_t)pitch) : 0;
+    const size_t dyn_f32 = (((size_t)KF_STAGES * std::max(rows32, 1) * pitch32 + 15) & ~(size_t)15) + (size_t)(KT_BUF + KT_SREG) * 16 + (size_t)2 * KT_BUF * 4 +
+                           (size_t)((h->d + 3) & ~3) * 12 + ((size_t)h->T * st.S + 1) * 4;
+    if (run_gather && use_tma && h->knn_filter32 && !dedup && grid_q == (unsigned)nq && (h->d % 4 == 0) && rows32 >= 4 && nb_exact >= 1 &&
+        k <= KT_SREG / 4 && dyn_f32 <= 112 * 1024 && !h->capturing && ensure_x32(h) == RPF_OK) {
+        uint8_t* fb = (uint8_t*)h->ws_get(WS_KNN_FB, (size_t)nq);
+        if (!fb) return RPF_ERR_NOMEM;
+        RPF_CUDA(h, cudaMemsetAsync(fb, 0, (size_t)nq, h->stream));
+        QArgs F = A;
+        F.X32 = h->dX32; F.xmax = h->d_xmax; F.fb = fb;
+        RPF_CUDA(h, cudaFuncSetAttribute(k_knn_f32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_f32));
+        RPF_CUDA(h, cudaFuncSetAttribute(k_knn_f32, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        RPF_LAUNCH(h, PH_Q_KNN, k_knn_f32, grid_q, KT_NT, dyn_f32, F, rows32, pitch32, pitch, nb_exact);
+        A.only = fb;
+    }
     if (!run_gather) {
     } else if (use_tma) {
         RPF_CUDA(h, cudaFuncSetAttribute(k_knn_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_tma));

@@ -10,11 +10,12 @@ __device__ __forceinline__ unsigned next_pow2_u32(unsigned v) { return v <= 1 ? 
 // 8-bit MSD radix select of rank r (0-based) over `c` uint64 values fetched by get(i); every thread of the CTA
 // must call it.  Returns the selected value; cl = #values < it, ce = #values == it.
 // sh: >= 264 uint32 of shared memory, sh64: 1 uint64 of shared memory.
-template <int NT, typename Get>
+// PASSES < 8: only the top 8 * PASSES bits are resolved (keys whose low bits are zero, e.g. 32-bit values << 32).
+template <int NT, int PASSES = 8, typename Get>
 __device__ ull cta_radix_select(uint32_t c, uint32_t r, Get get, uint32_t* sh, ull* sh64, uint32_t& cl, uint32_t& ce) {
     ull prefix = 0;
     uint32_t rr = r, below = 0;
-    for (int pass = 0; pass < 8; ++pass) {
+    for (int pass = 0; pass < PASSES; ++pass) {
         const int shift = 56 - 8 * pass;
         const ull mask_hi = pass == 0 ? 0ull : (~0ull << (shift + 8));
         for (int j = threadIdx.x; j < 256; j += NT) sh[j] = 0;

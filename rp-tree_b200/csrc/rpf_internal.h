@@ -112,7 +112,7 @@ enum rpf_ws_slot {
     WS_Q, WS_KEYSQ, WS_SEGS, WS_CNT, WS_MAXCNT, WS_OUT_D, WS_OUT_I, WS_OUT_C, WS_BF_D, WS_TRUTH_D, WS_TRUTH_I, WS_RECALL,
     WS_CANDCNT, WS_CANDOFF, WS_CANDOUT, WS_MRG_D, WS_MRG_I, WS_MRG_C, WS_QHIST, WS_QORDER,
     WS_S_ARENA0, WS_S_ARENA1, WS_S_CPERM, WS_S_TMPN, WS_S_POOL, WS_QLAST, WS_PRIO, WS_WORKLIST, WS_PBIN, WS_BF_CV, WS_BF_CI, WS_BF_AUX,
-    WS_RR_LEAVES, WS_RR_XN, WS_RR_QN, WS_RR_HIST, WS_RR_START, WS_RR_CC, WS_RR_QOFF, WS_RR_AUX, WS_RR_FB, WS_RR_ENTQ, WS_RR_ENTD, WS_RR_DAP,
+    WS_BOT_REDO, WS_KNN_FB, WS_RR_LEAVES, WS_RR_XN, WS_RR_QN, WS_RR_HIST, WS_RR_START, WS_RR_CC, WS_RR_QOFF, WS_RR_AUX, WS_RR_FB, WS_RR_ENTQ, WS_RR_ENTD, WS_RR_DAP,
     WS_COUNT
 };
 struct WsBuf { void* p = nullptr; size_t cap = 0; };
@@ -181,11 +181,17 @@ struct rpf_handle {
                                          //         finish kernel per level instead of finish_warp -> finish -> ties (measured slower: off)
     int rerank_gemm = 1;                 // option: leaf-grouped FP64 tensor-core re-rank (rerank.cu): 0 = never, 1 = when it pays (d >= 512,
                                          //         >= 2 queries per leaf), 2 = whenever applicable (tests)
+    int bottom_select = 0;               // option: warp-per-node bottom kernel (k_bottom4: median select + partition on the levels whose
+                                         //         children split again, sort only where Tips form); 0 = k_bottom3 everywhere
     int project_prefetch = 1;            // option: L2 prefetch of a later tile in the single-buffer projection kernel
     int project_pipe_maxh = 128;         // option: the pipelined projection kernel is used up to this many hyperplanes per launch
     int project_variant = 0;             // tuning hook: 0 = 1024 threads x 4 points/lane, 1 = 1024 x 2 (two CTAs/SM), 2 = 512 x 4
     bool no_query_order = false;         // test/tuning hook: answer queries in input order (no locality grouping)
     bool force_simple_topk = false;      // test hook: brute-force truth through the nine-pass radix select only
+    int knn_filter32 = 1;                // option: fp32 filter pass in front of the exact re-rank (k_knn_f32): 0 = exact gather kernel only
+    float* dX32 = nullptr; size_t x32_bytes = 0;     // fp32 image of X for the filter pass (built lazily by the first knn after the points change)
+    const double* x32_src = nullptr; int64_t x32_n = -1; int x32_d = -1; uint64_t x32_epoch = 0;
+    double* d_xmax = nullptr;            // [1] largest row norm of X (error margin of the filter)
     bool force_simple_knn = false;       // test hook: per-thread gather knn kernel instead of the TMA ring
     int top_chunk[3] = {0, 0, 0};        // tuning hook: points per CTA of the top-phase hist / compact / relabel kernels (0 = chosen per launch)
     bool lean_top = true;                // option "lean_top": 0 = generic top-phase compact / relabel kernels only (test hook)
@@ -322,6 +328,7 @@ struct BottomArgs {
     const ull* kmin;                     // [Tg][L] key range per (tree, level) (may be a sample's range, may be NULL):
     const ull* kmax;                     //         seeds the key prefixes of 32-bit sort words
     double *thr, *mlo, *mhi;
+    const uint8_t* only;                 // k_bottom3 as the second pass of k_bottom4: [tg][nroots], run a node only if its flag is set
 };
 int rpf_bottom_launch(rpf_handle* h, const BottomArgs& B, int nroots, int tg, bool fast, unsigned max_root, int levels);
 

@@ -66,6 +66,34 @@ def test_build_parity(built, n, d, T, maxd, minl, pnz, kind, cap, generic):
         assert order
 
 
+SELECT_CASES = [
+    # n, d, T, maxd, minl, pnz, kind   (bottom_cap 1024: nodes of 513 .. 1024 points with <= 5 levels below them are eligible)
+    pytest.param(20000, 16, 3, 12, 40, 0.3, "gauss", id="625-point-nodes-4-levels"),
+    pytest.param(31000, 8, 2, 14, 64, 0.5, "mixture", id="968-point-nodes-4-levels"),
+    pytest.param(16000, 6, 3, 12, 70, 0.5, "integer", id="integer-ties-every-node-goes-to-the-second-pass"),
+    pytest.param(16000, 5, 3, 12, 70, 0.6, "dupes", id="duplicate-rows"),
+    pytest.param(30000, 8, 3, 12, 120, 0.5, "outlier", id="outlier-collapses-prefixes"),
+    pytest.param(18000, 8, 2, 12, 150, 0.5, "gauss", id="tips-of-more-than-64-points"),
+    pytest.param(1000, 8, 3, 6, 10, 0.5, "gauss", id="bottom-only-root-node"),
+]
+
+
+@pytest.mark.parametrize("n,d,T,maxd,minl,pnz,kind", SELECT_CASES)
+def test_build_parity_select_bottom(built, n, d, T, maxd, minl, pnz, kind):
+    """Option bottom_select = 1: the warp-per-node kernel (median select + partition where the children split again, sort where
+    Tips form) followed by k_bottom3 on the nodes it flagged (prefix ties, equal keys, odd shapes) gives the oracle's forest."""
+    R, orc = _mods()
+    X = make_data(n, d, 3, kind)
+    hp = orc.gen_hyperplanes(77, T, maxd, pnz, d)
+    f = R.forestBatch(0, maxd, minl, T, pnz, d, X, hyperplanes=hp, bottom_cap=1024, options={"bottom_select": 1})
+    of = orc.Forest(X, hp, T, maxd, minl)
+    problems = []
+    for t in range(T):
+        problems += ["tree %d: %s" % (t, b) for b in compare_tree(f.treeExport(t), of.export(t))]
+    assert not problems, "\n".join(problems[:20])
+    assert f.leafOrderExact()
+
+
 GENERIC_TOP_CASES = [c for c in BUILD_CASES if c.id in (
     "top4-bottom", "top7-cap256", "integer-data-massive-ties", "duplicate-rows", "cap4096-integer-ties",
     "one-outlier-collapses-key-prefixes", "cap8192-top4")]
