@@ -1179,6 +1179,10 @@ int rpf_set_option(rpf_handle* h, const char* name, int64_t value) {
     if (s == "force_generic_bottom") { h->force_generic_bottom = value != 0; return RPF_OK; }
     if (s == "bottom_words64") { h->bottom_words64 = value != 0; return RPF_OK; }
     if (s == "force_simple_topk") { h->force_simple_topk = value != 0; return RPF_OK; }
+    if (s == "knn_f32_stages") { h->knn_f32_cfg[0] = (int)value; return RPF_OK; }
+    if (s == "knn_f32_rows") { h->knn_f32_cfg[1] = (int)value; return RPF_OK; }
+    if (s == "knn_f32_buf") { h->knn_f32_cfg[2] = (int)value; return RPF_OK; }
+    if (s == "knn_f32_sreg") { h->knn_f32_cfg[3] = (int)value; return RPF_OK; }
     if (s == "knn_filter32") { h->knn_filter32 = (int)value; return RPF_OK; }
     if (s == "force_simple_knn") { h->force_simple_knn = value != 0; return RPF_OK; }
     if (s == "no_query_order") { h->no_query_order = value != 0; return RPF_OK; }

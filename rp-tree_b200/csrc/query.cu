@@ -609,24 +609,24 @@ __global__ void k_x32_convert(const double* __restrict__ X, int64_t n, int d, fl
     if (lane == 0) atomicMax(xmax_bits, (ull)__double_as_longlong(best));
 }
 
-__global__ void __launch_bounds__(KT_NT) k_knn_f32(QArgs A, int rows_per_stage, int pitch32, int pitch64, int nb_exact) {
+__global__ void __launch_bounds__(KT_NT) k_knn_f32(QArgs A, int rows_per_stage, int pitch32, int pitch64, int nb_exact, int nstages, int BUF, int SREG) {
     __shared__ uint32_t part[KT_NT + 1];
     __shared__ unsigned s_n, s_nsurv;
     __shared__ uint32_t sh[264];
     __shared__ ull sh64;
     __shared__ double s_thr, s_qn;
-    __shared__ __align__(8) uint64_t full_bar[KF_STAGES], empty_bar[KF_STAGES], xbar;
+    __shared__ __align__(8) uint64_t full_bar[4], empty_bar[4], xbar;
     extern __shared__ __align__(16) unsigned char dyn[];
-    unsigned char* stage_buf = dyn;                                              // phase A: [KF_STAGES][rows][pitch32]; phase B: [nb_exact][pitch64]
-    const size_t stage_bytes = (size_t)KF_STAGES * rows_per_stage * pitch32;   // >= nb_exact * pitch64 (host)
+    unsigned char* stage_buf = dyn;                                              // phase A: [nstages][rows][pitch32]; phase B: [nb_exact][pitch64]
+    const size_t stage_bytes = (size_t)nstages * rows_per_stage * pitch32;   // >= nb_exact * pitch64 (host)
     ull* skey = (ull*)(dyn + ((stage_bytes + 15) & ~(size_t)15));
-    ull* rkey = skey + KT_BUF;
-    uint32_t* spos = (uint32_t*)(rkey + KT_SREG);
-    uint32_t* sid = spos + KT_BUF;
-    uint32_t* rpos = sid + KT_BUF;
-    uint32_t* rid = rpos + KT_SREG;
-    uint32_t* cid = rid + KT_SREG;                                               // [2][KT_BUF] row ids of the current / next chunk
-    double* sq = (double*)(cid + 2 * KT_BUF);
+    ull* rkey = skey + BUF;
+    uint32_t* spos = (uint32_t*)(rkey + SREG);
+    uint32_t* sid = spos + BUF;
+    uint32_t* rpos = sid + BUF;
+    uint32_t* rid = rpos + SREG;
+    uint32_t* cid = rid + SREG;                                               // [2][BUF] row ids of the current / next chunk
+    double* sq = (double*)(cid + 2 * BUF);
     float* sqf = (float*)(sq + ((A.d + 3) & ~3));
     uint32_t* pre = (uint32_t*)(sqf + ((A.d + 3) & ~3));
     const int64_t q = A.order ? (int64_t)A.order[blockIdx.x] : (int64_t)blockIdx.x;
@@ -636,7 +636,7 @@ __global__ void __launch_bounds__(KT_NT) k_knn_f32(QArgs A, int rows_per_stage, 
     const uint32_t row_bytes = (uint32_t)A.d * 4u;
 
     if (tid == 0) {
-        for (int s2 = 0; s2 < KF_STAGES; ++s2) { mbar_init(&full_bar[s2], KF_NPROD); mbar_init(&empty_bar[s2], 1); }
+        for (int s2 = 0; s2 < nstages; ++s2) { mbar_init(&full_bar[s2], KF_NPROD); mbar_init(&empty_bar[s2], 1); }
         mbar_init(&xbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -653,7 +653,7 @@ __global__ void __launch_bounds__(KT_NT) k_knn_f32(QArgs A, int rows_per_stage, 
     }
     __syncthreads();
     const uint32_t C = pre[nslots];
-    const unsigned k = (unsigned)A.k, CHK = KT_BUF - KT_SREG;                   // a chunk's survivors always fit next to the kept front
+    const unsigned k = (unsigned)A.k, CHK = (unsigned)(BUF - SREG);                   // a chunk's survivors always fit next to the kept front
     const double xm = *A.xmax, qn = s_qn;
     if (!(xm < 1e18) || !(qn < 1e18)) {                                          // fp32 would overflow: exact kernel
         if (tid == 0) A.fb[q] = 1;
@@ -693,11 +693,11 @@ __global__ void __launch_bounds__(KT_NT) k_knn_f32(QArgs A, int rows_per_stage, 
         const unsigned ntiles = (m + R - 1) / R;
         const uint32_t nbase = base + CHK;
         const unsigned next_m = nbase < C ? min((uint32_t)CHK, C - nbase) : 0u;
-        const uint32_t* ids = cid + cb * KT_BUF;
+        const uint32_t* ids = cid + cb * BUF;
         if (warp < KF_NPROD) {
             // ---- producers: warp p issues the rows p, p + NPROD, ... of every tile (lane l: row l * NPROD + p)
             for (unsigned ti = 0; ti < ntiles; ++ti) {
-                const uint32_t u = uses + ti, st = u % KF_STAGES, round = u / KF_STAGES;
+                const uint32_t u = uses + ti, st = u % (unsigned)nstages, round = u / (unsigned)nstages;
                 if (round > 0) mbar_wait(&empty_bar[st], (round - 1) & 1);
                 const unsigned nrows = min((unsigned)R, m - ti * R);
                 const unsigned rloc = (unsigned)lane * KF_NPROD + (unsigned)warp;
@@ -711,15 +711,15 @@ __global__ void __launch_bounds__(KT_NT) k_knn_f32(QArgs A, int rows_per_stage, 
                 __syncwarp();
                 if (valid) bulk_g2s(stage_buf + ((size_t)st * R + rloc) * pitch32, A.X32 + (int64_t)id * A.d, row_bytes, &full_bar[st]);
             }
-        } else if (warp < KF_NPROD + KF_STAGES) {
+        } else if (warp < KF_NPROD + nstages) {
             // ---- consumer of stage warp - NPROD: one lane per staged row, fp32, four partial sums
             const uint32_t st = warp - KF_NPROD;
             const float thr = (float)s_thr;                                      // (rounded up below: s_thr holds a float value)
             const int d4 = A.d >> 2;
             for (unsigned ti = 0; ti < ntiles; ++ti) {
                 const uint32_t u = uses + ti;
-                if (u % KF_STAGES != st) continue;
-                mbar_wait(&full_bar[st], (u / KF_STAGES) & 1);
+                if (u % (unsigned)nstages != st) continue;
+                mbar_wait(&full_bar[st], (u / (unsigned)nstages) & 1);
                 const unsigned j = ti * R + lane;
                 if (lane < R && j < m) {
                     const float4* row = (const float4*)(stage_buf + ((size_t)st * R + lane) * pitch32);
@@ -741,12 +741,12 @@ __global__ void __launch_bounds__(KT_NT) k_knn_f32(QArgs A, int rows_per_stage, 
                 if (lane == 0) mbar_arrive(&empty_bar[st]);
             }
         } else if (next_m) {
-            resolve(nbase, next_m, cid + (cb ^ 1) * KT_BUF, (unsigned)tid - 32u * (KF_NPROD + KF_STAGES), (unsigned)KT_NT - 32u * (KF_NPROD + KF_STAGES));
+            resolve(nbase, next_m, cid + (cb ^ 1) * BUF, (unsigned)tid - 32u * (unsigned)(KF_NPROD + nstages), (unsigned)KT_NT - 32u * (unsigned)(KF_NPROD + nstages));
         }
         uses += ntiles;
         __syncthreads();
         const unsigned nsurv = s_nsurv;
-        if (next_m == 0 || nsurv + next_m > KT_BUF) {
+        if (next_m == 0 || nsurv + next_m > (unsigned)BUF) {
             // tau~ = k-th smallest approximate distance so far (4 radix passes: the keys are 32-bit); keep what lies within the margin
             if (nsurv > k) {
                 uint32_t cl, ce;
@@ -758,11 +758,11 @@ __global__ void __launch_bounds__(KT_NT) k_knn_f32(QArgs A, int rows_per_stage, 
                 const ull tb = (ull)__float_as_uint(thr2) << 32;
                 for (unsigned i = tid; i < nsurv; i += KT_NT) {
                     const ull kv = skey[i];
-                    if (kv <= tb) { const unsigned p = atomicAdd(&s_n, 1u); if (p < KT_SREG) { rkey[p] = kv; rpos[p] = spos[i]; rid[p] = sid[i]; } }
+                    if (kv <= tb) { const unsigned p = atomicAdd(&s_n, 1u); if (p < (unsigned)SREG) { rkey[p] = kv; rpos[p] = spos[i]; rid[p] = sid[i]; } }
                 }
                 __syncthreads();
                 const unsigned cnt = s_n;
-                if (cnt > KT_SREG) {                                             // too many candidates within the margin: exact kernel
+                if (cnt > (unsigned)SREG) {                                             // too many candidates within the margin: exact kernel
                     if (tid == 0) A.fb[q] = 1;
                     return;
                 }
@@ -774,7 +774,7 @@ __global__ void __launch_bounds__(KT_NT) k_knn_f32(QArgs A, int rows_per_stage, 
     }
     // ================= phase B: exact distances of the survivors, then the reference's (distance, position) order
     const unsigned ns = s_nsurv;
-    if (ns > KT_SREG) { if (tid == 0) A.fb[q] = 1; return; }
+    if (ns > (unsigned)SREG) { if (tid == 0) A.fb[q] = 1; return; }
     const uint32_t row_bytes64 = (uint32_t)A.d * 8u;
     uint32_t xphase = 0;
     for (unsigned b0 = 0; b0 < ns; b0 += (unsigned)nb_exact, xphase ^= 1) {
@@ -793,7 +793,7 @@ __global__ void __launch_bounds__(KT_NT) k_knn_f32(QArgs A, int rows_per_stage, 
         }
     }
     __syncthreads();
-    const unsigned nbest = topk_front<KT_NT, KT_SREG>(skey, spos, sid, ns, k, 0, rkey, rpos, rid, sh, &sh64, &s_n);
+    const unsigned nbest = topk_front<KT_NT, 128>(skey, spos, sid, ns, k, 0, rkey, rpos, rid, sh, &sh64, &s_n);
     for (unsigned i = tid; i < k; i += KT_NT) {
         const bool ok = i < nbest;
         A.dist[q * k + i] = ok ? __longlong_as_double((long long)skey[i]) : __longlong_as_double(0x7ff0000000000000LL);
@@ -1455,12 +1455,19 @@ int rpf_knn_impl(rpf_handle* h, const double* Q, const int32_t* q_last, int64_t 
     // fp32 filter pass + exact re-rank of the survivors (plain knn, whole-forest batches); queries it flags, and every other
     // case, go through the exact TMA kernel
     const int pitch32 = h->d * 4 + 16;
-    const int rows32 = (int)std::min<size_t>(32, (size_t)(72 * 1024) / ((size_t)KF_STAGES * pitch32));
-    const int nb_exact = rows32 >= 1 ? (int)std::min<size_t>(KT_NT, ((size_t)KF_STAGES * rows32 * pitch32) / (size_t)pitch) : 0;
-    const size_t dyn_f32 = (((size_t)KF_STAGES * std::max(rows32, 1) * pitch32 + 15) & ~(size_t)15) + (size_t)(KT_BUF + KT_SREG) * 16 + (size_t)2 * KT_BUF * 4 +
+    // Occupancy decides here (sweep: profiles/r02_knn_f32_sweep.txt): per query the CTA drains its ring at every chunk end and
+    // runs selects behind barriers, so three or four resident CTAs per SM hide one another's bubbles -- 3 stages x 30 rows
+    // (72 KB per CTA, 3 per SM) for forests with many candidates per query, 2 x 28 (54 KB, 4 per SM) for few.
+    const bool many = h->T >= 16;
+    const int nst = std::max(1, std::min(4, h->knn_f32_cfg[0] ? h->knn_f32_cfg[0] : (many ? 3 : 2)));
+    const int fbuf = h->knn_f32_cfg[2] ? h->knn_f32_cfg[2] : 768, fsreg = h->knn_f32_cfg[3] ? h->knn_f32_cfg[3] : 256;
+    const size_t stage_budget = h->knn_f32_cfg[1] ? (size_t)(72 * 1024) : (many ? (size_t)47600 : (size_t)29700);
+    const int rows32 = (int)std::min<size_t>(h->knn_f32_cfg[1] ? h->knn_f32_cfg[1] : 32, stage_budget / ((size_t)nst * pitch32));
+    const int nb_exact = rows32 >= 1 ? (int)std::min<size_t>(KT_NT, ((size_t)nst * rows32 * pitch32) / (size_t)pitch) : 0;
+    const size_t dyn_f32 = (((size_t)nst * std::max(rows32, 1) * pitch32 + 15) & ~(size_t)15) + (size_t)(fbuf + fsreg) * 16 + (size_t)2 * fbuf * 4 +
                            (size_t)((h->d + 3) & ~3) * 12 + ((size_t)h->T * st.S + 1) * 4;
-    if (run_gather && use_tma && h->knn_filter32 && !dedup && grid_q == (unsigned)nq && (h->d % 4 == 0) && rows32 >= 4 && nb_exact >= 1 &&
-        k <= KT_SREG / 4 && dyn_f32 <= 112 * 1024 && !h->capturing && ensure_x32(h) == RPF_OK) {
+    if (run_gather && use_tma && h->knn_filter32 && !dedup && grid_q == (unsigned)nq && (h->d % 4 == 0) && rows32 >= 4 && rows32 <= 32 && nb_exact >= 1 &&
+        k <= fsreg / 4 && fsreg >= 128 && fbuf >= 2 * fsreg && dyn_f32 <= 112 * 1024 && !h->capturing && ensure_x32(h) == RPF_OK) {
         uint8_t* fb = (uint8_t*)h->ws_get(WS_KNN_FB, (size_t)nq);
         if (!fb) return RPF_ERR_NOMEM;
         RPF_CUDA(h, cudaMemsetAsync(fb, 0, (size_t)nq, h->stream));
@@ -1468,7 +1475,7 @@ int rpf_knn_impl(rpf_handle* h, const double* Q, const int32_t* q_last, int64_t 
         F.X32 = h->dX32; F.xmax = h->d_xmax; F.fb = fb;
         RPF_CUDA(h, cudaFuncSetAttribute(k_knn_f32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_f32));
         RPF_CUDA(h, cudaFuncSetAttribute(k_knn_f32, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        RPF_LAUNCH(h, PH_Q_KNN, k_knn_f32, grid_q, KT_NT, dyn_f32, F, rows32, pitch32, pitch, nb_exact);
+        RPF_LAUNCH(h, PH_Q_KNN, k_knn_f32, grid_q, KT_NT, dyn_f32, F, rows32, pitch32, pitch, nb_exact, nst, fbuf, fsreg);
         A.only = fb;
     }
     if (!run_gather) {

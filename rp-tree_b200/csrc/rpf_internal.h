@@ -188,6 +188,7 @@ struct rpf_handle {
     int project_variant = 0;             // tuning hook: 0 = 1024 threads x 4 points/lane, 1 = 1024 x 2 (two CTAs/SM), 2 = 512 x 4
     bool no_query_order = false;         // test/tuning hook: answer queries in input order (no locality grouping)
     bool force_simple_topk = false;      // test hook: brute-force truth through the nine-pass radix select only
+    int knn_f32_cfg[4] = {0, 0, 0, 0};  // tuning hook: ring stages, rows per stage, entry buffer, side region of k_knn_f32 (0 = default)
     int knn_filter32 = 1;                // option: fp32 filter pass in front of the exact re-rank (k_knn_f32): 0 = exact gather kernel only
     float* dX32 = nullptr; size_t x32_bytes = 0;     // fp32 image of X for the filter pass (built lazily by the first knn after the points change)
     const double* x32_src = nullptr; int64_t x32_n = -1; int x32_d = -1; uint64_t x32_epoch = 0;
