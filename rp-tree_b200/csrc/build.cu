@@ -553,7 +553,7 @@ static int launch_project_wide(rpf_handle* h, int phase, const double* dX, int64
 // Arithmetic: acc = fl(fl(val * x) + acc) from the LAST nonzero to the first, as innerSD (Internal.hs:369-382) -- the same
 // operations in the same order as k_project; the results are bit-identical (tests: both kernels against the oracle).
 struct ProjProg {
-    int t0 = 0, H = 0, L = 0, hpDepth = 0, d = 0, P = 0, NW = 0;
+    int t0 = 0, H = 0, L = 0, hpDepth = 0, d = 0, P = 0, NW = 0, c0 = 0, c1 = 0;       // columns [c0, c1) of the rows (whole rows: 0, d)
     int jpw = 0;                        // jobs (pairs of output rows) per warp
     int4* d_jobs = nullptr;             // [NW][jpw]: (first 16-byte unit of the pair's terms, iterations, row A, row B); row < 0: none
     uint4* d_terms = nullptr;
@@ -563,19 +563,22 @@ struct ProjProg {
 struct ProjProgCache { std::vector<ProjProg*> v; ~ProjProgCache() { for (auto* p : v) delete p; } };
 static void free_proj_progs(void* p) { delete (ProjProgCache*)p; }
 
-static int get_proj_prog(rpf_handle* h, int t0, int H, int L, int P, int NW, ProjProg** out) {
+static int get_proj_prog(rpf_handle* h, int t0, int H, int L, int P, int NW, int c0, int c1, ProjProg** out) {
     if (!h->proj_progs) { h->proj_progs = new ProjProgCache(); h->proj_progs_free = free_proj_progs; }
     ProjProgCache* C = (ProjProgCache*)h->proj_progs;
     for (ProjProg* q : C->v)
-        if (q->t0 == t0 && q->H == H && q->L == L && q->hpDepth == h->hpDepth && q->d == h->d && q->P == P && q->NW == NW) { *out = q; return RPF_OK; }
+        if (q->t0 == t0 && q->H == H && q->L == L && q->hpDepth == h->hpDepth && q->d == h->d && q->P == P && q->NW == NW && q->c0 == c0 && q->c1 == c1) { *out = q; return RPF_OK; }
     if (h->capturing) return rpf_fail(h, RPF_ERR_STATE, "projection program missing during graph capture");
-    if (C->v.size() >= 32) { cudaStreamSynchronize(h->stream); for (auto* q : C->v) delete q; C->v.clear(); }
+    if (C->v.size() >= 256) { cudaStreamSynchronize(h->stream); for (auto* q : C->v) delete q; C->v.clear(); }
     const int d = h->d;
     struct Row { int j; int64_t s; int cnt; };
     std::vector<Row> rows((size_t)H);
     for (int j = 0; j < H; ++j) {
         const int64_t r = (int64_t)(t0 + j / L) * h->hpDepth + (j % L);
-        const int64_t s0 = h->hp_off[r], e0 = std::min(h->hp_off[r + 1], s0 + (int64_t)d);      // innerSD's `i >= nz2` guard (Internal.hs:376)
+        int64_t s0 = h->hp_off[r], e0 = std::min(h->hp_off[r + 1], s0 + (int64_t)d);      // innerSD's `i >= nz2` guard (Internal.hs:376)
+        // column block: the nonzeros with c0 <= column < c1 (the indices ascend inside a row)
+        while (s0 < e0 && h->hp_idx[s0] < c0) ++s0;
+        while (e0 > s0 && h->hp_idx[e0 - 1] >= c1) --e0;
         rows[j] = Row{j, s0, (int)(e0 - s0)};
     }
     std::stable_sort(rows.begin(), rows.end(), [](const Row& a, const Row& b) { return a.cnt > b.cnt; });
@@ -593,7 +596,7 @@ static int get_proj_prog(rpf_handle* h, int t0, int H, int L, int P, int NW, Pro
         const int g = q / NW, i = q % NW, w = (g & 1) ? NW - 1 - i : i;            // serpentine deal
         jobs[(size_t)w * jpw + g] = make_int4((int)terms.size(), niter, A.j, B.j);
         auto val = [&](const Row& R, int k) { return k < R.cnt ? h->hp_val[R.s + R.cnt - 1 - k] : 0.0; };     // fold order: last nonzero first
-        auto rec = [&](const Row& R, int k) { return k < R.cnt ? enc(h->hp_idx[R.s + R.cnt - 1 - k]) : enc(0); };
+        auto rec = [&](const Row& R, int k) { return k < R.cnt ? enc(h->hp_idx[R.s + R.cnt - 1 - k] - c0) : enc(0); };
         for (int it = 0; it < niter; ++it) {
             // 48 bytes per iteration: [A_k0, A_k1] [B_k0, B_k1] [recA_k0, recA_k1] [recB_k0, recB_k1] -- a lane of half-warp s reads
             // its stream's 16 bytes of values at +16 s and its 8 bytes of offsets at +32 + 8 s
@@ -606,7 +609,7 @@ static int get_proj_prog(rpf_handle* h, int t0, int H, int L, int P, int NW, Pro
         }
     }
     ProjProg* Q = new ProjProg();
-    Q->t0 = t0; Q->H = H; Q->L = L; Q->hpDepth = h->hpDepth; Q->d = d; Q->P = P; Q->NW = NW; Q->jpw = jpw;
+    Q->t0 = t0; Q->H = H; Q->L = L; Q->hpDepth = h->hpDepth; Q->d = d; Q->P = P; Q->NW = NW; Q->jpw = jpw; Q->c0 = c0; Q->c1 = c1;
     Q->term_bytes = terms.size() * sizeof(uint4);
     if (cudaMalloc(&Q->d_jobs, jobs.size() * sizeof(int4)) != cudaSuccess || cudaMalloc(&Q->d_terms, std::max<size_t>(Q->term_bytes, 64)) != cudaSuccess ||
         cudaMemcpy(Q->d_jobs, jobs.data(), jobs.size() * sizeof(int4), cudaMemcpyHostToDevice) != cudaSuccess ||
@@ -634,8 +637,13 @@ template <int NT, int R, bool ORD, int MINB>
 __global__ void __launch_bounds__(NT, MINB) k_project_t(const double* __restrict__ X, int64_t n, int d,
                                                          const int4* __restrict__ jobs, int jpw, const uint4* __restrict__ terms,
                                                          void* __restrict__ out, int64_t ostride, ull* __restrict__ kmin, ull* __restrict__ kmax,
-                                                         int pf_ahead) {
+                                                         int pf_ahead, int c0, int dc, int flags) {
+    // Column blocks (rows too long for one tile: d = 768, 960, ...): a launch covers the columns [c0, c0 + dc) only.  The right
+    // fold runs from the LAST nonzero to the first, so the host launches the blocks from the highest columns down; every launch
+    // but the first (flags bit 0) resumes from the partial sums the previous one left in `out` as raw doubles, every launch but
+    // the last (bit 1) stores them back; the last one stores the finished keys.  Same operations, same order, same roundings.
     static_assert(R == 2 || R == 4, "tile of 64 or 128 points");
+    const bool first = flags & 1, last = flags & 2;
     constexpr int P = 32 * R, NW = NT / 32;
     constexpr int K = R;                                           // 16-byte point pairs per lane: a half-warp covers the tile
     constexpr unsigned ROWB = P * 8;                               // bytes of one tile row (one column, P points)
@@ -644,7 +652,7 @@ __global__ void __launch_bounds__(NT, MINB) k_project_t(const double* __restrict
     // the swizzle XORs address bits 4..6: the tile base must not carry into them
     const unsigned base = ((unsigned)__cvta_generic_to_shared(xs_raw) + 511u) & ~511u;
     const int64_t i0 = (int64_t)blockIdx.x * P;
-    if (pf_ahead > 0 && tid == 0) {
+    if (pf_ahead > 0 && dc == d && tid == 0) {
         // the tile a later wave will stage (its rows are contiguous in X) is pulled into L2 now
         const int64_t j0 = i0 + (int64_t)pf_ahead * P;
         if (j0 + P <= n) {
@@ -658,20 +666,20 @@ __global__ void __launch_bounds__(NT, MINB) k_project_t(const double* __restrict
     for (int q = w; q < P / 2; q += NW) {
         const int64_t r0 = i0 + 2 * q;
         const bool l0 = r0 < n, l1 = r0 + 1 < n;
-        const double* s0 = X + (l0 ? r0 : 0) * (int64_t)d;
-        const double* s1 = X + (l1 ? r0 + 1 : 0) * (int64_t)d;
-        for (int c0 = lane; c0 < d; c0 += 128) {
+        const double* s0 = X + (l0 ? r0 : 0) * (int64_t)d + c0;
+        const double* s1 = X + (l1 ? r0 + 1 : 0) * (int64_t)d + c0;
+        for (int cb = lane; cb < dc; cb += 128) {
             double v0[4], v1[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const int c = c0 + 32 * u;
-                v0[u] = (c < d && l0) ? ldg_stream_f64(s0 + c) : 0.0;
-                v1[u] = (c < d && l1) ? ldg_stream_f64(s1 + c) : 0.0;
+                const int c = cb + 32 * u;
+                v0[u] = (c < dc && l0) ? ldg_stream_f64(s0 + c) : 0.0;
+                v1[u] = (c < dc && l1) ? ldg_stream_f64(s1 + c) : 0.0;
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const int c = c0 + 32 * u;
-                if (c < d) {
+                const int c = cb + 32 * u;
+                if (c < dc) {
                     const unsigned a = base + (unsigned)c * ROWB + ((unsigned)(q ^ (c & 7)) << 4);
                     asm volatile("st.shared.v2.f64 [%0], {%1, %2};" :: "r"(a), "d"(v0[u]), "d"(v1[u]) : "memory");
                 }
@@ -689,7 +697,7 @@ __global__ void __launch_bounds__(NT, MINB) k_project_t(const double* __restrict
     const unsigned m16 = (unsigned)m << 4;
     const bool full = i0 + P <= n;
     const bool al16 = ((((uintptr_t)out) | ((uintptr_t)ostride << 3)) & 15) == 0;
-    const bool track = ORD && (blockIdx.x & 7) == 0;               // the key range only seeds bin maps: every 8th tile is enough
+    const bool track = ORD && last && (blockIdx.x & 7) == 0;       // the key range only seeds bin maps: every 8th tile is enough
     const int4* jw = jobs + (size_t)w * jpw;
     for (int k = 0; k < jpw; ++k) {                                // warp-uniform
         const int4 jb = __ldg(jw + k);
@@ -697,6 +705,15 @@ __global__ void __launch_bounds__(NT, MINB) k_project_t(const double* __restrict
         double acc[2 * K];
 #pragma unroll
         for (int r = 0; r < 2 * K; ++r) acc[r] = 0.0;
+        const int j = sgrp ? jb.w : jb.z;                                      // this half-warp's output row (< 0: none)
+        if (!first && j >= 0) {                                                // resume from the partial sums of the higher column blocks
+            const double* row = (const double*)out + (int64_t)j * ostride + i0 + 2 * m;
+#pragma unroll
+            for (int r = 0; r < 2 * K; ++r) {
+                const int off = (r >> 1) * 32 + (r & 1);
+                if (i0 + 2 * m + off < n) acc[r] = row[off];
+            }
+        }
         auto term = [&](const double v, const unsigned rec) {
             const unsigned a = (rec ^ m16) + base;
             double2 x[K];
@@ -726,9 +743,8 @@ __global__ void __launch_bounds__(NT, MINB) k_project_t(const double* __restrict
             }
         }
         // ---- this half-warp's output row: points i0 + 2m + 32q (+1)
-        const int j = sgrp ? jb.w : jb.z;
         if (j < 0) continue;                                           // odd row count: the last pair has no second stream
-        if (ORD) {
+        if (ORD && last) {
             ull o[2 * K];
 #pragma unroll
             for (int r = 0; r < 2 * K; ++r) o[r] = f2ord(acc[r]);
@@ -778,19 +794,27 @@ __global__ void __launch_bounds__(NT, MINB) k_project_t(const double* __restrict
 }
 
 template <int NT, int R, bool ORD, int MINB>
-static int launch_project_t(rpf_handle* h, int phase, const double* dX, int64_t n, int t0, int L, int H, void* out, int64_t ostride, ull* kmin, ull* kmax) {
+static int launch_project_t(rpf_handle* h, int phase, const double* dX, int64_t n, int t0, int L, int H, void* out, int64_t ostride, ull* kmin, ull* kmax,
+                            int nblk = 1) {
     constexpr int P = 32 * R;
-    ProjProg* Q = nullptr;
-    int rc = get_proj_prog(h, t0, H, L, P, NT / 32, &Q);
-    if (rc) return rc;
-    const size_t smem = (size_t)h->d * P * 8 + 512;
+    const int d = h->d, dcmax = (d + nblk - 1) / nblk;
+    const size_t smem = (size_t)dcmax * P * 8 + 512;
     auto kfn = k_project_t<NT, R, ORD, MINB>;
     RPF_CUDA(h, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t grid = (n + P - 1) / P;
     int occ = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, NT, smem);
-    const int pf = h->project_prefetch ? std::max(1, occ) * 148 : 0;
-    RPF_LAUNCH(h, phase, kfn, (unsigned)grid, NT, smem, dX, n, h->d, (const int4*)Q->d_jobs, Q->jpw, (const uint4*)Q->d_terms, out, ostride, kmin, kmax, pf);
+    const int pf = (h->project_prefetch && nblk == 1) ? std::max(1, occ) * 148 : 0;
+    for (int b = nblk - 1; b >= 0; --b) {                          // highest columns first: the right fold's order
+        const int c0 = b * dcmax, c1 = std::min(d, c0 + dcmax);
+        if (c1 <= c0) continue;
+        ProjProg* Q = nullptr;
+        int rc = get_proj_prog(h, t0, H, L, P, NT / 32, c0, c1, &Q);
+        if (rc) return rc;
+        const int flags = (b == nblk - 1 || c1 == d ? 1 : 0) | (b == 0 ? 2 : 0);
+        RPF_LAUNCH(h, phase, kfn, (unsigned)grid, NT, smem, dX, n, d, (const int4*)Q->d_jobs, Q->jpw, (const uint4*)Q->d_terms, out, ostride, kmin, kmax, pf,
+                   c0, c1 - c0, flags);
+    }
     return RPF_OK;
 }
 
@@ -815,6 +839,13 @@ int rpf_project_launch(rpf_handle* h, int phase, const double* dX, int64_t n, in
         if (pick == 12 && fitB)
             return ord ? launch_project_t<256, 2, true, 3>(h, phase, dX, n, t0, L, H, out, ostride, kmin, kmax)
                        : launch_project_t<256, 2, false, 3>(h, phase, dX, n, t0, L, H, out, ostride, kmin, kmax);
+        if ((pick == 0 || pick == 13) && !fitB) {
+            // long rows (d = 768, 960, ...): 128-point tiles over column blocks of <= 160 columns, partial sums carried in `out`
+            const int nblk = (d + 159) / 160;
+            if (nblk <= 64)
+                return ord ? launch_project_t<1024, 4, true, 1>(h, phase, dX, n, t0, L, H, out, ostride, kmin, kmax, nblk)
+                           : launch_project_t<1024, 4, false, 1>(h, phase, dX, n, t0, L, H, out, ostride, kmin, kmax, nblk);
+        }
     }
     if (h->project_variant == 1 && 64 * row <= 110 * 1024)
         return ord ? launch_project<1024, 2, true>(h, phase, dX, n, t0, L, H, out, ostride, kmin, kmax)

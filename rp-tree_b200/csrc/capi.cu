@@ -381,7 +381,7 @@ int rpf_set_points(rpf_handle* h, const double* X, int64_t n, int32_t d) {
     if (h->group) return rpfg_set_points(h, X, n, d);
     RPF_SETDEV(h);
     rpf_insert_drop(h);
-    ++h->cfg_epoch;
+    ++h->cfg_epoch; ++h->x_version;
     if (h->d_xlast) { cudaFree(h->d_xlast); h->d_xlast = nullptr; }
     double* p = nullptr;
     const int64_t pad = rpf_comm_world(h) > 1 ? rpf_comm_world(h) : 0;      // spill rows of the in-place all-gather
@@ -415,7 +415,7 @@ int rpf_set_points_device(rpf_handle* h, const double* X_dev, int64_t n, int32_t
     if (h->group) return rpf_fail(h, RPF_ERR_UNSUPPORTED, "set_points_device: a multi-GPU handle replicates the points itself (rpf_set_points)");
     RPF_SETDEV(h);
     rpf_insert_drop(h);
-    ++h->cfg_epoch;
+    ++h->cfg_epoch; ++h->x_version;
     if (h->d_xlast) { cudaFree(h->d_xlast); h->d_xlast = nullptr; }
     if (h->ownX && h->dX) cudaFree((void*)h->dX);
     free_forest_dev(h);
@@ -454,7 +454,7 @@ int rpf_set_points_sparse(rpf_handle* h, int64_t n, int32_t d, const int64_t* of
     if (h->group) return rpfg_set_points_sparse(h, n, d, off, idx, val);
     RPF_SETDEV(h);
     rpf_insert_drop(h);
-    ++h->cfg_epoch;
+    ++h->cfg_epoch; ++h->x_version;
     if (h->d_xlast) { cudaFree(h->d_xlast); h->d_xlast = nullptr; }
     if (h->ownX && h->dX) cudaFree((void*)h->dX);
     h->dX = nullptr; h->ownX = false; h->x_bytes = 0;
@@ -659,7 +659,7 @@ int rpf_build_from_host(rpf_handle* h, const double* X, int64_t n, int32_t d, in
     if (maxDepth > 62) return rpf_fail(h, RPF_ERR_UNSUPPORTED, "build: maxDepth > 62");
     for (int32_t q : h->hp_idx) if (q < 0 || q >= d) return rpf_fail(h, RPF_ERR_ARG, "build: hyperplane component index out of range");
     RPF_SETDEV(h);
-    ++h->cfg_epoch;
+    ++h->cfg_epoch; ++h->x_version;
     if (h->d_xlast) { cudaFree(h->d_xlast); h->d_xlast = nullptr; }
     const int64_t pad = rpf_comm_world(h) > 1 ? rpf_comm_world(h) : 0;      // spill rows of the in-place all-gather
     const size_t bytes = std::max<size_t>((size_t)(n + pad) * d * 8, 16);
@@ -871,7 +871,7 @@ static int forest_load_impl(rpf_handle* h, const char* path) {
 
     // ---- the file is sane: now replace the handle's state
     h->built = false; h->sink_pending = false;
-    ++h->cfg_epoch;
+    ++h->cfg_epoch; ++h->x_version;
     h->T = H.T; h->hpDepth = H.hpDepth;
     h->hp_off.swap(hp_off); h->hp_idx.swap(hp_idx); h->hp_val.swap(hp_val);
     auto fail_reset = [&](int code, const char* why) {      // the previous forest is gone; leave a consistent "not built" handle

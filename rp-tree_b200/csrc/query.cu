@@ -804,7 +804,9 @@ __global__ void __launch_bounds__(KT_NT) k_knn_f32(QArgs A, int rows_per_stage, 
 
 // fp32 image of X + largest row norm, rebuilt when the points changed
 static int ensure_x32(rpf_handle* h) {
-    if (h->dX32 && h->x32_src == h->dX && h->x32_n == h->n && h->x32_d == h->d && h->x32_epoch == h->cfg_epoch) return RPF_OK;
+    // (a borrowed buffer -- rpf_set_points_device -- can change under the handle: its image is rebuilt on every call)
+    const bool stable = h->ownX || h->insert_session;
+    if (stable && h->dX32 && h->x32_src == h->dX && h->x32_n == h->n && h->x32_d == h->d && h->x32_version == h->x_version) return RPF_OK;
     const size_t bytes = std::max<size_t>((size_t)h->n * h->d * 4, 16);
     if (!h->dX32 || h->x32_bytes < bytes) {
         if (h->dX32) { cudaStreamSynchronize(h->stream); cudaFree(h->dX32); h->dX32 = nullptr; h->x32_bytes = 0; }
@@ -814,7 +816,7 @@ static int ensure_x32(rpf_handle* h) {
     if (!h->d_xmax && cudaMalloc(&h->d_xmax, 16) != cudaSuccess) { cudaGetLastError(); return 1; }
     RPF_CUDA(h, cudaMemsetAsync(h->d_xmax, 0, 8, h->stream));
     RPF_LAUNCH(h, PH_Q_PROJECT, k_x32_convert, 148 * 8, 256, 0, h->dX, h->n, h->d, h->dX32, (ull*)h->d_xmax);
-    h->x32_src = h->dX; h->x32_n = h->n; h->x32_d = h->d; h->x32_epoch = h->cfg_epoch;
+    h->x32_src = h->dX; h->x32_n = h->n; h->x32_d = h->d; h->x32_version = h->x_version;
     return RPF_OK;
 }
 

@@ -191,7 +191,8 @@ struct rpf_handle {
     int knn_f32_cfg[4] = {0, 0, 0, 0};  // tuning hook: ring stages, rows per stage, entry buffer, side region of k_knn_f32 (0 = default)
     int knn_filter32 = 1;                // option: fp32 filter pass in front of the exact re-rank (k_knn_f32): 0 = exact gather kernel only
     float* dX32 = nullptr; size_t x32_bytes = 0;     // fp32 image of X for the filter pass (built lazily by the first knn after the points change)
-    const double* x32_src = nullptr; int64_t x32_n = -1; int x32_d = -1; uint64_t x32_epoch = 0;
+    const double* x32_src = nullptr; int64_t x32_n = -1; int x32_d = -1; uint64_t x32_version = 0;
+    uint64_t x_version = 1;              // bumped by every entry point that changes the CONTENT of dX
     double* d_xmax = nullptr;            // [1] largest row norm of X (error margin of the filter)
     bool force_simple_knn = false;       // test hook: per-thread gather knn kernel instead of the TMA ring
     int top_chunk[3] = {0, 0, 0};        // tuning hook: points per CTA of the top-phase hist / compact / relabel kernels (0 = chosen per launch)

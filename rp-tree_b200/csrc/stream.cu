@@ -741,7 +741,7 @@ int rpf_insert_begin_impl(rpf_handle* h, int d, int maxDepth, int minLeaf) {
     if (h->ownX && h->dX) cudaFree((void*)h->dX);
     h->dX = nullptr; h->ownX = false; h->x_bytes = 0; h->n = 0; h->d = d; h->x_pad_rows = 0;
     h->built = false; h->sink_pending = false;
-    ++h->cfg_epoch;
+    ++h->cfg_epoch; ++h->x_version;
     InsertSession* S = new InsertSession();
     S->maxDepth = maxDepth; S->minLeaf = minLeaf; S->Lk = std::max(maxDepth, 1); S->d = d; S->T = h->T;
     S->SP.begin(0, maxDepth, minLeaf);
@@ -785,7 +785,7 @@ int rpf_insert_chunk_impl(rpf_handle* h, const double* Xc, int64_t m) {
         rpf_insert_drop(h);                      // the planner's state is no longer the device's
         return rpf_fail(h, RPF_ERR_UNSUPPORTED, e + " (the insert session was closed)");
     }
-    ++h->cfg_epoch;
+    ++h->cfg_epoch; ++h->x_version;
     h->built = false;
     // ---- capacity of the per-point arrays
     if (n1 > S->cap) {
