@@ -11,12 +11,13 @@
 --
 -- NOTE: written against the C ABI but NOT compiled in the authoring environment (no GHC there).
 module Data.RPTree.CUDA
-  ( GpuForest, forestBatch, treeBatch, forest, forestOn, knn, knnPQ, knnH, candidates, recallWith, toRPForest
+  ( GpuForest, forestBatch, treeBatch, forest, forestStreaming, forestOn, knn, knnPQ, knnH, candidates, recallWith, toRPForest
   , withDevice, withDevices, saveForest, setPointsSparse
   ) where
 
 import Control.Exception (throwIO, ErrorCall(..))
 import Control.Monad (replicateM, when, forM, forM_)
+import Control.Monad.IO.Class (MonadIO(..))
 import Data.Int (Int32, Int64)
 import Data.Word (Word32, Word64)
 import Foreign.C.String (CString, peekCString, withCString)
@@ -31,6 +32,7 @@ import System.IO.Unsafe (unsafePerformIO)
 
 import qualified Data.Conduit as C
 import qualified Data.Conduit.Combinators as CC
+import qualified Data.Conduit.List as CL (chunksOf)
 import qualified Data.IntMap.Strict as IM
 import qualified Data.Vector as V
 import qualified Data.Vector.Storable as VS
@@ -55,6 +57,11 @@ foreign import ccall safe "rpf_set_hyperplanes"   c_setHp    :: Ptr RpfHandle ->
 foreign import ccall safe "rpf_build"             c_build    :: Ptr RpfHandle -> Int32 -> Int32 -> IO CInt
 foreign import ccall safe "rpf_build_from_host"   c_buildH   :: Ptr RpfHandle -> Ptr CDouble -> Int64 -> Int32 -> Int32 -> Int32 -> IO CInt
 foreign import ccall safe "rpf_build_chunked"     c_buildCh  :: Ptr RpfHandle -> Int32 -> Int32 -> Int64 -> IO CInt
+-- | The fold of Conduit.hs:157-176 driven from Haskell: one 'c_insChunk' == one insertMulti (Internal.hs:243-255); the forest is
+-- complete and queryable after every chunk, n is not known in advance.
+foreign import ccall safe "rpf_insert_begin"      c_insBegin :: Ptr RpfHandle -> Int32 -> Int32 -> Int32 -> IO CInt
+foreign import ccall safe "rpf_insert_chunk"      c_insChunk :: Ptr RpfHandle -> Ptr CDouble -> Int64 -> IO CInt
+foreign import ccall safe "rpf_insert_end"        c_insEnd   :: Ptr RpfHandle -> IO CInt
 foreign import ccall safe "rpf_num_nodes"         c_numNodes :: Ptr RpfHandle -> IO Int64
 foreign import ccall safe "rpf_topology"          c_topology :: Ptr RpfHandle -> Ptr Int64 -> Ptr Int32 -> Ptr Int64 -> Ptr Int64 -> IO CInt
 foreign import ccall safe "rpf_tree_export"       c_export   :: Ptr RpfHandle -> Int32 -> Ptr CDouble -> Ptr CDouble -> Ptr CDouble -> Ptr Word32 -> IO CInt
@@ -153,6 +160,28 @@ forest :: Monad m => Word64 -> Int -> Int -> Int -> Int -> Double -> Int -> C.Co
 forest seed maxd minl ntrees chunksize pnz dim src = do
   xs <- C.runConduit (src C..| CC.sinkVector)
   pure $! unsafePerformIO (buildWith [0] (Just chunksize) seed maxd minl ntrees pnz dim xs)
+
+-- | 'forest' without draining the source first: every @chunksize@ rows the conduit yields are handed to the engine as they
+-- arrive ('c_insChunk'), exactly the reference's @chunksOf n .| foldl insertMulti@ (Conduit.hs:157-176).  The handle holds a
+-- complete forest after every chunk, so a consumer may query between chunks; memory on the device grows geometrically.
+forestStreaming :: MonadIO m => Word64 -> Int -> Int -> Int -> Int -> Double -> Int -> C.ConduitT () (Embed DVector Double x) m () -> m (GpuForest x)
+forestStreaming seed maxd minl ntrees chunksize pnz dim src = do
+  let rvss = sample seed $ do                                   -- Conduit.hs:116-118, verbatim
+        rvs <- replicateM ntrees $ V.replicateM maxd (sparse pnz dim stdNormal)
+        pure $ IM.fromList $ zip [0 ..] rvs
+      (off, idx, val) = csrOf rvss
+  fh <- liftIO $ withDevices [0] pure
+  liftIO $ withForeignPtr fh $ \h -> do
+    withArray off $ \po -> withArray idx $ \pi' -> withArray val $ \pv ->
+      c_setHp h (fromIntegral ntrees) (fromIntegral maxd) po pi' pv >>= check h "rpf_set_hyperplanes"
+    c_insBegin h (fromIntegral dim) (fromIntegral maxd) (fromIntegral minl) >>= check h "rpf_insert_begin"
+  let insert1 chunk = liftIO $ withForeignPtr fh $ \h -> do
+        let xs = V.fromList chunk
+        VS.unsafeWith (packRows dim xs) $ \p -> c_insChunk h p (fromIntegral (V.length xs)) >>= check h "rpf_insert_chunk"
+        pure xs
+  xss <- C.runConduit (src C..| CL.chunksOf chunksize C..| CC.mapM insert1 C..| CC.sinkList)
+  liftIO $ withForeignPtr fh $ \h -> c_insEnd h >>= check h "rpf_insert_end"
+  pure (GpuForest fh (V.concat xss) rvss ntrees maxd)
 
 queryPtr :: DVector Double -> (Ptr CDouble -> IO a) -> IO a
 queryPtr (DV q) = VS.unsafeWith (VS.map realToFrac (VS.convert q))

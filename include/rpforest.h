@@ -212,7 +212,11 @@ int rpf_knn_h(rpf_handle* h, const double* Q, const int32_t* q_last, int64_t nq,
               double* dist, uint32_t* ids, int32_t* count);
 /* recallWith metricL2 forest k q (RPTree.hs:259-282): mean over this handle's trees of
  * |candidates(t,q) /\ true-top-k| / k.  recall_sum[q] = SUM over local trees (divide by the global
- * tree count after reducing across GPUs). */
+ * tree count after reducing across GPUs).
+ * Deviation after a LOSSY streaming build (rpf_points_lost > 0): the truth here ranks all n rows, ties by row id; the
+ * reference's recallWith1 ranks `points tt`, i.e. only the points that tree still holds, in leaf order with a stable sort
+ * (RPTree.hs:265-282) -- dropped rows can enter the truth set here.  With no points lost and no exact distance tie at rank k
+ * the two agree (tested against the oracle). */
 int rpf_recall(rpf_handle* h, const double* Q, int64_t nq, int32_t k, double* recall_sum);   /* multi-GPU handle / communicator rank: sum over ALL trees */
 /* Exact brute-force k nearest rows (ties by row id): ground truth for forest-level recall. */
 int rpf_brute_knn(rpf_handle* h, const double* Q, int64_t nq, int32_t k, double* dist, uint32_t* ids);

@@ -481,6 +481,38 @@ def test_incremental_insert_state_errors(built):
     assert f.topology()["seg_size"][0] == 50
 
 
+@pytest.mark.parametrize("kind,scale", [("gauss", 1.0), ("mixture", 1.0), ("integer", 1.0), ("dupes", 1.0), ("allsame", 1.0),
+                                        ("gauss", 1e19), ("gauss", 1e-30), ("offset", 1.0)])
+def test_knn_fp32_filter_equals_exact_kernel_and_oracle(built, kind, scale):
+    """k_knn_f32 (fp32 filter pass + exact re-rank of the survivors) against the exact kernel and the oracle: well separated data
+    (a handful of survivors), massive ties (integer data, duplicate rows, all rows equal: the query is flagged and answered by
+    the exact kernel), norms beyond fp32's range (filter refused), tiny magnitudes (squares underflow in fp32) and data far from
+    the origin (the fp32 image loses the low bits the distances live in: wide margin, more survivors, same answer)."""
+    R, orc = _mods()
+    n, d, T, maxd, minl, k = 6000, 16, 6, 8, 12, 10
+    if kind == "allsame":
+        X = np.tile(make_data(1, d, 2), (n, 1))
+    elif kind == "offset":
+        X = make_data(n, d, 2) * 1e-3 + 1000.0
+    else:
+        X = make_data(n, d, 2, kind) * scale
+    hp = orc.gen_hyperplanes(11, T, maxd, 0.5, d)
+    f = R.forestBatch(0, maxd, minl, T, 0.5, d, X, hyperplanes=hp)
+    of = orc.Forest(X, hp, T, maxd, minl)
+    rng = np.random.default_rng(9)
+    Q = X[rng.integers(0, n, size=96)] + (0.0 if kind in ("integer", "allsame") else 0.01 * scale * rng.normal(size=(96, d)))
+    f.setOption("knn_filter32", 0)
+    d0, i0, c0 = f.knnBatch(Q, k)
+    f.setOption("knn_filter32", 1)
+    d1, i1, c1 = f.knnBatch(Q, k)
+    assert np.array_equal(c0, c1) and np.array_equal(bits(d0), bits(d1)) and np.array_equal(i0, i1)
+    for q in range(0, 96, 8):
+        od, oi = of.knn(Q[q], k)
+        assert c1[q] == len(od) and np.array_equal(bits(d1[q, :c1[q]]), bits(od))
+        if kind in ("gauss", "mixture", "offset"):
+            assert np.array_equal(i1[q, :c1[q]], oi)
+
+
 def test_streaming_unsupported_shape_reports(built):
     """A Tip of more than 8192 points that must be re-split is outside the streaming path's limits."""
     R, orc = _mods()
