@@ -67,8 +67,10 @@ bufs["perm"] = torch.empty((t_local, n), dtype=torch.int32, pin_memory=True).num
 res["forestExport_ms"] = timed(lambda: f.forestExport(bufs))
 f.setExportSink(bufs)
 res["buildFromHost_plus_sink_export_ms"] = timed(lambda: (f.buildFromHost(X, maxd, W["min_leaf"]), f.forestExport(bufs)))
+if rank == 0:
+    print(json.dumps(res), flush=True)
 # reference: the same 16 x (n/16 rows) all-gathers through torch.distributed
-blk = n // 16
+blk = (n // 16 // world) * world
 full = torch.empty((blk, d), dtype=torch.float64, device=dev)
 part = full[rank * (blk // world):(rank + 1) * (blk // world)]
 
@@ -79,7 +81,8 @@ def ag():
 
 
 res["torch_16_allgathers_ms"] = timed(ag)
-one = torch.empty((n, d), dtype=torch.float64, device=dev)
+nw = (n // world) * world
+one = torch.empty((nw, d), dtype=torch.float64, device=dev)
 res["torch_1_allgather_full_ms"] = timed(lambda: dist.all_gather_into_tensor(one, one[rank * (n // world):(rank + 1) * (n // world)]))
 h2d = torch.empty((n // world, d), dtype=torch.float64, device=dev)
 res["h2d_own_rows_ms"] = timed(lambda: h2d.copy_(Xp[rank * (n // world):(rank + 1) * (n // world)], non_blocking=True))
