@@ -154,7 +154,9 @@ def algorithmic_bytes(W, tlocal, L, s_top, C_mean):
         "top_compact": tlocal * n * (2 + 2),                           # bin + label (keys only for the median bin)
         "top_relabel": tlocal * n * (2 + 2 + 2),                       # bin + label read, label write
         "bottom": tlocal * n * (4 + 4 + 8 * (L - s_top) + (8 if s_top > 0 else 0)),   # perm r/w + one key per bottom level
-        "q_knn": W["nq"] * (C_mean * (8 * d + 4) + 8 * d + 12 * W["k"]),
+        # fp32 filter pass (k_knn_f32: d % 4 == 0, plain knn): 4d bytes per candidate + ~(k + 4) exact rows; else the exact kernel
+        "q_knn": W["nq"] * ((C_mean * (4 * d + 4) + (W["k"] + 4) * 8 * d + 8 * d + 12 * W["k"]) if d % 4 == 0 and d < 512
+                            else (C_mean * (8 * d + 4) + 8 * d + 12 * W["k"])),
     }
 
 

@@ -1088,9 +1088,10 @@ struct TopArgs {
 #define SMEM_NODES 1024   /* compact/relabel keep per-node state in shared memory up to this many nodes */
 #define SCAT_MAX 2048     /* children handled by the CTA-aggregated scatter of the last top level */
 
-__device__ __forceinline__ int key_bin(ull o, double lo, double sc, int NB) {
-    double v = (ord2f(o) - lo) * sc;
-    int b = (int)v;
+// (monotone: difference in fp64 -- keys far from zero keep their resolution --, scaling and conversion in fp32: NB <= 65536
+//  bins against a 24-bit mantissa; three cheap instructions instead of an fp64 multiply and an fp64 -> int conversion)
+__device__ __forceinline__ int key_bin(ull o, double lo, float scf, int NB) {
+    const int b = __float2int_rz(__double2float_rz(ord2f(o) - lo) * scf);
     return b < 0 ? 0 : (b >= NB ? NB - 1 : b);
 }
 
@@ -1230,7 +1231,8 @@ __global__ void __launch_bounds__(TOP_NT) k_top_hist(TopArgs A) {
     const int64_t i0 = (int64_t)blockIdx.x * A.ch, i1 = min(A.n, i0 + A.ch);
     const ull* keys = A.keys + ((int64_t)t * A.L + A.l) * A.ks;
     const uint16_t* lab = A.label + (int64_t)t * A.n;
-    const double lo = A.binlo[t * A.L + A.l], sc = A.binscale[t * A.L + A.l];
+    const double lo = A.binlo[t * A.L + A.l];
+    const float sc = __double2float_rz(A.binscale[t * A.L + A.l]);
     const int NB = A.NB, tot = A.nnodes * NB;
     uint32_t* gh = A.hist + (int64_t)t * A.HSZ;
     if (A.smem_hist) {

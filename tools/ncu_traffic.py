@@ -1,5 +1,5 @@
 """DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) of every profiled kernel in one or more
-.ncu-rep files -> profiles/r01_traffic.json, keyed by the engine's phase names (what bench.py's `roofline.traffic` reads).
+.ncu-rep files -> profiles/r02_traffic.json (argument --out NAME: another file), keyed by the engine's phase names (what bench.py's `roofline.traffic` reads).
 
   python tools/ncu_traffic.py gpurun_out/prof_v8.ncu-rep gpurun_out/prof_v7.ncu-rep
 """
@@ -10,7 +10,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-PHASE = [("k_knn_tma", "q_knn"), ("k_knn", "q_knn"), ("k_project<", "project"), ("k_bottom", "bottom"), ("k_top_hist", "top_hist"),
+PHASE = [("k_knn_f32", "q_knn"), ("k_knn_tma", "q_knn"), ("k_knn", "q_knn"), ("k_project_t<", "project"), ("k_project<", "project"), ("k_bottom", "bottom"), ("k_top_hist", "top_hist"),
          ("k_top_compact", "top_compact"), ("k_top_relabel", "top_relabel"), ("k_top_scatter", "top_relabel")]
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
 TIME_MS = {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}
@@ -36,11 +36,15 @@ def main(paths):
     for ph, lst in acc.items():
         res[ph] = dict(dram_bytes_per_launch=sum(x[0] for x in lst) / len(lst), launches_profiled=len(lst),
                        ncu_ms_per_launch=sum(x[1] for x in lst) / len(lst), source=sorted({x[2] for x in lst}), kernel=lst[0][3])
-    dst = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    dst = os.path.join(ROOT, "profiles", OUT)
     with open(dst, "w") as fh:
         json.dump(res, fh, indent=1, sort_keys=True)
     print(json.dumps(res, indent=1, sort_keys=True))
 
 
+OUT = "r02_traffic.json"
 if __name__ == "__main__":
-    main(sys.argv[1:])
+    args = sys.argv[1:]
+    if "--out" in args:
+        i = args.index("--out"); OUT = args[i + 1]; del args[i:i + 2]
+    main(args)
