@@ -1462,7 +1462,8 @@ int rpf_knn_impl(rpf_handle* h, const double* Q, const int32_t* q_last, int64_t 
     // (72 KB per CTA, 3 per SM) for forests with many candidates per query, 2 x 28 (54 KB, 4 per SM) for few.
     const bool many = h->T >= 16;
     const int nst = std::max(1, std::min(4, h->knn_f32_cfg[0] ? h->knn_f32_cfg[0] : (many ? 3 : 2)));
-    const int fbuf = h->knn_f32_cfg[2] ? h->knn_f32_cfg[2] : 768, fsreg = h->knn_f32_cfg[3] ? h->knn_f32_cfg[3] : 256;
+    // (the side region holds the candidates within the margin of the k-th best: at least 4 k entries)
+    const int fbuf = h->knn_f32_cfg[2] ? h->knn_f32_cfg[2] : (k <= 64 ? 768 : 1280), fsreg = h->knn_f32_cfg[3] ? h->knn_f32_cfg[3] : (k <= 64 ? 256 : 512);
     const size_t stage_budget = h->knn_f32_cfg[1] ? (size_t)(72 * 1024) : (many ? (size_t)47600 : (size_t)29700);
     const int rows32 = (int)std::min<size_t>(h->knn_f32_cfg[1] ? h->knn_f32_cfg[1] : 32, stage_budget / ((size_t)nst * pitch32));
     const int nb_exact = rows32 >= 1 ? (int)std::min<size_t>(KT_NT, ((size_t)nst * rows32 * pitch32) / (size_t)pitch) : 0;

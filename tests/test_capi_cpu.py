@@ -147,3 +147,26 @@ def test_idx_loader_cpu_roundtrip(tmp_path):
         R.idx.read_idx_ubyte(bad)
 
 
+
+
+def test_chunksOf_groups_a_row_source_like_the_conduit(built):
+    """chunkedAccum's `C.chunksOf n` (Conduit.hs:168-176): n rows per chunk, a shorter last chunk, nothing for an empty source;
+    the source may yield single rows or blocks of rows."""
+    import rp_tree_b200 as R
+    X = np.arange(23 * 3, dtype=np.float64).reshape(23, 3)
+    chunks = list(R.chunksOf(5, (row for row in X), 3))
+    assert [c.shape[0] for c in chunks] == [5, 5, 5, 5, 3] and np.array_equal(np.concatenate(chunks), X)
+    chunks = list(R.chunksOf(5, iter([X[:7], X[7:8], X[8:23]]), 3))
+    assert [c.shape[0] for c in chunks] == [5, 5, 5, 5, 3] and np.array_equal(np.concatenate(chunks), X)
+    assert list(R.chunksOf(4, iter([]), 3)) == []
+    assert [c.shape[0] for c in R.chunksOf(23, iter([X]), 3)] == [23]
+
+
+def test_insert_entry_points_reject_bad_state_without_a_gpu(built):
+    """Argument / state errors of the insert entry points are decided on the host (no device needed): NULL handle."""
+    import ctypes as C
+    import rp_tree_b200 as R
+    L = R.lib()
+    assert L.rpf_insert_begin(None, 4, 3, 2) != 0
+    assert L.rpf_insert_chunk(None, None, 0) != 0
+    assert L.rpf_insert_end(None) != 0
