@@ -361,6 +361,8 @@ def run_ours(args):
         """Roofline record of one kernel class.  top_* entries of `ab` are bytes per level launch (every launch streams all
         local trees' points once); the others are bytes per step, issued in `launches` launches (one per tree group)."""
         ms, nl = kern[kname]
+        if kname == "q_knn":
+            nl = 1      # the filter kernel + the (nearly empty) exact second pass over its flagged queries: one logical launch
         per_launch = ab[kname] if kname.startswith("top_") else ab[kname] / nl
         avg_ms = ms / nl
         ach = per_launch / (avg_ms * 1e-3) / 1e9

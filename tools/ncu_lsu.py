@@ -4,7 +4,8 @@ import csv
 import subprocess
 import sys
 
-out = subprocess.run(['ncu', '-i', sys.argv[1], '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+# a .csv argument is the saved output of `ncu -i REP --page raw --csv` (the reports themselves are too big to pull from the GPU box)
+out = open(sys.argv[1]).read() if sys.argv[1].endswith('.csv') else subprocess.run(['ncu', '-i', sys.argv[1], '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
 r = list(csv.reader(out.splitlines()))
 h = r[0]
 want = ['gpu__time_duration.sum', 'smsp__inst_executed.sum', 'launch__registers_per_thread', 'sm__warps_active.avg.pct_of_peak_sustained_active',

@@ -19,7 +19,7 @@ TIME_MS = {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}
 def main(paths):
     acc = {}
     for path in paths:
-        out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        out = open(path).read() if path.endswith(".csv") else subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rows = list(csv.reader(out.splitlines()))
         hdr, units = rows[0], rows[1]
         ir, iw, it, ik = (hdr.index(x) for x in ("dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__time_duration.sum", "Kernel Name"))
