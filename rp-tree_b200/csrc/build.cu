@@ -2353,6 +2353,11 @@ __global__ void __launch_bounds__(NT, (NT == 128 ? RPF_BOT_MINB128 : 1)) k_botto
     constexpr unsigned SMASK = (1u << SB) - 1u;
     constexpr W WSENT = (W)~(W)0;
     static_assert(!W32 || lp0 <= 11, "32-bit sort words need at least 21 prefix bits");
+    // Shallow instance (<= 5 splitting levels): a segment keeps >= 16 slots and a child >= 8, so the 8 slots of a thread always
+    // share one segment and one child -- segment size, median rank and table lookups are per THREAD, not per slot (the
+    // per-slot form spent 60 % of the kernel's instructions outside the sort network: ncu source page, round 2).
+    constexpr bool UNI = (TAB == BOT2_TAB_SHALLOW);
+    static_assert(!UNI || (P0 >> 5) >= 8, "uniform-thread path needs 8 slots per child at the deepest level");
     extern __shared__ unsigned char smraw[];
     W* w = (W*)smraw;                             // [P0] sort words (the block is sized for 8-byte words: composite_sort
     ull* w64 = (ull*)smraw;                       //      uses it as linear uint64 scratch)
@@ -2361,6 +2366,9 @@ __global__ void __launch_bounds__(NT, (NT == 128 ? RPF_BOT_MINB128 : 1)) k_botto
     __shared__ uint16_t t_ps[2][TAB];        // offset of the segment inside this CTA's slice of perm
     __shared__ int32_t t_gid[2][TAB];        // BFS id
     __shared__ uint16_t t_lsz[TAB];          // size if the segment just became a Tip (to be emitted), else 0
+    __shared__ double s_plo[16];             // per level of this subtree: low end of the (tree, level) key range and the fp32
+    __shared__ float s_psc[16];              //   prefix scale of the 32-bit sort words (one fp64 division per level and CTA)
+    __shared__ uint32_t s_trash[UNI ? NT : 1];
     const int t = blockIdx.y, tid = threadIdx.x;
     if (A.only && !A.only[(size_t)t * gridDim.x + blockIdx.x]) return;      // second pass of k_bottom4: flagged nodes only
     const int e0 = A.first_gid + blockIdx.x;
@@ -2378,6 +2386,18 @@ __global__ void __launch_bounds__(NT, (NT == 128 ? RPF_BOT_MINB128 : 1)) k_botto
     auto TI = [](unsigned x) -> unsigned { return (x & 7u) * NT + (x >> 3); };
 #pragma unroll
     for (int q = 0; q < 8; ++q) { const uint32_t p = 8u * tid + q; sidx[q * NT + tid] = p < m ? perm[p] : 0u; }
+    if (W32 && tid < 16) {
+        double lo = 0.0; float scf = 0.f;
+        const int l = A.s + tid;
+        if (A.kmin && l < A.L) {
+            lo = ord2f(A.kmin[t * A.L + l]);
+            const double wdt = ord2f(A.kmax[t * A.L + l]) - lo;
+            const double psc = (wdt > 0.0 && isfinite(wdt)) ? (double)((1u << PB) - 2u) / wdt : 0.0;
+            scf = isfinite(psc) ? __double2float_rz(psc) : 0.f;
+            if (!isfinite(scf)) scf = 0.f;
+        }
+        s_plo[tid] = lo; s_psc[tid] = scf;
+    }
     __syncthreads();
 
     // composite order (key_{s-1}, ..., key_0, row id) of the whole node: only needed when the node arrives unordered
@@ -2444,14 +2464,8 @@ __global__ void __launch_bounds__(NT, (NT == 128 ? RPF_BOT_MINB128 : 1)) k_botto
         // almost all codes on magnitudes near zero, where no projections live.
         // (the difference is taken in fp64 -- keys far from zero keep their resolution -- the scaling in fp32: a 24-bit mantissa
         //  against <= 24 prefix bits, 3 instructions instead of an fp64 multiply, compare / select and fp64 -> int conversion)
-        double plo = 0.0; float pscf = 0.f;
-        if (W32 && A.kmin) {
-            plo = ord2f(A.kmin[t * A.L + l]);
-            const double wdt = ord2f(A.kmax[t * A.L + l]) - plo;
-            const double psc = (wdt > 0.0 && isfinite(wdt)) ? (double)((1u << PB) - 2u) / wdt : 0.0;
-            pscf = isfinite(psc) ? __double2float_rz(psc) : 0.f;
-            if (!isfinite(pscf)) pscf = 0.f;
-        }
+        const double plo = W32 ? s_plo[j & 15] : 0.0;
+        const float pscf = W32 ? s_psc[j & 15] : 0.f;
         auto make_word = [&](ull key, unsigned slot) -> W {
             if (W32) {
                 const float fv = __double2float_rz(ord2f(key) - plo) * pscf;
@@ -2489,7 +2503,17 @@ __global__ void __launch_bounds__(NT, (NT == 128 ? RPF_BOT_MINB128 : 1)) k_botto
         gather_and_sort();
 
         // ---- neighbours with equal key prefixes: re-check with the full keys
+        // (UNI) pairs (x0+q, x0+q+1) of this thread whose prefixes collide, bit q; swaps between equal prefixes leave it unchanged
+        unsigned cmask = 0;
         auto tie_flag = [&]() -> int {
+            if (UNI) {
+                const int lim = (int)sz[x0 >> lpv] - (int)(x0 & (Pv - 1));      // slots q < lim of this thread hold elements
+                cmask = 0;
+#pragma unroll
+                for (int q = 0; q < 7; ++q) cmask |= (unsigned)((q + 1 < lim) & ((v[q] >> SB) == (v[q + 1] >> SB))) << q;
+                if (8 < lim) cmask |= (unsigned)((v[7] >> SB) == (w[tid + 1] >> SB)) << 7;   // slot x0+8: same segment, thread tid+1
+                return __syncthreads_or((int)cmask);
+            }
             int f = 0;
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
@@ -2506,6 +2530,27 @@ __global__ void __launch_bounds__(NT, (NT == 128 ? RPF_BOT_MINB128 : 1)) k_botto
         // stable.  Returns whether two compared elements had EQUAL full keys (only then does the incoming order matter).
         auto fix_up = [&]() -> int {
             int eqfull = 0;
+            while (UNI) {              // each thread walks its own colliding pairs only (most threads have none)
+                int swapped = 0;
+                for (int par = 0; par < 2; ++par) {
+                    if (cmask & (0x55u << par)) {
+#pragma unroll
+                        for (int q2 = 0; q2 < 4; ++q2) {
+                            const int q = 2 * q2 + par;
+                            if (cmask & (1u << q)) {
+                                const unsigned slot = x0 + q;
+                                const W a = w[TI(slot)], b = w[TI(slot + 1)];
+                                const unsigned sa = (unsigned)(a & SMASK), sb2 = (unsigned)(b & SMASK);
+                                const ull fa = kl[sidx[TI(sa)]], fb = kl[sidx[TI(sb2)]];
+                                eqfull |= (fa == fb);
+                                if (fa > fb || (fa == fb && sa > sb2)) { w[TI(slot)] = b; w[TI(slot + 1)] = a; swapped = 1; }
+                            }
+                        }
+                    }
+                    __syncthreads();
+                }
+                if (!__syncthreads_or(swapped)) return __syncthreads_or(eqfull);
+            }
             while (true) {
                 int swapped = 0;
                 for (int par = 0; par < 2; ++par) {
@@ -2578,7 +2623,23 @@ __global__ void __launch_bounds__(NT, (NT == 128 ? RPF_BOT_MINB128 : 1)) k_botto
             }
         }
         // ---- move the row ids: left half stays, right half starts at the middle of the segment
-        {
+        if (UNI) {
+            const unsigned i0 = x0 & (Pv - 1), se = sz[x0 >> lpv], nh = se >> 1;
+            const int lim = (int)se - (int)i0;
+            const unsigned hd = (Pv >> 1) - nh;             // an element of rank i >= nh moves hd slots up
+            uint32_t val[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) val[q] = sidx[TI((unsigned)(v[q] & SMASK) & (P0 - 1u))];   // (padding words: any slot in range)
+            __syncthreads();
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {       // branch-free: padding slots store to a per-thread dummy word
+                const unsigned di = (i0 + q < nh) ? (unsigned)(q * NT + tid) : TI(x0 + q + hd);
+                uint32_t* dp = (q < lim) ? sidx + di : s_trash + tid;
+                *dp = val[q];
+            }
+            // (tried: prefetch.global.L2 of the keys two levels ahead while the ids move -- the node's point set is the same at
+            //  every level of the subtree; bottom 1.95 -> 1.98 ms, the gather latency is already hidden by the 10 resident CTAs)
+        } else {
             uint32_t val[8]; uint32_t dst[8];
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
@@ -2598,7 +2659,14 @@ __global__ void __launch_bounds__(NT, (NT == 128 ? RPF_BOT_MINB128 : 1)) k_botto
         any_internal = __syncthreads_or(any_internal);
         if (!can_grow) break;      // unreachable for the shapes the host routes here
         // ---- emit the children that are Tips
-        {
+        if (UNI) {
+            const unsigned Pc = Pv >> 1, c = x0 >> (lpv - 1), ic0 = x0 & (Pc - 1), lsz = t_lsz[c];
+            if (ic0 < lsz) {
+                uint32_t* dstp = perm + t_ps[nxt][c] + ic0;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) if (ic0 + q < lsz) dstp[q] = sidx[q * NT + tid];
+            }
+        } else {
             const unsigned Pc = Pv >> 1;
             const int lpc = lpv - 1;
 #pragma unroll
