@@ -1066,6 +1066,8 @@ struct TopArgs {
     ull* cand;
     uint32_t* cand_total;
     uint32_t* done;                  // [Tg] CTAs of k_top_hist that finished the tree (NULL: separate pick kernels)
+    int NB2, nnodes2;                // k_top_relabel_hist: bins per node / nodes of level l + 1 (its first node is child0)
+    uint32_t* done2;                 //   and its ticket counters (NULL: separate pick kernels), see `done`
     int fused_finish;                // k_top_finish_all instead of finish_warp -> finish -> ties
     uint32_t* wl_cnt;                // [2] work-list lengths of this level: big median bins (k_top_finish), straddling ties (k_top_ties)
     uint32_t* wl_big;                // [Tg * nnodes] entries t * nnodes + nl
@@ -1082,6 +1084,7 @@ struct TopArgs {
 #ifndef TOP_NT
 #define TOP_NT 512
 #endif
+#define HIST_CH_MAX 57344 /* points per CTA of the histogram kernels: multiples of 8192 below 65 536 (16-bit counters) */
 #define HBINS 32768       /* shared-memory histogram counters (16-bit, two per word; a CTA streams TOP_CH <= 65535 points) */
 #define HBINS_MAXNB 16384
 #define FIN_CAP 4096      /* in-bin sort capacity */
@@ -1277,10 +1280,10 @@ __global__ void __launch_bounds__(TOP_NT) k_top_hist(TopArgs A) {
     }
     if (A.smem_hist) {
         __syncthreads();
+        // one 64-bit RED per pair of adjacent 32-bit counters (the low one never carries: counts stay below 2^32)
         for (int w2 = tid; w2 < (tot + 1) / 2; w2 += TOP_NT) {
             const uint32_t v = sh[w2];
-            if (v & 0xffffu) atomicAdd(&gh[2 * w2], v & 0xffffu);
-            if (v >> 16) atomicAdd(&gh[2 * w2 + 1], v >> 16);
+            if (v) atomicAdd((ull*)gh + w2, (ull)(v & 0xffffu) | ((ull)(v >> 16) << 32));
         }
     }
     if (!A.done) return;
@@ -1819,12 +1822,14 @@ __global__ void __launch_bounds__(TOP_NT, RELABEL_MINB) k_top_relabel(TopArgs A,
 // 2-byte bins / labels).  They stream 8 points per load (one 16-byte load of bins + one of labels, LEAN_G such pairs in
 // flight per thread) and touch an 8-byte key only for a point in the median bin or in a margin-tracking bin
 // (NodeSel::lo_bin / hi_bin), so no level has to fall back to streaming the keys.
-struct LeanTabs { ull thr[SMEM_NODES]; uint16_t sbin[SMEM_NODES], lob[SMEM_NODES], hib[SMEM_NODES]; };
+// bins: x = median bin | lo_bin << 16, y = hi_bin -- ONE 8-byte shared-memory read per point (three 2-byte table reads were 17 %
+// of the fused kernel's issue slots, ncu source page)
+struct LeanTabs { ull thr[SMEM_NODES]; uint2 bins[SMEM_NODES]; };
 
 __device__ __forceinline__ void lean_load_tabs(const TopArgs& A, const NodeSel* sel, LeanTabs& T, int nthreads) {
     for (int j = threadIdx.x; j < A.nnodes; j += nthreads) {
         T.thr[j] = sel[j].thr;
-        T.sbin[j] = (uint16_t)sel[j].sel_bin; T.lob[j] = sel[j].lo_bin; T.hib[j] = sel[j].hi_bin;
+        T.bins[j] = make_uint2(((unsigned)sel[j].sel_bin & 0xffffu) | ((unsigned)sel[j].lo_bin << 16), (unsigned)sel[j].hi_bin);
     }
 }
 
@@ -1838,9 +1843,10 @@ __device__ __forceinline__ unsigned lean_sides8(const TopArgs& A, NodeSel* sel, 
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
         if ((unsigned)nl[u] < (unsigned)A.nnodes) {
-            const unsigned sb = T.sbin[nl[u]];
+            const uint2 tb = T.bins[nl[u]];
+            const unsigned sb = tb.x & 0xffffu;
             if (b[u] >= sb) right |= 1u << u;
-            const unsigned k = b[u] == sb ? 1u : (b[u] == T.lob[nl[u]] ? 2u : (b[u] == T.hib[nl[u]] ? 3u : 0u));
+            const unsigned k = b[u] == sb ? 1u : (b[u] == (tb.x >> 16) ? 2u : (b[u] == tb.y ? 3u : 0u));
             kind |= k << (2 * u);
         }
     }
@@ -1925,6 +1931,94 @@ __global__ void __launch_bounds__(TOP_NT, 2) k_top_relabel_lean(TopArgs A) {
             }
         }
     }
+}
+
+// relabel of level l FUSED with the histogram of level l + 1 (both levels lean, the next one with a shared-memory histogram):
+// one pass reads (bin_l, label_l, key_{l+1}) and writes (label_{l+1}, bin_{l+1}) -- 16 bytes per point instead of the 6 of the
+// relabel pass plus the 12 of a separate histogram pass, one launch (ramp, table loads, tail) less per level, and the key load of
+// the next level is in flight while the sides are decided.  The tail (flush, ticket, fused pick) is k_top_hist's.
+__global__ void __launch_bounds__(TOP_NT, 2) k_top_relabel_hist(TopArgs A) {
+    extern __shared__ uint32_t sh[];                             // level l + 1: 16-bit counters, two per word; then the key stage
+    __shared__ LeanTabs T;
+    const int t = blockIdx.y, tid = threadIdx.x;
+    const int64_t i0 = (int64_t)blockIdx.x * A.ch, i1 = min(A.n, i0 + A.ch);
+    const ull* keys_t = A.keys + (int64_t)t * A.L * A.ks;
+    const ull* keys = keys_t + (int64_t)A.l * A.ks;
+    const ull* keys2 = keys + A.ks;
+    uint16_t* lab = A.label + (int64_t)t * A.n;
+    uint16_t* pb = A.pbin + (int64_t)t * A.n;
+    NodeSel* sel = A.sel + (int64_t)t * A.NTOP + A.node0;
+    const double lo2 = A.binlo[t * A.L + A.l + 1];
+    const float sc2 = __double2float_rz(A.binscale[t * A.L + A.l + 1]);
+    const int NB2 = A.NB2, tot2 = A.nnodes2 * NB2;
+    // key stage: the 8 next-level keys of a thread's 8 points (64 bytes) travel global -> shared by cp.async one iteration
+    // ahead, as four 16-byte pieces at [piece][tid] (conflict-free both ways); held in registers they would pin 16 of the 64
+    // registers across the side decision and the compiler sinks the loads to their use -- three dependent latencies per iteration
+    uint4* stage = (uint4*)(sh + HBINS / 2);
+    const unsigned st0 = (unsigned)__cvta_generic_to_shared(stage + tid);
+    auto fetch_keys = [&](int64_t i) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(st0 + (unsigned)c * TOP_NT * 16u), "l"(keys2 + i + 2 * c) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    const int64_t ifirst = i0 + (int64_t)tid * 8;
+    if (ifirst < i1) fetch_keys(ifirst);
+    uint4 qb = make_uint4(0, 0, 0, 0), ql = make_uint4(0, 0, 0, 0);
+    if (ifirst < i1) { qb = __ldcs((const uint4*)(pb + ifirst)); if (A.haslab) ql = *(const uint4*)(lab + ifirst); }
+    lean_load_tabs(A, sel, T, TOP_NT);
+    for (int j = tid; j < (tot2 + 1) / 2; j += TOP_NT) sh[j] = 0;
+    __syncthreads();
+    const int nit = A.ch / (8 * TOP_NT);
+    for (int it = 0; it < nit; ++it) {
+        const int64_t i = i0 + ((int64_t)it * TOP_NT + tid) * 8;
+        if (i >= i1) break;
+        const int64_t inext = i + (int64_t)TOP_NT * 8;
+        const bool more = it + 1 < nit && inext < i1;
+        unsigned b[8], g[8];
+        int nl[8];
+        unpack8(qb, b); unpack8(ql, g);
+        if (more) { qb = __ldcs((const uint4*)(pb + inext)); if (A.haslab) ql = *(const uint4*)(lab + inext); }   // next iteration's rows
+#pragma unroll
+        for (int u = 0; u < 8; ++u) nl[u] = (int)g[u] - A.node0;
+        const unsigned right = lean_sides8(A, sel, T, keys, keys_t, t, i, b, nl);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        ull k2[8];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { const uint4 q = stage[c * TOP_NT + tid]; k2[2 * c] = (ull)q.x | ((ull)q.y << 32); k2[2 * c + 1] = (ull)q.z | ((ull)q.w << 32); }
+        if (more) fetch_keys(inext);                              // the stage words of this thread are in registers now
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            unsigned b2 = 0;
+            if ((unsigned)nl[u] < (unsigned)A.nnodes) {           // the point moves to child 2 nl + side: a node of level l + 1
+                const int c = 2 * nl[u] + (int)((right >> u) & 1u);
+                g[u] = (unsigned)(A.child0 + c);
+                b2 = (unsigned)key_bin(k2[u], lo2, sc2, NB2);
+                const int j = c * NB2 + (int)b2;
+                atomicAdd(&sh[j >> 1], 1u << ((j & 1) << 4));
+            }
+            b[u] = b2;
+        }
+        *(uint4*)(lab + i) = pack8(g);
+        *(uint4*)(pb + i) = pack8(b);
+    }
+    __syncthreads();
+    uint32_t* gh = A.hist + (int64_t)t * A.HSZ;
+    for (int w2 = tid; w2 < (tot2 + 1) / 2; w2 += TOP_NT) {
+        const uint32_t v = sh[w2];
+        if (v) atomicAdd((ull*)gh + w2, (ull)(v & 0xffffu) | ((ull)(v >> 16) << 32));
+    }
+    if (!A.done2) return;
+    __shared__ uint32_t s_last;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(&A.done2[t], 1u) == gridDim.x - 1) ? 1u : 0u;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    TopArgs A2 = A;
+    A2.l = A.l + 1; A2.node0 = A.child0; A2.nnodes = A.nnodes2; A2.NB = NB2;
+    for (int nl2 = tid >> 5; nl2 < A2.nnodes; nl2 += TOP_NT / 32) pick_node_warp(A2, t, nl2);
 }
 
 // last top level: children instead of labels, and the points are placed into their child's slice of perm.  The CTA's
@@ -3113,6 +3207,7 @@ void rpf_job_geometry(const Topology& tp, int cap_cfg, int Lk, JobGeom& G) {
         G.nb_level[l] = nb;
         G.HSZ = std::max<int64_t>(G.HSZ, (int64_t)nodes * nb);
     }
+    G.HSZ = (G.HSZ + 1) & ~(int64_t)1;          // 64-bit REDs on counter pairs (k_top_hist flush)
     G.MAXTD = L + 1;
     // fast bottom kernel: at most 10 splitting levels below s, and 2^levels slots fit one CTA (8192)
     G.bottom_levels = std::max(0, L - s);
@@ -3252,11 +3347,31 @@ int rpf_launch_job(rpf_handle* h, BuildJob& J, const JobPlan& P, const char* tab
         // chunk to reach 2 CTAs per SM; compact / relabel gain 3-5 % from the wave model)
         int ch_hist = TOP_CH;
         while (ch_hist > 8192 && ((n + ch_hist - 1) / ch_hist) * tg < 2 * 148) ch_hist >>= 1;
-        if (h->top_chunk[0] >= 8192 && h->top_chunk[0] <= TOP_CH && h->top_chunk[0] % 8192 == 0) ch_hist = h->top_chunk[0];
+        // ... and grows it (up to 57 344 points: 16-bit counters) when that saves a wave: the histogram kernels hold 2 CTAs per SM
+        // and pay a fixed ~16 K points' worth per CTA (zero + flush of the 64 KB histogram), so 16 trees x 1M points run as ONE
+        // wave of 288 CTAs instead of 496 CTAs in 1.7 waves
+        {
+            double best = 1e300; int best_ch = ch_hist;
+            for (int ch = ch_hist; ch <= HIST_CH_MAX; ch += 8192) {
+                const int64_t ctas = ((n + ch - 1) / ch) * tg;
+                const int64_t waves = (ctas + 2 * 148 - 1) / (2 * 148);
+                const double cost = (double)waves * (ch + 16384);
+                if (cost < best * 0.98) { best = cost; best_ch = ch; }
+            }
+            if (h->hist_big_chunk) ch_hist = best_ch;
+        }
+        if (h->top_chunk[0] >= 8192 && h->top_chunk[0] <= HIST_CH_MAX && h->top_chunk[0] % 8192 == 0) ch_hist = h->top_chunk[0];
         const int ch_compact = pick_chunk(3, 2048, h->top_chunk[1]);
         const int ch_relabel = pick_chunk(2, 2048, h->top_chunk[2]);
         auto grid_for = [&](int ch) { return dim3((unsigned)((n + ch - 1) / ch), (unsigned)tg); };
         bool all_top_internal = true;
+        auto done_for = [&](int nnodes_l) -> uint32_t* { return ((h->fused_top & 1) && nnodes_l >= 16 && tg >= 16) ? done : nullptr; };
+        auto lean_level = [&](int l) -> bool {
+            return h->lean_top && (n & 7) == 0 && (int)(P.level_off[l + 1] - P.level_off[l]) <= SMEM_NODES && P.lvl_all_internal[l];
+        };
+        RPF_CUDA(h, cudaFuncSetAttribute(k_top_relabel_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, HBINS * 2 + TOP_NT * 64));
+        RPF_CUDA(h, cudaFuncSetAttribute(k_top_relabel_hist, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        bool hist_prefused = false;        // this level's histogram (and pick) came out of the previous level's k_top_relabel_hist
         for (int l = 0; l < s_top; ++l) {
             A.l = l; A.node0 = (int)P.level_off[l]; A.nnodes = (int)(P.level_off[l + 1] - P.level_off[l]);
             A.haslab = (l > 0 || P.nroots > 1) ? 1 : 0;
@@ -3265,8 +3380,10 @@ int rpf_launch_job(rpf_handle* h, BuildJob& J, const JobPlan& P, const char* tab
             A.all_internal = P.lvl_all_internal[l];
             all_top_internal = all_top_internal && A.all_internal;
             A.scatter_fast = (all_top_internal && 2 * A.nnodes <= SCAT_MAX) ? 1 : 0;
-            RPF_CUDA(h, cudaMemsetAsync(hist, 0, (size_t)tg * HSZ * 4, h->stream));
-            RPF_CUDA(h, cudaMemsetAsync(cand_total, 0, (size_t)tg * 12 + 8, h->stream));
+            if (!hist_prefused) {
+                RPF_CUDA(h, cudaMemsetAsync(hist, 0, (size_t)tg * HSZ * 4, h->stream));
+                RPF_CUDA(h, cudaMemsetAsync(cand_total, 0, (size_t)tg * 12 + 8, h->stream));
+            }
             dim3 gn((unsigned)A.nnodes, (unsigned)tg);
             const size_t hs = A.smem_hist ? ((size_t)A.nnodes * A.NB + 1) / 2 * 4 : 0;     // 16-bit counters
             A.ch = ch_hist;
@@ -3275,8 +3392,9 @@ int rpf_launch_job(rpf_handle* h, BuildJob& J, const JobPlan& P, const char* tab
             // (measured, profiles/r02_top_fusion_sweep.txt: the ticket's __threadfence also waits for the CTA's streaming bin
             //  stores; with >= 16 trees per job other CTAs hide that and the fusion gains 0.15 ms at 32 trees, with 4 trees it
             //  costs 0.13 ms -- so it is only used for large jobs)
-            A.done = ((h->fused_top & 1) && A.nnodes >= 16 && tg >= 16) ? done : nullptr;
-            RPF_LAUNCH(h, PH_TOP_HIST, k_top_hist, grid_for(ch_hist), TOP_NT, hs, A);
+            A.done = done_for(A.nnodes);
+            if (!hist_prefused) RPF_LAUNCH(h, PH_TOP_HIST, k_top_hist, grid_for(ch_hist), TOP_NT, hs, A);
+            hist_prefused = false;
             if (!A.done) {
                 if (A.NB <= 256) RPF_LAUNCH(h, PH_TOP_PICK, k_top_pick_warp, (unsigned)(((int64_t)A.nnodes * tg + 7) / 8), 256, 0, A);
                 else RPF_LAUNCH(h, PH_TOP_PICK, k_top_pick, gn, 256, 0, A);
@@ -3296,6 +3414,15 @@ int rpf_launch_job(rpf_handle* h, BuildJob& J, const JobPlan& P, const char* tab
                 RPF_LAUNCH(h, PH_TOP_TIES, k_top_ties, gw, 512, 0, A);
             }
             A.ch = ch_relabel;
+            // relabel fused with the next level's histogram when that level is lean too and its histogram fits shared memory
+            if (lean && !last && h->fuse_relabel_hist && A.vec && lean_level(l + 1) && G.smem_level[l + 1]) {
+                A.nnodes2 = (int)(P.level_off[l + 2] - P.level_off[l + 1]); A.NB2 = G.nb_level[l + 1]; A.done2 = done_for(A.nnodes2);
+                RPF_CUDA(h, cudaMemsetAsync(hist, 0, (size_t)tg * HSZ * 4, h->stream));
+                RPF_CUDA(h, cudaMemsetAsync(cand_total, 0, (size_t)tg * 12 + 8, h->stream));
+                A.ch = ch_hist;
+                RPF_LAUNCH(h, PH_TOP_RELABEL, k_top_relabel_hist, grid_for(ch_hist), TOP_NT, (size_t)HBINS * 2 + TOP_NT * 64, A);
+                hist_prefused = true;
+            } else
             if (lean && !last) RPF_LAUNCH(h, PH_TOP_RELABEL, k_top_relabel_lean, grid_for(ch_relabel), TOP_NT, 0, A);
             else if (lean && A.scatter_fast)
                 RPF_LAUNCH(h, PH_TOP_RELABEL, k_top_scatter_lean, dim3((unsigned)((n + SCAT_CH - 1) / SCAT_CH), (unsigned)tg), SCAT_NT, (size_t)SCAT_CH * 4, A);
@@ -3533,6 +3660,9 @@ int rpf_build_impl(rpf_handle* h, const double* hostX) {
                 J.sink_groups = std::max(1, 8 / parts); J.sink_ev0 = part * J.sink_groups;
                 return rpf_launch_job(h, J, BP->P, BP->d_tab);
             };
+            // (tried: every branch projecting its own trees on its own stream, one branch after the other, so that the LSU-bound
+            //  projection of branch b + 1 runs beside the DRAM / issue-bound top phase of branch b: 6.5 -> 6.6 ms with 2 branches,
+            //  6.9 ms with 4 -- X is read once per branch and the kernels do not share an SM well)
             if (L > 0 && n > 0 && !pipelined) {       // one pass over X for all trees of the group
                 int rc2 = rpf_project_launch(h, PH_PROJECT, h->dX, n, t0, tg, L, true, keys, n, kmin, kmax);
                 if (rc2) return rc2;

@@ -181,6 +181,8 @@ struct rpf_handle {
                                          //         finish kernel per level instead of finish_warp -> finish -> ties (measured slower: off)
     int rerank_gemm = 1;                 // option: leaf-grouped FP64 tensor-core re-rank (rerank.cu): 0 = never, 1 = when it pays (d >= 512,
                                          //         >= 2 queries per leaf), 2 = whenever applicable (tests)
+    int hist_big_chunk = 1;              // option: histogram kernels may take up to 57 344 points per CTA when that saves a wave
+    int fuse_relabel_hist = 1;           // option: top-phase relabel of level l fused with the histogram of level l + 1 (k_top_relabel_hist)
     int bottom_select = 0;               // option: warp-per-node bottom kernel (k_bottom4: median select + partition on the levels whose
                                          //         children split again, sort only where Tips form); 0 = k_bottom3 everywhere
     int project_prefetch = 1;            // option: L2 prefetch of a later tile in the single-buffer projection kernel

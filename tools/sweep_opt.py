@@ -1,5 +1,6 @@
 """A/B of one engine option on configs[1] data: mean device build ms, per-phase profile, and a check that every setting gives
-the same forest.  Usage: python tools/sweep_opt.py <option> <v0,v1,...> [trees,...]"""
+the same forest.  Usage: python tools/sweep_opt.py <option> <v0,v1,...> [trees,...]
+       or: python tools/sweep_opt.py set "a=1,b=0;a=0,b=0;..." [trees,...]   (several options per setting)"""
 import json
 import os
 import sys
@@ -11,7 +12,11 @@ sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 import rp_tree_b200 as R  # noqa: E402
 
-opt, vals = sys.argv[1], [int(v) for v in sys.argv[2].split(",")]
+opt = sys.argv[1]
+if opt == "set":
+    vals = [dict((kv.split("=")[0], int(kv.split("=")[1])) for kv in st.split(",")) for st in sys.argv[2].split(";")]
+else:
+    vals = [{opt: int(v)} for v in sys.argv[2].split(",")]
 trees = [int(v) for v in sys.argv[3].split(",")] if len(sys.argv) > 3 else [32, 4]
 W = bench.WORKLOAD
 n, d = W["n"], W["d"]
@@ -25,7 +30,8 @@ for T in trees:
     f.setPoints(X)
     ref = None
     for v in vals:
-        f.setOption(opt, v)
+        for ok, ov in v.items():
+            f.setOption(ok, ov)
         ms = []
         for i in range(9):
             f.build(maxd, W["min_leaf"])
@@ -38,6 +44,6 @@ for T in trees:
         if ref is None:
             ref = sig
         f.setProfiling(True); f.build(maxd, W["min_leaf"]); prof = f.profile(); f.setProfiling(False)
-        print(json.dumps(dict(T=T, option=opt, value=v, build_ms=round(float(np.mean(ms)), 3), build_min=round(float(np.min(ms)), 3),
+        print(json.dumps(dict(T=T, setting=v, build_ms=round(float(np.mean(ms)), 3), build_min=round(float(np.min(ms)), 3),
                               phases={k: round(p[0], 3) for k, p in prof.items() if p[1]}, same_forest=sig == ref)), flush=True)
     f.close()
