@@ -145,14 +145,17 @@ class ClockSampler:
                     power_w_max=max(self.power) if self.power else None)
 
 
-def algorithmic_bytes(W, tlocal, L, s_top, C_mean):
-    """Algorithmic HBM bytes per launch for every kernel class."""
+def algorithmic_bytes(W, tlocal, L, s_top, C_mean, fused_levels=0):
+    """Algorithmic HBM bytes per launch for every kernel class.  fused_levels: top levels whose relabel
+    pass also produced the next level's histogram (k_top_relabel_hist: bin + label + next key read, label + bin write = 16
+    bytes per point instead of the 6 of a plain relabel; those levels have no k_top_hist launch)."""
     n, d = W["n"], W["d"]
+    nrel = max(s_top, 1)
     return {
         "project": 8 * d * n + 8 * tlocal * L * n,                     # read X once, write every (tree, level) key
         "top_hist": tlocal * n * (8 + 2 + 2),                          # key + label read, 2-byte bin write
         "top_compact": tlocal * n * (2 + 2),                           # bin + label (keys only for the median bin)
-        "top_relabel": tlocal * n * (2 + 2 + 2),                       # bin + label read, label write
+        "top_relabel": tlocal * n * (6 * (nrel - fused_levels) + 16 * fused_levels) // nrel,   # bin + label read, label write (mean over the launches)
         "bottom": tlocal * n * (4 + 4 + 8 * (L - s_top) + (8 if s_top > 0 else 0)),   # perm r/w + one key per bottom level
         # fp32 filter pass (k_knn_f32: d % 4 == 0, plain knn): 4d bytes per candidate + ~(k + 4) exact rows; else the exact kernel
         "q_knn": W["nq"] * ((C_mean * (4 * d + 4) + (W["k"] + 4) * 8 * d + 8 * d + 12 * W["k"]) if d % 4 == 0 and d < 512
@@ -344,7 +347,11 @@ def run_ours(args):
     lvl_max = [int(tp["seg_size"][tp["depth"] == l].max()) for l in range(int(tp["depth"].max()) + 1)]
     s_top = next((l for l, m in enumerate(lvl_max) if m <= cap), len(lvl_max))
     s_top = min(s_top, L)
-    ab = algorithmic_bytes(W, t_local, L, s_top, c_local)    # per-rank kernels: this rank's trees / candidates
+    nhist = prof["top_hist"][1] if "top_hist" in prof else 0
+    nrel = prof["top_relabel"][1] if "top_relabel" in prof else 0
+    # levels whose histogram came out of the previous level's fused pass (launch counts scale with the number of tree groups)
+    fused_levels = int(round(s_top * max(0, nrel - nhist) / nrel)) if nrel > 0 and nhist > 0 else 0
+    ab = algorithmic_bytes(W, t_local, L, s_top, c_local, fused_levels)    # per-rank kernels: this rank's trees / candidates
     kern = {kname: v for kname, v in prof.items() if v[1] > 0 and kname in ab}
     traffic_tab = {}
     for tf in ("r02_traffic.json", "r01_traffic.json"):      # DRAM bytes per launch from the committed `ncu --set full` captures
@@ -368,6 +375,8 @@ def run_ours(args):
         ach = per_launch / (avg_ms * 1e-3) / 1e9
         tj = traffic_tab.get(kname)
         traffic = int(tj["dram_bytes_per_launch"]) if tj else None
+        if tj and tj.get("trees_per_launch"):        # captured on one branch of the graph build (e.g. 16 of 32 trees per launch)
+            traffic = int(traffic * t_local / tj["trees_per_launch"])
         r = dict(bound="hbm", kernel=kname, achieved=round(ach, 1), peak=peak, unit="GB/s", frac=round(ach / peak, 4),
                  traffic=traffic, traffic_source=("ncu dram__bytes_read+write: profiles/%s" % ",".join(tj["source"])) if tj else None,
                  peak_source=peak_src, launches_per_step=nl, avg_launch_ms=round(avg_ms, 4),

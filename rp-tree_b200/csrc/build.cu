@@ -3365,7 +3365,7 @@ int rpf_launch_job(rpf_handle* h, BuildJob& J, const JobPlan& P, const char* tab
         const int ch_relabel = pick_chunk(2, 2048, h->top_chunk[2]);
         auto grid_for = [&](int ch) { return dim3((unsigned)((n + ch - 1) / ch), (unsigned)tg); };
         bool all_top_internal = true;
-        auto done_for = [&](int nnodes_l) -> uint32_t* { return ((h->fused_top & 1) && nnodes_l >= 16 && tg >= 16) ? done : nullptr; };
+        auto done_for = [&](int nnodes_l) -> uint32_t* { return ((h->fused_top & 1) && nnodes_l >= 16 && tg >= h->fused_pick_min_tg) ? done : nullptr; };
         auto lean_level = [&](int l) -> bool {
             return h->lean_top && (n & 7) == 0 && (int)(P.level_off[l + 1] - P.level_off[l]) <= SMEM_NODES && P.lvl_all_internal[l];
         };

@@ -1189,6 +1189,7 @@ int rpf_set_option(rpf_handle* h, const char* name, int64_t value) {
     if (s == "project_variant") { h->project_variant = (int)value; return RPF_OK; }
     if (s == "bottom_select") { h->bottom_select = (int)value; return RPF_OK; }
     if (s == "hist_big_chunk") { h->hist_big_chunk = (int)value; return RPF_OK; }
+    if (s == "fused_pick_min_tg") { h->fused_pick_min_tg = (int)value; return RPF_OK; }
     if (s == "fuse_relabel_hist") { h->fuse_relabel_hist = (int)value; return RPF_OK; }
     if (s == "fused_top") { h->fused_top = (int)value; return RPF_OK; }
     if (s == "rerank_gemm") { h->rerank_gemm = (int)value; return RPF_OK; }

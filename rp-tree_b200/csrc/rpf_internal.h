@@ -181,6 +181,7 @@ struct rpf_handle {
                                          //         finish kernel per level instead of finish_warp -> finish -> ties (measured slower: off)
     int rerank_gemm = 1;                 // option: leaf-grouped FP64 tensor-core re-rank (rerank.cu): 0 = never, 1 = when it pays (d >= 512,
                                          //         >= 2 queries per leaf), 2 = whenever applicable (tests)
+    int fused_pick_min_tg = 16;          // option: trees per job from which the histogram kernels also pick the median bins (ticket counter)
     int hist_big_chunk = 1;              // option: histogram kernels may take up to 57 344 points per CTA when that saves a wave
     int fuse_relabel_hist = 1;           // option: top-phase relabel of level l fused with the histogram of level l + 1 (k_top_relabel_hist)
     int bottom_select = 0;               // option: warp-per-node bottom kernel (k_bottom4: median select + partition on the levels whose

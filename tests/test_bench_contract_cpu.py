@@ -52,3 +52,5 @@ def test_algorithmic_bytes_table():
     assert ab["project"] == 8 * d * n + 8 * 32 * 14 * n
     assert ab["top_hist"] == 32 * n * 12 and ab["top_compact"] == 32 * n * 4 and ab["top_relabel"] == 32 * n * 6
     assert ab["bottom"] == 32 * n * (4 + 4 + 8 * 4 + 8)
+    fused = bench.algorithmic_bytes(W, 32, 14, 10, 1968.0, fused_levels=9)       # k_top_relabel_hist on 9 of the 10 top levels
+    assert fused["top_relabel"] == 32 * n * (6 * 1 + 16 * 9) // 10 and fused["top_hist"] == ab["top_hist"]

@@ -23,6 +23,7 @@ def main(paths):
         rows = list(csv.reader(out.splitlines()))
         hdr, units = rows[0], rows[1]
         ir, iw, it, ik = (hdr.index(x) for x in ("dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__time_duration.sum", "Kernel Name"))
+        ig = hdr.index("Grid Size") if "Grid Size" in hdr else None
         for r in rows[2:]:
             name = r[ik]
             ph = next((p for key, p in PHASE if key in name), None)
@@ -31,11 +32,20 @@ def main(paths):
             if ph == "project" and float(r[ir].replace(",", "")) * UNIT[units[ir]] < 1e8:
                 continue            # the query-projection launch of the same template
             b = float(r[ir].replace(",", "")) * UNIT[units[ir]] + float(r[iw].replace(",", "")) * UNIT[units[iw]]
-            acc.setdefault(ph, []).append((b, float(r[it].replace(",", "")) * TIME_MS.get(units[it], 1.0), os.path.basename(path), name[:48]))
+            # top-phase / bottom kernels: grid.y = trees of the launch (the graph build runs them per concurrent branch)
+            trees = None
+            if ig is not None and (ph.startswith("top_") or ph == "bottom"):
+                try:
+                    trees = int(r[ig].strip("() ").split(",")[1])
+                except Exception:
+                    trees = None
+            acc.setdefault(ph, []).append((b, float(r[it].replace(",", "")) * TIME_MS.get(units[it], 1.0), os.path.basename(path), name[:48], trees))
     res = {}
     for ph, lst in acc.items():
         res[ph] = dict(dram_bytes_per_launch=sum(x[0] for x in lst) / len(lst), launches_profiled=len(lst),
                        ncu_ms_per_launch=sum(x[1] for x in lst) / len(lst), source=sorted({x[2] for x in lst}), kernel=lst[0][3])
+        if lst[0][4]:
+            res[ph]["trees_per_launch"] = lst[0][4]      # bench.py scales the bytes to the trees of ITS launch
     dst = os.path.join(ROOT, "profiles", OUT)
     with open(dst, "w") as fh:
         json.dump(res, fh, indent=1, sort_keys=True)
