@@ -2645,7 +2645,7 @@ __global__ void __launch_bounds__(NT, (NT == 128 ? RPF_BOT_MINB128 : 1)) k_botto
                 }
                 if (!__syncthreads_or(swapped)) return __syncthreads_or(eqfull);
             }
-            while (true) {
+            while (!UNI) {
                 int swapped = 0;
                 for (int par = 0; par < 2; ++par) {
                     for (unsigned c = tid; c < (P0 >> 1); c += NT) {
