@@ -3460,9 +3460,15 @@ int rpf_launch_job(rpf_handle* h, BuildJob& J, const JobPlan& P, const char* tab
                 RPF_CUDA(h, cudaStreamWaitEvent(h->d2h_stream, h->sink_ev[J.sink_ev0 + gi], 0));
                 RPF_CUDA(h, cudaMemcpyAsync(h->sink_perm + (int64_t)(J.gt0 + ta) * n, J.perm + (int64_t)ta * J.ps, (size_t)(tb - ta) * n * 4,
                                             cudaMemcpyDeviceToHost, h->d2h_stream));
+                // the group's node arrays are final too (top-phase nodes: k_top_finalize above; the rest: this bottom launch), so
+                // they leave with the group instead of as a 25 MB tail after the last one
+                const size_t o = (size_t)(J.gt0 + ta) * (size_t)J.ns, nbn = (size_t)(tb - ta) * (size_t)J.ns * 8;
+                if (h->sink_thr) RPF_CUDA(h, cudaMemcpyAsync(h->sink_thr + o, J.thr + o, nbn, cudaMemcpyDeviceToHost, h->d2h_stream));
+                if (h->sink_mlo) RPF_CUDA(h, cudaMemcpyAsync(h->sink_mlo + o, J.mlo + o, nbn, cudaMemcpyDeviceToHost, h->d2h_stream));
+                if (h->sink_mhi) RPF_CUDA(h, cudaMemcpyAsync(h->sink_mhi + o, J.mhi + o, nbn, cudaMemcpyDeviceToHost, h->d2h_stream));
             }
         }
-        if (to_sink) h->sink_perm_streamed = true;
+        if (to_sink) { h->sink_perm_streamed = true; h->sink_nodes_streamed = true; }
     }
     return RPF_OK;
 }
@@ -3580,7 +3586,7 @@ int rpf_build_impl(rpf_handle* h, const double* hostX) {
     const bool pipelined = hostX && Tg == T && L > 0 && n > 0;
     // export sink: only the host-data build streams into it (never captured into the build graph)
     const bool sink = hostX && h->sink_perm != nullptr;
-    h->sink_pending = false; h->sink_perm_streamed = false;
+    h->sink_pending = false; h->sink_perm_streamed = false; h->sink_nodes_streamed = false;
     if (h->d2h_stream) RPF_CUDA(h, cudaStreamSynchronize(h->d2h_stream));   // a previous build's download is complete before its source is rewritten
     if (sink) {
         if (!h->d2h_stream) RPF_CUDA(h, cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
@@ -3697,9 +3703,11 @@ int rpf_build_impl(rpf_handle* h, const double* hostX) {
             RPF_CUDA(h, cudaEventRecord(h->sink_ev[8], h->stream));
             RPF_CUDA(h, cudaStreamWaitEvent(h->d2h_stream, h->sink_ev[8], 0));
             const size_t nb = (size_t)T * (size_t)nn * 8;
-            if (h->sink_thr && nb) RPF_CUDA(h, cudaMemcpyAsync(h->sink_thr, h->d_thr, nb, cudaMemcpyDeviceToHost, h->d2h_stream));
-            if (h->sink_mlo && nb) RPF_CUDA(h, cudaMemcpyAsync(h->sink_mlo, h->d_mlo, nb, cudaMemcpyDeviceToHost, h->d2h_stream));
-            if (h->sink_mhi && nb) RPF_CUDA(h, cudaMemcpyAsync(h->sink_mhi, h->d_mhi, nb, cudaMemcpyDeviceToHost, h->d2h_stream));
+            if (!h->sink_nodes_streamed) {
+                if (h->sink_thr && nb) RPF_CUDA(h, cudaMemcpyAsync(h->sink_thr, h->d_thr, nb, cudaMemcpyDeviceToHost, h->d2h_stream));
+                if (h->sink_mlo && nb) RPF_CUDA(h, cudaMemcpyAsync(h->sink_mlo, h->d_mlo, nb, cudaMemcpyDeviceToHost, h->d2h_stream));
+                if (h->sink_mhi && nb) RPF_CUDA(h, cudaMemcpyAsync(h->sink_mhi, h->d_mhi, nb, cudaMemcpyDeviceToHost, h->d2h_stream));
+            }
             if (!h->sink_perm_streamed && n > 0)
                 RPF_CUDA(h, cudaMemcpyAsync(h->sink_perm, h->d_perm, (size_t)T * n * 4, cudaMemcpyDeviceToHost, h->d2h_stream));
             RPF_CUDA(h, cudaEventRecord(h->sink_ev[9], h->d2h_stream));

@@ -142,6 +142,7 @@ struct rpf_handle {
     cudaStream_t d2h_stream = nullptr;
     cudaEvent_t sink_ev[10] = {nullptr};  // [0..7] bottom groups, [8] whole build, [9] sink complete
     bool sink_pending = false;            // the sink holds (or is receiving) the forest of the last build
+    bool sink_nodes_streamed = false;     // ... and the thr / mlo / mhi copies, tree group by tree group
     bool sink_perm_streamed = false;      // set by the job when it issued the perm copies itself
     std::string err;
 

@@ -22,9 +22,10 @@ cap() {
 cap 'k_project_t' 0 1 project
 cap 'k_bottom3' 0 2 bottom
 cap 'k_knn_f32' 0 1 knn
-cap 'k_top_hist' 5 1 hist
+cap 'k_top_hist' 0 1 hist
 cap 'k_top_compact_lean' 5 1 compact
-cap 'k_top_relabel_lean' 5 1 relabel
+cap 'k_top_relabel_hist' 5 1 relabel
 cap 'k_top_finish_warp' 5 1 finish
+cap 'k_top_scatter_lean' 0 1 scatter
 fi
 du -sh $O >> $O/fin_sizes.txt
