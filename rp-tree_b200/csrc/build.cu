@@ -1094,8 +1094,8 @@ struct TopArgs {
 // (monotone: difference in fp64 -- keys far from zero keep their resolution --, scaling and conversion in fp32: NB <= 65536
 //  bins against a 24-bit mantissa; three cheap instructions instead of an fp64 multiply and an fp64 -> int conversion)
 __device__ __forceinline__ int key_bin(ull o, double lo, float scf, int NB) {
-    const int b = __float2int_rz(__double2float_rz(ord2f(o) - lo) * scf);
-    return b < 0 ? 0 : (b >= NB ? NB - 1 : b);
+    // (the unsigned conversion saturates: negative and NaN -> 0, so one min() clamps both ends)
+    return (int)min(__float2uint_rz(__double2float_rz(ord2f(o) - lo) * scf), (unsigned)(NB - 1));
 }
 
 // Called by one whole warp.  When the margin neighbours sorted[nh-1] / sorted[nh+1] lie outside the median bin they are
