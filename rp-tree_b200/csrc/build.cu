@@ -2435,10 +2435,14 @@ __device__ __forceinline__ void bitonic_uniform(ull* w, unsigned nslots, unsigne
 // put in exact (full key, incoming slot) order by the neighbour fix-up below, so both forms give the same result; the
 // 32-bit form halves the compare/select, shuffle and shared-memory work of the network.
 #ifndef RPF_BOT_MINB128
-#define RPF_BOT_MINB128 10     /* resident CTAs per SM asked of the 128-thread instance (caps it at 48 registers) */
+#define RPF_BOT_MINB128 10     /* resident CTAs per SM asked of the 128-thread instances (caps them at 48 registers) */
+#endif
+#ifndef RPF_BOT_MINB128S
+#define RPF_BOT_MINB128S 12    /* ... of the shallow one: 40 registers (16 bytes of spills); the kernel waits on its MIO queue (shuffles + shared
+                                  memory), two more resident CTAs cover more of that: bottom 1.98 -> 1.93 ms (8: 2.08 ms; 16 would spill 248 bytes) */
 #endif
 template <int NT, int TAB, typename W>
-__global__ void __launch_bounds__(NT, (NT == 128 ? RPF_BOT_MINB128 : 1)) k_bottom3(BottomArgs A) {
+__global__ void __launch_bounds__(NT, (NT == 128 ? (TAB == BOT2_TAB_SHALLOW ? RPF_BOT_MINB128S : RPF_BOT_MINB128) : 1)) k_bottom3(BottomArgs A) {
     constexpr unsigned P0 = 8 * NT;               // slots (>= node size), 8 per thread
     constexpr int lp0 = (NT == 32 ? 8 : NT == 64 ? 9 : NT == 128 ? 10 : NT == 256 ? 11 : NT == 512 ? 12 : 13);
     constexpr bool W32 = sizeof(W) == 4;
