@@ -258,9 +258,14 @@ int rpf_get_profile(const rpf_handle* h, double* ms, int64_t* launches, int cap)
 const char* rpf_phase_name(int i);
 /* Total kernel launches issued by this handle since creation. */
 int64_t rpf_launch_count(const rpf_handle* h);
-/* Named options: "lean_top" (0/1, default 1: 0 = generic top-phase compact / relabel kernels only; test hook),
- * "force_generic_bottom" (0/1: use the generic bottom-phase kernel; test hook),
- * "release_workspace" (free the cached device workspace now). */
+/* Named options (tuning knobs and test hooks; results are identical under every setting):
+ *   "lean_top" (0/1, default 1: 0 = generic top-phase compact / relabel kernels only), "fuse_relabel_hist" (0/1, default 1: top-phase
+ *   relabel of level l fused with the histogram of level l + 1), "hist_big_chunk" (0/1, default 1), "fused_top" (bit mask, default 1),
+ *   "fused_pick_min_tg" (default 16), "top_chunk_hist" / "top_chunk_compact" / "top_chunk_relabel" (points per CTA, 0 = automatic),
+ *   "branches" (concurrent tree blocks per build, 0 = automatic), "cuda_graph" (0/1), "project_variant", "project_prefetch",
+ *   "project_pipe_maxh", "force_generic_bottom" (0/1), "bottom_words64" (0/1), "bottom_select" (0/1, default 0), "knn_filter32" (0/1,
+ *   default 1), "knn_f32_stages" / "knn_f32_rows" / "knn_f32_buf" / "knn_f32_sreg", "force_simple_knn", "force_simple_topk",
+ *   "no_query_order", "rerank_gemm" (0/1/2), "release_workspace" (free the cached device workspace now).  Unknown names: RPF_ERR_ARG. */
 int rpf_set_option(rpf_handle* h, const char* name, int64_t value);
 /* Tuning knob: bottom-phase shared-memory capacity in points (256, 1024, 4096 or 8192). */
 int rpf_set_bottom_cap(rpf_handle* h, int32_t cap);
