@@ -853,11 +853,14 @@ def test_leaf_grouped_tensor_core_rerank_equals_gather_path_and_oracle(built, n,
     f.close()
 
 
-@pytest.mark.parametrize("opts", [{"project_variant": 5}, {"fused_top": 3}, {"branches": 1}, {"branches": 4, "fused_top": 0}],
-                         ids=["register-accumulator-projection", "fused-top-chain", "no-branches", "four-branches"])
+@pytest.mark.parametrize("opts", [{"project_variant": 5}, {"fused_top": 3}, {"branches": 1}, {"branches": 4, "fused_top": 0},
+                                  {"fuse_relabel_hist": 0, "hist_big_chunk": 0}, {"fuse_relabel_hist": 1, "top_chunk_hist": 57344, "fused_pick_min_tg": 1}],
+                         ids=["register-accumulator-projection", "fused-top-chain", "no-branches", "four-branches",
+                              "separate-relabel-and-histogram", "fused-relabel-histogram-largest-chunk"])
 def test_build_variants_give_the_same_forest(built, opts):
     """A/B hooks of the build: the register-accumulator projection kernel for long rows (k_project_wide) instead of the
-    column-blocked launches, the fused top-phase kernels, the number of concurrent branches."""
+    column-blocked launches, the fused top-phase kernels, the number of concurrent branches, the relabel pass with and without
+    the next level's histogram (k_top_relabel_hist), the histogram chunk at its 16-bit-counter limit."""
     R, orc = _mods()
     for (n, d, T, minl, kind) in [(70000, 960 if "project_variant" in opts else 24, 3 if "project_variant" in opts else 6, 16, "mixture"),
                                   (66000, 12, 5, 8, "integer")]:
