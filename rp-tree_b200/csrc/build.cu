@@ -1042,7 +1042,7 @@ struct NodeSel {
 struct TopArgs {
     int64_t n;                       // points of this job (labels, cand are [Tg][n])
     int64_t ks, ps;                  // element stride between key rows / between the trees' slices of perm
-    int ch;                          // points per CTA of the streaming kernels (8192 .. TOP_CH: small tree groups use small chunks to fill the SMs)
+    int ch;                          // points per CTA of the streaming kernels (8192 .. TOP_CH, histogram kernels up to HIST_CH_MAX; small tree groups use small chunks to fill the SMs)
     int vec;                         // key rows and labels are 32-byte / 8-byte aligned: 4-point vector accesses allowed
     int haslab;                      // labels are valid (level > 0, or a job with several roots); else every point sits in node 0
     int Tg, L, l, node0, nnodes, NTOP, NB, HSZ, MAXTD, smem_hist, gt0;   // gt0: global tree id of the group's first tree
@@ -1085,7 +1085,7 @@ struct TopArgs {
 #define TOP_NT 512
 #endif
 #define HIST_CH_MAX 57344 /* points per CTA of the histogram kernels: multiples of 8192 below 65 536 (16-bit counters) */
-#define HBINS 32768       /* shared-memory histogram counters (16-bit, two per word; a CTA streams TOP_CH <= 65535 points) */
+#define HBINS 32768       /* shared-memory histogram counters (16-bit, two per word; a CTA streams at most HIST_CH_MAX <= 65535 points) */
 #define HBINS_MAXNB 16384
 #define FIN_CAP 4096      /* in-bin sort capacity */
 #define SMEM_NODES 1024   /* compact/relabel keep per-node state in shared memory up to this many nodes */
